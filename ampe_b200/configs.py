@@ -1,0 +1,214 @@
+"""Parameter records of the five BASELINE.json configurations.
+
+Each builder returns an `_abi.RhsConfig` whose fields follow
+QuatModelParameters (reference: source/QuatModelParameters.cc) with the values of
+the shipped input decks.  Grid sizes are arguments so that the parity tests can
+run the same model on small grids.
+"""
+import json
+import os
+
+from . import _abi
+
+_DATA = os.path.join(os.path.dirname(__file__), "data")
+
+
+def _ch(s):
+    return s.encode("ascii")[:1]
+
+
+def load_calphad(name="calphadAuNi.json"):
+    """thermodynamic_data/calphadAuNi.dat transcribed by tools/make_calphad_json.py"""
+    db = json.load(open(os.path.join(_DATA, name)))
+    out = _abi.CalphadBinary()
+    for si, sp in enumerate(("SpeciesA", "SpeciesB")):
+        for pi, ph in enumerate(("PhaseL", "PhaseA")):
+            rec = db[sp][ph]
+            g = out.g[si][pi]
+            tc = rec["Tc"]
+            g.nintervals = len(tc) - 1
+            assert g.nintervals <= _abi.AMPE_MAX_TC
+            for i, v in enumerate(tc):
+                g.Tc[i] = v
+            for key in ("a", "b", "c", "d2", "d3", "d4", "d7", "dm1", "dm9"):
+                vals = rec.get(key, [0.0] * g.nintervals)
+                arr = getattr(g, key)
+                for i in range(g.nintervals):
+                    arr[i] = vals[i]
+    for pi, ph in enumerate(("LmixPhaseL", "LmixPhaseA")):
+        for k in range(4):
+            v = db[ph].get("L%d" % k, [0.0, 0.0])
+            out.L[pi][k][0] = v[0]
+            out.L[pi][k][1] = v[1]
+    mob = db["MobilityParameters"]
+    for si in range(2):
+        for pi, ph in enumerate(("PhaseL", "PhaseA")):
+            rec = mob["Species%d" % si][ph]
+            out.qA[si][pi][0], out.qA[si][pi][1] = rec["qA"]
+            out.qB[si][pi][0], out.qB[si][pi][1] = rec["qB"]
+            n = 0
+            for k in range(4):
+                # defaults (0, 1): CALPHADMobility.cc initialize()
+                v = rec.get("q%dAB" % k, [0.0, 1.0])
+                if ("q%dAB" % k) in rec:
+                    n = k + 1
+                out.qAB[si][pi][k][0] = v[0]
+                out.qAB[si][pi][k][1] = v[1]
+            out.nqAB[si][pi] = n
+    return out
+
+
+def _base(ndim, n, lo, hi):
+    c = _abi.RhsConfig()
+    c.ndim = ndim
+    for d in range(3):
+        c.n[d] = n[d] if d < ndim else 1
+        c.dx[d] = (hi[d] - lo[d]) / n[d] if d < ndim else 1.0
+    # defaults of QuatModelParameters.cc
+    c.lag_quat_sidegrad = 1              # QuatIntegrator.cc:293-298
+    c.quat_grad_modulus_from_cells = 1   # quat_grad_modulus_type = "cells" (:692-693)
+    c.energy_interp = _ch("p")
+    c.conc_interp = _ch("p")
+    c.diffusion_interp = _ch("l")        # :1014-1017
+    c.orient_interp1 = _ch("q")          # :704-707
+    c.orient_interp2 = _ch("c")          # :708-711
+    c.avg_func = _ch("h")                # :1039-1041 default "harmonic"
+    c.conc_avg_func = _ch("h")
+    c.grad_floor_type = _ch("m")         # :683-684
+    c.quat_mobility_func = _ch("p")      # :730-731
+    c.knumber = 4                        # PhaseFluxStrategyFactory.h:27-28
+    c.min_quat_mobility = 1.0e-6         # :651
+    c.quat_grad_floor = 1.0e-2           # :671-672
+    c.quat_mobility_alt_scale = 1.0
+    c.conc_mobility = 1.0                # :291
+    c.ch_mobility = 1.0                  # CompositionRHSStrategyFactory.h:83-88
+    c.newton_max_its = 20                # Thermo4PFM NewtonSolver defaults
+    c.newton_tol = 1.0e-8
+    c.newton_alpha = 1.0
+    c.cp = 1.0
+    c.vm_liquid = c.vm_solid = 1.0e-6
+    c.nranks, c.rank = 1, 0
+    return c
+
+
+def pfhub1a(nx=200, ny=200):
+    """C1: benchmarks/PFHub1a/2d.input -- Cahn-Hilliard double well, 200 um box.
+    M = 5 applied as ConcentrationModel.mobility (tests/CahnHilliard/2d.input)."""
+    c = _base(2, (nx, ny), (0.0, 0.0), (200.0, 200.0))
+    c.with_concentration = 1
+    c.conc_rhs_form = _abi.CONC_CAHN_HILLIARD
+    c.T_uniform = 1000.0
+    c.ch_ca, c.ch_cb, c.ch_well_scale, c.ch_kappa = 0.3, 0.7, 5.0, 2.0
+    c.conc_mobility = 5.0
+    return c
+
+
+def dendrite2d(nx=2048, ny=2048):
+    """C2: examples/Dendrite2D/dendrite.input -- KWCcomplex (qlen=2), anisotropic
+    phase flux, bias double well, unsteady heat equation, periodic."""
+    c = _base(2, (nx, ny), (-4.5, -4.5), (4.5, 4.5))
+    c.qlen = 2
+    c.with_phase = 1
+    c.with_unsteady_temperature = 1
+    c.evolve_quat = 1
+    c.phase_flux_type = _abi.FLUX_ANISOTROPIC
+    c.free_energy = _abi.FE_BIASWELL
+    c.epsilon_anisotropy = 0.05
+    c.H_parameter = 0.001
+    c.epsilon_phase = 0.01
+    c.phi_mobility = 3333.3333
+    c.quat_mobility = 1.0
+    c.epsilon_q = 1.0e3
+    c.meltingT = 1.0
+    c.cp = 1.0
+    c.thermal_diffusivity = 1.0e-8 * 1.0e8   # cm^2/s -> um^2/s (:572-579)
+    c.vm_liquid = c.vm_solid = 1.0e-6
+    c.latent_heat = 1.0 * (1.0e-6 / 1.0e-6)  # J/mol -> pJ/um^3 (:611-617)
+    c.phi_well_scale = 0.015625
+    c.bias_well_alpha = 0.9
+    c.bias_well_gamma = 10.0
+    return c
+
+
+def auni2d(nx=4096, ny=4096, symmetry=True):
+    """C3: examples/AuNi_2D/9grains_AuNi.input -- phi + c + q[4], CALPHAD KKS,
+    EBS composition RHS, symmetry-aware quaternions, T = 1450 K uniform."""
+    c = _base(2, (nx, ny), (-1.6 * nx / 512, -1.6 * ny / 512), (1.6 * nx / 512, 1.6 * ny / 512))
+    _auni_common(c)
+    c.symmetry_aware = 1 if symmetry else 0
+    return c
+
+
+def auni3d(nx=1024, ny=1024, nz=128):
+    """C5: examples/AuNi_3D/1grain3D_AuNi.input scaled (h kept at 0.8/128 um)."""
+    h = 0.8 / 128
+    c = _base(3, (nx, ny, nz), (0.0, 0.0, 0.0), (nx * h, ny * h, nz * h))
+    _auni_common(c)
+    return c
+
+
+def _auni_common(c):
+    c.qlen = 4
+    c.with_phase = 1
+    c.with_concentration = 1
+    c.evolve_quat = 1
+    c.phase_flux_type = _abi.FLUX_SIMPLE
+    c.conc_rhs_form = _abi.CONC_EBS
+    c.free_energy = _abi.FE_CALPHAD
+    c.H_parameter = 0.25
+    c.epsilon_q = 0.3125
+    c.T_uniform = 1450.0
+    c.epsilon_phase = 0.25
+    c.phi_mobility = 6.4
+    c.quat_mobility = 0.64
+    c.phi_well_scale = 2.5
+    c.energy_interp = _ch("p")
+    c.conc_interp = _ch("p")
+    c.avg_func = _ch("a")
+    c.conc_avg_func = _ch("a")
+    c.vm_liquid = c.vm_solid = 7.68e-6
+    c.newton_max_its = 50
+    c.calphad = load_calphad()
+
+
+def gg3d_hbsm(nx=512, ny=512, nz=512):
+    """C4: examples/GG3D_HBSM with the maintained parameter set of
+    tests/TwoGrainsQuadratic/3d.input (H=0.001: quaternions evolve), quadratic
+    KKS free energy, KKS composition RHS, T = 873 K, h = 0.05 um."""
+    h = 3.2 / 64
+    c = _base(3, (nx, ny, nz), (0.0, 0.0, 0.0), (nx * h, ny * h, nz * h))
+    c.qlen = 4
+    c.with_phase = 1
+    c.with_concentration = 1
+    c.evolve_quat = 1
+    c.phase_flux_type = _abi.FLUX_SIMPLE
+    c.conc_rhs_form = _abi.CONC_KKS
+    c.free_energy = _abi.FE_QUADRATIC
+    c.H_parameter = 0.001
+    c.epsilon_q = 0.1
+    c.T_uniform = 873.0
+    c.epsilon_phase = 0.165
+    c.quat_mobility = 200.0
+    c.phi_mobility = 200.0
+    c.phi_well_scale = 0.4125
+    c.energy_interp = _ch("h")
+    c.conc_interp = _ch("h")
+    c.avg_func = _ch("a")
+    c.conc_avg_func = _ch("a")
+    c.vm_liquid = c.vm_solid = 1.5e-5
+    c.D_solid, c.D_liquid = 1.3e8, 5.6e4
+    c.Q0_solid, c.Q0_liquid = 156377.0, 55329.0
+    c.quad_Tref = 873.0
+    c.quad_A_l = c.quad_A_s = 1.0e4
+    c.quad_Ceq_l, c.quad_Ceq_s = 0.05, 0.10
+    c.quad_m_l = c.quad_m_s = 0.0
+    return c
+
+
+BUILDERS = {
+    "pfhub1a": pfhub1a,
+    "dendrite2d": dendrite2d,
+    "auni2d": auni2d,
+    "gg3d_hbsm": gg3d_hbsm,
+    "auni3d": auni3d,
+}

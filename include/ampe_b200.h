@@ -1,0 +1,205 @@
+/*
+ * ampe_b200.h -- C ABI of libampe_b200.so: the B200-native phase-field
+ * right-hand-side evaluation that AMPE drives from
+ * QuatIntegrator::evaluateRHSFunction (reference: source/QuatIntegrator.cc:3134-3295).
+ *
+ * Two families of entry points ("lower boundary"):
+ *
+ *  (i)  ampe_rhs_*       the fused evaluateRHSFunction-shaped path: one context
+ *                        per GPU, y / ydot are caller-owned DEVICE pointers laid
+ *                        out like SAMRAI CellData with ghost width 0 (i fastest,
+ *                        component slowest).
+ *  (ii) ampe_k_*         one symbol per Fortran kernel AMPE binds through
+ *                        source/fortran/{QuatFort,ConcFort}.h, same argument
+ *                        order, scalars by value, arrays are DEVICE pointers in
+ *                        SAMRAI CellData/SideData layout with ghost widths
+ *                        (declared in ampe_b200_kernels.h).
+ *
+ * Every function returns 0 on success and a negative AMPE_E* code on error;
+ * nothing here ever calls exit() (the Fortran kernels `stop`).
+ * No torch types, no C++ types: plain pointers, ints and doubles only.
+ */
+#ifndef AMPE_B200_H
+#define AMPE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMPE_OK 0
+#define AMPE_EINVAL (-1)   /* bad argument / unsupported combination          */
+#define AMPE_ECUDA (-2)    /* CUDA runtime error (see ampe_last_error)        */
+#define AMPE_ENEWTON (-3)  /* per-cell KKS Newton did not converge            */
+#define AMPE_ENOGPU (-4)   /* no CUDA device: there is no CPU fallback        */
+
+/* phase flux stencils: PhaseFluxStrategyFactory.h:11-36 */
+#define AMPE_FLUX_SIMPLE 0      /* gradient_flux            quatrhs.m4        */
+#define AMPE_FLUX_ISOTROPIC 1   /* compute_flux_isotropic   2d/quatrhs.m4:106 */
+#define AMPE_FLUX_ANISOTROPIC 2 /* anisotropic_gradient_flux                  */
+
+/* concentration RHS forms: CompositionRHSStrategyFactory.h:27-102 */
+#define AMPE_CONC_NONE 0
+#define AMPE_CONC_CAHN_HILLIARD 1 /* CahnHilliardDoubleWell                   */
+#define AMPE_CONC_KKS 2           /* KKSCompositionRHSStrategy (quadratic)    */
+#define AMPE_CONC_EBS 3           /* EBSCompositionRHSStrategy (CALPHAD)      */
+
+/* free energy / driving force: FreeEnergyStrategyFactory.h:37-263 */
+#define AMPE_FE_NONE 0
+#define AMPE_FE_BIASWELL 1  /* BiasDoubleWellUTRCFreeEnergyStrategy           */
+#define AMPE_FE_CALPHAD 2   /* CALPHADFreeEnergyStrategyBinary                */
+#define AMPE_FE_QUADRATIC 3 /* QuadraticFreeEnergyStrategy                    */
+
+#define AMPE_MAX_TC 6 /* max number of temperature intervals per species G(T) */
+
+/* One species/phase Gibbs energy, thermodynamic_data/calphadAuNi.dat:1-46
+ * G = a + b T + c T ln T + d2 T^2 + d3 T^3 + d4 T^4 + d7 T^7 + dm1/T + dm9/T^9
+ * on interval [Tc[i], Tc[i+1]).                                              */
+typedef struct ampe_calphad_species {
+   int nintervals;
+   double Tc[AMPE_MAX_TC + 1];
+   double a[AMPE_MAX_TC], b[AMPE_MAX_TC], c[AMPE_MAX_TC];
+   double d2[AMPE_MAX_TC], d3[AMPE_MAX_TC], d4[AMPE_MAX_TC], d7[AMPE_MAX_TC];
+   double dm1[AMPE_MAX_TC], dm9[AMPE_MAX_TC];
+} ampe_calphad_species;
+
+/* CALPHAD binary two-phase data base + mobility block (calphadAuNi.dat).     */
+typedef struct ampe_calphad_binary {
+   ampe_calphad_species g[2][2]; /* [species A,B][phase L,A]                  */
+   double L[2][4][2];            /* [phase][k][0:const,1:*T] Redlich-Kister   */
+   /* MobilityParameters: [species][phase] qA,qB,q0AB..q3AB, each (a0,a1):
+    * Q(T) = a0 + R T ln(a1)   (CALPHADMobility.h getQ)                       */
+   double qA[2][2][2], qB[2][2][2], qAB[2][2][4][2];
+   int nqAB[2][2];
+} ampe_calphad_binary;
+
+/* All parameters of one RHS evaluation (QuatModelParameters subset that the
+ * hot path reads; names follow QuatModelParameters.h accessors).             */
+typedef struct ampe_rhs_config {
+   int ndim;      /* 2 or 3 (reference: compile-time -DNDIM)                  */
+   int n[3];      /* LOCAL interior cells per direction (n[2]=1 in 2D)        */
+   double dx[3];  /* mesh spacing                                             */
+   int qlen;      /* 0: no orientation field; 1, 2 (KWCcomplex) or 4 (Quat)   */
+
+   int with_phase;
+   int with_concentration;
+   int with_unsteady_temperature; /* Temperature{equation_type="unsteady"}    */
+   int evolve_quat;               /* H_parameter > 0                          */
+
+   int phase_flux_type; /* AMPE_FLUX_*                                        */
+   int conc_rhs_form;   /* AMPE_CONC_*                                        */
+   int free_energy;     /* AMPE_FE_*                                          */
+   int symmetry_aware;  /* Symmetry{enabled=TRUE}                             */
+   int lag_quat_sidegrad;            /* Integrator default TRUE               */
+   int quat_grad_modulus_from_cells; /* quat_grad_modulus_type=="cells"       */
+
+   /* selector characters: only the first character of the reference's
+    * strings is significant (functions.f:28-83)                              */
+   char energy_interp;    /* phi_interp_func_type  'p','h','l'                */
+   char conc_interp;      /* conc_interp_func_type                            */
+   char diffusion_interp; /* diffusion_interp_func_type (default 'l')         */
+   char orient_interp1;   /* default 'q'                                      */
+   char orient_interp2;   /* default 'c'                                      */
+   char avg_func;         /* 'a' or 'h'                                       */
+   char grad_floor_type;  /* 'm','t','s'                                      */
+   char quat_mobility_func; /* 'p','e','i'                                    */
+   char conc_avg_func;    /* ConcentrationModel.avg_func_type 'a' or 'h'      */
+
+   /* phase */
+   double epsilon_phase, epsilon_anisotropy;
+   int knumber;
+   double phi_well_scale, phi_mobility;
+   /* orientation */
+   double H_parameter, epsilon_q, quat_mobility, min_quat_mobility;
+   double quat_grad_floor, quat_mobility_alt_scale;
+   /* temperature */
+   double T_uniform; /* value of the T field when it is not evolved           */
+   double thermal_diffusivity, latent_heat, cp, meltingT;
+   double bias_well_alpha, bias_well_gamma;
+   /* composition */
+   double conc_mobility;                          /* ConcentrationModel.mobility */
+   double ch_ca, ch_cb, ch_well_scale, ch_kappa, ch_mobility;
+   /* quadratic KKS (QuadraticFreeEnergyStrategy.cc:56-68)                    */
+   double quad_Tref, quad_A_l, quad_Ceq_l, quad_m_l, quad_A_s, quad_Ceq_s, quad_m_s;
+   double D_liquid, D_solid, Q0_liquid, Q0_solid; /* concentration_pfmdiffusion */
+   double vm_liquid, vm_solid;                    /* molar volumes [m^3/mol]  */
+   /* per-cell Newton (Thermo4PFM NewtonSolver block)                         */
+   int newton_max_its;
+   double newton_tol, newton_alpha;
+
+   ampe_calphad_binary calphad;
+
+   /* slab decomposition along the slowest axis (z in 3D, y in 2D): this
+    * rank owns n[ndim-1] planes; ghost planes come from the neighbours.      */
+   int nranks, rank;
+} ampe_rhs_config;
+
+/* Device pointers of one state / RHS vector, SAMRAI CellData ghost 0:
+ * index (i,j,k,m) -> i + n0*(j + n1*(k + n2*m)).  Unused components NULL.
+ * Order mirrors createSolutionvector (QuatIntegrator.cc:1623-1674).          */
+typedef struct ampe_rhs_fields {
+   double* phase;
+   double* quat;        /* depth qlen */
+   double* conc;
+   double* temperature;
+} ampe_rhs_fields;
+
+typedef struct ampe_rhs_ctx ampe_rhs_ctx;
+
+/* Replaces the constructor-time wiring of QuatIntegrator (RegisterVariables,
+ * QuatIntegrator.cc:787-985): allocates every intermediate on the device.    */
+int ampe_rhs_create(const ampe_rhs_config* cfg, ampe_rhs_ctx** out);
+int ampe_rhs_destroy(ampe_rhs_ctx* ctx);
+
+/* QuatModel::resetRefPhaseConcentrations (QuatModel.cc:5218-5231): set the
+ * Newton initial guess (c_l_ref, c_a_ref), ghost-0 device arrays; NULL means
+ * "copy the last computed c_l, c_a".                                         */
+int ampe_rhs_set_ref_concentrations(ampe_rhs_ctx* ctx, const double* cl_ref,
+                                    const double* ca_ref, void* stream);
+/* quat_symm_rotation SideData<int> (QuatModel.cc:1714-1722): one int per
+ * LOWER face per direction, ghost 0 (device).                                */
+int ampe_rhs_set_symmetry_rotations(ampe_rhs_ctx* ctx, const int* const* iqrot,
+                                    void* stream);
+/* Ghost planes from the slab neighbours (fillScratch, QuatIntegrator.cc:2873-2955).
+ * lo/hi: fields with `nghosts` planes each, for the lower / upper neighbour.
+ * NULL = periodic wrap inside this rank (single GPU).                        */
+int ampe_rhs_set_halo(ampe_rhs_ctx* ctx, const ampe_rhs_fields* lo,
+                      const ampe_rhs_fields* hi);
+int ampe_rhs_nghosts(const ampe_rhs_ctx* ctx);
+
+/* QuatIntegrator::evaluateRHSFunction(time, y, y_dot, fd_flag)
+ * (QuatIntegrator.h:204-222).  y is not modified.  stream: cudaStream_t.     */
+int ampe_rhs_eval(ampe_rhs_ctx* ctx, double time, const ampe_rhs_fields* y,
+                  const ampe_rhs_fields* ydot, int fd_flag, void* stream);
+/* Split evaluation for halo/compute overlap: interior planes first (no ghost
+ * needed), boundary planes after the halo arrived.                           */
+int ampe_rhs_eval_interior(ampe_rhs_ctx* ctx, double time,
+                           const ampe_rhs_fields* y,
+                           const ampe_rhs_fields* ydot, int fd_flag,
+                           void* stream);
+int ampe_rhs_eval_boundary(ampe_rhs_ctx* ctx, double time,
+                           const ampe_rhs_fields* y,
+                           const ampe_rhs_fields* ydot, int fd_flag,
+                           void* stream);
+
+/* device pointers to ctx-owned c_l, c_a (ghost 0) after an evaluation        */
+int ampe_rhs_get_phase_concentrations(ampe_rhs_ctx* ctx, double** cl,
+                                      double** ca);
+/* number of cells whose Newton failed in the last evaluation (synchronises)  */
+int ampe_rhs_newton_failures(ampe_rhs_ctx* ctx, void* stream);
+/* kernels launched by the last ampe_rhs_eval                                 */
+int ampe_rhs_last_launch_count(const ampe_rhs_ctx* ctx);
+
+/* host-buffer convenience used by the reference-facing plugin path: copies
+ * y host->device, evaluates, copies ydot device->host (pinned or pageable).  */
+int ampe_rhs_eval_host(ampe_rhs_ctx* ctx, double time, const ampe_rhs_fields* y_host,
+                       const ampe_rhs_fields* ydot_host, int fd_flag);
+
+const char* ampe_last_error(void);
+const char* ampe_version(void);
+/* sizeof(ampe_rhs_config) as compiled, for binding sanity checks */
+int ampe_abi_sizeof_config(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

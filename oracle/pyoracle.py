@@ -1,0 +1,138 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes access to the CPU oracle (liboracle.so).
+
+Imported only by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  Never imported by the product package ampe_b200.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+from ampe_b200 import _abi  # noqa: E402  (struct layouts only)
+
+
+def build(perf=False):
+    target = "liboracle_perf.so" if perf else "liboracle.so"
+    subprocess.check_call(["make", "-s", "-C", _HERE, target])
+    return os.path.join(_HERE, target)
+
+
+_libs = {}
+
+
+def lib(perf=False):
+    if perf not in _libs:
+        path = os.path.join(_HERE, "liboracle_perf.so" if perf else "liboracle.so")
+        if not os.path.exists(path):
+            build(perf)
+        L = C.CDLL(path)
+        dbl = C.c_double
+        L.oracle_create.restype = C.c_void_p
+        L.oracle_create.argtypes = [C.POINTER(_abi.RhsConfig)]
+        L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_set_ref.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_set_rotations.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.oracle_eval.restype = C.c_int
+        L.oracle_eval.argtypes = [C.c_void_p, dbl, C.POINTER(_abi.RhsFields),
+                                  C.POINTER(_abi.RhsFields), C.c_int]
+        L.oracle_get_phase_concentrations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        for f in ("interp_func", "deriv_interp_func", "second_deriv_interp_func", "well_func",
+                  "deriv_well_func"):
+            fn = getattr(L, "oracle_" + f)
+            fn.restype = dbl
+            fn.argtypes = [dbl, C.c_char]
+        L.oracle_average_func.restype = dbl
+        L.oracle_average_func.argtypes = [dbl, dbl, C.c_char]
+        for f in ("interp_ratio_func", "compl_interp_ratio_func"):
+            fn = getattr(L, "oracle_" + f)
+            fn.restype = dbl
+            fn.argtypes = [dbl, C.c_char, C.c_char]
+        L.oracle_eval_grad_normi.restype = dbl
+        L.oracle_eval_grad_normi.argtypes = [dbl, C.c_char, dbl, dbl]
+        L.oracle_quatsymmrotate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.oracle_qr_table4.argtypes = [C.c_void_p]
+        pdb = C.POINTER(_abi.CalphadBinary)
+        for f in ("calphad_free_energy", "calphad_deriv_free_energy",
+                  "calphad_second_deriv_free_energy"):
+            fn = getattr(L, "oracle_" + f)
+            fn.restype = dbl
+            fn.argtypes = [pdb, dbl, dbl, C.c_int]
+        L.oracle_calphad_phase_concentrations.restype = C.c_int
+        L.oracle_calphad_phase_concentrations.argtypes = [pdb, dbl, dbl, dbl, C.c_void_p, dbl,
+                                                          C.c_int, dbl]
+        L.oracle_calphad_ceq.restype = C.c_int
+        L.oracle_calphad_ceq.argtypes = [pdb, dbl, C.c_void_p, dbl, C.c_int, dbl]
+        for f in ("calphad_fmix", "calphad_fmix_deriv", "calphad_fmix_deriv2"):
+            fn = getattr(L, "oracle_" + f)
+            fn.restype = dbl
+            fn.argtypes = [dbl] * 5
+        for f in ("xlogx", "xlogx_deriv", "xlogx_deriv2"):
+            fn = getattr(L, "oracle_" + f)
+            fn.restype = dbl
+            fn.argtypes = [dbl]
+        L.oracle_calphad_diffusion_mobility.restype = dbl
+        L.oracle_calphad_diffusion_mobility.argtypes = [pdb, C.c_int, dbl, dbl]
+        _libs[perf] = L
+    return _libs[perf]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _fields(d):
+    f = _abi.RhsFields()
+    f.phase = _ptr(d.get("phase"))
+    f.quat = _ptr(d.get("quat"))
+    f.conc = _ptr(d.get("conc"))
+    f.temperature = _ptr(d.get("temperature"))
+    return f
+
+
+class Oracle:
+    """CPU restatement of QuatIntegrator::evaluateRHSFunction on one periodic level."""
+
+    def __init__(self, cfg, perf=False):
+        self.L = lib(perf)
+        self.cfg = cfg
+        self.h = self.L.oracle_create(C.byref(cfg))
+        self.ncell = cfg.n[0] * cfg.n[1] * (cfg.n[2] if cfg.ndim == 3 else 1)
+
+    def close(self):
+        if self.h:
+            self.L.oracle_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def set_ref(self, cl, ca):
+        self.L.oracle_set_ref(self.h, _ptr(cl), _ptr(ca))
+
+    def set_rotations(self, iqrot):
+        arr = (C.c_void_p * 3)()
+        self._iq = [np.ascontiguousarray(a, dtype=np.int32) for a in iqrot]
+        for d, a in enumerate(self._iq):
+            arr[d] = a.ctypes.data
+        self.L.oracle_set_rotations(self.h, arr)
+
+    def alloc_like(self, y):
+        return {k: (None if v is None else np.zeros_like(v)) for k, v in y.items()}
+
+    def eval(self, time, y, fd_flag=0, ydot=None):
+        """y: dict of contiguous float64 numpy arrays (ghost-0 SAMRAI order)."""
+        if ydot is None:
+            ydot = self.alloc_like(y)
+        fy, fd = _fields(y), _fields(ydot)
+        st = self.L.oracle_eval(self.h, float(time), C.byref(fy), C.byref(fd), int(fd_flag))
+        return st, ydot
+
+    def phase_concentrations(self):
+        cl = np.zeros(self.ncell)
+        ca = np.zeros(self.ncell)
+        self.L.oracle_get_phase_concentrations(self.h, _ptr(cl), _ptr(ca))
+        return cl, ca
