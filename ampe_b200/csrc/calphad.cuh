@@ -1,0 +1,122 @@
+// Per-cell CALPHAD binary two-phase thermodynamics and the KKS Newton solve, in
+// registers.  Replaces the Thermo4PFM calls AMPE makes from
+//   CALPHADequilibriumPhaseConcentrationsStrategy.cc:385-387  (computePhaseConcentrations)
+//   CALPHADFreeEnergyStrategyBinary.cc:321-323, 676-680       (computeFreeEnergy, computeDerivFreeEnergy)
+//   MobilityCompositionDiffusionStrategy.cc:57-69             (second derivative)
+// and the in-tree CALPHADMobility.{h,cc} formulas.  Model equations:
+// doc/latex/manual/appendix.tex:517-599.
+#pragma once
+#include "params.h"
+#include "pointwise.cuh"
+
+namespace ampe {
+
+// xlogx family with the C2 quadratic extension below 1e-8
+#define AMPE_SMALLX 1.0e-8
+AMPE_DEV double xlogx(double x, double log_smallx)
+{
+   if (x > AMPE_SMALLX) return x * log(x);
+   const double inv = 1. / AMPE_SMALLX;
+   return AMPE_SMALLX * log_smallx + (x - AMPE_SMALLX) * (1. + log_smallx) +
+          0.5 * (x * x * inv - 2.0 * x + AMPE_SMALLX);
+}
+AMPE_DEV double xlogx_deriv(double x, double log_smallx)
+{
+   if (x > AMPE_SMALLX) return log(x) + 1.0;
+   return (1. + log_smallx) + (x - AMPE_SMALLX) * (1. / AMPE_SMALLX);
+}
+AMPE_DEV double xlogx_deriv2(double x)
+{
+   if (x > AMPE_SMALLX) return 1. / x;
+   return 1. / AMPE_SMALLX;
+}
+// log(1e-8) as glibc rounds it (host-evaluated constant, same value the CPU side uses)
+#define AMPE_LOG_SMALLX (-18.420680743952367)
+
+AMPE_DEV double fmix(const double* L, double c)
+{
+   const double t = 2.0 * c - 1.0;
+   return c * (1.0 - c) * (L[0] + L[1] * t + L[2] * t * t + L[3] * t * t * t);
+}
+AMPE_DEV double fmix_deriv(const double* L, double c)
+{
+   const double t = 2.0 * c - 1.0;
+   const double cc = c * (1. - c);
+   return (1.0 - 2.0 * c) * (L[0] + L[1] * t + L[2] * t * t + L[3] * t * t * t) +
+          cc * (2.0 * L[1] + 4.0 * L[2] * t + 6.0 * L[3] * t * t);
+}
+AMPE_DEV double fmix_deriv2(const double* L, double c)
+{
+   const double t = 2.0 * c - 1.0;
+   const double cc = c * (1. - c);
+   return -2.0 * (L[0] + L[1] * t + L[2] * t * t + L[3] * t * t * t) +
+          2.0 * (1.0 - 2.0 * c) * (2.0 * L[1] + 4.0 * L[2] * t + 6.0 * L[3] * t * t) +
+          cc * (8.0 * L[2] + 24.0 * L[3] * t);
+}
+
+AMPE_DEV double calphad_f(const CalphadT& t, double c, int pi)
+{
+   return c * t.fA[pi] + (1.0 - c) * t.fB[pi] + fmix(t.L[pi], c) +
+          t.RT * (xlogx(c, AMPE_LOG_SMALLX) + xlogx(1.0 - c, AMPE_LOG_SMALLX));
+}
+AMPE_DEV double calphad_mu(const CalphadT& t, double c, int pi)
+{
+   return (t.fA[pi] - t.fB[pi]) + fmix_deriv(t.L[pi], c) +
+          t.RT * (xlogx_deriv(c, AMPE_LOG_SMALLX) - xlogx_deriv(1.0 - c, AMPE_LOG_SMALLX));
+}
+AMPE_DEV double calphad_d2f(const CalphadT& t, double c, int pi)
+{
+   return fmix_deriv2(t.L[pi], c) + t.RT * (xlogx_deriv2(c) + xlogx_deriv2(1.0 - c));
+}
+
+// KKS: (1-h) c_l + h c_a = c0,  mu_l(c_l) = mu_a(c_a)  (scaled by 1/RT), Cramer update,
+// stop when both |F_i| < tol.  Returns iteration count, -1 if not converged.
+AMPE_DEV int kks_newton(const CalphadT& t, double c0, double hphi, double& cl, double& ca,
+                        double tol, int max_its, double alpha)
+{
+   c0 = c0 >= 0. ? c0 : 0.;
+   c0 = c0 <= 1. ? c0 : 1.;
+   int it = 0;
+   while (true) {
+      const double xi0 = t.RTinv * (t.fA[0] - t.fB[0] + fmix_deriv(t.L[0], cl));
+      const double xi1 = t.RTinv * (t.fA[1] - t.fB[1] + fmix_deriv(t.L[1], ca));
+      const double f0 = -c0 + (1.0 - hphi) * cl + hphi * ca;
+      const double f1 = xlogx_deriv(cl, AMPE_LOG_SMALLX) - xlogx_deriv(1. - cl, AMPE_LOG_SMALLX) -
+                        xlogx_deriv(ca, AMPE_LOG_SMALLX) + xlogx_deriv(1. - ca, AMPE_LOG_SMALLX) +
+                        (xi0 - xi1);
+      if (fabs(f0) < tol && fabs(f1) < tol) return it;
+      if (it == max_its) return -1;
+      const double dxi0 = t.RTinv * fmix_deriv2(t.L[0], cl);
+      const double dxi1 = t.RTinv * fmix_deriv2(t.L[1], ca);
+      const double J00 = (1.0 - hphi), J01 = hphi;
+      const double J10 = dxi0 + xlogx_deriv2(cl) + xlogx_deriv2(1. - cl);
+      const double J11 = -dxi1 - xlogx_deriv2(ca) - xlogx_deriv2(1. - ca);
+      const double D = J00 * J11 - J01 * J10;
+      const double Dinv = 1.0 / D;
+      const double D0 = f0 * J11 - J01 * f1;
+      const double D1 = J00 * f1 - f0 * J10;
+      cl = cl - alpha * (Dinv * D0);
+      ca = ca - alpha * (Dinv * D1);
+      it++;
+   }
+}
+
+// computeDiffusionMobilityBinaryPhase (CALPHADMobility.cc:200-219) with
+// getAtomicMobility / getDeltaG (CALPHADMobility.h:108-120, .cc:158-168)
+AMPE_DEV double diffusion_mobility(const CalphadT& t, int phase, double c0)
+{
+   const double c1 = 1. - c0;
+   const double dc = c0 - c1;
+   double m[2];
+#pragma unroll
+   for (int sp = 0; sp < 2; sp++) {
+      const double* qq = t.qAB[sp][phase];
+      const double dG = c0 * t.qA[sp][phase] + c1 * t.qB[sp][phase] +
+                        c0 * c1 * (qq[0] + dc * (qq[1] + dc * (qq[2] + dc * qq[3])));
+      m[sp] = exp(dG * t.RTinv) * t.RTinv;
+   }
+   const double mm = c0 * m[1] + c1 * m[0];
+   return c0 * c1 * mm * 1.e12;
+}
+
+}  // namespace ampe

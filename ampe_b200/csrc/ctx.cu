@@ -1,0 +1,689 @@
+// Host side of the fused path: context (device intermediates, lagged face
+// data), parameter derivation, kernel dispatch and the extern "C" entry points
+// declared in include/ampe_b200.h.  Mirrors the wiring QuatIntegrator does in
+// RegisterVariables / evaluateRHSFunction (source/QuatIntegrator.cc:787-985,
+// 3134-3295) without SAMRAI.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "rhs_fused.cuh"
+
+using namespace ampe;
+
+static thread_local std::string g_err;
+static int set_err(int code, const std::string& msg)
+{
+   g_err = msg;
+   return code;
+}
+#define CUDA_OK(call)                                                              \
+   do {                                                                            \
+      cudaError_t e_ = (call);                                                     \
+      if (e_ != cudaSuccess)                                                       \
+         return set_err(AMPE_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+   } while (0)
+
+static const double R_GAS = 8.314472;  // GASCONSTANT_R_JPKPMOL
+
+struct ampe_rhs_ctx {
+   ampe_rhs_config cfg;
+   Params p;
+   int ns;            // planes along the slab axis
+   long long plane;   // cells per plane
+   long long ncell;
+   int ng;
+   double *cl = nullptr, *ca = nullptr, *cl_ref = nullptr, *ca_ref = nullptr;  // slab-ghosted
+   int* iq[3] = {nullptr, nullptr, nullptr};
+   double* lagN[3] = {nullptr, nullptr, nullptr};
+   double* lagD0[3] = {nullptr, nullptr, nullptr};
+   double* lagD1[3] = {nullptr, nullptr, nullptr};
+   int* nfail = nullptr;
+   double* qr_dev = nullptr;  // 48x4 cubic symmetry rotations (setqr)
+   int* conj_dev = nullptr;
+   ampe_rhs_fields halo_lo, halo_hi;
+   bool have_halo = false;
+   bool have_ref = false;
+   bool lag_valid = false;
+   int launches = 0;
+   // staging buffers for ampe_rhs_eval_host
+   ampe_rhs_fields dev_y, dev_ydot;
+   bool have_dev = false;
+   cudaStream_t own_stream = nullptr;
+};
+
+// ---- CALPHAD T-dependent coefficients on the host (uniform T) --------------------------
+// G = a + bT + cT ln T + d2 T^2 + d3 T^3 + d4 T^4 + d7 T^7 + dm1/T + dm9/T^9
+// (thermodynamic_data/calphadAuNi.dat:1-6)
+static double species_fenergy(const ampe_calphad_species& s, double T)
+{
+   int iv = s.nintervals - 1;
+   for (int i = 0; i < s.nintervals; i++)
+      if (T >= s.Tc[i] && T < s.Tc[i + 1]) {
+         iv = i;
+         break;
+      }
+   if (T < s.Tc[0]) iv = 0;
+   const double T2 = T * T, T4 = T2 * T2;
+   return s.a[iv] + s.b[iv] * T + s.c[iv] * T * log(T) + s.d2[iv] * T2 + s.d3[iv] * T2 * T +
+          s.d4[iv] * T4 + s.d7[iv] * T4 * T2 * T + s.dm1[iv] / T + s.dm9[iv] / (T4 * T4 * T);
+}
+static double getQ(const double* a, double T) { return a[0] + R_GAS * T * log(a[1]); }
+
+static void fill_calphadT(const ampe_calphad_binary& db, double T, CalphadT& o)
+{
+   for (int ph = 0; ph < 2; ph++) {
+      o.fA[ph] = species_fenergy(db.g[0][ph], T);
+      o.fB[ph] = species_fenergy(db.g[1][ph], T);
+      for (int k = 0; k < 4; k++) o.L[ph][k] = db.L[ph][k][0] + db.L[ph][k][1] * T;
+   }
+   o.RT = R_GAS * T;
+   o.RTinv = 1.0 / (R_GAS * T);
+   for (int sp = 0; sp < 2; sp++)
+      for (int ph = 0; ph < 2; ph++) {
+         o.qA[sp][ph] = getQ(db.qA[sp][ph], T);
+         o.qB[sp][ph] = getQ(db.qB[sp][ph], T);
+         for (int k = 0; k < 4; k++) o.qAB[sp][ph][k] = getQ(db.qAB[sp][ph][k], T);
+      }
+}
+
+static int derive_params(const ampe_rhs_config& c, Params& p)
+{
+   memset(&p, 0, sizeof(p));
+   if (c.ndim != 2 && c.ndim != 3) return set_err(AMPE_EINVAL, "ndim must be 2 or 3");
+   if (c.qlen != 0 && c.qlen != 2 && c.qlen != 4)
+      return set_err(AMPE_EINVAL, "qlen must be 0, 2 or 4");
+   for (int d = 0; d < c.ndim; d++)
+      if (c.n[d] < 4) return set_err(AMPE_EINVAL, "each direction needs at least 4 cells");
+   p.ndim = c.ndim;
+   p.qlen = c.qlen;
+   for (int d = 0; d < 3; d++) p.n[d] = d < c.ndim ? c.n[d] : 1;
+   p.ng = (c.conc_rhs_form == AMPE_CONC_CAHN_HILLIARD) ? 2 : 1;
+   p.with_phase = c.with_phase;
+   p.with_conc = c.with_concentration;
+   p.with_T = c.with_unsteady_temperature;
+   p.evolve_quat = c.evolve_quat && c.qlen > 0;
+   p.flux_type = c.phase_flux_type;
+   p.conc_form = c.with_concentration ? c.conc_rhs_form : 0;
+   p.free_energy = c.free_energy;
+   p.symm = c.symmetry_aware && p.evolve_quat;
+   p.modulus_from_cells = c.quat_grad_modulus_from_cells;
+   p.energy_interp = c.energy_interp;
+   p.conc_interp = c.conc_interp;
+   p.diffusion_interp = c.diffusion_interp;
+   p.orient_interp1 = c.orient_interp1;
+   p.orient_interp2 = c.orient_interp2;
+   p.avg_func = c.avg_func;
+   p.conc_avg_func = c.conc_avg_func;
+   p.grad_floor_type = c.grad_floor_type;
+   p.quat_mobility_func = c.quat_mobility_func;
+   if (p.flux_type == AMPE_FLUX_ANISOTROPIC && (c.ndim != 2 || c.qlen == 0))
+      return set_err(AMPE_EINVAL, "anisotropic phase flux: 2D with orientation only (this build)");
+   if (p.flux_type == AMPE_FLUX_ISOTROPIC && c.ndim != 2)
+      return set_err(AMPE_EINVAL, "isotropic stencil is incomplete in 3D (reference stops)");
+   if (p.conc_form == AMPE_CONC_EBS && c.free_energy != AMPE_FE_CALPHAD)
+      return set_err(AMPE_EINVAL, "EBS composition RHS needs the CALPHAD free energy");
+   if (p.conc_form == AMPE_CONC_KKS && c.free_energy != AMPE_FE_QUADRATIC)
+      return set_err(AMPE_EINVAL, "KKS composition RHS needs the quadratic free energy");
+   if ((p.conc_form == AMPE_CONC_EBS || p.conc_form == AMPE_CONC_KKS) && p.with_T)
+      return set_err(AMPE_EINVAL, "KKS/EBS with an evolved temperature field is not supported");
+   if (p.conc_form == AMPE_CONC_CAHN_HILLIARD && (c.with_phase || c.evolve_quat))
+      return set_err(AMPE_EINVAL, "Cahn-Hilliard is a composition-only model");
+
+   const double eps2 = c.epsilon_phase * c.epsilon_phase;
+   for (int d = 0; d < c.ndim; d++) {
+      const double h = c.dx[d];
+      p.h[d] = h;
+      p.dinv[d] = 1.0 / h;
+      p.p5inv[d] = 0.5 / h;
+      p.p25inv[d] = 0.25 * (1.0 / h);
+      p.dinv2[d] = 1.0 / (h * h);
+      p.eps2_dinv[d] = eps2 / h;
+      if (d < 2) p.iso_dinv[d] = (1.0 / 12.0) * eps2 / h;
+      p.ch_dinv2[d] = p.dinv[d] * p.dinv[d];
+      p.ch_mdinv[d] = c.ch_mobility * p.dinv[d];
+   }
+   p.epsilon_phase = c.epsilon_phase;
+   p.nu = c.epsilon_anisotropy;
+   p.knumber = c.knumber;
+   p.phi_well_scale = c.phi_well_scale;
+   p.phi_mobility = c.phi_mobility;
+   p.misorientation_factor = 2.0 * c.H_parameter;
+   p.epsilonq2_half = 0.5 * c.epsilon_q * c.epsilon_q;
+   p.epsq2 = c.epsilon_q * c.epsilon_q;
+   p.floor2 = c.quat_grad_floor * c.quat_grad_floor;
+   p.max_normi = 1.0 / c.quat_grad_floor;
+   p.quat_mobility = c.quat_mobility;
+   p.min_quat_mobility = c.min_quat_mobility;
+   p.quat_mobility_alt = c.quat_mobility_alt_scale;
+   p.T_uniform = c.T_uniform;
+   p.thermal_diffusivity = c.thermal_diffusivity;
+   p.latent_heat = c.latent_heat;
+   p.cp = c.cp;
+   p.meltingT = c.meltingT;
+   // computerhsbiaswell: pi = 4.*atan(1.) is REAL*4 (2d/quatrhs.m4:834)
+   p.bias_coeff = c.bias_well_alpha / (double)(4.f * atanf(1.f));
+   p.bias_gamma = c.bias_well_gamma;
+   p.conc_mobility = c.conc_mobility;
+   p.ch_ca = c.ch_ca;
+   p.ch_cb = c.ch_cb;
+   p.ch_well_scale = c.ch_well_scale;
+   p.ch_kappa = c.ch_kappa;
+   const double T = c.T_uniform;
+   p.quad_A[0] = c.quad_A_l;
+   p.quad_A[1] = c.quad_A_s;
+   p.quad_ceq[0] = c.quad_Ceq_l + (T - c.quad_Tref) * c.quad_m_l;
+   p.quad_ceq[1] = c.quad_Ceq_s + (T - c.quad_Tref) * c.quad_m_s;
+   if (c.free_energy == AMPE_FE_QUADRATIC) {
+      p.quad_rla = c.quad_A_l / c.quad_A_s;
+      p.quad_ral = c.quad_A_s / c.quad_A_l;
+   }
+   if (p.conc_form == AMPE_CONC_KKS) {
+      // concentration_pfmdiffusion (3d/concentrationdiffusion.m4:43-75) for uniform T
+      const double q0l = c.Q0_liquid / R_GAS, q0s = c.Q0_solid / R_GAS;
+      const double invT = 2.0 / (T + T);
+      p.D_liquid = c.D_liquid * exp(-q0l * invT);
+      p.D_solid = c.D_solid * exp(-q0s * invT);
+   }
+   p.inv_vm_l = 1.e-6 / c.vm_liquid;
+   p.inv_vm_a = 1.e-6 / c.vm_solid;
+   p.newton_max_its = c.newton_max_its;
+   p.newton_tol = c.newton_tol;
+   p.newton_alpha = c.newton_alpha;
+   if (c.free_energy == AMPE_FE_CALPHAD) fill_calphadT(c.calphad, T, p.ct);
+   return AMPE_OK;
+}
+
+// ---- quaternion symmetry table (setqr, quat.f:165-286) ----------------------------------
+static int upload_qr_table(ampe_rhs_ctx* c)
+{
+   static const int raw[48][4] = {
+       {1, 0, 0, 0},    {0, 1, 0, 0},    {0, 0, 1, 0},    {0, 0, 0, 1},    {-1, 0, 0, 0},
+       {0, -1, 0, 0},   {0, 0, -1, 0},   {0, 0, 0, -1},   {1, 1, 0, 0},    {1, 0, 1, 0},
+       {1, 0, 0, 1},    {0, 1, 1, 0},    {0, 1, 0, 1},    {0, 0, 1, 1},    {-1, 1, 0, 0},
+       {-1, 0, 1, 0},   {-1, 0, 0, 1},   {0, -1, 1, 0},   {0, -1, 0, 1},   {0, 0, -1, 1},
+       {1, -1, 0, 0},   {1, 0, -1, 0},   {1, 0, 0, -1},   {0, 1, -1, 0},   {0, 1, 0, -1},
+       {0, 0, 1, -1},   {-1, -1, 0, 0},  {-1, 0, -1, 0},  {-1, 0, 0, -1},  {0, -1, -1, 0},
+       {0, -1, 0, -1},  {0, 0, -1, -1},  {1, 1, 1, 1},    {-1, 1, 1, 1},   {1, -1, 1, 1},
+       {1, 1, -1, 1},   {1, 1, 1, -1},   {-1, -1, 1, 1},  {-1, 1, -1, 1},  {-1, 1, 1, -1},
+       {1, -1, -1, 1},  {1, -1, 1, -1},  {1, 1, -1, -1},  {1, -1, -1, -1}, {-1, 1, -1, -1},
+       {-1, -1, 1, -1}, {-1, -1, -1, 1}, {-1, -1, -1, -1}};
+   static const int conj[48] = {1,  6,  7,  8,  5,  2,  3,  4,  21, 22, 23, 30, 31, 32, 27, 28,
+                                29, 24, 25, 26, 9,  10, 11, 18, 19, 20, 15, 16, 17, 12, 13, 14,
+                                44, 48, 43, 42, 41, 45, 46, 47, 37, 36, 35, 33, 38, 39, 40, 34};
+   double qr[48][4];
+   for (int n = 0; n < 48; n++) {
+      double q[4] = {(double)raw[n][0], (double)raw[n][1], (double)raw[n][2], (double)raw[n][3]};
+      const double m = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+      const double minv = (m < 1.e-15) ? 0.0 : 1.0 / m;
+      for (int k = 0; k < 4; k++) qr[n][k] = q[k] * minv;
+   }
+   CUDA_OK(cudaMalloc(&c->qr_dev, sizeof(qr)));
+   CUDA_OK(cudaMalloc(&c->conj_dev, sizeof(conj)));
+   CUDA_OK(cudaMemcpy(c->qr_dev, qr, sizeof(qr), cudaMemcpyHostToDevice));
+   CUDA_OK(cudaMemcpy(c->conj_dev, conj, sizeof(conj), cudaMemcpyHostToDevice));
+   return AMPE_OK;
+}
+
+// ---- kernel dispatch (instantiations live in fused_inst_*.cu) ------------------------------
+namespace ampe {
+template <int ND, int Q>
+int dispatch_conc(const FusedArgs& A, cudaStream_t st, const char** err);
+extern template int dispatch_conc<2, 0>(const FusedArgs&, cudaStream_t, const char**);
+extern template int dispatch_conc<2, 2>(const FusedArgs&, cudaStream_t, const char**);
+extern template int dispatch_conc<2, 4>(const FusedArgs&, cudaStream_t, const char**);
+extern template int dispatch_conc<3, 0>(const FusedArgs&, cudaStream_t, const char**);
+extern template int dispatch_conc<3, 2>(const FusedArgs&, cudaStream_t, const char**);
+extern template int dispatch_conc<3, 4>(const FusedArgs&, cudaStream_t, const char**);
+}  // namespace ampe
+
+template <int ND>
+static int dispatch_q(const FusedArgs& A, cudaStream_t st)
+{
+   const char* err = nullptr;
+   int rc = AMPE_EINVAL;
+   switch (A.p.qlen) {
+      case 0: rc = dispatch_conc<ND, 0>(A, st, &err); break;
+      case 2: rc = dispatch_conc<ND, 2>(A, st, &err); break;
+      case 4: rc = dispatch_conc<ND, 4>(A, st, &err); break;
+      default: err = "unsupported qlen";
+   }
+   if (rc) return set_err(rc, err ? err : "kernel launch failed");
+   return AMPE_OK;
+}
+
+// ---- context ------------------------------------------------------------------------------
+static long long slab_ghosted_cells(const ampe_rhs_ctx* c) { return c->plane * (c->ns + 2LL * c->ng); }
+
+extern "C" int ampe_rhs_create(const ampe_rhs_config* cfg, ampe_rhs_ctx** out)
+{
+   if (!cfg || !out) return set_err(AMPE_EINVAL, "null argument");
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+      return set_err(AMPE_ENOGPU, "no CUDA device: libampe_b200 has no CPU fallback");
+   ampe_rhs_ctx* c = new ampe_rhs_ctx;
+   c->cfg = *cfg;
+   int rc = derive_params(*cfg, c->p);
+   if (rc) {
+      delete c;
+      return rc;
+   }
+   const Params& p = c->p;
+   c->ng = p.ng;
+   c->ns = (p.ndim == 3) ? p.n[2] : p.n[1];
+   c->plane = (p.ndim == 3) ? (long long)p.n[0] * p.n[1] : p.n[0];
+   c->ncell = (long long)p.n[0] * p.n[1] * p.n[2];
+   memset(&c->halo_lo, 0, sizeof(c->halo_lo));
+   memset(&c->halo_hi, 0, sizeof(c->halo_hi));
+   memset(&c->dev_y, 0, sizeof(c->dev_y));
+   memset(&c->dev_ydot, 0, sizeof(c->dev_ydot));
+   *out = c;
+   const size_t gb = (size_t)slab_ghosted_cells(c) * sizeof(double);
+   if (p.conc_form == AMPE_CONC_KKS || p.conc_form == AMPE_CONC_EBS) {
+      CUDA_OK(cudaMalloc(&c->cl, gb));
+      CUDA_OK(cudaMalloc(&c->ca, gb));
+      CUDA_OK(cudaMalloc(&c->cl_ref, gb));
+      CUDA_OK(cudaMalloc(&c->ca_ref, gb));
+      CUDA_OK(cudaMalloc(&c->nfail, sizeof(int)));
+      CUDA_OK(cudaMemset(c->nfail, 0, sizeof(int)));
+   }
+   const size_t lagb = (size_t)c->plane * (c->ns + 1) * sizeof(double);
+   if (cfg->lag_quat_sidegrad) {
+      for (int d = 0; d < p.ndim; d++) {
+         if (p.evolve_quat) CUDA_OK(cudaMalloc(&c->lagN[d], lagb));
+         if (p.conc_form == AMPE_CONC_KKS || p.conc_form == AMPE_CONC_EBS) {
+            CUDA_OK(cudaMalloc(&c->lagD0[d], lagb));
+            CUDA_OK(cudaMalloc(&c->lagD1[d], lagb));
+         }
+      }
+   }
+   if (p.symm) {
+      rc = upload_qr_table(c);
+      if (rc) return rc;
+      for (int d = 0; d < p.ndim; d++) {
+         const size_t ib = (size_t)slab_ghosted_cells(c) * sizeof(int);
+         CUDA_OK(cudaMalloc(&c->iq[d], ib));
+      }
+   }
+   return AMPE_OK;
+}
+
+extern "C" int ampe_rhs_destroy(ampe_rhs_ctx* c)
+{
+   if (!c) return AMPE_OK;
+   cudaFree(c->cl);
+   cudaFree(c->ca);
+   cudaFree(c->cl_ref);
+   cudaFree(c->ca_ref);
+   cudaFree(c->nfail);
+   cudaFree(c->qr_dev);
+   cudaFree(c->conj_dev);
+   for (int d = 0; d < 3; d++) {
+      cudaFree(c->iq[d]);
+      cudaFree(c->lagN[d]);
+      cudaFree(c->lagD0[d]);
+      cudaFree(c->lagD1[d]);
+   }
+   if (c->have_dev) {
+      cudaFree(c->dev_y.phase);
+      cudaFree(c->dev_y.quat);
+      cudaFree(c->dev_y.conc);
+      cudaFree(c->dev_y.temperature);
+      cudaFree(c->dev_ydot.phase);
+      cudaFree(c->dev_ydot.quat);
+      cudaFree(c->dev_ydot.conc);
+      cudaFree(c->dev_ydot.temperature);
+   }
+   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+   delete c;
+   return AMPE_OK;
+}
+
+extern "C" int ampe_rhs_nghosts(const ampe_rhs_ctx* c) { return c ? c->ng : AMPE_EINVAL; }
+
+// copy a ghost-0 array into a slab-ghosted one; ghost planes = periodic wrap (single rank)
+template <typename T>
+static int fill_slab_ghosted(ampe_rhs_ctx* c, T* dst, const T* src, cudaStream_t st)
+{
+   const long long pl = c->plane;
+   const int ng = c->ng, ns = c->ns;
+   CUDA_OK(cudaMemcpyAsync(dst + ng * pl, src, sizeof(T) * pl * ns, cudaMemcpyDeviceToDevice, st));
+   CUDA_OK(cudaMemcpyAsync(dst, src + (long long)(ns - ng) * pl, sizeof(T) * pl * ng,
+                           cudaMemcpyDeviceToDevice, st));
+   CUDA_OK(cudaMemcpyAsync(dst + (long long)(ng + ns) * pl, src, sizeof(T) * pl * ng,
+                           cudaMemcpyDeviceToDevice, st));
+   return AMPE_OK;
+}
+
+extern "C" int ampe_rhs_set_ref_concentrations(ampe_rhs_ctx* c, const double* cl_ref,
+                                               const double* ca_ref, void* stream)
+{
+   if (!c || !c->cl) return set_err(AMPE_EINVAL, "context has no phase concentrations");
+   cudaStream_t st = (cudaStream_t)stream;
+   if (cl_ref && ca_ref) {
+      if (c->cfg.nranks > 1)
+         return set_err(AMPE_EINVAL,
+                        "multi-rank: pass NULL (copy last c_l,c_a incl. ghost planes)");
+      int rc = fill_slab_ghosted(c, c->cl_ref, cl_ref, st);
+      if (rc) return rc;
+      rc = fill_slab_ghosted(c, c->ca_ref, ca_ref, st);
+      if (rc) return rc;
+   } else {
+      // resetRefPhaseConcentrations: whole-array copy incl. ghosts (QuatModel.cc:5218-5231)
+      const size_t gb = (size_t)slab_ghosted_cells(c) * sizeof(double);
+      CUDA_OK(cudaMemcpyAsync(c->cl_ref, c->cl, gb, cudaMemcpyDeviceToDevice, st));
+      CUDA_OK(cudaMemcpyAsync(c->ca_ref, c->ca, gb, cudaMemcpyDeviceToDevice, st));
+   }
+   c->have_ref = true;
+   return AMPE_OK;
+}
+
+// multi-rank warm start: the reference value on ghost planes too (slab-ghosted arrays)
+extern "C" int ampe_rhs_set_ref_concentrations_ghosted(ampe_rhs_ctx* c, const double* cl_ref_g,
+                                                       const double* ca_ref_g, void* stream)
+{
+   if (!c || !c->cl) return set_err(AMPE_EINVAL, "context has no phase concentrations");
+   const size_t gb = (size_t)slab_ghosted_cells(c) * sizeof(double);
+   cudaStream_t st = (cudaStream_t)stream;
+   CUDA_OK(cudaMemcpyAsync(c->cl_ref, cl_ref_g, gb, cudaMemcpyDeviceToDevice, st));
+   CUDA_OK(cudaMemcpyAsync(c->ca_ref, ca_ref_g, gb, cudaMemcpyDeviceToDevice, st));
+   c->have_ref = true;
+   return AMPE_OK;
+}
+
+extern "C" int ampe_rhs_set_symmetry_rotations(ampe_rhs_ctx* c, const int* const* iqrot,
+                                               void* stream)
+{
+   if (!c || !c->p.symm) return set_err(AMPE_EINVAL, "context is not symmetry aware");
+   if (c->cfg.nranks > 1)
+      return set_err(AMPE_EINVAL, "symmetry-aware path is single-rank in this build");
+   for (int d = 0; d < c->p.ndim; d++) {
+      int rc = fill_slab_ghosted(c, c->iq[d], iqrot[d], (cudaStream_t)stream);
+      if (rc) return rc;
+   }
+   return AMPE_OK;
+}
+
+extern "C" int ampe_rhs_set_halo(ampe_rhs_ctx* c, const ampe_rhs_fields* lo,
+                                 const ampe_rhs_fields* hi)
+{
+   if (!c) return set_err(AMPE_EINVAL, "null context");
+   if (lo && hi) {
+      c->halo_lo = *lo;
+      c->halo_hi = *hi;
+      c->have_halo = true;
+   } else {
+      c->have_halo = false;
+   }
+   return AMPE_OK;
+}
+
+static Field make_field(const ampe_rhs_ctx* c, const double* base, const double* lo,
+                        const double* hi, int depth)
+{
+   Field f;
+   f.base = base;
+   f.comp = c->ncell;
+   if (c->have_halo && lo && hi) {
+      f.lo = lo;
+      f.hi = hi;
+      f.hcomp = (long long)c->ng * c->plane;
+   } else {
+      // periodic wrap inside this rank: the ghost planes ARE the opposite interior planes
+      f.lo = base ? base + (long long)(c->ns - c->ng) * c->plane : nullptr;
+      f.hi = base;
+      f.hcomp = c->ncell;
+   }
+   (void)depth;
+   return f;
+}
+
+// part: 0 = everything, 1 = interior (no ghost plane needed), 2 = boundary planes
+static int eval_part(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
+                     const ampe_rhs_fields* ydot, int fd_flag, cudaStream_t st, int part)
+{
+   (void)time;
+   if (!c || !y || !ydot) return set_err(AMPE_EINVAL, "null argument");
+   const Params& p = c->p;
+   if (p.with_phase && (!y->phase || !ydot->phase)) return set_err(AMPE_EINVAL, "phase missing");
+   if (p.qlen > 0 && !y->quat) return set_err(AMPE_EINVAL, "quat missing");
+   if (p.evolve_quat && !ydot->quat) return set_err(AMPE_EINVAL, "ydot quat missing");
+   if (p.with_conc && (!y->conc || !ydot->conc)) return set_err(AMPE_EINVAL, "conc missing");
+   if (p.with_T && (!y->temperature || !ydot->temperature))
+      return set_err(AMPE_EINVAL, "temperature missing");
+   const int ns = c->ns, ng = c->ng;
+   if (part != 0 && ns < 4 * ng) return set_err(AMPE_EINVAL, "slab too thin to split");
+   if (part != 2) c->launches = 0;
+
+   // QuatIntegrator.cc:3189
+   const bool recompute = (fd_flag == 0) || !c->cfg.lag_quat_sidegrad;
+   const bool has_lag_data = c->lagN[0] || c->lagD0[0];
+   const bool use_lag = !recompute && has_lag_data;
+   if (use_lag && !c->lag_valid)
+      return set_err(AMPE_EINVAL, "fd_flag=1 before any fd_flag=0 evaluation (no lagged data)");
+
+   // ---- Cahn-Hilliard: composition-only model -------------------------------------------
+   if (p.conc_form == AMPE_CONC_CAHN_HILLIARD) {
+      ChArgs A;
+      A.p = p;
+      A.conc = make_field(c, y->conc, c->halo_lo.conc, c->halo_hi.conc, 1);
+      A.out_c = ydot->conc;
+      int ranges[2][2];
+      int nr = 0;
+      if (part == 0) {
+         ranges[nr][0] = 0, ranges[nr++][1] = ns;
+      } else if (part == 1) {
+         ranges[nr][0] = ng, ranges[nr++][1] = ns - ng;
+      } else {
+         ranges[nr][0] = 0, ranges[nr++][1] = ng;
+         ranges[nr][0] = ns - ng, ranges[nr++][1] = ns;
+      }
+      for (int r = 0; r < nr; r++) {
+         A.s_begin = ranges[r][0];
+         A.s_end = ranges[r][1];
+         const long long total = c->plane * (A.s_end - A.s_begin);
+         const int blocks = (int)((total + 255) / 256);
+         if (p.ndim == 2)
+            ch_kernel<2><<<blocks, 256, 0, st>>>(A);
+         else
+            ch_kernel<3><<<blocks, 256, 0, st>>>(A);
+         CUDA_OK(cudaGetLastError());
+         c->launches++;
+      }
+      return AMPE_OK;
+   }
+
+   Field fphi = make_field(c, y->phase, c->halo_lo.phase, c->halo_hi.phase, 1);
+   Field fT = make_field(c, y->temperature, c->halo_lo.temperature, c->halo_hi.temperature, 1);
+   Field fq = make_field(c, y->quat, c->halo_lo.quat, c->halo_hi.quat, p.qlen);
+   Field fc = make_field(c, y->conc, c->halo_lo.conc, c->halo_hi.conc, 1);
+
+   // ---- per-cell KKS solve on the slab and its ghost planes ------------------------------
+   if (p.conc_form == AMPE_CONC_KKS || p.conc_form == AMPE_CONC_EBS) {
+      if (p.free_energy == AMPE_FE_CALPHAD && !c->have_ref)
+         return set_err(AMPE_EINVAL, "ampe_rhs_set_ref_concentrations must be called first");
+      KksArgs K;
+      K.p = p;
+      K.phi = fphi;
+      K.conc = fc;
+      K.cl_ref = c->cl_ref;
+      K.ca_ref = c->ca_ref;
+      K.cl = c->cl;
+      K.ca = c->ca;
+      K.nfail = c->nfail;
+      int ranges[2][2];
+      int nr = 0;
+      if (part == 0) {
+         ranges[nr][0] = -ng, ranges[nr++][1] = ns + ng;
+      } else if (part == 1) {
+         ranges[nr][0] = 0, ranges[nr++][1] = ns;
+      } else {
+         ranges[nr][0] = -ng, ranges[nr++][1] = 0;
+         ranges[nr][0] = ns, ranges[nr++][1] = ns + ng;
+      }
+      for (int r = 0; r < nr; r++) {
+         K.s_begin = ranges[r][0];
+         K.s_end = ranges[r][1];
+         const long long total = c->plane * (K.s_end - K.s_begin);
+         const int blocks = (int)((total + 255) / 256);
+         if (p.ndim == 2)
+            kks_kernel<2><<<blocks, 256, 0, st>>>(K);
+         else
+            kks_kernel<3><<<blocks, 256, 0, st>>>(K);
+         CUDA_OK(cudaGetLastError());
+         c->launches++;
+      }
+   }
+
+   FusedArgs A;
+   A.p = p;
+   A.phi = fphi;
+   A.T = fT;
+   A.q = fq;
+   A.conc = fc;
+   A.cl = c->cl;
+   A.ca = c->ca;
+   A.qr = c->qr_dev;
+   A.conj = c->conj_dev;
+   for (int d = 0; d < 3; d++) {
+      A.iq[d] = c->iq[d];
+      A.lagN[d] = c->lagN[d];
+      A.lagD0[d] = c->lagD0[d];
+      A.lagD1[d] = c->lagD1[d];
+   }
+   A.out_phi = ydot->phase;
+   A.out_q = ydot->quat;
+   A.out_c = ydot->conc;
+   A.out_T = ydot->temperature;
+   A.use_lag = use_lag ? 1 : 0;
+   A.write_lag = (recompute && c->cfg.lag_quat_sidegrad) ? 1 : 0;
+   int ranges[2][2];
+   int nr = 0;
+   if (part == 0) {
+      ranges[nr][0] = 0, ranges[nr++][1] = ns;
+   } else if (part == 1) {
+      ranges[nr][0] = ng, ranges[nr++][1] = ns - ng;
+   } else {
+      ranges[nr][0] = 0, ranges[nr++][1] = ng;
+      ranges[nr][0] = ns - ng, ranges[nr++][1] = ns;
+   }
+   for (int r = 0; r < nr; r++) {
+      A.s_begin = ranges[r][0];
+      A.s_end = ranges[r][1];
+      int rc = (p.ndim == 2) ? dispatch_q<2>(A, st) : dispatch_q<3>(A, st);
+      if (rc) return rc;
+      c->launches++;
+   }
+   if (part != 1 && A.write_lag) c->lag_valid = true;
+   return AMPE_OK;
+}
+
+extern "C" int ampe_rhs_eval(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
+                             const ampe_rhs_fields* ydot, int fd_flag, void* stream)
+{
+   return eval_part(c, time, y, ydot, fd_flag, (cudaStream_t)stream, 0);
+}
+extern "C" int ampe_rhs_eval_interior(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
+                                      const ampe_rhs_fields* ydot, int fd_flag, void* stream)
+{
+   return eval_part(c, time, y, ydot, fd_flag, (cudaStream_t)stream, 1);
+}
+extern "C" int ampe_rhs_eval_boundary(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
+                                      const ampe_rhs_fields* ydot, int fd_flag, void* stream)
+{
+   return eval_part(c, time, y, ydot, fd_flag, (cudaStream_t)stream, 2);
+}
+
+extern "C" int ampe_rhs_get_phase_concentrations(ampe_rhs_ctx* c, double** cl, double** ca)
+{
+   if (!c || !c->cl) return set_err(AMPE_EINVAL, "context has no phase concentrations");
+   // interior planes of the slab-ghosted arrays are contiguous ghost-0 arrays
+   *cl = c->cl + (long long)c->ng * c->plane;
+   *ca = c->ca + (long long)c->ng * c->plane;
+   return AMPE_OK;
+}
+
+extern "C" int ampe_rhs_copy_phase_concentrations(ampe_rhs_ctx* c, double* cl, double* ca,
+                                                  void* stream)
+{
+   if (!c || !c->cl) return set_err(AMPE_EINVAL, "context has no phase concentrations");
+   const size_t nb = (size_t)c->ncell * sizeof(double);
+   cudaStream_t st = (cudaStream_t)stream;
+   CUDA_OK(cudaMemcpyAsync(cl, c->cl + (long long)c->ng * c->plane, nb, cudaMemcpyDeviceToDevice, st));
+   CUDA_OK(cudaMemcpyAsync(ca, c->ca + (long long)c->ng * c->plane, nb, cudaMemcpyDeviceToDevice, st));
+   return AMPE_OK;
+}
+
+extern "C" int ampe_rhs_newton_failures(ampe_rhs_ctx* c, void* stream)
+{
+   if (!c) return AMPE_EINVAL;
+   if (!c->nfail) return 0;
+   int h = 0;
+   cudaStream_t st = (cudaStream_t)stream;
+   if (cudaMemcpyAsync(&h, c->nfail, sizeof(int), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      return AMPE_ECUDA;
+   if (cudaStreamSynchronize(st) != cudaSuccess) return AMPE_ECUDA;
+   cudaMemsetAsync(c->nfail, 0, sizeof(int), st);
+   return h;
+}
+
+extern "C" int ampe_rhs_last_launch_count(const ampe_rhs_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int ampe_rhs_eval_host(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* yh,
+                                  const ampe_rhs_fields* ydh, int fd_flag)
+{
+   if (!c || !yh || !ydh) return set_err(AMPE_EINVAL, "null argument");
+   const Params& p = c->p;
+   const size_t nb = (size_t)c->ncell * sizeof(double);
+   if (!c->have_dev) {
+      if (p.with_phase) {
+         CUDA_OK(cudaMalloc(&c->dev_y.phase, nb));
+         CUDA_OK(cudaMalloc(&c->dev_ydot.phase, nb));
+      }
+      if (p.qlen > 0) {
+         CUDA_OK(cudaMalloc(&c->dev_y.quat, nb * p.qlen));
+         CUDA_OK(cudaMalloc(&c->dev_ydot.quat, nb * p.qlen));
+      }
+      if (p.with_conc) {
+         CUDA_OK(cudaMalloc(&c->dev_y.conc, nb));
+         CUDA_OK(cudaMalloc(&c->dev_ydot.conc, nb));
+      }
+      if (p.with_T) {
+         CUDA_OK(cudaMalloc(&c->dev_y.temperature, nb));
+         CUDA_OK(cudaMalloc(&c->dev_ydot.temperature, nb));
+      }
+      CUDA_OK(cudaStreamCreate(&c->own_stream));
+      c->have_dev = true;
+   }
+   cudaStream_t st = c->own_stream;
+   if (p.with_phase)
+      CUDA_OK(cudaMemcpyAsync(c->dev_y.phase, yh->phase, nb, cudaMemcpyHostToDevice, st));
+   if (p.qlen > 0)
+      CUDA_OK(cudaMemcpyAsync(c->dev_y.quat, yh->quat, nb * p.qlen, cudaMemcpyHostToDevice, st));
+   if (p.with_conc)
+      CUDA_OK(cudaMemcpyAsync(c->dev_y.conc, yh->conc, nb, cudaMemcpyHostToDevice, st));
+   if (p.with_T)
+      CUDA_OK(cudaMemcpyAsync(c->dev_y.temperature, yh->temperature, nb, cudaMemcpyHostToDevice,
+                              st));
+   int rc = eval_part(c, time, &c->dev_y, &c->dev_ydot, fd_flag, st, 0);
+   if (rc) return rc;
+   if (p.with_phase)
+      CUDA_OK(cudaMemcpyAsync(ydh->phase, c->dev_ydot.phase, nb, cudaMemcpyDeviceToHost, st));
+   if (p.evolve_quat)
+      CUDA_OK(cudaMemcpyAsync(ydh->quat, c->dev_ydot.quat, nb * p.qlen, cudaMemcpyDeviceToHost,
+                              st));
+   if (p.with_conc)
+      CUDA_OK(cudaMemcpyAsync(ydh->conc, c->dev_ydot.conc, nb, cudaMemcpyDeviceToHost, st));
+   if (p.with_T)
+      CUDA_OK(cudaMemcpyAsync(ydh->temperature, c->dev_ydot.temperature, nb,
+                              cudaMemcpyDeviceToHost, st));
+   CUDA_OK(cudaStreamSynchronize(st));
+   return AMPE_OK;
+}
+
+extern "C" const char* ampe_last_error(void) { return g_err.c_str(); }
+extern "C" const char* ampe_version(void) { return "ampe_b200 0.1 (sm_100a)"; }
+extern "C" int ampe_abi_sizeof_config(void) { return (int)sizeof(ampe_rhs_config); }

@@ -1,0 +1,70 @@
+"""Loader of the C-ABI shared library libampe_b200.so (include/ampe_b200.h).
+
+There is no CPU fallback: if the library is missing or no CUDA device is
+present, the calls fail loudly."""
+import ctypes as C
+import os
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libampe_b200.so")
+
+_lib = None
+
+
+class AmpeError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AmpeError(
+            "libampe_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, dbl, ci = C.c_void_p, C.c_double, C.c_int
+    pcfg, pf = C.POINTER(_abi.RhsConfig), C.POINTER(_abi.RhsFields)
+    L.ampe_rhs_create.restype = ci
+    L.ampe_rhs_create.argtypes = [pcfg, C.POINTER(vp)]
+    L.ampe_rhs_destroy.argtypes = [vp]
+    L.ampe_rhs_set_ref_concentrations.restype = ci
+    L.ampe_rhs_set_ref_concentrations.argtypes = [vp, vp, vp, vp]
+    L.ampe_rhs_set_ref_concentrations_ghosted.restype = ci
+    L.ampe_rhs_set_ref_concentrations_ghosted.argtypes = [vp, vp, vp, vp]
+    L.ampe_rhs_set_symmetry_rotations.restype = ci
+    L.ampe_rhs_set_symmetry_rotations.argtypes = [vp, C.POINTER(vp), vp]
+    L.ampe_rhs_set_halo.restype = ci
+    L.ampe_rhs_set_halo.argtypes = [vp, pf, pf]
+    L.ampe_rhs_nghosts.restype = ci
+    L.ampe_rhs_nghosts.argtypes = [vp]
+    for name in ("ampe_rhs_eval", "ampe_rhs_eval_interior", "ampe_rhs_eval_boundary"):
+        fn = getattr(L, name)
+        fn.restype = ci
+        fn.argtypes = [vp, dbl, pf, pf, ci, vp]
+    L.ampe_rhs_eval_host.restype = ci
+    L.ampe_rhs_eval_host.argtypes = [vp, dbl, pf, pf, ci]
+    L.ampe_rhs_get_phase_concentrations.restype = ci
+    L.ampe_rhs_get_phase_concentrations.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.ampe_rhs_copy_phase_concentrations.restype = ci
+    L.ampe_rhs_copy_phase_concentrations.argtypes = [vp, vp, vp, vp]
+    L.ampe_rhs_newton_failures.restype = ci
+    L.ampe_rhs_newton_failures.argtypes = [vp, vp]
+    L.ampe_rhs_last_launch_count.restype = ci
+    L.ampe_rhs_last_launch_count.argtypes = [vp]
+    L.ampe_last_error.restype = C.c_char_p
+    L.ampe_version.restype = C.c_char_p
+    L.ampe_abi_sizeof_config.restype = ci
+    if L.ampe_abi_sizeof_config() != C.sizeof(_abi.RhsConfig):
+        raise AmpeError("ABI mismatch between _abi.py and libampe_b200.so")
+    _lib = L
+    return L
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().ampe_last_error().decode()
+        raise AmpeError("%s failed (%d): %s" % (what, rc, msg))

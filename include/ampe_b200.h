@@ -155,6 +155,10 @@ int ampe_rhs_destroy(ampe_rhs_ctx* ctx);
  * "copy the last computed c_l, c_a".                                         */
 int ampe_rhs_set_ref_concentrations(ampe_rhs_ctx* ctx, const double* cl_ref,
                                     const double* ca_ref, void* stream);
+/* Multi-rank variant: arrays that already carry the ghost planes along the
+ * slab axis (n_slab + 2*nghosts planes, first plane = lower ghost).          */
+int ampe_rhs_set_ref_concentrations_ghosted(ampe_rhs_ctx* ctx, const double* cl_ref_g,
+                                            const double* ca_ref_g, void* stream);
 /* quat_symm_rotation SideData<int> (QuatModel.cc:1714-1722): one int per
  * LOWER face per direction, ghost 0 (device).                                */
 int ampe_rhs_set_symmetry_rotations(ampe_rhs_ctx* ctx, const int* const* iqrot,
@@ -184,6 +188,9 @@ int ampe_rhs_eval_boundary(ampe_rhs_ctx* ctx, double time,
 /* device pointers to ctx-owned c_l, c_a (ghost 0) after an evaluation        */
 int ampe_rhs_get_phase_concentrations(ampe_rhs_ctx* ctx, double** cl,
                                       double** ca);
+/* copy c_l, c_a (ghost 0) into caller-owned device arrays                   */
+int ampe_rhs_copy_phase_concentrations(ampe_rhs_ctx* ctx, double* cl_out, double* ca_out,
+                                       void* stream);
 /* number of cells whose Newton failed in the last evaluation (synchronises)  */
 int ampe_rhs_newton_failures(ampe_rhs_ctx* ctx, void* stream);
 /* kernels launched by the last ampe_rhs_eval                                 */

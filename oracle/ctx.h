@@ -3,6 +3,14 @@
 #include "oracle.h"
 #include <vector>
 
+#ifdef ORACLE_OMP
+#define ORACLE_PAR _Pragma("omp parallel for collapse(2) schedule(static)")
+#define ORACLE_PAR_RED(v) _Pragma("omp parallel for collapse(2) schedule(static) reduction(+:nfail)")
+#else
+#define ORACLE_PAR
+#define ORACLE_PAR_RED(v)
+#endif
+
 namespace oracle {
 
 struct Ctx {

@@ -94,6 +94,7 @@ static void fill_periodic(const Box& b, const double* src, Field& dst, int ng, i
    const int n0 = b.hi[0] + 1, n1 = b.hi[1] + 1, n2 = b.hi[2] + 1;
    const int g2 = (b.ndim == 3) ? ng : 0;
    for (int m = 0; m < depth; m++)
+      ORACLE_PAR
       for (int k = -g2; k < n2 + g2; k++)
          for (int j = -ng; j < n1 + ng; j++)
             for (int i = -ng; i < n0 + ng; i++) {
@@ -118,6 +119,7 @@ static void copy_out(const Box& b, const Field& src, double* dst, int depth)
 {
    const int n0 = b.hi[0] + 1, n1 = b.hi[1] + 1, n2 = b.hi[2] + 1;
    for (int m = 0; m < depth; m++)
+      ORACLE_PAR
       for (int k = 0; k < n2; k++)
          for (int j = 0; j < n1; j++)
             for (int i = 0; i < n0; i++)
@@ -250,6 +252,7 @@ int eval(Ctx* c, double time, const ampe_rhs_fields* y, const ampe_rhs_fields* y
          add_driving_force(c);
       }
       // multiply by mobility (PhaseRHSStrategyWithQ.cc:297)
+      ORACLE_PAR
       for (int k = b.lo[2]; k <= b.hi[2]; k++)
          for (int j = b.lo[1]; j <= b.hi[1]; j++)
             for (int i = b.lo[0]; i <= b.hi[0]; i++)

@@ -59,7 +59,19 @@ void SideField::alloc(const Box& b, int ng, int depth)
 
 static inline int E(int a, int d) { return a == d ? 1 : 0; }
 // loop bounds of the side box of axis a grown by g in the transverse dirs
+// The perf build (liboracle_perf.so, -DORACLE_OMP) threads the two outer loops of every
+// sweep; the parity build is serial.  Loop bodies only write their own (i,j,k).
+#ifdef ORACLE_OMP
+#define ORACLE_OMP_FOR _Pragma("omp parallel for collapse(2) schedule(static)")
+#else
+#define ORACLE_OMP_FOR
+#endif
+#define FOR_BOX_SERIAL(i, j, k, L0, H0, L1, H1, L2, H2) \
+   for (int k = (L2); k <= (H2); k++)                   \
+      for (int j = (L1); j <= (H1); j++)                \
+         for (int i = (L0); i <= (H0); i++)
 #define FOR_BOX(i, j, k, L0, H0, L1, H1, L2, H2) \
+   ORACLE_OMP_FOR                                \
    for (int k = (L2); k <= (H2); k++)            \
       for (int j = (L1); j <= (H1); j++)         \
          for (int i = (L0); i <= (H0); i++)
@@ -351,7 +363,6 @@ void quatdiffs(const Box& b, int depth, View q, View* diff)
 // quatdiffs_symm: 2d/quatdiffs.m4:90-150, 3d/quatdiffs.m4:131-218
 void quatdiffs_symm(const Box& b, int depth, View q, View* diff, IView* iqrot)
 {
-   double q2[4], q2_prime[4];
    for (int a = 0; a < b.ndim; a++) {
       int L[3], H[3];
       for (int d = 0; d < 3; d++) {
@@ -361,6 +372,7 @@ void quatdiffs_symm(const Box& b, int depth, View q, View* diff, IView* iqrot)
       }
       FOR_BOX(i, j, k, L[0], H[0], L[1], H[1], L[2], H[2])
       {
+         double q2[4], q2_prime[4];
          for (int m = 0; m < depth; m++)
             q2[m] = q(i - E(a, 0), j - E(a, 1), k - E(a, 2), m);
          quatsymmrotate(q2, iqrot[a](i, j, k), q2_prime, depth);
@@ -389,11 +401,11 @@ void quatgrad_cell(const Box& b, int depth, const double* h, View* diff, View* g
 void quatgrad_cell_symm(const Box& b, int depth, const double* h, View* diff, View* grad,
                         IView* iqrot)
 {
-   double dtmp[4], dprime[4];
    for (int a = 0; a < b.ndim; a++) {
       const double p5inv = 0.5 / h[a];
       FOR_CELLS(b, i, j, k)
       {
+         double dtmp[4], dprime[4];
          const int ip = i + E(a, 0), jp = j + E(a, 1), kp = k + E(a, 2);
          if (depth > 1) {
             for (int m = 0; m < depth; m++) dtmp[m] = diff[a](ip, jp, kp, m);
@@ -436,10 +448,10 @@ void quatgrad_side(const Box& b, int depth, const double* h, View* diff, View* g
 void quatgrad_side_symm(const Box& b, int depth, const double* h, View* diff, View* grad,
                         IView* iqrot)
 {
-   double d1[4], d1p[4], d2[4], d2p[4], d3[4], d4[4], d4p[4];
    for (int a = 0; a < b.ndim; a++) {
       FOR_SIDES(b, a, i, j, k)
       {
+         double d1[4], d1p[4], d2[4], d2p[4], d3[4], d4[4], d4p[4];
          const int im = i - E(a, 0), jm = j - E(a, 1), km = k - E(a, 2);
          for (int t = 0; t < b.ndim; t++) {
             if (t == a) continue;
@@ -623,9 +635,9 @@ void correctrhsquatforsymmetry(const Box& b, int depth, const double* dx, View* 
 {
    double invdx2[3] = {0, 0, 0};
    for (int d = 0; d < b.ndim; d++) invdx2[d] = 1.0 / (dx[d] * dx[d]);
-   double tmp[4], dtmp[4], dprime[3][4];
    FOR_CELLS(b, i, j, k)
    {
+      double tmp[4], dtmp[4], dprime[3][4];
       for (int a = 0; a < b.ndim; a++) {
          const int ip = i + E(a, 0), jp = j + E(a, 1), kp = k + E(a, 2);
          if (depth > 1) {
@@ -719,7 +731,7 @@ void add_cahnhilliarddoublewell_flux(const Box& b, const double* dx, View conc,
       L[d] = b.lo[d] - g;
       H[d] = b.hi[d] + g;
    }
-   FOR_BOX(i, j, k, L[0], H[0], L[1], H[1], L[2], H[2])
+   FOR_BOX_SERIAL(i, j, k, L[0], H[0], L[1], H[1], L[2], H[2])
    {
       double lap = dinv2[0] * (-2.0 * conc(i, j, k) + conc(i - 1, j, k) + conc(i + 1, j, k)) +
                    dinv2[1] * (-2.0 * conc(i, j, k) + conc(i, j - 1, k) + conc(i, j + 1, k));

@@ -37,6 +37,7 @@ int compute_phase_concentrations(Ctx* c)
    }
    int nfail = 0;
    const Quadratic quad = quad_params(p);
+   ORACLE_PAR_RED(nfail)
    for (int k = L[2]; k <= H[2]; k++)
       for (int j = L[1]; j <= H[1]; j++)
          for (int i = L[0]; i <= H[0]; i++) {
@@ -71,6 +72,7 @@ void compute_free_energies(Ctx* c)
    const double inv_vm_a = 1.e-6 / p.vm_solid;
    const Quadratic quad = quad_params(p);
    for (int pass = 0; pass < 2; pass++)
+      ORACLE_PAR
       for (int k = b.lo[2]; k <= b.hi[2]; k++)
          for (int j = b.lo[1]; j <= b.hi[1]; j++)
             for (int i = b.lo[0]; i <= b.hi[0]; i++) {
@@ -93,6 +95,7 @@ void add_driving_force(Ctx* c)
    const ampe_rhs_config& p = c->cfg;
    const Box& b = c->box;
    const Quadratic quad = quad_params(p);
+   ORACLE_PAR
    for (int k = b.lo[2]; k <= b.hi[2]; k++)
       for (int j = b.lo[1]; j <= b.hi[1]; j++)
          for (int i = b.lo[0]; i <= b.hi[0]; i++) {
@@ -127,6 +130,7 @@ void set_diffusion_coeff_for_concentration(Ctx* c)
       // MobilityCompositionDiffusionStrategy::setDiffCoeffInEachPhaseOnPatch (:197-407)
       // then setPFMDiffOnPatch (:409-611); stored already multiplied by (1-h) / h.
       for (int a = 0; a < b.ndim; a++)
+         ORACLE_PAR
          for (int k = b.lo[2]; k <= b.hi[2] + E(a, 2); k++)
             for (int j = b.lo[1]; j <= b.hi[1] + E(a, 1); j++)
                for (int i = b.lo[0]; i <= b.hi[0] + E(a, 0); i++) {
@@ -159,6 +163,7 @@ void set_diffusion_coeff_for_concentration(Ctx* c)
                                  p.conc_avg_func);
       // setDiffCoeffForPhaseOnPatch (:210-373)
       for (int a = 0; a < b.ndim; a++)
+         ORACLE_PAR
          for (int k = b.lo[2]; k <= b.hi[2] + E(a, 2); k++)
             for (int j = b.lo[1]; j <= b.hi[1] + E(a, 1); j++)
                for (int i = b.lo[0]; i <= b.hi[0] + E(a, 0); i++) {
