@@ -7,6 +7,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -15,7 +16,9 @@
 using namespace ampe;
 
 static thread_local std::string g_err;
-static int set_err(int code, const std::string& msg)
+int ampe_set_err(int code, const std::string& msg);
+static int set_err(int code, const std::string& msg) { return ampe_set_err(code, msg); }
+int ampe_set_err(int code, const std::string& msg)
 {
    g_err = msg;
    return code;
@@ -90,7 +93,7 @@ static void fill_calphadT(const ampe_calphad_binary& db, double T, CalphadT& o)
       }
 }
 
-static int derive_params(const ampe_rhs_config& c, Params& p)
+int ampe_derive_params(const ampe_rhs_config& c, Params& p)
 {
    memset(&p, 0, sizeof(p));
    if (c.ndim != 2 && c.ndim != 3) return set_err(AMPE_EINVAL, "ndim must be 2 or 3");
@@ -111,6 +114,7 @@ static int derive_params(const ampe_rhs_config& c, Params& p)
    p.free_energy = c.free_energy;
    p.symm = c.symmetry_aware && p.evolve_quat;
    p.modulus_from_cells = c.quat_grad_modulus_from_cells;
+   p.libm_trig = (getenv("AMPE_B200_LIBM_TRIG") != nullptr) ? 1 : 0;
    p.energy_interp = c.energy_interp;
    p.conc_interp = c.conc_interp;
    p.diffusion_interp = c.diffusion_interp;
@@ -266,7 +270,7 @@ extern "C" int ampe_rhs_create(const ampe_rhs_config* cfg, ampe_rhs_ctx** out)
       return set_err(AMPE_ENOGPU, "no CUDA device: libampe_b200 has no CPU fallback");
    ampe_rhs_ctx* c = new ampe_rhs_ctx;
    c->cfg = *cfg;
-   int rc = derive_params(*cfg, c->p);
+   int rc = ampe_derive_params(*cfg, c->p);
    if (rc) {
       delete c;
       return rc;

@@ -11,15 +11,26 @@ namespace ampe {
 template <int ND, int Q, int CONC, bool SYMM>
 static int launch_fused(const FusedArgs& A, cudaStream_t st, const char** err)
 {
+   // tile shape and block size (tuned on B200, see profiles/): 2D 32x16 cells, 256 threads;
+   // 3D 32x4x4 cells, 512 threads (shared memory, not registers, bounds the 3D occupancy)
+#ifndef AMPE_T2Y
+#define AMPE_T2Y 16
+#define AMPE_NT2 256
+#endif
+#ifndef AMPE_T3Y
+#define AMPE_T3Y 4
+#define AMPE_T3Z 4
+#define AMPE_NT3 512
+#endif
    constexpr int TX = 32;
-   constexpr int TY = (ND == 2) ? 16 : 4;
-   constexpr int TZ = (ND == 2) ? 1 : 4;
-   constexpr int NT = 256;
+   constexpr int TY = (ND == 2) ? AMPE_T2Y : AMPE_T3Y;
+   constexpr int TZ = (ND == 2) ? 1 : AMPE_T3Z;
+   constexpr int NT = (ND == 2) ? AMPE_NT2 : AMPE_NT3;
    using G = TileGeom<ND, TX, TY, TZ>;
    const Params& p = A.p;
    size_t doubles = (size_t)G::S * (1 + (p.with_T ? 1 : 0) + Q + (CONC == AMPE_CONC_KKS ? 1 : 0) +
                                     (CONC != 0 ? 2 : 0));
-   doubles += (size_t)G::NF * ((p.evolve_quat ? 1 : 0) + (p.flux_type != AMPE_FLUX_SIMPLE ? 1 : 0) +
+   doubles += (size_t)ND * G::NFB * (((Q > 0 && p.evolve_quat) ? 1 : 0) + (p.flux_type != AMPE_FLUX_SIMPLE ? 1 : 0) +
                                (CONC != 0 ? 1 : 0));
    size_t bytes = doubles * sizeof(double) + (SYMM ? (size_t)ND * G::S * sizeof(int) : 0);
    auto kern = rhs_fused_kernel<ND, Q, CONC, SYMM, TX, TY, TZ, NT>;

@@ -25,6 +25,7 @@ struct Params {
    int ng;        // ghost width of the state (1; 2 for Cahn-Hilliard)
    int with_phase, with_conc, with_T, evolve_quat;
    int flux_type, conc_form, free_energy, symm, modulus_from_cells;
+   int libm_trig;  // 1: evaluate the anisotropy with atan/acos/sincos exactly as written in the reference
    char energy_interp, conc_interp, diffusion_interp, orient_interp1, orient_interp2;
    char avg_func, conc_avg_func, grad_floor_type, quat_mobility_func;
 

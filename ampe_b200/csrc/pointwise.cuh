@@ -13,18 +13,15 @@ namespace ampe {
 
 AMPE_DEV double clamp01(double x) { return fmax(0.0, fmin(1.0, x)); }
 
-// interp_func, functions.f:17-91
-AMPE_DEV double interp_func(double phi, char type)
+// Rarely selected forms are kept out of line: inlining their log/cosh/tanh expansions at
+// every call site bloated the fused kernel to ~12k SASS lines and showed up as
+// instruction-fetch stalls (profiles/r01_dendrite2d.md).
+#define AMPE_DEV_NOINLINE __device__ __noinline__
+static AMPE_DEV_NOINLINE double interp_func_rare(double phi, char type)
 {
    double phit;
    switch (type) {
-      case 'q': phit = fmax(0.0, phi); return phit * phit;
-      case 'p':
-         phit = clamp01(phi);
-         return phit * phit * phit * (10.0 - 15.0 * phit + 6.0 * phit * phit);
-      case 'h': phit = clamp01(phi); return phit * phit * (3.0 - 2.0 * phit);
       case 'w': phit = fmax(0.0, phi); return phit * phit * (2.0 - phit);
-      case 'l': phit = fmax(0.0, phi); return fmin(1.0, phit);
       case 'm':
          phit = clamp01(phi);
          return phit * phit / (2.0 * phit * (phit - 1.0) + 1.0);
@@ -33,19 +30,35 @@ AMPE_DEV double interp_func(double phi, char type)
       default: return 1.0;  // 'c'
    }
 }
+// interp_func, functions.f:17-91
+AMPE_DEV double interp_func(double phi, char type)
+{
+   double phit;
+   if (type == 'p') {
+      phit = clamp01(phi);
+      return phit * phit * phit * (10.0 - 15.0 * phit + 6.0 * phit * phit);
+   }
+   if (type == 'q') {
+      phit = fmax(0.0, phi);
+      return phit * phit;
+   }
+   if (type == 'c') return 1.0;
+   if (type == 'h') {
+      phit = clamp01(phi);
+      return phit * phit * (3.0 - 2.0 * phit);
+   }
+   if (type == 'l') {
+      phit = fmax(0.0, phi);
+      return fmin(1.0, phit);
+   }
+   return interp_func_rare(phi, type);
+}
 
-// deriv_interp_func, functions.f:95-172
-AMPE_DEV double deriv_interp_func(double phi, char type)
+static AMPE_DEV_NOINLINE double deriv_interp_func_rare(double phi, char type)
 {
    double phit, tmp;
    switch (type) {
-      case 'q': phit = fmax(0.0, phi); return 2.0 * phit;
-      case 'p':
-         phit = clamp01(phi);
-         return 30.0 * phit * phit * (1.0 - phit) * (1.0 - phit);
-      case 'h': phit = clamp01(phi); return 6.0 * phit * (1.0 - phit);
       case 'w': phit = fmax(0.0, phi); return phit * (4.0 - 3.0 * phit);
-      case 'l': return (phi > 0.0 || phi < 1.0) ? 1.0 : 0.0;  // `.or.`: functions.f:134-141
       case 'm':
          phit = clamp01(phi);
          tmp = 2.0 * phit * (phit - 1.0) + 1.0;
@@ -54,6 +67,26 @@ AMPE_DEV double deriv_interp_func(double phi, char type)
       case 's': phit = fmax(0.0, phi); return 10.0 * tanh(10.0 * phit) / log(cosh(10.0));
       default: return 0.0;  // 'c'
    }
+}
+// deriv_interp_func, functions.f:95-172
+AMPE_DEV double deriv_interp_func(double phi, char type)
+{
+   double phit;
+   if (type == 'p') {
+      phit = clamp01(phi);
+      return 30.0 * phit * phit * (1.0 - phit) * (1.0 - phit);
+   }
+   if (type == 'q') {
+      phit = fmax(0.0, phi);
+      return 2.0 * phit;
+   }
+   if (type == 'c') return 0.0;
+   if (type == 'h') {
+      phit = clamp01(phi);
+      return 6.0 * phit * (1.0 - phit);
+   }
+   if (type == 'l') return (phi > 0.0 || phi < 1.0) ? 1.0 : 0.0;  // `.or.`: functions.f:134-141
+   return deriv_interp_func_rare(phi, type);
 }
 
 // deriv_well_func('d'|'s'), functions.f:276-300
@@ -76,12 +109,10 @@ AMPE_DEV double average_func(double a, double b, char type)
    return 2.0 / (1.0 / a + 1.0 / b);
 }
 
-// eval_grad_normi, quat.f:1497-1537 (x**(-0.5) evaluated as 1/sqrt(x))
-AMPE_DEV double eval_grad_normi(double g2, char floor_type, double floor2, double max_normi)
+static AMPE_DEV_NOINLINE double eval_grad_normi_rare(double g2, char floor_type, double floor2,
+                                                     double max_normi)
 {
-   if (floor_type == 'm') {
-      return (g2 > floor2) ? 1.0 / sqrt(g2) : max_normi;
-   } else if (floor_type == 't') {
+   if (floor_type == 't') {
       const double gng2 = g2 * max_normi * max_normi;
       if (gng2 > 0.01) {
          const double gn = sqrt(g2);
@@ -91,16 +122,18 @@ AMPE_DEV double eval_grad_normi(double g2, char floor_type, double floor2, doubl
    }
    return 1.0 / sqrt(g2 + floor2);  // 's'
 }
+// eval_grad_normi, quat.f:1497-1537 (x**(-0.5) evaluated as 1/sqrt(x))
+AMPE_DEV double eval_grad_normi(double g2, char floor_type, double floor2, double max_normi)
+{
+   if (floor_type == 'm') return (g2 > floor2) ? 1.0 / sqrt(g2) : max_normi;
+   return eval_grad_normi_rare(g2, floor_type, floor2, max_normi);
+}
 
-// quatmobility, 3d/mobility.m4:42-92
-AMPE_DEV double quat_mobility(double phi, char func, double scale, double minm, double alt)
+static AMPE_DEV_NOINLINE double quat_mobility_rare(double phi, char func, double scale, double minm,
+                                                   double alt)
 {
    double qfunc;
-   if (func == 'p' || func == 'P') {
-      phi = clamp01(phi);
-      qfunc = phi * phi * phi * (10.0 - 15.0 * phi + 6.0 * phi * phi);
-      qfunc = 1.0 - qfunc;
-   } else if (func == 'e' || func == 'E') {
+   if (func == 'e' || func == 'E') {
       phi = clamp01(phi);
       qfunc = (1.0 - exp(alt * phi)) / (1.0 - exp(alt));
       qfunc = 1.0 - qfunc;
@@ -110,6 +143,17 @@ AMPE_DEV double quat_mobility(double phi, char func, double scale, double minm, 
       qfunc = fmin(qfunc, alt);
    }
    return minm + (scale - minm) * qfunc;
+}
+// quatmobility, 3d/mobility.m4:42-92
+AMPE_DEV double quat_mobility(double phi, char func, double scale, double minm, double alt)
+{
+   if (func == 'p' || func == 'P') {
+      phi = clamp01(phi);
+      double qfunc = phi * phi * phi * (10.0 - 15.0 * phi + 6.0 * phi * phi);
+      qfunc = 1.0 - qfunc;
+      return minm + (scale - minm) * qfunc;
+   }
+   return quat_mobility_rare(phi, func, scale, minm, alt);
 }
 
 // quatmult4 / quatmult2, quat.f:867-911

@@ -15,11 +15,13 @@
 //   CALPHAD/Quadratic free energies + driving force, EBS face diffusivities,
 //   add_flux / concentrationflux / concentration_pfmdiffusion, computerhsconcentration
 //
-// Structure: (A) stage tile+halo in smem; (B) every FACE of the tile once:
-// anisotropic phase flux, quaternion face coefficient, composition flux ->
-// smem; (C) every CELL: divergences + pointwise terms -> global.  Operation
-// order inside each expression follows the Fortran so that results agree with
-// the CPU restatement to rounding of the transcendental functions only.
+// Structure: (A) stage tile+halo in smem with cp.async; (B) every FACE of the tile
+// exactly once -- each thread computes the lower faces of the cells it owns, the
+// tile's upper boundary faces are spread over the block -- anisotropic phase flux,
+// quaternion face coefficient, composition flux -> smem; (C) every CELL:
+// divergences + pointwise terms -> global.  Operation order inside each
+// expression follows the Fortran so that results agree with the CPU restatement
+// to rounding of the transcendental functions only.
 #pragma once
 #include "calphad.cuh"
 #include "params.h"
@@ -59,7 +61,6 @@ struct FusedArgs {
    int s_begin, s_end;  // slab-axis range of cells to compute [begin, end)
 };
 
-
 template <int Q>
 AMPE_DEV void symm_rotate(const double* q, int iq, double* qp, const double (*s_qr)[4],
                           const int* s_conj)
@@ -87,18 +88,46 @@ AMPE_DEV void symm_rotate(const double* q, int iq, double* qp, const double (*s_
    }
 }
 
+// libm evaluation of the 2D anisotropy angle functions exactly as written in
+// anisotropic_gradient_flux (2d/quatrhs.m4:192-214); selected with AMPE_B200_LIBM_TRIG=1
+static __device__ __noinline__ void aniso_trig_libm(double dphidx, double dphidy, double qa,
+                                                    int knumber, int qlen, double* sn, double* cs)
+{
+   double theta;
+   if (fabs(dphidx) > (double)1.e-12f)
+      theta = atan(dphidy / dphidx);
+   else
+      theta = 0.5 * 3.141592653589793;  // 4.d0*atan(1.d0)
+   const double ang = (qlen == 4) ? 2.0 * acos(qa) : acos(qa);
+   sincos(knumber * (theta - ang), sn, cs);
+}
+
+AMPE_DEV void cp_async8(void* smem_dst, const void* gmem_src)
+{
+   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src));
+}
+AMPE_DEV void cp_async4(void* smem_dst, const void* gmem_src)
+{
+   const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src));
+}
+AMPE_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 template <int ND, int TX, int TY, int TZ>
 struct TileGeom {
    static constexpr int HZ = (ND == 3) ? 1 : 0;
    static constexpr int SX = TX + 2, SY = TY + 2, SZ = TZ + 2 * HZ;
-   static constexpr int S = SX * SY * SZ;  // staged cells
-   static constexpr int NC = TX * TY * TZ;  // computed cells
-   static constexpr int F0 = (TX + 1) * TY * TZ;
-   static constexpr int F1 = TX * (TY + 1) * TZ;
-   static constexpr int F2 = (ND == 3) ? TX * TY * (TZ + 1) : 0;
-   static constexpr int NF = F0 + F1 + F2;
-   // staged index of local cell (i,j,k), i in [-1,TX] ...
+   static constexpr int S = SX * SY * SZ;    // staged cells
+   static constexpr int NC = TX * TY * TZ;   // computed cells
+   // face box: lower faces of the cells (0..TX, 0..TY, 0..TZ), one array per direction
+   static constexpr int FX = TX + 1, FY = TY + 1, FZ = TZ + HZ;
+   static constexpr int NFB = FX * FY * FZ;
+   // faces on the upper boundary of the tile, not owned by a cell of the tile
+   static constexpr int E0 = TY * TZ, E1 = TX * TZ, E2 = (ND == 3) ? TX * TY : 0;
+   static constexpr int NE = E0 + E1 + E2;
    AMPE_DEV static int sidx(int i, int j, int k) { return (i + 1) + SX * ((j + 1) + SY * (k + HZ)); }
+   AMPE_DEV static int fidx(int i, int j, int k) { return i + FX * (j + FY * k); }
 };
 
 // CONC: 0 none, 2 KKS(quadratic), 3 EBS(CALPHAD)  (AMPE_CONC_*)
@@ -108,6 +137,12 @@ __global__ void __launch_bounds__(NT)
 {
    using G = TileGeom<ND, TX, TY, TZ>;
    constexpr int S = G::S;
+   constexpr int NFB = G::NFB;
+   constexpr int QN = (Q > 0) ? Q : 1;
+   static_assert(TX == 32, "one warp per tile row");
+   static_assert((TX * TY * TZ) % NT == 0, "cells per thread must be integral");
+   constexpr int CPT = TX * TY * TZ / NT;  // cells owned by a thread
+   constexpr int RP = NT / TX;             // tile rows per pass (= warps)
    const Params& p = A.p;
    extern __shared__ double smem[];
 
@@ -118,13 +153,13 @@ __global__ void __launch_bounds__(NT)
    double* s_c = s_q + Q * S;                     // conc (KKS form)
    double* s_cl = s_c + (CONC == AMPE_CONC_KKS ? S : 0);
    double* s_ca = s_cl + (CONC != 0 ? S : 0);
-   double* s_fc = s_ca + (CONC != 0 ? S : 0);     // quaternion face coefficient, NF
-   double* s_pf = s_fc + (p.evolve_quat ? G::NF : 0);  // phase flux (non-simple stencils)
-   double* s_cf = s_pf + (p.flux_type != AMPE_FLUX_SIMPLE ? G::NF : 0);  // composition flux
-   double* s_end = s_cf + (CONC != 0 ? G::NF : 0);
+   double* s_fc = s_ca + (CONC != 0 ? S : 0);     // quaternion face coefficient, ND*NFB
+   double* s_pf = s_fc + ((Q > 0 && p.evolve_quat) ? ND * NFB : 0);  // phase flux (non-simple)
+   double* s_cf = s_pf + (p.flux_type != AMPE_FLUX_SIMPLE ? ND * NFB : 0);  // composition flux
+   double* s_end = s_cf + (CONC != 0 ? ND * NFB : 0);
    int* s_iq = reinterpret_cast<int*>(s_end);     // ND*S ints (SYMM)
-   __shared__ double s_qr[48][4];
-   __shared__ int s_conj[48];
+   __shared__ double s_qr[SYMM ? 48 : 1][4];
+   __shared__ int s_conj[SYMM ? 48 : 1];
    if (SYMM && Q == 4) {
       for (int t = threadIdx.x; t < 48 * 4; t += NT) s_qr[t / 4][t % 4] = A.qr[t];
       for (int t = threadIdx.x; t < 48; t += NT) s_conj[t] = A.conj[t];
@@ -139,65 +174,80 @@ __global__ void __launch_bounds__(NT)
    const long long plane = (ND == 3) ? (long long)n0 * n1 : (long long)n0;  // slab plane size
    const long long ncell = (long long)n0 * n1 * n2;
    const double Tuni = p.T_uniform;
+   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
 
-   // ---- (A) stage ---------------------------------------------------------------
-   for (int s = threadIdx.x; s < S; s += NT) {
-      const int li = s % G::SX - 1;
-      const int lj = (s / G::SX) % G::SY - 1;
-      const int lk = (ND == 3) ? (s / (G::SX * G::SY) - 1) : 0;
-      int gi = ox + li, gj = oy + lj, gk = oz + lk;
-      // x: periodic wrap inside the rank
-      gi = gi % n0;
-      gi = (gi < 0) ? gi + n0 : gi;
-      int sl;  // slab-axis index (may be -1 or ns)
-      long long inplane;
-      if (ND == 3) {
-         gj = gj % n1;
-         gj = (gj < 0) ? gj + n1 : gj;
-         sl = gk;
-         inplane = gi + (long long)n0 * gj;
-      } else {
-         sl = gj;
-         inplane = gi;
-      }
-      // tiles may overhang the domain (n not multiple of tile): clamp the slab index of
-      // cells that are only read by out-of-range cells
-      if (sl > ns) sl = ns;
-      const bool below = sl < 0, above = sl >= ns;
-      const long long off_base = (long long)sl * plane + inplane;
-      const long long off_lo = (long long)(sl + 1) * plane + inplane;   // ng = 1
-      const long long off_hi = (long long)(sl - ns) * plane + inplane;
-      auto ld = [&](const Field& f, int m) -> double {
-         if (below) return f.lo[off_lo + m * f.hcomp];
-         if (above) return f.hi[off_hi + m * f.hcomp];
-         return f.base[off_base + m * f.comp];
-      };
-      s_phi[s] = ld(A.phi, 0);
-      if (p.with_T) s_T[s] = ld(A.T, 0);
+   // ---- (A) stage: one warp per staged row, cp.async (no register staging) ------------
+   {
+      // x indices of the two elements a lane copies: staged x = lane and lane + 32 (< SX)
+      int gx0 = (ox + lane - 1) % n0;
+      gx0 = (gx0 < 0) ? gx0 + n0 : gx0;
+      const int gx1 = (ox + lane + 31) % n0;
+      const bool second = lane < G::SX - 32;
+      for (int r = warp; r < G::SY * G::SZ; r += RP) {
+         const int lj = r % G::SY - 1;
+         const int lk = (ND == 3) ? (r / G::SY - 1) : 0;
+         int gj = oy + lj, sl;
+         long long rowoff;
+         if (ND == 3) {
+            gj = gj % n1;
+            gj = (gj < 0) ? gj + n1 : gj;
+            sl = oz + lk;
+            rowoff = (long long)n0 * gj;
+         } else {
+            sl = gj;
+            rowoff = 0;
+         }
+         // tiles may overhang the domain: rows beyond the upper ghost plane are only read by
+         // out-of-range cells, clamp them onto the ghost plane
+         if (sl > ns) sl = ns;
+         const bool below = sl < 0, above = sl >= ns;
+         const long long og = (long long)(sl + 1) * plane + rowoff;  // slab-ghosted arrays
+         const int srow = r * G::SX;
+         auto row_copy = [&](const Field& f, int m, double* dst) {
+            const double* src;
+            if (below)
+               src = f.lo + (long long)(sl + 1) * plane + rowoff + m * f.hcomp;
+            else if (above)
+               src = f.hi + (long long)(sl - ns) * plane + rowoff + m * f.hcomp;
+            else
+               src = f.base + (long long)sl * plane + rowoff + m * f.comp;
+            cp_async8(dst + srow + lane, src + gx0);
+            if (second) cp_async8(dst + srow + lane + 32, src + gx1);
+         };
+         row_copy(A.phi, 0, s_phi);
+         if (p.with_T) row_copy(A.T, 0, s_T);
 #pragma unroll
-      for (int m = 0; m < Q; m++) s_q[m * S + s] = ld(A.q, m);
-      if (CONC == AMPE_CONC_KKS) s_c[s] = ld(A.conc, 0);
-      if (CONC != 0) {
-         const long long og = (long long)(sl + 1) * plane + inplane;  // slab-ghosted arrays
-         s_cl[s] = A.cl[og];
-         s_ca[s] = A.ca[og];
-      }
-      if (SYMM) {
-         const long long og = (long long)(sl + 1) * plane + inplane;
+         for (int m = 0; m < Q; m++) row_copy(A.q, m, s_q + m * S);
+         if (CONC == AMPE_CONC_KKS) row_copy(A.conc, 0, s_c);
+         if (CONC != 0) {
+            cp_async8(s_cl + srow + lane, A.cl + og + gx0);
+            cp_async8(s_ca + srow + lane, A.ca + og + gx0);
+            if (second) {
+               cp_async8(s_cl + srow + lane + 32, A.cl + og + gx1);
+               cp_async8(s_ca + srow + lane + 32, A.ca + og + gx1);
+            }
+         }
+         if (SYMM) {
 #pragma unroll
-         for (int a = 0; a < ND; a++) s_iq[a * S + s] = A.iq[a][og];
+            for (int a = 0; a < ND; a++) {
+               cp_async4(s_iq + a * S + srow + lane, A.iq[a] + og + gx0);
+               if (second) cp_async4(s_iq + a * S + srow + lane + 32, A.iq[a] + og + gx1);
+            }
+         }
       }
+      cp_async_wait_all();
    }
    __syncthreads();
 
    const int soff[3] = {1, G::SX, G::SX * G::SY};  // staged strides
+   const int foff[3] = {1, G::FX, G::FX * G::FY};  // face-box strides
 
    // symmetric / plain difference of direction a at staged cell c (lower face of c)
    auto qdiff = [&](int a, int c, double* d) {
       const int cm = c - soff[a];
       if constexpr (Q == 0) {
       } else if constexpr (SYMM) {
-         double q2[Q > 0 ? Q : 1], q2p[Q > 0 ? Q : 1];
+         double q2[QN], q2p[QN];
 #pragma unroll
          for (int m = 0; m < Q; m++) q2[m] = s_q[m * S + cm];
          symm_rotate<Q>(q2, s_iq[a * S + c], q2p, s_qr, s_conj);
@@ -209,43 +259,23 @@ __global__ void __launch_bounds__(NT)
       }
    };
 
-   // ---- (B) faces -----------------------------------------------------------------
-   for (int f = threadIdx.x; f < G::NF; f += NT) {
-      int a, li, lj, lk;
-      if (f < G::F0) {
-         a = 0;
-         li = f % (TX + 1);
-         lj = (f / (TX + 1)) % TY;
-         lk = f / ((TX + 1) * TY);
-      } else if (f < G::F0 + G::F1) {
-         const int g = f - G::F0;
-         a = 1;
-         li = g % TX;
-         lj = (g / TX) % (TY + 1);
-         lk = g / (TX * (TY + 1));
-      } else {
-         const int g = f - G::F0 - G::F1;
-         a = 2;
-         li = g % TX;
-         lj = (g / TX) % TY;
-         lk = g / (TX * TY);
-      }
+   // ---- (B) one face: lower face of local cell (li,lj,lk) in direction a --------------
+   // lag_owner: this work item is the one that refreshes the lagged arrays for the face
+   auto face = [&](int a, int li, int lj, int lk, bool lag_owner) {
       const int c = G::sidx(li, lj, lk);
       const int cm = c - soff[a];
+      const int f = a * NFB + G::fidx(li, lj, lk);
       const double phi_c = s_phi[c], phi_m = s_phi[cm];
 
       // global (wrapped) face index for the lagged arrays
-      int gi = ox + li, gj = oy + lj, gk = oz + lk;
-      const bool inrange = (ox + li - (a == 0) < n0) && (oy + lj - (a == 1) < n1) &&
-                           (oz + lk - (a == 2) < n2);
-      gi = gi % n0;
-      if (ND == 3) gj = gj % n1;
+      int gi = ox + li, gj = oy + lj;
+      const int gk = oz + lk;
+      const bool inrange = (gi - (a == 0) < n0) && (gj - (a == 1) < n1) && (gk - (a == 2) < n2);
+      gi = (gi >= n0) ? gi % n0 : gi;
+      if (ND == 3) gj = (gj >= n1) ? gj % n1 : gj;
       const long long gface = (ND == 3) ? (gi + (long long)n0 * (gj + (long long)n1 * gk))
                                         : (gi + (long long)n0 * gj);
-      // a face is written to the lag arrays by the tile that owns its upper cell, or by
-      // the last tile for the extra plane ns along the slab axis
-      const bool owner = inrange && (li < TX) && (lj < TY || (ND == 2 && gj == ns)) &&
-                         (ND == 2 || lk < TZ || gk == ns);
+      const bool wr = A.write_lag && lag_owner && inrange;
 
       // ---- quaternion face coefficient (compute_face_coef) ----
       if constexpr (Q > 0) if (p.evolve_quat) {
@@ -257,7 +287,7 @@ __global__ void __launch_bounds__(NT)
 #pragma unroll
             for (int n = 0; n < ND; n++) {
                if (n == a) {
-                  double d[Q];
+                  double d[QN];
                   qdiff(a, c, d);
 #pragma unroll
                   for (int m = 0; m < Q; m++) {
@@ -266,9 +296,9 @@ __global__ void __launch_bounds__(NT)
                   }
                } else {
                   const int ct = c + soff[n], cmt = cm + soff[n];
-                  double g[Q];
+                  double g[QN];
                   if (SYMM && Q > 1) {
-                     double d1[Q], d1p[Q], d2[Q], d2p[Q], d3[Q], d4[Q], d4p[Q], d0[Q];
+                     double d1[QN], d1p[QN], d2[QN], d2p[QN], d3[QN], d4[QN], d4p[QN], d0[QN];
                      qdiff(n, ct, d1);
                      qdiff(n, cmt, d2);
                      qdiff(n, cm, d3);
@@ -295,7 +325,7 @@ __global__ void __launch_bounds__(NT)
                }
             }
             normi = eval_grad_normi(g2, p.grad_floor_type, p.floor2, p.max_normi);
-            if (A.write_lag && owner) A.lagN[a][gface] = normi;
+            if (wr) A.lagN[a][gface] = normi;
          }
          const double phia = average_func(phi_m, phi_c, p.avg_func);
          const double tempa = p.with_T ? 0.5 * (s_T[cm] + s_T[c]) : 0.5 * (Tuni + Tuni);
@@ -315,24 +345,43 @@ __global__ void __launch_bounds__(NT)
                            p.dinv[t];
          const double dphidx = (a == 0) ? dn : dt;
          const double dphidy = (a == 0) ? dt : dn;
-         double theta;
-         if (fabs(dphidx) > (double)1.e-12f)
-            theta = atan(dphidy / dphidx);
-         else
-            theta = 0.5 * 3.141592653589793;  // 4.d0*atan(1.d0)
          double qa = 0.5 * (s_q[cm] + s_q[c]);
          if (qa > 1.0) qa = 1.0;
          if (qa < -1.0) qa = -1.0;
-         const double ang = (Q == 4) ? 2.0 * acos(qa) : acos(qa);
-         const double arg = p.knumber * (theta - ang);
          double sn, cs;
-         sincos(arg, &sn, &cs);
+         if (p.knumber == 4 && !p.libm_trig) {
+            // cos/sin of 4(theta - psi) without atan/acos/sincos: theta = atan(y/x) enters only
+            // through cos 4theta = 1 - 8 x^2 y^2 / r^4, sin 4theta = 4 x y (x^2 - y^2) / r^4, and
+            // psi = acos(q) through the Chebyshev polynomials cos 4psi = T4(q),
+            // sin 4psi = sqrt((1-q)(1+q)) U3(q).  Absolute error ~1e-16, the same as the libm
+            // evaluation of the reference's expression (DESIGN.md "Transcendentals").
+            double c4t = 1.0, s4t = 0.0;  // theta = pi/2 branch
+            if (fabs(dphidx) > (double)1.e-12f) {
+               const double x2 = dphidx * dphidx, y2 = dphidy * dphidy;
+               const double r2 = x2 + y2;
+               const double inv = 1.0 / (r2 * r2);
+               c4t = 1.0 - 8.0 * x2 * y2 * inv;
+               s4t = 4.0 * dphidx * dphidy * (x2 - y2) * inv;
+            }
+            const double q2 = qa * qa;
+            double c4p = 8.0 * q2 * (q2 - 1.0) + 1.0;
+            double s4p = sqrt((1.0 - qa) * (1.0 + qa)) * (4.0 * qa * (2.0 * q2 - 1.0));
+            if (Q == 4) {  // psi = 2 acos(q): one more angle doubling
+               const double c8 = 2.0 * c4p * c4p - 1.0;
+               s4p = 2.0 * s4p * c4p;
+               c4p = c8;
+            }
+            cs = c4t * c4p + s4t * s4p;
+            sn = s4t * c4p - c4t * s4p;
+         } else {
+            aniso_trig_libm(dphidx, dphidy, qa, p.knumber, Q, &sn, &cs);
+         }
          const double epstheta = p.epsilon_phase * (1.0 + p.nu * cs);
          const double depsdtheta = -p.knumber * p.epsilon_phase * p.nu * sn;
          s_pf[f] = (a == 0) ? (epstheta * epstheta * dphidx - epstheta * depsdtheta * dphidy)
                             : (epstheta * epstheta * dphidy + epstheta * depsdtheta * dphidx);
       }
-      if (p.flux_type == AMPE_FLUX_ISOTROPIC && ND == 2) {
+      if (ND == 2 && p.flux_type == AMPE_FLUX_ISOTROPIC) {
          // compute_flux_isotropic, 2d/quatrhs.m4:106-151
          const int t = 1 - a;
          s_pf[f] = p.iso_dinv[a] * ((s_phi[c - soff[t]] - s_phi[cm - soff[t]]) +
@@ -341,7 +390,7 @@ __global__ void __launch_bounds__(NT)
       }
 
       // ---- composition flux ----
-      if (CONC == AMPE_CONC_EBS) {
+      if constexpr (CONC == AMPE_CONC_EBS) {
          double Dl, Da;
          if (A.use_lag) {
             Dl = inrange ? A.lagD0[a][gface] : 0.0;
@@ -356,7 +405,7 @@ __global__ void __launch_bounds__(NT)
             const double hphi = interp_func(phia, p.diffusion_interp);
             Dl = (1. - hphi) * dl;
             Da = hphi * da;
-            if (A.write_lag && owner) {
+            if (wr) {
                A.lagD0[a][gface] = Dl;
                A.lagD1[a][gface] = Da;
             }
@@ -365,7 +414,7 @@ __global__ void __launch_bounds__(NT)
          double fl = p.dinv[a] * (Dl * (s_cl[c] - s_cl[cm]));
          fl = fl + p.dinv[a] * (Da * (s_ca[c] - s_ca[cm]));
          s_cf[f] = fl;
-      } else if (CONC == AMPE_CONC_KKS) {
+      } else if constexpr (CONC == AMPE_CONC_KKS) {
          double D0, Dp;
          if (A.use_lag) {
             D0 = inrange ? A.lagD0[a][gface] : 0.0;
@@ -382,7 +431,7 @@ __global__ void __launch_bounds__(NT)
             const double hp = deriv_interp_func(average_func(phi_c, phi_m, p.conc_avg_func),
                                                 p.energy_interp);
             Dp = D0 * hp * (c_l - c_a);
-            if (A.write_lag && owner) {
+            if (wr) {
                A.lagD0[a][gface] = D0;
                A.lagD1[a][gface] = Dp;
             }
@@ -390,23 +439,53 @@ __global__ void __launch_bounds__(NT)
          // concentrationflux (2d/concentrationrhs.m4:52-76)
          s_cf[f] = p.dinv[a] * (D0 * (s_c[c] - s_c[cm]) + Dp * (phi_c - phi_m));
       }
+   };
+
+   const bool need_faces = (Q > 0 && p.evolve_quat) || p.flux_type != AMPE_FLUX_SIMPLE || CONC != 0;
+   if (need_faces) {
+      // lower faces of the owned cells
+#pragma unroll 1
+      for (int u = 0; u < CPT; u++) {
+         const int r = warp + u * RP;
+         const int lj = r % TY, lk = r / TY;
+#pragma unroll 1
+         for (int a = 0; a < ND; a++) face(a, lane, lj, lk, true);
+      }
+      // upper boundary faces of the tile; they belong to the neighbouring tile except on the
+      // extra plane ns of the slab axis, which this tile refreshes in the lagged arrays
+#pragma unroll 1
+      for (int e = threadIdx.x; e < G::NE; e += NT) {
+         int a, li, lj, lk;
+         if (e < G::E0) {
+            a = 0, li = TX, lj = e % TY, lk = e / TY;
+         } else if (e < G::E0 + G::E1) {
+            const int g = e - G::E0;
+            a = 1, li = g % TX, lj = TY, lk = g / TX;
+         } else {
+            const int g = e - G::E0 - G::E1;
+            a = 2, li = g % TX, lj = g / TX, lk = TZ;
+         }
+         const bool top = (a == ND - 1) && (((ND == 2) ? oy + lj : oz + lk) == ns);
+         face(a, li, lj, lk, top);
+      }
    }
    __syncthreads();
 
    // ---- (C) cells -----------------------------------------------------------------
-   for (int t = threadIdx.x; t < G::NC; t += NT) {
-      const int li = t % TX, lj = (t / TX) % TY, lk = t / (TX * TY);
+#pragma unroll 1
+   for (int u = 0; u < CPT; u++) {
+      const int r = warp + u * RP;
+      const int li = lane, lj = r % TY, lk = r / TY;
       const int gi = ox + li, gj = oy + lj, gk = oz + lk;
       if (gi >= n0 || gj >= n1 || gk >= n2) continue;
       if (ND == 2 && gj >= A.s_end) continue;
       if (ND == 3 && gk >= A.s_end) continue;
       const long long gcell = gi + (long long)n0 * (gj + (long long)n1 * gk);
       const int c = G::sidx(li, lj, lk);
-      // local face indices: lower / upper face per direction
-      const int fxl = li + (TX + 1) * (lj + TY * lk), fxu = fxl + 1;
-      const int fyl = G::F0 + li + TX * (lj + (TY + 1) * lk), fyu = fyl + TX;
-      const int fzl = G::F0 + G::F1 + li + TX * (lj + TY * lk), fzu = fzl + TX * TY;
-      const int flo[3] = {fxl, fyl, fzl}, fup[3] = {fxu, fyu, fzu};
+      const int fb = G::fidx(li, lj, lk);
+      // lower / upper face per direction in the face box
+      const int flo[3] = {fb, NFB + fb, 2 * NFB + fb};
+      const int fup[3] = {fb + foff[0], NFB + fb + foff[1], 2 * NFB + fb + foff[2]};
       const double phi = s_phi[c];
       const double temp = p.with_T ? s_T[c] : Tuni;
 
@@ -426,9 +505,9 @@ __global__ void __launch_bounds__(NT)
                                         (phi - s_phi[c - soff[2]]) * p.eps2_dinv[2]) *
                                            p.dinv[2];
          } else {
-            diff_term = (s_pf[fxu] - s_pf[fxl]) * p.dinv[0];
-            diff_term = diff_term + (s_pf[fyu] - s_pf[fyl]) * p.dinv[1];
-            if (ND == 3) diff_term = diff_term + (s_pf[fzu] - s_pf[fzl]) * p.dinv[2];
+            diff_term = (s_pf[fup[0]] - s_pf[flo[0]]) * p.dinv[0];
+            diff_term = diff_term + (s_pf[fup[1]] - s_pf[flo[1]]) * p.dinv[1];
+            if (ND == 3) diff_term = diff_term + (s_pf[fup[2]] - s_pf[flo[2]]) * p.dinv[2];
          }
          double rhs = diff_term;
          rhs = rhs - p.phi_well_scale * deriv_well_func(phi, 'd');
@@ -436,14 +515,14 @@ __global__ void __launch_bounds__(NT)
             // gradient modulus (quatgrad_cell[_symm] + quatgrad_modulus, or from sides compact)
             double s = 0.0;
             if (p.modulus_from_cells) {
-               double gc[ND][Q > 0 ? Q : 1];
+               double gc[ND][QN];
 #pragma unroll
                for (int a = 0; a < ND; a++) {
-                  double dl[Q], du[Q];
+                  double dl[QN], du[QN];
                   qdiff(a, c, dl);
                   qdiff(a, c + soff[a], du);
                   if (SYMM && Q > 1) {
-                     double dup[Q];
+                     double dup[QN];
                      symm_rotate<Q>(du, -s_iq[a * S + c + soff[a]], dup, s_qr, s_conj);
 #pragma unroll
                      for (int m = 0; m < Q; m++) gc[a][m] = (dup[m] + dl[m]) * p.p5inv[a];
@@ -461,7 +540,7 @@ __global__ void __launch_bounds__(NT)
             } else {
 #pragma unroll
                for (int a = 0; a < ND; a++) {
-                  double dl[Q], du[Q];
+                  double dl[QN], du[QN];
                   qdiff(a, c, dl);
                   qdiff(a, c + soff[a], du);
 #pragma unroll
@@ -486,7 +565,7 @@ __global__ void __launch_bounds__(NT)
             // computerhsbiaswell (2d/quatrhs.m4:834-843)
             const double m = p.bias_coeff * atan(p.bias_gamma * (p.meltingT - temp));
             rhs = rhs + m * phi * (1.0 - phi);
-         } else if (p.free_energy == AMPE_FE_CALPHAD) {
+         } else if (CONC == AMPE_CONC_EBS && p.free_energy == AMPE_FE_CALPHAD) {
             // CALPHADFreeEnergyStrategyBinary.cc:321-323, 638-663
             const double c_l = s_cl[c], c_a = s_ca[c];
             double f_l = calphad_f(p.ct, c_l, 0);
@@ -497,7 +576,7 @@ __global__ void __launch_bounds__(NT)
             mu *= p.inv_vm_a;
             const double hp = deriv_interp_func(phi, p.energy_interp);
             rhs += hp * ((f_l - f_a) - mu * (c_l - c_a));
-         } else if (p.free_energy == AMPE_FE_QUADRATIC) {
+         } else if (CONC == AMPE_CONC_KKS && p.free_energy == AMPE_FE_QUADRATIC) {
             // QuadraticFreeEnergyStrategy.cc:242-243, 512-530
             const double c_l = s_cl[c], c_a = s_ca[c];
             double f_l = p.quad_A[0] * (c_l - p.quad_ceq[0]) * (c_l - p.quad_ceq[0]);
@@ -514,8 +593,8 @@ __global__ void __launch_bounds__(NT)
 
       if constexpr (Q > 0) if (p.evolve_quat) {
          // compute_flux_from_gradq + compute_lambda_flux + add_quat_proj_op
-         double divm[Q], qc[Q];
-         double dlo[ND][Q > 0 ? Q : 1], dup_[ND][Q > 0 ? Q : 1];
+         double divm[QN], qc[QN];
+         double dlo[ND][QN], dup_[ND][QN];
 #pragma unroll
          for (int a = 0; a < ND; a++) {
             qdiff(a, c, dlo[a]);
@@ -540,7 +619,7 @@ __global__ void __launch_bounds__(NT)
          lam = lam / sumq2;
          const double mob = quat_mobility(phi, p.quat_mobility_func, p.quat_mobility,
                                           p.min_quat_mobility, p.quat_mobility_alt);
-         double rq[Q];
+         double rq[QN];
 #pragma unroll
          for (int m = 0; m < Q; m++) {
             if (Q != 1)
@@ -550,8 +629,8 @@ __global__ void __launch_bounds__(NT)
          }
          if (SYMM) {
             // correctrhsquatforsymmetry (2d/...m4:73-140): dlo/dup_ are the symmetric diffs
-            double tmp[Q];
-            double dpr[ND][Q > 0 ? Q : 1];
+            double tmp[QN];
+            double dpr[ND][QN];
 #pragma unroll
             for (int a = 0; a < ND; a++) {
                if (Q > 1)
@@ -592,8 +671,8 @@ __global__ void __launch_bounds__(NT)
 
       if (CONC != 0) {
          // computerhsconcentration (3d/concentrationrhs.m4:412-458)
-         double s = p.dinv[0] * (s_cf[fxu] - s_cf[fxl]) + p.dinv[1] * (s_cf[fyu] - s_cf[fyl]);
-         if (ND == 3) s = s + p.dinv[2] * (s_cf[fzu] - s_cf[fzl]);
+         double s = p.dinv[0] * (s_cf[fup[0]] - s_cf[flo[0]]) + p.dinv[1] * (s_cf[fup[1]] - s_cf[flo[1]]);
+         if (ND == 3) s = s + p.dinv[2] * (s_cf[fup[2]] - s_cf[flo[2]]);
          A.out_c[gcell] = p.conc_mobility * s;
       }
 

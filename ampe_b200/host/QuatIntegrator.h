@@ -1,0 +1,349 @@
+// Host-side mirror of QuatIntegrator's RHS methods (reference: source/QuatIntegrator.cc
+// RegisterVariables 787-985, fillScratch 2873-2955, computeQuatGradients 2782-2827,
+// setCoefficients 2994-3083, evaluateRHSFunction 3134-3295) on one uniform periodic level.
+//
+//   use_fused = true  : evaluateRHSFunction -> ampe_rhs_eval (the fused sm_100a path)
+//   use_fused = false : the reference's own sequence of Strategy calls, each one a piecewise
+//                       CUDA kernel on SAMRAI-layout PatchData (drop-in check of every Strategy)
+#pragma once
+#include "ampe_host.h"
+
+namespace ampe_host {
+
+class QuatIntegrator
+{
+ public:
+   QuatIntegrator(const ampe_rhs_config& cfg, bool use_fused) : d_cfg(cfg), d_use_fused(use_fused)
+   {
+      Box box;
+      box.ndim = cfg.ndim;
+      for (int d = 0; d < cfg.ndim; d++) box.upper[d] = cfg.n[d] - 1;
+      d_hierarchy.reset(new PatchHierarchy);
+      d_hierarchy->level.reset(new PatchLevel);
+      d_patch.reset(new Patch(box, cfg.dx));
+      d_hierarchy->level->patches.push_back(d_patch);
+      d_ncell = 1;
+      for (int d = 0; d < cfg.ndim; d++) d_ncell *= (size_t)cfg.n[d];
+      check(ampe_rhs_create(&d_cfg, &d_ctx), "ampe_rhs_create");
+      RegisterVariables();
+      buildStrategies();
+   }
+   ~QuatIntegrator() { ampe_rhs_destroy(d_ctx); }
+
+   // QuatModel::resetRefPhaseConcentrations (QuatModel.cc:5218-5231); ghost-0 device arrays
+   void resetRefPhaseConcentrations(const double* cl_ref, const double* ca_ref)
+   {
+      check(ampe_rhs_set_ref_concentrations(d_ctx, cl_ref, ca_ref, nullptr), "set_ref");
+      if (d_conc_l_ref_id < 0) return;
+      const Box& b = d_patch->getBox();
+      if (cl_ref && ca_ref) {
+         check(ampe_k_fill_periodic(b.ndim, b.lower, b.upper, 1, cl_ref,
+                                    d_patch->cell<double>(d_conc_l_ref_id)->getPointer(), d_ng, nullptr),
+               "fill ref");
+         check(ampe_k_fill_periodic(b.ndim, b.lower, b.upper, 1, ca_ref,
+                                    d_patch->cell<double>(d_conc_a_ref_id)->getPointer(), d_ng, nullptr),
+               "fill ref");
+      } else {
+         auto cl = d_patch->cell<double>(d_conc_l_id), ca = d_patch->cell<double>(d_conc_a_id);
+         cudaMemcpy(d_patch->cell<double>(d_conc_l_ref_id)->getPointer(), cl->getPointer(),
+                    cl->size() * sizeof(double), cudaMemcpyDeviceToDevice);
+         cudaMemcpy(d_patch->cell<double>(d_conc_a_ref_id)->getPointer(), ca->getPointer(),
+                    ca->size() * sizeof(double), cudaMemcpyDeviceToDevice);
+      }
+   }
+   // quat_symm_rotation: one int per lower face per direction, ghost-0 device arrays
+   void setSymmetryRotations(const int* const* iqrot)
+   {
+      check(ampe_rhs_set_symmetry_rotations(d_ctx, iqrot, nullptr), "set_rotations");
+      const Box& b = d_patch->getBox();
+      auto rot = d_patch->side<int>(d_quat_symm_rotation_id);
+      for (int a = 0; a < b.ndim; a++)
+         check(ampe_k_fill_periodic_int(b.ndim, b.lower, b.upper, a, iqrot[a], rot->getPointer(a), 1,
+                                        nullptr),
+               "fill rotations");
+   }
+
+   // QuatIntegrator::evaluateRHSFunction(time, y, y_dot, fd_flag); y / y_dot: ghost-0 device arrays
+   int evaluateRHSFunction(double time, const ampe_rhs_fields* y, const ampe_rhs_fields* y_dot,
+                           int fd_flag)
+   {
+      if (d_use_fused) {
+         check(ampe_rhs_eval(d_ctx, time, y, y_dot, fd_flag, nullptr), "ampe_rhs_eval");
+         return 0;
+      }
+      const ampe_rhs_config& p = d_cfg;
+      const bool recompute_quat_sidegrad = (fd_flag == 0) || !p.lag_quat_sidegrad;  // :3189
+      setCoefficients(time, y, recompute_quat_sidegrad);
+      const Box& b = d_patch->getBox();
+      if (p.with_phase) {
+         d_phase_rhs_strategy->evaluateRHS(time, d_hierarchy, d_ydot_phase_id, fd_flag == 0);
+         copyOut(d_ydot_phase_id, y_dot->phase, 1);
+      }
+      if (p.evolve_quat) {
+         // evaluateQuatRHS (:2691-2780): the literal `true` = use_gradq_for_flux
+         d_quat_sys_solver->evaluateRHS(d_phase_scratch_id, d_temperature_scratch_id,
+                                        d_quat_grad_side_id, d_quat_grad_side_copy_id, -1,
+                                        d_quat_mobility_id, d_quat_scratch_id, d_ydot_quat_id, true);
+         if (p.symmetry_aware) correctRhsForSymmetry();
+         copyOut(d_ydot_quat_id, y_dot->quat, p.qlen);
+      }
+      if (p.with_concentration) {
+         if (recompute_quat_sidegrad) d_composition_rhs_strategy->setDiffusionCoeff(d_hierarchy, time);
+         d_composition_rhs_strategy->computeFluxOnPatch(*d_patch, d_flux_conc_id);
+         auto flux = d_patch->side<double>(d_flux_conc_id);
+         auto f = flux->pointers(0);
+         auto rhs = d_patch->cell<double>(d_ydot_conc_id);
+         check(ampe_k_computerhsconcentration(b.ndim, b.lower, b.upper, d_patch->getDx(), f.data(),
+                                              flux->getGhostCellWidth(), p.conc_mobility,
+                                              rhs->getPointer(), 0, nullptr),
+               "COMPUTERHSCONCENTRATION");
+         copyOut(d_ydot_conc_id, y_dot->conc, 1);
+      }
+      if (p.with_unsteady_temperature) {
+         d_temperature_rhs_strategy->evaluateRHS(d_hierarchy, d_ydot_temperature_id,
+                                                 p.with_phase ? d_ydot_phase_id : -1);
+         copyOut(d_ydot_temperature_id, y_dot->temperature, 1);
+      }
+      cuda_check(cudaDeviceSynchronize(), "evaluateRHSFunction");
+      return 0;  // Always successful (QuatIntegrator.cc:3294)
+   }
+
+   std::shared_ptr<Patch> patch() const { return d_patch; }
+   ampe_rhs_ctx* fusedContext() const { return d_ctx; }
+   int concLId() const { return d_conc_l_id; }
+   int concAId() const { return d_conc_a_id; }
+   int nghosts() const { return d_ng; }
+
+ private:
+   template <typename T>
+   int cellVar(int depth, int ghosts)
+   {
+      return d_patch->registerPatchData(std::make_shared<CellData<T>>(d_patch->getBox(), depth, ghosts));
+   }
+   template <typename T>
+   int sideVar(int depth, int ghosts)
+   {
+      return d_patch->registerPatchData(std::make_shared<SideData<T>>(d_patch->getBox(), depth, ghosts));
+   }
+
+   // ghost widths as registered by the reference (SURVEY.md 8b "Array layout")
+   void RegisterVariables()
+   {
+      const ampe_rhs_config& p = d_cfg;
+      const int Q = p.qlen, D = p.ndim;
+      d_ng = (p.conc_rhs_form == AMPE_CONC_CAHN_HILLIARD) ? 2 : 1;  // nghosts_required()
+      d_temperature_scratch_id = cellVar<double>(1, d_ng);
+      if (p.with_phase) {
+         d_phase_scratch_id = cellVar<double>(1, d_ng);
+         d_phase_mobility_id = cellVar<double>(1, 1);
+         d_flux_id = sideVar<double>(1, 0);
+         d_ydot_phase_id = cellVar<double>(1, 0);
+      }
+      if (Q > 0) d_quat_scratch_id = cellVar<double>(Q, d_ng);
+      if (p.evolve_quat) {
+         d_quat_diffs_id = sideVar<double>(p.symmetry_aware ? 2 * Q : Q, 1);
+         d_quat_grad_cell_id = cellVar<double>(D * Q, 0);
+         d_quat_grad_side_id = sideVar<double>(D * Q, 0);
+         d_quat_grad_side_copy_id = sideVar<double>(D * Q, 0);
+         d_quat_grad_modulus_id = cellVar<double>(1, 0);
+         d_quat_mobility_id = cellVar<double>(1, 1);
+         d_face_coef_id = sideVar<double>(1, 0);
+         d_quat_flux_id = sideVar<double>(Q, 0);
+         d_lambda_id = cellVar<double>(1, 0);
+         d_ydot_quat_id = cellVar<double>(Q, 0);
+         if (p.symmetry_aware) d_quat_symm_rotation_id = sideVar<int>(1, 1);
+      }
+      if (p.with_concentration) {
+         d_conc_scratch_id = cellVar<double>(1, d_ng);
+         d_flux_conc_id = sideVar<double>(1, p.conc_rhs_form == AMPE_CONC_CAHN_HILLIARD ? 1 : 0);
+         d_ydot_conc_id = cellVar<double>(1, 0);
+         if (p.conc_rhs_form == AMPE_CONC_KKS || p.conc_rhs_form == AMPE_CONC_EBS) {
+            d_conc_l_id = cellVar<double>(1, d_ng);
+            d_conc_a_id = cellVar<double>(1, d_ng);
+            d_conc_l_ref_id = cellVar<double>(1, d_ng);
+            d_conc_a_ref_id = cellVar<double>(1, d_ng);
+            d_f_l_id = cellVar<double>(1, 0);
+            d_f_a_id = cellVar<double>(1, 0);
+            d_diff0_id = sideVar<double>(1, 0);  // EBS: D_l  | KKS: D0
+            d_diff1_id = sideVar<double>(1, 0);  // EBS: D_a  | KKS: D_phi
+         }
+      }
+      if (p.with_unsteady_temperature) {
+         d_cp_id = cellVar<double>(1, 0);
+         d_ydot_temperature_id = cellVar<double>(1, 0);
+         fillConstant(d_cp_id, p.cp);
+      }
+      if (p.free_energy == AMPE_FE_BIASWELL) {
+         d_eq_temperature_id = cellVar<double>(1, 0);
+         fillConstant(d_eq_temperature_id, p.meltingT);  // ConstantMeltingTemperatureStrategy
+      }
+   }
+
+   void buildStrategies()
+   {
+      const ampe_rhs_config& p = d_cfg;
+      if (p.with_phase) {
+         // PhaseFluxStrategyFactory.h:11-36
+         if (p.phase_flux_type == AMPE_FLUX_ANISOTROPIC)
+            d_phase_flux_strategy.reset(
+                new PhaseFluxStrategyAnisotropy(p.epsilon_phase, p.epsilon_anisotropy, p.knumber));
+         else if (p.phase_flux_type == AMPE_FLUX_ISOTROPIC)
+            d_phase_flux_strategy.reset(new PhaseFluxStrategyIsotropic(p.epsilon_phase));
+         else
+            d_phase_flux_strategy.reset(new PhaseFluxStrategySimple(p.epsilon_phase));
+         // FreeEnergyStrategyFactory.h:37-263
+         if (p.free_energy == AMPE_FE_BIASWELL)
+            d_free_energy_strategy.reset(new BiasDoubleWellUTRCFreeEnergyStrategy(
+                p.bias_well_alpha, p.bias_well_gamma, d_eq_temperature_id));
+         else if (p.free_energy == AMPE_FE_CALPHAD || p.free_energy == AMPE_FE_QUADRATIC)
+            d_free_energy_strategy.reset(new KKSFreeEnergyStrategy(p, d_conc_l_id, d_conc_a_id));
+         d_phase_rhs_strategy.reset(new PhaseRHSStrategyWithQ(
+             p, d_phase_scratch_id, d_conc_scratch_id, d_quat_scratch_id, d_temperature_scratch_id,
+             d_f_l_id, d_f_a_id, d_phase_mobility_id, d_flux_id, d_quat_grad_modulus_id,
+             d_phase_flux_strategy, d_free_energy_strategy));
+      }
+      d_mobility_strategy.reset(new QuatMobilityStrategy(p));
+      if (p.evolve_quat) {
+         d_quat_grad_strategy.reset(
+             new QuatGradStrategy(p.qlen, p.symmetry_aware != 0, d_quat_symm_rotation_id));
+         d_quat_face_coeff.reset(new QuatFaceCoeff(p));
+         d_quat_sys_solver.reset(new QuatSysSolver(p, d_hierarchy, d_quat_face_coeff, d_face_coef_id,
+                                                   d_quat_flux_id, d_lambda_id));
+      }
+      if (p.with_concentration) {
+         // CompositionRHSStrategyFactory.h:27-102
+         if (p.conc_rhs_form == AMPE_CONC_CAHN_HILLIARD)
+            d_composition_rhs_strategy.reset(new CahnHilliardDoubleWell(p, d_conc_scratch_id));
+         else if (p.conc_rhs_form == AMPE_CONC_EBS)
+            d_composition_rhs_strategy.reset(new EBSCompositionRHSStrategy(
+                p, d_phase_scratch_id, d_conc_l_id, d_conc_a_id, d_diff0_id, d_diff1_id));
+         else
+            d_composition_rhs_strategy.reset(new KKSCompositionRHSStrategy(
+                p, d_conc_scratch_id, d_phase_scratch_id, d_temperature_scratch_id, d_conc_l_id,
+                d_conc_a_id, d_diff0_id, d_diff1_id));
+         if (p.conc_rhs_form == AMPE_CONC_KKS || p.conc_rhs_form == AMPE_CONC_EBS)
+            d_phase_conc_strategy.reset(new PhaseConcentrationsStrategy(
+                p, d_conc_l_id, d_conc_a_id, d_conc_l_ref_id, d_conc_a_ref_id));
+      }
+      if (p.with_unsteady_temperature)
+         d_temperature_rhs_strategy.reset(new TemperatureRHSStrategy(
+             d_temperature_scratch_id, d_cp_id, p.thermal_diffusivity, p.latent_heat));
+   }
+
+   void fillConstant(int id, double v)
+   {
+      auto c = d_patch->cell<double>(id);
+      std::vector<double> h(c->size(), v);
+      cuda_check(cudaMemcpy(c->getPointer(), h.data(), h.size() * sizeof(double),
+                            cudaMemcpyHostToDevice),
+                 "fillConstant");
+   }
+   // fillScratch (:2873-2955): y -> scratch, ghosts = periodic images
+   void fillScratchField(const double* src, int id, int depth)
+   {
+      const Box& b = d_patch->getBox();
+      auto c = d_patch->cell<double>(id);
+      check(ampe_k_fill_periodic(b.ndim, b.lower, b.upper, depth, src, c->getPointer(),
+                                 c->getGhostCellWidth(), nullptr),
+            "fillScratch");
+   }
+   void copyOut(int id, double* dst, int depth)
+   {
+      auto c = d_patch->cell<double>(id);
+      cuda_check(cudaMemcpy(dst, c->getPointer(), d_ncell * depth * sizeof(double),
+                            cudaMemcpyDeviceToDevice),
+                 "copyOut");
+   }
+
+   // setCoefficients (:2994-3083)
+   void setCoefficients(double time, const ampe_rhs_fields* y, bool recompute_quat_sidegrad)
+   {
+      (void)time;
+      const ampe_rhs_config& p = d_cfg;
+      if (!p.with_unsteady_temperature) fillConstant(d_temperature_scratch_id, p.T_uniform);
+      if (p.with_phase) fillScratchField(y->phase, d_phase_scratch_id, 1);
+      if (p.qlen > 0) fillScratchField(y->quat, d_quat_scratch_id, p.qlen);
+      if (p.with_concentration) fillScratchField(y->conc, d_conc_scratch_id, 1);
+      if (p.with_unsteady_temperature) fillScratchField(y->temperature, d_temperature_scratch_id, 1);
+      if (p.evolve_quat) computeQuatGradients(recompute_quat_sidegrad);
+      if (d_phase_conc_strategy) {
+         int nfail = d_phase_conc_strategy->computePhaseConcentrations(
+             d_hierarchy, d_temperature_scratch_id, d_phase_scratch_id, -1, d_conc_scratch_id);
+         if (nfail > 0) throw std::runtime_error("computePhaseConcentrations: Newton failed");
+      }
+      // computeMobilities (:2959-2990)
+      if (p.with_phase)
+         d_mobility_strategy->computePhaseMobility(d_hierarchy, d_phase_scratch_id, d_phase_mobility_id);
+      if (p.evolve_quat)
+         d_mobility_strategy->computeQuatMobility(d_hierarchy, d_phase_scratch_id, d_quat_mobility_id);
+   }
+   // computeQuatGradients (:2782-2827)
+   void computeQuatGradients(bool recompute_quat_sidegrad)
+   {
+      d_quat_grad_strategy->computeDiffs(d_hierarchy, d_quat_scratch_id, d_quat_diffs_id);
+      d_quat_grad_strategy->computeGradCell(d_hierarchy, d_quat_diffs_id, d_quat_grad_cell_id);
+      d_quat_grad_strategy->computeGradSide(d_hierarchy, d_quat_diffs_id, d_quat_grad_side_id);
+      if (recompute_quat_sidegrad)
+         d_patch->side<double>(d_quat_grad_side_copy_id)->copy(*d_patch->side<double>(d_quat_grad_side_id));
+      if (d_cfg.quat_grad_modulus_from_cells)
+         d_quat_grad_strategy->computeGradModulus(d_hierarchy, d_quat_grad_cell_id,
+                                                  d_quat_grad_modulus_id);
+      else
+         d_quat_grad_strategy->computeGradModulusFromSides(d_hierarchy, d_quat_grad_side_id,
+                                                           d_quat_grad_modulus_id);
+   }
+   // correctRhsForSymmetry (:3967-4073)
+   void correctRhsForSymmetry()
+   {
+      const Box& b = d_patch->getBox();
+      const int Q = d_cfg.qlen;
+      auto diffs = d_patch->side<double>(d_quat_diffs_id);
+      auto nonsymm = diffs->pointers(Q), symm = diffs->pointers(0);
+      auto rhs = d_patch->cell<double>(d_ydot_quat_id), q = d_patch->cell<double>(d_quat_scratch_id);
+      auto fc = d_patch->side<double>(d_quat_sys_solver->getFaceDiffCoeffScratchId());
+      auto f = fc->pointers(0);
+      auto mob = d_patch->cell<double>(d_quat_mobility_id);
+      auto rot = d_patch->side<int>(d_quat_symm_rotation_id);
+      auto iq = rot->pointers();
+      std::vector<const int*> ciq(iq.begin(), iq.end());
+      check(ampe_k_correctrhsquatforsymmetry(b.ndim, b.lower, b.upper, Q, d_patch->getDx(),
+                                             nonsymm.data(), symm.data(), diffs->getGhostCellWidth(),
+                                             rhs->getPointer(), rhs->getGhostCellWidth(),
+                                             q->getPointer(), q->getGhostCellWidth(), f.data(),
+                                             fc->getGhostCellWidth(), mob->getPointer(),
+                                             mob->getGhostCellWidth(), ciq.data(),
+                                             rot->getGhostCellWidth(), nullptr),
+            "CORRECTRHSQUATFORSYMMETRY");
+   }
+
+   ampe_rhs_config d_cfg;
+   bool d_use_fused;
+   ampe_rhs_ctx* d_ctx = nullptr;
+   std::shared_ptr<PatchHierarchy> d_hierarchy;
+   std::shared_ptr<Patch> d_patch;
+   size_t d_ncell;
+   int d_ng = 1;
+   // PatchData ids, named like the reference's members
+   int d_phase_scratch_id = -1, d_quat_scratch_id = -1, d_conc_scratch_id = -1,
+       d_temperature_scratch_id = -1;
+   int d_phase_mobility_id = -1, d_quat_mobility_id = -1, d_flux_id = -1, d_flux_conc_id = -1;
+   int d_quat_diffs_id = -1, d_quat_grad_cell_id = -1, d_quat_grad_side_id = -1,
+       d_quat_grad_side_copy_id = -1, d_quat_grad_modulus_id = -1, d_quat_symm_rotation_id = -1;
+   int d_face_coef_id = -1, d_quat_flux_id = -1, d_lambda_id = -1;
+   int d_conc_l_id = -1, d_conc_a_id = -1, d_conc_l_ref_id = -1, d_conc_a_ref_id = -1;
+   int d_f_l_id = -1, d_f_a_id = -1, d_diff0_id = -1, d_diff1_id = -1;
+   int d_cp_id = -1, d_eq_temperature_id = -1;
+   int d_ydot_phase_id = -1, d_ydot_quat_id = -1, d_ydot_conc_id = -1, d_ydot_temperature_id = -1;
+   std::shared_ptr<PhaseFluxStrategy> d_phase_flux_strategy;
+   std::shared_ptr<FreeEnergyStrategy> d_free_energy_strategy;
+   std::shared_ptr<PhaseRHSStrategyWithQ> d_phase_rhs_strategy;
+   std::shared_ptr<QuatMobilityStrategy> d_mobility_strategy;
+   std::shared_ptr<QuatGradStrategy> d_quat_grad_strategy;
+   std::shared_ptr<QuatFaceCoeff> d_quat_face_coeff;
+   std::shared_ptr<QuatSysSolver> d_quat_sys_solver;
+   std::shared_ptr<CompositionRHSStrategy> d_composition_rhs_strategy;
+   std::shared_ptr<PhaseConcentrationsStrategy> d_phase_conc_strategy;
+   std::shared_ptr<TemperatureRHSStrategy> d_temperature_rhs_strategy;
+};
+
+}  // namespace ampe_host

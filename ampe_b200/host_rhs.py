@@ -1,0 +1,72 @@
+"""ctypes access to the C++ host-side Strategy mirror (ampe_b200/host/*.h,
+libampe_b200_host.so): QuatIntegrator::evaluateRHSFunction either through the fused
+path or through the reference's own sequence of Strategy calls (piecewise kernels)."""
+import ctypes as C
+import os
+
+import torch
+
+from . import _abi
+from .lib import AmpeError, load
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "libampe_b200_host.so")
+_lib = None
+
+
+def load_host():
+    global _lib
+    if _lib is None:
+        load()  # libampe_b200.so first (dependency, resolved through rpath $ORIGIN)
+        if not os.path.exists(_PATH):
+            raise AmpeError("libampe_b200_host.so is not built (run __graft_entry__.build())")
+        L = C.CDLL(_PATH)
+        vp = C.c_void_p
+        L.ampe_host_create.restype = vp
+        L.ampe_host_create.argtypes = [C.POINTER(_abi.RhsConfig), C.c_int]
+        L.ampe_host_destroy.argtypes = [vp]
+        L.ampe_host_last_error.restype = C.c_char_p
+        L.ampe_host_reset_ref_phase_concentrations.restype = C.c_int
+        L.ampe_host_reset_ref_phase_concentrations.argtypes = [vp, vp, vp]
+        L.ampe_host_set_symmetry_rotations.restype = C.c_int
+        L.ampe_host_set_symmetry_rotations.argtypes = [vp, C.POINTER(vp)]
+        L.ampe_host_evaluate_rhs_function.restype = C.c_int
+        L.ampe_host_evaluate_rhs_function.argtypes = [vp, C.c_double, C.POINTER(_abi.RhsFields),
+                                                      C.POINTER(_abi.RhsFields), C.c_int]
+        _lib = L
+    return _lib
+
+
+class HostQuatIntegrator:
+    def __init__(self, cfg, use_fused):
+        self.L = load_host()
+        self.h = self.L.ampe_host_create(C.byref(cfg), 1 if use_fused else 0)
+        if not self.h:
+            raise AmpeError(self.L.ampe_host_last_error().decode())
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise AmpeError(self.L.ampe_host_last_error().decode())
+
+    def resetRefPhaseConcentrations(self, cl=None, ca=None):
+        self._chk(self.L.ampe_host_reset_ref_phase_concentrations(
+            self.h, None if cl is None else cl.data_ptr(), None if ca is None else ca.data_ptr()))
+
+    def setSymmetryRotations(self, iqrot):
+        self._iq = [t.to(torch.int32).contiguous() for t in iqrot]
+        arr = (C.c_void_p * 3)()
+        for d, t in enumerate(self._iq):
+            arr[d] = t.data_ptr()
+        self._chk(self.L.ampe_host_set_symmetry_rotations(self.h, arr))
+
+    def evaluateRHSFunction(self, time, y, y_dot, fd_flag=0):
+        fy, fd = y.fields(), y_dot.fields()
+        self._chk(self.L.ampe_host_evaluate_rhs_function(self.h, float(time), C.byref(fy), C.byref(fd),
+                                                         int(fd_flag)))
+        torch.cuda.synchronize()
+        return 0
+
+    def close(self):
+        if self.h:
+            self.L.ampe_host_destroy(self.h)
+            self.h = None

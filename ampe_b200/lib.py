@@ -8,7 +8,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libampe_b200.so")
+LIB_PATH = os.environ.get("AMPE_B200_LIB", os.path.join(_HERE, "libampe_b200.so"))
 
 _lib = None
 

@@ -56,49 +56,53 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region"""
+    """SM clock and throttle reasons DURING the timed region (NVML polled every 2 ms in a
+    thread; the nvidia-smi CLI is too slow for millisecond regions)."""
 
     def __init__(self, gpu_index):
-        self.samples, self.reasons, self.proc = [], set(), None
-        self.gpu = gpu_index
+        self.samples, self.reasons = [], set()
+        self.gpu, self.run, self.t, self.h = gpu_index, False, None, None
+        self.max_mhz = None
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
         except Exception:
-            self.proc = None
+            self.h = None
+            return
+        self.run = True
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.proc.stdout:
-            f = [x.strip() for x in line.split(",")]
+    def _poll(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+                "hw_thermal_slowdown": 0x40}
+        while self.run:
             try:
-                self.samples.append((float(f[0]), float(f[1])))
-                for n, v in zip(names, f[2:6]):
-                    if v.lower().startswith("active"):
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = get_reasons(self.h)
+                for n, b in bits.items():
+                    if r & b:
                         self.reasons.add(n)
             except Exception:
                 pass
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm = sorted(s[0] for s in self.samples)
-        return {"sm_mhz": (sm[len(sm) // 2] if sm else None),
-                "sm_max_mhz": (max(s[1] for s in self.samples) if self.samples else None),
-                "reasons": sorted(self.reasons)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
+        self.run = False
+        self.t.join(timeout=1)
+        sm = sorted(self.samples)
+        return {"sm_mhz": (sm[len(sm) // 2] if sm else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 def cpu_reference(workload, steps, warmup, budget_s=25.0):
