@@ -71,8 +71,11 @@ AMPE_DEV double calphad_d2f(const CalphadT& t, double c, int pi)
 
 // KKS: (1-h) c_l + h c_a = c0,  mu_l(c_l) = mu_a(c_a)  (scaled by 1/RT), Cramer update,
 // stop when both |F_i| < tol.  Returns iteration count, -1 if not converged.
+// lg[0..3] = log(c_l), log(1-c_l), log(c_a), log(1-c_a) of the final iterate (entries whose
+// argument is <= 1e-8 are not set): the driving force below reuses them, so that the
+// free-energy evaluation costs no further transcendental.
 AMPE_DEV int kks_newton(const CalphadT& t, double c0, double hphi, double& cl, double& ca,
-                        double tol, int max_its, double alpha)
+                        double tol, int max_its, double alpha, double* lg)
 {
    c0 = c0 >= 0. ? c0 : 0.;
    c0 = c0 <= 1. ? c0 : 1.;
@@ -81,9 +84,14 @@ AMPE_DEV int kks_newton(const CalphadT& t, double c0, double hphi, double& cl, d
       const double xi0 = t.RTinv * (t.fA[0] - t.fB[0] + fmix_deriv(t.L[0], cl));
       const double xi1 = t.RTinv * (t.fA[1] - t.fB[1] + fmix_deriv(t.L[1], ca));
       const double f0 = -c0 + (1.0 - hphi) * cl + hphi * ca;
-      const double f1 = xlogx_deriv(cl, AMPE_LOG_SMALLX) - xlogx_deriv(1. - cl, AMPE_LOG_SMALLX) -
-                        xlogx_deriv(ca, AMPE_LOG_SMALLX) + xlogx_deriv(1. - ca, AMPE_LOG_SMALLX) +
-                        (xi0 - xi1);
+      // xlogx_deriv(x) = log(x) + 1 above the 1e-8 extension
+      const double a0 = cl, a1 = 1. - cl, a2 = ca, a3 = 1. - ca;
+      double d0, d1, d2, d3;
+      if (a0 > AMPE_SMALLX) { lg[0] = log(a0); d0 = lg[0] + 1.0; } else d0 = xlogx_deriv(a0, AMPE_LOG_SMALLX);
+      if (a1 > AMPE_SMALLX) { lg[1] = log(a1); d1 = lg[1] + 1.0; } else d1 = xlogx_deriv(a1, AMPE_LOG_SMALLX);
+      if (a2 > AMPE_SMALLX) { lg[2] = log(a2); d2 = lg[2] + 1.0; } else d2 = xlogx_deriv(a2, AMPE_LOG_SMALLX);
+      if (a3 > AMPE_SMALLX) { lg[3] = log(a3); d3 = lg[3] + 1.0; } else d3 = xlogx_deriv(a3, AMPE_LOG_SMALLX);
+      const double f1 = d0 - d1 - d2 + d3 + (xi0 - xi1);
       if (fabs(f0) < tol && fabs(f1) < tol) return it;
       if (it == max_its) return -1;
       const double dxi0 = t.RTinv * fmix_deriv2(t.L[0], cl);
@@ -99,6 +107,28 @@ AMPE_DEV int kks_newton(const CalphadT& t, double c0, double hphi, double& cl, d
       ca = ca - alpha * (Dinv * D1);
       it++;
    }
+}
+
+// (f_l - f_a) - mu (c_l - c_a) with f_i = f(c_i) 1e-6/V_m, mu = df_a/dc(c_a) 1e-6/V_m
+// (CALPHADFreeEnergyStrategyBinary.cc:321-323 computeFreeEnergy, 638-663 addDrivingForce),
+// same expression order as calphad_f / calphad_mu, logs taken from the Newton residual
+AMPE_DEV double calphad_driving_force(const CalphadT& t, double cl, double ca, const double* lg,
+                                      double inv_vm_l, double inv_vm_a)
+{
+   const double a0 = cl, a1 = 1.0 - cl, a2 = ca, a3 = 1.0 - ca;
+   const double x0 = (a0 > AMPE_SMALLX) ? a0 * lg[0] : xlogx(a0, AMPE_LOG_SMALLX);
+   const double x1 = (a1 > AMPE_SMALLX) ? a1 * lg[1] : xlogx(a1, AMPE_LOG_SMALLX);
+   const double x2 = (a2 > AMPE_SMALLX) ? a2 * lg[2] : xlogx(a2, AMPE_LOG_SMALLX);
+   const double x3 = (a3 > AMPE_SMALLX) ? a3 * lg[3] : xlogx(a3, AMPE_LOG_SMALLX);
+   const double d2 = (a2 > AMPE_SMALLX) ? lg[2] + 1.0 : xlogx_deriv(a2, AMPE_LOG_SMALLX);
+   const double d3 = (a3 > AMPE_SMALLX) ? lg[3] + 1.0 : xlogx_deriv(a3, AMPE_LOG_SMALLX);
+   double f_l = cl * t.fA[0] + (1.0 - cl) * t.fB[0] + fmix(t.L[0], cl) + t.RT * (x0 + x1);
+   f_l *= inv_vm_l;
+   double f_a = ca * t.fA[1] + (1.0 - ca) * t.fB[1] + fmix(t.L[1], ca) + t.RT * (x2 + x3);
+   f_a *= inv_vm_a;
+   double mu = (t.fA[1] - t.fB[1]) + fmix_deriv(t.L[1], ca) + t.RT * (d2 - d3);
+   mu *= inv_vm_a;
+   return (f_l - f_a) - mu * (cl - ca);
 }
 
 // computeDiffusionMobilityBinaryPhase (CALPHADMobility.cc:200-219) with

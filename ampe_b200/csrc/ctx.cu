@@ -40,6 +40,7 @@ struct ampe_rhs_ctx {
    long long ncell;
    int ng;
    double *cl = nullptr, *ca = nullptr, *cl_ref = nullptr, *ca_ref = nullptr;  // slab-ghosted
+   double* df = nullptr;  // ghost-0 CALPHAD driving force (written by the KKS kernel)
    int* iq[3] = {nullptr, nullptr, nullptr};
    double* lagN[3] = {nullptr, nullptr, nullptr};
    double* lagD0[3] = {nullptr, nullptr, nullptr};
@@ -51,6 +52,7 @@ struct ampe_rhs_ctx {
    bool have_halo = false;
    bool have_ref = false;
    bool lag_valid = false;
+   bool generic_only = false;  // AMPE_B200_GENERIC at create time
    int launches = 0;
    // staging buffers for ampe_rhs_eval_host
    ampe_rhs_fields dev_y, dev_ydot;
@@ -232,16 +234,20 @@ static int upload_qr_table(ampe_rhs_ctx* c)
    return AMPE_OK;
 }
 
-// ---- kernel dispatch (instantiations live in fused_inst_*.cu) ------------------------------
+// ---- kernel dispatch (instantiations live in fused3_*.cu) ----------------------------------
 namespace ampe {
 template <int ND, int Q>
-int dispatch_conc(const FusedArgs& A, cudaStream_t st, const char** err);
-extern template int dispatch_conc<2, 0>(const FusedArgs&, cudaStream_t, const char**);
-extern template int dispatch_conc<2, 2>(const FusedArgs&, cudaStream_t, const char**);
-extern template int dispatch_conc<2, 4>(const FusedArgs&, cudaStream_t, const char**);
-extern template int dispatch_conc<3, 0>(const FusedArgs&, cudaStream_t, const char**);
-extern template int dispatch_conc<3, 2>(const FusedArgs&, cudaStream_t, const char**);
-extern template int dispatch_conc<3, 4>(const FusedArgs&, cudaStream_t, const char**);
+int dispatch3_runtime(const FusedArgs& A, cudaStream_t st, const char** err);
+extern template int dispatch3_runtime<2, 0>(const FusedArgs&, cudaStream_t, const char**);
+extern template int dispatch3_runtime<2, 2>(const FusedArgs&, cudaStream_t, const char**);
+extern template int dispatch3_runtime<2, 4>(const FusedArgs&, cudaStream_t, const char**);
+extern template int dispatch3_runtime<3, 0>(const FusedArgs&, cudaStream_t, const char**);
+extern template int dispatch3_runtime<3, 2>(const FusedArgs&, cudaStream_t, const char**);
+extern template int dispatch3_runtime<3, 4>(const FusedArgs&, cudaStream_t, const char**);
+// compile-time selector sets of the shipped decks; return 1 when they handled the launch
+int dispatch3_fixed_dendrite(const FusedArgs& A, cudaStream_t st, const char** err, int* rc);
+int dispatch3_fixed_auni2d(const FusedArgs& A, cudaStream_t st, const char** err, int* rc);
+int dispatch3_fixed_3d(const FusedArgs& A, cudaStream_t st, const char** err, int* rc);
 }  // namespace ampe
 
 template <int ND>
@@ -249,11 +255,22 @@ static int dispatch_q(const FusedArgs& A, cudaStream_t st)
 {
    const char* err = nullptr;
    int rc = AMPE_EINVAL;
-   switch (A.p.qlen) {
-      case 0: rc = dispatch_conc<ND, 0>(A, st, &err); break;
-      case 2: rc = dispatch_conc<ND, 2>(A, st, &err); break;
-      case 4: rc = dispatch_conc<ND, 4>(A, st, &err); break;
-      default: err = "unsupported qlen";
+   // AMPE_B200_GENERIC=1 forces the runtime-selector instantiation (tests compare both)
+   const bool generic_only = A.force_generic != 0;
+   bool done = false;
+   if (!generic_only) {
+      if (ND == 2)
+         done = dispatch3_fixed_dendrite(A, st, &err, &rc) || dispatch3_fixed_auni2d(A, st, &err, &rc);
+      else
+         done = dispatch3_fixed_3d(A, st, &err, &rc);
+   }
+   if (!done) {
+      switch (A.p.qlen) {
+         case 0: rc = dispatch3_runtime<ND, 0>(A, st, &err); break;
+         case 2: rc = dispatch3_runtime<ND, 2>(A, st, &err); break;
+         case 4: rc = dispatch3_runtime<ND, 4>(A, st, &err); break;
+         default: err = "unsupported qlen";
+      }
    }
    if (rc) return set_err(rc, err ? err : "kernel launch failed");
    return AMPE_OK;
@@ -270,6 +287,7 @@ extern "C" int ampe_rhs_create(const ampe_rhs_config* cfg, ampe_rhs_ctx** out)
       return set_err(AMPE_ENOGPU, "no CUDA device: libampe_b200 has no CPU fallback");
    ampe_rhs_ctx* c = new ampe_rhs_ctx;
    c->cfg = *cfg;
+   c->generic_only = getenv("AMPE_B200_GENERIC") != nullptr;
    int rc = ampe_derive_params(*cfg, c->p);
    if (rc) {
       delete c;
@@ -293,6 +311,7 @@ extern "C" int ampe_rhs_create(const ampe_rhs_config* cfg, ampe_rhs_ctx** out)
       CUDA_OK(cudaMalloc(&c->ca_ref, gb));
       CUDA_OK(cudaMalloc(&c->nfail, sizeof(int)));
       CUDA_OK(cudaMemset(c->nfail, 0, sizeof(int)));
+      if (p.free_energy == AMPE_FE_CALPHAD) CUDA_OK(cudaMalloc(&c->df, (size_t)c->ncell * sizeof(double)));
    }
    const size_t lagb = (size_t)c->plane * (c->ns + 1) * sizeof(double);
    if (cfg->lag_quat_sidegrad) {
@@ -323,6 +342,7 @@ extern "C" int ampe_rhs_destroy(ampe_rhs_ctx* c)
    cudaFree(c->cl_ref);
    cudaFree(c->ca_ref);
    cudaFree(c->nfail);
+   cudaFree(c->df);
    cudaFree(c->qr_dev);
    cudaFree(c->conj_dev);
    for (int d = 0; d < 3; d++) {
@@ -517,6 +537,7 @@ static int eval_part(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
       K.ca_ref = c->ca_ref;
       K.cl = c->cl;
       K.ca = c->ca;
+      K.df = c->df;
       K.nfail = c->nfail;
       int ranges[2][2];
       int nr = 0;
@@ -562,6 +583,9 @@ static int eval_part(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
    A.out_q = ydot->quat;
    A.out_c = ydot->conc;
    A.out_T = ydot->temperature;
+   A.force_generic = c->generic_only ? 1 : 0;
+   A.wrap_slab = c->have_halo ? 0 : 1;
+   A.df = c->df;
    A.use_lag = use_lag ? 1 : 0;
    A.write_lag = (recompute && c->cfg.lag_quat_sidegrad) ? 1 : 0;
    int ranges[2][2];

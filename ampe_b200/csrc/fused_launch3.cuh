@@ -1,0 +1,106 @@
+// Launch + template dispatch of the generation-3 fused kernel.  Included only by the
+// fused3_*.cu translation units (one per (NDIM, qlen, selector policy) so that the
+// instantiations compile in parallel); ctx.cu sees the dispatch3_* prototypes.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rhs_v3.cuh"
+
+namespace ampe {
+
+// tile shape and block size (swept on B200, profiles/README.md)
+#ifndef AMPE_T2Y
+#define AMPE_T2Y 16
+#define AMPE_NT2 256
+#endif
+#ifndef AMPE_T3Y
+#define AMPE_T3Y 4
+#define AMPE_T3Z 4
+#define AMPE_NT3 512
+#endif
+
+template <int ND, int Q, int CONC, bool SYMM, bool WT, class SEL>
+static int launch3(const FusedArgs& A, cudaStream_t st, const char** err)
+{
+   constexpr int TX = 32;
+   constexpr int TY = (ND == 2) ? AMPE_T2Y : AMPE_T3Y;
+   constexpr int TZ = (ND == 2) ? 1 : AMPE_T3Z;
+   constexpr int NT = (ND == 2) ? AMPE_NT2 : AMPE_NT3;
+   using TT = Tile3<ND, Q, CONC, SYMM, WT, SEL, TX, TY, TZ, NT>;
+   const Params& p = A.p;
+   auto kern = rhs_fused3_kernel<TT>;
+   static bool configured = false;
+   if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TT::SMEM_BYTES);
+      if (e != cudaSuccess) {
+         *err = cudaGetErrorString(e);
+         return AMPE_ECUDA;
+      }
+      configured = true;
+   }
+   const int nslab = A.s_end - A.s_begin;
+   if (nslab <= 0) return AMPE_OK;
+   dim3 grid;
+   grid.x = (p.n[0] + TX - 1) / TX;
+   if (ND == 2) {
+      grid.y = (nslab + TY - 1) / TY;
+      grid.z = 1;
+   } else {
+      grid.y = (p.n[1] + TY - 1) / TY;
+      grid.z = (nslab + TZ - 1) / TZ;
+   }
+   kern<<<grid, NT, TT::SMEM_BYTES, st>>>(A);
+   cudaError_t e2 = cudaGetLastError();
+   if (e2 != cudaSuccess) {
+      *err = cudaGetErrorString(e2);
+      return AMPE_ECUDA;
+   }
+   return AMPE_OK;
+}
+
+// does the parameter record select exactly the compile-time model SEL?
+template <class SEL>
+static bool sel_matches(const Params& p)
+{
+   return p.with_phase == SEL::with_phase && p.evolve_quat == SEL::evolve_quat &&
+          p.flux_type == SEL::flux_type && p.free_energy == SEL::free_energy &&
+          p.modulus_from_cells == SEL::modulus_from_cells && p.knumber == SEL::knumber &&
+          p.libm_trig == SEL::libm_trig && p.energy_interp == SEL::energy_interp &&
+          p.diffusion_interp == SEL::diffusion_interp && p.orient_interp1 == SEL::orient_interp1 &&
+          p.orient_interp2 == SEL::orient_interp2 && p.avg_func == SEL::avg_func &&
+          p.conc_avg_func == SEL::conc_avg_func && p.grad_floor_type == SEL::grad_floor_type &&
+          p.quat_mobility_func == SEL::quat_mobility_func;
+}
+
+// runtime-selector instantiations of one (NDIM, qlen): every composition form, symmetry for qlen 4
+template <int ND, int Q>
+int dispatch3_runtime(const FusedArgs& A, cudaStream_t st, const char** err)
+{
+   const Params& p = A.p;
+   const bool symm = p.symm;
+   if (symm && Q != 4) {
+      *err = "symmetry needs qlen=4 in this build";
+      return AMPE_EINVAL;
+   }
+   constexpr bool S4 = (Q == 4);
+   switch (p.conc_form) {
+      case 0:
+      case AMPE_CONC_CAHN_HILLIARD:
+         if (p.with_T) {
+            if (symm) return launch3<ND, Q, 0, S4, true, SelRuntime>(A, st, err);
+            return launch3<ND, Q, 0, false, true, SelRuntime>(A, st, err);
+         }
+         if (symm) return launch3<ND, Q, 0, S4, false, SelRuntime>(A, st, err);
+         return launch3<ND, Q, 0, false, false, SelRuntime>(A, st, err);
+      case AMPE_CONC_KKS:
+         if (symm) return launch3<ND, Q, AMPE_CONC_KKS, S4, false, SelRuntime>(A, st, err);
+         return launch3<ND, Q, AMPE_CONC_KKS, false, false, SelRuntime>(A, st, err);
+      case AMPE_CONC_EBS:
+         if (symm) return launch3<ND, Q, AMPE_CONC_EBS, S4, false, SelRuntime>(A, st, err);
+         return launch3<ND, Q, AMPE_CONC_EBS, false, false, SelRuntime>(A, st, err);
+   }
+   *err = "unknown conc_rhs_form";
+   return AMPE_EINVAL;
+}
+
+}  // namespace ampe

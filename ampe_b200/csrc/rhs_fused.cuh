@@ -59,6 +59,9 @@ struct FusedArgs {
    int use_lag;    // fd_flag != 0 && lag_quat_sidegrad
    int write_lag;  // refresh the lagged data
    int s_begin, s_end;  // slab-axis range of cells to compute [begin, end)
+   int force_generic;   // host side only: use the runtime-selector instantiation
+   int wrap_slab;       // 1: no halo buffers, ghost planes = opposite interior planes (one rank)
+   const double* df;    // CALPHAD driving force (f_l-f_a)-mu(c_l-c_a) per cell from the KKS kernel
 };
 
 template <int Q>
@@ -705,6 +708,7 @@ struct KksArgs {
    const double* ca_ref;
    double* cl;            // slab-ghosted outputs
    double* ca;
+   double* df;            // ghost-0: CALPHAD driving force per interior cell (may be null)
    int* nfail;
    int s_begin, s_end;    // slab index range incl. ghosts: [-1, ns+1)
 };
@@ -738,9 +742,13 @@ __global__ void __launch_bounds__(256) kks_kernel(const __grid_constant__ KksArg
       if (p.free_energy == AMPE_FE_CALPHAD) {
          x0 = A.cl_ref[og];
          x1 = A.ca_ref[og];
+         double lg[4];
          const int st = kks_newton(p.ct, conc, hphi, x0, x1, p.newton_tol, p.newton_max_its,
-                                   p.newton_alpha);
+                                   p.newton_alpha, lg);
          if (st < 0) atomicAdd(A.nfail, 1);
+         if (A.df && sl >= 0 && sl < ns)
+            A.df[(long long)sl * plane + inplane] =
+                calphad_driving_force(p.ct, x0, x1, lg, p.inv_vm_l, p.inv_vm_a);
       } else {
          const double h = clamp01(hphi);
          x0 = (conc - h * (p.quad_ceq[1] - p.quad_rla * p.quad_ceq[0])) /
