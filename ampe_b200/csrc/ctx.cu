@@ -169,6 +169,7 @@ int ampe_derive_params(const ampe_rhs_config& c, Params& p)
    p.thermal_diffusivity = c.thermal_diffusivity;
    p.latent_heat = c.latent_heat;
    p.cp = c.cp;
+   p.latent_over_cp = c.latent_heat / c.cp;
    p.meltingT = c.meltingT;
    // computerhsbiaswell: pi = 4.*atan(1.) is REAL*4 (2d/quatrhs.m4:834)
    p.bias_coeff = c.bias_well_alpha / (double)(4.f * atanf(1.f));

@@ -49,6 +49,7 @@ struct Params {
    double quat_mobility, min_quat_mobility, quat_mobility_alt;
    double T_uniform;
    double thermal_diffusivity, latent_heat, cp, meltingT;
+   double latent_over_cp;          // latent_heat/cp   computerhstemp
    double bias_coeff, bias_gamma;  // alpha/pi_f32, gamma   computerhsbiaswell
    double conc_mobility;
    double ch_ca, ch_cb, ch_well_scale, ch_kappa;

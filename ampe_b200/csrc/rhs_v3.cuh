@@ -100,6 +100,17 @@ AMPE_DEV double interp3(double phi, char type)
    return interp_func(phi, type);
 }
 
+// quatmobility 'p' (3d/mobility.m4:42-92) with explicit fma
+AMPE_DEV double quat_mobility3(double phi, char func, double scale, double minm, double alt)
+{
+   if (func == 'p' || func == 'P') {
+      const double t = clamp01(phi);
+      const double qfunc = 1.0 - t * t * t * fma(t, fma(6.0, t, -15.0), 10.0);
+      return fma(scale - minm, qfunc, minm);
+   }
+   return quat_mobility_rare(phi, func, scale, minm, alt);
+}
+
 // CALPHAD face diffusivity of one phase at face-averaged concentration c0:
 //   D = [c0 c1 (c0 M1 + c1 M0) 1e12] * d2f/dc2,  d2f = fmix'' + RT (1/c0 + 1/c1)
 // (computeDiffusionMobilityBinaryPhase, CALPHADMobility.cc:200-219, times
@@ -477,8 +488,11 @@ struct Rhs3 {
                sm = sqrt_fast(0.5 * sm);
             }
             const double p1p = deriv_interp_func(phi, AMPE_SEL(orient_interp1));
-            const double p2p = deriv_interp_func(phi, AMPE_SEL(orient_interp2));
-            rhs = rhs - p.misorientation_factor * temp * p1p * sm - p2p * p.epsilonq2_half * sm * sm;
+            rhs = rhs - p.misorientation_factor * temp * p1p * sm;
+            if (AMPE_SEL(orient_interp2) != 'c') {  // p2 constant: its derivative term vanishes
+               const double p2p = deriv_interp_func(phi, AMPE_SEL(orient_interp2));
+               rhs = rhs - p2p * p.epsilonq2_half * sm * sm;
+            }
          }
          // addDrivingForce
          if (free_energy == AMPE_FE_BIASWELL) {
@@ -514,31 +528,35 @@ struct Rhs3 {
             fcl[a] = fc[a * NFB + fb];
             fcu[a] = fc[a * NFB + fb + TT::ftr(a)];
          }
+         // div(fc grad q) per component in the reference's operation order: the projection
+         // below (and the symmetry correction) cancel most of it, so parity needs its exact
+         // rounding.  compute_lambda_flux sums the same face differences scaled by 0.5/h, which
+         // is exactly half of 1/h: lambda = -(q.div)/(2|q|^2) bit for bit, and
+         // 2 q lambda = -q (q.div)/|q|^2 needs no second accumulation.
          double divm[QN], qc[QN];
-         double lam = 0.0, sumq2 = 0.0;
+         double qdiv = 0.0, sumq2 = 0.0;
 #pragma unroll
          for (int m = 0; m < Q; m++) {
             qc[m] = sq[m * S + c];
-            double dv = 0.0, lv = 0.0;
+            double dv = 0.0;
 #pragma unroll
             for (int a = 0; a < ND; a++) {
                const double fu = fcu[a] * (p.dinv[a] * dup[a][m]);
                const double fl = fcl[a] * (p.dinv[a] * dlo[a][m]);
                dv = (a == 0) ? (fu - fl) * p.dinv[a] : dv + (fu - fl) * p.dinv[a];
-               lv = (a == 0) ? (fu - fl) * p.p5inv[a] : lv + (fu - fl) * p.p5inv[a];
             }
             divm[m] = dv;
-            lam = lam - qc[m] * lv;
+            qdiv = qdiv + qc[m] * dv;
             sumq2 = sumq2 + qc[m] * qc[m];
          }
-         lam = lam * rcp_fast(sumq2);
+         const double lamq = qdiv / sumq2;
          const double mob = quat_mobility(phi, AMPE_SEL(quat_mobility_func), p.quat_mobility,
                                           p.min_quat_mobility, p.quat_mobility_alt);
          double rq[QN];
 #pragma unroll
          for (int m = 0; m < Q; m++) {
             if (Q != 1)
-               rq[m] = 0.0 - mob * (divm[m] + 2.0 * qc[m] * lam);
+               rq[m] = 0.0 - mob * (divm[m] - qc[m] * lamq);
             else
                rq[m] = 0.0 - mob * divm[m];
          }
@@ -604,8 +622,7 @@ struct Rhs3 {
          }
          double r = p.thermal_diffusivity * dterm;
          if (AMPE_SEL(with_phase)) {
-            const double gamma = p.latent_heat / p.cp;
-            r = r + gamma * phase_rhs;
+            r = fma(p.latent_over_cp, phase_rhs, r);
          }
          A.out_T[gcell] = r;
       }

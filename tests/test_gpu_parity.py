@@ -140,8 +140,10 @@ def test_fd_flag_lagging_semantics_gpu():
     torch.cuda.synchronize()
     for k in ("phase", "quat", "conc"):
         tol = TOL_CALPHAD_CONC if k == "conc" else TOL
-        assert parity.rel_err(lag[k].cpu().numpy(), o_lag[k]) <= tol, k
-        assert parity.rel_err(full[k].cpu().numpy(), o_full[k]) <= tol, k
+        e_lag = parity.rel_err(lag[k].cpu().numpy(), o_lag[k])
+        e_full = parity.rel_err(full[k].cpu().numpy(), o_full[k])
+        assert e_lag <= tol, (k, "lagged", e_lag)
+        assert e_full <= tol, (k, "full", e_full)
     assert not np.array_equal(o_lag["quat"], o_full["quat"])
     assert not torch.equal(lag["quat"], full["quat"])
     assert not torch.equal(lag["conc"], full["conc"])
