@@ -11,7 +11,7 @@
 #include <cstring>
 #include <string>
 
-#include "rhs_fused.cuh"
+#include "rhs_common.cuh"
 
 using namespace ampe;
 

@@ -7,11 +7,11 @@ int dispatch3_fixed_3d(const FusedArgs& A, cudaStream_t st, const char** err, in
    const Params& p = A.p;
    if (p.ndim != 3 || p.qlen != 4 || p.with_T || p.symm) return 0;
    if (p.conc_form == AMPE_CONC_EBS && sel_matches<SelAuNi>(p)) {
-      *rc = launch3<3, 4, AMPE_CONC_EBS, false, false, SelAuNi>(A, st, err);
+      *rc = launch_any<3, 4, AMPE_CONC_EBS, false, false, SelAuNi>(A, st, err);
       return 1;
    }
    if (p.conc_form == AMPE_CONC_KKS && sel_matches<SelHBSM>(p)) {
-      *rc = launch3<3, 4, AMPE_CONC_KKS, false, false, SelHBSM>(A, st, err);
+      *rc = launch_any<3, 4, AMPE_CONC_KKS, false, false, SelHBSM>(A, st, err);
       return 1;
    }
    return 0;

@@ -4,7 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#include "rhs_v3.cuh"
+#include "rhs_march.cuh"
+#include "rhs_tile.cuh"
 
 namespace ampe {
 
@@ -28,7 +29,7 @@ static int launch3(const FusedArgs& A, cudaStream_t st, const char** err)
    constexpr int NT = (ND == 2) ? AMPE_NT2 : AMPE_NT3;
    using TT = Tile3<ND, Q, CONC, SYMM, WT, SEL, TX, TY, TZ, NT>;
    const Params& p = A.p;
-   auto kern = rhs_fused3_kernel<TT>;
+   auto kern = rhs_tile_kernel<TT>;
    static bool configured = false;
    if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TT::SMEM_BYTES);
@@ -58,18 +59,46 @@ static int launch3(const FusedArgs& A, cudaStream_t st, const char** err)
    return AMPE_OK;
 }
 
-// does the parameter record select exactly the compile-time model SEL?
-template <class SEL>
-static bool sel_matches(const Params& p)
+// 3D plane-marching kernel (no quaternion symmetry): column 32 x TY, NZ planes per block
+#ifndef AMPE_MY
+#define AMPE_MY 8
+#define AMPE_MZ 16
+#endif
+template <int Q, int CONC, bool WT, class SEL>
+static int launch_march(const FusedArgs& A, cudaStream_t st, const char** err)
 {
-   return p.with_phase == SEL::with_phase && p.evolve_quat == SEL::evolve_quat &&
-          p.flux_type == SEL::flux_type && p.free_energy == SEL::free_energy &&
-          p.modulus_from_cells == SEL::modulus_from_cells && p.knumber == SEL::knumber &&
-          p.libm_trig == SEL::libm_trig && p.energy_interp == SEL::energy_interp &&
-          p.diffusion_interp == SEL::diffusion_interp && p.orient_interp1 == SEL::orient_interp1 &&
-          p.orient_interp2 == SEL::orient_interp2 && p.avg_func == SEL::avg_func &&
-          p.conc_avg_func == SEL::conc_avg_func && p.grad_floor_type == SEL::grad_floor_type &&
-          p.quat_mobility_func == SEL::quat_mobility_func;
+   using TT = March3<Q, CONC, WT, SEL, AMPE_MY, AMPE_MZ>;
+   const Params& p = A.p;
+   auto kern = rhs_march_kernel<TT>;
+   static bool configured = false;
+   if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TT::SMEM_BYTES);
+      if (e != cudaSuccess) {
+         *err = cudaGetErrorString(e);
+         return AMPE_ECUDA;
+      }
+      configured = true;
+   }
+   const int nslab = A.s_end - A.s_begin;
+   if (nslab <= 0) return AMPE_OK;
+   dim3 grid((p.n[0] + TT::TX - 1) / TT::TX, (p.n[1] + TT::TY - 1) / TT::TY, (nslab + TT::NZ - 1) / TT::NZ);
+   kern<<<grid, TT::NT, TT::SMEM_BYTES, st>>>(A);
+   cudaError_t e2 = cudaGetLastError();
+   if (e2 != cudaSuccess) {
+      *err = cudaGetErrorString(e2);
+      return AMPE_ECUDA;
+   }
+   return AMPE_OK;
+}
+
+// launch of one (NDIM, qlen, CONC, SYMM, WT, SEL): 3D without symmetry marches, the rest tiles
+template <int ND, int Q, int CONC, bool SYMM, bool WT, class SEL>
+static int launch_any(const FusedArgs& A, cudaStream_t st, const char** err)
+{
+   if constexpr (ND == 3 && !SYMM)
+      return launch_march<Q, CONC, WT, SEL>(A, st, err);
+   else
+      return launch3<ND, Q, CONC, SYMM, WT, SEL>(A, st, err);
 }
 
 // runtime-selector instantiations of one (NDIM, qlen): every composition form, symmetry for qlen 4
@@ -87,17 +116,17 @@ int dispatch3_runtime(const FusedArgs& A, cudaStream_t st, const char** err)
       case 0:
       case AMPE_CONC_CAHN_HILLIARD:
          if (p.with_T) {
-            if (symm) return launch3<ND, Q, 0, S4, true, SelRuntime>(A, st, err);
-            return launch3<ND, Q, 0, false, true, SelRuntime>(A, st, err);
+            if (symm) return launch_any<ND, Q, 0, S4, true, SelRuntime>(A, st, err);
+            return launch_any<ND, Q, 0, false, true, SelRuntime>(A, st, err);
          }
-         if (symm) return launch3<ND, Q, 0, S4, false, SelRuntime>(A, st, err);
-         return launch3<ND, Q, 0, false, false, SelRuntime>(A, st, err);
+         if (symm) return launch_any<ND, Q, 0, S4, false, SelRuntime>(A, st, err);
+         return launch_any<ND, Q, 0, false, false, SelRuntime>(A, st, err);
       case AMPE_CONC_KKS:
-         if (symm) return launch3<ND, Q, AMPE_CONC_KKS, S4, false, SelRuntime>(A, st, err);
-         return launch3<ND, Q, AMPE_CONC_KKS, false, false, SelRuntime>(A, st, err);
+         if (symm) return launch_any<ND, Q, AMPE_CONC_KKS, S4, false, SelRuntime>(A, st, err);
+         return launch_any<ND, Q, AMPE_CONC_KKS, false, false, SelRuntime>(A, st, err);
       case AMPE_CONC_EBS:
-         if (symm) return launch3<ND, Q, AMPE_CONC_EBS, S4, false, SelRuntime>(A, st, err);
-         return launch3<ND, Q, AMPE_CONC_EBS, false, false, SelRuntime>(A, st, err);
+         if (symm) return launch_any<ND, Q, AMPE_CONC_EBS, S4, false, SelRuntime>(A, st, err);
+         return launch_any<ND, Q, AMPE_CONC_EBS, false, false, SelRuntime>(A, st, err);
    }
    *err = "unknown conc_rhs_form";
    return AMPE_EINVAL;

@@ -1,7 +1,7 @@
 // One CUDA kernel per Fortran routine / per-patch C++ loop of AMPE's RHS path, on
 // SAMRAI-layout device arrays with ghost widths (include/ampe_b200_kernels.h).  This is
 // the piecewise boundary: a Strategy class of the reference can be re-pointed at these
-// symbols one call at a time.  The hot path proper is the fused kernel (rhs_fused.cuh);
+// symbols one call at a time.  The hot path proper is the fused kernel (rhs_tile.cuh, rhs_march.cuh);
 // these kernels keep the reference's unfused pass structure (one thread per loop point,
 // intermediates in global memory) and the same operation order.
 #include <cuda_runtime.h>
