@@ -13,9 +13,15 @@ import torch.distributed as dist
 from .rhs import COMPONENTS, SolutionVector
 
 
+def slab_dim(ndim):
+    """the slab axis counted from the end: z of (..., nz, ny, nx) in 3D, y of (..., ny, nx) in 2D
+    (components may or may not carry a leading depth dimension)"""
+    return -3 if ndim == 3 else -2
+
+
 def slab_planes(t, ndim, sl):
-    """view of planes `sl` along the slab axis of a (depth, nz, ny, nx) tensor"""
-    return t[:, sl] if ndim == 3 else t[:, :, sl]
+    """view of planes `sl` along the slab axis of a (..., nz, ny, nx) tensor"""
+    return t[..., sl, :, :] if ndim == 3 else t[..., sl, :]
 
 
 class SlabHalo:
@@ -52,7 +58,7 @@ class SlabHalo:
                 continue
             s_low, s_high = self._send[k]
             s_low.copy_(slab_planes(t, self.ndim, slice(0, ng)))
-            s_high.copy_(slab_planes(t, self.ndim, slice(t.shape[1 if self.ndim == 3 else 2] - ng, None)))
+            s_high.copy_(slab_planes(t, self.ndim, slice(t.shape[slab_dim(self.ndim)] - ng, None)))
             ops.append(dist.P2POp(dist.isend, s_low, self.prev, self.group))
             ops.append(dist.P2POp(dist.isend, s_high, self.next, self.group))
             # order matters when prev == next (2 ranks): the peer's LOW planes are my HIGH ghosts
@@ -73,8 +79,7 @@ class SlabHalo:
         tmp.finish(tmp.start(y))
         if t.is_cuda:
             torch.cuda.current_stream().synchronize()
-        dim = 1 if self.ndim == 3 else 2
-        return torch.cat([tmp.lo["phase"], t, tmp.hi["phase"]], dim=dim).contiguous()
+        return torch.cat([tmp.lo["phase"], t, tmp.hi["phase"]], dim=slab_dim(self.ndim)).contiguous()
 
 
 class DistributedRHS:

@@ -256,3 +256,71 @@ def test_full_size_properties(name):
     for k, v in out.items():
         if v is not None:
             assert torch.equal(torch.roll(v, shifts[:cfg.ndim], dims), outs[k]), k
+
+
+@pytest.mark.parametrize("name", ["dendrite2d", "auni2d", "gg3d_hbsm", "auni3d", "pfhub1a"])
+def test_slab_decomposition_equals_single_rank(name):
+    """two slab 'ranks' on one GPU, ghost planes handed over through ampe_rhs_set_halo (what
+    halo.py receives from the neighbour over NCCL): the union of the two slab evaluations is
+    bit-identical to the single-rank evaluation of the whole periodic domain, for the full
+    launch and for the interior/boundary split used to overlap the exchange"""
+    from ampe_b200 import configs, rhs
+    from ampe_b200.halo import slab_dim, slab_planes
+    cfg, st = parity.make_case(name)
+    cfg.symmetry_aware = 0
+    ndim = cfg.ndim
+    y = rhs.to_device(st)
+    r = rhs.QuatIntegratorRHS(cfg)
+    kks = cfg.conc_rhs_form in (2, 3)
+    if kks:
+        c0 = y["conc"].reshape(-1).clone()
+        r.resetRefPhaseConcentrations(c0, c0.clone())
+    ref = y.like()
+    r.evaluateRHSFunction(0.0, y, ref, 0)
+    ref1 = y.like()
+    r.evaluateRHSFunction(0.0, y, ref1, 1)
+    torch.cuda.synchronize()
+    ns = cfg.n[ndim - 1]
+    half = ns // 2
+    ng = r.nghosts()
+    dim = slab_dim(ndim)
+    for rank in (0, 1):
+        lo_i, hi_i = rank * half, (rank + 1) * half if rank == 0 else ns
+        kw = dict(nx=cfg.n[0], ny=cfg.n[1])
+        if ndim == 3:
+            kw["nz"] = hi_i - lo_i
+        else:
+            kw["ny"] = hi_i - lo_i
+        c2 = configs.BUILDERS[name](**kw)
+        for d in range(3):
+            c2.dx[d] = cfg.dx[d]
+        c2.symmetry_aware = 0
+        c2.nranks, c2.rank = 2, rank
+        take = lambda t, idx: t.index_select(dim, torch.tensor([i % ns for i in idx], device=t.device)).contiguous()
+        ys = rhs.SolutionVector({k: (None if v is None else slab_planes(v, ndim, slice(lo_i, hi_i)).contiguous())
+                                 for k, v in y.items()})
+        lo = rhs.SolutionVector({k: (None if v is None else take(v, range(lo_i - ng, lo_i))) for k, v in y.items()})
+        hi = rhs.SolutionVector({k: (None if v is None else take(v, range(hi_i, hi_i + ng))) for k, v in y.items()})
+        r2 = rhs.QuatIntegratorRHS(c2)
+        r2.setHalo(lo, hi)
+        if kks:
+            g = take(y["conc"], range(lo_i - ng, hi_i + ng))
+            r2.setRefPhaseConcentrationsGhosted(g, g.clone())
+        for split in (False, True):
+            out = ys.like()
+            if split:
+                r2.evaluateRHSFunction(0.0, ys, out, 0, part=1)
+                r2.evaluateRHSFunction(0.0, ys, out, 0, part=2)
+            else:
+                r2.evaluateRHSFunction(0.0, ys, out, 0)
+            out1 = ys.like()
+            r2.evaluateRHSFunction(0.0, ys, out1, 1)
+            torch.cuda.synchronize()
+            assert r2.newtonFailures() == 0
+            for k, v in ref.items():
+                if v is None or (k == "quat" and not cfg.evolve_quat):
+                    continue
+                assert torch.equal(out[k], slab_planes(v, ndim, slice(lo_i, hi_i))), (name, rank, split, k)
+                assert torch.equal(out1[k], slab_planes(ref1[k], ndim, slice(lo_i, hi_i))), (name, rank, split, k, "fd1")
+        r2.close()
+    r.close()

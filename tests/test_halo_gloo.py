@@ -34,9 +34,10 @@ def _worker(rank, world, port, ndim, ng, q):
         g = torch.Generator().manual_seed(1234)
         glob = {"phase": torch.rand((1,) + gshape, generator=g, dtype=torch.float64),
                 "quat": torch.rand((4,) + gshape, generator=g, dtype=torch.float64),
-                "conc": None,
+                # a component WITHOUT the leading depth dimension, like fields.make_state's phase
+                "conc": torch.rand(gshape, generator=g, dtype=torch.float64),
                 "temperature": torch.rand((1,) + gshape, generator=g, dtype=torch.float64)}
-        dim = 1 if ndim == 3 else 2
+        dim = -3 if ndim == 3 else -2
         sl = slice(rank * nzl, (rank + 1) * nzl)
         y = SolutionVector({k: (None if v is None else slab_planes(v, ndim, sl).contiguous())
                             for k, v in glob.items()})

@@ -13,7 +13,7 @@ timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/b
 for w in dendrite2d auni3d; do
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$w.csv \
   python bench.py --workload $w --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launch_$w.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:fused -s 3 -c 2 -f -o gpurun_out/prof_$w \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:rhs_ -s 3 -c 2 -f -o gpurun_out/prof_$w \
   python bench.py --workload $w --steps 3 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_$w.log 2>&1
 done
 kill $SMI
