@@ -32,6 +32,8 @@ int ampe_set_err(int code, const std::string& msg)
 
 static const double R_GAS = 8.314472;  // GASCONSTANT_R_JPKPMOL
 
+#define AMPE_MAX_HOST_CHUNKS 32
+
 struct ampe_rhs_ctx {
    ampe_rhs_config cfg;
    Params p;
@@ -57,7 +59,8 @@ struct ampe_rhs_ctx {
    // staging buffers for ampe_rhs_eval_host
    ampe_rhs_fields dev_y, dev_ydot;
    bool have_dev = false;
-   cudaStream_t own_stream = nullptr;
+   cudaStream_t own_stream = nullptr, k_stream = nullptr, out_stream = nullptr;
+   cudaEvent_t ev_in[AMPE_MAX_HOST_CHUNKS], ev_k[AMPE_MAX_HOST_CHUNKS];
 };
 
 // ---- CALPHAD T-dependent coefficients on the host (uniform T) --------------------------
@@ -362,7 +365,15 @@ extern "C" int ampe_rhs_destroy(ampe_rhs_ctx* c)
       cudaFree(c->dev_ydot.conc);
       cudaFree(c->dev_ydot.temperature);
    }
-   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+   if (c->own_stream) {
+      cudaStreamDestroy(c->own_stream);
+      cudaStreamDestroy(c->k_stream);
+      cudaStreamDestroy(c->out_stream);
+      for (int j = 0; j < AMPE_MAX_HOST_CHUNKS; j++) {
+         cudaEventDestroy(c->ev_in[j]);
+         cudaEventDestroy(c->ev_k[j]);
+      }
+   }
    delete c;
    return AMPE_OK;
 }
@@ -466,11 +477,22 @@ static Field make_field(const ampe_rhs_ctx* c, const double* base, const double*
    return f;
 }
 
-// part: 0 = everything, 1 = interior (no ghost plane needed), 2 = boundary planes
-static int eval_part(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
-                     const ampe_rhs_fields* ydot, int fd_flag, cudaStream_t st, int part)
+// One evaluation restricted to slab-axis ranges: the KKS pre-pass runs on kks[r] (slab indices
+// incl. ghost planes, [-ng, ns+ng)), the fused / Cahn-Hilliard kernel on cells[r] ([0, ns)).
+// `first` resets the launch counter, `last` marks the lagged data valid.
+struct Ranges {
+   int n = 0;
+   int r[3][2];
+   void add(int b, int e)
+   {
+      if (e > b) r[n][0] = b, r[n++][1] = e;
+   }
+};
+
+static int eval_ranges(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs_fields* ydot,
+                       int fd_flag, cudaStream_t st, const Ranges& kks, const Ranges& cells,
+                       bool first, bool last)
 {
-   (void)time;
    if (!c || !y || !ydot) return set_err(AMPE_EINVAL, "null argument");
    const Params& p = c->p;
    if (p.with_phase && (!y->phase || !ydot->phase)) return set_err(AMPE_EINVAL, "phase missing");
@@ -479,9 +501,7 @@ static int eval_part(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
    if (p.with_conc && (!y->conc || !ydot->conc)) return set_err(AMPE_EINVAL, "conc missing");
    if (p.with_T && (!y->temperature || !ydot->temperature))
       return set_err(AMPE_EINVAL, "temperature missing");
-   const int ns = c->ns, ng = c->ng;
-   if (part != 0 && ns < 4 * ng) return set_err(AMPE_EINVAL, "slab too thin to split");
-   if (part != 2) c->launches = 0;
+   if (first) c->launches = 0;
 
    // QuatIntegrator.cc:3189
    const bool recompute = (fd_flag == 0) || !c->cfg.lag_quat_sidegrad;
@@ -496,19 +516,9 @@ static int eval_part(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
       A.p = p;
       A.conc = make_field(c, y->conc, c->halo_lo.conc, c->halo_hi.conc, 1);
       A.out_c = ydot->conc;
-      int ranges[2][2];
-      int nr = 0;
-      if (part == 0) {
-         ranges[nr][0] = 0, ranges[nr++][1] = ns;
-      } else if (part == 1) {
-         ranges[nr][0] = ng, ranges[nr++][1] = ns - ng;
-      } else {
-         ranges[nr][0] = 0, ranges[nr++][1] = ng;
-         ranges[nr][0] = ns - ng, ranges[nr++][1] = ns;
-      }
-      for (int r = 0; r < nr; r++) {
-         A.s_begin = ranges[r][0];
-         A.s_end = ranges[r][1];
+      for (int r = 0; r < cells.n; r++) {
+         A.s_begin = cells.r[r][0];
+         A.s_end = cells.r[r][1];
          const long long total = c->plane * (A.s_end - A.s_begin);
          const int blocks = (int)((total + 255) / 256);
          if (p.ndim == 2)
@@ -540,19 +550,9 @@ static int eval_part(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
       K.ca = c->ca;
       K.df = c->df;
       K.nfail = c->nfail;
-      int ranges[2][2];
-      int nr = 0;
-      if (part == 0) {
-         ranges[nr][0] = -ng, ranges[nr++][1] = ns + ng;
-      } else if (part == 1) {
-         ranges[nr][0] = 0, ranges[nr++][1] = ns;
-      } else {
-         ranges[nr][0] = -ng, ranges[nr++][1] = 0;
-         ranges[nr][0] = ns, ranges[nr++][1] = ns + ng;
-      }
-      for (int r = 0; r < nr; r++) {
-         K.s_begin = ranges[r][0];
-         K.s_end = ranges[r][1];
+      for (int r = 0; r < kks.n; r++) {
+         K.s_begin = kks.r[r][0];
+         K.s_end = kks.r[r][1];
          const long long total = c->plane * (K.s_end - K.s_begin);
          const int blocks = (int)((total + 255) / 256);
          if (p.ndim == 2)
@@ -589,25 +589,39 @@ static int eval_part(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
    A.df = c->df;
    A.use_lag = use_lag ? 1 : 0;
    A.write_lag = (recompute && c->cfg.lag_quat_sidegrad) ? 1 : 0;
-   int ranges[2][2];
-   int nr = 0;
-   if (part == 0) {
-      ranges[nr][0] = 0, ranges[nr++][1] = ns;
-   } else if (part == 1) {
-      ranges[nr][0] = ng, ranges[nr++][1] = ns - ng;
-   } else {
-      ranges[nr][0] = 0, ranges[nr++][1] = ng;
-      ranges[nr][0] = ns - ng, ranges[nr++][1] = ns;
-   }
-   for (int r = 0; r < nr; r++) {
-      A.s_begin = ranges[r][0];
-      A.s_end = ranges[r][1];
+   for (int r = 0; r < cells.n; r++) {
+      A.s_begin = cells.r[r][0];
+      A.s_end = cells.r[r][1];
       int rc = (p.ndim == 2) ? dispatch_q<2>(A, st) : dispatch_q<3>(A, st);
       if (rc) return rc;
       c->launches++;
    }
-   if (part != 1 && A.write_lag) c->lag_valid = true;
+   if (last && A.write_lag) c->lag_valid = true;
    return AMPE_OK;
+}
+
+// part: 0 = everything, 1 = interior (no ghost plane needed), 2 = boundary planes
+static int eval_part(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
+                     const ampe_rhs_fields* ydot, int fd_flag, cudaStream_t st, int part)
+{
+   (void)time;
+   if (!c) return set_err(AMPE_EINVAL, "null argument");
+   const int ns = c->ns, ng = c->ng;
+   if (part != 0 && ns < 4 * ng) return set_err(AMPE_EINVAL, "slab too thin to split");
+   Ranges kks, cells;
+   if (part == 0) {
+      kks.add(-ng, ns + ng);
+      cells.add(0, ns);
+   } else if (part == 1) {
+      kks.add(0, ns);
+      cells.add(ng, ns - ng);
+   } else {
+      kks.add(-ng, 0);
+      kks.add(ns, ns + ng);
+      cells.add(0, ng);
+      cells.add(ns - ng, ns);
+   }
+   return eval_ranges(c, y, ydot, fd_flag, st, kks, cells, part != 2, part != 1);
 }
 
 extern "C" int ampe_rhs_eval(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
@@ -685,31 +699,98 @@ extern "C" int ampe_rhs_eval_host(ampe_rhs_ctx* c, double time, const ampe_rhs_f
          CUDA_OK(cudaMalloc(&c->dev_ydot.temperature, nb));
       }
       CUDA_OK(cudaStreamCreate(&c->own_stream));
+      CUDA_OK(cudaStreamCreate(&c->k_stream));
+      CUDA_OK(cudaStreamCreate(&c->out_stream));
+      for (int j = 0; j < AMPE_MAX_HOST_CHUNKS; j++) {
+         CUDA_OK(cudaEventCreateWithFlags(&c->ev_in[j], cudaEventDisableTiming));
+         CUDA_OK(cudaEventCreateWithFlags(&c->ev_k[j], cudaEventDisableTiming));
+      }
       c->have_dev = true;
    }
-   cudaStream_t st = c->own_stream;
-   if (p.with_phase)
-      CUDA_OK(cudaMemcpyAsync(c->dev_y.phase, yh->phase, nb, cudaMemcpyHostToDevice, st));
-   if (p.qlen > 0)
-      CUDA_OK(cudaMemcpyAsync(c->dev_y.quat, yh->quat, nb * p.qlen, cudaMemcpyHostToDevice, st));
-   if (p.with_conc)
-      CUDA_OK(cudaMemcpyAsync(c->dev_y.conc, yh->conc, nb, cudaMemcpyHostToDevice, st));
-   if (p.with_T)
-      CUDA_OK(cudaMemcpyAsync(c->dev_y.temperature, yh->temperature, nb, cudaMemcpyHostToDevice,
-                              st));
-   int rc = eval_part(c, time, &c->dev_y, &c->dev_ydot, fd_flag, st, 0);
-   if (rc) return rc;
-   if (p.with_phase)
-      CUDA_OK(cudaMemcpyAsync(ydh->phase, c->dev_ydot.phase, nb, cudaMemcpyDeviceToHost, st));
-   if (p.evolve_quat)
-      CUDA_OK(cudaMemcpyAsync(ydh->quat, c->dev_ydot.quat, nb * p.qlen, cudaMemcpyDeviceToHost,
-                              st));
-   if (p.with_conc)
-      CUDA_OK(cudaMemcpyAsync(ydh->conc, c->dev_ydot.conc, nb, cudaMemcpyDeviceToHost, st));
-   if (p.with_T)
-      CUDA_OK(cudaMemcpyAsync(ydh->temperature, c->dev_ydot.temperature, nb,
-                              cudaMemcpyDeviceToHost, st));
-   CUDA_OK(cudaStreamSynchronize(st));
+   // Pipeline over chunks of slab planes: the H2D copy of chunk j+1, the kernels of chunk j and
+   // the D2H copy of chunk j-1 run concurrently on three streams (PCIe is full duplex, and the
+   // copies, not the kernels, bound this entry point).  A plane can be evaluated once its two
+   // neighbour planes are on the device; plane 0 and the last plane close the periodic wrap
+   // at the end.  Small problems run as one chunk.
+   const int ns = c->ns, ng = c->ng;
+   const long long pl = c->plane;
+   int nfields = (p.with_phase ? 1 : 0) + p.qlen + (p.with_conc ? 1 : 0) + (p.with_T ? 1 : 0);
+   const double chunk_target = 16.0e6;  // bytes per chunk (swept on B200: profiles/README.md)
+   int nchunk = (int)((double)nb * nfields / chunk_target);
+   if (nchunk > AMPE_MAX_HOST_CHUNKS) nchunk = AMPE_MAX_HOST_CHUNKS;
+   if (const char* e = getenv("AMPE_B200_HOST_CHUNKS")) nchunk = atoi(e);
+   if (nchunk > ns / (4 * ng)) nchunk = ns / (4 * ng);
+   if (nchunk > AMPE_MAX_HOST_CHUNKS) nchunk = AMPE_MAX_HOST_CHUNKS;
+   if (nchunk < 1) nchunk = 1;
+   if (c->have_halo) nchunk = 1;  // halo buffers: the caller sequences the exchange itself
+   cudaStream_t s_in = c->own_stream, s_k = c->k_stream, s_out = c->out_stream;
+   auto h2d_planes = [&](int b, int e) -> int {
+      const size_t off = (size_t)b * pl, bytes = (size_t)(e - b) * pl * sizeof(double);
+      if (p.with_phase)
+         CUDA_OK(cudaMemcpyAsync(c->dev_y.phase + off, yh->phase + off, bytes, cudaMemcpyHostToDevice, s_in));
+      for (int m = 0; m < p.qlen; m++)
+         CUDA_OK(cudaMemcpyAsync(c->dev_y.quat + m * c->ncell + off, yh->quat + m * c->ncell + off, bytes,
+                                 cudaMemcpyHostToDevice, s_in));
+      if (p.with_conc)
+         CUDA_OK(cudaMemcpyAsync(c->dev_y.conc + off, yh->conc + off, bytes, cudaMemcpyHostToDevice, s_in));
+      if (p.with_T)
+         CUDA_OK(cudaMemcpyAsync(c->dev_y.temperature + off, yh->temperature + off, bytes,
+                                 cudaMemcpyHostToDevice, s_in));
+      return AMPE_OK;
+   };
+   auto d2h_planes = [&](int b, int e) -> int {
+      if (e <= b) return AMPE_OK;
+      const size_t off = (size_t)b * pl, bytes = (size_t)(e - b) * pl * sizeof(double);
+      if (p.with_phase)
+         CUDA_OK(cudaMemcpyAsync(ydh->phase + off, c->dev_ydot.phase + off, bytes, cudaMemcpyDeviceToHost, s_out));
+      if (p.evolve_quat)
+         for (int m = 0; m < p.qlen; m++)
+            CUDA_OK(cudaMemcpyAsync(ydh->quat + m * c->ncell + off, c->dev_ydot.quat + m * c->ncell + off,
+                                    bytes, cudaMemcpyDeviceToHost, s_out));
+      if (p.with_conc)
+         CUDA_OK(cudaMemcpyAsync(ydh->conc + off, c->dev_ydot.conc + off, bytes, cudaMemcpyDeviceToHost, s_out));
+      if (p.with_T)
+         CUDA_OK(cudaMemcpyAsync(ydh->temperature + off, c->dev_ydot.temperature + off, bytes,
+                                 cudaMemcpyDeviceToHost, s_out));
+      return AMPE_OK;
+   };
+   int done_to = ng;  // cells [ng, done_to) have been evaluated
+   for (int j = 0; j < nchunk; j++) {
+      const int b = (int)((long long)ns * j / nchunk), e = (int)((long long)ns * (j + 1) / nchunk);
+      int rc = h2d_planes(b, e);
+      if (rc) return rc;
+      CUDA_OK(cudaEventRecord(c->ev_in[j], s_in));
+      CUDA_OK(cudaStreamWaitEvent(s_k, c->ev_in[j], 0));
+      Ranges kks, cells;
+      const bool fin = (j == nchunk - 1);
+      if (nchunk == 1) {
+         kks.add(-ng, ns + ng);
+         cells.add(0, ns);
+      } else if (!fin) {
+         kks.add(b, e);
+         cells.add(done_to, e - ng);
+      } else {
+         // everything is on the device: ghost planes of the KKS arrays, the rest of the slab,
+         // then the first ng planes (their lower neighbours are the last planes)
+         kks.add(b, ns + ng);
+         kks.add(-ng, 0);
+         cells.add(done_to, ns);
+         cells.add(0, ng);
+      }
+      rc = eval_ranges(c, &c->dev_y, &c->dev_ydot, fd_flag, s_k, kks, cells, j == 0, fin);
+      if (rc) return rc;
+      CUDA_OK(cudaEventRecord(c->ev_k[j], s_k));
+      CUDA_OK(cudaStreamWaitEvent(s_out, c->ev_k[j], 0));
+      for (int r = 0; r < cells.n; r++) {
+         rc = d2h_planes(cells.r[r][0], cells.r[r][1]);
+         if (rc) return rc;
+      }
+      if (!fin) done_to = (e - ng > done_to) ? e - ng : done_to;
+   }
+   CUDA_OK(cudaStreamSynchronize(s_out));
+   // the next call overwrites dev_y on s_in: it must not overtake this call's kernels
+   CUDA_OK(cudaStreamSynchronize(s_k));
+   (void)time;
    return AMPE_OK;
 }
 

@@ -290,7 +290,7 @@ def main():
         dt = (time.perf_counter() - t0) / n_e2e
         e2e = {"value": r.ncell / dt / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": dt * 1e3, "steps": n_e2e,
-               "path": "ampe_rhs_eval_host: pinned host y -> device, evaluate, ydot -> pinned host"}
+               "path": "ampe_rhs_eval_host: pinned host y -> device, evaluate, ydot -> pinned host, slab chunks pipelined on three streams (H2D | kernels | D2H)"}
     elif world > 1:
         e2e = {"value": None, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "measured at N=1 only"}
