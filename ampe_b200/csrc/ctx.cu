@@ -32,36 +32,7 @@ int ampe_set_err(int code, const std::string& msg)
 
 static const double R_GAS = 8.314472;  // GASCONSTANT_R_JPKPMOL
 
-#define AMPE_MAX_HOST_CHUNKS 32
-
-struct ampe_rhs_ctx {
-   ampe_rhs_config cfg;
-   Params p;
-   int ns;            // planes along the slab axis
-   long long plane;   // cells per plane
-   long long ncell;
-   int ng;
-   double *cl = nullptr, *ca = nullptr, *cl_ref = nullptr, *ca_ref = nullptr;  // slab-ghosted
-   double* df = nullptr;  // ghost-0 CALPHAD driving force (written by the KKS kernel)
-   int* iq[3] = {nullptr, nullptr, nullptr};
-   double* lagN[3] = {nullptr, nullptr, nullptr};
-   double* lagD0[3] = {nullptr, nullptr, nullptr};
-   double* lagD1[3] = {nullptr, nullptr, nullptr};
-   int* nfail = nullptr;
-   double* qr_dev = nullptr;  // 48x4 cubic symmetry rotations (setqr)
-   int* conj_dev = nullptr;
-   ampe_rhs_fields halo_lo, halo_hi;
-   bool have_halo = false;
-   bool have_ref = false;
-   bool lag_valid = false;
-   bool generic_only = false;  // AMPE_B200_GENERIC at create time
-   int launches = 0;
-   // staging buffers for ampe_rhs_eval_host
-   ampe_rhs_fields dev_y, dev_ydot;
-   bool have_dev = false;
-   cudaStream_t own_stream = nullptr, k_stream = nullptr, out_stream = nullptr;
-   cudaEvent_t ev_in[AMPE_MAX_HOST_CHUNKS], ev_k[AMPE_MAX_HOST_CHUNKS];
-};
+#include "ctx_internal.h"
 
 // ---- CALPHAD T-dependent coefficients on the host (uniform T) --------------------------
 // G = a + bT + cT ln T + d2 T^2 + d3 T^3 + d4 T^4 + d7 T^7 + dm1/T + dm9/T^9
@@ -347,6 +318,8 @@ extern "C" int ampe_rhs_destroy(ampe_rhs_ctx* c)
    cudaFree(c->ca_ref);
    cudaFree(c->nfail);
    cudaFree(c->df);
+   cudaFree(c->partials);
+   cudaFree(c->red_out);
    cudaFree(c->qr_dev);
    cudaFree(c->conj_dev);
    for (int d = 0; d < 3; d++) {
@@ -491,22 +464,23 @@ struct Ranges {
 
 static int eval_ranges(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs_fields* ydot,
                        int fd_flag, cudaStream_t st, const Ranges& kks, const Ranges& cells,
-                       bool first, bool last)
+                       bool first, bool last, double* energy_partials = nullptr)
 {
    if (!c || !y || !ydot) return set_err(AMPE_EINVAL, "null argument");
    const Params& p = c->p;
-   if (p.with_phase && (!y->phase || !ydot->phase)) return set_err(AMPE_EINVAL, "phase missing");
+   const bool en = energy_partials != nullptr;  // energy diagnostics: ydot is not written
+   if (p.with_phase && (!y->phase || (!en && !ydot->phase))) return set_err(AMPE_EINVAL, "phase missing");
    if (p.qlen > 0 && !y->quat) return set_err(AMPE_EINVAL, "quat missing");
-   if (p.evolve_quat && !ydot->quat) return set_err(AMPE_EINVAL, "ydot quat missing");
-   if (p.with_conc && (!y->conc || !ydot->conc)) return set_err(AMPE_EINVAL, "conc missing");
-   if (p.with_T && (!y->temperature || !ydot->temperature))
+   if (p.evolve_quat && !en && !ydot->quat) return set_err(AMPE_EINVAL, "ydot quat missing");
+   if (p.with_conc && (!y->conc || (!en && !ydot->conc))) return set_err(AMPE_EINVAL, "conc missing");
+   if (p.with_T && (!y->temperature || (!en && !ydot->temperature)))
       return set_err(AMPE_EINVAL, "temperature missing");
    if (first) c->launches = 0;
 
    // QuatIntegrator.cc:3189
    const bool recompute = (fd_flag == 0) || !c->cfg.lag_quat_sidegrad;
    const bool has_lag_data = c->lagN[0] || c->lagD0[0];
-   const bool use_lag = !recompute && has_lag_data;
+   const bool use_lag = !recompute && has_lag_data && !en;
    if (use_lag && !c->lag_valid)
       return set_err(AMPE_EINVAL, "fd_flag=1 before any fd_flag=0 evaluation (no lagged data)");
 
@@ -584,11 +558,12 @@ static int eval_ranges(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs
    A.out_q = ydot->quat;
    A.out_c = ydot->conc;
    A.out_T = ydot->temperature;
-   A.force_generic = c->generic_only ? 1 : 0;
+   A.force_generic = (c->generic_only || en) ? 1 : 0;
+   A.energy_partials = energy_partials;
    A.wrap_slab = c->have_halo ? 0 : 1;
    A.df = c->df;
    A.use_lag = use_lag ? 1 : 0;
-   A.write_lag = (recompute && c->cfg.lag_quat_sidegrad) ? 1 : 0;
+   A.write_lag = (recompute && c->cfg.lag_quat_sidegrad && !en) ? 1 : 0;
    for (int r = 0; r < cells.n; r++) {
       A.s_begin = cells.r[r][0];
       A.s_end = cells.r[r][1];
@@ -598,6 +573,35 @@ static int eval_ranges(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs
    }
    if (last && A.write_lag) c->lag_valid = true;
    return AMPE_OK;
+}
+
+// energy diagnostics through the fused kernel family: KKS pre-pass + energy_tile_kernel
+int ampe_launch_energy(ampe_rhs_ctx* c, const ampe_rhs_fields* y, cudaStream_t st, long long* nblocks)
+{
+   const Params& p = c->p;
+   const int ns = c->ns, ng = c->ng;
+   const int TY = (p.ndim == 2) ? AMPE_T2Y : AMPE_T3Y, TZ = (p.ndim == 2) ? 1 : AMPE_T3Z;
+   long long nb = (p.n[0] + 31) / 32;
+   if (p.ndim == 2)
+      nb *= (ns + TY - 1) / TY;
+   else
+      nb *= (long long)((p.n[1] + TY - 1) / TY) * ((ns + TZ - 1) / TZ);
+   if (nb > c->partials_cap) {
+      cudaFree(c->partials);
+      c->partials = nullptr;
+      CUDA_OK(cudaMalloc(&c->partials, (size_t)nb * 6 * sizeof(double)));
+      c->partials_cap = nb;
+   }
+   *nblocks = nb;
+   Ranges kks, cells;
+   kks.add(-ng, ns + ng);
+   cells.add(0, ns);
+   ampe_rhs_fields none;
+   memset(&none, 0, sizeof(none));
+   const int saved = c->launches;
+   int rc = eval_ranges(c, y, &none, 0, st, kks, cells, false, false, c->partials);
+   c->launches = saved;
+   return rc;
 }
 
 // part: 0 = everything, 1 = interior (no ghost plane needed), 2 = boundary planes

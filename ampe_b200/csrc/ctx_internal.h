@@ -1,0 +1,47 @@
+// Private definition of the context behind the C ABI (shared by ctx.cu and vecops.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+
+#include "rhs_common.cuh"
+#include "tile_shape.h"
+
+#define AMPE_MAX_HOST_CHUNKS 32
+
+struct ampe_rhs_ctx {
+   ampe_rhs_config cfg;
+   ampe::Params p;
+   int ns;            // planes along the slab axis
+   long long plane;   // cells per plane
+   long long ncell;
+   int ng;
+   double *cl = nullptr, *ca = nullptr, *cl_ref = nullptr, *ca_ref = nullptr;  // slab-ghosted
+   double* df = nullptr;  // ghost-0 CALPHAD driving force (written by the KKS kernel)
+   int* iq[3] = {nullptr, nullptr, nullptr};
+   double* lagN[3] = {nullptr, nullptr, nullptr};
+   double* lagD0[3] = {nullptr, nullptr, nullptr};
+   double* lagD1[3] = {nullptr, nullptr, nullptr};
+   int* nfail = nullptr;
+   double* qr_dev = nullptr;  // 48x4 cubic symmetry rotations (setqr)
+   int* conj_dev = nullptr;
+   ampe_rhs_fields halo_lo, halo_hi;
+   bool have_halo = false;
+   bool have_ref = false;
+   bool lag_valid = false;
+   bool generic_only = false;  // AMPE_B200_GENERIC at create time
+   int launches = 0;
+   // staging buffers for ampe_rhs_eval_host
+   ampe_rhs_fields dev_y, dev_ydot;
+   bool have_dev = false;
+   // energy diagnostics / reductions (vecops.cu): per-block partial sums + device results
+   double* partials = nullptr;
+   long long partials_cap = 0;
+   double* red_out = nullptr;
+   cudaStream_t own_stream = nullptr, k_stream = nullptr, out_stream = nullptr;
+   cudaEvent_t ev_in[AMPE_MAX_HOST_CHUNKS], ev_k[AMPE_MAX_HOST_CHUNKS];
+};
+
+int ampe_set_err(int code, const std::string& msg);
+// one evaluation of the fused kernel family in "energy" mode (ctx.cu): fills c->partials
+int ampe_launch_energy(ampe_rhs_ctx* c, const ampe_rhs_fields* y, cudaStream_t st, long long* nblocks);

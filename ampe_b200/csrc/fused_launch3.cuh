@@ -4,21 +4,45 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "energy_tile.cuh"
 #include "rhs_march.cuh"
 #include "rhs_tile.cuh"
+#include "tile_shape.h"
 
 namespace ampe {
 
-// tile shape and block size (swept on B200, profiles/README.md)
-#ifndef AMPE_T2Y
-#define AMPE_T2Y 16
-#define AMPE_NT2 256
-#endif
-#ifndef AMPE_T3Y
-#define AMPE_T3Y 4
-#define AMPE_T3Z 4
-#define AMPE_NT3 512
-#endif
+
+// energy diagnostics on the same tile geometry (energy_tile.cuh)
+template <class TT>
+static int launch_energy(const FusedArgs& A, cudaStream_t st, const char** err)
+{
+   const Params& p = A.p;
+   auto kern = energy_tile_kernel<TT>;
+   static bool configured = false;
+   if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TT::SMEM_BYTES);
+      if (e != cudaSuccess) {
+         *err = cudaGetErrorString(e);
+         return AMPE_ECUDA;
+      }
+      configured = true;
+   }
+   const int nslab = A.s_end - A.s_begin;
+   dim3 grid((p.n[0] + TT::TX - 1) / TT::TX, 1, 1);
+   if (TT::ND == 2) {
+      grid.y = (nslab + TT::TY - 1) / TT::TY;
+   } else {
+      grid.y = (p.n[1] + TT::TY - 1) / TT::TY;
+      grid.z = (nslab + TT::TZ - 1) / TT::TZ;
+   }
+   kern<<<grid, TT::NT, TT::SMEM_BYTES, st>>>(A);
+   cudaError_t e2 = cudaGetLastError();
+   if (e2 != cudaSuccess) {
+      *err = cudaGetErrorString(e2);
+      return AMPE_ECUDA;
+   }
+   return AMPE_OK;
+}
 
 template <int ND, int Q, int CONC, bool SYMM, bool WT, class SEL>
 static int launch3(const FusedArgs& A, cudaStream_t st, const char** err)
@@ -60,10 +84,6 @@ static int launch3(const FusedArgs& A, cudaStream_t st, const char** err)
 }
 
 // 3D plane-marching kernel (no quaternion symmetry): column 32 x TY, NZ planes per block
-#ifndef AMPE_MY
-#define AMPE_MY 8
-#define AMPE_MZ 16
-#endif
 template <int Q, int CONC, bool WT, class SEL>
 static int launch_march(const FusedArgs& A, cudaStream_t st, const char** err)
 {
@@ -95,8 +115,17 @@ static int launch_march(const FusedArgs& A, cudaStream_t st, const char** err)
 template <int ND, int Q, int CONC, bool SYMM, bool WT, class SEL>
 static int launch_any(const FusedArgs& A, cudaStream_t st, const char** err)
 {
-   if constexpr (ND == 3 && !SYMM)
+   if constexpr (!SEL::fixed) {
+      // energy diagnostics: tile geometry for every model, runtime selectors only
+      if (A.energy_partials) {
+         using TT = Tile3<ND, Q, CONC, SYMM, WT, SEL, 32, (ND == 2) ? AMPE_T2Y : AMPE_T3Y, (ND == 2) ? 1 : AMPE_T3Z,
+                          (ND == 2) ? AMPE_NT2 : AMPE_NT3>;
+         return launch_energy<TT>(A, st, err);
+      }
+   }
+   if constexpr (ND == 3 && !SYMM) {
       return launch_march<Q, CONC, WT, SEL>(A, st, err);
+   }
    else
       return launch3<ND, Q, CONC, SYMM, WT, SEL>(A, st, err);
 }

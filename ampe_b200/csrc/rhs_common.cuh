@@ -41,6 +41,7 @@ struct FusedArgs {
    int force_generic;   // host side only: use the runtime-selector instantiation
    int wrap_slab;       // 1: no halo buffers, ghost planes = opposite interior planes (one rank)
    const double* df;    // CALPHAD driving force (f_l-f_a)-mu(c_l-c_a) per cell from the KKS kernel
+   double* energy_partials;  // non-null: energy diagnostics instead of the RHS (energy_tile.cuh)
 };
 
 template <int Q>

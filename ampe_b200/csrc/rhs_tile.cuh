@@ -52,36 +52,20 @@ struct Tile3 {
    AMPE_DEV static int fidx(int i, int j, int k) { return i + FX * (j + FY * k); }
 };
 
+// ---- (A) stage a tile (+1-cell halo incl. edges/corners) of every state field ---------------
+// cp.async straight into shared memory (no register staging).  fillScratch
+// (QuatIntegrator.cc:2873-2955) = the periodic wrap / halo-plane selection done here.
 template <class TT>
-__global__ void __launch_bounds__(TT::NT) rhs_tile_kernel(const __grid_constant__ FusedArgs A)
+AMPE_DEV void stage_tile(const FusedArgs& A, double* s, int* s_iq, int ox, int oy, int oz)
 {
-   using R = Rhs3<TT>;
-   using SEL = typename TT::SEL;
    constexpr int ND = TT::ND, Q = TT::Q, CONC = TT::CONC, S = TT::S, NT = TT::NT, NW = TT::NW;
-   constexpr int TX = TT::TX, TY = TT::TY, TZ = TT::TZ, CPT = TT::CPT;
    constexpr bool SYMM = TT::SYMM, WT = TT::WT;
    const Params& p = A.p;
-   extern __shared__ double smem[];
-   double* s = smem;
-   int* s_iq = reinterpret_cast<int*>(smem + TT::O_END);  // ND*S ints (SYMM)
-   __shared__ double s_qr[SYMM ? 48 : 1][4];
-   __shared__ int s_conj[SYMM ? 48 : 1];
-   if (SYMM && Q == 4) {
-      for (int t = threadIdx.x; t < 48 * 4; t += NT) s_qr[t / 4][t % 4] = A.qr[t];
-      for (int t = threadIdx.x; t < 48; t += NT) s_conj[t] = A.conj[t];
-   }
-
-   // ---- tile origin -------------------------------------------------------------
    const int n0 = p.n[0], n1 = p.n[1], n2 = (ND == 3) ? p.n[2] : 1;
-   const int ns = (ND == 3) ? n2 : n1;  // planes along the slab axis
-   const int ox = blockIdx.x * TX;
-   const int oy = blockIdx.y * TY + ((ND == 2) ? A.s_begin : 0);
-   const int oz = (ND == 3) ? (blockIdx.z * TZ + A.s_begin) : 0;
-   const long long plane = (ND == 3) ? (long long)n0 * n1 : (long long)n0;  // slab plane size
-   const long long ncell = (long long)n0 * n1 * n2;
+   const int ns = (ND == 3) ? n2 : n1;
+   const long long plane = (ND == 3) ? (long long)n0 * n1 : (long long)n0;
    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
-
-   // ---- (A) stage: cp.async straight into shared memory (no register staging) ------------
+   (void)n1;
    // A staged row has SX = 34 elements: one warp copies x = 0..31 of a row per instruction,
    // the two tail elements of all rows are gathered into one extra pass of the block.
    {
@@ -145,6 +129,38 @@ __global__ void __launch_bounds__(TT::NT) rhs_tile_kernel(const __grid_constant_
       for (int t = threadIdx.x; t < 2 * NROWS; t += NT) copy_elem(t >> 1, 32 + (t & 1));
       cp_async_wait_all();
    }
+}
+
+template <class TT>
+__global__ void __launch_bounds__(TT::NT) rhs_tile_kernel(const __grid_constant__ FusedArgs A)
+{
+   using R = Rhs3<TT>;
+   using SEL = typename TT::SEL;
+   constexpr int ND = TT::ND, Q = TT::Q, CONC = TT::CONC, S = TT::S, NT = TT::NT, NW = TT::NW;
+   constexpr int TX = TT::TX, TY = TT::TY, TZ = TT::TZ, CPT = TT::CPT;
+   constexpr bool SYMM = TT::SYMM, WT = TT::WT;
+   const Params& p = A.p;
+   extern __shared__ double smem[];
+   double* s = smem;
+   int* s_iq = reinterpret_cast<int*>(smem + TT::O_END);  // ND*S ints (SYMM)
+   __shared__ double s_qr[SYMM ? 48 : 1][4];
+   __shared__ int s_conj[SYMM ? 48 : 1];
+   if (SYMM && Q == 4) {
+      for (int t = threadIdx.x; t < 48 * 4; t += NT) s_qr[t / 4][t % 4] = A.qr[t];
+      for (int t = threadIdx.x; t < 48; t += NT) s_conj[t] = A.conj[t];
+   }
+
+   // ---- tile origin -------------------------------------------------------------
+   const int n0 = p.n[0], n1 = p.n[1], n2 = (ND == 3) ? p.n[2] : 1;
+   const int ns = (ND == 3) ? n2 : n1;  // planes along the slab axis
+   const int ox = blockIdx.x * TX;
+   const int oy = blockIdx.y * TY + ((ND == 2) ? A.s_begin : 0);
+   const int oz = (ND == 3) ? (blockIdx.z * TZ + A.s_begin) : 0;
+   const long long plane = (ND == 3) ? (long long)n0 * n1 : (long long)n0;  // slab plane size
+   const long long ncell = (long long)n0 * n1 * n2;
+   const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
+
+   stage_tile<TT>(A, s, s_iq, ox, oy, oz);
    __syncthreads();
 
    // rows owned by this warp: r = warp + u*NW; inside a plane the row stride is constant

@@ -1,0 +1,16 @@
+// Tile shapes and block sizes of the fused kernels (swept on B200, profiles/README.md)
+#pragma once
+#ifndef AMPE_T2Y
+#define AMPE_T2Y 16
+#define AMPE_NT2 256
+#endif
+#ifndef AMPE_T3Y
+#define AMPE_T3Y 4
+#define AMPE_T3Z 4
+#define AMPE_NT3 512
+#endif
+// 3D plane-marching kernel: column 32 x AMPE_MY, AMPE_MZ planes per block
+#ifndef AMPE_MY
+#define AMPE_MY 8
+#define AMPE_MZ 16
+#endif

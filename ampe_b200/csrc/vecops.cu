@@ -1,0 +1,430 @@
+// Device-resident pieces around the RHS evaluation, behind the C ABI
+// of include/ampe_b200.h:
+//   * N_Vector operations CVODE needs on the solution vector (samrai/Sundials_SAMRAIVector.cc:
+//     linearSum, scale, dotWith, weightedRMSNorm, maxNorm), over the evolved components;
+//   * QuatModel::normalizeQuat (QuatModel.cc:4222-4262);
+//   * scalar energy diagnostics (QuatModel::evaluateEnergy, quatenergy.m4) -- reduction of the
+//     per-block partial sums written by energy_tile_kernel, and the PFHub-1a Cahn-Hilliard energy;
+//   * a fixed-step explicit integrator (forward Euler / Heun) that keeps y on the device between
+//     evaluations -- the minimal stand-in for the CVODE loop of QuatIntegrator::Advance used by
+//     the trajectory parity tests.
+// All bandwidth-trivial grid-stride kernels; deterministic two-stage reductions.
+#include <cstring>
+
+#include "ctx_internal.h"
+
+using namespace ampe;
+
+#define CUDA_OKV(call)                                                                       \
+   do {                                                                                      \
+      cudaError_t e_ = (call);                                                               \
+      if (e_ != cudaSuccess)                                                                 \
+         return ampe_set_err(AMPE_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+   } while (0)
+
+namespace {
+
+constexpr int VT = 256;
+constexpr int RED_BLOCKS = 592;  // 4 per SM on B200
+
+int grid_for(long long n)
+{
+   long long b = (n + VT - 1) / VT;
+   if (b > 148LL * 16) b = 148LL * 16;
+   return (int)(b < 1 ? 1 : b);
+}
+
+// the evolved components of the solution vector (createSolutionvector, QuatIntegrator.cc:1623-1674)
+struct Comp {
+   int n = 0;
+   const double* x[4];
+   const double* y[4];
+   double* z[4];
+   long long len[4];
+};
+
+int components(const ampe_rhs_ctx* c, const ampe_rhs_fields* x, const ampe_rhs_fields* y,
+               const ampe_rhs_fields* z, Comp& o)
+{
+   const Params& p = c->p;
+   auto add = [&](bool on, double* ampe_rhs_fields::*m, long long len) -> int {
+      if (!on) return 0;
+      if ((x && !(x->*m)) || (y && !(y->*m)) || (z && !(z->*m)))
+         return ampe_set_err(AMPE_EINVAL, "vector operation: an evolved component is NULL");
+      o.x[o.n] = x ? x->*m : nullptr;
+      o.y[o.n] = y ? y->*m : nullptr;
+      o.z[o.n] = z ? z->*m : nullptr;
+      o.len[o.n++] = len;
+      return 0;
+   };
+   int rc = add(p.with_phase, &ampe_rhs_fields::phase, c->ncell);
+   if (!rc) rc = add(p.evolve_quat, &ampe_rhs_fields::quat, c->ncell * p.qlen);
+   if (!rc) rc = add(p.with_conc, &ampe_rhs_fields::conc, c->ncell);
+   if (!rc) rc = add(p.with_T, &ampe_rhs_fields::temperature, c->ncell);
+   return rc;
+}
+
+__global__ void linear_sum_kernel(double a, const double* x, double b, const double* y, double* z, long long n)
+{
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      z[i] = a * x[i] + b * y[i];
+}
+__global__ void axpy_kernel(double a, const double* x, double* z, long long n)  // z += a x
+{
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      z[i] = z[i] + a * x[i];
+}
+__global__ void scale_kernel(double a, const double* x, double* z, long long n)
+{
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      z[i] = a * x[i];
+}
+
+// mode 0: sum x*y   1: sum (x*w)^2   2: max |x|
+template <int MODE>
+__global__ void reduce_kernel(const double* x, const double* y, long long n, double* partial)
+{
+   double acc = 0.0;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      if (MODE == 0) acc += x[i] * y[i];
+      if (MODE == 1) {
+         const double t = x[i] * y[i];
+         acc += t * t;
+      }
+      if (MODE == 2) acc = fmax(acc, fabs(x[i]));
+   }
+   __shared__ double red[VT / 32];
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) {
+      const double t = __shfl_down_sync(0xffffffffu, acc, o);
+      acc = (MODE == 2) ? fmax(acc, t) : acc + t;
+   }
+   if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      double r = red[0];
+      for (int w = 1; w < VT / 32; w++) r = (MODE == 2) ? fmax(r, red[w]) : r + red[w];
+      partial[blockIdx.x] = r;
+   }
+}
+// out[v] (+)= reduction of partial[b*nvals + v] over b, fixed order (one block, one warp per value)
+template <int MODE>
+__global__ void final_reduce_kernel(const double* partial, long long nblocks, int nvals, double* out, int accumulate)
+{
+   const int v = threadIdx.x / 32, lane = threadIdx.x % 32;
+   if (v >= nvals) return;
+   double acc = 0.0;
+   for (long long b = lane; b < nblocks; b += 32) {
+      const double t = partial[b * nvals + v];
+      acc = (MODE == 2) ? fmax(acc, t) : acc + t;
+   }
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) {
+      const double t = __shfl_down_sync(0xffffffffu, acc, o);
+      acc = (MODE == 2) ? fmax(acc, t) : acc + t;
+   }
+   if (lane == 0) {
+      if (accumulate) acc = (MODE == 2) ? fmax(acc, out[v]) : acc + out[v];
+      out[v] = acc;
+   }
+}
+
+// QuatModel::normalizeQuat (QuatModel.cc:4237-4262): q *= 1/sqrt(sum q^2), per cell
+template <int Q>
+__global__ void normalize_quat_kernel(double* q, long long ncell)
+{
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < ncell; i += (long long)gridDim.x * blockDim.x) {
+      double v[Q], n2 = 0.0;
+#pragma unroll
+      for (int m = 0; m < Q; m++) {
+         v[m] = q[i + m * ncell];
+         n2 = n2 + v[m] * v[m];
+      }
+      const double inv = 1.0 / sqrt(n2);
+#pragma unroll
+      for (int m = 0; m < Q; m++) q[i + m * ncell] = v[m] * inv;
+   }
+}
+
+// PFHub 1a free energy of the Cahn-Hilliard model (no evaluator in the reference; the functional
+// whose variational derivative is the mu of add_cahnhilliarddoublewell_flux,
+// 2d/concentrationrhs.m4:85-137): w (c-ca)^2 (cb-c)^2 + kappa/2 |grad c|^2, the gradient as the
+// mean of the squared face gradients.  partial[b*6 + {0 total, 1 gradient, 4 well}]
+template <int ND>
+__global__ void ch_energy_kernel(const __grid_constant__ ChArgs A, double* partial)
+{
+   const Params& p = A.p;
+   const int n0 = p.n[0], n1 = p.n[1], n2 = (ND == 3) ? p.n[2] : 1;
+   const int ns = (ND == 3) ? n2 : n1;
+   const long long plane = (ND == 3) ? (long long)n0 * n1 : (long long)n0;
+   const long long total = plane * ns;
+   auto at = [&](int i, int j, int k) -> double {
+      i = (i < 0) ? i + n0 : ((i >= n0) ? i - n0 : i);
+      int sl;
+      long long inplane;
+      if (ND == 3) {
+         j = (j < 0) ? j + n1 : ((j >= n1) ? j - n1 : j);
+         sl = k;
+         inplane = i + (long long)n0 * j;
+      } else {
+         sl = j;
+         inplane = i;
+      }
+      if (sl < 0) return A.conc.lo[(long long)(sl + 2) * plane + inplane];
+      if (sl >= ns) return A.conc.hi[(long long)(sl - ns) * plane + inplane];
+      return A.conc.base[(long long)sl * plane + inplane];
+   };
+   double weight = p.h[0] * p.h[1];
+   if (ND == 3) weight = weight * p.h[2];
+   double aw = 0.0, ag = 0.0;
+   for (long long cell = blockIdx.x * (long long)blockDim.x + threadIdx.x; cell < total;
+        cell += (long long)gridDim.x * blockDim.x) {
+      const int i = (int)(cell % n0);
+      const int j = (int)((cell / n0) % n1);
+      const int k = (int)(cell / ((long long)n0 * n1));
+      const double c = at(i, j, k);
+      const double w = p.ch_well_scale * (c - p.ch_ca) * (c - p.ch_ca) * (p.ch_cb - c) * (p.ch_cb - c);
+      double g2 = 0.0;
+#pragma unroll
+      for (int a = 0; a < ND; a++) {
+         const double gl = (c - at(i - (a == 0), j - (a == 1), k - (a == 2))) * p.dinv[a];
+         const double gu = (at(i + (a == 0), j + (a == 1), k + (a == 2)) - c) * p.dinv[a];
+         g2 = g2 + 0.5 * (gl * gl + gu * gu);
+      }
+      aw += w * weight;
+      ag += (0.5 * p.ch_kappa * g2) * weight;
+   }
+   __shared__ double red[2][VT / 32];
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) {
+      aw += __shfl_down_sync(0xffffffffu, aw, o);
+      ag += __shfl_down_sync(0xffffffffu, ag, o);
+   }
+   if (threadIdx.x % 32 == 0) red[0][threadIdx.x / 32] = aw, red[1][threadIdx.x / 32] = ag;
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      double w = 0.0, g = 0.0;
+      for (int t = 0; t < VT / 32; t++) w += red[0][t], g += red[1][t];
+      double* o = partial + (long long)blockIdx.x * 6;
+      o[0] = w + g, o[1] = g, o[2] = 0.0, o[3] = 0.0, o[4] = w, o[5] = 0.0;
+   }
+}
+
+int ensure_scratch(ampe_rhs_ctx* c, long long nblocks)
+{
+   if (nblocks > c->partials_cap) {
+      cudaFree(c->partials);
+      c->partials = nullptr;
+      CUDA_OKV(cudaMalloc(&c->partials, (size_t)nblocks * 6 * sizeof(double)));
+      c->partials_cap = nblocks;
+   }
+   if (!c->red_out) CUDA_OKV(cudaMalloc(&c->red_out, 8 * sizeof(double)));
+   return AMPE_OK;
+}
+
+template <int MODE>
+int reduce_components(ampe_rhs_ctx* c, const Comp& v, double* host_out, cudaStream_t st)
+{
+   int rc = ensure_scratch(c, RED_BLOCKS);
+   if (rc) return rc;
+   for (int n = 0; n < v.n; n++) {
+      const int blocks = (int)((v.len[n] + VT - 1) / VT < RED_BLOCKS ? (v.len[n] + VT - 1) / VT : RED_BLOCKS);
+      reduce_kernel<MODE><<<blocks, VT, 0, st>>>(v.x[n], v.y[n], v.len[n], c->partials);
+      final_reduce_kernel<MODE><<<1, 32, 0, st>>>(c->partials, blocks, 1, c->red_out, n > 0);
+   }
+   CUDA_OKV(cudaGetLastError());
+   CUDA_OKV(cudaMemcpyAsync(host_out, c->red_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+   CUDA_OKV(cudaStreamSynchronize(st));
+   return AMPE_OK;
+}
+
+}  // namespace
+
+// z = a x + b y
+extern "C" int ampe_vec_linear_sum(ampe_rhs_ctx* c, double a, const ampe_rhs_fields* x, double b,
+                                   const ampe_rhs_fields* y, const ampe_rhs_fields* z, void* stream)
+{
+   if (!c || !x || !y || !z) return ampe_set_err(AMPE_EINVAL, "null argument");
+   Comp v;
+   int rc = components(c, x, y, z, v);
+   if (rc) return rc;
+   for (int n = 0; n < v.n; n++)
+      linear_sum_kernel<<<grid_for(v.len[n]), VT, 0, (cudaStream_t)stream>>>(a, v.x[n], b, v.y[n], v.z[n], v.len[n]);
+   CUDA_OKV(cudaGetLastError());
+   return AMPE_OK;
+}
+
+// z = a x
+extern "C" int ampe_vec_scale(ampe_rhs_ctx* c, double a, const ampe_rhs_fields* x,
+                              const ampe_rhs_fields* z, void* stream)
+{
+   if (!c || !x || !z) return ampe_set_err(AMPE_EINVAL, "null argument");
+   Comp v;
+   int rc = components(c, x, nullptr, z, v);
+   if (rc) return rc;
+   for (int n = 0; n < v.n; n++)
+      scale_kernel<<<grid_for(v.len[n]), VT, 0, (cudaStream_t)stream>>>(a, v.x[n], v.z[n], v.len[n]);
+   CUDA_OKV(cudaGetLastError());
+   return AMPE_OK;
+}
+
+extern "C" int ampe_vec_dot(ampe_rhs_ctx* c, const ampe_rhs_fields* x, const ampe_rhs_fields* y,
+                            double* result, void* stream)
+{
+   if (!c || !x || !y || !result) return ampe_set_err(AMPE_EINVAL, "null argument");
+   Comp v;
+   int rc = components(c, x, y, nullptr, v);
+   if (rc) return rc;
+   return reduce_components<0>(c, v, result, (cudaStream_t)stream);
+}
+
+// sqrt( sum (x_i w_i)^2 / N )
+extern "C" int ampe_vec_wrms_norm(ampe_rhs_ctx* c, const ampe_rhs_fields* x, const ampe_rhs_fields* w,
+                                  double* result, void* stream)
+{
+   if (!c || !x || !w || !result) return ampe_set_err(AMPE_EINVAL, "null argument");
+   Comp v;
+   int rc = components(c, x, w, nullptr, v);
+   if (rc) return rc;
+   rc = reduce_components<1>(c, v, result, (cudaStream_t)stream);
+   if (rc) return rc;
+   long long n = 0;
+   for (int k = 0; k < v.n; k++) n += v.len[k];
+   *result = sqrt(*result / (double)n);
+   return AMPE_OK;
+}
+
+extern "C" int ampe_vec_max_norm(ampe_rhs_ctx* c, const ampe_rhs_fields* x, double* result, void* stream)
+{
+   if (!c || !x || !result) return ampe_set_err(AMPE_EINVAL, "null argument");
+   Comp v;
+   int rc = components(c, x, x, nullptr, v);
+   if (rc) return rc;
+   return reduce_components<2>(c, v, result, (cudaStream_t)stream);
+}
+
+extern "C" int ampe_normalize_quat(ampe_rhs_ctx* c, const ampe_rhs_fields* y, void* stream)
+{
+   if (!c || !y) return ampe_set_err(AMPE_EINVAL, "null argument");
+   const Params& p = c->p;
+   if (p.qlen <= 1) return AMPE_OK;
+   if (!y->quat) return ampe_set_err(AMPE_EINVAL, "quat missing");
+   cudaStream_t st = (cudaStream_t)stream;
+   if (p.qlen == 2)
+      normalize_quat_kernel<2><<<grid_for(c->ncell), VT, 0, st>>>(y->quat, c->ncell);
+   else
+      normalize_quat_kernel<4><<<grid_for(c->ncell), VT, 0, st>>>(y->quat, c->ncell);
+   CUDA_OKV(cudaGetLastError());
+   return AMPE_OK;
+}
+
+// out[8]: total, phase interface, orientational, q interface, double well, bulk free energy, 0, 0
+// (this rank's cells only: a multi-rank caller sums the ranks)
+extern "C" int ampe_energy_eval(ampe_rhs_ctx* c, const ampe_rhs_fields* y, double* out, void* stream)
+{
+   if (!c || !y || !out) return ampe_set_err(AMPE_EINVAL, "null argument");
+   const Params& p = c->p;
+   cudaStream_t st = (cudaStream_t)stream;
+   for (int n = 0; n < 8; n++) out[n] = 0.0;
+   long long nblocks = 0;
+   if (p.conc_form == AMPE_CONC_CAHN_HILLIARD) {
+      if (!y->conc) return ampe_set_err(AMPE_EINVAL, "conc missing");
+      nblocks = RED_BLOCKS;
+      int rc = ensure_scratch(c, nblocks);
+      if (rc) return rc;
+      ChArgs A;
+      A.p = p;
+      A.conc.base = y->conc;
+      A.conc.comp = c->ncell;
+      if (c->have_halo && c->halo_lo.conc && c->halo_hi.conc) {
+         A.conc.lo = c->halo_lo.conc;
+         A.conc.hi = c->halo_hi.conc;
+      } else {
+         A.conc.lo = y->conc + (long long)(c->ns - c->ng) * c->plane;
+         A.conc.hi = y->conc;
+      }
+      A.conc.hcomp = 0;
+      A.out_c = nullptr;
+      A.s_begin = 0;
+      A.s_end = c->ns;
+      if (p.ndim == 2)
+         ch_energy_kernel<2><<<(int)nblocks, VT, 0, st>>>(A, c->partials);
+      else
+         ch_energy_kernel<3><<<(int)nblocks, VT, 0, st>>>(A, c->partials);
+   } else {
+      if (!p.with_phase) return AMPE_OK;  // QuatModel.cc:4953: no evaluator without a phase field
+      if (p.ndim == 3 && p.nu > 0.0)
+         return ampe_set_err(AMPE_EINVAL, "3D anisotropic interface energy is not on the path");
+      int rc = ensure_scratch(c, 1);
+      if (rc) return rc;
+      rc = ampe_launch_energy(c, y, st, &nblocks);
+      if (rc) return rc;
+   }
+   final_reduce_kernel<0><<<1, 32 * 6, 0, st>>>(c->partials, nblocks, 6, c->red_out, 0);
+   CUDA_OKV(cudaGetLastError());
+   CUDA_OKV(cudaMemcpyAsync(out, c->red_out, 6 * sizeof(double), cudaMemcpyDeviceToHost, st));
+   CUDA_OKV(cudaStreamSynchronize(st));
+   return AMPE_OK;
+}
+
+// Fixed-step explicit integration of nsteps steps, y updated in place on the device.
+//   scheme 0: forward Euler   y += dt f(y)
+//   scheme 1: Heun (RK2)      y* = y + dt f(y);  y += dt/2 (f(y) + f(y*))
+// After every step the quaternions are renormalised (QuatModel::normalizeQuat, as
+// QuatModel::Advance does after the integrator returns) and, for the CALPHAD models, the Newton
+// initial guess is refreshed from the converged c_l, c_a (resetRefPhaseConcentrations,
+// QuatModel.cc:5218-5231).  work1/work2: caller-owned vectors shaped like y (work2 only for Heun).
+extern "C" int ampe_integrate_fixed(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs_fields* work1,
+                                    const ampe_rhs_fields* work2, double t0, double dt, int nsteps,
+                                    int scheme, void* stream)
+{
+   if (!c || !y || !work1) return ampe_set_err(AMPE_EINVAL, "null argument");
+   if (scheme != 0 && scheme != 1) return ampe_set_err(AMPE_EINVAL, "scheme: 0 (Euler) or 1 (Heun)");
+   if (scheme == 1 && !work2) return ampe_set_err(AMPE_EINVAL, "Heun needs work2");
+   if (c->have_halo) return ampe_set_err(AMPE_EINVAL, "multi-rank stepping: drive the exchange from the caller");
+   const Params& p = c->p;
+   cudaStream_t st = (cudaStream_t)stream;
+   Comp vy, v1;
+   int rc = components(c, work1, nullptr, const_cast<ampe_rhs_fields*>(y), vy);
+   if (rc) return rc;
+   const bool kks = p.conc_form == AMPE_CONC_KKS || p.conc_form == AMPE_CONC_EBS;
+   double t = t0;
+   for (int s = 0; s < nsteps; s++) {
+      rc = ampe_rhs_eval(c, t, y, work1, 0, stream);
+      if (rc) return rc;
+      if (scheme == 0) {
+         for (int n = 0; n < vy.n; n++)
+            axpy_kernel<<<grid_for(vy.len[n]), VT, 0, st>>>(dt, vy.x[n], vy.z[n], vy.len[n]);
+      } else {
+         // work2 <- y + dt k1 (all components, the non-evolved ones copied)
+         ampe_rhs_fields ystar = *work2;
+         Comp vs;
+         rc = components(c, y, work1, &ystar, vs);
+         if (rc) return rc;
+         for (int n = 0; n < vs.n; n++)
+            linear_sum_kernel<<<grid_for(vs.len[n]), VT, 0, st>>>(1.0, vs.x[n], dt, vs.y[n], vs.z[n], vs.len[n]);
+         if (p.qlen > 0 && !p.evolve_quat)
+            CUDA_OKV(cudaMemcpyAsync(ystar.quat, y->quat, sizeof(double) * c->ncell * p.qlen,
+                                     cudaMemcpyDeviceToDevice, st));
+         // y += dt/2 k1 now; k2 overwrites work1 afterwards
+         for (int n = 0; n < vy.n; n++)
+            axpy_kernel<<<grid_for(vy.len[n]), VT, 0, st>>>(0.5 * dt, vy.x[n], vy.z[n], vy.len[n]);
+         rc = ampe_rhs_eval(c, t + dt, &ystar, work1, 0, stream);
+         if (rc) return rc;
+         for (int n = 0; n < vy.n; n++)
+            axpy_kernel<<<grid_for(vy.len[n]), VT, 0, st>>>(0.5 * dt, vy.x[n], vy.z[n], vy.len[n]);
+      }
+      if (p.evolve_quat) {
+         rc = ampe_normalize_quat(c, y, stream);
+         if (rc) return rc;
+      }
+      if (kks && p.free_energy == AMPE_FE_CALPHAD) {
+         rc = ampe_rhs_set_ref_concentrations(c, nullptr, nullptr, stream);
+         if (rc) return rc;
+      }
+      t += dt;
+   }
+   CUDA_OKV(cudaGetLastError());
+   (void)v1;
+   return AMPE_OK;
+}

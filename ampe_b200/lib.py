@@ -55,6 +55,23 @@ def load():
     L.ampe_rhs_newton_failures.argtypes = [vp, vp]
     L.ampe_rhs_last_launch_count.restype = ci
     L.ampe_rhs_last_launch_count.argtypes = [vp]
+    pd = C.POINTER(C.c_double)
+    L.ampe_vec_linear_sum.restype = ci
+    L.ampe_vec_linear_sum.argtypes = [vp, dbl, pf, dbl, pf, pf, vp]
+    L.ampe_vec_scale.restype = ci
+    L.ampe_vec_scale.argtypes = [vp, dbl, pf, pf, vp]
+    L.ampe_vec_dot.restype = ci
+    L.ampe_vec_dot.argtypes = [vp, pf, pf, pd, vp]
+    L.ampe_vec_wrms_norm.restype = ci
+    L.ampe_vec_wrms_norm.argtypes = [vp, pf, pf, pd, vp]
+    L.ampe_vec_max_norm.restype = ci
+    L.ampe_vec_max_norm.argtypes = [vp, pf, pd, vp]
+    L.ampe_normalize_quat.restype = ci
+    L.ampe_normalize_quat.argtypes = [vp, pf, vp]
+    L.ampe_integrate_fixed.restype = ci
+    L.ampe_integrate_fixed.argtypes = [vp, pf, pf, pf, dbl, dbl, ci, ci, vp]
+    L.ampe_energy_eval.restype = ci
+    L.ampe_energy_eval.argtypes = [vp, pf, pd, vp]
     L.ampe_last_error.restype = C.c_char_p
     L.ampe_version.restype = C.c_char_p
     L.ampe_abi_sizeof_config.restype = ci

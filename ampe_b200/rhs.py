@@ -112,6 +112,56 @@ class QuatIntegratorRHS:
               "evaluateRHSFunctionHost")
         return 0
 
+    # ---- device vector operations, normalizeQuat, fixed-step integrator, energy
+    def linearSum(self, a, x, b, y, z):
+        """z = a x + b y on the evolved components (Sundials_SAMRAIVector::linearSum)"""
+        fx, fy, fz = x.fields(), y.fields(), z.fields()
+        check(self.L.ampe_vec_linear_sum(self.h, float(a), C.byref(fx), float(b), C.byref(fy), C.byref(fz),
+                                         self._stream()), "linearSum")
+
+    def scale(self, a, x, z):
+        fx, fz = x.fields(), z.fields()
+        check(self.L.ampe_vec_scale(self.h, float(a), C.byref(fx), C.byref(fz), self._stream()), "scale")
+
+    def _reduce(self, fn, *vecs):
+        out = C.c_double(0.0)
+        fs = [v.fields() for v in vecs]
+        check(fn(self.h, *[C.byref(f) for f in fs], C.byref(out), self._stream()), fn.__name__)
+        return out.value
+
+    def dotWith(self, x, y):
+        return self._reduce(self.L.ampe_vec_dot, x, y)
+
+    def weightedRMSNorm(self, x, w):
+        return self._reduce(self.L.ampe_vec_wrms_norm, x, w)
+
+    def maxNorm(self, x):
+        return self._reduce(self.L.ampe_vec_max_norm, x)
+
+    def normalizeQuat(self, y):
+        """QuatModel::normalizeQuat (QuatModel.cc:4222-4262)"""
+        fy = y.fields()
+        check(self.L.ampe_normalize_quat(self.h, C.byref(fy), self._stream()), "normalizeQuat")
+
+    def integrateFixed(self, y, dt, nsteps, scheme=0, t0=0.0):
+        """nsteps explicit steps of size dt on the device, y updated in place"""
+        w1 = y.like()
+        w2 = y.like() if scheme == 1 else None
+        fy, f1 = y.fields(), w1.fields()
+        f2 = w2.fields() if w2 is not None else None
+        check(self.L.ampe_integrate_fixed(self.h, C.byref(fy), C.byref(f1),
+                                          C.byref(f2) if f2 is not None else None, float(t0), float(dt),
+                                          int(nsteps), int(scheme), self._stream()), "integrateFixed")
+        torch.cuda.current_stream().synchronize()  # work vectors are released on return
+
+    def evaluateEnergy(self, y):
+        """QuatModel::evaluateEnergy: dict of total / phase / orient / qint / well / free"""
+        out = (C.c_double * 8)()
+        fy = y.fields()
+        check(self.L.ampe_energy_eval(self.h, C.byref(fy), out, self._stream()), "evaluateEnergy")
+        names = ("total", "phase", "orient", "qint", "well", "free")
+        return {k: out[i] for i, k in enumerate(names)}
+
     def phaseConcentrations(self):
         """copies of the ctx-owned c_l, c_a (ghost-0) after an evaluation"""
         cl = torch.empty(self.ncell, dtype=torch.float64, device=self.device)

@@ -201,6 +201,35 @@ int ampe_rhs_last_launch_count(const ampe_rhs_ctx* ctx);
 int ampe_rhs_eval_host(ampe_rhs_ctx* ctx, double time, const ampe_rhs_fields* y_host,
                        const ampe_rhs_fields* ydot_host, int fd_flag);
 
+/* ---- device-resident vector operations on the evolved components of the
+ * solution vector -- the N_Vector operations CVODE calls (samrai/Sundials_SAMRAIVector.cc:
+ * linearSum, scale, dotWith, weightedRMSNorm, maxNorm).  Reductions return to the host and
+ * synchronise the stream; this rank's cells only.                                          */
+int ampe_vec_linear_sum(ampe_rhs_ctx* ctx, double a, const ampe_rhs_fields* x, double b,
+                        const ampe_rhs_fields* y, const ampe_rhs_fields* z, void* stream);
+int ampe_vec_scale(ampe_rhs_ctx* ctx, double a, const ampe_rhs_fields* x,
+                   const ampe_rhs_fields* z, void* stream);
+int ampe_vec_dot(ampe_rhs_ctx* ctx, const ampe_rhs_fields* x, const ampe_rhs_fields* y,
+                 double* result, void* stream);
+int ampe_vec_wrms_norm(ampe_rhs_ctx* ctx, const ampe_rhs_fields* x, const ampe_rhs_fields* w,
+                       double* result, void* stream);
+int ampe_vec_max_norm(ampe_rhs_ctx* ctx, const ampe_rhs_fields* x, double* result, void* stream);
+/* QuatModel::normalizeQuat (QuatModel.cc:4222-4262): q <- q/|q| per cell, in place.        */
+int ampe_normalize_quat(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, void* stream);
+/* Fixed-step explicit integrator keeping y on the device (scheme 0 forward Euler, 1 Heun):
+ * stand-in for the CVODE loop of QuatIntegrator::Advance in trajectory tests; after each step
+ * normalizeQuat and, for CALPHAD, resetRefPhaseConcentrations.  work1 (and work2 for Heun) are
+ * caller-owned vectors shaped like y.                                                      */
+int ampe_integrate_fixed(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, const ampe_rhs_fields* work1,
+                         const ampe_rhs_fields* work2, double t0, double dt, int nsteps, int scheme,
+                         void* stream);
+/* ---- QuatModel::evaluateEnergy (QuatModel.cc:4888-4976) ->
+ * quatenergy / bulkenergy ({2d,3d}/quatenergy.m4).  out[8] = total, phase interface,
+ * orientational, q interface, double well, bulk free energy, 0, 0 (host array).  For the
+ * Cahn-Hilliard model (no evaluator in the reference) the PFHub-1a functional
+ * sum [w (c-ca)^2 (cb-c)^2 + kappa/2 |grad c|^2] dV: out[0] total, [1] gradient, [4] well.   */
+int ampe_energy_eval(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, double* out, void* stream);
+
 const char* ampe_last_error(void);
 const char* ampe_version(void);
 /* sizeof(ampe_rhs_config) as compiled, for binding sanity checks */

@@ -23,6 +23,7 @@ void oracle_get_phase_concentrations(void* c, double* cl, double* ca)
 {
    get_phase_concentrations((Ctx*)c, cl, ca);
 }
+int oracle_energy(void* c, const ampe_rhs_fields* y, double* out) { return energy((Ctx*)c, y, out); }
 int oracle_abi_sizeof_config() { return (int)sizeof(ampe_rhs_config); }
 int oracle_num_threads()
 {

@@ -49,4 +49,7 @@ void add_driving_force(Ctx* c);
 void set_diffusion_coeff_for_concentration(Ctx* c);
 void compute_conc_flux_kks_ebs(Ctx* c);
 
+// scalar energy diagnostics (energy.cc)
+int energy(Ctx* c, const ampe_rhs_fields* y, double* out);
+
 }  // namespace oracle

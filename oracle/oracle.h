@@ -209,6 +209,8 @@ void set_rotations(Ctx*, const int* const* iqrot);
 // y / ydot: ghost-0 host arrays.  Returns 0, or -3 if a Newton failed.
 int eval(Ctx*, double time, const ampe_rhs_fields* y, const ampe_rhs_fields* ydot,
          int fd_flag);
+// scalar energy diagnostics (energy.cc): out[8] = total, phi, orient, qint, well, free, 0, 0
+int energy(Ctx* c, const ampe_rhs_fields* y, double* out);
 void get_phase_concentrations(Ctx*, double* cl, double* ca);
 
 }  // namespace oracle

@@ -40,6 +40,8 @@ def lib(perf=False):
         L.oracle_eval.argtypes = [C.c_void_p, dbl, C.POINTER(_abi.RhsFields),
                                   C.POINTER(_abi.RhsFields), C.c_int]
         L.oracle_get_phase_concentrations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_energy.restype = C.c_int
+        L.oracle_energy.argtypes = [C.c_void_p, C.POINTER(_abi.RhsFields), C.c_void_p]
         for f in ("interp_func", "deriv_interp_func", "second_deriv_interp_func", "well_func",
                   "deriv_well_func"):
             fn = getattr(L, "oracle_" + f)
@@ -130,6 +132,12 @@ class Oracle:
         fy, fd = _fields(y), _fields(ydot)
         st = self.L.oracle_eval(self.h, float(time), C.byref(fy), C.byref(fd), int(fd_flag))
         return st, ydot
+
+    def energy(self, y):
+        """QuatModel::evaluateEnergy: (status, [total, phi, orient, qint, well, free, 0, 0])"""
+        out = np.zeros(8)
+        st = self.L.oracle_energy(self.h, C.byref(_fields(y)), _ptr(out))
+        return st, out
 
     def phase_concentrations(self):
         cl = np.zeros(self.ncell)

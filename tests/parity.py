@@ -129,3 +129,91 @@ def compare(name, cfg, st, fd_flags=(0,), rotations=None):
         errs["cl"] = rel_err(g_extra[0], o_extra[0])
         errs["ca"] = rel_err(g_extra[1], o_extra[1])
     return errs
+
+
+# ---- fixed-step trajectories (north_star: field trajectories within 1e-8 after 100 steps) ----
+# Explicit Euler step sizes per small case: about 1/5 of the empirical stability limit of the
+# stiffest term on these grids (found with the oracle, tools/find_stable_dt.py).
+TRAJ_DT = {
+    "pfhub1a": 5.0e-3,     # limit ~2e-2
+    "dendrite2d": 1.0e-9,  # limit ~5e-9 (singular orientation diffusivity 1/|grad q|)
+    "auni2d": 5.0e-11,     # limit ~2e-10
+    "gg3d_hbsm": 2.0e-8,   # limit ~1e-7
+    "auni3d": 1.0e-10,     # limit ~5e-10
+}
+
+
+def normalize_quat_np(q):
+    """QuatModel::normalizeQuat (QuatModel.cc:4237-4262), same operation order"""
+    n2 = np.zeros_like(q[0])
+    for m in range(q.shape[0]):
+        n2 = n2 + q[m] * q[m]
+    inv = 1.0 / np.sqrt(n2)
+    return q * inv[None]
+
+
+def oracle_trajectory(cfg, st, dt, nsteps, rotations=None, energy_every=0, scheme=0):
+    """forward Euler (scheme 0) / Heun (1) with the CPU oracle; mirrors ampe_integrate_fixed"""
+    from oracle import pyoracle
+    y = {k: (None if v is None else v.numpy().copy()) for k, v in st.items()}
+    o = pyoracle.Oracle(cfg)
+    kks = cfg.conc_rhs_form in (2, 3)
+    if kks:
+        o.set_ref(y["conc"].ravel().copy(), y["conc"].ravel().copy())
+    if cfg.symmetry_aware:
+        o.set_rotations(rotations)
+    evolved = [k for k in ("phase", "quat", "conc", "temperature")
+               if y.get(k) is not None and not (k == "quat" and not cfg.evolve_quat)
+               and not (k == "temperature" and not cfg.with_unsteady_temperature)]
+    energies = []
+    for s in range(nsteps):
+        if energy_every and s % energy_every == 0:
+            energies.append(o.energy(y)[1].copy())
+        status, k1 = o.eval(0.0, y, 0)
+        assert status == 0
+        if scheme == 0:
+            for k in evolved:
+                y[k] = y[k] + dt * k1[k]
+        else:
+            ys = dict(y)
+            for k in evolved:
+                ys[k] = 1.0 * y[k] + dt * k1[k]
+                y[k] = y[k] + (0.5 * dt) * k1[k]
+            status, k2 = o.eval(0.0, ys, 0)
+            assert status == 0
+            for k in evolved:
+                y[k] = y[k] + (0.5 * dt) * k2[k]
+        if cfg.evolve_quat and cfg.qlen > 1:
+            q = y["quat"]
+            y["quat"] = np.ascontiguousarray(normalize_quat_np(q.reshape(cfg.qlen, -1)).reshape(q.shape))
+        if kks and cfg.free_energy == 2:
+            o.set_ref(None, None)
+    if energy_every:
+        energies.append(o.energy(y)[1].copy())
+    o.close()
+    return y, energies
+
+
+def gpu_trajectory(cfg, st, dt, nsteps, rotations=None, energy_every=0, scheme=0):
+    from ampe_b200 import rhs
+    y = rhs.to_device(st)
+    r = rhs.QuatIntegratorRHS(cfg)
+    if cfg.conc_rhs_form in (2, 3):
+        c0 = y["conc"].reshape(-1).clone()
+        r.resetRefPhaseConcentrations(c0, c0.clone())
+    if cfg.symmetry_aware:
+        r.setSymmetryRotations([torch.as_tensor(a).cuda() for a in rotations])
+    energies = []
+    if energy_every:
+        for s in range(0, nsteps, energy_every):
+            energies.append(r.evaluateEnergy(y))
+            r.integrateFixed(y, dt, min(energy_every, nsteps - s), scheme)
+        energies.append(r.evaluateEnergy(y))
+    else:
+        r.integrateFixed(y, dt, nsteps, scheme)
+    torch.cuda.synchronize()
+    out = {k: (None if v is None else v.cpu().numpy()) for k, v in y.items()}
+    if cfg.conc_rhs_form in (2, 3):
+        assert r.newtonFailures() == 0
+    r.close()
+    return out, energies
