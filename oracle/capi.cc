@@ -34,6 +34,16 @@ int oracle_num_threads()
 #endif
 }
 
+// torchrun exports OMP_NUM_THREADS=1; the CPU baseline asks for the host's cores explicitly
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+   if (n > 0) omp_set_num_threads(n);
+#else
+   (void)n;
+#endif
+}
+
 // ---- pointwise (functions.f / quat.f) ----
 double oracle_interp_func(double phi, char t) { return interp_func(phi, t); }
 double oracle_deriv_interp_func(double phi, char t) { return deriv_interp_func(phi, t); }

@@ -19,7 +19,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, ndim, ng, q):
+def _worker(rank, world, port, ndim, ng, q, mode=None):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -41,7 +41,7 @@ def _worker(rank, world, port, ndim, ng, q):
         sl = slice(rank * nzl, (rank + 1) * nzl)
         y = SolutionVector({k: (None if v is None else slab_planes(v, ndim, sl).contiguous())
                             for k, v in glob.items()})
-        h = SlabHalo(ndim, ng, rank, world)
+        h = SlabHalo(ndim, ng, rank, world, mode=mode)
         h.finish(h.start(y))
         ntot = nzl * world
         for k, v in glob.items():
@@ -68,12 +68,14 @@ def _worker(rank, world, port, ndim, ng, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,ndim,ng", [(2, 2, 1), (2, 3, 1), (3, 3, 1), (2, 2, 2)])
-def test_slab_halo_exchange(world, ndim, ng):
+@pytest.mark.parametrize("world,ndim,ng,mode", [(2, 2, 1, "p2p"), (2, 3, 1, "p2p"), (3, 3, 1, "p2p"),
+                                                (2, 2, 2, "p2p"), (2, 2, 1, "allgather"),
+                                                (3, 3, 1, "allgather"), (2, 2, 2, None)])
+def test_slab_halo_exchange(world, ndim, ng, mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, ndim, ng, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ndim, ng, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in range(world)]
