@@ -6,7 +6,7 @@ int dispatch3_fixed_dendrite(const FusedArgs& A, cudaStream_t st, const char** e
 {
    const Params& p = A.p;
    if (p.ndim == 2 && p.qlen == 2 && p.conc_form == 0 && p.with_T && !p.symm && sel_matches<SelDendrite>(p)) {
-      *rc = launch3<2, 2, 0, false, true, SelDendrite>(A, st, err);
+      *rc = launch_any<2, 2, 0, false, true, SelDendrite>(A, st, err);
       return 1;
    }
    return 0;

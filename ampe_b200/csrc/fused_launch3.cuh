@@ -7,6 +7,7 @@
 #include "energy_tile.cuh"
 #include "rhs_march.cuh"
 #include "rhs_tile.cuh"
+#include "rhs_tile_tma.cuh"
 #include "tile_shape.h"
 
 namespace ampe {
@@ -36,6 +37,59 @@ static int launch_energy(const FusedArgs& A, cudaStream_t st, const char** err)
       grid.z = (nslab + TT::TZ - 1) / TT::TZ;
    }
    kern<<<grid, TT::NT, TT::SMEM_BYTES, st>>>(A);
+   cudaError_t e2 = cudaGetLastError();
+   if (e2 != cudaSuccess) {
+      *err = cudaGetErrorString(e2);
+      return AMPE_ECUDA;
+   }
+   return AMPE_OK;
+}
+
+bool tma_enabled();
+int tma_encode_3d(CUtensorMap* out, const double* base, unsigned long long n0, unsigned long long rows,
+                  unsigned long long depth, unsigned long long comp_stride, unsigned box0, unsigned box1);
+
+// 2D persistent kernel with TMA staging (rhs_tile_tma.cuh).  Returns -1 when this evaluation
+// cannot use it (odd row length, misaligned arrays, no driver entry point): the caller then
+// launches the cp.async tile kernel.
+template <int Q, int CONC, bool WT, class SEL>
+static int launch_tma(const FusedArgs& A, cudaStream_t st, const char** err)
+{
+   using TT = Tile3<2, Q, CONC, false, WT, SEL, 32, AMPE_TMA_TY, 1, AMPE_TMA_NT, 2>;
+   using TM = TmaTile<TT>;
+   const Params& p = A.p;
+   const int nslab = A.s_end - A.s_begin;
+   if (nslab <= 0) return AMPE_OK;
+   if (!tma_enabled()) return -1;
+   const unsigned long long n0 = p.n[0], ns = p.n[1], ncell = n0 * ns;
+   TmaMaps M;
+   int bad = tma_encode_3d(&M.phi, A.phi.base, n0, ns, 1, ncell, TT::SX, TT::SY);
+   if (WT) bad |= tma_encode_3d(&M.T, A.T.base, n0, ns, 1, ncell, TT::SX, TT::SY);
+   if (Q > 0) bad |= tma_encode_3d(&M.q, A.q.base, n0, ns, Q, (unsigned long long)A.q.comp, TT::SX, TT::SY);
+   if (CONC == AMPE_CONC_KKS) bad |= tma_encode_3d(&M.conc, A.conc.base, n0, ns, 1, ncell, TT::SX, TT::SY);
+   if (CONC != 0) {
+      bad |= tma_encode_3d(&M.cl, A.cl, n0, ns + 2, 1, ncell, TT::SX, TT::SY);
+      bad |= tma_encode_3d(&M.ca, A.ca, n0, ns + 2, 1, ncell, TT::SX, TT::SY);
+   }
+   if (bad) return -1;
+   auto kern = rhs_tile_tma_kernel<TT>;
+   static int resident = 0;  // persistent grid: resident blocks per SM x SMs
+   if (!resident) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM::SMEM_BYTES);
+      int per_sm = 0, dev = 0, sms = 0;
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TT::NT, TM::SMEM_BYTES);
+      if (e == cudaSuccess) e = cudaGetDevice(&dev);
+      if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (e != cudaSuccess || per_sm < 1) {
+         (void)cudaGetLastError();
+         return -1;
+      }
+      resident = per_sm * sms;
+   }
+   const int tiles_x = (p.n[0] + TT::TX - 1) / TT::TX;
+   const int ntiles = tiles_x * ((nslab + TT::TY - 1) / TT::TY);
+   const int grid = ntiles < resident ? ntiles : resident;
+   kern<<<grid, TT::NT, TM::SMEM_BYTES, st>>>(A, M, tiles_x, ntiles);
    cudaError_t e2 = cudaGetLastError();
    if (e2 != cudaSuccess) {
       *err = cudaGetErrorString(e2);
@@ -126,8 +180,13 @@ static int launch_any(const FusedArgs& A, cudaStream_t st, const char** err)
    if constexpr (ND == 3 && !SYMM) {
       return launch_march<Q, CONC, WT, SEL>(A, st, err);
    }
-   else
+   else {
+      if constexpr (ND == 2 && !SYMM) {
+         const int rc = launch_tma<Q, CONC, WT, SEL>(A, st, err);
+         if (rc >= 0) return rc;
+      }
       return launch3<ND, Q, CONC, SYMM, WT, SEL>(A, st, err);
+   }
 }
 
 // runtime-selector instantiations of one (NDIM, qlen): every composition form, symmetry for qlen 4

@@ -17,14 +17,19 @@
 namespace ampe {
 
 // ---- tile geometry + shared-memory carve-up -----------------------------------------------
-template <int ND_, int Q_, int CONC_, bool SYMM_, bool WT_, class SEL_, int TX_, int TY_, int TZ_, int NT_>
+// XH: staged halo width in x.  1 is what the stencils need; the TMA kernel stages 2 so that every
+// box starts on an even column (cp.async.bulk.tensor faults on a box start that is not 16-byte
+// aligned: measured, tools/probe/tma_probe3.cu).
+template <int ND_, int Q_, int CONC_, bool SYMM_, bool WT_, class SEL_, int TX_, int TY_, int TZ_, int NT_, int XH_ = 1>
 struct Tile3 {
    static constexpr int ND = ND_, Q = Q_, CONC = CONC_, TX = TX_, TY = TY_, TZ = TZ_, NT = NT_;
    static constexpr bool SYMM = SYMM_, WT = WT_;
    using SEL = SEL_;
    static constexpr int HZ = (ND == 3) ? 1 : 0;
-   static constexpr int SX = TX + 2, SY = TY + 2, SZ = TZ + 2 * HZ;
-   static constexpr int S = SX * SY * SZ;
+   static constexpr int XH = XH_;
+   static constexpr int SX = TX + 2 * XH, SY = TY + 2, SZ = TZ + 2 * HZ;
+   // doubles per staged field, padded to 128 B: a TMA box may land on every field
+   static constexpr int S = (SX * SY * SZ + 15) / 16 * 16;
    static constexpr int FX = TX + 1, FY = TY + 1, FZ = TZ + HZ;
    static constexpr int NFB = FX * FY * FZ;
    static constexpr int NW = NT / 32;          // warps
@@ -45,10 +50,12 @@ struct Tile3 {
    static constexpr int O_CF = O_PF + (HAS_PF ? ND * NFB : 0);
    static constexpr int O_END = O_CF + (CONC != 0 ? ND * NFB : 0);
    static constexpr size_t SMEM_BYTES = (size_t)O_END * sizeof(double) + (SYMM ? (size_t)ND * S * sizeof(int) : 0);
+   // the same face arrays relative to O_FC (kernels that keep them outside the staged fields)
+   static constexpr int F_FC = 0, F_PF = O_PF - O_FC, F_CF = O_CF - O_FC, F_END = O_END - O_FC;
    // staged strides / face-box strides per direction
    __host__ __device__ static constexpr int str(int a) { return a == 0 ? 1 : (a == 1 ? SX : SX * SY); }
    __host__ __device__ static constexpr int ftr(int a) { return a == 0 ? 1 : (a == 1 ? FX : FX * FY); }
-   AMPE_DEV static int sidx(int i, int j, int k) { return (i + 1) + SX * ((j + 1) + SY * (k + HZ)); }
+   AMPE_DEV static int sidx(int i, int j, int k) { return (i + XH) + SX * ((j + 1) + SY * (k + HZ)); }
    AMPE_DEV static int fidx(int i, int j, int k) { return i + FX * (j + FY * k); }
 };
 
@@ -66,13 +73,13 @@ AMPE_DEV void stage_tile(const FusedArgs& A, double* s, int* s_iq, int ox, int o
    const long long plane = (ND == 3) ? (long long)n0 * n1 : (long long)n0;
    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
    (void)n1;
-   // A staged row has SX = 34 elements: one warp copies x = 0..31 of a row per instruction,
-   // the two tail elements of all rows are gathered into one extra pass of the block.
+   // A staged row has SX = 32 + 2 XH elements: one warp copies x = 0..31 of a row per instruction,
+   // the tail elements of all rows are gathered into one extra pass of the block.
    {
       constexpr int NROWS = TT::SY * TT::SZ;
       // element (row r, staged x) of every staged field
       auto copy_elem = [&](int r, int xs) {
-         int gx = (ox - 1 + xs) % n0;
+         int gx = (ox - TT::XH + xs) % n0;
          gx = (gx < 0) ? gx + n0 : gx;
          const int lj = r % TT::SY - 1;
          const int lk = (ND == 3) ? (r / TT::SY - 1) : 0;
@@ -126,42 +133,28 @@ AMPE_DEV void stage_tile(const FusedArgs& A, double* s, int* s_iq, int ox, int o
 #pragma unroll 1
       for (int r = warp; r < NROWS; r += NW) copy_elem(r, lane);
 #pragma unroll 1
-      for (int t = threadIdx.x; t < 2 * NROWS; t += NT) copy_elem(t >> 1, 32 + (t & 1));
+      for (int t = threadIdx.x; t < (TT::SX - 32) * NROWS; t += NT) copy_elem(t / (TT::SX - 32), 32 + t % (TT::SX - 32));
       cp_async_wait_all();
    }
 }
 
+// ---- (B) faces + (C) cells of one staged tile ------------------------------------------------
+// s: staged fields (Tile3 offsets), sf: face arrays (F_FC / F_PF / F_CF), origin (ox, oy, oz).
+// Ends with the cells' global stores; the caller synchronises before s / sf are reused.
 template <class TT>
-__global__ void __launch_bounds__(TT::NT) rhs_tile_kernel(const __grid_constant__ FusedArgs A)
+AMPE_DEV void tile_compute(const FusedArgs& A, const double* s, double* sf, const int* s_iq,
+                           const double (*s_qr)[4], const int* s_conj, int ox, int oy, int oz)
 {
    using R = Rhs3<TT>;
    using SEL = typename TT::SEL;
-   constexpr int ND = TT::ND, Q = TT::Q, CONC = TT::CONC, S = TT::S, NT = TT::NT, NW = TT::NW;
+   constexpr int ND = TT::ND, Q = TT::Q, CONC = TT::CONC, NT = TT::NT, NW = TT::NW;
    constexpr int TX = TT::TX, TY = TT::TY, TZ = TT::TZ, CPT = TT::CPT;
-   constexpr bool SYMM = TT::SYMM, WT = TT::WT;
    const Params& p = A.p;
-   extern __shared__ double smem[];
-   double* s = smem;
-   int* s_iq = reinterpret_cast<int*>(smem + TT::O_END);  // ND*S ints (SYMM)
-   __shared__ double s_qr[SYMM ? 48 : 1][4];
-   __shared__ int s_conj[SYMM ? 48 : 1];
-   if (SYMM && Q == 4) {
-      for (int t = threadIdx.x; t < 48 * 4; t += NT) s_qr[t / 4][t % 4] = A.qr[t];
-      for (int t = threadIdx.x; t < 48; t += NT) s_conj[t] = A.conj[t];
-   }
-
-   // ---- tile origin -------------------------------------------------------------
    const int n0 = p.n[0], n1 = p.n[1], n2 = (ND == 3) ? p.n[2] : 1;
    const int ns = (ND == 3) ? n2 : n1;  // planes along the slab axis
-   const int ox = blockIdx.x * TX;
-   const int oy = blockIdx.y * TY + ((ND == 2) ? A.s_begin : 0);
-   const int oz = (ND == 3) ? (blockIdx.z * TZ + A.s_begin) : 0;
    const long long plane = (ND == 3) ? (long long)n0 * n1 : (long long)n0;  // slab plane size
    const long long ncell = (long long)n0 * n1 * n2;
    const int lane = threadIdx.x % 32, warp = threadIdx.x / 32;
-
-   stage_tile<TT>(A, s, s_iq, ox, oy, oz);
-   __syncthreads();
 
    // rows owned by this warp: r = warp + u*NW; inside a plane the row stride is constant
    constexpr int RSTEP_J = (NW < TY) ? NW : 0;            // rows advance in y ...
@@ -187,9 +180,9 @@ __global__ void __launch_bounds__(TT::NT) rhs_tile_kernel(const __grid_constant_
    auto do_face = [&](auto dir, int c, int f, long long gface, bool inr, bool wr) {
       constexpr int a = decltype(dir)::value;
       const FaceVal v = R::template face<a>(A, s, s_iq, s_qr, s_conj, c, c - TT::str(a), ZT, gface, inr, wr);
-      if (Q > 0) s[TT::O_FC + a * TT::NFB + f] = v.fc;
-      if constexpr (TT::HAS_PF && a < 2) s[TT::O_PF + a * TT::NFB + f] = v.pf;
-      if (CONC != 0) s[TT::O_CF + a * TT::NFB + f] = v.cf;
+      if (Q > 0) sf[TT::F_FC + a * TT::NFB + f] = v.fc;
+      if constexpr (TT::HAS_PF && a < 2) sf[TT::F_PF + a * TT::NFB + f] = v.pf;
+      if (CONC != 0) sf[TT::F_CF + a * TT::NFB + f] = v.cf;
    };
    using D0 = std::integral_constant<int, 0>;
    using D1 = std::integral_constant<int, 1>;
@@ -281,13 +274,13 @@ __global__ void __launch_bounds__(TT::NT) rhs_tile_kernel(const __grid_constant_
 #pragma unroll
             for (int a = 0; a < ND; a++) {
                const int fl = a * TT::NFB + fb, fu = fl + TT::ftr(a);
-               F.fcl[a] = (Q > 0) ? s[TT::O_FC + fl] : 0.0;
-               F.fcu[a] = (Q > 0) ? s[TT::O_FC + fu] : 0.0;
-               F.cfl[a] = (CONC != 0) ? s[TT::O_CF + fl] : 0.0;
-               F.cfu[a] = (CONC != 0) ? s[TT::O_CF + fu] : 0.0;
+               F.fcl[a] = (Q > 0) ? sf[TT::F_FC + fl] : 0.0;
+               F.fcu[a] = (Q > 0) ? sf[TT::F_FC + fu] : 0.0;
+               F.cfl[a] = (CONC != 0) ? sf[TT::F_CF + fl] : 0.0;
+               F.cfu[a] = (CONC != 0) ? sf[TT::F_CF + fu] : 0.0;
                if (a < 2) {
-                  F.pfl[a] = TT::HAS_PF ? s[TT::O_PF + fl] : 0.0;
-                  F.pfu[a] = TT::HAS_PF ? s[TT::O_PF + fu] : 0.0;
+                  F.pfl[a] = TT::HAS_PF ? sf[TT::F_PF + fl] : 0.0;
+                  F.pfu[a] = TT::HAS_PF ? sf[TT::F_PF + fu] : 0.0;
                }
             }
             R::cell(A, s, s_iq, s_qr, s_conj, c, ZT, F, gcell, ncell);
@@ -298,6 +291,34 @@ __global__ void __launch_bounds__(TT::NT) rhs_tile_kernel(const __grid_constant_
          gk += RSTEP_K;
       }
    }
+}
+
+template <class TT>
+__global__ void __launch_bounds__(TT::NT, (TT::NT <= 256) ? (TT::SYMM ? 2 : (TT::SEL::fixed ? 4 : 3)) : 1) rhs_tile_kernel(const __grid_constant__ FusedArgs A)
+{
+   using R = Rhs3<TT>;
+   using SEL = typename TT::SEL;
+   constexpr int ND = TT::ND, Q = TT::Q, CONC = TT::CONC, S = TT::S, NT = TT::NT, NW = TT::NW;
+   constexpr int TX = TT::TX, TY = TT::TY, TZ = TT::TZ, CPT = TT::CPT;
+   constexpr bool SYMM = TT::SYMM, WT = TT::WT;
+   const Params& p = A.p;
+   extern __shared__ double smem[];
+   double* s = smem;
+   int* s_iq = reinterpret_cast<int*>(smem + TT::O_END);  // ND*S ints (SYMM)
+   __shared__ double s_qr[SYMM ? 48 : 1][4];
+   __shared__ int s_conj[SYMM ? 48 : 1];
+   if (SYMM && Q == 4) {
+      for (int t = threadIdx.x; t < 48 * 4; t += NT) s_qr[t / 4][t % 4] = A.qr[t];
+      for (int t = threadIdx.x; t < 48; t += NT) s_conj[t] = A.conj[t];
+   }
+
+   // ---- tile origin -------------------------------------------------------------
+   const int ox = blockIdx.x * TX;
+   const int oy = blockIdx.y * TY + ((ND == 2) ? A.s_begin : 0);
+   const int oz = (ND == 3) ? (blockIdx.z * TZ + A.s_begin) : 0;
+   stage_tile<TT>(A, s, s_iq, ox, oy, oz);
+   __syncthreads();
+   tile_compute<TT>(A, s, s + TT::O_FC, s_iq, s_qr, s_conj, ox, oy, oz);
 }
 
 }  // namespace ampe

@@ -14,3 +14,8 @@
 #define AMPE_MY 8
 #define AMPE_MZ 16
 #endif
+// 2D persistent TMA kernel: tile 32 x AMPE_TMA_TY, AMPE_TMA_NT threads
+#ifndef AMPE_TMA_TY
+#define AMPE_TMA_TY 32
+#define AMPE_TMA_NT 512
+#endif

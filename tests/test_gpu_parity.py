@@ -215,6 +215,42 @@ def test_pipelined_host_entry_point_equals_device_path(name, chunks, monkeypatch
         assert rh.newtonFailures() == 0
 
 
+@pytest.mark.parametrize("name,kw", [("dendrite2d", dict(nx=256, ny=200)), ("auni2d", dict(nx=192, ny=136)),
+                                     ("dendrite2d", dict(nx=130, ny=97))])
+def test_tma_staging_equals_cp_async_staging(name, kw, monkeypatch):
+    """the opt-in persistent TMA kernel (AMPE_B200_TMA=1: interior tiles by cp.async.bulk.tensor,
+    boundary tiles by cp.async) and the default tile kernel produce the same bits: full, lagged and
+    split launches"""
+    from ampe_b200 import rhs
+    cfg, st = parity.make_case(name, **kw)
+    cfg.symmetry_aware = 0
+    y = rhs.to_device(st)
+    outs = {}
+    for mode in ("tma", "cp_async"):
+        if mode == "tma":
+            monkeypatch.setenv("AMPE_B200_TMA", "1")
+        else:
+            monkeypatch.delenv("AMPE_B200_TMA", raising=False)
+        r = rhs.QuatIntegratorRHS(cfg)
+        if cfg.conc_rhs_form in (2, 3):
+            c0 = y["conc"].reshape(-1).clone()
+            r.resetRefPhaseConcentrations(c0, c0.clone())
+        res = []
+        for fd, parts in ((0, (0,)), (1, (0,)), (0, (1, 2))):
+            yd = y.like()
+            for part in parts:
+                r.evaluateRHSFunction(0.0, y, yd, fd, part=part)
+            res.append(yd)
+        torch.cuda.synchronize()
+        outs[mode] = res
+        r.close()
+    for a, b in zip(outs["tma"], outs["cp_async"]):
+        for k, v in a.items():
+            if v is not None and not (k == "quat" and not cfg.evolve_quat):
+                assert torch.isfinite(v).all(), k
+                assert torch.equal(v, b[k]), (name, k)
+
+
 def test_split_evaluation_equals_full():
     """interior + boundary launches (used to overlap the halo exchange) == one full launch"""
     from ampe_b200 import rhs
