@@ -11,7 +11,11 @@ namespace ampe {
 
 #define AMPE_DEV __device__ __forceinline__
 
-AMPE_DEV double clamp01(double x) { return fmax(0.0, fmin(1.0, x)); }
+// max/min as compare + select (the state is never NaN; fmax/fmin expand to 5-7 instructions
+// for their NaN rules, profiles/README.md)
+AMPE_DEV double max0(double x) { return (x > 0.0) ? x : 0.0; }
+AMPE_DEV double min1(double x) { return (x < 1.0) ? x : 1.0; }
+AMPE_DEV double clamp01(double x) { return max0(min1(x)); }
 
 // Rarely selected forms are kept out of line: inlining their log/cosh/tanh expansions at
 // every call site bloated the fused kernel to ~12k SASS lines and showed up as
@@ -21,11 +25,11 @@ static AMPE_DEV_NOINLINE double interp_func_rare(double phi, char type)
 {
    double phit;
    switch (type) {
-      case 'w': phit = fmax(0.0, phi); return phit * phit * (2.0 - phit);
+      case 'w': phit = max0(phi); return phit * phit * (2.0 - phit);
       case 'm':
          phit = clamp01(phi);
          return phit * phit / (2.0 * phit * (phit - 1.0) + 1.0);
-      case '3': phit = fmax(0.0, phi); return phit * phit * phit;
+      case '3': phit = max0(phi); return phit * phit * phit;
       case 's': return log(cosh(10.0 * phi)) / log(cosh(10.0));  // unclamped: functions.f:74-77
       default: return 1.0;  // 'c'
    }
@@ -39,7 +43,7 @@ AMPE_DEV double interp_func(double phi, char type)
       return phit * phit * phit * (10.0 - 15.0 * phit + 6.0 * phit * phit);
    }
    if (type == 'q') {
-      phit = fmax(0.0, phi);
+      phit = max0(phi);
       return phit * phit;
    }
    if (type == 'c') return 1.0;
@@ -48,8 +52,8 @@ AMPE_DEV double interp_func(double phi, char type)
       return phit * phit * (3.0 - 2.0 * phit);
    }
    if (type == 'l') {
-      phit = fmax(0.0, phi);
-      return fmin(1.0, phit);
+      phit = max0(phi);
+      return min1(phit);
    }
    return interp_func_rare(phi, type);
 }
@@ -58,13 +62,13 @@ static AMPE_DEV_NOINLINE double deriv_interp_func_rare(double phi, char type)
 {
    double phit, tmp;
    switch (type) {
-      case 'w': phit = fmax(0.0, phi); return phit * (4.0 - 3.0 * phit);
+      case 'w': phit = max0(phi); return phit * (4.0 - 3.0 * phit);
       case 'm':
          phit = clamp01(phi);
          tmp = 2.0 * phit * (phit - 1.0) + 1.0;
          return 2.0 * phit * (1.0 - phit) / (tmp * tmp);
-      case '3': phit = fmax(0.0, phi); return 3.0 * phit * phit;
-      case 's': phit = fmax(0.0, phi); return 10.0 * tanh(10.0 * phit) / log(cosh(10.0));
+      case '3': phit = max0(phi); return 3.0 * phit * phit;
+      case 's': phit = max0(phi); return 10.0 * tanh(10.0 * phit) / log(cosh(10.0));
       default: return 0.0;  // 'c'
    }
 }
@@ -77,7 +81,7 @@ AMPE_DEV double deriv_interp_func(double phi, char type)
       return 30.0 * phit * phit * (1.0 - phit) * (1.0 - phit);
    }
    if (type == 'q') {
-      phit = fmax(0.0, phi);
+      phit = max0(phi);
       return 2.0 * phit;
    }
    if (type == 'c') return 0.0;

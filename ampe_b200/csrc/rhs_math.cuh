@@ -87,7 +87,7 @@ AMPE_DEV double average3(double a, double b, char type)
 AMPE_DEV double grad_normi3(double g2, char floor_type, double floor2, double max_normi)
 {
    if (floor_type == 'm') {
-      const double r = rsqrt_fast(fmax(g2, floor2));
+      const double r = rsqrt_fast((g2 > floor2) ? g2 : floor2);
       return (g2 > floor2) ? r : max_normi;
    }
    return eval_grad_normi_rare(g2, floor_type, floor2, max_normi);
@@ -119,7 +119,7 @@ AMPE_DEV double ebs_phase_diffusivity(const CalphadT& t, int ph, double c0)
       const double* qq = t.qAB[sp][ph];
       const double poly = fma(dc, fma(dc, fma(dc, qq[3], qq[2]), qq[1]), qq[0]);
       const double dG = fma(cc, poly, fma(c0, t.qA[sp][ph], c1 * t.qB[sp][ph]));
-      m[sp] = exp(dG * t.RTinv);
+      m[sp] = exp_fast(dG * t.RTinv);
    }
    const double mm = fma(c0, m[1], c1 * m[0]) * t.RTinv;
    if (c0 > AMPE_SMALLX && c1 > AMPE_SMALLX) {
@@ -292,7 +292,7 @@ struct Rhs3 {
          const double dphidx = (a == 0) ? dn_ : dt;
          const double dphidy = (a == 0) ? dt : dn_;
          double qa = 0.5 * (s[TT::O_Q + cm] + s[TT::O_Q + c]);
-         qa = fmin(1.0, fmax(-1.0, qa));
+         qa = (qa > 1.0) ? 1.0 : ((qa < -1.0) ? -1.0 : qa);
          double sn, cs;
          if (AMPE_SEL(knumber) == 4 && !AMPE_SEL(libm_trig)) {
             // cos/sin of 4(theta - psi) without atan/acos/sincos: theta = atan(y/x) enters only
