@@ -108,6 +108,54 @@ class QuatIntegrator
       return 0;  // Always successful (QuatIntegrator.cc:3294)
    }
 
+   // ---- what sits around the RHS in the CVODE loop, device resident --------------
+   // Sundials_SAMRAIVector operations on the evolved components (samrai/Sundials_SAMRAIVector.cc)
+   void linearSum(double a, const ampe_rhs_fields* x, double b, const ampe_rhs_fields* y,
+                  const ampe_rhs_fields* z)
+   {
+      check(ampe_vec_linear_sum(d_ctx, a, x, b, y, z, nullptr), "linearSum");
+   }
+   void scale(double a, const ampe_rhs_fields* x, const ampe_rhs_fields* z)
+   {
+      check(ampe_vec_scale(d_ctx, a, x, z, nullptr), "scale");
+   }
+   double dotWith(const ampe_rhs_fields* x, const ampe_rhs_fields* y)
+   {
+      double r = 0.0;
+      check(ampe_vec_dot(d_ctx, x, y, &r, nullptr), "dotWith");
+      return r;
+   }
+   double weightedRMSNorm(const ampe_rhs_fields* x, const ampe_rhs_fields* w)
+   {
+      double r = 0.0;
+      check(ampe_vec_wrms_norm(d_ctx, x, w, &r, nullptr), "weightedRMSNorm");
+      return r;
+   }
+   double maxNorm(const ampe_rhs_fields* x)
+   {
+      double r = 0.0;
+      check(ampe_vec_max_norm(d_ctx, x, &r, nullptr), "maxNorm");
+      return r;
+   }
+   // QuatModel::normalizeQuat (QuatModel.cc:4222-4262)
+   void normalizeQuat(const ampe_rhs_fields* y) { check(ampe_normalize_quat(d_ctx, y, nullptr), "normalizeQuat"); }
+   // QuatModel::evaluateEnergy (QuatModel.cc:4888-4976): total, phase, orient, qint, well, free
+   void evaluateEnergy(const ampe_rhs_fields* y, double& total_energy, double& total_phase_e,
+                       double& total_orient_e, double& total_qint_e, double& total_well_e,
+                       double& total_free_e)
+   {
+      double e[8];
+      check(ampe_energy_eval(d_ctx, y, e, nullptr), "evaluateEnergy");
+      total_energy = e[0], total_phase_e = e[1], total_orient_e = e[2], total_qint_e = e[3];
+      total_well_e = e[4], total_free_e = e[5];
+   }
+   // fixed-step explicit stand-in for QuatIntegrator::Advance (scheme 0 Euler, 1 Heun)
+   void integrateFixed(const ampe_rhs_fields* y, const ampe_rhs_fields* work1, const ampe_rhs_fields* work2,
+                       double t0, double dt, int nsteps, int scheme)
+   {
+      check(ampe_integrate_fixed(d_ctx, y, work1, work2, t0, dt, nsteps, scheme, nullptr), "integrateFixed");
+   }
+
    std::shared_ptr<Patch> patch() const { return d_patch; }
    ampe_rhs_ctx* fusedContext() const { return d_ctx; }
    int concLId() const { return d_conc_l_id; }
