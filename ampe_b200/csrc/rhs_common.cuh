@@ -5,6 +5,7 @@
 #include "calphad.cuh"
 #include "params.h"
 #include "pointwise.cuh"
+#include "tile_shape.h"
 
 namespace ampe {
 
@@ -113,7 +114,7 @@ struct KksArgs {
 };
 
 template <int ND>
-__global__ void __launch_bounds__(256) kks_kernel(const __grid_constant__ KksArgs A)
+__global__ void __launch_bounds__(256, AMPE_KKS_MINB) kks_kernel(const __grid_constant__ KksArgs A)
 {
    const Params& p = A.p;
    const int n0 = p.n[0], n1 = p.n[1], n2 = (ND == 3) ? p.n[2] : 1;

@@ -16,6 +16,7 @@
 // planes along z (opposite interior planes on one rank, halo buffers on several).
 #pragma once
 #include "rhs_math.cuh"
+#include "tile_shape.h"
 
 namespace ampe {
 
@@ -43,7 +44,7 @@ struct March3 {
 };
 
 template <class TT>
-__global__ void __launch_bounds__(TT::NT, 2) rhs_march_kernel(const __grid_constant__ FusedArgs A)
+__global__ void __launch_bounds__(TT::NT, AMPE_MARCH_MINB) rhs_march_kernel(const __grid_constant__ FusedArgs A)
 {
    using R = Rhs3<TT>;
    using SEL = typename TT::SEL;

@@ -12,10 +12,17 @@
 // 3D plane-marching kernel: column 32 x AMPE_MY, AMPE_MZ planes per block
 #ifndef AMPE_MY
 #define AMPE_MY 8
-#define AMPE_MZ 16
+#define AMPE_MZ 32
 #endif
 // 2D persistent TMA kernel: tile 32 x AMPE_TMA_TY, AMPE_TMA_NT threads
 #ifndef AMPE_TMA_TY
 #define AMPE_TMA_TY 32
 #define AMPE_TMA_NT 512
+#endif
+// resident blocks per SM the register allocation is capped for
+#ifndef AMPE_MARCH_MINB
+#define AMPE_MARCH_MINB 2
+#endif
+#ifndef AMPE_KKS_MINB
+#define AMPE_KKS_MINB 4
 #endif
