@@ -154,6 +154,9 @@ def main():
     ap.add_argument("--workload", default="dendrite2d", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ampe_b200", choices=["ampe_b200", "reference"])
     ap.add_argument("--fd-flag", type=int, default=0)
+    ap.add_argument("--cold-ref", action="store_true",
+                    help="KKS Newton starts from c_l_ref = c_a_ref = c in every evaluation (default: warm start "
+                         "from the converged values, as after QuatModel::Advance)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -162,8 +165,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     kw, bytes_per_cell = WORKLOADS[args.workload]
-    config = {"workload": "%s %s per GPU, uniform periodic grid, fd_flag=%d" % (
-        args.workload, "x".join(str(v) for v in kw.values()), args.fd_flag),
+    config = {"workload": "%s %s per GPU, uniform periodic grid, fd_flag=%d%s" % (
+        args.workload, "x".join(str(v) for v in kw.values()), args.fd_flag,
+        ", cold Newton start" if args.cold_ref else ""),
         "parallelism": "slab%d" % world if world > 1 else "single",
         "l2": "inputs larger than L2 (%.0f MB state per evaluation)" % (
             bytes_per_cell * 1e-6 * eval("*".join(str(v) for v in kw.values())))}
@@ -216,7 +220,9 @@ def main():
         drv.resetRefPhaseConcentrations(c0, c0.clone())
         drv.evaluateRHSFunction(0.0, y, ydot, 0)
         torch.cuda.synchronize()
-        if world > 1:
+        if args.cold_ref:
+            pass  # keep c_l_ref = c_a_ref = c: several Newton iterations per cell and evaluation
+        elif world > 1:
             cl, ca = r.phaseConcentrations()
             drv.resetRefPhaseConcentrations(cl, ca)
         else:
