@@ -384,7 +384,7 @@ extern "C" int ampe_integrate_fixed(ampe_rhs_ctx* c, const ampe_rhs_fields* y, c
    if (c->have_halo) return ampe_set_err(AMPE_EINVAL, "multi-rank stepping: drive the exchange from the caller");
    const Params& p = c->p;
    cudaStream_t st = (cudaStream_t)stream;
-   Comp vy, v1;
+   Comp vy;
    int rc = components(c, work1, nullptr, const_cast<ampe_rhs_fields*>(y), vy);
    if (rc) return rc;
    const bool kks = p.conc_form == AMPE_CONC_KKS || p.conc_form == AMPE_CONC_EBS;
@@ -425,6 +425,5 @@ extern "C" int ampe_integrate_fixed(ampe_rhs_ctx* c, const ampe_rhs_fields* y, c
       t += dt;
    }
    CUDA_OKV(cudaGetLastError());
-   (void)v1;
    return AMPE_OK;
 }
