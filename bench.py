@@ -273,13 +273,16 @@ def main():
     kms = k0.elapsed_time(k1) / args.steps
     achieved = bytes_per_cell * r.ncell / (kms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                "frac": achieved / peaks["hbm_gbs"], "frac_of_nominal_8tbs": achieved / 8000.0,
+                "traffic": None, "peak_kind": peak_kind,
                 "kernel": "one evaluateRHSFunction on one GPU (%d launch(es))" % r.lastLaunchCount(),
                 "algorithmic_bytes_per_cell": bytes_per_cell}
     tr = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
     if os.path.exists(tr):
         try:
-            roofline["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+            tj = json.load(open(tr))
+            roofline["traffic"] = tj.get("dram_bytes_per_launch")
+            roofline["ncu"] = tj.get("ncu")  # FP64 pipe / issue-slot utilisation of the same kernel (offline capture)
         except Exception:
             pass
 
