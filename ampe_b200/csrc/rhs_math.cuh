@@ -60,6 +60,12 @@ using SelAuNi = SelFixed<AMPE_FLUX_SIMPLE, AMPE_FE_CALPHAD, 'p', 'a', 'a'>;     
 using SelHBSM = SelFixed<AMPE_FLUX_SIMPLE, AMPE_FE_QUADRATIC, 'h', 'a', 'a'>;          // tests/TwoGrainsQuadratic
 
 #define AMPE_SEL(name) (SEL::fixed ? SEL::name : p.name)
+// -DAMPE_NO_STREAM_DIFFS keeps all 2*ND*Q quaternion differences of a cell live (A/B builds)
+#ifdef AMPE_NO_STREAM_DIFFS
+#define AMPE_STREAM_DIFFS &&false
+#else
+#define AMPE_STREAM_DIFFS
+#endif
 
 // does the parameter record select exactly the compile-time model SEL?
 template <class SEL>
@@ -402,16 +408,59 @@ struct Rhs3 {
       const double* sp = s + TT::O_PHI;
       const double* sq = s + TT::O_Q;
 
-      // quaternion differences on the lower / upper faces (symmetric ones in SYMM mode)
-      double dlo[ND][QN], dup[ND][QN];
+      // quaternion differences on the lower / upper faces (symmetric ones in SYMM mode).
+      // Without symmetry the cell streams direction by direction: the differences of one
+      // direction feed the gradient modulus and the divergence accumulators div_m right away, so
+      // that only 2Q differences are live instead of 2*ND*Q (the 3D kernel is register-bound).
+      // The accumulation order per component (a = 0, 1, 2) is the reference's either way.
+      constexpr bool STREAM = !SYMM && (Q > 0) AMPE_STREAM_DIFFS;
+      double dlo[STREAM ? 1 : ND][QN], dup[STREAM ? 1 : ND][QN];
+      double divm[QN];
+      double sm_acc = 0.0;
       if constexpr (Q > 0) if (evolve_quat) {
-         qdiff<0>(s, s_iq, s_qr, s_conj, c, c - 1, dlo[0]);
-         qdiff<0>(s, s_iq, s_qr, s_conj, c + 1, c, dup[0]);
-         qdiff<1>(s, s_iq, s_qr, s_conj, c, c - TT::SX, dlo[1]);
-         qdiff<1>(s, s_iq, s_qr, s_conj, c + TT::SX, c, dup[1]);
-         if constexpr (ND == 3) {
-            qdiff<2>(s, s_iq, s_qr, s_conj, c, c + z.m, dlo[ND - 1]);
-            qdiff<2>(s, s_iq, s_qr, s_conj, c + z.p, c, dup[ND - 1]);
+         if constexpr (STREAM) {
+            auto dir = [&](auto dtag, int cu, int cd) {
+               constexpr int a = decltype(dtag)::value;
+               double lo[QN], hi[QN];
+               qdiff<a>(s, s_iq, s_qr, s_conj, c, cd, lo);
+               qdiff<a>(s, s_iq, s_qr, s_conj, cu, c, hi);
+               if (AMPE_SEL(modulus_from_cells)) {
+#pragma unroll
+                  for (int m = 0; m < Q; m++) {
+                     const double g = (hi[m] + lo[m]) * p.p5inv[a];
+                     sm_acc = fma(g, g, sm_acc);
+                  }
+               } else {
+#pragma unroll
+                  for (int m = 0; m < Q; m++) {
+                     const double g = p.dinv[a] * lo[m];
+                     sm_acc = fma(g, g, sm_acc);
+                  }
+#pragma unroll
+                  for (int m = 0; m < Q; m++) {
+                     const double g = p.dinv[a] * hi[m];
+                     sm_acc = fma(g, g, sm_acc);
+                  }
+               }
+#pragma unroll
+               for (int m = 0; m < Q; m++) {
+                  const double fu = F.fcu[a] * (p.dinv[a] * hi[m]);
+                  const double fl = F.fcl[a] * (p.dinv[a] * lo[m]);
+                  divm[m] = (a == 0) ? (fu - fl) * p.dinv[a] : divm[m] + (fu - fl) * p.dinv[a];
+               }
+            };
+            dir(std::integral_constant<int, 0>(), c + 1, c - 1);
+            dir(std::integral_constant<int, 1>(), c + TT::SX, c - TT::SX);
+            if constexpr (ND == 3) dir(std::integral_constant<int, 2>(), c + z.p, c + z.m);
+         } else {
+            qdiff<0>(s, s_iq, s_qr, s_conj, c, c - 1, dlo[0]);
+            qdiff<0>(s, s_iq, s_qr, s_conj, c + 1, c, dup[0]);
+            qdiff<1>(s, s_iq, s_qr, s_conj, c, c - TT::SX, dlo[1]);
+            qdiff<1>(s, s_iq, s_qr, s_conj, c + TT::SX, c, dup[1]);
+            if constexpr (ND == 3) {
+               qdiff<2>(s, s_iq, s_qr, s_conj, c, c + z.m, dlo[ND - 1]);
+               qdiff<2>(s, s_iq, s_qr, s_conj, c + z.p, c, dup[ND - 1]);
+            }
          }
       }
 
@@ -436,38 +485,42 @@ struct Rhs3 {
          if constexpr (Q > 0) if (evolve_quat) {
             // gradient modulus (quatgrad_cell[_symm] + quatgrad_modulus, or from sides compact)
             double sm = 0.0;
-            if (AMPE_SEL(modulus_from_cells)) {
-#pragma unroll
-               for (int a = 0; a < ND; a++) {
-                  double du[QN];
-                  if (SYMM && Q > 1) {
-                     symm_rotate<Q>(dup[a], -s_iq[a * S + c + up(a, z)], du, s_qr, s_conj);
-                  } else {
-#pragma unroll
-                     for (int m = 0; m < Q; m++) du[m] = dup[a][m];
-                  }
-#pragma unroll
-                  for (int m = 0; m < Q; m++) {
-                     const double g = (du[m] + dlo[a][m]) * p.p5inv[a];
-                     sm = fma(g, g, sm);
-                  }
-               }
-               sm = sqrt_fast(sm);
+            if constexpr (STREAM) {
+               sm = AMPE_SEL(modulus_from_cells) ? sqrt_fast(sm_acc) : sqrt_fast(0.5 * sm_acc);
             } else {
+               if (AMPE_SEL(modulus_from_cells)) {
 #pragma unroll
-               for (int a = 0; a < ND; a++) {
+                  for (int a = 0; a < ND; a++) {
+                     double du[QN];
+                     if (SYMM && Q > 1) {
+                        symm_rotate<Q>(dup[a], -s_iq[a * S + c + up(a, z)], du, s_qr, s_conj);
+                     } else {
 #pragma unroll
-                  for (int m = 0; m < Q; m++) {
-                     const double g = p.dinv[a] * dlo[a][m];
-                     sm = fma(g, g, sm);
+                        for (int m = 0; m < Q; m++) du[m] = dup[a][m];
+                     }
+#pragma unroll
+                     for (int m = 0; m < Q; m++) {
+                        const double g = (du[m] + dlo[a][m]) * p.p5inv[a];
+                        sm = fma(g, g, sm);
+                     }
                   }
+                  sm = sqrt_fast(sm);
+               } else {
 #pragma unroll
-                  for (int m = 0; m < Q; m++) {
-                     const double g = p.dinv[a] * dup[a][m];
-                     sm = fma(g, g, sm);
+                  for (int a = 0; a < ND; a++) {
+#pragma unroll
+                     for (int m = 0; m < Q; m++) {
+                        const double g = p.dinv[a] * dlo[a][m];
+                        sm = fma(g, g, sm);
+                     }
+#pragma unroll
+                     for (int m = 0; m < Q; m++) {
+                        const double g = p.dinv[a] * dup[a][m];
+                        sm = fma(g, g, sm);
+                     }
                   }
+                  sm = sqrt_fast(0.5 * sm);
                }
-               sm = sqrt_fast(0.5 * sm);
             }
             const double p1p = deriv_interp_func(phi, AMPE_SEL(orient_interp1));
             rhs = rhs - p.misorientation_factor * temp * p1p * sm;
@@ -508,20 +561,22 @@ struct Rhs3 {
          // rounding.  compute_lambda_flux sums the same face differences scaled by 0.5/h, which
          // is exactly half of 1/h: lambda = -(q.div)/(2|q|^2) bit for bit, and
          // 2 q lambda = -q (q.div)/|q|^2 needs no second accumulation.
-         double divm[QN], qc[QN];
+         double qc[QN];
          double qdiv = 0.0, sumq2 = 0.0;
 #pragma unroll
          for (int m = 0; m < Q; m++) {
             qc[m] = sq[m * S + c];
-            double dv = 0.0;
+            if constexpr (!STREAM) {
+               double dv = 0.0;
 #pragma unroll
-            for (int a = 0; a < ND; a++) {
-               const double fu = F.fcu[a] * (p.dinv[a] * dup[a][m]);
-               const double fl = F.fcl[a] * (p.dinv[a] * dlo[a][m]);
-               dv = (a == 0) ? (fu - fl) * p.dinv[a] : dv + (fu - fl) * p.dinv[a];
+               for (int a = 0; a < ND; a++) {
+                  const double fu = F.fcu[a] * (p.dinv[a] * dup[a][m]);
+                  const double fl = F.fcl[a] * (p.dinv[a] * dlo[a][m]);
+                  dv = (a == 0) ? (fu - fl) * p.dinv[a] : dv + (fu - fl) * p.dinv[a];
+               }
+               divm[m] = dv;
             }
-            divm[m] = dv;
-            qdiv = qdiv + qc[m] * dv;
+            qdiv = qdiv + qc[m] * divm[m];
             sumq2 = sumq2 + qc[m] * qc[m];
          }
          const double lamq = qdiv / sumq2;
