@@ -12,6 +12,13 @@
 
 namespace ampe {
 
+#define AMPE_MAX_DEVICES 64
+static inline int current_device()
+{
+   int dev = 0;
+   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= AMPE_MAX_DEVICES) dev = 0;
+   return dev;
+}
 
 // energy diagnostics on the same tile geometry (energy_tile.cuh)
 template <class TT>
@@ -19,7 +26,9 @@ static int launch_energy(const FusedArgs& A, cudaStream_t st, const char** err)
 {
    const Params& p = A.p;
    auto kern = energy_tile_kernel<TT>;
-   static bool configured = false;
+   // the dynamic shared-memory attribute belongs to the device's context: one flag per device
+   static bool configured_dev[AMPE_MAX_DEVICES] = {};
+   bool& configured = configured_dev[current_device()];
    if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TT::SMEM_BYTES);
       if (e != cudaSuccess) {
@@ -73,7 +82,8 @@ static int launch_tma(const FusedArgs& A, cudaStream_t st, const char** err)
    }
    if (bad) return -1;
    auto kern = rhs_tile_tma_kernel<TT>;
-   static int resident = 0;  // persistent grid: resident blocks per SM x SMs
+   static int resident_dev[AMPE_MAX_DEVICES] = {};  // persistent grid: resident blocks per SM x SMs
+   int& resident = resident_dev[current_device()];
    if (!resident) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM::SMEM_BYTES);
       int per_sm = 0, dev = 0, sms = 0;
@@ -108,7 +118,9 @@ static int launch3(const FusedArgs& A, cudaStream_t st, const char** err)
    using TT = Tile3<ND, Q, CONC, SYMM, WT, SEL, TX, TY, TZ, NT>;
    const Params& p = A.p;
    auto kern = rhs_tile_kernel<TT>;
-   static bool configured = false;
+   // the dynamic shared-memory attribute belongs to the device's context: one flag per device
+   static bool configured_dev[AMPE_MAX_DEVICES] = {};
+   bool& configured = configured_dev[current_device()];
    if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TT::SMEM_BYTES);
       if (e != cudaSuccess) {
@@ -144,7 +156,9 @@ static int launch_march(const FusedArgs& A, cudaStream_t st, const char** err)
    using TT = March3<Q, CONC, WT, SEL, AMPE_MY, AMPE_MZ>;
    const Params& p = A.p;
    auto kern = rhs_march_kernel<TT>;
-   static bool configured = false;
+   // the dynamic shared-memory attribute belongs to the device's context: one flag per device
+   static bool configured_dev[AMPE_MAX_DEVICES] = {};
+   bool& configured = configured_dev[current_device()];
    if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TT::SMEM_BYTES);
       if (e != cudaSuccess) {
