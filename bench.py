@@ -233,6 +233,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    if world > 1:
+        # set-up, before the W warm-up steps: NCCL builds its channels lazily during the first
+        # exchanges (at N=2 a 20-step timing right after 3 evaluations read 0.31 ms/step, the same
+        # code 0.17 ms/step over 100 steps: profiles/README.md)
+        for _ in range(30):
+            drv.evaluateRHSFunction(0.0, y, ydot, 0)
+        barrier()
+        config["setup_evaluations_before_warmup"] = 30
     for _ in range(args.warmup):
         drv.evaluateRHSFunction(0.0, y, ydot, 0)
     if args.fd_flag:
