@@ -304,6 +304,7 @@ extern "C" int ampe_rhs_create(const ampe_rhs_config* cfg, ampe_rhs_ctx** out)
       for (int d = 0; d < p.ndim; d++) {
          const size_t ib = (size_t)slab_ghosted_cells(c) * sizeof(int);
          CUDA_OK(cudaMalloc(&c->iq[d], ib));
+         CUDA_OK(cudaMemset(c->iq[d], 0, ib));  // 0 = "no rotation known yet" (quatfindsymm starts from 1)
       }
    }
    return AMPE_OK;

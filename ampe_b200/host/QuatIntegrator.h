@@ -149,6 +149,25 @@ class QuatIntegrator
       total_energy = e[0], total_phase_e = e[1], total_orient_e = e[2], total_qint_e = e[3];
       total_well_e = e[4], total_free_e = e[5];
    }
+   // QuatIntegrator::applyProjection(time, y, corr, epsProj, err) (QuatIntegrator.cc:3911-3962): CVODE's
+   // projection hook; "Always successful" like the reference.
+   int applyProjection(double time, const ampe_rhs_fields* y, const ampe_rhs_fields* corr, double epsProj,
+                       const ampe_rhs_fields* err)
+   {
+      (void)time;
+      (void)epsProj;
+      check(ampe_apply_projection(d_ctx, y, corr, err, nullptr), "applyProjection");
+      return 0;
+   }
+   // QuatModel::computeSymmetryRotations (QuatModel.cc:4978-5055) and makeQuatFundamental (:5059-5104)
+   void computeSymmetryRotations(const ampe_rhs_fields* y)
+   {
+      check(ampe_rhs_compute_symmetry_rotations(d_ctx, y, nullptr), "computeSymmetryRotations");
+   }
+   void makeQuatFundamental(const ampe_rhs_fields* y)
+   {
+      check(ampe_quat_fundamental(d_ctx, y, nullptr), "makeQuatFundamental");
+   }
    // fixed-step explicit stand-in for QuatIntegrator::Advance (scheme 0 Euler, 1 Heun)
    void integrateFixed(const ampe_rhs_fields* y, const ampe_rhs_fields* work1, const ampe_rhs_fields* work2,
                        double t0, double dt, int nsteps, int scheme)

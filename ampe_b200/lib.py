@@ -72,6 +72,14 @@ def load():
     L.ampe_integrate_fixed.argtypes = [vp, pf, pf, pf, dbl, dbl, ci, ci, vp]
     L.ampe_energy_eval.restype = ci
     L.ampe_energy_eval.argtypes = [vp, pf, pd, vp]
+    L.ampe_apply_projection.restype = ci
+    L.ampe_apply_projection.argtypes = [vp, pf, pf, pf, vp]
+    L.ampe_rhs_compute_symmetry_rotations.restype = ci
+    L.ampe_rhs_compute_symmetry_rotations.argtypes = [vp, pf, vp]
+    L.ampe_rhs_get_symmetry_rotations.restype = ci
+    L.ampe_rhs_get_symmetry_rotations.argtypes = [vp, C.POINTER(vp), vp]
+    L.ampe_quat_fundamental.restype = ci
+    L.ampe_quat_fundamental.argtypes = [vp, pf, vp]
     L.ampe_last_error.restype = C.c_char_p
     L.ampe_version.restype = C.c_char_p
     L.ampe_abi_sizeof_config.restype = ci

@@ -162,6 +162,35 @@ class QuatIntegratorRHS:
         names = ("total", "phase", "orient", "qint", "well", "free")
         return {k: out[i] for i, k in enumerate(names)}
 
+    def applyProjection(self, time, y, corr, epsProj, err):
+        """QuatIntegrator::applyProjection (QuatIntegrator.cc:3911-3962): corr <- 0 except the
+        quaternion part, where y + corr is normalised; err loses its component along q.  Returns 0."""
+        fy, fc, fe = y.fields(), corr.fields(), err.fields()
+        check(self.L.ampe_apply_projection(self.h, C.byref(fy), C.byref(fc), C.byref(fe), self._stream()),
+              "applyProjection")
+        return 0
+
+    def computeSymmetryRotations(self, y):
+        """QuatModel::computeSymmetryRotations (QuatModel.cc:4978-5055): rotation index of every
+        lower face from y['quat'], kept in the context for the symmetry-aware evaluation"""
+        fy = y.fields()
+        check(self.L.ampe_rhs_compute_symmetry_rotations(self.h, C.byref(fy), self._stream()),
+              "computeSymmetryRotations")
+
+    def symmetryRotations(self):
+        """copies of the context's rotation indices: one int32 tensor (ghost 0) per direction"""
+        out = [torch.empty(self.ncell, dtype=torch.int32, device=self.device) for _ in range(self.cfg.ndim)]
+        arr = (C.c_void_p * 3)()
+        for d, t in enumerate(out):
+            arr[d] = t.data_ptr()
+        check(self.L.ampe_rhs_get_symmetry_rotations(self.h, arr, self._stream()), "get_rotations")
+        return out
+
+    def makeQuatFundamental(self, y):
+        """QuatModel::makeQuatFundamental (QuatModel.cc:5059-5104), y['quat'] in place"""
+        fy = y.fields()
+        check(self.L.ampe_quat_fundamental(self.h, C.byref(fy), self._stream()), "makeQuatFundamental")
+
     def phaseConcentrations(self):
         """copies of the ctx-owned c_l, c_a (ghost-0) after an evaluation"""
         cl = torch.empty(self.ncell, dtype=torch.float64, device=self.device)

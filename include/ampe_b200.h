@@ -230,6 +230,26 @@ int ampe_integrate_fixed(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, const ampe
  * sum [w (c-ca)^2 (cb-c)^2 + kappa/2 |grad c|^2] dV: out[0] total, [1] gradient, [4] well.   */
 int ampe_energy_eval(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, double* out, void* stream);
 
+/* ---- the CVODE projection hook.
+ * QuatIntegrator::applyProjection(time, y, corr, epsProj, err) (QuatIntegrator.cc:3911-3962,
+ * CVODEAbstractFunctions.h applyProjection): every evolved component of corr is zeroed; when the
+ * orientation is evolved with qlen > 1, QuatSysSolver::applyProjection -> PROJECT{2,3}D
+ * (QuatFACOps.cc:2395-2434, 3d/quatfacops.m4:1022-1081) makes y + corr a unit quaternion per cell
+ * and removes from err its component along q.  y is not modified; err is updated in place.  */
+int ampe_apply_projection(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, const ampe_rhs_fields* corr,
+                          const ampe_rhs_fields* err, void* stream);
+/* ---- the symmetry pre-pass that produces the inputs of rows a7 / a10.
+ * QuatModel::computeSymmetryRotations (QuatModel.cc:4978-5055 -> QUAT_SYMM_ROTATION,
+ * {2d,3d}/quatrotation.m4:12-89): rotation index of every lower face from y->quat on the periodic
+ * level; kept in the context (same storage as ampe_rhs_set_symmetry_rotations).  The previous
+ * indices seed the search like the reference's in/out SideData<int>; 0 after creation.        */
+int ampe_rhs_compute_symmetry_rotations(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, void* stream);
+/* the context's rotation indices, ghost 0, one caller-owned device array per direction       */
+int ampe_rhs_get_symmetry_rotations(ampe_rhs_ctx* ctx, int* const* iqrot_out, void* stream);
+/* QuatModel::makeQuatFundamental (QuatModel.cc:5059-5104 -> QUAT_FUNDAMENTAL,
+ * quatrotation.m4:93-147): y->quat <- symmetric equivalent closest to the identity, in place.  */
+int ampe_quat_fundamental(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, void* stream);
+
 const char* ampe_last_error(void);
 const char* ampe_version(void);
 /* sizeof(ampe_rhs_config) as compiled, for binding sanity checks */

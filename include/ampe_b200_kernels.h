@@ -197,6 +197,17 @@ int ampe_k_fill_periodic(int ndim, const int* ifirst, const int* ilast, int dept
 /* math::PatchCellDataOpsReal::multiply(dst, a, b, box): dst = a * b on the interior box */
 int ampe_k_cell_multiply(int ndim, const int* ifirst, const int* ilast, const double* a, int nga,
                          const double* b, int ngb, double* dst, int ngdst, void* stream);
+/* ---- quatrotation.m4 / quatfacops.m4: symmetry pre-pass and projection (symmetry.cu) -------- */
+/* QUAT_SYMM_ROTATION (QuatFort.h:319): rot[a] = SideData<int> of axis a, ghost ngrot, IN/OUT   */
+int ampe_k_quat_symm_rotation(int ndim, const int* ifirst, const int* ilast, const double* q, int ngq,
+                              int depth, int* const* rot, int ngrot, void* stream);
+/* QUAT_FUNDAMENTAL (QuatFort.h:331): qlo/qhi = ghost box of the array (passed like the reference) */
+int ampe_k_quat_fundamental(int ndim, const int* ifirst, const int* ilast, double* quat, const int* qlo,
+                            const int* qhi, int depth, void* stream);
+/* PROJECT2D / PROJECT3D (QuatFort.h:883, 1022): lo/hi boxes of q, corr, err as in the reference  */
+int ampe_k_project(int ndim, const int* lo, const int* hi, int depth, const double* q, const int* qlo,
+                   const int* qhi, double* corr, const int* clo, const int* chi, double* err, const int* elo,
+                   const int* ehi, void* stream);
 int ampe_k_fill_periodic_int(int ndim, const int* ifirst, const int* ilast, int axis,
                              const int* src, int* dst, int ng, void* stream);
 

@@ -70,6 +70,12 @@ void oracle_quatsymmrotate(const double* q, int iq, double* qp, int qlen)
 {
    quatsymmrotate(q, iq, qp, qlen);
 }
+// quatfindsymm (quat.f:9-37): returns the rotation index (iq is in/out in the reference)
+int oracle_quatfindsymm(const double* q1, const double* q2, int iq, double* q2p, int qlen)
+{
+   quatfindsymm(q1, q2, &iq, q2p, qlen);
+   return iq;
+}
 void oracle_qr_table4(double* out) { memcpy(out, qr_table4(), 48 * 4 * sizeof(double)); }
 
 // ---- kernel-level wrappers (SAMRAI layouts) for the reference's KATs ----
@@ -82,6 +88,27 @@ static Box mkbox(int ndim, const int* lo, const int* hi)
       b.hi[d] = d < ndim ? hi[d] : 0;
    }
    return b;
+}
+// QUAT_SYMM_ROTATION (QuatFort.h:319), QUAT_FUNDAMENTAL (:331), PROJECT{2,3}D (:883, :1022)
+void oracle_k_quat_symm_rotation(int ndim, const int* lo, const int* hi, double* q, int ngq, int depth,
+                                 int* const* rot, int ngrot)
+{
+   Box b = mkbox(ndim, lo, hi);
+   IView r[3];
+   for (int a = 0; a < ndim; a++) r[a] = make_iview(rot[a], b, a, ngrot);
+   quat_symm_rotation(b, make_view(q, b, -1, ngq, depth), depth, r);
+}
+void oracle_k_quat_fundamental(int ndim, const int* lo, const int* hi, double* q, int ngq, int depth)
+{
+   Box b = mkbox(ndim, lo, hi);
+   quat_fundamental(b, make_view(q, b, -1, ngq, depth), depth);
+}
+void oracle_k_project(int ndim, const int* lo, const int* hi, int depth, double* q, int ngq,
+                      double* corr, int ngc, double* err, int nge)
+{
+   Box b = mkbox(ndim, lo, hi);
+   project(b, depth, make_view(q, b, -1, ngq, depth), make_view(corr, b, -1, ngc, depth),
+           make_view(err, b, -1, nge, depth));
 }
 // QUATDIFFS (QuatFort.h), tests/testGradQ.cc
 void oracle_k_quatdiffs(int ndim, const int* lo, const int* hi, int depth, double* q, int ngq,

@@ -94,6 +94,12 @@ double eval_grad_normi(double grad_norm2, char floor_type, double floor_grad_nor
                        double max_grad_normi);
 const double* qr_table4();  // 48x4, normalised (setqr)
 
+// ---- symmetry pre-pass and CVODE projection hook (symmetry.cc) --------------
+void quatfindsymm(const double* q1, const double* q2, int* iq_io, double* q2_prime, int qlen);
+void quat_symm_rotation(const Box& b, View q, int depth, IView* rot);
+void quat_fundamental(const Box& b, View quat, int depth);
+void project(const Box& b, int depth, View q, View corr, View err);
+
 // ---- quatrhs.m4 ------------------------------------------------------------
 void gradient_flux(const Box& b, const double* h, double epsilon, View phase, View* flux);
 void compute_flux_isotropic(const Box& b, const double* h, double epsilon, View phase,

@@ -57,6 +57,13 @@ def lib(perf=False):
         L.oracle_eval_grad_normi.argtypes = [dbl, C.c_char, dbl, dbl]
         L.oracle_quatsymmrotate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oracle_qr_table4.argtypes = [C.c_void_p]
+        L.oracle_quatfindsymm.restype = C.c_int
+        L.oracle_quatfindsymm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.oracle_k_quat_symm_rotation.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                                  C.c_int, C.POINTER(C.c_void_p), C.c_int]
+        L.oracle_k_quat_fundamental.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.oracle_k_project.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         pdb = C.POINTER(_abi.CalphadBinary)
         for f in ("calphad_free_energy", "calphad_deriv_free_energy",
                   "calphad_second_deriv_free_energy"):
@@ -144,3 +151,41 @@ class Oracle:
         ca = np.zeros(self.ncell)
         self.L.oracle_get_phase_concentrations(self.h, _ptr(cl), _ptr(ca))
         return cl, ca
+
+
+# ---- symmetry pre-pass / projection (oracle/symmetry.cc), SAMRAI layouts ----
+def _ivec(v):
+    return (C.c_int * 3)(*(list(v) + [0] * (3 - len(v))))
+
+
+def quatfindsymm(q1, q2, iq, qlen):
+    """quatfindsymm (quat.f:9-37): (rotation index, rotated q2)"""
+    q1 = np.ascontiguousarray(q1, dtype=np.float64)
+    q2 = np.ascontiguousarray(q2, dtype=np.float64)
+    out = np.zeros(qlen)
+    r = lib().oracle_quatfindsymm(_ptr(q1), _ptr(q2), int(iq), _ptr(out), int(qlen))
+    return r, out
+
+
+def quat_symm_rotation(n, q_ghosted, ngq, depth, rot, ngrot):
+    """QUAT_SYMM_ROTATION on the box [0, n-1]; q_ghosted: (depth, [nz+2g,] ny+2g, nx+2g);
+    rot: list of int32 side arrays (in/out)"""
+    ndim = len(n)
+    arr = (C.c_void_p * 3)()
+    for d, a in enumerate(rot):
+        assert a.dtype == np.int32 and a.flags.c_contiguous
+        arr[d] = a.ctypes.data
+    lib().oracle_k_quat_symm_rotation(ndim, _ivec([0] * ndim), _ivec([v - 1 for v in n]), _ptr(q_ghosted),
+                                      int(ngq), int(depth), arr, int(ngrot))
+
+
+def quat_fundamental(n, q_ghosted, ngq, depth):
+    ndim = len(n)
+    lib().oracle_k_quat_fundamental(ndim, _ivec([0] * ndim), _ivec([v - 1 for v in n]), _ptr(q_ghosted),
+                                    int(ngq), int(depth))
+
+
+def project(n, depth, q, ngq, corr, ngc, err, nge):
+    ndim = len(n)
+    lib().oracle_k_project(ndim, _ivec([0] * ndim), _ivec([v - 1 for v in n]), int(depth), _ptr(q), int(ngq),
+                           _ptr(corr), int(ngc), _ptr(err), int(nge))
