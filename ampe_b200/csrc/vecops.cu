@@ -129,6 +129,32 @@ __global__ void final_reduce_kernel(const double* partial, long long nblocks, in
    }
 }
 
+// sum w^2 x y : the inner product of CVODE's scaled Krylov solver (SPGMR with s1 = s2 = ewt)
+__global__ void wdot_kernel(const double* x, const double* y, const double* w, long long n, double* partial)
+{
+   double acc = 0.0;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const double a = x[i] * w[i], b = y[i] * w[i];
+      acc += a * b;
+   }
+   __shared__ double red[VT / 32];
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+   if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = acc;
+   __syncthreads();
+   if (threadIdx.x == 0) {
+      double r = red[0];
+      for (int k = 1; k < VT / 32; k++) r += red[k];
+      partial[blockIdx.x] = r;
+   }
+}
+// CVODE error weights (cvEwtSetSS): w = 1 / (rtol |y| + atol)
+__global__ void ewt_kernel(const double* y, double rtol, double atol, double* w, long long n)
+{
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      w[i] = 1.0 / (rtol * fabs(y[i]) + atol);
+}
+
 // QuatModel::normalizeQuat (QuatModel.cc:4237-4262): q *= 1/sqrt(sum q^2), per cell
 template <int Q>
 __global__ void normalize_quat_kernel(double* q, long long ncell)
@@ -301,6 +327,44 @@ extern "C" int ampe_vec_max_norm(ampe_rhs_ctx* c, const ampe_rhs_fields* x, doub
    int rc = components(c, x, x, nullptr, v);
    if (rc) return rc;
    return reduce_components<2>(c, v, result, (cudaStream_t)stream);
+}
+
+// sum over the evolved components of (w x)(w y)
+extern "C" int ampe_vec_wdot(ampe_rhs_ctx* c, const ampe_rhs_fields* x, const ampe_rhs_fields* y,
+                             const ampe_rhs_fields* w, double* result, void* stream)
+{
+   if (!c || !x || !y || !w || !result) return ampe_set_err(AMPE_EINVAL, "null argument");
+   Comp v, vw;
+   int rc = components(c, x, y, nullptr, v);
+   if (!rc) rc = components(c, w, nullptr, nullptr, vw);
+   if (!rc) rc = ensure_scratch(c, RED_BLOCKS);
+   if (rc) return rc;
+   cudaStream_t st = (cudaStream_t)stream;
+   for (int n = 0; n < v.n; n++) {
+      const int blocks = (int)((v.len[n] + VT - 1) / VT < RED_BLOCKS ? (v.len[n] + VT - 1) / VT : RED_BLOCKS);
+      wdot_kernel<<<blocks, VT, 0, st>>>(v.x[n], v.y[n], vw.x[n], v.len[n], c->partials);
+      final_reduce_kernel<0><<<1, 32, 0, st>>>(c->partials, blocks, 1, c->red_out, n > 0);
+   }
+   CUDA_OKV(cudaGetLastError());
+   CUDA_OKV(cudaMemcpyAsync(result, c->red_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+   CUDA_OKV(cudaStreamSynchronize(st));
+   return AMPE_OK;
+}
+
+// w = 1 / (rtol |y| + atol) on the evolved components (CVODE cvEwtSetSS)
+extern "C" int ampe_vec_error_weights(ampe_rhs_ctx* c, const ampe_rhs_fields* y, double rtol, double atol,
+                                      const ampe_rhs_fields* w, void* stream)
+{
+   if (!c || !y || !w) return ampe_set_err(AMPE_EINVAL, "null argument");
+   if (!(rtol >= 0.0) || !(atol >= 0.0) || (rtol == 0.0 && atol == 0.0))
+      return ampe_set_err(AMPE_EINVAL, "error weights: rtol, atol >= 0 and not both 0 (CVODESolver.cc:147-151)");
+   Comp v;
+   int rc = components(c, y, nullptr, w, v);
+   if (rc) return rc;
+   for (int n = 0; n < v.n; n++)
+      ewt_kernel<<<grid_for(v.len[n]), VT, 0, (cudaStream_t)stream>>>(v.x[n], rtol, atol, v.z[n], v.len[n]);
+   CUDA_OKV(cudaGetLastError());
+   return AMPE_OK;
 }
 
 extern "C" int ampe_normalize_quat(ampe_rhs_ctx* c, const ampe_rhs_fields* y, void* stream)

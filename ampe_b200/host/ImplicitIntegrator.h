@@ -1,0 +1,234 @@
+// Minimal implicit time integrator around the RHS evaluation: fixed-step
+// BDF1 / BDF2 with an inexact Newton iteration whose linear systems are solved by a matrix-free
+// scaled GMRES, shaped like the CVODE configuration AMPE uses
+//   (QuatIntegrator::setSundialsOptions, QuatIntegrator.cc:1569-1594: BDF, max_order 2, SPGMR with
+//    max_krylov_dimension 5, scalar rtol/atol, projection function, JTimes RHS function;
+//    samrai/CVODESolver.cc:157-247):
+//   * residual evaluations call evaluateRHSFunction(t, y, ydot, fd_flag = 0), Jacobian-vector
+//     products the difference quotient  J v ~ [f(y + sigma v) - f(y)] / sigma,  sigma = 1/||v||_WRMS,
+//     with fd_flag = 1 (CVODEJTimesRHSFuncEval, CVODESolver.h:1186-1195: lagged face coefficients,
+//     QuatIntegrator.cc:3183-3189);
+//   * norms are CVODE's weighted RMS norms with w = 1/(rtol |y_n| + atol);
+//   * after the nonlinear solve the projection hook (QuatIntegrator::applyProjection,
+//     QuatIntegrator.cc:3911-3962) puts the quaternions back on the unit sphere, then the
+//     post-step work of QuatModel::Advance (normalizeQuat, resetRefPhaseConcentrations).
+// CVODE itself (variable step / order, error test, preconditioning) is out of scope: the step is
+// fixed and a Newton failure is returned to the caller instead of retried with a smaller step.
+//
+// The algorithm is a template over the vector backend so that the same code drives the device
+// vectors (DeviceOps in QuatIntegrator.h, everything through the C ABI of libampe_b200.so) and a
+// host backend used by the CPU tests of the host logic.
+#pragma once
+#include <cmath>
+#include <vector>
+
+namespace ampe_host {
+
+struct ImplicitOptions {
+   int order = 2;                          // max_order (QuatIntegrator.cc:291): 1 or 2
+   double rtol = 3.e-6, atol = 3.e-4;      // QuatIntegrator.cc:285-289
+   int max_krylov_dimension = 5;           // QuatIntegrator.cc:300-301
+   int max_newton_iterations = 3;          // CVODE NLS_MAXCOR
+   double newton_tolerance = 0.1;          // CVODE nlscoef
+   double linear_tolerance_factor = 0.05;  // CVODE eplifac
+};
+
+struct ImplicitStats {
+   long steps = 0, rhs_evals = 0, jtimes_evals = 0, newton_iterations = 0, linear_iterations = 0,
+        projections = 0;
+   double last_newton_update = 0.0;  // WRMS norm of the last Newton correction
+   double last_linear_residual = 0.0;
+};
+
+enum { IMPLICIT_OK = 0, IMPLICIT_EINVAL = -1, IMPLICIT_ENEWTON = -20, IMPLICIT_ERHS = -21 };
+
+// Ops concept:
+//   typedef ... Vec;
+//   Vec  clone(const Vec& y)                 new vector, every component (evolved or not) copied
+//   void release(Vec& v)
+//   void linearSum(double a, const Vec& x, double b, const Vec& y, Vec& z)   evolved components
+//   void scale(double a, const Vec& x, Vec& z)
+//   double wdot(const Vec& x, const Vec& y, const Vec& w)                     sum (w x)(w y)
+//   long long length()                                                        evolved unknowns
+//   void errorWeights(const Vec& y, double rtol, double atol, Vec& w)
+//   int  rhs(double t, const Vec& y, Vec& ydot, int fd_flag)                  0 = success
+//   void applyProjection(double t, const Vec& y, Vec& corr, Vec& err)
+//   void postStep(Vec& y)
+template <class Ops>
+class ImplicitIntegrator
+{
+ public:
+   typedef typename Ops::Vec Vec;
+
+   ImplicitIntegrator(Ops& ops, const ImplicitOptions& opt) : d_ops(ops), d_opt(opt) {}
+
+   const ImplicitStats& stats() const { return d_stats; }
+
+   // nsteps steps of size h from t0; y is updated in place
+   int advance(Vec& y, double t0, double h, int nsteps)
+   {
+      if (!(h > 0.0) || nsteps < 0 || (d_opt.order != 1 && d_opt.order != 2) || d_opt.max_krylov_dimension < 1 ||
+          d_opt.max_newton_iterations < 1)
+         return IMPLICIT_EINVAL;
+      const int m = d_opt.max_krylov_dimension;
+      Vec yprev = d_ops.clone(y), psi = d_ops.clone(y), ycur = d_ops.clone(y), fy = d_ops.clone(y),
+          ewt = d_ops.clone(y), res = d_ops.clone(y), delta = d_ops.clone(y), acor = d_ops.clone(y),
+          ytmp = d_ops.clone(y), wk = d_ops.clone(y);
+      std::vector<Vec> V;
+      for (int j = 0; j <= m; j++) V.push_back(d_ops.clone(y));
+      int rc = IMPLICIT_OK;
+      double t = t0;
+      for (int n = 0; n < nsteps && rc == IMPLICIT_OK; n++) {
+         const bool bdf2 = d_opt.order == 2 && n > 0;
+         // y_{n+1} = psi + gamma f(y_{n+1})
+         const double gamma = bdf2 ? (2.0 / 3.0) * h : h;
+         if (bdf2)
+            d_ops.linearSum(4.0 / 3.0, y, -1.0 / 3.0, yprev, psi);
+         else
+            d_ops.scale(1.0, y, psi);
+         d_ops.errorWeights(y, d_opt.rtol, d_opt.atol, ewt);
+         // predictor: extrapolation through the last two solutions (y_n + h f(y_n) at the first step)
+         if (n == 0) {
+            if (d_ops.rhs(t, y, fy, 0) != 0) {
+               rc = IMPLICIT_ERHS;
+               break;
+            }
+            d_stats.rhs_evals++;
+            d_ops.linearSum(1.0, y, h, fy, ycur);
+         } else {
+            d_ops.linearSum(2.0, y, -1.0, yprev, ycur);
+         }
+         d_ops.scale(0.0, acor, acor);  // accumulated correction = CVODE's local error estimate
+         rc = newton(t + h, gamma, psi, ewt, ycur, fy, res, delta, acor, ytmp, wk, V);
+         if (rc != IMPLICIT_OK) break;
+         // projection onto the constraint |q| = 1 (CVodeSetProjFn): y <- y + corr
+         d_ops.applyProjection(t + h, ycur, delta, acor);
+         d_ops.linearSum(1.0, ycur, 1.0, delta, ycur);
+         d_stats.projections++;
+         d_ops.scale(1.0, y, yprev);
+         d_ops.scale(1.0, ycur, y);
+         d_ops.postStep(y);
+         t += h;
+         d_stats.steps++;
+      }
+      for (auto& v : V) d_ops.release(v);
+      Vec* all[] = {&yprev, &psi, &ycur, &fy, &ewt, &res, &delta, &acor, &ytmp, &wk};
+      for (Vec* v : all) d_ops.release(*v);
+      return rc;
+   }
+
+ private:
+   double wrms(const Vec& x, const Vec& w) { return std::sqrt(d_ops.wdot(x, x, w) / (double)d_ops.length()); }
+
+   // inexact Newton on G(y) = y - psi - gamma f(y); ycur holds the predictor on entry, the solution on exit
+   int newton(double t, double gamma, const Vec& psi, const Vec& ewt, Vec& ycur, Vec& fy, Vec& res, Vec& delta,
+              Vec& acor, Vec& ytmp, Vec& wk, std::vector<Vec>& V)
+   {
+      double delp = 0.0, crate = 1.0;
+      for (int it = 0; it < d_opt.max_newton_iterations; it++) {
+         if (d_ops.rhs(t, ycur, fy, 0) != 0) return IMPLICIT_ERHS;
+         d_stats.rhs_evals++;
+         // res = -G = psi + gamma f - y
+         d_ops.linearSum(1.0, psi, gamma, fy, res);
+         d_ops.linearSum(1.0, res, -1.0, ycur, res);
+         const double lin_tol = d_opt.linear_tolerance_factor * d_opt.newton_tolerance;
+         int rc = gmres(t, gamma, ewt, ycur, fy, res, delta, ytmp, wk, V, lin_tol);
+         if (rc != IMPLICIT_OK) return rc;
+         d_ops.linearSum(1.0, ycur, 1.0, delta, ycur);
+         d_ops.linearSum(1.0, acor, 1.0, delta, acor);
+         d_stats.newton_iterations++;
+         const double del = wrms(delta, ewt);
+         d_stats.last_newton_update = del;
+         if (it > 0) {
+            crate = std::fmax(0.3 * crate, del / delp);  // CVODE CRDOWN
+            if (del > 2.0 * delp) return IMPLICIT_ENEWTON;  // CVODE RDIV: diverging
+         }
+         if (del * std::fmin(1.0, crate) <= d_opt.newton_tolerance) return IMPLICIT_OK;
+         delp = del;
+      }
+      return IMPLICIT_ENEWTON;
+   }
+
+   // (I - gamma J) v with the difference-quotient Jacobian (CVODE cvLsDQJtimes with the JTimes RHS)
+   int jtimes(double t, double gamma, const Vec& ewt, const Vec& y, const Vec& fy, const Vec& v, Vec& out, Vec& ytmp)
+   {
+      const double vn = wrms(v, ewt);
+      if (!(vn > 0.0)) {
+         d_ops.scale(1.0, v, out);
+         return IMPLICIT_OK;
+      }
+      const double sig = 1.0 / vn;
+      d_ops.linearSum(1.0, y, sig, v, ytmp);
+      if (d_ops.rhs(t, ytmp, out, 1) != 0) return IMPLICIT_ERHS;
+      d_stats.jtimes_evals++;
+      d_ops.linearSum(1.0 / sig, out, -1.0 / sig, fy, out);  // J v
+      d_ops.linearSum(1.0, v, -gamma, out, out);
+      return IMPLICIT_OK;
+   }
+
+   // GMRES(m) without restart in the ewt-weighted inner product (= SPGMR with s1 = s2 = ewt), modified
+   // Gram-Schmidt, Givens rotations; x0 = 0; stops when the WRMS norm of the linear residual <= tol
+   int gmres(double t, double gamma, const Vec& ewt, const Vec& y, const Vec& fy, const Vec& b, Vec& x, Vec& ytmp,
+             Vec& wk, std::vector<Vec>& V, double tol)
+   {
+      const int m = d_opt.max_krylov_dimension;
+      const double invN = 1.0 / (double)d_ops.length();
+      d_ops.scale(0.0, x, x);
+      const double beta = std::sqrt(d_ops.wdot(b, b, ewt) * invN);
+      d_stats.last_linear_residual = beta;
+      if (beta <= tol) return IMPLICIT_OK;
+      std::vector<std::vector<double> > H(m + 1, std::vector<double>(m, 0.0));
+      std::vector<double> cs(m, 0.0), sn(m, 0.0), g(m + 1, 0.0);
+      g[0] = beta;
+      d_ops.scale(1.0 / beta, b, V[0]);
+      int k = 0;
+      for (int j = 0; j < m; j++) {
+         int rc = jtimes(t, gamma, ewt, y, fy, V[j], wk, ytmp);
+         if (rc != IMPLICIT_OK) return rc;
+         d_stats.linear_iterations++;
+         double col2 = 0.0;  // |A v_j|^2 = sum_i H[i][j]^2 (Pythagoras over the orthonormal basis)
+         for (int i = 0; i <= j; i++) {
+            H[i][j] = d_ops.wdot(wk, V[i], ewt) * invN;
+            d_ops.linearSum(1.0, wk, -H[i][j], V[i], wk);
+            col2 += H[i][j] * H[i][j];
+         }
+         H[j + 1][j] = std::sqrt(d_ops.wdot(wk, wk, ewt) * invN);
+         // breakdown: A v_j lies in the current Krylov space up to rounding -- the remainder is
+         // difference-quotient noise and must not become a basis vector
+         const bool breakdown = !(H[j + 1][j] > 1.0e-12 * std::sqrt(col2 + H[j + 1][j] * H[j + 1][j]));
+         if (breakdown) H[j + 1][j] = 0.0;
+         for (int i = 0; i < j; i++) {
+            const double a = cs[i] * H[i][j] + sn[i] * H[i + 1][j];
+            H[i + 1][j] = -sn[i] * H[i][j] + cs[i] * H[i + 1][j];
+            H[i][j] = a;
+         }
+         const double r = std::hypot(H[j][j], H[j + 1][j]);
+         cs[j] = (r > 0.0) ? H[j][j] / r : 1.0;
+         sn[j] = (r > 0.0) ? H[j + 1][j] / r : 0.0;
+         const double hsub = H[j + 1][j];
+         H[j][j] = r;
+         H[j + 1][j] = 0.0;
+         g[j + 1] = -sn[j] * g[j];
+         g[j] = cs[j] * g[j];
+         k = j + 1;
+         d_stats.last_linear_residual = std::fabs(g[j + 1]);
+         if (std::fabs(g[j + 1]) <= tol || !(hsub > 0.0)) break;
+         d_ops.scale(1.0 / hsub, wk, V[j + 1]);
+      }
+      // back substitution, x = sum c_i V_i
+      std::vector<double> c(k, 0.0);
+      for (int i = k - 1; i >= 0; i--) {
+         double s = g[i];
+         for (int l = i + 1; l < k; l++) s -= H[i][l] * c[l];
+         c[i] = s / H[i][i];
+      }
+      for (int i = 0; i < k; i++) d_ops.linearSum(1.0, x, c[i], V[i], x);
+      return IMPLICIT_OK;  // like CVODE, a reduced residual is accepted; Newton decides
+   }
+
+   Ops& d_ops;
+   ImplicitOptions d_opt;
+   ImplicitStats d_stats;
+};
+
+}  // namespace ampe_host

@@ -6,9 +6,93 @@
 //   use_fused = false : the reference's own sequence of Strategy calls, each one a piecewise
 //                       CUDA kernel on SAMRAI-layout PatchData (drop-in check of every Strategy)
 #pragma once
+#include "ImplicitIntegrator.h"
 #include "ampe_host.h"
 
 namespace ampe_host {
+
+// Device vector backend of ImplicitIntegrator: the solution vector is an ampe_rhs_fields of device
+// arrays; every operation is a C-ABI call into libampe_b200.so (the N_Vector operations CVODE would
+// issue through Sundials_SAMRAIVector, samrai/Sundials_SAMRAIVector.cc).
+class DeviceVectorOps
+{
+ public:
+   typedef ampe_rhs_fields Vec;
+   DeviceVectorOps(ampe_rhs_ctx* ctx, const ampe_rhs_config& cfg) : d_ctx(ctx), d_cfg(cfg)
+   {
+      d_ncell = 1;
+      for (int d = 0; d < cfg.ndim; d++) d_ncell *= (size_t)cfg.n[d];
+      d_length = 0;
+      if (cfg.with_phase) d_length += (long long)d_ncell;
+      if (cfg.evolve_quat) d_length += (long long)d_ncell * cfg.qlen;
+      if (cfg.with_concentration) d_length += (long long)d_ncell;
+      if (cfg.with_unsteady_temperature) d_length += (long long)d_ncell;
+   }
+   Vec clone(const Vec& y)
+   {
+      Vec v = {nullptr, nullptr, nullptr, nullptr};
+      dup(y.phase, &v.phase, 1);
+      dup(y.quat, &v.quat, d_cfg.qlen);
+      dup(y.conc, &v.conc, 1);
+      dup(y.temperature, &v.temperature, 1);
+      return v;
+   }
+   void release(Vec& v)
+   {
+      cudaFree(v.phase);
+      cudaFree(v.quat);
+      cudaFree(v.conc);
+      cudaFree(v.temperature);
+      v = Vec{nullptr, nullptr, nullptr, nullptr};
+   }
+   void linearSum(double a, const Vec& x, double b, const Vec& y, Vec& z)
+   {
+      check(ampe_vec_linear_sum(d_ctx, a, &x, b, &y, &z, nullptr), "linearSum");
+   }
+   void scale(double a, const Vec& x, Vec& z) { check(ampe_vec_scale(d_ctx, a, &x, &z, nullptr), "scale"); }
+   double wdot(const Vec& x, const Vec& y, const Vec& w)
+   {
+      double r = 0.0;
+      check(ampe_vec_wdot(d_ctx, &x, &y, &w, &r, nullptr), "wdot");
+      return r;
+   }
+   long long length() const { return d_length; }
+   void errorWeights(const Vec& y, double rtol, double atol, Vec& w)
+   {
+      check(ampe_vec_error_weights(d_ctx, &y, rtol, atol, &w, nullptr), "errorWeights");
+   }
+   int rhs(double t, const Vec& y, Vec& ydot, int fd_flag)
+   {
+      check(ampe_rhs_eval(d_ctx, t, &y, &ydot, fd_flag, nullptr), "ampe_rhs_eval");
+      return 0;
+   }
+   void applyProjection(double, const Vec& y, Vec& corr, Vec& err)
+   {
+      check(ampe_apply_projection(d_ctx, &y, &corr, &err, nullptr), "applyProjection");
+   }
+   // what QuatModel::Advance does after the integrator returns: normalizeQuat (QuatModel.cc:4222-4262)
+   // and resetRefPhaseConcentrations (QuatModel.cc:5218-5231)
+   void postStep(Vec& y)
+   {
+      if (d_cfg.evolve_quat) check(ampe_normalize_quat(d_ctx, &y, nullptr), "normalizeQuat");
+      const bool kks = d_cfg.conc_rhs_form == AMPE_CONC_KKS || d_cfg.conc_rhs_form == AMPE_CONC_EBS;
+      if (kks && d_cfg.free_energy == AMPE_FE_CALPHAD)
+         check(ampe_rhs_set_ref_concentrations(d_ctx, nullptr, nullptr, nullptr), "resetRef");
+   }
+
+ private:
+   void dup(const double* src, double** dst, int depth)
+   {
+      if (!src || depth < 1) return;
+      const size_t nb = d_ncell * (size_t)depth * sizeof(double);
+      cuda_check(cudaMalloc(dst, nb), "clone");
+      cuda_check(cudaMemcpy(*dst, src, nb, cudaMemcpyDeviceToDevice), "clone");
+   }
+   ampe_rhs_ctx* d_ctx;
+   ampe_rhs_config d_cfg;
+   size_t d_ncell;
+   long long d_length;
+};
 
 class QuatIntegrator
 {
@@ -167,6 +251,19 @@ class QuatIntegrator
    void makeQuatFundamental(const ampe_rhs_fields* y)
    {
       check(ampe_quat_fundamental(d_ctx, y, nullptr), "makeQuatFundamental");
+   }
+   // nsteps fixed BDF steps (ImplicitIntegrator.h: Newton + matrix-free GMRES, fd_flag = 1 Jacobian-vector
+   // products, projection): the CVODE-shaped stand-in for QuatIntegrator::Advance, y stays on the device
+   int integrateImplicit(const ampe_rhs_fields* y, double t0, double dt, int nsteps, const ImplicitOptions& opt,
+                         ImplicitStats* stats)
+   {
+      DeviceVectorOps ops(d_ctx, d_cfg);
+      ImplicitIntegrator<DeviceVectorOps> integ(ops, opt);
+      ampe_rhs_fields yy = *y;
+      const int rc = integ.advance(yy, t0, dt, nsteps);
+      if (stats) *stats = integ.stats();
+      cuda_check(cudaDeviceSynchronize(), "integrateImplicit");
+      return rc;
    }
    // fixed-step explicit stand-in for QuatIntegrator::Advance (scheme 0 Euler, 1 Heun)
    void integrateFixed(const ampe_rhs_fields* y, const ampe_rhs_fields* work1, const ampe_rhs_fields* work2,

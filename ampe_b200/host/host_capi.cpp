@@ -52,4 +52,29 @@ int ampe_host_evaluate_rhs_function(void* h, double time, const ampe_rhs_fields*
       return -1;
    }
 }
+// options: {order, max_krylov_dimension, max_newton_iterations} ints, {rtol, atol, newton_tolerance,
+// linear_tolerance_factor} doubles (NULL = AMPE's defaults); stats_out[8]: steps, rhs_evals, jtimes_evals,
+// newton_iterations, linear_iterations, projections, last_newton_update, last_linear_residual
+int ampe_host_integrate_implicit(void* h, const ampe_rhs_fields* y, double t0, double dt, int nsteps,
+                                 const int* iopt, const double* dopt, double* stats_out)
+{
+   try {
+      ampe_host::ImplicitOptions o;
+      if (iopt) o.order = iopt[0], o.max_krylov_dimension = iopt[1], o.max_newton_iterations = iopt[2];
+      if (dopt) o.rtol = dopt[0], o.atol = dopt[1], o.newton_tolerance = dopt[2], o.linear_tolerance_factor = dopt[3];
+      ampe_host::ImplicitStats st;
+      const int rc = static_cast<ampe_host::QuatIntegrator*>(h)->integrateImplicit(y, t0, dt, nsteps, o, &st);
+      if (stats_out) {
+         stats_out[0] = (double)st.steps, stats_out[1] = (double)st.rhs_evals, stats_out[2] = (double)st.jtimes_evals;
+         stats_out[3] = (double)st.newton_iterations, stats_out[4] = (double)st.linear_iterations;
+         stats_out[5] = (double)st.projections, stats_out[6] = st.last_newton_update;
+         stats_out[7] = st.last_linear_residual;
+      }
+      if (rc != 0) g_host_err = "integrateImplicit: " + std::string(rc == ampe_host::IMPLICIT_ENEWTON ? "Newton did not converge" : "failed");
+      return rc;
+   } catch (const std::exception& e) {
+      g_host_err = e.what();
+      return -1;
+   }
+}
 }

@@ -33,6 +33,9 @@ def load_host():
         L.ampe_host_evaluate_rhs_function.restype = C.c_int
         L.ampe_host_evaluate_rhs_function.argtypes = [vp, C.c_double, C.POINTER(_abi.RhsFields),
                                                       C.POINTER(_abi.RhsFields), C.c_int]
+        L.ampe_host_integrate_implicit.restype = C.c_int
+        L.ampe_host_integrate_implicit.argtypes = [vp, C.POINTER(_abi.RhsFields), C.c_double, C.c_double, C.c_int,
+                                                   vp, vp, vp]
         _lib = L
     return _lib
 
@@ -65,6 +68,26 @@ class HostQuatIntegrator:
                                                          int(fd_flag)))
         torch.cuda.synchronize()
         return 0
+
+    IMPLICIT_ENEWTON = -20
+
+    def integrateImplicit(self, y, dt, nsteps, t0=0.0, order=2, max_krylov=5, max_newton=3, rtol=3e-6,
+                          atol=3e-4, newton_tol=0.1, lin_factor=0.05):
+        """nsteps fixed BDF steps on the device (host/ImplicitIntegrator.h: Newton + matrix-free GMRES with
+        fd_flag = 1 Jacobian-vector products, applyProjection after every step), y updated in place.
+        Defaults are AMPE's integrator defaults (QuatIntegrator.cc:285-301).  Returns (rc, stats):
+        rc 0, or IMPLICIT_ENEWTON when the Newton iteration of a step did not converge."""
+        iopt = (C.c_int * 3)(int(order), int(max_krylov), int(max_newton))
+        dopt = (C.c_double * 4)(float(rtol), float(atol), float(newton_tol), float(lin_factor))
+        st = (C.c_double * 8)()
+        fy = y.fields()
+        rc = self.L.ampe_host_integrate_implicit(self.h, C.byref(fy), float(t0), float(dt), int(nsteps), iopt,
+                                                 dopt, st)
+        if rc not in (0, self.IMPLICIT_ENEWTON):
+            raise AmpeError(self.L.ampe_host_last_error().decode())
+        names = ("steps", "rhs_evals", "jtimes_evals", "newton_iterations", "linear_iterations", "projections",
+                 "last_newton_update", "last_linear_residual")
+        return rc, dict(zip(names, list(st)))
 
     def close(self):
         if self.h:

@@ -66,6 +66,10 @@ def load():
     L.ampe_vec_wrms_norm.argtypes = [vp, pf, pf, pd, vp]
     L.ampe_vec_max_norm.restype = ci
     L.ampe_vec_max_norm.argtypes = [vp, pf, pd, vp]
+    L.ampe_vec_wdot.restype = ci
+    L.ampe_vec_wdot.argtypes = [vp, pf, pf, pf, pd, vp]
+    L.ampe_vec_error_weights.restype = ci
+    L.ampe_vec_error_weights.argtypes = [vp, pf, dbl, dbl, pf, vp]
     L.ampe_normalize_quat.restype = ci
     L.ampe_normalize_quat.argtypes = [vp, pf, vp]
     L.ampe_integrate_fixed.restype = ci

@@ -214,6 +214,12 @@ int ampe_vec_dot(ampe_rhs_ctx* ctx, const ampe_rhs_fields* x, const ampe_rhs_fie
 int ampe_vec_wrms_norm(ampe_rhs_ctx* ctx, const ampe_rhs_fields* x, const ampe_rhs_fields* w,
                        double* result, void* stream);
 int ampe_vec_max_norm(ampe_rhs_ctx* ctx, const ampe_rhs_fields* x, double* result, void* stream);
+/* sum (w x)(w y): inner product of CVODE's scaled SPGMR (CVODESolver.cc:183-187, s1 = s2 = ewt)  */
+int ampe_vec_wdot(ampe_rhs_ctx* ctx, const ampe_rhs_fields* x, const ampe_rhs_fields* y,
+                  const ampe_rhs_fields* w, double* result, void* stream);
+/* CVODE error weights from CVodeSStolerances(rtol, atol) (CVODESolver.cc:179): w = 1/(rtol|y|+atol) */
+int ampe_vec_error_weights(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, double rtol, double atol,
+                           const ampe_rhs_fields* w, void* stream);
 /* QuatModel::normalizeQuat (QuatModel.cc:4222-4262): q <- q/|q| per cell, in place.        */
 int ampe_normalize_quat(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, void* stream);
 /* Fixed-step explicit integrator keeping y on the device (scheme 0 forward Euler, 1 Heun):

@@ -57,6 +57,9 @@ def lib(perf=False):
         L.oracle_eval_grad_normi.argtypes = [dbl, C.c_char, dbl, dbl]
         L.oracle_quatsymmrotate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oracle_qr_table4.argtypes = [C.c_void_p]
+        L.oracle_integrate_implicit.restype = C.c_int
+        L.oracle_integrate_implicit.argtypes = [C.c_void_p, C.POINTER(_abi.RhsFields), dbl, dbl, C.c_int,
+                                                C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_quatfindsymm.restype = C.c_int
         L.oracle_quatfindsymm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oracle_k_quat_symm_rotation.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
@@ -145,6 +148,20 @@ class Oracle:
         out = np.zeros(8)
         st = self.L.oracle_energy(self.h, C.byref(_fields(y)), _ptr(out))
         return st, out
+
+    def integrate_implicit(self, y, dt, nsteps, t0=0.0, order=2, max_krylov=5, max_newton=3, rtol=3e-6,
+                           atol=3e-4, newton_tol=0.1, lin_factor=0.05):
+        """the product's ImplicitIntegrator template (ampe_b200/host/ImplicitIntegrator.h) driven by the
+        oracle's RHS: y (dict of numpy arrays) is advanced in place; returns (rc, stats dict)"""
+        iopt = np.array([order, max_krylov, max_newton], dtype=np.int32)
+        dopt = np.array([rtol, atol, newton_tol, lin_factor], dtype=np.float64)
+        st = np.zeros(8)
+        fy = _fields(y)
+        rc = self.L.oracle_integrate_implicit(self.h, C.byref(fy), float(t0), float(dt), int(nsteps),
+                                              _ptr(iopt), _ptr(dopt), _ptr(st))
+        names = ("steps", "rhs_evals", "jtimes_evals", "newton_iterations", "linear_iterations", "projections",
+                 "last_newton_update", "last_linear_residual")
+        return rc, dict(zip(names, st.tolist()))
 
     def phase_concentrations(self):
         cl = np.zeros(self.ncell)
