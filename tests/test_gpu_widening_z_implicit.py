@@ -70,13 +70,20 @@ def test_implicit_trajectory_matches_oracle_backend(name, mult, nsteps):
         assert np.abs((q * q).sum(0) - 1.0).max() < 1e-14
 
 
-def test_default_options_and_newton_failure_code():
-    """AMPE's default tolerances run; a step far beyond what three Newton iterations can absorb comes back
-    as IMPLICIT_ENEWTON instead of a silent wrong answer"""
+def test_default_options_run():
+    """AMPE's default integrator options (QuatIntegrator.cc:285-301) on the device"""
+    dt = parity.TRAJ_DT["dendrite2d"]
+    cfg, st, y, rc, stats = _device_run("dendrite2d", 20 * dt, 5, None)
+    assert rc == 0 and stats["steps"] == 5
+
+
+def test_newton_failure_code():
+    """a step far beyond what two Newton iterations can absorb comes back as IMPLICIT_ENEWTON instead of a
+    silent wrong answer (the CPU run of the same template returns the same code)"""
     from ampe_b200.host_rhs import HostQuatIntegrator
     dt = parity.TRAJ_DT["dendrite2d"]
-    cfg, st, y, rc, stats = _device_run("dendrite2d", 20 * dt, 5)
-    assert rc == 0 and stats["steps"] == 5
-    cfg, st, y, rc, stats = _device_run("dendrite2d", 1e4 * dt, 1, order=1, rtol=1e-10, atol=1e-12, max_krylov=3,
-                                        max_newton=2)
+    kw = dict(order=1, rtol=1e-10, atol=1e-12, max_krylov=3, max_newton=2)
+    _, rc_o, _ = _oracle_run("dendrite2d", 1e4 * dt, 1, None, **kw)
+    cfg, st, y, rc, stats = _device_run("dendrite2d", 1e4 * dt, 1, None, **kw)
+    assert rc_o == HostQuatIntegrator.IMPLICIT_ENEWTON
     assert rc == HostQuatIntegrator.IMPLICIT_ENEWTON

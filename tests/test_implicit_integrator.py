@@ -2,7 +2,7 @@
 the CPU: (1) a toy vector backend with closed-form discrete solutions pins the BDF1/BDF2 coefficients,
 the Newton iteration and the matrix-free GMRES; (2) the same template driven by the oracle's RHS is
 checked against small-step explicit trajectories (observed order 1 and 2), mass conservation and the
-quaternion constraint.  The device backend is compared with (2) in tests/test_gpu_widening_implicit.py."""
+quaternion constraint.  The device backend is compared with (2) in tests/test_gpu_widening_z_implicit.py."""
 import os
 import subprocess
 
