@@ -226,18 +226,22 @@ int dispatch3_fixed_3d(const FusedArgs& A, cudaStream_t st, const char** err, in
 }  // namespace ampe
 
 template <int ND>
-static int dispatch_q(const FusedArgs& A, cudaStream_t st)
+static int dispatch_q(const FusedArgs& A, cudaStream_t st, int* nlaunch)
 {
    const char* err = nullptr;
    int rc = AMPE_EINVAL;
+   *nlaunch = 1;
    // AMPE_B200_GENERIC=1 forces the runtime-selector instantiation (tests compare both)
    const bool generic_only = A.force_generic != 0;
    bool done = false;
    if (!generic_only) {
       if (ND == 2)
          done = dispatch3_fixed_dendrite(A, st, &err, &rc) || dispatch3_fixed_auni2d(A, st, &err, &rc);
-      else
-         done = dispatch3_fixed_3d(A, st, &err, &rc);
+      else {
+         const int n = dispatch3_fixed_3d(A, st, &err, &rc);
+         done = n != 0;
+         if (n > 1) *nlaunch = n;
+      }
    }
    if (!done) {
       switch (A.p.qlen) {
@@ -263,6 +267,7 @@ extern "C" int ampe_rhs_create(const ampe_rhs_config* cfg, ampe_rhs_ctx** out)
    ampe_rhs_ctx* c = new ampe_rhs_ctx;
    c->cfg = *cfg;
    c->generic_only = getenv("AMPE_B200_GENERIC") != nullptr;
+   c->split3d = getenv("AMPE_B200_SPLIT3D") != nullptr;
    int rc = ampe_derive_params(*cfg, c->p);
    if (rc) {
       delete c;
@@ -563,14 +568,16 @@ static int eval_ranges(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs
    A.energy_partials = energy_partials;
    A.wrap_slab = c->have_halo ? 0 : 1;
    A.df = c->df;
+   A.split3d = c->split3d ? 1 : 0;
    A.use_lag = use_lag ? 1 : 0;
    A.write_lag = (recompute && c->cfg.lag_quat_sidegrad && !en) ? 1 : 0;
    for (int r = 0; r < cells.n; r++) {
       A.s_begin = cells.r[r][0];
       A.s_end = cells.r[r][1];
-      int rc = (p.ndim == 2) ? dispatch_q<2>(A, st) : dispatch_q<3>(A, st);
+      int nlaunch = 1;
+      int rc = (p.ndim == 2) ? dispatch_q<2>(A, st, &nlaunch) : dispatch_q<3>(A, st, &nlaunch);
       if (rc) return rc;
-      c->launches++;
+      c->launches += nlaunch;
    }
    if (last && A.write_lag) c->lag_valid = true;
    return AMPE_OK;

@@ -30,6 +30,7 @@ struct ampe_rhs_ctx {
    bool have_ref = false;
    bool lag_valid = false;
    bool generic_only = false;  // AMPE_B200_GENERIC at create time
+   bool split3d = false;       // AMPE_B200_SPLIT3D at create time (experiment, rhs_march.cuh)
    int launches = 0;
    // staging buffers for ampe_rhs_eval_host
    ampe_rhs_fields dev_y, dev_ydot;

@@ -150,10 +150,10 @@ static int launch3(const FusedArgs& A, cudaStream_t st, const char** err)
 }
 
 // 3D plane-marching kernel (no quaternion symmetry): column 32 x TY, NZ planes per block
-template <int Q, int CONC, bool WT, class SEL>
+template <int Q, int CONC, bool WT, class SEL, int PART = 0>
 static int launch_march(const FusedArgs& A, cudaStream_t st, const char** err)
 {
-   using TT = March3<Q, CONC, WT, SEL, AMPE_MY, AMPE_MZ>;
+   using TT = March3<Q, CONC, WT, SEL, AMPE_MY, AMPE_MZ, PART>;
    const Params& p = A.p;
    auto kern = rhs_march_kernel<TT>;
    // the dynamic shared-memory attribute belongs to the device's context: one flag per device

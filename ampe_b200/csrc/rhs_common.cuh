@@ -43,6 +43,7 @@ struct FusedArgs {
    int wrap_slab;       // 1: no halo buffers, ghost planes = opposite interior planes (one rank)
    const double* df;    // CALPHAD driving force (f_l-f_a)-mu(c_l-c_a) per cell from the KKS kernel
    double* energy_partials;  // non-null: energy diagnostics instead of the RHS (energy_tile.cuh)
+   int split3d;              // host side only: AMPE_B200_SPLIT3D, two launches per 3D EBS evaluation
 };
 
 template <int Q>

@@ -20,10 +20,22 @@
 
 namespace ampe {
 
-template <int Q_, int CONC_, bool WT_, class SEL_, int TY_, int NZ_>
+// PART selects the outputs of one launch (experiment AMPE_B200_SPLIT3D, EBS models only):
+//   0  everything (one launch per evaluation, the default)
+//   1  phase, quaternion (and temperature) RHS: no composition flux, c_l / c_a are not staged
+//   2  composition RHS only: instantiated with Q_ = 0, the quaternions are not staged
+// Every output is computed by the same expressions in either form (bit-identical); two light
+// kernels trade re-staged phi planes (HBM has 4x headroom) for registers and resident warps.
+template <int Q_, int CONC_, bool WT_, class SEL_, int TY_, int NZ_, int PART_ = 0>
 struct March3 {
    static constexpr int ND = 3, Q = Q_, CONC = CONC_, TX = 32, TY = TY_, NZ = NZ_, NT = 32 * TY_;
    static constexpr bool SYMM = false, WT = WT_, HAS_PF = false;
+   static constexpr int PART = PART_;
+   // resident blocks per SM the register allocation is capped for (tile_shape.h)
+   static constexpr int MINB = (PART_ == 0) ? AMPE_MARCH_MINB : ((PART_ == 1) ? AMPE_SPLIT_MINB1 : AMPE_SPLIT_MINB2);
+   static constexpr int CF = (PART_ == 1) ? 0 : CONC_;  // composition-flux form this launch evaluates
+   static_assert(PART_ == 0 || CONC_ == AMPE_CONC_EBS, "split launches: EBS composition model only");
+   static_assert(PART_ != 2 || Q_ == 0, "the composition part does not stage the quaternions");
    using SEL = SEL_;
    static constexpr int SX = TX + 2, SYP = TY + 2;
    static constexpr int SP = SX * SYP;  // staged cells of one plane
@@ -32,9 +44,9 @@ struct March3 {
    static constexpr int O_T = SP;
    static constexpr int O_Q = O_T + (WT ? SP : 0);
    static constexpr int O_C = O_Q + Q * SP;
-   static constexpr int O_CL = O_C + (CONC == AMPE_CONC_KKS ? SP : 0);
-   static constexpr int O_CA = O_CL + (CONC != 0 ? SP : 0);
-   static constexpr int SLOT = O_CA + (CONC != 0 ? SP : 0);  // doubles per ring slot
+   static constexpr int O_CL = O_C + (CF == AMPE_CONC_KKS ? SP : 0);
+   static constexpr int O_CA = O_CL + (CF != 0 ? SP : 0);
+   static constexpr int SLOT = O_CA + (CF != 0 ? SP : 0);  // doubles per ring slot
    static constexpr int NSLOT = 4;
    // in-plane face values, indexed like the staged plane (lower face of staged cell c)
    static constexpr int O_FXQ = NSLOT * SLOT, O_FYQ = O_FXQ + SP, O_FXC = O_FYQ + SP, O_FYC = O_FXC + SP;
@@ -44,11 +56,11 @@ struct March3 {
 };
 
 template <class TT>
-__global__ void __launch_bounds__(TT::NT, AMPE_MARCH_MINB) rhs_march_kernel(const __grid_constant__ FusedArgs A)
+__global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __grid_constant__ FusedArgs A)
 {
    using R = Rhs3<TT>;
    using SEL = typename TT::SEL;
-   constexpr int Q = TT::Q, CONC = TT::CONC, NT = TT::NT, TX = TT::TX, TY = TT::TY, SX = TT::SX;
+   constexpr int Q = TT::Q, CONC = TT::CF, NT = TT::NT, TX = TT::TX, TY = TT::TY, SX = TT::SX;
    constexpr int SP = TT::SP, SLOT = TT::SLOT, NE = TT::NE;
    constexpr bool WT = TT::WT;
    const Params& p = A.p;

@@ -165,6 +165,8 @@ template <class TT>
 struct Rhs3 {
    using SEL = typename TT::SEL;
    static constexpr int ND = TT::ND, Q = TT::Q, CONC = TT::CONC, S = TT::S;
+   static constexpr int CF = TT::CF;      // composition-flux form evaluated by this launch (0: none)
+   static constexpr int PART = TT::PART;  // 2: composition outputs only (rhs_march.cuh)
    static constexpr bool SYMM = TT::SYMM, WT = TT::WT;
    static constexpr int QN = (Q > 0) ? Q : 1;
 
@@ -339,7 +341,7 @@ struct Rhs3 {
       }
 
       // ---- composition flux ----
-      if constexpr (CONC == AMPE_CONC_EBS) {
+      if constexpr (CF == AMPE_CONC_EBS) {
          const double* scl = s + TT::O_CL;
          const double* sca = s + TT::O_CA;
          double Dl, Da;
@@ -365,7 +367,7 @@ struct Rhs3 {
          double fl = p.dinv[a] * (Dl * (scl[c] - scl[cm]));
          fl = fl + p.dinv[a] * (Da * (sca[c] - sca[cm]));
          out.cf = fl;
-      } else if constexpr (CONC == AMPE_CONC_KKS) {
+      } else if constexpr (CF == AMPE_CONC_KKS) {
          const double* scl = s + TT::O_CL;
          const double* sca = s + TT::O_CA;
          double D0, Dp;
@@ -465,7 +467,7 @@ struct Rhs3 {
       }
 
       double phase_rhs = 0.0;
-      if (AMPE_SEL(with_phase)) {
+      if (PART != 2 && AMPE_SEL(with_phase)) {
          // computerhspbg (2d/quatrhs.m4:328-402, 3d:430-512)
          double diff_term;
          if (!TT::HAS_PF || flux_type == AMPE_FLUX_SIMPLE) {
@@ -632,14 +634,14 @@ struct Rhs3 {
          for (int m = 0; m < Q; m++) A.out_q[gcell + m * ncell] = rq[m];
       }
 
-      if constexpr (CONC != 0) {
+      if constexpr (CF != 0) {
          // computerhsconcentration (3d/concentrationrhs.m4:412-458)
          double sm = p.dinv[0] * (F.cfu[0] - F.cfl[0]) + p.dinv[1] * (F.cfu[1] - F.cfl[1]);
          if constexpr (ND == 3) sm = sm + p.dinv[2] * (F.cfu[ND - 1] - F.cfl[ND - 1]);
          A.out_c[gcell] = p.conc_mobility * sm;
       }
 
-      if constexpr (WT) {
+      if constexpr (WT && PART != 2) {
          // computerhstemp + laplacian (2d/quatrhs.m4:787-803, 2d/laplacian.m4:37-52)
          const double* sT = s + TT::O_T;
          const double dtx = (sT[c - 1] - 2.0 * temp + sT[c + 1]);

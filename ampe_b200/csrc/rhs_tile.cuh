@@ -24,6 +24,7 @@ template <int ND_, int Q_, int CONC_, bool SYMM_, bool WT_, class SEL_, int TX_,
 struct Tile3 {
    static constexpr int ND = ND_, Q = Q_, CONC = CONC_, TX = TX_, TY = TY_, TZ = TZ_, NT = NT_;
    static constexpr bool SYMM = SYMM_, WT = WT_;
+   static constexpr int PART = 0, CF = CONC_;  // the tile kernels always evaluate every component
    using SEL = SEL_;
    static constexpr int HZ = (ND == 3) ? 1 : 0;
    static constexpr int XH = XH_;

@@ -23,6 +23,13 @@
 #ifndef AMPE_MARCH_MINB
 #define AMPE_MARCH_MINB 2
 #endif
+// split 3D launches (AMPE_B200_SPLIT3D): phase + quaternion part / composition part
+#ifndef AMPE_SPLIT_MINB1
+#define AMPE_SPLIT_MINB1 3
+#endif
+#ifndef AMPE_SPLIT_MINB2
+#define AMPE_SPLIT_MINB2 3
+#endif
 #ifndef AMPE_KKS_MINB
 #define AMPE_KKS_MINB 4
 #endif
