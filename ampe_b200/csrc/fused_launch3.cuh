@@ -153,7 +153,7 @@ static int launch3(const FusedArgs& A, cudaStream_t st, const char** err)
 template <int Q, int CONC, bool WT, class SEL, int PART = 0>
 static int launch_march(const FusedArgs& A, cudaStream_t st, const char** err)
 {
-   using TT = March3<Q, CONC, WT, SEL, AMPE_MY, AMPE_MZ, PART>;
+   using TT = March3<Q, CONC, WT, SEL, (PART == 0) ? AMPE_MY : ((PART == 1) ? AMPE_SPLIT_MY1 : AMPE_SPLIT_MY2), AMPE_MZ, PART>;
    const Params& p = A.p;
    auto kern = rhs_march_kernel<TT>;
    // the dynamic shared-memory attribute belongs to the device's context: one flag per device

@@ -67,6 +67,14 @@ using SelHBSM = SelFixed<AMPE_FLUX_SIMPLE, AMPE_FE_QUADRATIC, 'h', 'a', 'a'>;   
 #define AMPE_STREAM_DIFFS
 #endif
 
+// -DAMPE_ATAN_FAST: straight-line atan_fast (fastmath.cuh, <= 1.9 ulp) in the bias-well term instead of
+// CUDA's atan (A/B builds; the default stays CUDA's until measured and parity-checked on the GPU)
+#ifdef AMPE_ATAN_FAST
+#define AMPE_ATAN(x) atan_fast(x)
+#else
+#define AMPE_ATAN(x) atan(x)
+#endif
+
 // does the parameter record select exactly the compile-time model SEL?
 template <class SEL>
 static bool sel_matches(const Params& p)
@@ -534,7 +542,7 @@ struct Rhs3 {
          // addDrivingForce
          if (free_energy == AMPE_FE_BIASWELL) {
             // computerhsbiaswell (2d/quatrhs.m4:834-843)
-            const double m = p.bias_coeff * atan(p.bias_gamma * (p.meltingT - temp));
+            const double m = p.bias_coeff * AMPE_ATAN(p.bias_gamma * (p.meltingT - temp));
             rhs = rhs + m * phi * (1.0 - phi);
          } else if (CONC == AMPE_CONC_EBS && free_energy == AMPE_FE_CALPHAD) {
             // CALPHADFreeEnergyStrategyBinary.cc:321-323, 638-663: (f_l-f_a) - mu (c_l-c_a) comes

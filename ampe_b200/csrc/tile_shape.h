@@ -30,6 +30,13 @@
 #ifndef AMPE_SPLIT_MINB2
 #define AMPE_SPLIT_MINB2 3
 #endif
+// column height (rows of 32 cells per block) of the two split kernels
+#ifndef AMPE_SPLIT_MY1
+#define AMPE_SPLIT_MY1 AMPE_MY
+#endif
+#ifndef AMPE_SPLIT_MY2
+#define AMPE_SPLIT_MY2 AMPE_MY
+#endif
 #ifndef AMPE_KKS_MINB
 #define AMPE_KKS_MINB 4
 #endif

@@ -2,6 +2,8 @@
 device vectors through the C ABI -- ampe_rhs_eval with fd_flag = 0 / 1, ampe_vec_*, ampe_apply_projection,
 ampe_normalize_quat -- against the SAME integrator template driven by the CPU oracle.  Tight integrator
 tolerances keep the two runs on the same iteration path; the bar is the north_star's 1e-8 on the fields."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -77,6 +79,8 @@ def test_default_options_run():
     assert rc == 0 and stats["steps"] == 5
 
 
+@pytest.mark.skipif(not os.environ.get("AMPE_B200_RUN_EXPERIMENTS"),
+                    reason="written after the last GPU call of round 1: set AMPE_B200_RUN_EXPERIMENTS=1")
 def test_newton_failure_code():
     """a step far beyond what two Newton iterations can absorb comes back as IMPLICIT_ENEWTON instead of a
     silent wrong answer (the CPU run of the same template returns the same code)"""

@@ -13,7 +13,7 @@ for l in sys.stdin:
         d=json.loads(l); print('$label: ms/step %.3f  GCUPS %.2f  launches/step %d  clocks %s'%(d['ms_per_step'], d['value'], d['gpu_launches']//d['steps'], d['clocks']['sm_mhz']))
     elif 'rror' in l: print(l.strip()[:300])"
 }
-python -m pytest tests/test_gpu_widening_zz_split3d.py -q -m gpu 2>&1 | tail -3
+AMPE_B200_RUN_EXPERIMENTS=1 python -m pytest tests/test_gpu_widening_zz_split3d.py tests/test_gpu_widening_z_implicit.py -q -m gpu 2>&1 | tail -3
 for rep in 1 2; do
   run fused X=1
   run split-default AMPE_B200_SPLIT3D=1
