@@ -1,0 +1,453 @@
+// Block preconditioners of the CVODE Newton-Krylov loop on the device, behind
+// the C ABI of include/ampe_b200_precond.h:
+//   ampe_mg_set_elliptic   EllipticFACOps::setM / setC / setD* + PoissonSpecifications
+//                          (PhaseFACOps.cc:33-51, ConcFACOps.cc:19-50, QuatIntegrator.cc:3340-3346)
+//   ampe_mg_set_quat       QuatFACOps::setOperatorCoefficients (QuatFACOps.cc:735-818) ->
+//                          QuatLevelSolver::setMatrixCoefficients (set_j_ij / set_stencil,
+//                          2d/quatlevelsolver.m4:9-118)
+//   ampe_mg_solve          EllipticFACSolver::solveSystem / QuatSysSolver::solveSystem
+//                          (QuatSysSolver.cc:296-347, including divide/multiplyMobilitySqrt)
+//   ampe_mg_apply          the operator itself (efo_compfluxvardc + efo_compresvarsca,
+//                          2d/ellipticfacops.m4:16-56, 346-393)
+//   ampe_k_phasefacops_setc  PhaseFACOps::setCOnPatchPrivate (PhaseFACOps.cc:100-186)
+// The reference solves its single level with hypre PFMG (third party, not in its tree).  Here:
+// geometric multigrid V-cycles, every level resident in HBM, one thread per cell; the smoother is
+// the reference's red-black Gauss-Seidel update.  Per-cell arithmetic: mg_cell.h.  A FIXED number
+// of cycles from a zero initial guess makes the solve a fixed linear operator, which is what right-
+// preconditioned GMRES needs, and needs no host synchronisation.
+// All kernels are HBM-bound sweeps (a half sweep reads u, f, c, m, the ND face arrays and writes u:
+// (5 + ND) * 8 bytes per updated cell before cache reuse of the neighbours).
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ampe_b200_precond.h"
+#include "ctx_internal.h"
+#include "mg_cell.h"
+
+using ampe_mg_cell::Level;
+
+#define CUDA_OKM(call)                                                                       \
+   do {                                                                                      \
+      cudaError_t e_ = (call);                                                               \
+      if (e_ != cudaSuccess)                                                                 \
+         return ampe_set_err(AMPE_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+   } while (0)
+
+struct ampe_mg {
+   int ndim = 2;
+   int n[3] = {1, 1, 1};
+   double inv_h2[3] = {0, 0, 0};
+   bool with_s = false;          // quaternion block: column multiplier present
+   bool coefficients_set = false;
+   std::vector<Level> levels;
+   std::vector<double*> blocks;  // one allocation per level
+   std::vector<char> two_colour; // level can be red-black coloured (all extents even)
+   int pre = 1, post = 1, coarse = 8;
+   int launches = 0;
+};
+
+namespace {
+using namespace ampe_mg_cell;
+
+constexpr int MT = 256;
+constexpr double JACOBI_OMEGA = 0.8;
+
+struct P3 {
+   const double* a[3];
+};
+
+long long cells(const Level& L) { return (long long)L.n[0] * L.n[1] * L.n[2]; }
+int grid_for(long long n)
+{
+   long long b = (n + MT - 1) / MT;
+   const long long cap = 148LL * 32;  // grid-stride beyond 32 blocks per SM
+   if (b > cap) b = cap;
+   return (int)(b < 1 ? 1 : b);
+}
+
+__device__ __forceinline__ void decode(const Level& L, long long idx, int& i, int& j, int& k)
+{
+   i = (int)(idx % L.n[0]);
+   const long long t = idx / L.n[0];
+   j = (int)(t % L.n[1]);
+   k = (int)(t / L.n[1]);
+}
+
+__global__ void mg_smooth_rb_kernel(Level L, int colour)
+{
+   // one thread per cell of the colour: (i + j + k) & 1 == colour; n[0] is even on these levels
+   const int h0 = L.n[0] >> 1;
+   const long long total = (long long)h0 * L.n[1] * L.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x) {
+      const int ii = (int)(idx % h0);
+      const long long t = idx / h0;
+      const int j = (int)(t % L.n[1]);
+      const int k = (int)(t / L.n[1]);
+      const int i = 2 * ii + ((j + k + colour) & 1);
+      mg_smooth_cell(L, i, j, k);
+   }
+}
+__global__ void mg_residual_kernel(Level L)
+{
+   const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x) {
+      int i, j, k;
+      decode(L, idx, i, j, k);
+      mg_residual_cell(L, i, j, k);
+   }
+}
+__global__ void mg_jacobi_kernel(Level L, double omega)
+{
+   const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x) {
+      int i, j, k;
+      decode(L, idx, i, j, k);
+      mg_jacobi_cell(L, omega, i, j, k);
+   }
+}
+__global__ void mg_restrict_kernel(Level F, Level C)
+{
+   const long long total = (long long)C.n[0] * C.n[1] * C.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x) {
+      int i, j, k;
+      decode(C, idx, i, j, k);
+      mg_restrict_cell(F, C, i, j, k);
+   }
+}
+__global__ void mg_coarsen_kernel(Level F, Level C)
+{
+   const long long total = (long long)C.n[0] * C.n[1] * C.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x) {
+      int i, j, k;
+      decode(C, idx, i, j, k);
+      mg_coarsen_cell(F, C, i, j, k);
+   }
+}
+__global__ void mg_prolong_kernel(Level C, Level F)
+{
+   const long long total = (long long)F.n[0] * F.n[1] * F.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x) {
+      int i, j, k;
+      decode(F, idx, i, j, k);
+      mg_prolong_cell(C, F, i, j, k);
+   }
+}
+__global__ void mg_apply_kernel(Level L, const double* u, double* out)
+{
+   const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x) {
+      int i, j, k;
+      decode(L, idx, i, j, k);
+      out[idx] = mg_apply_cell(L, u, i, j, k);
+   }
+}
+// f = rhs (divided by s: QuatFACOps::divideMobilitySqrt), u = 0
+__global__ void mg_load_kernel(Level L, const double* rhs, int symmetrized)
+{
+   const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x) {
+      L.f[idx] = (symmetrized && L.s) ? rhs[idx] / L.s[idx] : rhs[idx];
+      L.u[idx] = 0.0;
+   }
+}
+// soln = u (times s: QuatFACOps::multiplyMobilitySqrt)
+__global__ void mg_store_kernel(Level L, double* soln, int symmetrized)
+{
+   const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x)
+      soln[idx] = (symmetrized && L.s) ? L.u[idx] * L.s[idx] : L.u[idx];
+}
+__global__ void mg_set_elliptic_kernel(Level L, const double* m, int ngm, double m_const, const double* c,
+                                       int ngc, double c_const, P3 d, P3 d2, int have_d, int have_d2, int ngd,
+                                       double d_scale, double d_const, double ih0, double ih1, double ih2)
+{
+   const double inv_h2[3] = {ih0, ih1, ih2};
+   const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x) {
+      int i, j, k;
+      decode(L, idx, i, j, k);
+      mg_set_elliptic_cell(L, m, ngm, m_const, c, ngc, c_const, have_d ? d.a : nullptr,
+                           have_d2 ? d2.a : nullptr, ngd, d_scale, d_const, inv_h2, i, j, k);
+   }
+}
+__global__ void mg_set_quat_kernel(Level L, double gamma, const double* mobility, int ngm, P3 fc, int ngfc,
+                                   double ih0, double ih1, double ih2)
+{
+   const double inv_h2[3] = {ih0, ih1, ih2};
+   const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x) {
+      int i, j, k;
+      decode(L, idx, i, j, k);
+      mg_set_quat_cell(L, gamma, mobility, ngm, fc.a, ngfc, inv_h2, i, j, k);
+   }
+}
+// PhaseFACOps::setCOnPatchPrivate: C = 1 + gamma m w g''(phi)
+__global__ void phasefacops_setc_kernel(Level L, const double* phi, int ngphi, const double* m, int ngm,
+                                        double gamma, double well_scale, char well_type, double* c, int ngc)
+{
+   const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x) {
+      int i, j, k;
+      decode(L, idx, i, j, k);
+      const double p = phi[mg_samrai_index(L, -1, ngphi, i, j, k)];
+      const double mm = m[mg_samrai_index(L, -1, ngm, i, j, k)];
+      // second_deriv_well_func (functions.f): 'd' 32 (1 + 6 phi (phi - 1)), 's' 2
+      const double g2 = (well_type == 's') ? 2.0 : 32.0 * (1.0 + 6.0 * p * (p - 1.0));
+      const double gamma_m = gamma * mm;
+      c[mg_samrai_index(L, -1, ngc, i, j, k)] = 1.0 + gamma_m * well_scale * g2;
+   }
+}
+
+void smooth(ampe_mg* g, int l, int sweeps, cudaStream_t st)
+{
+   const Level& L = g->levels[l];
+   const long long nc = cells(L);
+   for (int s = 0; s < sweeps; s++) {
+      if (g->two_colour[l]) {
+         mg_smooth_rb_kernel<<<grid_for(nc / 2), MT, 0, st>>>(L, 0);
+         mg_smooth_rb_kernel<<<grid_for(nc / 2), MT, 0, st>>>(L, 1);
+      } else {
+         mg_residual_kernel<<<grid_for(nc), MT, 0, st>>>(L);
+         mg_jacobi_kernel<<<grid_for(nc), MT, 0, st>>>(L, JACOBI_OMEGA);
+      }
+      g->launches += 2;
+   }
+}
+
+void vcycle(ampe_mg* g, cudaStream_t st)
+{
+   const int nl = (int)g->levels.size();
+   for (int l = 0; l + 1 < nl; l++) {
+      smooth(g, l, g->pre, st);
+      mg_residual_kernel<<<grid_for(cells(g->levels[l])), MT, 0, st>>>(g->levels[l]);
+      mg_restrict_kernel<<<grid_for(cells(g->levels[l + 1])), MT, 0, st>>>(g->levels[l], g->levels[l + 1]);
+      g->launches += 2;
+   }
+   smooth(g, nl - 1, g->coarse, st);
+   for (int l = nl - 2; l >= 0; l--) {
+      mg_prolong_kernel<<<grid_for(cells(g->levels[l])), MT, 0, st>>>(g->levels[l + 1], g->levels[l]);
+      g->launches += 1;
+      smooth(g, l, g->post, st);
+   }
+}
+
+int build_coarse(ampe_mg* g, cudaStream_t st)
+{
+   for (size_t l = 0; l + 1 < g->levels.size(); l++) {
+      mg_coarsen_kernel<<<grid_for(cells(g->levels[l + 1])), MT, 0, st>>>(g->levels[l], g->levels[l + 1]);
+      g->launches += 1;
+   }
+   CUDA_OKM(cudaGetLastError());
+   g->coefficients_set = true;
+   return AMPE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_scale, ampe_mg** out)
+{
+   if (!out || !n || !dx || (ndim != 2 && ndim != 3)) return ampe_set_err(AMPE_EINVAL, "ampe_mg_create: bad argument");
+   int ndev = 0;
+   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+      return ampe_set_err(AMPE_ENOGPU, "ampe_mg_create: no CUDA device (there is no CPU fallback)");
+   for (int d = 0; d < ndim; d++)
+      if (n[d] < 1 || !(dx[d] > 0.0)) return ampe_set_err(AMPE_EINVAL, "ampe_mg_create: bad extent or spacing");
+   ampe_mg* g = new ampe_mg;
+   g->ndim = ndim;
+   g->with_s = with_column_scale != 0;
+   for (int d = 0; d < 3; d++) {
+      g->n[d] = d < ndim ? n[d] : 1;
+      g->inv_h2[d] = d < ndim ? 1.0 / (dx[d] * dx[d]) : 0.0;
+   }
+   // levels: halve every direction while all extents are even and the coarse extents stay >= 2
+   int cur[3] = {g->n[0], g->n[1], g->n[2]};
+   for (int l = 0; l < 16; l++) {
+      Level L;
+      L.ndim = ndim;
+      for (int d = 0; d < 3; d++) L.n[d] = cur[d];
+      const long long nc = (long long)cur[0] * cur[1] * cur[2];
+      const int narr = 2 + (g->with_s ? 1 : 0) + ndim + 3;
+      double* blk = nullptr;
+      cudaError_t e = cudaMalloc(&blk, sizeof(double) * nc * narr);
+      if (e != cudaSuccess) {
+         for (double* b : g->blocks) cudaFree(b);
+         delete g;
+         return ampe_set_err(AMPE_ECUDA, std::string("ampe_mg_create: cudaMalloc: ") + cudaGetErrorString(e));
+      }
+      cudaMemset(blk, 0, sizeof(double) * nc * narr);
+      g->blocks.push_back(blk);
+      double* p = blk;
+      L.c = p, p += nc;
+      L.m = p, p += nc;
+      L.s = nullptr;
+      if (g->with_s) L.s = p, p += nc;
+      for (int d = 0; d < 3; d++) L.d[d] = nullptr;
+      for (int d = 0; d < ndim; d++) L.d[d] = p, p += nc;
+      L.u = p, p += nc;
+      L.f = p, p += nc;
+      L.r = p, p += nc;
+      g->levels.push_back(L);
+      bool even = true;
+      for (int d = 0; d < ndim; d++) even = even && (cur[d] % 2 == 0);
+      g->two_colour.push_back(even ? 1 : 0);
+      bool can = even;
+      for (int d = 0; d < ndim; d++) can = can && (cur[d] / 2 >= 2);
+      if (!can) break;
+      for (int d = 0; d < ndim; d++) cur[d] /= 2;
+   }
+   *out = g;
+   return AMPE_OK;
+}
+
+int ampe_mg_destroy(ampe_mg* g)
+{
+   if (!g) return AMPE_OK;
+   for (double* b : g->blocks) cudaFree(b);
+   delete g;
+   return AMPE_OK;
+}
+
+int ampe_mg_num_levels(const ampe_mg* g) { return g ? (int)g->levels.size() : 0; }
+int ampe_mg_last_launch_count(const ampe_mg* g) { return g ? g->launches : 0; }
+
+int ampe_mg_set_sweeps(ampe_mg* g, int pre, int post, int coarse)
+{
+   if (!g || pre < 0 || post < 0 || coarse < 1 || pre + post < 1)
+      return ampe_set_err(AMPE_EINVAL, "ampe_mg_set_sweeps: bad argument");
+   g->pre = pre, g->post = post, g->coarse = coarse;
+   return AMPE_OK;
+}
+
+int ampe_mg_level_extents(const ampe_mg* g, int level, int* n_out)
+{
+   if (!g || !n_out || level < 0 || level >= (int)g->levels.size())
+      return ampe_set_err(AMPE_EINVAL, "ampe_mg_level_extents: bad argument");
+   for (int d = 0; d < 3; d++) n_out[d] = g->levels[level].n[d];
+   return AMPE_OK;
+}
+
+int ampe_mg_copy_level(ampe_mg* g, int level, int which, double* out, void* stream)
+{
+   if (!g || !out || level < 0 || level >= (int)g->levels.size() || which < 0 || which > 5)
+      return ampe_set_err(AMPE_EINVAL, "ampe_mg_copy_level: bad argument");
+   const Level& L = g->levels[level];
+   const double* src = which == 0 ? L.c : which == 1 ? L.m : which == 2 ? L.s : L.d[which - 3];
+   if (!src) return ampe_set_err(AMPE_EINVAL, "ampe_mg_copy_level: this operator has no such array");
+   CUDA_OKM(cudaMemcpyAsync(out, src, sizeof(double) * cells(L), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+   return AMPE_OK;
+}
+
+int ampe_mg_set_elliptic(ampe_mg* g, const double* m, int ngm, double m_const, const double* c, int ngc,
+                         double c_const, const double* const* d, const double* const* d2, int ngd,
+                         double d_scale, double d_const, void* stream)
+{
+   if (!g) return ampe_set_err(AMPE_EINVAL, "ampe_mg_set_elliptic: NULL solver");
+   if (g->with_s) return ampe_set_err(AMPE_EINVAL, "ampe_mg_set_elliptic: solver was created for the quaternion block");
+   if (d2 && !d) return ampe_set_err(AMPE_EINVAL, "ampe_mg_set_elliptic: second diffusion array without the first");
+   P3 p = {{nullptr, nullptr, nullptr}}, p2 = {{nullptr, nullptr, nullptr}};
+   for (int a = 0; a < g->ndim; a++) {
+      if (d) {
+         if (!d[a]) return ampe_set_err(AMPE_EINVAL, "ampe_mg_set_elliptic: NULL diffusion side array");
+         p.a[a] = d[a];
+      }
+      if (d2) {
+         if (!d2[a]) return ampe_set_err(AMPE_EINVAL, "ampe_mg_set_elliptic: NULL diffusion side array");
+         p2.a[a] = d2[a];
+      }
+   }
+   cudaStream_t st = (cudaStream_t)stream;
+   g->launches = 0;
+   const Level& L = g->levels[0];
+   mg_set_elliptic_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, m, ngm, m_const, c, ngc, c_const, p, p2, d ? 1 : 0,
+                                                             d2 ? 1 : 0, ngd, d_scale, d_const, g->inv_h2[0],
+                                                             g->inv_h2[1], g->inv_h2[2]);
+   g->launches += 1;
+   return build_coarse(g, st);
+}
+
+int ampe_mg_set_quat(ampe_mg* g, double gamma, const double* mobility, int ngm, const double* const* face_coef,
+                     int ngfc, void* stream)
+{
+   if (!g || !mobility || !face_coef) return ampe_set_err(AMPE_EINVAL, "ampe_mg_set_quat: NULL argument");
+   if (!g->with_s) return ampe_set_err(AMPE_EINVAL, "ampe_mg_set_quat: solver was created without the column scale");
+   P3 p = {{nullptr, nullptr, nullptr}};
+   for (int a = 0; a < g->ndim; a++) {
+      if (!face_coef[a]) return ampe_set_err(AMPE_EINVAL, "ampe_mg_set_quat: NULL face coefficient array");
+      p.a[a] = face_coef[a];
+   }
+   cudaStream_t st = (cudaStream_t)stream;
+   g->launches = 0;
+   const Level& L = g->levels[0];
+   mg_set_quat_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, gamma, mobility, ngm, p, ngfc, g->inv_h2[0],
+                                                         g->inv_h2[1], g->inv_h2[2]);
+   g->launches += 1;
+   return build_coarse(g, st);
+}
+
+int ampe_mg_solve(ampe_mg* g, const double* rhs, double* soln, int ncycles, int symmetrized, void* stream)
+{
+   if (!g || !rhs || !soln || ncycles < 1) return ampe_set_err(AMPE_EINVAL, "ampe_mg_solve: bad argument");
+   if (!g->coefficients_set) return ampe_set_err(AMPE_EINVAL, "ampe_mg_solve: operator coefficients not set");
+   cudaStream_t st = (cudaStream_t)stream;
+   g->launches = 0;
+   const Level& L = g->levels[0];
+   mg_load_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, rhs, symmetrized);
+   for (int c = 0; c < ncycles; c++) vcycle(g, st);
+   mg_store_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, soln, symmetrized);
+   g->launches += 2;
+   CUDA_OKM(cudaGetLastError());
+   return AMPE_OK;
+}
+
+int ampe_mg_apply(ampe_mg* g, const double* u, double* out, void* stream)
+{
+   if (!g || !u || !out || u == out) return ampe_set_err(AMPE_EINVAL, "ampe_mg_apply: bad argument");
+   if (!g->coefficients_set) return ampe_set_err(AMPE_EINVAL, "ampe_mg_apply: operator coefficients not set");
+   const Level& L = g->levels[0];
+   mg_apply_kernel<<<grid_for(cells(L)), MT, 0, (cudaStream_t)stream>>>(L, u, out);
+   g->launches = 1;
+   CUDA_OKM(cudaGetLastError());
+   return AMPE_OK;
+}
+
+int ampe_k_phasefacops_setc(int ndim, const int* ifirst, const int* ilast, const double* phi, int ngphi,
+                            const double* m, int ngm, double gamma, double phi_well_scale,
+                            const char* phi_well_func_type, double* c, int ngc, void* stream)
+{
+   if (!ifirst || !ilast || !phi || !m || !c || !phi_well_func_type || (ndim != 2 && ndim != 3))
+      return ampe_set_err(AMPE_EINVAL, "ampe_k_phasefacops_setc: bad argument");
+   const char t = phi_well_func_type[0];
+   if (t != 'd' && t != 's')
+      return ampe_set_err(AMPE_EINVAL, "ampe_k_phasefacops_setc: well type must be 'd' or 's' (functions.f)");
+   Level L;
+   L.ndim = ndim;
+   for (int d = 0; d < 3; d++) {
+      if (d < ndim && ifirst[d] != 0)
+         return ampe_set_err(AMPE_EINVAL, "ampe_k_phasefacops_setc: the level box starts at 0");
+      L.n[d] = d < ndim ? ilast[d] - ifirst[d] + 1 : 1;
+   }
+   L.c = L.m = L.s = L.u = L.f = L.r = nullptr;
+   L.d[0] = L.d[1] = L.d[2] = nullptr;
+   phasefacops_setc_kernel<<<grid_for(cells(L)), MT, 0, (cudaStream_t)stream>>>(L, phi, ngphi, m, ngm, gamma,
+                                                                              phi_well_scale, t, c, ngc);
+   CUDA_OKM(cudaGetLastError());
+   return AMPE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,244 @@
+// Per-cell arithmetic of the block preconditioners: one periodic uniform
+// level of AMPE's cell-centred block operators and the geometric multigrid that inverts them.
+//
+// Operators (reference):
+//   scalar blocks  A u = M div(D grad u) + C u       EllipticFACOps.h:35, 2d/ellipticfacops.m4:16-56
+//                                                    (efo_compfluxvardc2d) and :346-393 (efo_compresvarsca2d)
+//     phase        M = phase mobility, C = 1 + gamma M w g''(phi), D = -gamma eps^2
+//                                                    PhaseFACOps.cc:33-51, :100-186
+//     composition  M = conc mobility, C = 1, D = -gamma D_pfm         ConcFACOps.cc:19-50
+//     temperature  M = 1, C = 1, D = -gamma kappa                     QuatIntegrator.cc:3340-3346
+//   quaternion     A w = w + gamma sqrt(m) div(fc grad(sqrt(m) w)), one matrix for every component
+//                                                    2d/quatlevelsolver.m4:9-118 (set_j_ij2d, set_stencil2d)
+// Both are written   (A u)_i = c_i u_i + m_i sum_faces d_f (s_nb u_nb - s_i u_i),   d_f = D_f / h_f^2,
+// with s = 1 for the scalar blocks and c = 1, m = gamma sqrt(mobility), s = sqrt(mobility) for the
+// quaternion block.
+//
+// Smoother: the reference's red-black Gauss-Seidel update (efo_rbgswithfluxmaxvardcvarsf2d,
+// 2d/ellipticfacops.m4:60-130): u_i += (f - A u)_i / diag_i.  The reference hands the single level
+// to hypre PFMG (not in its tree); here the level is inverted by V-cycles over rediscretised
+// coarse levels (coefficients averaged, residual averaged, cell-centred (bi/tri)linear prolongation).
+//
+// The functions are __host__ __device__ so that the very same arithmetic can be looped on the host
+// by the
+// test infrastructure outside this package -- the product only calls them from the mg.cu kernels.
+#pragma once
+#ifdef __CUDACC__
+#define MG_HD __host__ __device__ __forceinline__
+#else
+#define MG_HD inline
+#endif
+
+namespace ampe_mg_cell {
+
+struct Level {
+   int ndim;
+   int n[3];      // cells per direction (n[2] = 1 in 2D); periodic
+   double* c;     // cell: C
+   double* m;     // cell: row multiplier
+   double* s;     // cell: column multiplier, or nullptr (= 1)
+   double* d[3];  // lower-face coefficient per direction, divided by h^2
+   double* u;     // solution / correction
+   double* f;     // right-hand side
+   double* r;     // residual (and Jacobi work array)
+};
+
+MG_HD long long mg_index(const Level& L, int i, int j, int k)
+{
+   return (long long)i + (long long)L.n[0] * ((long long)j + (long long)L.n[1] * (long long)k);
+}
+MG_HD int mg_up(int i, int n) { return i + 1 == n ? 0 : i + 1; }
+MG_HD int mg_dn(int i, int n) { return i == 0 ? n - 1 : i - 1; }
+
+// sum over the faces of cell (i,j,k) of d_f (s_nb u_nb - s_i u_i), and sum of d_f
+MG_HD void mg_face_sums(const Level& L, const double* u, int i, int j, int k, double& flux, double& dsum)
+{
+   const long long o = mg_index(L, i, j, k);
+   const double si = L.s ? L.s[o] : 1.0;
+   const double ui = si * u[o];
+   flux = 0.0;
+   dsum = 0.0;
+   {
+      const long long ou = mg_index(L, mg_up(i, L.n[0]), j, k), od = mg_index(L, mg_dn(i, L.n[0]), j, k);
+      const double du = L.d[0][ou], dd = L.d[0][o];
+      const double uu = (L.s ? L.s[ou] : 1.0) * u[ou], ud = (L.s ? L.s[od] : 1.0) * u[od];
+      flux += du * (uu - ui) - dd * (ui - ud);
+      dsum += du + dd;
+   }
+   {
+      const long long ou = mg_index(L, i, mg_up(j, L.n[1]), k), od = mg_index(L, i, mg_dn(j, L.n[1]), k);
+      const double du = L.d[1][ou], dd = L.d[1][o];
+      const double uu = (L.s ? L.s[ou] : 1.0) * u[ou], ud = (L.s ? L.s[od] : 1.0) * u[od];
+      flux += du * (uu - ui) - dd * (ui - ud);
+      dsum += du + dd;
+   }
+   if (L.ndim == 3) {
+      const long long ou = mg_index(L, i, j, mg_up(k, L.n[2])), od = mg_index(L, i, j, mg_dn(k, L.n[2]));
+      const double du = L.d[2][ou], dd = L.d[2][o];
+      const double uu = (L.s ? L.s[ou] : 1.0) * u[ou], ud = (L.s ? L.s[od] : 1.0) * u[od];
+      flux += du * (uu - ui) - dd * (ui - ud);
+      dsum += du + dd;
+   }
+}
+
+// (A u)_i
+MG_HD double mg_apply_cell(const Level& L, const double* u, int i, int j, int k)
+{
+   double flux, dsum;
+   mg_face_sums(L, u, i, j, k, flux, dsum);
+   const long long o = mg_index(L, i, j, k);
+   return L.c[o] * u[o] + L.m[o] * flux;
+}
+
+// r_i = f_i - (A u)_i   (efo_compresvarsca2d)
+MG_HD void mg_residual_cell(const Level& L, int i, int j, int k)
+{
+   const long long o = mg_index(L, i, j, k);
+   L.r[o] = L.f[o] - mg_apply_cell(L, L.u, i, j, k);
+}
+
+// Gauss-Seidel update of one cell (efo_rbgswithfluxmaxvardcvarsf2d): u += residual / diagonal
+MG_HD void mg_smooth_cell(const Level& L, int i, int j, int k)
+{
+   double flux, dsum;
+   mg_face_sums(L, L.u, i, j, k, flux, dsum);
+   const long long o = mg_index(L, i, j, k);
+   const double si = L.s ? L.s[o] : 1.0;
+   const double residual = L.f[o] - (L.c[o] * L.u[o] + L.m[o] * flux);
+   const double diag = L.c[o] - L.m[o] * si * dsum;
+   L.u[o] += residual / diag;
+}
+
+// damped Jacobi for levels whose periodic wrap breaks the two-colouring (an odd extent):
+// u += omega r / diagonal with r computed beforehand by mg_residual_cell
+MG_HD void mg_jacobi_cell(const Level& L, double omega, int i, int j, int k)
+{
+   double dsum = 0.0;
+   const long long o = mg_index(L, i, j, k);
+   dsum += L.d[0][mg_index(L, mg_up(i, L.n[0]), j, k)] + L.d[0][o];
+   dsum += L.d[1][mg_index(L, i, mg_up(j, L.n[1]), k)] + L.d[1][o];
+   if (L.ndim == 3) dsum += L.d[2][mg_index(L, i, j, mg_up(k, L.n[2]))] + L.d[2][o];
+   const double si = L.s ? L.s[o] : 1.0;
+   const double diag = L.c[o] - L.m[o] * si * dsum;
+   L.u[o] += omega * L.r[o] / diag;
+}
+
+// coarse cell (I,J,K): f_c = mean of the children's residuals, u_c = 0
+MG_HD void mg_restrict_cell(const Level& F, const Level& C, int I, int J, int K)
+{
+   const int nk = F.ndim == 3 ? 2 : 1;
+   double acc = 0.0;
+   for (int c = 0; c < nk; c++)
+      for (int b = 0; b < 2; b++)
+         for (int a = 0; a < 2; a++) acc += F.r[mg_index(F, 2 * I + a, 2 * J + b, (F.ndim == 3 ? 2 * K : 0) + c)];
+   const long long o = mg_index(C, I, J, K);
+   C.f[o] = acc * (F.ndim == 3 ? 0.125 : 0.25);
+   C.u[o] = 0.0;
+}
+
+// coarse coefficients of cell (I,J,K): cell fields are the children's mean; the lower face in
+// direction a is the mean of the fine faces it covers, divided by 4 (h doubles)
+MG_HD void mg_coarsen_cell(const Level& F, const Level& C, int I, int J, int K)
+{
+   const int nk = F.ndim == 3 ? 2 : 1;
+   const int k0 = F.ndim == 3 ? 2 * K : 0;
+   const double wcell = F.ndim == 3 ? 0.125 : 0.25;
+   const long long o = mg_index(C, I, J, K);
+   double ac = 0.0, am = 0.0, as = 0.0;
+   for (int c = 0; c < nk; c++)
+      for (int b = 0; b < 2; b++)
+         for (int a = 0; a < 2; a++) {
+            const long long of = mg_index(F, 2 * I + a, 2 * J + b, k0 + c);
+            ac += F.c[of];
+            am += F.m[of];
+            if (F.s) as += F.s[of];
+         }
+   C.c[o] = ac * wcell;
+   C.m[o] = am * wcell;
+   if (C.s) C.s[o] = as * wcell;
+   const double wface = (F.ndim == 3 ? 0.25 : 0.5) * 0.25;
+   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+   for (int c = 0; c < nk; c++)
+      for (int b = 0; b < 2; b++) a0 += F.d[0][mg_index(F, 2 * I, 2 * J + b, k0 + c)];
+   for (int c = 0; c < nk; c++)
+      for (int a = 0; a < 2; a++) a1 += F.d[1][mg_index(F, 2 * I + a, 2 * J, k0 + c)];
+   C.d[0][o] = a0 * wface;
+   C.d[1][o] = a1 * wface;
+   if (F.ndim == 3) {
+      for (int b = 0; b < 2; b++)
+         for (int a = 0; a < 2; a++) a2 += F.d[2][mg_index(F, 2 * I + a, 2 * J + b, k0)];
+      C.d[2][o] = a2 * wface;
+   }
+}
+
+// fine cell (i,j,k): u_f += cell-centred (bi/tri)linear interpolation of the coarse correction
+// (weights 3/4 towards the parent, 1/4 towards the parent's neighbour on the child's side)
+MG_HD void mg_prolong_cell(const Level& C, const Level& F, int i, int j, int k)
+{
+   const int I = i >> 1, J = j >> 1, K = F.ndim == 3 ? (k >> 1) : 0;
+   const int I2 = (i & 1) ? mg_up(I, C.n[0]) : mg_dn(I, C.n[0]);
+   const int J2 = (j & 1) ? mg_up(J, C.n[1]) : mg_dn(J, C.n[1]);
+   double e;
+   if (F.ndim == 3) {
+      const int K2 = (k & 1) ? mg_up(K, C.n[2]) : mg_dn(K, C.n[2]);
+      const double ea = 0.75 * (0.75 * C.u[mg_index(C, I, J, K)] + 0.25 * C.u[mg_index(C, I2, J, K)]) +
+                        0.25 * (0.75 * C.u[mg_index(C, I, J2, K)] + 0.25 * C.u[mg_index(C, I2, J2, K)]);
+      const double eb = 0.75 * (0.75 * C.u[mg_index(C, I, J, K2)] + 0.25 * C.u[mg_index(C, I2, J, K2)]) +
+                        0.25 * (0.75 * C.u[mg_index(C, I, J2, K2)] + 0.25 * C.u[mg_index(C, I2, J2, K2)]);
+      e = 0.75 * ea + 0.25 * eb;
+   } else {
+      e = 0.75 * (0.75 * C.u[mg_index(C, I, J, 0)] + 0.25 * C.u[mg_index(C, I2, J, 0)]) +
+          0.25 * (0.75 * C.u[mg_index(C, I, J2, 0)] + 0.25 * C.u[mg_index(C, I2, J2, 0)]);
+   }
+   F.u[mg_index(F, i, j, k)] += e;
+}
+
+// ---- finest-level coefficients from SAMRAI-layout PatchData ------------------------------------
+// element (i,j,k) of a CellData (axis = -1) or of the `axis` array of a SideData with ghost width
+// ng over the box [0, n-1] (pdat_m4arrdim*.i): Fortran order
+MG_HD long long mg_samrai_index(const Level& L, int axis, int ng, int i, int j, int k)
+{
+   const int g2 = L.ndim == 3 ? ng : 0;
+   const long long n0 = L.n[0] + 2 * ng + (axis == 0), n1 = L.n[1] + 2 * ng + (axis == 1);
+   return (long long)(i + ng) + n0 * ((long long)(j + ng) + n1 * (long long)(k + g2));
+}
+
+// scalar block (EllipticFACOps::setM / setC / setD*): arrays may be NULL = the constant
+MG_HD void mg_set_elliptic_cell(const Level& L, const double* m, int ngm, double m_const, const double* c,
+                                int ngc, double c_const, const double* const* d, const double* const* d2,
+                                int ngd, double d_scale, double d_const, const double* inv_h2, int i, int j,
+                                int k)
+{
+   const long long o = mg_index(L, i, j, k);
+   L.m[o] = m ? m[mg_samrai_index(L, -1, ngm, i, j, k)] : m_const;
+   L.c[o] = c ? c[mg_samrai_index(L, -1, ngc, i, j, k)] : c_const;
+   for (int a = 0; a < L.ndim; a++) {
+      double D = d_const;
+      if (d) {
+         const long long os = mg_samrai_index(L, a, ngd, i, j, k);
+         D = d[a][os];
+         if (d2) D += d2[a][os];
+         D *= d_scale;
+      }
+      L.d[a][o] = D * inv_h2[a];
+   }
+}
+
+// quaternion block (QuatFACOps::setOperatorCoefficients, QuatFACOps.cc:735-818: sqrt of the mobility;
+// QuatLevelSolver::setMatrixCoefficients -> set_j_ij / set_stencil)
+MG_HD void mg_set_quat_cell(const Level& L, double gamma, const double* mobility, int ngm,
+                            const double* const* face_coef, int ngfc, const double* inv_h2, int i, int j, int k)
+{
+   const long long o = mg_index(L, i, j, k);
+#ifdef __CUDA_ARCH__
+   const double sq = ::sqrt(mobility[mg_samrai_index(L, -1, ngm, i, j, k)]);
+#else
+   const double sq = __builtin_sqrt(mobility[mg_samrai_index(L, -1, ngm, i, j, k)]);
+#endif
+   L.s[o] = sq;
+   L.m[o] = gamma * sq;
+   L.c[o] = 1.0;
+   for (int a = 0; a < L.ndim; a++) L.d[a][o] = face_coef[a][mg_samrai_index(L, a, ngfc, i, j, k)] * inv_h2[a];
+}
+
+}  // namespace ampe_mg_cell

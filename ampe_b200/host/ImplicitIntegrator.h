@@ -12,7 +12,10 @@
 //   * after the nonlinear solve the projection hook (QuatIntegrator::applyProjection,
 //     QuatIntegrator.cc:3911-3962) puts the quaternions back on the unit sphere, then the
 //     post-step work of QuatModel::Advance (normalizeQuat, resetRefPhaseConcentrations).
-// CVODE itself (variable step / order, error test, preconditioning) is out of scope: the step is
+//   * optional RIGHT preconditioning by the backend's block preconditioner (the
+//     reference's CVSpgmrPrecondSet / CVSpgmrPrecondSolve, QuatIntegrator.cc:3300-3771): set up after
+//     every fd_flag = 0 residual evaluation, applied once per Krylov vector and once to the solution.
+// CVODE itself (variable step / order, error test) is out of scope: the step is
 // fixed and a Newton failure is returned to the caller instead of retried with a smaller step.
 //
 // The algorithm is a template over the vector backend so that the same code drives the device
@@ -35,7 +38,7 @@ struct ImplicitOptions {
 
 struct ImplicitStats {
    long steps = 0, rhs_evals = 0, jtimes_evals = 0, newton_iterations = 0, linear_iterations = 0,
-        projections = 0;
+        projections = 0, precond_setups = 0, precond_solves = 0;
    double last_newton_update = 0.0;  // WRMS norm of the last Newton correction
    double last_linear_residual = 0.0;
 };
@@ -54,6 +57,9 @@ enum { IMPLICIT_OK = 0, IMPLICIT_EINVAL = -1, IMPLICIT_ENEWTON = -20, IMPLICIT_E
 //   int  rhs(double t, const Vec& y, Vec& ydot, int fd_flag)                  0 = success
 //   void applyProjection(double t, const Vec& y, Vec& corr, Vec& err)
 //   void postStep(Vec& y)
+//   bool preconditioned() const                                               false: the two below are not called
+//   int  precondSetup(double t, const Vec& y, double gamma)                   coefficients frozen at y; 0 = ok
+//   void precondSolve(const Vec& r, Vec& z)                                   z ~ (I - gamma J_blockdiag)^-1 r
 template <class Ops>
 class ImplicitIntegrator
 {
@@ -74,6 +80,7 @@ class ImplicitIntegrator
       Vec yprev = d_ops.clone(y), psi = d_ops.clone(y), ycur = d_ops.clone(y), fy = d_ops.clone(y),
           ewt = d_ops.clone(y), res = d_ops.clone(y), delta = d_ops.clone(y), acor = d_ops.clone(y),
           ytmp = d_ops.clone(y), wk = d_ops.clone(y);
+      d_pv = d_ops.clone(y);  // P v of the current Krylov vector
       std::vector<Vec> V;
       for (int j = 0; j <= m; j++) V.push_back(d_ops.clone(y));
       int rc = IMPLICIT_OK;
@@ -114,6 +121,7 @@ class ImplicitIntegrator
       for (auto& v : V) d_ops.release(v);
       Vec* all[] = {&yprev, &psi, &ycur, &fy, &ewt, &res, &delta, &acor, &ytmp, &wk};
       for (Vec* v : all) d_ops.release(*v);
+      d_ops.release(d_pv);
       return rc;
    }
 
@@ -128,6 +136,10 @@ class ImplicitIntegrator
       for (int it = 0; it < d_opt.max_newton_iterations; it++) {
          if (d_ops.rhs(t, ycur, fy, 0) != 0) return IMPLICIT_ERHS;
          d_stats.rhs_evals++;
+         if (d_ops.preconditioned()) {
+            if (d_ops.precondSetup(t, ycur, gamma) != 0) return IMPLICIT_ERHS;
+            d_stats.precond_setups++;
+         }
          // res = -G = psi + gamma f - y
          d_ops.linearSum(1.0, psi, gamma, fy, res);
          d_ops.linearSum(1.0, res, -1.0, ycur, res);
@@ -183,7 +195,14 @@ class ImplicitIntegrator
       d_ops.scale(1.0 / beta, b, V[0]);
       int k = 0;
       for (int j = 0; j < m; j++) {
-         int rc = jtimes(t, gamma, ewt, y, fy, V[j], wk, ytmp);
+         int rc;
+         if (d_ops.preconditioned()) {
+            d_ops.precondSolve(V[j], d_pv);  // right preconditioning: the Krylov space of A P
+            d_stats.precond_solves++;
+            rc = jtimes(t, gamma, ewt, y, fy, d_pv, wk, ytmp);
+         } else {
+            rc = jtimes(t, gamma, ewt, y, fy, V[j], wk, ytmp);
+         }
          if (rc != IMPLICIT_OK) return rc;
          d_stats.linear_iterations++;
          double col2 = 0.0;  // |A v_j|^2 = sum_i H[i][j]^2 (Pythagoras over the orthonormal basis)
@@ -223,10 +242,16 @@ class ImplicitIntegrator
          c[i] = s / H[i][i];
       }
       for (int i = 0; i < k; i++) d_ops.linearSum(1.0, x, c[i], V[i], x);
+      if (d_ops.preconditioned() && k > 0) {
+         d_ops.scale(1.0, x, wk);
+         d_ops.precondSolve(wk, x);  // x = P (sum c_i v_i)
+         d_stats.precond_solves++;
+      }
       return IMPLICIT_OK;  // like CVODE, a reduced residual is accepted; Newton decides
    }
 
    Ops& d_ops;
+   Vec d_pv;
    ImplicitOptions d_opt;
    ImplicitStats d_stats;
 };

@@ -11,6 +11,8 @@
 
 namespace ampe_host {
 
+class QuatIntegrator;
+
 // Device vector backend of ImplicitIntegrator: the solution vector is an ampe_rhs_fields of device
 // arrays; every operation is a C-ABI call into libampe_b200.so (the N_Vector operations CVODE would
 // issue through Sundials_SAMRAIVector, samrai/Sundials_SAMRAIVector.cc).
@@ -18,7 +20,8 @@ class DeviceVectorOps
 {
  public:
    typedef ampe_rhs_fields Vec;
-   DeviceVectorOps(ampe_rhs_ctx* ctx, const ampe_rhs_config& cfg) : d_ctx(ctx), d_cfg(cfg)
+   DeviceVectorOps(ampe_rhs_ctx* ctx, const ampe_rhs_config& cfg, QuatIntegrator* owner = nullptr)
+       : d_ctx(ctx), d_cfg(cfg), d_owner(owner)
    {
       d_ncell = 1;
       for (int d = 0; d < cfg.ndim; d++) d_ncell *= (size_t)cfg.n[d];
@@ -79,6 +82,10 @@ class DeviceVectorOps
       if (kks && d_cfg.free_energy == AMPE_FE_CALPHAD)
          check(ampe_rhs_set_ref_concentrations(d_ctx, nullptr, nullptr, nullptr), "resetRef");
    }
+   // CVSpgmrPrecondSet / CVSpgmrPrecondSolve of the owning QuatIntegrator (defined below the class)
+   inline bool preconditioned() const;
+   inline int precondSetup(double t, const Vec& y, double gamma);
+   inline void precondSolve(const Vec& r, Vec& z);
 
  private:
    void dup(const double* src, double** dst, int depth)
@@ -90,6 +97,7 @@ class DeviceVectorOps
    }
    ampe_rhs_ctx* d_ctx;
    ampe_rhs_config d_cfg;
+   QuatIntegrator* d_owner;
    size_t d_ncell;
    long long d_length;
 };
@@ -257,7 +265,7 @@ class QuatIntegrator
    int integrateImplicit(const ampe_rhs_fields* y, double t0, double dt, int nsteps, const ImplicitOptions& opt,
                          ImplicitStats* stats)
    {
-      DeviceVectorOps ops(d_ctx, d_cfg);
+      DeviceVectorOps ops(d_ctx, d_cfg, this);
       ImplicitIntegrator<DeviceVectorOps> integ(ops, opt);
       ampe_rhs_fields yy = *y;
       const int rc = integ.advance(yy, t0, dt, nsteps);
@@ -271,6 +279,103 @@ class QuatIntegrator
    {
       check(ampe_integrate_fixed(d_ctx, y, work1, work2, t0, dt, nsteps, scheme, nullptr), "integrateFixed");
    }
+
+   // ---- block preconditioners ----------------------------------------------
+   // QuatIntegrator::setupPreconditioners (QuatIntegrator.cc:428-545) with the Preconditioner{} block's
+   // defaults except precond_has_dquatdphi = false (block diagonal).  ncycles = V-cycles per block
+   // solve (the reference iterates FAC cycles to CVODE's delta; a fixed count keeps the
+   // preconditioner a fixed linear operator); 0 switches the preconditioner off.
+   void setupPreconditioners(int ncycles)
+   {
+      const ampe_rhs_config& p = d_cfg;
+      d_precond_cycles = ncycles;
+      d_use_preconditioner = ncycles > 0;
+      if (!d_use_preconditioner) return;
+      if (p.nranks > 1) throw std::runtime_error("setupPreconditioners: single rank only");
+      if (p.with_phase && !d_phase_sys_solver) {
+         d_phase_precond_c_id = cellVar<double>(1, 0);
+         d_phase_sys_solver.reset(new PhaseFACSolver(d_hierarchy, d_phase_precond_c_id));
+      }
+      const bool kks = p.conc_rhs_form == AMPE_CONC_KKS || p.conc_rhs_form == AMPE_CONC_EBS;
+      if (p.with_concentration && kks && !d_conc_sys_solver) {
+         d_conc_sys_solver.reset(new ConcFACSolver(d_hierarchy));
+         d_conc_l_g0_id = cellVar<double>(1, 0);
+         d_conc_a_g0_id = cellVar<double>(1, 0);
+      }
+      if (p.with_unsteady_temperature && !d_temperature_sys_solver)
+         d_temperature_sys_solver.reset(new TemperatureFACSolver(d_hierarchy));
+   }
+   bool usePreconditioner() const { return d_use_preconditioner; }
+   // QuatIntegrator::CVSpgmrPrecondSet(t, y, fy, jok, jcurPtr, gamma) (QuatIntegrator.cc:3300-3376)
+   int CVSpgmrPrecondSet(double t, const ampe_rhs_fields* y, double gamma)
+   {
+      if (!d_use_preconditioner) throw std::runtime_error("CVSpgmrPrecondSet: call setupPreconditioners first");
+      const ampe_rhs_config& p = d_cfg;
+      const bool kks = p.conc_rhs_form == AMPE_CONC_KKS || p.conc_rhs_form == AMPE_CONC_EBS;
+      if (d_use_fused && d_phase_conc_strategy) {
+         // the fused evaluation at this y (the fd_flag = 0 residual evaluation that precedes every
+         // set-up) has already solved the per-cell KKS problem: take c_l, c_a from the context
+         // instead of repeating the Newton solve
+         setCoefficients(t, y, true, false);
+         auto cl0 = d_patch->cell<double>(d_conc_l_g0_id), ca0 = d_patch->cell<double>(d_conc_a_g0_id);
+         check(ampe_rhs_copy_phase_concentrations(d_ctx, cl0->getPointer(), ca0->getPointer(), nullptr),
+               "copy_phase_concentrations");
+         fillScratchField(cl0->getPointer(), d_conc_l_id, 1);
+         fillScratchField(ca0->getPointer(), d_conc_a_id, 1);
+      } else {
+         setCoefficients(t, y, true);
+      }
+      if (p.with_phase)
+         d_phase_sys_solver->setOperatorCoefficients(d_phase_scratch_id, d_phase_mobility_id, p.epsilon_phase, gamma,
+                                                     p.phi_well_scale, "double");
+      if (p.with_unsteady_temperature)
+         d_temperature_sys_solver->setOperatorCoefficients(1., 1., -gamma * p.thermal_diffusivity);
+      if (p.with_concentration && kks) {
+         // setCompositionOperatorCoefficients (:3378-3387): D_pfm = D_l + D_a (EBS,
+         // setDiffusionCoeffForPreconditioner) or D0 (KKS)
+         d_composition_rhs_strategy->setDiffusionCoeff(d_hierarchy, t);
+         d_conc_sys_solver->setOperatorCoefficients(gamma, d_diff0_id,
+                                                    p.conc_rhs_form == AMPE_CONC_EBS ? d_diff1_id : -1,
+                                                    p.conc_mobility);
+      }
+      if (p.evolve_quat)
+         d_quat_sys_solver->setOperatorCoefficients(gamma, d_quat_mobility_id, -1, d_phase_scratch_id,
+                                                    d_temperature_scratch_id, -1, d_quat_grad_side_copy_id,
+                                                    d_quat_scratch_id);
+      d_precond_setups++;
+      return 0;
+   }
+   // QuatIntegrator::CVSpgmrPrecondSolve(t, y, fy, r, z, gamma, delta, lr) (QuatIntegrator.cc:3666-3771):
+   // z_block = A_block^-1 r_block, block by block; r, z: ghost-0 device vectors
+   int CVSpgmrPrecondSolve(const ampe_rhs_fields* r, const ampe_rhs_fields* z)
+   {
+      if (!d_use_preconditioner) throw std::runtime_error("CVSpgmrPrecondSolve: call setupPreconditioners first");
+      const ampe_rhs_config& p = d_cfg;
+      if (p.with_phase) d_phase_sys_solver->solveSystem(z->phase, r->phase, d_precond_cycles);
+      if (p.evolve_quat) d_quat_sys_solver->solveSystem(z->quat, r->quat, d_precond_cycles);
+      if (p.with_unsteady_temperature)
+         d_temperature_sys_solver->solveSystem(z->temperature, r->temperature, d_precond_cycles);
+      if (p.with_concentration) {
+         if (d_conc_sys_solver)
+            d_conc_sys_solver->solveSystem(z->conc, r->conc, d_precond_cycles);
+         else if (z->conc != r->conc)  // Cahn-Hilliard: no block solver, identity
+            cuda_check(cudaMemcpy(z->conc, r->conc, d_ncell * sizeof(double), cudaMemcpyDeviceToDevice),
+                       "CVSpgmrPrecondSolve");
+      }
+      d_precond_solves++;
+      return 0;
+   }
+   // the device multigrid of a block (0 phase, 1 quaternion, 2 composition, 3 temperature), or NULL
+   ampe_mg* preconditionerLevelSolver(int block) const
+   {
+      if (block == 0) return d_phase_sys_solver ? d_phase_sys_solver->levelSolver() : nullptr;
+      if (block == 1) return d_quat_sys_solver ? d_quat_sys_solver->levelSolver() : nullptr;
+      if (block == 2) return d_conc_sys_solver ? d_conc_sys_solver->levelSolver() : nullptr;
+      if (block == 3) return d_temperature_sys_solver ? d_temperature_sys_solver->levelSolver() : nullptr;
+      return nullptr;
+   }
+   long precondSetups() const { return d_precond_setups; }
+   long precondSolves() const { return d_precond_solves; }
 
    std::shared_ptr<Patch> patch() const { return d_patch; }
    ampe_rhs_ctx* fusedContext() const { return d_ctx; }
@@ -420,7 +525,8 @@ class QuatIntegrator
    }
 
    // setCoefficients (:2994-3083)
-   void setCoefficients(double time, const ampe_rhs_fields* y, bool recompute_quat_sidegrad)
+   void setCoefficients(double time, const ampe_rhs_fields* y, bool recompute_quat_sidegrad,
+                        bool solve_phase_concentrations = true)
    {
       (void)time;
       const ampe_rhs_config& p = d_cfg;
@@ -430,7 +536,7 @@ class QuatIntegrator
       if (p.with_concentration) fillScratchField(y->conc, d_conc_scratch_id, 1);
       if (p.with_unsteady_temperature) fillScratchField(y->temperature, d_temperature_scratch_id, 1);
       if (p.evolve_quat) computeQuatGradients(recompute_quat_sidegrad);
-      if (d_phase_conc_strategy) {
+      if (d_phase_conc_strategy && solve_phase_concentrations) {
          int nfail = d_phase_conc_strategy->computePhaseConcentrations(
              d_hierarchy, d_temperature_scratch_id, d_phase_scratch_id, -1, d_conc_scratch_id);
          if (nfail > 0) throw std::runtime_error("computePhaseConcentrations: Newton failed");
@@ -508,6 +614,21 @@ class QuatIntegrator
    std::shared_ptr<CompositionRHSStrategy> d_composition_rhs_strategy;
    std::shared_ptr<PhaseConcentrationsStrategy> d_phase_conc_strategy;
    std::shared_ptr<TemperatureRHSStrategy> d_temperature_rhs_strategy;
+   // block preconditioners (named like the reference's members, QuatIntegrator.h)
+   bool d_use_preconditioner = false;
+   int d_precond_cycles = 0;
+   long d_precond_setups = 0, d_precond_solves = 0;
+   int d_phase_precond_c_id = -1, d_conc_l_g0_id = -1, d_conc_a_g0_id = -1;
+   std::shared_ptr<PhaseFACSolver> d_phase_sys_solver;
+   std::shared_ptr<ConcFACSolver> d_conc_sys_solver;
+   std::shared_ptr<TemperatureFACSolver> d_temperature_sys_solver;
 };
+
+inline bool DeviceVectorOps::preconditioned() const { return d_owner && d_owner->usePreconditioner(); }
+inline int DeviceVectorOps::precondSetup(double t, const Vec& y, double gamma)
+{
+   return d_owner->CVSpgmrPrecondSet(t, &y, gamma);
+}
+inline void DeviceVectorOps::precondSolve(const Vec& r, Vec& z) { d_owner->CVSpgmrPrecondSolve(&r, &z); }
 
 }  // namespace ampe_host

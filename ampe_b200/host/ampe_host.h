@@ -20,6 +20,7 @@
 
 #include "../../include/ampe_b200.h"
 #include "../../include/ampe_b200_kernels.h"
+#include "../../include/ampe_b200_precond.h"
 
 namespace ampe_host {
 
@@ -553,7 +554,47 @@ class QuatSysSolver
          d_flux_id(flux_scratch_id), d_lambda_id(lambda_id)
    {
    }
+   ~QuatSysSolver() { ampe_mg_destroy(d_mg); }
    int getFaceDiffCoeffScratchId() const { return d_fc_id; }
+   // ---- preconditioner side ---------------------------------------------
+   // QuatSysSolver::setOperatorCoefficients (QuatSysSolver.cc:268-292) -> QuatFACOps::
+   // setOperatorCoefficients (QuatFACOps.cc:735-818): face coefficients from (phase, T, grad_q), the
+   // square root of the mobility, then QuatLevelSolver::setMatrixCoefficients.  The derivative ids
+   // feed the dquat/dphi coupling block only (precond_has_dquatdphi), which is not built: pass -1.
+   void setOperatorCoefficients(double gamma, int mobility_id, int mobility_deriv_id, int phase_id,
+                                int temperature_id, int face_coef_deriv_id, int grad_q_id, int q_id)
+   {
+      (void)q_id;
+      if (mobility_deriv_id >= 0 || face_coef_deriv_id >= 0)
+         throw std::runtime_error("QuatSysSolver::setOperatorCoefficients: the dquat/dphi block is not built");
+      d_face_coeff->computeFaceCoefs(d_h, phase_id, temperature_id, grad_q_id, d_fc_id);
+      auto patch = d_h->getPatchLevel(0)->patches.front();
+      if (!d_mg) {
+         int n[3];
+         for (int d = 0; d < 3; d++) n[d] = patch->getBox().numberCells(d);
+         check(ampe_mg_create(patch->getBox().ndim, n, patch->getDx(), 1, &d_mg), "ampe_mg_create(quat)");
+      }
+      auto mob = patch->cell<double>(mobility_id);
+      auto fc = patch->side<double>(d_fc_id);
+      auto f = fc->pointers(0);
+      std::vector<const double*> cf(f.begin(), f.end());
+      check(ampe_mg_set_quat(d_mg, gamma, mob->getPointer(), mob->getGhostCellWidth(), cf.data(),
+                             fc->getGhostCellWidth(), nullptr),
+            "QuatSysSolver::setOperatorCoefficients");
+   }
+   // QuatSysSolver::solveSystem (QuatSysSolver.cc:296-347), one depth after the other like
+   // QuatLevelSolver::solveSystem; q_soln / q_rhs: ghost-0 device arrays of depth qlen
+   bool solveSystem(double* q_soln, const double* q_rhs, int ncycles)
+   {
+      if (!d_mg) throw std::runtime_error("QuatSysSolver::solveSystem before setOperatorCoefficients");
+      auto patch = d_h->getPatchLevel(0)->patches.front();
+      size_t nc = 1;
+      for (int d = 0; d < patch->getBox().ndim; d++) nc *= (size_t)patch->getBox().numberCells(d);
+      for (int m = 0; m < d_cfg.qlen; m++)
+         check(ampe_mg_solve(d_mg, q_rhs + nc * m, q_soln + nc * m, ncycles, 1, nullptr), "QuatSysSolver::solveSystem");
+      return true;
+   }
+   ampe_mg* levelSolver() const { return d_mg; }
    void evaluateRHS(int phase_id, int temperature_id, int grad_q_id, int grad_q_copy_id,
                     int rotations_id, int mobility_id, int solution_id, int rhs_id,
                     bool use_gradq_for_flux)
@@ -605,6 +646,7 @@ class QuatSysSolver
    std::shared_ptr<PatchHierarchy> d_h;
    std::shared_ptr<QuatFaceCoeff> d_face_coeff;
    int d_fc_id, d_flux_id, d_lambda_id;
+   ampe_mg* d_mg = nullptr;
 };
 
 // ---- PhaseRHSStrategyWithQ (PhaseRHSStrategyWithQ.cc:90-312) ------------------------------------
@@ -843,6 +885,124 @@ class TemperatureRHSStrategy
  private:
    int d_T, d_cp;
    double d_alpha, d_L;
+};
+
+// ---- block preconditioner solvers ----------------------------------------
+// EllipticFACSolver + EllipticFACOps (EllipticFACSolver.cc, EllipticFACOps.h:35): M div(D grad u) + C u
+// on the single level, inverted by the device multigrid behind ampe_mg_* (csrc/mg.cu) instead of
+// hypre PFMG.  The coefficient setters keep the reference's names; finalizeCoefficients() hands
+// them to the device (the reference reads them lazily at solve time).
+class EllipticFACSolver
+{
+ public:
+   explicit EllipticFACSolver(std::shared_ptr<PatchHierarchy> h) : d_h(h)
+   {
+      auto patch = d_h->getPatchLevel(0)->patches.front();
+      int n[3];
+      for (int d = 0; d < 3; d++) n[d] = patch->getBox().numberCells(d);
+      check(ampe_mg_create(patch->getBox().ndim, n, patch->getDx(), 0, &d_mg), "ampe_mg_create");
+   }
+   virtual ~EllipticFACSolver() { ampe_mg_destroy(d_mg); }
+   void setM(int m_id) { d_m_id = m_id; }
+   void setMConstant(double m) { d_m_id = -1, d_m_const = m; }
+   void setCPatchDataId(int c_id) { d_c_id = c_id; }
+   void setCConstant(double c) { d_c_id = -1, d_c_const = c; }
+   // D = scale * (side data id [+ side data id2])
+   void setDPatchDataId(int d_id, int d_id2 = -1, double scale = 1.0) { d_d_id = d_id, d_d_id2 = d_id2, d_d_scale = scale; }
+   void setDConstant(double d) { d_d_id = d_d_id2 = -1, d_d_const = d; }
+   void finalizeCoefficients()
+   {
+      auto patch = d_h->getPatchLevel(0)->patches.front();
+      const double *m = nullptr, *c = nullptr;
+      int ngm = 0, ngc = 0, ngd = 0;
+      if (d_m_id >= 0) m = patch->cell<double>(d_m_id)->getPointer(), ngm = patch->cell<double>(d_m_id)->getGhostCellWidth();
+      if (d_c_id >= 0) c = patch->cell<double>(d_c_id)->getPointer(), ngc = patch->cell<double>(d_c_id)->getGhostCellWidth();
+      std::vector<const double*> d1, d2;
+      if (d_d_id >= 0) {
+         auto sd = patch->side<double>(d_d_id);
+         auto v = sd->pointers(0);
+         d1.assign(v.begin(), v.end());
+         ngd = sd->getGhostCellWidth();
+         if (d_d_id2 >= 0) {
+            auto sd2 = patch->side<double>(d_d_id2);
+            if (sd2->getGhostCellWidth() != ngd) throw std::runtime_error("EllipticFACSolver: ghost widths of D differ");
+            auto v2 = sd2->pointers(0);
+            d2.assign(v2.begin(), v2.end());
+         }
+      }
+      check(ampe_mg_set_elliptic(d_mg, m, ngm, d_m_const, c, ngc, d_c_const, d1.empty() ? nullptr : d1.data(),
+                                 d2.empty() ? nullptr : d2.data(), ngd, d_d_scale, d_d_const, nullptr),
+            "EllipticFACSolver::finalizeCoefficients");
+   }
+   // solveSystem(u, f): ghost-0 device arrays; zero initial guess, fixed number of V-cycles
+   bool solveSystem(double* u, const double* f, int ncycles)
+   {
+      check(ampe_mg_solve(d_mg, f, u, ncycles, 0, nullptr), "EllipticFACSolver::solveSystem");
+      return true;
+   }
+   ampe_mg* levelSolver() const { return d_mg; }
+
+ protected:
+   std::shared_ptr<PatchHierarchy> d_h;
+   ampe_mg* d_mg = nullptr;
+   int d_m_id = -1, d_c_id = -1, d_d_id = -1, d_d_id2 = -1;
+   double d_m_const = 1.0, d_c_const = 1.0, d_d_const = 0.0, d_d_scale = 1.0;
+};
+
+// PhaseFACSolver / PhaseFACOps::setOperatorCoefficients (PhaseFACOps.cc:33-51)
+class PhaseFACSolver : public EllipticFACSolver
+{
+ public:
+   PhaseFACSolver(std::shared_ptr<PatchHierarchy> h, int c_scratch_id) : EllipticFACSolver(h), d_c_scratch_id(c_scratch_id) {}
+   void setOperatorCoefficients(int phase_id, int phase_mobility_id, double epsilon_phase, double gamma,
+                                double phase_well_scale, const std::string& phase_well_func_type)
+   {
+      setM(phase_mobility_id);
+      // C to be set after M since it uses M (setC, PhaseFACOps.cc:58-98)
+      auto patch = d_h->getPatchLevel(0)->patches.front();
+      auto phi = patch->cell<double>(phase_id), m = patch->cell<double>(phase_mobility_id);
+      auto c = patch->cell<double>(d_c_scratch_id);
+      check(ampe_k_phasefacops_setc(AMPE_BOX_ARGS(patch), phi->getPointer(), phi->getGhostCellWidth(),
+                                    m->getPointer(), m->getGhostCellWidth(), gamma, phase_well_scale,
+                                    phase_well_func_type.c_str(), c->getPointer(), c->getGhostCellWidth(), nullptr),
+            "PhaseFACOps::setC");
+      setCPatchDataId(d_c_scratch_id);
+      setDConstant(-gamma * epsilon_phase * epsilon_phase);
+      finalizeCoefficients();
+   }
+
+ private:
+   int d_c_scratch_id;
+};
+
+// ConcFACSolver / ConcFACOps::setOperatorCoefficients (ConcFACOps.cc:19-50); diffusion_id2 >= 0: the
+// sum EBSCompositionRHSStrategy::setDiffusionCoeffForPreconditioner forms (D_l + D_a)
+class ConcFACSolver : public EllipticFACSolver
+{
+ public:
+   explicit ConcFACSolver(std::shared_ptr<PatchHierarchy> h) : EllipticFACSolver(h) {}
+   void setOperatorCoefficients(double gamma, int diffusion_id, int diffusion_id2, double mobility)
+   {
+      assert(gamma >= 0. && mobility > 0.);
+      setDPatchDataId(diffusion_id, diffusion_id2, -gamma);
+      setCConstant(1.);
+      setMConstant(mobility);
+      finalizeCoefficients();
+   }
+};
+
+// TemperatureFACSolver::setOperatorCoefficients(m, c, d) (QuatIntegrator.cc:3340-3346)
+class TemperatureFACSolver : public EllipticFACSolver
+{
+ public:
+   explicit TemperatureFACSolver(std::shared_ptr<PatchHierarchy> h) : EllipticFACSolver(h) {}
+   void setOperatorCoefficients(double m, double c, double d)
+   {
+      setMConstant(m);
+      setCConstant(c);
+      setDConstant(d);
+      finalizeCoefficients();
+   }
 };
 
 }  // namespace ampe_host

@@ -77,4 +77,48 @@ int ampe_host_integrate_implicit(void* h, const ampe_rhs_fields* y, double t0, d
       return -1;
    }
 }
+// ---- block preconditioners ------------------------------------------------
+// QuatIntegrator::setupPreconditioners; ncycles V-cycles per block solve, 0 = preconditioner off
+int ampe_host_set_preconditioner(void* h, int ncycles)
+{
+   try {
+      static_cast<ampe_host::QuatIntegrator*>(h)->setupPreconditioners(ncycles);
+      return 0;
+   } catch (const std::exception& e) {
+      g_host_err = e.what();
+      return -1;
+   }
+}
+// QuatIntegrator::CVSpgmrPrecondSet(t, y, ..., gamma)
+int ampe_host_precond_set(void* h, double t, const ampe_rhs_fields* y, double gamma)
+{
+   try {
+      return static_cast<ampe_host::QuatIntegrator*>(h)->CVSpgmrPrecondSet(t, y, gamma);
+   } catch (const std::exception& e) {
+      g_host_err = e.what();
+      return -1;
+   }
+}
+// QuatIntegrator::CVSpgmrPrecondSolve(..., r, z, ...)
+int ampe_host_precond_solve(void* h, const ampe_rhs_fields* r, const ampe_rhs_fields* z)
+{
+   try {
+      const int rc = static_cast<ampe_host::QuatIntegrator*>(h)->CVSpgmrPrecondSolve(r, z);
+      cudaDeviceSynchronize();
+      return rc;
+   } catch (const std::exception& e) {
+      g_host_err = e.what();
+      return -1;
+   }
+}
+// borrowed ampe_mg handle of a block (0 phase, 1 quaternion, 2 composition, 3 temperature) or NULL
+void* ampe_host_precond_level_solver(void* h, int block)
+{
+   return static_cast<ampe_host::QuatIntegrator*>(h)->preconditionerLevelSolver(block);
+}
+void ampe_host_precond_stats(void* h, double* out2)
+{
+   out2[0] = (double)static_cast<ampe_host::QuatIntegrator*>(h)->precondSetups();
+   out2[1] = (double)static_cast<ampe_host::QuatIntegrator*>(h)->precondSolves();
+}
 }

@@ -1,6 +1,8 @@
 // TEST INFRASTRUCTURE ONLY (see oracle.h).  C entry points for ctypes (tests/,
 // smoke(), bench.py's cpu_baseline / --impl reference legs).
+#include "ctx.h"
 #include "oracle.h"
+#include "precond.h"
 #include <cstring>
 #ifdef _OPENMP
 #include <omp.h>
@@ -24,6 +26,102 @@ void oracle_get_phase_concentrations(void* c, double* cl, double* ca)
    get_phase_concentrations((Ctx*)c, cl, ca);
 }
 int oracle_energy(void* c, const ampe_rhs_fields* y, double* out) { return energy((Ctx*)c, y, out); }
+// ---- block preconditioners (precond.cc) --------------------------------------------------------
+// ncycles > 0: oracle_integrate_implicit runs right-preconditioned GMRES with that many V-cycles
+void oracle_set_preconditioner(void* c, int ncycles) { ((Ctx*)c)->precond_cycles = ncycles; }
+void oracle_precond_stats(void* c, double* out2)
+{
+   out2[0] = ((Ctx*)c)->precond_stats[0];
+   out2[1] = ((Ctx*)c)->precond_stats[1];
+}
+// after an fd_flag = 0 evaluation at the state the coefficients are frozen at
+int oracle_precond_setup(void* c, double gamma, int ncycles) { return precond_setup((Ctx*)c, gamma, ncycles); }
+int oracle_precond_solve(void* c, const ampe_rhs_fields* r, const ampe_rhs_fields* z)
+{
+   return precond_solve((Ctx*)c, r, z);
+}
+// restated reference operator of one block: 0 phase, 1 quaternion component, 2 composition, 3 temperature
+int oracle_precond_apply(void* c, int block, const double* u, double* out)
+{
+   return precond_apply((Ctx*)c, block, u, out);
+}
+// the multigrid of one block of the context (borrowed handle for the oracle_mg_* calls below)
+void* oracle_precond_block(void* c, int block) { return precond_block((Ctx*)c, block); }
+
+// host loop over the product's per-cell multigrid functions, same calls as ampe_mg_* with HOST arrays
+void* oracle_mg_create(int ndim, const int* n, const double* dx, int with_s)
+{
+   return new HostMG(ndim, n, dx, with_s != 0);
+}
+void oracle_mg_destroy(void* g) { delete (HostMG*)g; }
+int oracle_mg_set_elliptic(void* g, const double* m, int ngm, double m_const, const double* c, int ngc,
+                           double c_const, const double* const* d, const double* const* d2, int ngd,
+                           double d_scale, double d_const)
+{
+   try {
+      ((HostMG*)g)->setElliptic(m, ngm, m_const, c, ngc, c_const, d, d2, ngd, d_scale, d_const);
+      return 0;
+   } catch (...) {
+      return -1;
+   }
+}
+int oracle_mg_set_quat(void* g, double gamma, const double* mobility, int ngm, const double* const* fc, int ngfc)
+{
+   try {
+      ((HostMG*)g)->setQuat(gamma, mobility, ngm, fc, ngfc);
+      return 0;
+   } catch (...) {
+      return -1;
+   }
+}
+int oracle_mg_solve(void* g, const double* rhs, double* soln, int ncycles, int symmetrized)
+{
+   try {
+      ((HostMG*)g)->solve(rhs, soln, ncycles, symmetrized != 0);
+      return 0;
+   } catch (...) {
+      return -1;
+   }
+}
+void oracle_mg_apply(void* g, const double* u, double* out) { ((HostMG*)g)->apply(u, out); }
+void oracle_mg_set_sweeps(void* g, int pre, int post, int coarse) { ((HostMG*)g)->setSweeps(pre, post, coarse); }
+int oracle_mg_num_levels(void* g) { return ((HostMG*)g)->numLevels(); }
+void oracle_mg_level_extents(void* g, int level, int* n_out)
+{
+   const int* n = ((HostMG*)g)->levelExtents(level);
+   n_out[0] = n[0], n_out[1] = n[1], n_out[2] = n[2];
+}
+int oracle_mg_copy_level(void* g, int level, int which, double* out)
+{
+   HostMG* mg = (HostMG*)g;
+   const double* src = mg->levelArray(level, which);
+   if (!src) return -1;
+   const int* n = mg->levelExtents(level);
+   memcpy(out, src, sizeof(double) * (size_t)n[0] * n[1] * n[2]);
+   return 0;
+}
+// the restated reference operators on caller-supplied SAMRAI-layout arrays over the box [0, n-1]:
+// m, c ghost ngm / ngc cell arrays, d side arrays ghost 0, u / out ghost 0
+void oracle_k_elliptic_apply(int ndim, const int* n, const double* dx, double* m, int ngm, double* c, int ngc,
+                             double* const* d, const double* u, double* out)
+{
+   Box b;
+   b.ndim = ndim;
+   for (int a = 0; a < 3; a++) b.lo[a] = 0, b.hi[a] = a < ndim ? n[a] - 1 : 0;
+   View dv[3];
+   for (int a = 0; a < ndim; a++) dv[a] = make_view(d[a], b, a, 0, 1);
+   elliptic_apply(b, dx, make_view(m, b, -1, ngm, 1), make_view(c, b, -1, ngc, 1), dv, u, out);
+}
+void oracle_k_quat_stencil_apply(int ndim, const int* n, const double* dx, double gamma, double* sqrt_m, int ngm,
+                                 double* const* fc, const double* w, double* out)
+{
+   Box b;
+   b.ndim = ndim;
+   for (int a = 0; a < 3; a++) b.lo[a] = 0, b.hi[a] = a < ndim ? n[a] - 1 : 0;
+   View fv[3];
+   for (int a = 0; a < ndim; a++) fv[a] = make_view(fc[a], b, a, 0, 1);
+   quat_stencil_apply(b, dx, gamma, make_view(sqrt_m, b, -1, ngm, 1), fv, w, out);
+}
 int oracle_abi_sizeof_config() { return (int)sizeof(ampe_rhs_config); }
 int oracle_num_threads()
 {

@@ -39,6 +39,9 @@ struct Ctx {
    // rhs work arrays g=0
    Field rhs_phase, rhs_quat, rhs_conc, rhs_temp;
    bool have_ref = false;
+   void* precond = nullptr;     // block preconditioners (precond.cc)
+   int precond_cycles = 0;      // > 0: the implicit integrator runs right-preconditioned (stepper.cc)
+   double precond_stats[2] = {0, 0};  // set-ups, solves of the last implicit integration
 };
 
 

@@ -3,6 +3,7 @@
 // single uniform periodic level: same order of passes, every intermediate
 // materialised in an array between passes exactly like the reference.
 #include "ctx.h"
+#include "precond.h"
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -79,7 +80,11 @@ Ctx* create(const ampe_rhs_config& cfg)
    return c;
 }
 
-void destroy(Ctx* c) { delete c; }
+void destroy(Ctx* c)
+{
+   precond_destroy(c);
+   delete c;
+}
 
 static inline int wrap(int i, int n)
 {

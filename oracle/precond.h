@@ -1,0 +1,55 @@
+// TEST INFRASTRUCTURE ONLY (see oracle.h).  Block preconditioners: see precond.cc.
+#pragma once
+#include <memory>
+#include <vector>
+
+#include "../ampe_b200/csrc/mg_cell.h"
+#include "oracle.h"
+
+namespace oracle {
+
+struct Ctx;
+
+// restated reference operators (independent of the product's arithmetic)
+void elliptic_apply(const Box& b, const double* dx, View m, View c, View* d, const double* u, double* out);
+void quat_stencil_apply(const Box& b, const double* h, double gamma, View sqrt_m, View* fc, const double* w,
+                        double* out);
+
+// host loop over the product's per-cell multigrid functions (ampe_b200/csrc/mg_cell.h); same
+// interface and cycle structure as the device solver behind ampe_mg_* (ampe_b200/csrc/mg.cu)
+class HostMG
+{
+ public:
+   HostMG(int ndim, const int* n, const double* dx, bool with_s);
+   void setElliptic(const double* m, int ngm, double m_const, const double* c, int ngc, double c_const,
+                    const double* const* d, const double* const* d2, int ngd, double d_scale, double d_const);
+   void setQuat(double gamma, const double* mobility, int ngm, const double* const* face_coef, int ngfc);
+   void solve(const double* rhs, double* soln, int ncycles, bool symmetrized);
+   void apply(const double* u, double* out) const;
+   void setSweeps(int pre, int post, int coarse) { d_pre = pre, d_post = post, d_coarse = coarse; }
+   int numLevels() const { return (int)d_levels.size(); }
+   const int* levelExtents(int l) const { return d_levels.at(l).n; }
+   const double* levelArray(int level, int which) const;
+
+ private:
+   void buildCoarse();
+   void smooth(int l, int sweeps);
+   void vcycle();
+   int d_ndim;
+   bool d_with_s;
+   bool d_set = false;
+   int d_n[3];
+   double d_inv_h2[3];
+   int d_pre = 1, d_post = 1, d_coarse = 8;
+   std::vector<ampe_mg_cell::Level> d_levels;
+   std::vector<std::vector<double>> d_store;
+   std::vector<bool> d_two_colour;
+};
+
+int precond_setup(Ctx* c, double gamma, int ncycles);
+int precond_solve(Ctx* c, const ampe_rhs_fields* r, const ampe_rhs_fields* z);
+int precond_apply(Ctx* c, int block, const double* u, double* out);
+HostMG* precond_block(Ctx* c, int block);
+void precond_destroy(Ctx* c);
+
+}  // namespace oracle

@@ -88,6 +88,36 @@ def lib(perf=False):
             fn.argtypes = [dbl]
         L.oracle_calphad_diffusion_mobility.restype = dbl
         L.oracle_calphad_diffusion_mobility.argtypes = [pdb, C.c_int, dbl, dbl]
+        # block preconditioners (precond.cc)
+        vp, pvp, ci = C.c_void_p, C.POINTER(C.c_void_p), C.c_int
+        L.oracle_set_preconditioner.argtypes = [vp, ci]
+        L.oracle_precond_stats.argtypes = [vp, vp]
+        L.oracle_precond_setup.restype = ci
+        L.oracle_precond_setup.argtypes = [vp, dbl, ci]
+        L.oracle_precond_solve.restype = ci
+        L.oracle_precond_solve.argtypes = [vp, C.POINTER(_abi.RhsFields), C.POINTER(_abi.RhsFields)]
+        L.oracle_precond_apply.restype = ci
+        L.oracle_precond_apply.argtypes = [vp, ci, vp, vp]
+        L.oracle_precond_block.restype = vp
+        L.oracle_precond_block.argtypes = [vp, ci]
+        L.oracle_mg_create.restype = vp
+        L.oracle_mg_create.argtypes = [ci, vp, vp, ci]
+        L.oracle_mg_destroy.argtypes = [vp]
+        L.oracle_mg_set_elliptic.restype = ci
+        L.oracle_mg_set_elliptic.argtypes = [vp, vp, ci, dbl, vp, ci, dbl, pvp, pvp, ci, dbl, dbl]
+        L.oracle_mg_set_quat.restype = ci
+        L.oracle_mg_set_quat.argtypes = [vp, dbl, vp, ci, pvp, ci]
+        L.oracle_mg_solve.restype = ci
+        L.oracle_mg_solve.argtypes = [vp, vp, vp, ci, ci]
+        L.oracle_mg_apply.argtypes = [vp, vp, vp]
+        L.oracle_mg_set_sweeps.argtypes = [vp, ci, ci, ci]
+        L.oracle_mg_num_levels.restype = ci
+        L.oracle_mg_num_levels.argtypes = [vp]
+        L.oracle_mg_level_extents.argtypes = [vp, ci, vp]
+        L.oracle_mg_copy_level.restype = ci
+        L.oracle_mg_copy_level.argtypes = [vp, ci, ci, vp]
+        L.oracle_k_elliptic_apply.argtypes = [ci, vp, vp, vp, ci, vp, ci, pvp, vp, vp]
+        L.oracle_k_quat_stencil_apply.argtypes = [ci, vp, vp, dbl, vp, ci, pvp, vp, vp]
         _libs[perf] = L
     return _libs[perf]
 
@@ -163,6 +193,40 @@ class Oracle:
                  "last_newton_update", "last_linear_residual")
         return rc, dict(zip(names, st.tolist()))
 
+    # ---- block preconditioners (precond.cc) ----
+    def set_preconditioner(self, ncycles):
+        """ncycles > 0: integrate_implicit runs right-preconditioned GMRES (CVSpgmrPrecondSet / Solve)"""
+        self.L.oracle_set_preconditioner(self.h, int(ncycles))
+
+    def precond_stats(self):
+        out = np.zeros(2)
+        self.L.oracle_precond_stats(self.h, _ptr(out))
+        return {"precond_setups": out[0], "precond_solves": out[1]}
+
+    def precond_setup(self, gamma, ncycles=2):
+        """coefficients frozen at the state of the last fd_flag = 0 eval (CVSpgmrPrecondSet)"""
+        return self.L.oracle_precond_setup(self.h, float(gamma), int(ncycles))
+
+    def precond_solve(self, r, z=None):
+        if z is None:
+            z = self.alloc_like(r)
+        fr, fz = _fields(r), _fields(z)
+        return self.L.oracle_precond_solve(self.h, C.byref(fr), C.byref(fz)), z
+
+    def precond_apply(self, block, u):
+        """restated reference operator of a block (0 phase, 1 quaternion component, 2 composition,
+        3 temperature) applied to one ghost-0 cell array"""
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        out = np.zeros_like(u)
+        rc = self.L.oracle_precond_apply(self.h, int(block), _ptr(u), _ptr(out))
+        if rc != 0:
+            raise RuntimeError("oracle_precond_apply: no such block")
+        return out
+
+    def precond_block(self, block):
+        h = self.L.oracle_precond_block(self.h, int(block))
+        return HostMG(handle=h, owner=self) if h else None
+
     def phase_concentrations(self):
         cl = np.zeros(self.ncell)
         ca = np.zeros(self.ncell)
@@ -170,9 +234,100 @@ class Oracle:
         return cl, ca
 
 
-# ---- symmetry pre-pass / projection (oracle/symmetry.cc), SAMRAI layouts ----
 def _ivec(v):
     return (C.c_int * 3)(*(list(v) + [0] * (3 - len(v))))
+
+
+def _parr(arrays):
+    """host array of pointers (NULL-padded to 3) from a list of numpy arrays, or None"""
+    if arrays is None:
+        return None
+    arr = (C.c_void_p * 3)()
+    for d, a in enumerate(arrays):
+        assert a.dtype == np.float64 and a.flags.c_contiguous
+        arr[d] = a.ctypes.data
+    return arr
+
+
+class HostMG:
+    """host loop over the product's per-cell multigrid functions (oracle/precond.cc part 2): the same
+    calls as ampe_b200's device solver (ampe_mg_*), on numpy arrays"""
+
+    def __init__(self, n=None, dx=None, with_s=False, handle=None, owner=None):
+        self.L = lib()
+        self._owner = owner  # borrowed handle of an Oracle context
+        if handle is not None:
+            self.h, self._own = handle, False
+        else:
+            self.h = self.L.oracle_mg_create(len(n), _ivec(n), (C.c_double * 3)(*(list(dx) + [0.0] * (3 - len(dx)))),
+                                             1 if with_s else 0)
+            self._own = True
+        self._keep = []
+
+    def __del__(self):
+        if getattr(self, "_own", False) and self.h:
+            self.L.oracle_mg_destroy(self.h)
+            self.h = None
+
+    def set_elliptic(self, m=None, ngm=0, m_const=0.0, c=None, ngc=0, c_const=0.0, d=None, d2=None, ngd=0,
+                     d_scale=1.0, d_const=0.0):
+        rc = self.L.oracle_mg_set_elliptic(self.h, _ptr(m), ngm, m_const, _ptr(c), ngc, c_const, _parr(d), _parr(d2),
+                                           ngd, d_scale, d_const)
+        assert rc == 0
+
+    def set_quat(self, gamma, mobility, ngm, face_coef, ngfc):
+        assert self.L.oracle_mg_set_quat(self.h, gamma, _ptr(mobility), ngm, _parr(face_coef), ngfc) == 0
+
+    def solve(self, rhs, ncycles=2, symmetrized=False):
+        rhs = np.ascontiguousarray(rhs, dtype=np.float64)
+        out = np.zeros_like(rhs)
+        assert self.L.oracle_mg_solve(self.h, _ptr(rhs), _ptr(out), int(ncycles), 1 if symmetrized else 0) == 0
+        return out
+
+    def apply(self, u):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        out = np.zeros_like(u)
+        self.L.oracle_mg_apply(self.h, _ptr(u), _ptr(out))
+        return out
+
+    def set_sweeps(self, pre, post, coarse):
+        self.L.oracle_mg_set_sweeps(self.h, pre, post, coarse)
+
+    def num_levels(self):
+        return self.L.oracle_mg_num_levels(self.h)
+
+    def level_extents(self, level):
+        n = (C.c_int * 3)()
+        self.L.oracle_mg_level_extents(self.h, level, n)
+        return list(n)
+
+    def level_array(self, level, which):
+        n = self.level_extents(level)
+        out = np.zeros((n[2], n[1], n[0]))
+        if self.L.oracle_mg_copy_level(self.h, level, which, _ptr(out)) != 0:
+            return None
+        return out
+
+
+def elliptic_apply(n, dx, m, ngm, c, ngc, d, u):
+    """restated efo_compfluxvardc + efo_compresvarsca: M div(D grad u) + C u (SAMRAI-layout m, c, d)"""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.zeros_like(u)
+    lib().oracle_k_elliptic_apply(len(n), _ivec(n), (C.c_double * 3)(*(list(dx) + [0.0] * (3 - len(dx)))), _ptr(m),
+                                  ngm, _ptr(c), ngc, _parr(d), _ptr(u), _ptr(out))
+    return out
+
+
+def quat_stencil_apply(n, dx, gamma, sqrt_m, ngm, fc, w):
+    """restated set_j_ij + set_stencil applied to one component"""
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    out = np.zeros_like(w)
+    lib().oracle_k_quat_stencil_apply(len(n), _ivec(n), (C.c_double * 3)(*(list(dx) + [0.0] * (3 - len(dx)))),
+                                      float(gamma), _ptr(sqrt_m), ngm, _parr(fc), _ptr(w), _ptr(out))
+    return out
+
+
+# ---- symmetry pre-pass / projection (oracle/symmetry.cc), SAMRAI layouts ----
 
 
 def quatfindsymm(q1, q2, iq, qlen):

@@ -12,6 +12,7 @@
 #include "../ampe_b200/host/ImplicitIntegrator.h"
 #include "ctx.h"
 #include "oracle.h"
+#include "precond.h"
 
 namespace {
 using namespace oracle;
@@ -123,6 +124,14 @@ class OracleOps
       const bool kks = d_cfg.conc_rhs_form == AMPE_CONC_KKS || d_cfg.conc_rhs_form == AMPE_CONC_EBS;
       if (kks && d_cfg.free_energy == AMPE_FE_CALPHAD) set_ref(d_c, nullptr, nullptr);
    }
+   // CVSpgmrPrecondSet / CVSpgmrPrecondSolve (QuatIntegrator.cc:3300-3376, 3666-3771), precond.cc
+   bool preconditioned() const { return d_c->precond_cycles > 0; }
+   int precondSetup(double, const Vec&, double gamma) { return precond_setup(d_c, gamma, d_c->precond_cycles); }
+   void precondSolve(const Vec& r, Vec& z)
+   {
+      ampe_rhs_fields fr = fields(r), fz = fields(z);
+      precond_solve(d_c, &fr, &fz);
+   }
 
  private:
    Ctx* d_c;
@@ -159,6 +168,7 @@ extern "C" int oracle_integrate_implicit(void* ctx, const ampe_rhs_fields* y, do
       stats_out[5] = (double)st.projections, stats_out[6] = st.last_newton_update;
       stats_out[7] = st.last_linear_residual;
    }
+   c->precond_stats[0] = (double)st.precond_setups, c->precond_stats[1] = (double)st.precond_solves;
    for (int k = 0; k < 4; k++)
       if (src[k]) memcpy(src[k], v.comp[k].data(), sizeof(double) * ncell * depth[k]);
    return rc;

@@ -55,6 +55,9 @@ struct ToyOps {
       for (auto& c : corr) c = 0.0;
    }
    void postStep(Vec&) {}
+   bool preconditioned() const { return false; }
+   int precondSetup(double, const Vec&, double) { return 0; }
+   void precondSolve(const Vec& r, Vec& z) { z = r; }
 };
 
 int main()

@@ -1,0 +1,291 @@
+"""Block preconditioners on the CPU.
+
+(1) The product's per-cell multigrid arithmetic (ampe_b200/csrc/mg_cell.h, looped on the host by
+    oracle/precond.cc part 2) applies the SAME operator as the reference's routines restated on their own
+    layouts (efo_compfluxvardc + efo_compresvarsca, set_j_ij + set_stencil), and both reproduce the closed-form
+    eigenvalues of the constant-coefficient operator.
+(2) The solve: the reference hands its single level to hypre PFMG (absent from its tree), so there is no solver
+    to restate -- the V-cycle is judged by the residual the RESTATED operator measures (contraction per cycle,
+    odd extents, jumping coefficients).
+(3) CVSpgmrPrecondSet / CVSpgmrPrecondSolve on the five configurations: operator identity with the context's own
+    coefficients, residual after the default two cycles, and what the preconditioner does to the Newton-Krylov
+    iteration of the implicit integrator (fewer Krylov vectors, same trajectory).
+The device solver is compared with this host loop in tests/test_gpu_widening_zzz_precond.py."""
+import numpy as np
+import pytest
+
+import parity
+from oracle import pyoracle
+
+
+def _ghosted(a, ng, ndim):
+    """periodic ghost fill of a (nz, ny, nx) cell array in the first ndim directions"""
+    pad = [(ng, ng) if (3 - 1 - ax) < ndim else (0, 0) for ax in range(3)]
+    return np.ascontiguousarray(np.pad(a, pad, mode="wrap"))
+
+
+def _side_from_lower(low, axis_np):
+    """SideData array of one direction from its ghost-0 lower-face values (periodic: the extra upper
+    face repeats face 0)"""
+    first = np.take(low, [0], axis=axis_np)
+    return np.ascontiguousarray(np.concatenate([low, first], axis=axis_np))
+
+
+def _random_elliptic(n, seed, jump=1.0):
+    rng = np.random.default_rng(seed)
+    ndim = len(n)
+    shape = (n[2] if ndim == 3 else 1, n[1], n[0])
+    m = 0.5 + rng.random(shape)
+    c = 1.0 + rng.random(shape)
+    lows = [-(0.2 + rng.random(shape)) * np.where(rng.random(shape) < 0.3, jump, 1.0) for _ in range(ndim)]
+    d = [_side_from_lower(lows[a], 2 - a) for a in range(ndim)]
+    return shape, m, c, lows, d
+
+
+@pytest.mark.parametrize("n,dx", [((12, 10), (0.3, 0.2)), ((8, 6, 10), (0.5, 0.4, 0.25)), ((9, 7), (1.0, 1.0))])
+def test_scalar_operator_is_the_reference_operator(n, dx):
+    """M div(D grad u) + C u with variable M, C, D: product arithmetic == restated efo_* routines"""
+    ndim = len(n)
+    shape, m, c, lows, d = _random_elliptic(n, 3)
+    rng = np.random.default_rng(4)
+    u = rng.standard_normal(shape)
+    mg = pyoracle.HostMG(n, dx)
+    mg_m, mg_c = _ghosted(m, 1, ndim), _ghosted(c, 2, ndim)
+    mg.set_elliptic(m=mg_m, ngm=1, c=mg_c, ngc=2, d=d, ngd=0, d_scale=1.0)
+    ref = pyoracle.elliptic_apply(n, dx, mg_m, 1, mg_c, 2, d, u)
+    got = mg.apply(u)
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+    # the scale factor and the second diffusion array (EBS: D_l + D_a, times -gamma)
+    mg.set_elliptic(m=None, m_const=0.7, c=None, c_const=1.0, d=d, d2=d, ngd=0, d_scale=-0.25)
+    d_eff = [-0.25 * (x + x) for x in d]
+    ones = np.ones(shape)
+    ref2 = pyoracle.elliptic_apply(n, dx, 0.7 * ones, 0, ones, 0, d_eff, u)
+    assert np.abs(mg.apply(u) - ref2).max() <= 1e-13 * np.abs(ref2).max()
+
+
+@pytest.mark.parametrize("n,dx", [((12, 10), (0.3, 0.2)), ((8, 6, 10), (0.5, 0.4, 0.25))])
+def test_quaternion_operator_is_the_reference_stencil(n, dx):
+    """w + gamma sqrt(m) div(fc grad(sqrt(m) w)): product arithmetic == restated set_j_ij + set_stencil"""
+    ndim = len(n)
+    rng = np.random.default_rng(5)
+    shape = (n[2] if ndim == 3 else 1, n[1], n[0])
+    mob = 0.1 + rng.random(shape)
+    lows = [-(0.2 + rng.random(shape)) for _ in range(ndim)]
+    fc = [_side_from_lower(lows[a], 2 - a) for a in range(ndim)]
+    w = rng.standard_normal(shape)
+    gamma = 0.37
+    mg = pyoracle.HostMG(n, dx, with_s=True)
+    mob_g = _ghosted(mob, 1, ndim)
+    mg.set_quat(gamma, mob_g, 1, fc, 0)
+    ref = pyoracle.quat_stencil_apply(n, dx, gamma, np.sqrt(mob_g), 1, fc, w)
+    got = mg.apply(w)
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+    # symmetric matrix (what set_symmetric_stencil relies on): <x, A y> == <A x, y>
+    x = rng.standard_normal(shape)
+    assert abs((x * mg.apply(w)).sum() - (mg.apply(x) * w).sum()) < 1e-11 * np.abs(got).sum()
+
+
+def test_constant_coefficient_eigenvalues():
+    """Fourier modes are eigenvectors: lambda = C + M D sum_a (2 cos(2 pi k_a / n_a) - 2) / h_a^2"""
+    n, dx = (16, 12), (0.5, 0.25)
+    M, Cc, D = 1.3, 1.0, -0.04
+    mg = pyoracle.HostMG(n, dx)
+    mg.set_elliptic(m_const=M, c_const=Cc, d_const=D)
+    jj, ii = np.meshgrid(np.arange(n[1]), np.arange(n[0]), indexing="ij")
+    for k in ((0, 0), (1, 0), (3, 5), (8, 6)):
+        u = np.cos(2 * np.pi * (k[0] * ii / n[0] + k[1] * jj / n[1]))[None]
+        lam = Cc + M * D * sum((2 * np.cos(2 * np.pi * k[a] / n[a]) - 2) / dx[a] ** 2 for a in range(2))
+        assert np.abs(mg.apply(u) - lam * u).max() < 1e-12 * max(1.0, abs(lam))
+        # and the V-cycles invert it: one mode in, the same mode out, scaled by 1 / lambda
+        z = mg.solve(u, ncycles=10)
+        assert np.abs(z - u / lam).max() < 1e-9
+
+
+def _contraction(mg, apply_ref, rhs, cycles, symmetrized=False):
+    hist = []
+    for nc in cycles:
+        z = mg.solve(rhs, ncycles=nc, symmetrized=symmetrized)
+        hist.append(np.linalg.norm(rhs - apply_ref(z)) / np.linalg.norm(rhs))
+    return hist
+
+
+@pytest.mark.parametrize("n,dx,stiff", [((64, 48), (1.0, 1.0), 400.0), ((32, 16, 24), (1.0, 1.0, 1.0), 50.0)])
+def test_vcycle_contracts_the_reference_residual(n, dx, stiff):
+    """diffusion number gamma D / h^2 >> 1 (an essentially singular-perturbed Poisson problem): the residual
+    measured by the RESTATED operator drops by >= 4x per cycle (cell-to-cell random coefficients, contrast 6) and keeps dropping"""
+    ndim = len(n)
+    shape, m, c, lows, d = _random_elliptic(n, 8)
+    m[:] = 1.0
+    c[:] = 1.0
+    d = [stiff * x for x in d]
+    rng = np.random.default_rng(9)
+    rhs = rng.standard_normal(shape)
+    mg = pyoracle.HostMG(n, dx)
+    assert mg.num_levels() >= 4
+    mg.set_elliptic(m=m, ngm=0, c=c, ngc=0, d=d, ngd=0)
+    hist = _contraction(mg, lambda z: pyoracle.elliptic_apply(n, dx, m, 0, c, 0, d, z), rhs, (1, 2, 3, 4, 14))
+    assert hist[0] < 0.25
+    for a, b in zip(hist[:3], hist[1:4]):
+        assert b < 0.25 * a, hist
+    assert hist[-1] < 1e-7, hist
+
+
+def test_coarse_levels_are_rediscretised_means():
+    n, dx = (16, 8), (1.0, 0.5)
+    shape, m, c, lows, d = _random_elliptic(n, 12)
+    mg = pyoracle.HostMG(n, dx)
+    mg.set_elliptic(m=m, ngm=0, c=c, ngc=0, d=d, ngd=0)
+    assert [mg.level_extents(l) for l in range(mg.num_levels())] == [[16, 8, 1], [8, 4, 1], [4, 2, 1]]
+    c1 = mg.level_array(1, 0)[0]
+    assert np.allclose(c1, c[0].reshape(4, 2, 8, 2).mean(axis=(1, 3)), rtol=0, atol=1e-15)
+    # x faces: mean of the two fine faces stacked in y, / h^2 with h doubled
+    d0 = mg.level_array(0, 3)[0]
+    assert np.allclose(d0, lows[0][0] / dx[0] ** 2, rtol=1e-15)
+    d0c = mg.level_array(1, 3)[0]
+    expect = 0.25 * d0[:, ::2].reshape(4, 2, 8).mean(axis=1)
+    assert np.allclose(d0c, expect, rtol=1e-14)
+    d1c = mg.level_array(1, 4)[0]
+    d1 = mg.level_array(0, 4)[0]
+    assert np.allclose(d1c, 0.25 * d1[::2, :].reshape(4, 8, 2).mean(axis=2), rtol=1e-14)
+
+
+def test_odd_extents_fall_back_to_jacobi_and_jumps_still_converge():
+    """an odd extent cannot be two-coloured across the periodic wrap: single level, damped Jacobi; a 1e3
+    diffusivity ratio across a diffuse interface (solid / liquid) does not break the cycle"""
+    n, dx = (15, 9), (1.0, 1.0)
+    shape, m, c, lows, d = _random_elliptic(n, 21)
+    rng = np.random.default_rng(22)
+    rhs = rng.standard_normal(shape)
+    mg = pyoracle.HostMG(n, dx)
+    assert mg.num_levels() == 1
+    mg.set_sweeps(1, 1, 60)
+    mg.set_elliptic(m=m, ngm=0, c=c, ngc=0, d=d, ngd=0)
+    z = mg.solve(rhs, ncycles=4)
+    r = rhs - pyoracle.elliptic_apply(n, dx, m, 0, c, 0, d, z)
+    assert np.linalg.norm(r) < 1e-6 * np.linalg.norm(rhs)
+    # a solid disc in liquid, interface 4 cells wide, diffusivity ratio 1e3 (face value = mean of the cells)
+    n = (64, 64)
+    jj, ii = np.meshgrid(np.arange(n[1]), np.arange(n[0]), indexing="ij")
+    phi = 0.5 * (1.0 - np.tanh((np.hypot(ii - 31.5, jj - 31.5) - 18.0) / 2.0))[None]
+    dcell = -40.0 * (1.0e-3 * phi + (1.0 - phi))
+    lows = [0.5 * (dcell + np.roll(dcell, 1, axis=2 - a)) for a in range(2)]
+    d = [_side_from_lower(lows[a], 2 - a) for a in range(2)]
+    ones = np.ones_like(phi)
+    rhs = rng.standard_normal(phi.shape)
+    mg = pyoracle.HostMG(n, dx)
+    mg.set_elliptic(m_const=1.0, c_const=1.0, d=d, ngd=0)
+    hist = _contraction(mg, lambda z: pyoracle.elliptic_apply(n, dx, ones, 0, ones, 0, d, z), rhs, (1, 2, 3, 12))
+    assert hist[0] < 0.3 and hist[1] < 0.3 * hist[0] and hist[2] < 0.3 * hist[1] and hist[3] < 1e-6, hist
+
+
+# ---- CVSpgmrPrecondSet / CVSpgmrPrecondSolve on the configurations -----------------------------------------
+BLOCKS = {"phase": 0, "quat": 1, "conc": 2, "temperature": 3}
+
+
+def _context(name):
+    cfg, st = parity.make_case(name)
+    y = {k: (None if v is None else v.numpy().copy()) for k, v in st.items()}
+    o = pyoracle.Oracle(cfg)
+    if cfg.conc_rhs_form in (2, 3):
+        o.set_ref(y["conc"].ravel().copy(), y["conc"].ravel().copy())
+    if cfg.symmetry_aware:
+        o.set_rotations(parity.random_rotations(cfg))
+    status, _ = o.eval(0.0, y, fd_flag=0)
+    assert status == 0
+    return cfg, y, o
+
+
+def _evolved(cfg):
+    out = []
+    if cfg.with_phase:
+        out.append("phase")
+    if cfg.evolve_quat:
+        out.append("quat")
+    if cfg.with_concentration and cfg.conc_rhs_form in (2, 3):
+        out.append("conc")
+    if cfg.with_unsteady_temperature:
+        out.append("temperature")
+    return out
+
+
+@pytest.mark.parametrize("name", ["dendrite2d", "auni2d", "gg3d_hbsm", "auni3d"])
+def test_precond_set_and_solve_on_the_configurations(name):
+    """gamma = 20x the explicit step: every block's multigrid applies the restated reference operator built
+    from the context's own coefficient arrays, and two V-cycles leave < 10 % of the residual (the
+    quaternion block through divide/multiplyMobilitySqrt)"""
+    cfg, y, o = _context(name)
+    gamma = 20 * parity.TRAJ_DT[name]
+    assert o.precond_setup(gamma, 2) == 0
+    rng = np.random.default_rng(31)
+    shape = y["phase"].shape
+    r = {k: (None if v is None else rng.standard_normal(v.shape)) for k, v in y.items()}
+    rc, z = o.precond_solve(r)
+    assert rc == 0
+    for k in _evolved(cfg):
+        b = BLOCKS[k]
+        mg = o.precond_block(b)
+        u = rng.standard_normal(shape)
+        ref = o.precond_apply(b, u)
+        assert np.abs(mg.apply(u) - ref).max() <= 1e-12 * np.abs(ref).max(), k
+        if k == "quat":
+            # QuatSysSolver::solveSystem: the level solver sees rhs / sqrt(m) and returns w, z = sqrt(m) w
+            s = mg.level_array(0, 2).reshape(shape)
+            for m in range(cfg.qlen):
+                res = r[k][m] / s - o.precond_apply(b, z[k][m] / s)
+                assert np.linalg.norm(res) < 0.1 * np.linalg.norm(r[k][m] / s), (k, m)
+        else:
+            res = r[k] - o.precond_apply(b, z[k])
+            assert np.linalg.norm(res) < 0.1 * np.linalg.norm(r[k]), k
+    o.close()
+
+
+def test_phase_block_coefficients_follow_phasefacops():
+    """C = 1 + gamma M w g''(phi), g'' = 32 (1 + 6 phi (phi - 1)); D = -gamma eps^2 / h^2; M = phi_mobility"""
+    cfg, y, o = _context("auni2d")
+    gamma = 3.0e-9
+    o.precond_setup(gamma, 2)
+    mg = o.precond_block(0)
+    phi = y["phase"].reshape(mg.level_array(0, 0).shape)
+    expect = 1.0 + gamma * cfg.phi_mobility * cfg.phi_well_scale * 32.0 * (1.0 + 6.0 * phi * (phi - 1.0))
+    assert np.allclose(mg.level_array(0, 0), expect, rtol=1e-14)
+    assert np.allclose(mg.level_array(0, 1), cfg.phi_mobility, rtol=0)
+    assert np.allclose(mg.level_array(0, 3), -gamma * cfg.epsilon_phase ** 2 / cfg.dx[0] ** 2, rtol=1e-15)
+    assert mg.level_array(0, 2) is None
+    o.close()
+
+
+def _implicit(name, dt, nsteps, precond, **kw):
+    cfg, st = parity.make_case(name)
+    y = {k: (None if v is None else v.numpy().copy()) for k, v in st.items()}
+    o = pyoracle.Oracle(cfg)
+    if cfg.conc_rhs_form in (2, 3):
+        o.set_ref(y["conc"].ravel().copy(), y["conc"].ravel().copy())
+    if cfg.symmetry_aware:
+        o.set_rotations(parity.random_rotations(cfg))
+    o.set_preconditioner(precond)
+    rc, stats = o.integrate_implicit(y, dt, nsteps, **kw)
+    stats.update(o.precond_stats())
+    o.close()
+    return cfg, y, rc, stats
+
+
+@pytest.mark.parametrize("name,mult,ratio", [("dendrite2d", 50, 0.9), ("gg3d_hbsm", 40, 0.4), ("auni2d", 20, 0.7),
+                                             ("auni3d", 20, 0.5)])
+def test_preconditioner_cuts_the_krylov_work_and_keeps_the_trajectory(name, mult, ratio):
+    """stiff steps (20-50x the explicit trajectory step): right-preconditioned GMRES needs fewer Jacobian-vector
+    products for the same Newton tolerance (measured: 266 -> 60 for GG3D, 35 -> 13 for AuNi_3D, 20 -> 11 for
+    AuNi_2D; only 134 -> 104 for Dendrite2D, whose stiffness sits in the derivative of the singular 1/|grad q|
+    diffusivity that the frozen-coefficient blocks -- the reference's too -- do not contain), and the step it
+    converges to is the same"""
+    dt = parity.TRAJ_DT[name] * mult
+    kw = dict(order=2, rtol=1e-8, atol=1e-10, max_krylov=30, max_newton=8)
+    cfg, y0, rc0, s0 = _implicit(name, dt, 3, 0, **kw)
+    cfg, y1, rc1, s1 = _implicit(name, dt, 3, 2, **kw)
+    assert rc0 == 0 and rc1 == 0, (s0, s1)
+    assert s0["precond_setups"] == 0 and s1["precond_setups"] == s1["newton_iterations"] > 0
+    assert s1["precond_solves"] >= s1["linear_iterations"]
+    assert s1["linear_iterations"] < ratio * s0["linear_iterations"], (s0, s1)
+    for k in ("phase", "quat", "conc", "temperature"):
+        if y0.get(k) is not None:
+            scale = max(np.abs(y0[k]).max(), 1e-300)
+            assert np.abs(y1[k] - y0[k]).max() < 1e-6 * scale, k
