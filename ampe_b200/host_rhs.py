@@ -36,6 +36,15 @@ def load_host():
         L.ampe_host_integrate_implicit.restype = C.c_int
         L.ampe_host_integrate_implicit.argtypes = [vp, C.POINTER(_abi.RhsFields), C.c_double, C.c_double, C.c_int,
                                                    vp, vp, vp]
+        L.ampe_host_set_preconditioner.restype = C.c_int
+        L.ampe_host_set_preconditioner.argtypes = [vp, C.c_int]
+        L.ampe_host_precond_set.restype = C.c_int
+        L.ampe_host_precond_set.argtypes = [vp, C.c_double, C.POINTER(_abi.RhsFields), C.c_double]
+        L.ampe_host_precond_solve.restype = C.c_int
+        L.ampe_host_precond_solve.argtypes = [vp, C.POINTER(_abi.RhsFields), C.POINTER(_abi.RhsFields)]
+        L.ampe_host_precond_level_solver.restype = vp
+        L.ampe_host_precond_level_solver.argtypes = [vp, C.c_int]
+        L.ampe_host_precond_stats.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -88,6 +97,31 @@ class HostQuatIntegrator:
         names = ("steps", "rhs_evals", "jtimes_evals", "newton_iterations", "linear_iterations", "projections",
                  "last_newton_update", "last_linear_residual")
         return rc, dict(zip(names, list(st)))
+
+    # ---- block preconditioners ----
+    def setupPreconditioners(self, ncycles=2):
+        """QuatIntegrator::setupPreconditioners: ncycles V-cycles per block solve; 0 = off.  integrateImplicit
+        then runs right-preconditioned GMRES."""
+        self._chk(self.L.ampe_host_set_preconditioner(self.h, int(ncycles)))
+
+    def CVSpgmrPrecondSet(self, t, y, gamma):
+        fy = y.fields()
+        self._chk(self.L.ampe_host_precond_set(self.h, float(t), C.byref(fy), float(gamma)))
+
+    def CVSpgmrPrecondSolve(self, r, z):
+        fr, fz = r.fields(), z.fields()
+        self._chk(self.L.ampe_host_precond_solve(self.h, C.byref(fr), C.byref(fz)))
+
+    def preconditionerLevelSolver(self, block):
+        """the device multigrid of a block (0 phase, 1 quaternion, 2 composition, 3 temperature) or None"""
+        from .precond import LevelSolver
+        h = self.L.ampe_host_precond_level_solver(self.h, int(block))
+        return LevelSolver(handle=h, owner=self) if h else None
+
+    def precondStats(self):
+        out = (C.c_double * 2)()
+        self.L.ampe_host_precond_stats(self.h, out)
+        return {"precond_setups": out[0], "precond_solves": out[1]}
 
     def close(self):
         if self.h:

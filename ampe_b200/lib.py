@@ -84,6 +84,33 @@ def load():
     L.ampe_rhs_get_symmetry_rotations.argtypes = [vp, C.POINTER(vp), vp]
     L.ampe_quat_fundamental.restype = ci
     L.ampe_quat_fundamental.argtypes = [vp, pf, vp]
+    # block preconditioners (include/ampe_b200_precond.h)
+    pvp = C.POINTER(vp)
+    L.ampe_mg_create.restype = ci
+    L.ampe_mg_create.argtypes = [ci, C.POINTER(ci), pd, ci, pvp]
+    L.ampe_mg_destroy.restype = ci
+    L.ampe_mg_destroy.argtypes = [vp]
+    L.ampe_mg_set_elliptic.restype = ci
+    L.ampe_mg_set_elliptic.argtypes = [vp, vp, ci, dbl, vp, ci, dbl, pvp, pvp, ci, dbl, dbl, vp]
+    L.ampe_mg_set_quat.restype = ci
+    L.ampe_mg_set_quat.argtypes = [vp, dbl, vp, ci, pvp, ci, vp]
+    L.ampe_mg_solve.restype = ci
+    L.ampe_mg_solve.argtypes = [vp, vp, vp, ci, ci, vp]
+    L.ampe_mg_apply.restype = ci
+    L.ampe_mg_apply.argtypes = [vp, vp, vp, vp]
+    L.ampe_mg_set_sweeps.restype = ci
+    L.ampe_mg_set_sweeps.argtypes = [vp, ci, ci, ci]
+    L.ampe_mg_num_levels.restype = ci
+    L.ampe_mg_num_levels.argtypes = [vp]
+    L.ampe_mg_level_extents.restype = ci
+    L.ampe_mg_level_extents.argtypes = [vp, ci, C.POINTER(ci)]
+    L.ampe_mg_copy_level.restype = ci
+    L.ampe_mg_copy_level.argtypes = [vp, ci, ci, vp, vp]
+    L.ampe_mg_last_launch_count.restype = ci
+    L.ampe_mg_last_launch_count.argtypes = [vp]
+    L.ampe_k_phasefacops_setc.restype = ci
+    L.ampe_k_phasefacops_setc.argtypes = [ci, C.POINTER(ci), C.POINTER(ci), vp, ci, vp, ci, dbl, dbl, C.c_char_p,
+                                          vp, ci, vp]
     L.ampe_last_error.restype = C.c_char_p
     L.ampe_version.restype = C.c_char_p
     L.ampe_abi_sizeof_config.restype = ci

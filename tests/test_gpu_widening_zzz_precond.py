@@ -1,0 +1,211 @@
+"""SURVEY.md 8f rank 3 on the device: the block preconditioners behind include/ampe_b200_precond.h
+(csrc/mg.cu) and the host mirror's CVSpgmrPrecondSet / CVSpgmrPrecondSolve.
+
+* ampe_mg_apply against the reference's operators restated on the CPU (efo_compfluxvardc + efo_compresvarsca,
+  set_j_ij + set_stencil): 1e-13.
+* the device V-cycles against the host loop over the same per-cell functions (oracle/precond.cc part 2): the
+  arithmetic is identical (--fmad=false / -ffp-contract=off, red-black order independent) -- 1e-12 -- and the
+  residual measured by the RESTATED operator contracts.
+* CVSpgmrPrecondSet on the five configurations: every level-0 coefficient array of every block equals the CPU
+  context's (1e-12), CVSpgmrPrecondSolve equals the CPU solve (1e-10).
+* the right-preconditioned implicit trajectory on the device against the same template driven by the CPU
+  oracle: 1e-8, and fewer Krylov vectors than the unpreconditioned run.
+Added at the end of round 1 without a GPU left: first executed by a later GPU run."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import parity
+
+# new code, not yet executed on a GPU: the tests join the default GPU suite once a run has shown them green
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.environ.get("AMPE_B200_RUN_EXPERIMENTS"),
+                                 reason="set AMPE_B200_RUN_EXPERIMENTS=1 (first GPU run pending)")]
+
+from test_oracle_precond import BLOCKS, _evolved, _ghosted, _random_elliptic, _side_from_lower  # noqa: E402
+
+
+def _cuda(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("n,dx", [((64, 48), (0.3, 0.2)), ((32, 16, 24), (0.5, 0.4, 0.25)), ((15, 9), (1.0, 1.0))])
+def test_scalar_block_operator_and_solve(n, dx):
+    from ampe_b200.precond import LevelSolver
+    from oracle import pyoracle
+    ndim = len(n)
+    shape, m, c, lows, d = _random_elliptic(n, 3)
+    d = [40.0 * x for x in d]
+    rng = np.random.default_rng(4)
+    u = rng.standard_normal(shape)
+    mg_m, mg_c = _ghosted(m, 1, ndim), _ghosted(c, 2, ndim)
+    g = LevelSolver(n, dx)
+    g.set_elliptic(m=_cuda(mg_m), ngm=1, c=_cuda(mg_c), ngc=2, d=[_cuda(x) for x in d], ngd=0)
+    ref = pyoracle.elliptic_apply(n, dx, mg_m, 1, mg_c, 2, d, u)
+    got = g.apply(_cuda(u)).cpu().numpy()
+    assert np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max()
+    h = pyoracle.HostMG(n, dx)
+    h.set_elliptic(m=mg_m, ngm=1, c=mg_c, ngc=2, d=d, ngd=0)
+    assert g.num_levels() == h.num_levels()
+    for lvl in range(g.num_levels()):
+        assert g.level_extents(lvl) == h.level_extents(lvl)
+        for which in (0, 1, 3, 4) + ((5,) if ndim == 3 else ()):
+            a, b = g.level_array(lvl, which).cpu().numpy(), h.level_array(lvl, which)
+            assert np.abs(a - b).max() <= 1e-14 * np.abs(b).max(), (lvl, which)
+    rhs = rng.standard_normal(shape)
+    hist = []
+    for nc in (1, 2, 3):
+        z = g.solve(_cuda(rhs), ncycles=nc).cpu().numpy()
+        zh = h.solve(rhs, ncycles=nc)
+        assert np.abs(z - zh).max() <= 1e-12 * np.abs(zh).max(), nc
+        hist.append(np.linalg.norm(rhs - pyoracle.elliptic_apply(n, dx, mg_m, 1, mg_c, 2, d, z)))
+    assert hist[2] < hist[1] < hist[0] < np.linalg.norm(rhs)
+    assert g.last_launch_count() > 0
+    # constants, second diffusion array and scale (the EBS composition block)
+    g.set_elliptic(m_const=0.7, c_const=1.0, d=[_cuda(x) for x in d], d2=[_cuda(x) for x in d], ngd=0, d_scale=-0.25)
+    ones = np.ones(shape)
+    ref2 = pyoracle.elliptic_apply(n, dx, 0.7 * ones, 0, ones, 0, [-0.5 * x for x in d], u)
+    assert np.abs(g.apply(_cuda(u)).cpu().numpy() - ref2).max() <= 1e-13 * np.abs(ref2).max()
+    g.close()
+
+
+@pytest.mark.parametrize("n,dx", [((48, 40), (0.3, 0.2)), ((16, 12, 20), (0.5, 0.4, 0.25))])
+def test_quaternion_block_operator_and_solve(n, dx):
+    from ampe_b200.precond import LevelSolver
+    from oracle import pyoracle
+    ndim = len(n)
+    rng = np.random.default_rng(5)
+    shape = (n[2] if ndim == 3 else 1, n[1], n[0])
+    mob = 0.1 + rng.random(shape)
+    fc = [_side_from_lower(-(5.0 + 20.0 * rng.random(shape)), 2 - a) for a in range(ndim)]
+    w = rng.standard_normal(shape)
+    gamma = 0.37
+    mob_g = _ghosted(mob, 1, ndim)
+    g = LevelSolver(n, dx, with_column_scale=True)
+    g.set_quat(gamma, _cuda(mob_g), 1, [_cuda(x) for x in fc], 0)
+    ref = pyoracle.quat_stencil_apply(n, dx, gamma, np.sqrt(mob_g), 1, fc, w)
+    assert np.abs(g.apply(_cuda(w)).cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+    h = pyoracle.HostMG(n, dx, with_s=True)
+    h.set_quat(gamma, mob_g, 1, fc, 0)
+    rhs = rng.standard_normal(shape)
+    z = g.solve(_cuda(rhs), ncycles=3, symmetrized=True).cpu().numpy()
+    zh = h.solve(rhs, ncycles=3, symmetrized=True)
+    assert np.abs(z - zh).max() <= 1e-12 * np.abs(zh).max()
+    s = np.sqrt(mob)
+    res = rhs / s - pyoracle.quat_stencil_apply(n, dx, gamma, np.sqrt(mob_g), 1, fc, z / s)
+    assert np.linalg.norm(res) < 0.05 * np.linalg.norm(rhs / s)
+    g.close()
+
+
+def test_phasefacops_setc_kernel():
+    from ampe_b200.precond import phasefacops_setc
+    n = (20, 12, 8)
+    rng = np.random.default_rng(6)
+    phi = rng.random((8, 12, 20))
+    m = 0.5 + rng.random((8, 12, 20))
+    phi_g, m_g = _ghosted(phi, 2, 3), _ghosted(m, 1, 3)
+    c = torch.zeros((8, 12, 20), dtype=torch.float64, device="cuda")
+    phasefacops_setc(n, _cuda(phi_g), 2, _cuda(m_g), 1, 0.3, 1.7, "double", c, 0)
+    expect = 1.0 + (0.3 * m) * 1.7 * (32.0 * (1.0 + 6.0 * phi * (phi - 1.0)))
+    assert np.abs(c.cpu().numpy() - expect).max() <= 1e-14 * np.abs(expect).max()
+
+
+def _device_context(name):
+    from ampe_b200 import rhs
+    from ampe_b200.host_rhs import HostQuatIntegrator
+    cfg, st = parity.make_case(name)
+    y = rhs.to_device(st)
+    h = HostQuatIntegrator(cfg, True)
+    if cfg.conc_rhs_form in (2, 3):
+        c0 = y["conc"].reshape(-1).clone()
+        h.resetRefPhaseConcentrations(c0, c0.clone())
+    rot = parity.random_rotations(cfg) if cfg.symmetry_aware else None
+    if rot is not None:
+        h.setSymmetryRotations([torch.as_tensor(a).cuda() for a in rot])
+    return cfg, st, y, h, rot
+
+
+@pytest.mark.parametrize("name", ["dendrite2d", "auni2d", "gg3d_hbsm", "auni3d"])
+def test_precond_set_and_solve_match_the_cpu_context(name):
+    from oracle import pyoracle
+    cfg, st, y, h, rot = _device_context(name)
+    yd = y.like()
+    h.evaluateRHSFunction(0.0, y, yd, 0)  # the fd_flag = 0 evaluation that precedes every set-up
+    h.setupPreconditioners(2)
+    gamma = 20 * parity.TRAJ_DT[name]
+    h.CVSpgmrPrecondSet(0.0, y, gamma)
+    torch.cuda.synchronize()
+    yo = {k: (None if v is None else v.numpy().copy()) for k, v in st.items()}
+    o = pyoracle.Oracle(cfg)
+    if cfg.conc_rhs_form in (2, 3):
+        o.set_ref(yo["conc"].ravel().copy(), yo["conc"].ravel().copy())
+    if rot is not None:
+        o.set_rotations(rot)
+    assert o.eval(0.0, yo, fd_flag=0)[0] == 0
+    assert o.precond_setup(gamma, 2) == 0
+    for k in _evolved(cfg):
+        g, ho = h.preconditionerLevelSolver(BLOCKS[k]), o.precond_block(BLOCKS[k])
+        assert g is not None and g.num_levels() == ho.num_levels()
+        for which in (0, 1, 2, 3, 4, 5):
+            b = ho.level_array(0, which)
+            if b is None:
+                continue
+            a = g.level_array(0, which).cpu().numpy()
+            # the composition diffusivities carry the Newton-solved c_l, c_a (1e-11 like the composition RHS)
+            tol = 1e-10 if k == "conc" else 1e-12
+            assert np.abs(a - b).max() <= tol * np.abs(b).max(), (k, which)
+    rng = np.random.default_rng(31)
+    r = {k: (None if v is None else rng.standard_normal(v.shape)) for k, v in yo.items()}
+    rc, zo = o.precond_solve(r)
+    assert rc == 0
+    rd = y.like()
+    zd = y.like()
+    for k in ("phase", "quat", "conc", "temperature"):
+        if r.get(k) is not None and rd[k] is not None:
+            rd[k].copy_(torch.as_tensor(r[k]))
+    h.CVSpgmrPrecondSolve(rd, zd)
+    torch.cuda.synchronize()
+    for k in _evolved(cfg):
+        z = zd[k].cpu().numpy()
+        assert np.abs(z - zo[k]).max() <= 1e-10 * np.abs(zo[k]).max(), k
+    assert h.precondStats() == {"precond_setups": 1.0, "precond_solves": 1.0}
+    o.close()
+    h.close()
+
+
+@pytest.mark.parametrize("name,mult,nsteps", [("dendrite2d", 50, 4), ("auni2d", 20, 3), ("gg3d_hbsm", 40, 3),
+                                              ("auni3d", 20, 3)])
+def test_preconditioned_trajectory_matches_oracle_backend(name, mult, nsteps):
+    from oracle import pyoracle
+    kw = dict(order=2, rtol=1e-8, atol=1e-10, max_krylov=30, max_newton=8)
+    dt = parity.TRAJ_DT[name] * mult
+    cfg, st, y, h, rot = _device_context(name)
+    h.setupPreconditioners(2)
+    rc, sg = h.integrateImplicit(y, dt, nsteps, **kw)
+    torch.cuda.synchronize()
+    sg.update(h.precondStats())
+    yo = {k: (None if v is None else v.numpy().copy()) for k, v in st.items()}
+    o = pyoracle.Oracle(cfg)
+    if cfg.conc_rhs_form in (2, 3):
+        o.set_ref(yo["conc"].ravel().copy(), yo["conc"].ravel().copy())
+    if rot is not None:
+        o.set_rotations(rot)
+    o.set_preconditioner(2)
+    rco, so = o.integrate_implicit(yo, dt, nsteps, **kw)
+    so.update(o.precond_stats())
+    assert rc == 0 and rco == 0, (sg, so)
+    assert sg["precond_setups"] == sg["newton_iterations"] > 0
+    for k in ("phase", "quat", "conc", "temperature"):
+        if yo.get(k) is None:
+            continue
+        scale = max(np.abs(yo[k]).max(), 1e-300)
+        assert np.abs(y[k].cpu().numpy() - yo[k]).max() <= 1e-8 * scale, (k, sg, so)
+    # unpreconditioned device run of the same steps: more Krylov vectors
+    cfg, st, y2, h2, rot = _device_context(name)
+    rc2, s2 = h2.integrateImplicit(y2, dt, nsteps, **kw)
+    assert rc2 == 0 and sg["linear_iterations"] < s2["linear_iterations"], (sg, s2)
+    o.close()
+    h.close()
+    h2.close()
