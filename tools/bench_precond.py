@@ -1,0 +1,78 @@
+"""Timing of the block-preconditioner solve (csrc/mg.cu) on one GPU: ms per V-cycle and per level-0
+half sweep at the BASELINE workload sizes, against the HBM roofline.  One JSON line per case.
+Algorithmic bytes: a colour half-sweep touches u (read + write), f, c, m and ND face
+arrays for half of the cells -> (5 + ND) * 8 B per updated cell; a V(1,1) cycle = 4 half-sweeps +
+residual ((4 + ND) * 8 B / cell + 8 B write) + restriction (8 B / cell read) + prolongation (16 B / cell)
+on level 0, times 1 / (1 - 2^-ND) for the coarse levels.
+usage (GPU box): python tools/bench_precond.py [--cases 2d:2048x2048,3d:256x256x256] [--cycles 10]"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return json.load(open(p))["hbm_gbs"], "MEASURED_PEAKS.json"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def main():
+    from ampe_b200.precond import LevelSolver
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", default="2d:2048x2048,2d:4096x4096,3d:256x256x256,3d:512x512x512")
+    ap.add_argument("--cycles", type=int, default=10)
+    ap.add_argument("--reps", type=int, default=5)
+    a = ap.parse_args()
+    hbm, src = peak()
+    for case in a.cases.split(","):
+        kind, dims = case.split(":")
+        n = [int(v) for v in dims.split("x")]
+        nd = len(n)
+        ncell = 1
+        for v in n:
+            ncell *= v
+        shape = (n[2] if nd == 3 else 1, n[1], n[0])
+        torch.manual_seed(1)
+        g = LevelSolver(n, [1.0] * nd)
+        sides = []
+        for ax in range(nd):
+            s = list(shape)
+            s[2 - ax] += 1
+            sides.append(-(50.0 + 10.0 * torch.rand(s, dtype=torch.float64, device="cuda")))
+        g.set_elliptic(m_const=1.0, c_const=1.0, d=sides, ngd=0)
+        rhs = torch.randn(shape, dtype=torch.float64, device="cuda")
+        out = torch.empty_like(rhs)
+        g.solve(rhs, ncycles=2, out=out)
+        torch.cuda.synchronize()
+        res0 = float((rhs - g.apply(out)).norm() / rhs.norm())
+        best = None
+        for _ in range(a.reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()  # the library launches on the legacy default stream (stream = NULL), as torch does
+            g.solve(rhs, ncycles=a.cycles, out=out)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        launches = g.last_launch_count()
+        per_cycle = best / a.cycles
+        lvl0 = 4 * 0.5 * (5 + nd) * 8 + ((4 + nd) * 8 + 8) + 8 + 16
+        bytes_cycle = ncell * lvl0 / (1.0 - 0.5 ** nd)
+        gbs = bytes_cycle / (per_cycle * 1e-3) / 1e9
+        print(json.dumps({"case": case, "levels": g.num_levels(), "ms_per_vcycle": per_cycle,
+                          "launches_per_solve": launches, "algorithmic_bytes_per_vcycle": bytes_cycle,
+                          "achieved_gbs": gbs, "hbm_peak_gbs": hbm, "peak_source": src, "frac": gbs / hbm,
+                          "rel_residual_after_2_cycles": res0, "cells": ncell}))
+        g.close()
+
+
+if __name__ == "__main__":
+    main()
