@@ -285,10 +285,11 @@ class QuatIntegrator
    // defaults except precond_has_dquatdphi = false (block diagonal).  ncycles = V-cycles per block
    // solve (the reference iterates FAC cycles to CVODE's delta; a fixed count keeps the
    // preconditioner a fixed linear operator); 0 switches the preconditioner off.
-   void setupPreconditioners(int ncycles)
+   void setupPreconditioners(int ncycles, bool precond_has_dquatdphi = false)
    {
       const ampe_rhs_config& p = d_cfg;
       d_precond_cycles = ncycles;
+      d_precond_has_dquatdphi = precond_has_dquatdphi && p.with_phase && p.evolve_quat;  // :485
       d_use_preconditioner = ncycles > 0;
       if (!d_use_preconditioner) return;
       if (p.nranks > 1) throw std::runtime_error("setupPreconditioners: single rank only");
@@ -304,6 +305,17 @@ class QuatIntegrator
       }
       if (p.with_unsteady_temperature && !d_temperature_sys_solver)
          d_temperature_sys_solver.reset(new TemperatureFACSolver(d_hierarchy));
+      if (d_precond_has_dquatdphi && !d_diffusion4quatderiv) {
+         // RegisterVariables with d_precond_has_dquatdphi (QuatIntegrator.cc:1170-1190) and the
+         // solver-owned scratch of QuatFACOps (d_sqrt_m_id, d_face_coef_scratch_id)
+         d_quat_mobility_deriv_id = cellVar<double>(1, 0);
+         d_quat_diffusion_deriv_id = sideVar<double>(2, 0);
+         d_phase_sol_id = cellVar<double>(1, 1);
+         d_quat_rhs_id = cellVar<double>(p.qlen, 0);
+         d_sqrt_m_id = cellVar<double>(1, 1);
+         d_face_coef_scratch_id = sideVar<double>(1, 0);
+         d_diffusion4quatderiv.reset(new DerivDiffusionCoeffForQuat(p, d_quat_diffusion_deriv_id));
+      }
    }
    bool usePreconditioner() const { return d_use_preconditioner; }
    // QuatIntegrator::CVSpgmrPrecondSet(t, y, fy, jok, jcurPtr, gamma) (QuatIntegrator.cc:3300-3376)
@@ -338,10 +350,19 @@ class QuatIntegrator
                                                     p.conc_rhs_form == AMPE_CONC_EBS ? d_diff1_id : -1,
                                                     p.conc_mobility);
       }
+      if (d_precond_has_dquatdphi) {
+         // setCoefficients with d_precond_has_dquatdphi (:2978-2983, :3064-3070)
+         d_mobility_strategy->computeQuatMobilityDeriv(d_hierarchy, d_phase_scratch_id, d_quat_mobility_deriv_id);
+         d_diffusion4quatderiv->setDerivDiffusion(d_hierarchy, d_phase_scratch_id, d_temperature_scratch_id,
+                                                  d_quat_grad_side_copy_id);
+      }
       if (p.evolve_quat)
-         d_quat_sys_solver->setOperatorCoefficients(gamma, d_quat_mobility_id, -1, d_phase_scratch_id,
-                                                    d_temperature_scratch_id, -1, d_quat_grad_side_copy_id,
-                                                    d_quat_scratch_id);
+         d_quat_sys_solver->setOperatorCoefficients(gamma, d_quat_mobility_id,
+                                                    d_precond_has_dquatdphi ? d_quat_mobility_deriv_id : -1,
+                                                    d_phase_scratch_id, d_temperature_scratch_id,
+                                                    d_precond_has_dquatdphi ? d_quat_diffusion_deriv_id : -1,
+                                                    d_quat_grad_side_copy_id, d_quat_scratch_id);
+      d_precond_gamma = gamma;
       d_precond_setups++;
       return 0;
    }
@@ -352,7 +373,22 @@ class QuatIntegrator
       if (!d_use_preconditioner) throw std::runtime_error("CVSpgmrPrecondSolve: call setupPreconditioners first");
       const ampe_rhs_config& p = d_cfg;
       if (p.with_phase) d_phase_sys_solver->solveSystem(z->phase, r->phase, d_precond_cycles);
-      if (p.evolve_quat) d_quat_sys_solver->solveSystem(z->quat, r->quat, d_precond_cycles);
+      if (p.evolve_quat) {
+         const double* r_quat = r->quat;
+         if (d_precond_has_dquatdphi) {
+            // QuatPrecondSolve (:3602-3612): quat_rhs = r_quat + gamma [dF_q/dphi] phase_sol
+            fillScratchField(z->phase, d_phase_sol_id, 1);
+            d_quat_sys_solver->multiplyDQuatDPhiBlock(d_phase_sol_id, d_quat_rhs_id, d_sqrt_m_id,
+                                                      d_face_coef_scratch_id);
+            auto qr = d_patch->cell<double>(d_quat_rhs_id);
+            const Box& b = d_patch->getBox();
+            check(ampe_k_cell_axpy(b.ndim, b.lower, b.upper, p.qlen, d_precond_gamma, qr->getPointer(), 0, r->quat, 0,
+                                   qr->getPointer(), 0, nullptr),
+                  "axpy");
+            r_quat = qr->getPointer();
+         }
+         d_quat_sys_solver->solveSystem(z->quat, r_quat, d_precond_cycles);
+      }
       if (p.with_unsteady_temperature)
          d_temperature_sys_solver->solveSystem(z->temperature, r->temperature, d_precond_cycles);
       if (p.with_concentration) {
@@ -373,6 +409,14 @@ class QuatIntegrator
       if (block == 2) return d_conc_sys_solver ? d_conc_sys_solver->levelSolver() : nullptr;
       if (block == 3) return d_temperature_sys_solver ? d_temperature_sys_solver->levelSolver() : nullptr;
       return nullptr;
+   }
+   // QuatSysSolver::multiplyDQuatDPhiBlock on a ghost-0 phase vector; out: ghost-0 device array of depth qlen
+   void multiplyDQuatDPhiBlock(const double* phase, double* out)
+   {
+      if (!d_precond_has_dquatdphi) throw std::runtime_error("multiplyDQuatDPhiBlock: coupling block not set up");
+      fillScratchField(phase, d_phase_sol_id, 1);
+      d_quat_sys_solver->multiplyDQuatDPhiBlock(d_phase_sol_id, d_quat_rhs_id, d_sqrt_m_id, d_face_coef_scratch_id);
+      copyOut(d_quat_rhs_id, out, d_cfg.qlen);
    }
    long precondSetups() const { return d_precond_setups; }
    long precondSolves() const { return d_precond_solves; }
@@ -619,6 +663,11 @@ class QuatIntegrator
    int d_precond_cycles = 0;
    long d_precond_setups = 0, d_precond_solves = 0;
    int d_phase_precond_c_id = -1, d_conc_l_g0_id = -1, d_conc_a_g0_id = -1;
+   bool d_precond_has_dquatdphi = false;
+   double d_precond_gamma = 0.0;
+   int d_quat_mobility_deriv_id = -1, d_quat_diffusion_deriv_id = -1, d_phase_sol_id = -1, d_quat_rhs_id = -1,
+       d_sqrt_m_id = -1, d_face_coef_scratch_id = -1;
+   std::shared_ptr<DerivDiffusionCoeffForQuat> d_diffusion4quatderiv;
    std::shared_ptr<PhaseFACSolver> d_phase_sys_solver;
    std::shared_ptr<ConcFACSolver> d_conc_sys_solver;
    std::shared_ptr<TemperatureFACSolver> d_temperature_sys_solver;

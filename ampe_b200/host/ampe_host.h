@@ -511,9 +511,51 @@ class QuatMobilityStrategy
                "QUATMOBILITY");
       }
    }
+   // computeQuatMobilityDeriv (QuatIntegrator.cc:2978-2983, with precond_has_dquatdphi)
+   void computeQuatMobilityDeriv(std::shared_ptr<PatchHierarchy> h, int phase_id, int mobility_deriv_id)
+   {
+      for (auto& patch : *h->getPatchLevel(0)) {
+         auto phi = patch->cell<double>(phase_id);
+         auto m = patch->cell<double>(mobility_deriv_id);
+         check(ampe_k_quatmobilityderiv(AMPE_BOX_ARGS(patch), phi->getPointer(), phi->getGhostCellWidth(),
+                                        m->getPointer(), m->getGhostCellWidth(), d_cfg.quat_mobility,
+                                        d_cfg.min_quat_mobility, d_cfg.quat_mobility_func,
+                                        d_cfg.quat_mobility_alt_scale, nullptr),
+               "QUATMOBILITYDERIV");
+      }
+   }
 
  private:
    ampe_rhs_config d_cfg;
+};
+
+// ---- DerivDiffusionCoeffForQuat (DerivDiffusionCoeffForQuat.cc:60-148) ---------------------------
+class DerivDiffusionCoeffForQuat
+{
+ public:
+   DerivDiffusionCoeffForQuat(const ampe_rhs_config& cfg, int quat_diffusion_deriv_id)
+       : d_cfg(cfg), d_quat_diffusion_deriv_id(quat_diffusion_deriv_id)
+   {
+   }
+   void setDerivDiffusion(std::shared_ptr<PatchHierarchy> h, int phase_scratch_id, int temperature_scratch_id,
+                          int quat_grad_side_id)
+   {
+      for (auto& patch : *h->getPatchLevel(0)) {
+         auto phi = patch->cell<double>(phase_scratch_id), T = patch->cell<double>(temperature_scratch_id);
+         auto gq = patch->side<double>(quat_grad_side_id), dd = patch->side<double>(d_quat_diffusion_deriv_id);
+         auto g = gq->pointers(0), d = dd->pointers(0);
+         check(ampe_k_quatdiffusionderiv(AMPE_BOX_ARGS(patch), 2. * d_cfg.H_parameter, T->getPointer(),
+                                         T->getGhostCellWidth(), phi->getPointer(), phi->getGhostCellWidth(),
+                                         d_cfg.qlen, g.data(), gq->getGhostCellWidth(), d.data(),
+                                         dd->getGhostCellWidth(), d_cfg.quat_grad_floor, d_cfg.grad_floor_type,
+                                         d_cfg.orient_interp1, d_cfg.avg_func, nullptr),
+               "QUATDIFFUSIONDERIV");
+      }
+   }
+
+ private:
+   ampe_rhs_config d_cfg;
+   int d_quat_diffusion_deriv_id;
 };
 
 // ---- QuatFaceCoeff (QuatFaceCoeff.cc:39-121) ----------------------------------------------------
@@ -560,13 +602,14 @@ class QuatSysSolver
    // QuatSysSolver::setOperatorCoefficients (QuatSysSolver.cc:268-292) -> QuatFACOps::
    // setOperatorCoefficients (QuatFACOps.cc:735-818): face coefficients from (phase, T, grad_q), the
    // square root of the mobility, then QuatLevelSolver::setMatrixCoefficients.  The derivative ids
-   // feed the dquat/dphi coupling block only (precond_has_dquatdphi), which is not built: pass -1.
+   // feed the dquat/dphi coupling block only (precond_has_dquatdphi; -1 without it).
    void setOperatorCoefficients(double gamma, int mobility_id, int mobility_deriv_id, int phase_id,
                                 int temperature_id, int face_coef_deriv_id, int grad_q_id, int q_id)
    {
-      (void)q_id;
-      if (mobility_deriv_id >= 0 || face_coef_deriv_id >= 0)
-         throw std::runtime_error("QuatSysSolver::setOperatorCoefficients: the dquat/dphi block is not built");
+      d_q_local_id = q_id;  // the reference copies q (q_local_data->copy); the scratch q is not touched in between
+      d_mobility_id = mobility_id;
+      d_m_deriv_id = mobility_deriv_id;
+      d_face_coef_deriv_id = face_coef_deriv_id;
       d_face_coeff->computeFaceCoefs(d_h, phase_id, temperature_id, grad_q_id, d_fc_id);
       auto patch = d_h->getPatchLevel(0)->patches.front();
       if (!d_mg) {
@@ -595,6 +638,57 @@ class QuatSysSolver
       return true;
    }
    ampe_mg* levelSolver() const { return d_mg; }
+   // QuatSysSolver::multiplyDQuatDPhiBlock -> QuatFACOps::multiplyDQuatDPhiBlock (QuatFACOps.cc:1892-1956):
+   // out = [mobility'(phi) div(fc grad q)] phase + sqrt_m div(fc'[phase] grad q); phase_id: CellData with
+   // filled ghosts, out_id: CellData depth qlen; scratch ids: sqrt_m (cell, ghosts of the mobility),
+   // face_coef_scratch (side, depth 1)
+   void multiplyDQuatDPhiBlock(int phase_id, int out_id, int sqrt_m_id, int face_coef_scratch_id)
+   {
+      if (d_m_deriv_id < 0 || d_face_coef_deriv_id < 0)
+         throw std::runtime_error("multiplyDQuatDPhiBlock: setOperatorCoefficients was called without the derivatives");
+      const int Q = d_cfg.qlen;
+      for (auto& patch : *d_h->getPatchLevel(0)) {
+         auto out = patch->cell<double>(out_id), q = patch->cell<double>(d_q_local_id);
+         auto phase = patch->cell<double>(phase_id);
+         auto mob = patch->cell<double>(d_mobility_id), sq = patch->cell<double>(sqrt_m_id);
+         auto mder = patch->cell<double>(d_m_deriv_id);
+         auto fc = patch->side<double>(d_fc_id), fcs = patch->side<double>(face_coef_scratch_id);
+         auto dpr = patch->side<double>(d_face_coef_deriv_id), flux = patch->side<double>(d_flux_id);
+         auto c = fc->pointers(0), cs = fcs->pointers(0), dp = dpr->pointers(0), f = flux->pointers(0);
+         out->fillAll(0);
+         // takeSquareRootOnPatch of a copy of the mobility (QuatFACOps.cc:779-783)
+         cuda_check(cudaMemcpy(sq->getPointer(), mob->getPointer(), mob->size() * sizeof(double),
+                               cudaMemcpyDeviceToDevice),
+                    "sqrt_m copy");
+         check(ampe_k_take_square_root(AMPE_BOX_ARGS(patch), sq->getPointer(), sq->getGhostCellWidth(), nullptr),
+               "TAKE_SQUARE_ROOT");
+         // accumulateOperatorOnLevel(d_m_deriv_id, d_face_coef_id, d_q_local_id, -1, out_id, ...)
+         check(ampe_k_compute_flux(AMPE_BOX_ARGS(patch), Q, c.data(), fc->getGhostCellWidth(), q->getPointer(),
+                                   q->getGhostCellWidth(), patch->getDx(), f.data(), flux->getGhostCellWidth(),
+                                   nullptr),
+               "COMPUTE_FLUX");
+         check(ampe_k_add_quat_op(AMPE_BOX_ARGS(patch), Q, mder->getPointer(), mder->getGhostCellWidth(), f.data(),
+                                  flux->getGhostCellWidth(), patch->getDx(), out->getPointer(),
+                                  out->getGhostCellWidth(), nullptr),
+               "ADD_QUAT_OP");
+         check(ampe_k_multicomponent_multiply(AMPE_BOX_ARGS(patch), phase->getPointer(), phase->getGhostCellWidth(),
+                                              out->getPointer(), out->getGhostCellWidth(), Q, nullptr),
+               "MULTICOMPONENT_MULTIPLY");
+         // computeDQuatDPhiFaceCoefs + accumulateOperatorOnLevel(d_sqrt_m_id, d_face_coef_scratch_id, ...)
+         check(ampe_k_compute_dquatdphi_face_coef(AMPE_BOX_ARGS(patch), Q, dp.data(), dpr->getGhostCellWidth(),
+                                                  phase->getPointer(), phase->getGhostCellWidth(), cs.data(),
+                                                  fcs->getGhostCellWidth(), nullptr),
+               "COMPUTE_DQUATDPHI_FACE_COEF");
+         check(ampe_k_compute_flux(AMPE_BOX_ARGS(patch), Q, cs.data(), fcs->getGhostCellWidth(), q->getPointer(),
+                                   q->getGhostCellWidth(), patch->getDx(), f.data(), flux->getGhostCellWidth(),
+                                   nullptr),
+               "COMPUTE_FLUX");
+         check(ampe_k_add_quat_op(AMPE_BOX_ARGS(patch), Q, sq->getPointer(), sq->getGhostCellWidth(), f.data(),
+                                  flux->getGhostCellWidth(), patch->getDx(), out->getPointer(),
+                                  out->getGhostCellWidth(), nullptr),
+               "ADD_QUAT_OP");
+      }
+   }
    void evaluateRHS(int phase_id, int temperature_id, int grad_q_id, int grad_q_copy_id,
                     int rotations_id, int mobility_id, int solution_id, int rhs_id,
                     bool use_gradq_for_flux)
@@ -647,6 +741,7 @@ class QuatSysSolver
    std::shared_ptr<QuatFaceCoeff> d_face_coeff;
    int d_fc_id, d_flux_id, d_lambda_id;
    ampe_mg* d_mg = nullptr;
+   int d_q_local_id = -1, d_mobility_id = -1, d_m_deriv_id = -1, d_face_coef_deriv_id = -1;
 };
 
 // ---- PhaseRHSStrategyWithQ (PhaseRHSStrategyWithQ.cc:90-312) ------------------------------------

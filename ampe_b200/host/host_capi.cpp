@@ -79,10 +79,10 @@ int ampe_host_integrate_implicit(void* h, const ampe_rhs_fields* y, double t0, d
 }
 // ---- block preconditioners ------------------------------------------------
 // QuatIntegrator::setupPreconditioners; ncycles V-cycles per block solve, 0 = preconditioner off
-int ampe_host_set_preconditioner(void* h, int ncycles)
+int ampe_host_set_preconditioner(void* h, int ncycles, int precond_has_dquatdphi)
 {
    try {
-      static_cast<ampe_host::QuatIntegrator*>(h)->setupPreconditioners(ncycles);
+      static_cast<ampe_host::QuatIntegrator*>(h)->setupPreconditioners(ncycles, precond_has_dquatdphi != 0);
       return 0;
    } catch (const std::exception& e) {
       g_host_err = e.what();
@@ -106,6 +106,18 @@ int ampe_host_precond_solve(void* h, const ampe_rhs_fields* r, const ampe_rhs_fi
       const int rc = static_cast<ampe_host::QuatIntegrator*>(h)->CVSpgmrPrecondSolve(r, z);
       cudaDeviceSynchronize();
       return rc;
+   } catch (const std::exception& e) {
+      g_host_err = e.what();
+      return -1;
+   }
+}
+// QuatSysSolver::multiplyDQuatDPhiBlock: out (depth qlen, ghost 0, device) = [dF_q/dphi] phase
+int ampe_host_precond_dquatdphi(void* h, const double* phase, double* out)
+{
+   try {
+      static_cast<ampe_host::QuatIntegrator*>(h)->multiplyDQuatDPhiBlock(phase, out);
+      cudaDeviceSynchronize();
+      return 0;
    } catch (const std::exception& e) {
       g_host_err = e.what();
       return -1;

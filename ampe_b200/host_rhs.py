@@ -37,7 +37,9 @@ def load_host():
         L.ampe_host_integrate_implicit.argtypes = [vp, C.POINTER(_abi.RhsFields), C.c_double, C.c_double, C.c_int,
                                                    vp, vp, vp]
         L.ampe_host_set_preconditioner.restype = C.c_int
-        L.ampe_host_set_preconditioner.argtypes = [vp, C.c_int]
+        L.ampe_host_set_preconditioner.argtypes = [vp, C.c_int, C.c_int]
+        L.ampe_host_precond_dquatdphi.restype = C.c_int
+        L.ampe_host_precond_dquatdphi.argtypes = [vp, vp, vp]
         L.ampe_host_precond_set.restype = C.c_int
         L.ampe_host_precond_set.argtypes = [vp, C.c_double, C.POINTER(_abi.RhsFields), C.c_double]
         L.ampe_host_precond_solve.restype = C.c_int
@@ -99,10 +101,16 @@ class HostQuatIntegrator:
         return rc, dict(zip(names, list(st)))
 
     # ---- block preconditioners ----
-    def setupPreconditioners(self, ncycles=2):
+    def setupPreconditioners(self, ncycles=2, precond_has_dquatdphi=False):
         """QuatIntegrator::setupPreconditioners: ncycles V-cycles per block solve; 0 = off.  integrateImplicit
-        then runs right-preconditioned GMRES."""
-        self._chk(self.L.ampe_host_set_preconditioner(self.h, int(ncycles)))
+        then runs right-preconditioned GMRES.  precond_has_dquatdphi: with the dquat/dphi coupling block."""
+        self._chk(self.L.ampe_host_set_preconditioner(self.h, int(ncycles), 1 if precond_has_dquatdphi else 0))
+
+    def multiplyDQuatDPhiBlock(self, phase, qlen):
+        """QuatSysSolver::multiplyDQuatDPhiBlock on a ghost-0 CUDA tensor; returns (qlen, ...) tensor"""
+        out = torch.empty((qlen,) + tuple(phase.shape[-3:]), dtype=torch.float64, device=phase.device)
+        self._chk(self.L.ampe_host_precond_dquatdphi(self.h, phase.data_ptr(), out.data_ptr()))
+        return out
 
     def CVSpgmrPrecondSet(self, t, y, gamma):
         fy = y.fields()

@@ -211,6 +211,30 @@ int ampe_k_project(int ndim, const int* lo, const int* hi, int depth, const doub
 int ampe_k_fill_periodic_int(int ndim, const int* ifirst, const int* ilast, int axis,
                              const int* src, int* dst, int ng, void* stream);
 
+/* ---- the dquat/dphi coupling block of the preconditioner (precond_coupling.cu) ----------------- */
+/* QUATDIFFUSIONDERIV (QuatFort.h:546): diff[a] = SideData depth 2 (d/dphi of the lower, upper cell) */
+int ampe_k_quatdiffusionderiv(int ndim, const int* ifirst, const int* ilast, double misorientation_factor,
+                              const double* temperature, int tghosts, const double* var, int ngvar, int depth,
+                              double* const* gradq, int nggradq, double* const* diff, int ngdiff,
+                              double gradient_floor, char smooth_floor_type, char interp_type, char avg_type,
+                              void* stream);
+/* QUATMOBILITYDERIV (QuatFort.h:659) */
+int ampe_k_quatmobilityderiv(int ndim, const int* ifirst, const int* ilast, const double* phase, int ngphase,
+                             double* dmobility, int ngmobility, double scale_mobility, double min_mobility,
+                             char func_type, double alt_scale_factor, void* stream);
+/* COMPUTE_DQUATDPHI_FACE_COEF2D/3D (QuatFort.h:790) */
+int ampe_k_compute_dquatdphi_face_coef(int ndim, const int* lo, const int* hi, int depth, double* const* dprime,
+                                       int ngdprime, const double* phi, int ngphi, double* const* face_coef,
+                                       int ngfc, void* stream);
+/* MULTICOMPONENT_MULTIPLY2D/3D (QuatFort.h:892): var(:,n) *= factor for n < vnc */
+int ampe_k_multicomponent_multiply(int ndim, const int* lo, const int* hi, const double* factor, int ngfactor,
+                                   double* var, int ngvar, int vnc, void* stream);
+/* TAKE_SQUARE_ROOT2D/3D (QuatFort.h:890): in place over the ghost box */
+int ampe_k_take_square_root(int ndim, const int* lo, const int* hi, double* data, int ng, void* stream);
+/* HierarchyCellDataOpsReal::axpy as used by QuatPrecondSolve (QuatIntegrator.cc:3612): dst = alpha x + y */
+int ampe_k_cell_axpy(int ndim, const int* lo, const int* hi, int depth, double alpha, const double* x, int ngx,
+                     const double* y, int ngy, double* dst, int ngdst, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

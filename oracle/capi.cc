@@ -28,14 +28,26 @@ void oracle_get_phase_concentrations(void* c, double* cl, double* ca)
 int oracle_energy(void* c, const ampe_rhs_fields* y, double* out) { return energy((Ctx*)c, y, out); }
 // ---- block preconditioners (precond.cc) --------------------------------------------------------
 // ncycles > 0: oracle_integrate_implicit runs right-preconditioned GMRES with that many V-cycles
-void oracle_set_preconditioner(void* c, int ncycles) { ((Ctx*)c)->precond_cycles = ncycles; }
+void oracle_set_preconditioner(void* c, int ncycles, int has_dquatdphi)
+{
+   ((Ctx*)c)->precond_cycles = ncycles;
+   ((Ctx*)c)->precond_dquatdphi = has_dquatdphi != 0;
+}
 void oracle_precond_stats(void* c, double* out2)
 {
    out2[0] = ((Ctx*)c)->precond_stats[0];
    out2[1] = ((Ctx*)c)->precond_stats[1];
 }
 // after an fd_flag = 0 evaluation at the state the coefficients are frozen at
-int oracle_precond_setup(void* c, double gamma, int ncycles) { return precond_setup((Ctx*)c, gamma, ncycles); }
+int oracle_precond_setup(void* c, double gamma, int ncycles, int has_dquatdphi)
+{
+   return precond_setup((Ctx*)c, gamma, ncycles, has_dquatdphi != 0);
+}
+// QuatFACOps::multiplyDQuatDPhiBlock: out (depth qlen, ghost 0) = [dF_q/dphi] z_phase
+int oracle_precond_dquatdphi(void* c, const double* z_phase, double* out)
+{
+   return precond_dquatdphi((Ctx*)c, z_phase, out);
+}
 int oracle_precond_solve(void* c, const ampe_rhs_fields* r, const ampe_rhs_fields* z)
 {
    return precond_solve((Ctx*)c, r, z);

@@ -41,6 +41,7 @@ struct Ctx {
    bool have_ref = false;
    void* precond = nullptr;     // block preconditioners (precond.cc)
    int precond_cycles = 0;      // > 0: the implicit integrator runs right-preconditioned (stepper.cc)
+   bool precond_dquatdphi = false;  // with the dquat/dphi coupling block
    double precond_stats[2] = {0, 0};  // set-ups, solves of the last implicit integration
 };
 

@@ -120,6 +120,90 @@ void quat_stencil_apply(const Box& b, const double* h, double gamma, View sqrt_m
          }
 }
 
+// ---- (1b) the dquat/dphi coupling block (precond_has_dquatdphi, QuatIntegrator.cc:114, 468-470) ---
+// quatdiffusionderiv ({2d,3d}/quatdiffusion.m4:11-150): derivative of the orientation diffusivity
+// 2HT p'(phi_face) / |grad q| with respect to the two cells of a face; depth 1 = lower cell, 2 = upper
+void quatdiffusionderiv(const Box& b, double misorientation_factor, View temperature, View var, int depth,
+                        View* gradq, View* diff, double gradient_floor, char smooth_floor_type, char interp_type,
+                        char avg_type)
+{
+   const double jlf_threshold = 1.0e-16;
+   const double floor_grad_norm2 = gradient_floor * gradient_floor;
+   const double max_grad_normi = 1.0 / gradient_floor;
+   for (int a = 0; a < b.ndim; a++) {
+      const int e0 = a == 0, e1 = a == 1, e2 = a == 2;
+      for (int k = b.lo[2]; k <= b.hi[2] + e2; k++)
+         for (int j = b.lo[1]; j <= b.hi[1] + e1; j++)
+            for (int i = b.lo[0]; i <= b.hi[0] + e0; i++) {
+               const double vm = var(i - e0, j - e1, k - e2), vp = var(i, j, k);
+               if (vm < jlf_threshold || vp < jlf_threshold) {
+                  diff[a](i, j, k, 0) = 0.0;
+                  diff[a](i, j, k, 1) = 0.0;
+                  continue;
+               }
+               const double phi = average_func(vm, vp, avg_type);
+               const double t = 0.5 * (temperature(i - e0, j - e1, k - e2) + temperature(i, j, k));
+               const double d_deriv = misorientation_factor * t * deriv_interp_func(phi, interp_type);
+               double grad_norm2 = 0.0;
+               for (int n = 0; n < b.ndim; n++)
+                  for (int m = 0; m < depth; m++) {
+                     const double g = gradq[a](i, j, k, n * depth + m);
+                     grad_norm2 = grad_norm2 + g * g;
+                  }
+               const double grad_normi = eval_grad_normi(grad_norm2, smooth_floor_type, floor_grad_norm2, max_grad_normi);
+               const double fac = grad_normi * d_deriv;
+               diff[a](i, j, k, 0) = fac * deriv_average_func(phi, vm, avg_type);
+               diff[a](i, j, k, 1) = fac * deriv_average_func(phi, vp, avg_type);
+            }
+   }
+}
+
+// quatmobilityderiv ({2d,3d}/mobility.m4:97-170)
+void quatmobilityderiv(const Box& b, View phase, View dmobility, double scale_mobility, double min_mobility,
+                       char func_type, double alt_scale_factor)
+{
+   for (int k = b.lo[2]; k <= b.hi[2]; k++)
+      for (int j = b.lo[1]; j <= b.hi[1]; j++)
+         for (int i = b.lo[0]; i <= b.hi[0]; i++) {
+            double phi = phase(i, j, k), dqfunc;
+            if (func_type == 'p' || func_type == 'P') {
+               phi = fmax(0.0, fmin(1.0, phi));
+               dqfunc = -30.0 * phi * phi * (1.0 - phi) * (1.0 - phi);
+            } else if (func_type == 'e' || func_type == 'E') {
+               const double c = alt_scale_factor;
+               phi = fmax(0.0, fmin(1.0, phi));
+               dqfunc = (c * exp(c * phi)) / (1. - exp(c));
+            } else if (func_type == 'i' || func_type == 'I') {
+               phi = fmax(1.e-6, fmin(1.0, phi));
+               dqfunc = (phi - 2.0) / (phi * phi * phi);
+            } else {
+               throw std::runtime_error("Error in quatmobilityderiv: unknown function type");
+            }
+            dmobility(i, j, k) = (scale_mobility - min_mobility) * dqfunc;
+         }
+}
+
+// compute_dquatdphi_face_coef ({2d,3d}/quatfacops.m4:124-170): fc = -D'_lower phi_lower - D'_upper phi_upper
+void compute_dquatdphi_face_coef(const Box& b, View* dprime, View phi, View* fc)
+{
+   for (int a = 0; a < b.ndim; a++) {
+      const int e0 = a == 0, e1 = a == 1, e2 = a == 2;
+      for (int k = b.lo[2]; k <= b.hi[2] + e2; k++)
+         for (int j = b.lo[1]; j <= b.hi[1] + e1; j++)
+            for (int i = b.lo[0]; i <= b.hi[0] + e0; i++)
+               fc[a](i, j, k) = -dprime[a](i, j, k, 0) * phi(i - e0, j - e1, k - e2) - dprime[a](i, j, k, 1) * phi(i, j, k);
+   }
+}
+
+// multicomponent_multiply ({2d,3d}/quatfacops.m4:1022-1049)
+void multicomponent_multiply(const Box& b, View factor, View var, int vnc)
+{
+   for (int n = 0; n < vnc; n++)
+      for (int k = b.lo[2]; k <= b.hi[2]; k++)
+         for (int j = b.lo[1]; j <= b.hi[1]; j++)
+            for (int i = b.lo[0]; i <= b.hi[0]; i++) var(i, j, k, n) = var(i, j, k, n) * factor(i, j, k);
+}
+
 // ---- (2) host loop over the product's per-cell multigrid arithmetic ------------------------------
 using ampe_mg_cell::Level;
 
@@ -264,6 +348,12 @@ struct Precond {
    Field sqrt_m;        // sqrt of the quaternion mobility, ghost 1
    Field ones, conc_m;  // constants as fields for elliptic_apply
    SideField const_d;   // constant D as side field (phase / temperature)
+   // dquat/dphi coupling block (precond_has_dquatdphi)
+   bool has_dquatdphi = false;
+   Field m_deriv;        // d(quat mobility)/d(phi), ghost 0
+   SideField d_deriv;    // d(face diffusivity)/d(phi of the lower, upper cell), depth 2, ghost 0
+   SideField fc_scratch, flux;  // face_coef_scratch, flux scratch (depth Q)
+   Field phase_sol, quat_rhs;   // z_phase with ghosts (ghost 1); coupled right-hand side (depth Q)
 };
 
 static void views3(SideField& s, View* v, int ndim)
@@ -280,7 +370,7 @@ void precond_destroy(Ctx* c)
 // Requires the context's intermediates at the state y of the last fd_flag = 0 evaluation (the
 // reference calls setCoefficients(t, y, true) here, QuatIntegrator.cc:3319; the integrator template
 // calls this hook right after that evaluation).
-int precond_setup(Ctx* c, double gamma, int ncycles)
+int precond_setup(Ctx* c, double gamma, int ncycles, bool has_dquatdphi)
 {
    const ampe_rhs_config& p = c->cfg;
    const Box& b = c->box;
@@ -343,7 +433,60 @@ int precond_setup(Ctx* c, double gamma, int ncycles)
       if (!P.quat) P.quat.reset(new HostMG(D, n, p.dx, true));
       P.quat->setQuat(gamma, c->quat_mobility.data.data(), 1, fc, 0);
    }
+   // setCoefficients with d_precond_has_dquatdphi (QuatIntegrator.cc:2978-2983, 3064-3070)
+   P.has_dquatdphi = has_dquatdphi && p.with_phase && p.evolve_quat;
+   if (P.has_dquatdphi) {
+      const int Q = p.qlen;
+      if (P.m_deriv.data.empty()) {
+         P.m_deriv.alloc(b, -1, 0, 1);
+         P.d_deriv.alloc(b, 0, 2);
+         P.fc_scratch.alloc(b, 0, 1);
+         P.flux.alloc(b, 0, Q);
+         P.phase_sol.alloc(b, -1, 1, 1);
+         P.quat_rhs.alloc(b, -1, 0, Q);
+      }
+      quatmobilityderiv(b, c->phase.v, P.m_deriv.v, p.quat_mobility, p.min_quat_mobility, p.quat_mobility_func,
+                        p.quat_mobility_alt_scale);
+      View gq[3], dd[3];
+      views3(c->quat_grad_side_copy, gq, D);
+      views3(P.d_deriv, dd, D);
+      // DerivDiffusionCoeffForQuat (QuatIntegrator.cc:1954-1957): interp = orient_interp_func_type1
+      quatdiffusionderiv(b, 2. * p.H_parameter, c->temp.v, c->phase.v, Q, gq, dd, p.quat_grad_floor, p.grad_floor_type,
+                         p.orient_interp1, p.avg_func);
+   }
    return 0;
+}
+
+// QuatFACOps::multiplyDQuatDPhiBlock(phase_id, out_id) (QuatFACOps.cc:1892-1956): out = dF_q/dphi z_phase with
+// the frozen q: [mobility'(phi) div(fc grad q)] z_phase + sqrt_m div(fc' grad q), fc' = -D'_- z_- - D'_+ z_+
+static void multiply_dquatdphi_block(Ctx* c, Precond& P, const double* z_phase, View out)
+{
+   const ampe_rhs_config& p = c->cfg;
+   const Box& b = c->box;
+   const int D = p.ndim, Q = p.qlen;
+   const int n0 = b.hi[0] + 1, n1 = b.hi[1] + 1, n2 = b.hi[2] + 1;
+   const int g2 = D == 3 ? 1 : 0;
+   for (int k = -g2; k < n2 + g2; k++)
+      for (int j = -1; j < n1 + 1; j++)
+         for (int i = -1; i < n0 + 1; i++)
+            P.phase_sol.v(i, j, k) = z_phase[(size_t)wrapi(i, n0) + (size_t)n0 * (wrapi(j, n1) + (size_t)n1 * wrapi(k, n2))];
+   for (int m = 0; m < Q; m++)
+      for (int k = 0; k < n2; k++)
+         for (int j = 0; j < n1; j++)
+            for (int i = 0; i < n0; i++) out(i, j, k, m) = 0.0;
+   View fc[3], fcs[3], fl[3], dd[3];
+   views3(c->face_coef, fc, D);
+   views3(P.fc_scratch, fcs, D);
+   views3(P.flux, fl, D);
+   views3(P.d_deriv, dd, D);
+   // accumulateOperatorOnLevel(d_m_deriv_id, d_face_coef_id, d_q_local_id, -1, out_id, ...)
+   compute_flux(b, Q, fc, c->quat.v, p.dx, fl);
+   add_quat_op(b, Q, P.m_deriv.v, fl, p.dx, out);
+   multicomponent_multiply(b, P.phase_sol.v, out, Q);
+   // computeDQuatDPhiFaceCoefs + accumulateOperatorOnLevel(d_sqrt_m_id, d_face_coef_scratch_id, ...)
+   compute_dquatdphi_face_coef(b, dd, P.phase_sol.v, fcs);
+   compute_flux(b, Q, fcs, c->quat.v, p.dx, fl);
+   add_quat_op(b, Q, P.sqrt_m.v, fl, p.dx, out);
 }
 
 static size_t ncell_of(const Ctx* c)
@@ -362,8 +505,16 @@ int precond_solve(Ctx* c, const ampe_rhs_fields* r, const ampe_rhs_fields* z)
    const ampe_rhs_config& p = c->cfg;
    const size_t nc = ncell_of(c);
    if (p.with_phase) P.phase->solve(r->phase, z->phase, P.ncycles, false);
-   if (p.evolve_quat)
-      for (int m = 0; m < p.qlen; m++) P.quat->solve(r->quat + nc * m, z->quat + nc * m, P.ncycles, true);
+   if (p.evolve_quat) {
+      const double* rq = r->quat;
+      if (P.has_dquatdphi) {
+         // QuatPrecondSolve (QuatIntegrator.cc:3602-3612): rhs_q = r_q + gamma [dF_q/dphi] z_phase
+         multiply_dquatdphi_block(c, P, z->phase, P.quat_rhs.v);
+         for (size_t o = 0; o < nc * (size_t)p.qlen; o++) P.quat_rhs.data[o] = P.gamma * P.quat_rhs.data[o] + r->quat[o];
+         rq = P.quat_rhs.data.data();
+      }
+      for (int m = 0; m < p.qlen; m++) P.quat->solve(rq + nc * m, z->quat + nc * m, P.ncycles, true);
+   }
    if (p.with_unsteady_temperature) P.temp->solve(r->temperature, z->temperature, P.ncycles, false);
    if (p.with_concentration) {
       if (P.conc)
@@ -420,6 +571,15 @@ int precond_apply(Ctx* c, int block, const double* u, double* out)
       return 0;
    }
    return -1;
+}
+
+int precond_dquatdphi(Ctx* c, const double* z_phase, double* out)
+{
+   if (!c->precond || !((Precond*)c->precond)->has_dquatdphi) return -1;
+   Precond& P = *(Precond*)c->precond;
+   multiply_dquatdphi_block(c, P, z_phase, P.quat_rhs.v);
+   memcpy(out, P.quat_rhs.data.data(), sizeof(double) * P.quat_rhs.data.size());
+   return 0;
 }
 
 HostMG* precond_block(Ctx* c, int block)

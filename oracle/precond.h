@@ -46,7 +46,15 @@ class HostMG
    std::vector<bool> d_two_colour;
 };
 
-int precond_setup(Ctx* c, double gamma, int ncycles);
+int precond_setup(Ctx* c, double gamma, int ncycles, bool has_dquatdphi);
+int precond_dquatdphi(Ctx* c, const double* z_phase, double* out);
+void quatdiffusionderiv(const Box& b, double misorientation_factor, View temperature, View var, int depth,
+                        View* gradq, View* diff, double gradient_floor, char smooth_floor_type, char interp_type,
+                        char avg_type);
+void quatmobilityderiv(const Box& b, View phase, View dmobility, double scale_mobility, double min_mobility,
+                       char func_type, double alt_scale_factor);
+void compute_dquatdphi_face_coef(const Box& b, View* dprime, View phi, View* fc);
+void multicomponent_multiply(const Box& b, View factor, View var, int vnc);
 int precond_solve(Ctx* c, const ampe_rhs_fields* r, const ampe_rhs_fields* z);
 int precond_apply(Ctx* c, int block, const double* u, double* out);
 HostMG* precond_block(Ctx* c, int block);

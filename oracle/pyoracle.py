@@ -24,10 +24,21 @@ def build(perf=False):
 _libs = {}
 
 
+def _stale(path):
+    """a source newer than the library (an edit without a rebuild): let make decide"""
+    try:
+        t = os.path.getmtime(path)
+        srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cc", ".h"))]
+        srcs.append(os.path.join(os.path.dirname(_HERE), "ampe_b200", "csrc", "mg_cell.h"))
+        return any(os.path.getmtime(f) > t for f in srcs if os.path.exists(f))
+    except OSError:
+        return False
+
+
 def lib(perf=False):
     if perf not in _libs:
         path = os.path.join(_HERE, "liboracle_perf.so" if perf else "liboracle.so")
-        if not os.path.exists(path):
+        if not os.path.exists(path) or _stale(path):
             build(perf)
         L = C.CDLL(path)
         dbl = C.c_double
@@ -90,10 +101,12 @@ def lib(perf=False):
         L.oracle_calphad_diffusion_mobility.argtypes = [pdb, C.c_int, dbl, dbl]
         # block preconditioners (precond.cc)
         vp, pvp, ci = C.c_void_p, C.POINTER(C.c_void_p), C.c_int
-        L.oracle_set_preconditioner.argtypes = [vp, ci]
+        L.oracle_set_preconditioner.argtypes = [vp, ci, ci]
+        L.oracle_precond_dquatdphi.restype = ci
+        L.oracle_precond_dquatdphi.argtypes = [vp, vp, vp]
         L.oracle_precond_stats.argtypes = [vp, vp]
         L.oracle_precond_setup.restype = ci
-        L.oracle_precond_setup.argtypes = [vp, dbl, ci]
+        L.oracle_precond_setup.argtypes = [vp, dbl, ci, ci]
         L.oracle_precond_solve.restype = ci
         L.oracle_precond_solve.argtypes = [vp, C.POINTER(_abi.RhsFields), C.POINTER(_abi.RhsFields)]
         L.oracle_precond_apply.restype = ci
@@ -194,18 +207,27 @@ class Oracle:
         return rc, dict(zip(names, st.tolist()))
 
     # ---- block preconditioners (precond.cc) ----
-    def set_preconditioner(self, ncycles):
-        """ncycles > 0: integrate_implicit runs right-preconditioned GMRES (CVSpgmrPrecondSet / Solve)"""
-        self.L.oracle_set_preconditioner(self.h, int(ncycles))
+    def set_preconditioner(self, ncycles, dquatdphi=False):
+        """ncycles > 0: integrate_implicit runs right-preconditioned GMRES (CVSpgmrPrecondSet / Solve);
+        dquatdphi: with the lower-triangular dquat/dphi coupling block (precond_has_dquatdphi)"""
+        self.L.oracle_set_preconditioner(self.h, int(ncycles), 1 if dquatdphi else 0)
 
     def precond_stats(self):
         out = np.zeros(2)
         self.L.oracle_precond_stats(self.h, _ptr(out))
         return {"precond_setups": out[0], "precond_solves": out[1]}
 
-    def precond_setup(self, gamma, ncycles=2):
+    def precond_setup(self, gamma, ncycles=2, dquatdphi=False):
         """coefficients frozen at the state of the last fd_flag = 0 eval (CVSpgmrPrecondSet)"""
-        return self.L.oracle_precond_setup(self.h, float(gamma), int(ncycles))
+        return self.L.oracle_precond_setup(self.h, float(gamma), int(ncycles), 1 if dquatdphi else 0)
+
+    def precond_dquatdphi(self, z_phase):
+        """QuatFACOps::multiplyDQuatDPhiBlock: [dF_q/dphi] z_phase, shape (qlen, ...)"""
+        z = np.ascontiguousarray(z_phase, dtype=np.float64)
+        out = np.zeros((self.cfg.qlen,) + z.shape[-3:] if z.ndim >= 3 else (self.cfg.qlen, z.size))
+        if self.L.oracle_precond_dquatdphi(self.h, _ptr(z), _ptr(out)) != 0:
+            raise RuntimeError("oracle_precond_dquatdphi: block not set up")
+        return out
 
     def precond_solve(self, r, z=None):
         if z is None:

@@ -126,7 +126,7 @@ class OracleOps
    }
    // CVSpgmrPrecondSet / CVSpgmrPrecondSolve (QuatIntegrator.cc:3300-3376, 3666-3771), precond.cc
    bool preconditioned() const { return d_c->precond_cycles > 0; }
-   int precondSetup(double, const Vec&, double gamma) { return precond_setup(d_c, gamma, d_c->precond_cycles); }
+   int precondSetup(double, const Vec&, double gamma) { return precond_setup(d_c, gamma, d_c->precond_cycles, d_c->precond_dquatdphi); }
    void precondSolve(const Vec& r, Vec& z)
    {
       ampe_rhs_fields fr = fields(r), fz = fields(z);

@@ -209,3 +209,42 @@ def test_preconditioned_trajectory_matches_oracle_backend(name, mult, nsteps):
     o.close()
     h.close()
     h2.close()
+
+
+@pytest.mark.parametrize("name", ["auni2d", "gg3d_hbsm", "auni3d"])
+def test_dquatdphi_block_matches_the_cpu_restatement(name):
+    """QuatFACOps::multiplyDQuatDPhiBlock through the piecewise kernels (QUATMOBILITYDERIV, QUATDIFFUSIONDERIV,
+    COMPUTE_DQUATDPHI_FACE_COEF, COMPUTE_FLUX, ADD_QUAT_OP, MULTICOMPONENT_MULTIPLY) against the restatement,
+    and the coupled CVSpgmrPrecondSolve against the CPU one"""
+    from oracle import pyoracle
+    cfg, st, y, h, rot = _device_context(name)
+    yd = y.like()
+    h.evaluateRHSFunction(0.0, y, yd, 0)
+    h.setupPreconditioners(2, precond_has_dquatdphi=True)
+    gamma = 20 * parity.TRAJ_DT[name]
+    h.CVSpgmrPrecondSet(0.0, y, gamma)
+    yo = {k: (None if v is None else v.numpy().copy()) for k, v in st.items()}
+    o = pyoracle.Oracle(cfg)
+    if cfg.conc_rhs_form in (2, 3):
+        o.set_ref(yo["conc"].ravel().copy(), yo["conc"].ravel().copy())
+    if rot is not None:
+        o.set_rotations(rot)
+    assert o.eval(0.0, yo, fd_flag=0)[0] == 0
+    assert o.precond_setup(gamma, 2, dquatdphi=True) == 0
+    rng = np.random.default_rng(43)
+    z = rng.standard_normal(yo["phase"].shape)
+    ref = o.precond_dquatdphi(z)
+    got = h.multiplyDQuatDPhiBlock(_cuda(z), cfg.qlen).cpu().numpy()
+    assert np.abs(got.reshape(ref.shape) - ref).max() <= 1e-11 * np.abs(ref).max()
+    r = {k: (None if v is None else rng.standard_normal(v.shape)) for k, v in yo.items()}
+    rc, zo = o.precond_solve(r)
+    rd, zd = y.like(), y.like()
+    for k in ("phase", "quat", "conc", "temperature"):
+        if r.get(k) is not None and rd[k] is not None:
+            rd[k].copy_(torch.as_tensor(r[k]))
+    h.CVSpgmrPrecondSolve(rd, zd)
+    torch.cuda.synchronize()
+    for k in _evolved(cfg):
+        assert np.abs(zd[k].cpu().numpy() - zo[k]).max() <= 1e-10 * np.abs(zo[k]).max(), k
+    o.close()
+    h.close()

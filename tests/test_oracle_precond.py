@@ -262,7 +262,10 @@ def _implicit(name, dt, nsteps, precond, **kw):
         o.set_ref(y["conc"].ravel().copy(), y["conc"].ravel().copy())
     if cfg.symmetry_aware:
         o.set_rotations(parity.random_rotations(cfg))
-    o.set_preconditioner(precond)
+    if isinstance(precond, tuple):
+        o.set_preconditioner(precond[0], dquatdphi=precond[1])
+    else:
+        o.set_preconditioner(precond)
     rc, stats = o.integrate_implicit(y, dt, nsteps, **kw)
     stats.update(o.precond_stats())
     o.close()
@@ -289,3 +292,72 @@ def test_preconditioner_cuts_the_krylov_work_and_keeps_the_trajectory(name, mult
         if y0.get(k) is not None:
             scale = max(np.abs(y0[k]).max(), 1e-300)
             assert np.abs(y1[k] - y0[k]).max() < 1e-6 * scale, k
+
+
+# ---- the dquat/dphi coupling block (precond_has_dquatdphi) ----------------------------------------------------
+def _quat_op(d, q, ndim):
+    """-sum_a [d_a(i+1) (q(i+1) - q(i)) - d_a(i) (q(i) - q(i-1))] with d = fc / h^2 on lower faces (periodic):
+    compute_flux + add_quat_op (rhs = rhs - mobility * divergence) without the mobility
+    (2d/quatfacops.m4:173-229, 487-540)"""
+    out = np.zeros_like(q)
+    for a in range(ndim):
+        ax = q.ndim - 1 - a
+        flux = d[a][None] * (q - np.roll(q, 1, axis=ax))
+        out -= np.roll(flux, -1, axis=ax) - flux
+    return out
+
+
+@pytest.mark.parametrize("name", ["auni2d", "gg3d_hbsm", "auni3d"])
+def test_dquatdphi_block_is_the_phase_derivative_of_the_frozen_operator(name):
+    """QuatFACOps::multiplyDQuatDPhiBlock restated from quatmobilityderiv / quatdiffusionderiv /
+    compute_dquatdphi_face_coef against difference quotients of the level solver's own coefficients set up at
+    phi and at phi + eps z:  out = [m'(phi) z] L(fc, q) + sqrt(m) L(fc'[z], q)  (the second term carries
+    sqrt(m), not m: d_sqrt_m_id at QuatFACOps.cc:1953, restated as is)"""
+    rng = np.random.default_rng(41)
+    gamma = 20 * parity.TRAJ_DT[name]
+    cfg, y, o = _context(name)
+    o.precond_setup(gamma, 2, dquatdphi=True)
+    shape = y["phase"].shape
+    z = rng.standard_normal(shape)
+    got = o.precond_dquatdphi(z).reshape((cfg.qlen,) + shape[-3:])
+    mg0 = o.precond_block(1)
+    s0 = mg0.level_array(0, 2)
+    d0 = [mg0.level_array(0, 3 + a) for a in range(cfg.ndim)]
+    eps = 1e-7
+    cfg1, st1 = parity.make_case(name)
+    y1 = {k: (None if v is None else v.numpy().copy()) for k, v in st1.items()}
+    y1["phase"] = y1["phase"] + eps * z
+    o1 = pyoracle.Oracle(cfg1)
+    if cfg1.conc_rhs_form in (2, 3):
+        o1.set_ref(y["conc"].ravel().copy(), y["conc"].ravel().copy())
+    if cfg1.symmetry_aware:
+        o1.set_rotations(parity.random_rotations(cfg1))
+    assert o1.eval(0.0, y1, fd_flag=0)[0] == 0
+    o1.precond_setup(gamma, 2)
+    mg1 = o1.precond_block(1)
+    s1 = mg1.level_array(0, 2)
+    d1 = [mg1.level_array(0, 3 + a) for a in range(cfg.ndim)]
+    q = y["quat"].reshape((cfg.qlen,) + s0.shape)
+    dm = (s1 * s1 - s0 * s0) / eps
+    dfc = [(d1[a] - d0[a]) / eps for a in range(cfg.ndim)]
+    expect = dm[None] * _quat_op(d0, q, cfg.ndim) + s0[None] * _quat_op(dfc, q, cfg.ndim)
+    scale = np.abs(expect).max()
+    assert scale > 0
+    assert np.abs(got.reshape(expect.shape) - expect).max() < 2e-4 * scale
+    o.close()
+    o1.close()
+
+
+@pytest.mark.parametrize("name,mult", [("gg3d_hbsm", 40), ("auni3d", 20)])
+def test_coupled_preconditioner_in_the_integrator(name, mult):
+    """the lower-triangular coupling (z_q sees gamma dF_q/dphi z_phi, QuatIntegrator.cc:3602-3612) keeps the
+    trajectory and does not cost Krylov vectors"""
+    dt = parity.TRAJ_DT[name] * mult
+    kw = dict(order=2, rtol=1e-8, atol=1e-10, max_krylov=30, max_newton=8)
+    cfg, y1, rc1, s1 = _implicit(name, dt, 3, 2, **kw)
+    cfg, y2, rc2, s2 = _implicit(name, dt, 3, (2, True), **kw)
+    assert rc1 == 0 and rc2 == 0, (s1, s2)
+    assert s2["linear_iterations"] <= s1["linear_iterations"] + 2, (s1, s2)
+    for k in ("phase", "quat", "conc"):
+        if y1.get(k) is not None:
+            assert np.abs(y2[k] - y1[k]).max() < 1e-6 * max(np.abs(y1[k]).max(), 1e-300), k
