@@ -248,3 +248,38 @@ def test_dquatdphi_block_matches_the_cpu_restatement(name):
         assert np.abs(zd[k].cpu().numpy() - zo[k]).max() <= 1e-10 * np.abs(zo[k]).max(), k
     o.close()
     h.close()
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_reference_kat_facpoisson_on_the_device(ndim):
+    """tests/testFACPoisson.cc on the device solver (periodic image of the Dirichlet problem, see
+    test_oracle_precond.facpoisson_case): max |computed - exact| < 1e-2"""
+    from ampe_b200.precond import LevelSolver
+    from test_oracle_precond import facpoisson_case
+    n, dx, exact, rhs, nc = facpoisson_case(ndim)
+    g = LevelSolver(n, dx)
+    g.set_elliptic(m_const=1.0, c_const=5.0, d_const=-1.0)
+    z = g.solve(_cuda(rhs), ncycles=10).cpu().numpy()
+    assert np.abs(z - exact).max() < 1.0e-2
+    res = rhs - g.apply(_cuda(z)).cpu().numpy()
+    assert np.linalg.norm(res) < (1e-8 if ndim == 2 else 1e-6) * np.linalg.norm(rhs)
+    g.close()
+
+
+def test_reference_kat_phasefac_on_the_device():
+    """tests/testPhaseFAC.cc on the device: PhaseFACOps::setC kernel + solver, max |computed - exact| < 1e-2"""
+    from ampe_b200.precond import LevelSolver, phasefacops_setc
+    from test_oracle_precond import phasefac_case
+    k = phasefac_case()
+    ny = 8
+    n, dx = (4 * k["nc"], ny), (k["h"], k["h"])
+    tile = lambda a: np.ascontiguousarray(np.tile(a, (1, ny, 1)))
+    exact, rhs, phi = tile(k["exact"]), tile(k["rhs"]), tile(k["phi_coef"])
+    mob = _cuda(np.full(phi.shape, k["mob"]))
+    c = torch.empty(phi.shape, dtype=torch.float64, device="cuda")
+    phasefacops_setc(n, _cuda(phi), 0, mob, 0, k["gamma"], k["w"], "double", c, 0)
+    g = LevelSolver(n, dx)
+    g.set_elliptic(m=mob, ngm=0, c=c, ngc=0, d_const=-k["gamma"] * k["eps"] ** 2)
+    z = g.solve(_cuda(rhs), ncycles=10).cpu().numpy()
+    assert np.abs(z - exact)[0, :, :k["nc"]].max() < 1.0e-2
+    g.close()

@@ -361,3 +361,75 @@ def test_coupled_preconditioner_in_the_integrator(name, mult):
     for k in ("phase", "quat", "conc"):
         if y1.get(k) is not None:
             assert np.abs(y2[k] - y1[k]).max() < 1e-6 * max(np.abs(y1[k]).max(), 1e-300), k
+
+
+# ---- the reference's own solver tests, mapped onto periodic domains by reflection ----------------------------
+def facpoisson_case(ndim):
+    """tests/testFACPoisson.cc (FACPoisson.cc:230-231 D = -1, C = 5; setexactandrhs{2,3}d, hyprepoisson.m4:40-75):
+    exact = 1 + prod sin(pi x_a) on [0,1]^ndim with value 1 on every boundary, 32^2 / 16^3 cells.  (u - 1) is odd
+    about every boundary face, so the periodic problem on [0,2]^ndim with twice the cells has the same discrete
+    equations: SAMRAI's Dirichlet ghost value 2 - u_interior IS the periodic image."""
+    nc = 32 if ndim == 2 else 16
+    h = 1.0 / nc
+    pi = 3.141592654  # the reference's literal
+    x = (np.arange(2 * nc) + 0.5) * h
+    grids = np.meshgrid(*([x] * ndim), indexing="ij")  # axis order irrelevant: symmetric in the coordinates
+    sinsin = np.ones_like(grids[0])
+    for g in grids:
+        sinsin = sinsin * np.sin(pi * g)
+    exact = 1.0 + sinsin
+    rhs = 5.0 * exact + ndim * pi * pi * sinsin
+    shape = (1,) + exact.shape if ndim == 2 else exact.shape
+    return [2 * nc] * ndim, [h] * ndim, exact.reshape(shape), rhs.reshape(shape), nc
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_reference_kat_facpoisson(ndim):
+    """acceptance of testFACPoisson.cc:274: max |computed - exact| < 1e-2 after at most 10 cycles"""
+    n, dx, exact, rhs, nc = facpoisson_case(ndim)
+    mg = pyoracle.HostMG(n, dx)
+    mg.set_elliptic(m_const=1.0, c_const=5.0, d_const=-1.0)
+    z = mg.solve(rhs, ncycles=10)
+    sub = (slice(0, nc if ndim == 3 else 1),) + (slice(0, nc),) * 2
+    assert np.abs(z - exact)[sub].max() < 1.0e-2
+    assert np.abs(z - exact).max() < (3e-3 if ndim == 2 else 1.2e-2)  # second-order discretisation error
+    ones = np.ones_like(rhs)
+    side = [np.full(tuple(s + (1 if ax == 2 - a else 0) for ax, s in enumerate(rhs.shape)), -1.0) for a in range(ndim)]
+    res = rhs - pyoracle.elliptic_apply(n, dx, ones, 0, 5.0 * ones, 0, side, z)
+    # fac_solver.residual_tol = 1e-8 within max_cycles = 10 (FACPoisson/2d.input); 3D contracts by ~0.2 per cycle
+    assert np.linalg.norm(res) < (1e-8 if ndim == 2 else 1e-6) * np.linalg.norm(rhs)
+
+
+def phasefac_case():
+    """tests/testPhaseFAC.cc:183-192 + PhaseFAC/2d.input: epsilon 0.1, well scale 0.1, mobility 10, gamma 0.1,
+    delta = epsilon / sqrt(32 w); exact = (1 + tanh(x / 2 delta)) / 2 on x in [-1,1] (32 cells), value 0 at x_lo,
+    slope 0 at x_up, periodic in y; rhs from phasesetexactandrhs2d (2d/phase.m4:5-49).  Odd reflection about
+    x = -1 and even reflection about x = +1 give a period of 8 (128 cells); the coefficient C(phi_exact) is a
+    given field and is reflected evenly."""
+    eps, w, mob, gamma = 0.1, 0.1, 10.0, 0.1
+    delta = eps / np.sqrt(32.0 * w)
+    nc, h = 32, 2.0 / 32
+    x = -1.0 + h * (np.arange(nc) + 0.5)
+    t = 0.5 * (1.0 + np.tanh(0.5 / delta * x))
+    f1 = 32.0 * gamma * mob * w
+    rhs = -f1 * t * (1.0 - t) * (1.0 - 2.0 * t) + t + f1 * (1.0 + 6.0 * t * (t - 1.0)) * t
+    even = lambda a: np.concatenate([a, a[::-1]])            # [-1,1] -> [-1,3]: even about +1
+    full = lambda a, s: np.concatenate([even(a), s * even(a)[::-1]])  # -> [-1,7]: odd (s=-1) / even (s=+1) about -1 == 7
+    phi_coef = full(t, +1.0)
+    return dict(eps=eps, w=w, mob=mob, gamma=gamma, nc=nc, h=h, exact=full(t, -1.0), rhs=full(rhs, -1.0),
+                phi_coef=phi_coef)
+
+
+def test_reference_kat_phasefac():
+    """acceptance of testPhaseFAC.cc:60: max |computed - exact| < 1e-2 (the interface is one cell wide)"""
+    k = phasefac_case()
+    ny = 8
+    n, dx = (4 * k["nc"], ny), (k["h"], k["h"])
+    tile = lambda a: np.ascontiguousarray(np.tile(a, (1, ny, 1)))
+    exact, rhs, phi = tile(k["exact"]), tile(k["rhs"]), tile(k["phi_coef"])
+    c = 1.0 + k["gamma"] * k["mob"] * k["w"] * 32.0 * (1.0 + 6.0 * phi * (phi - 1.0))  # PhaseFACOps::setC
+    mg = pyoracle.HostMG(n, dx)
+    mg.set_elliptic(m_const=k["mob"], c=c, ngc=0, d_const=-k["gamma"] * k["eps"] ** 2)
+    z = mg.solve(rhs, ncycles=10)
+    err = np.abs(z - exact)[0, :, :k["nc"]].max()
+    assert err < 1.0e-2, err
