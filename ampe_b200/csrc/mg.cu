@@ -19,6 +19,7 @@
 // (5 + ND) * 8 bytes per updated cell before cache reuse of the neighbours).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -46,6 +47,13 @@ struct ampe_mg {
    std::vector<char> two_colour; // level can be red-black coloured (all extents even)
    int pre = 1, post = 1, coarse = 8;
    int launches = 0;
+   int tail_level = -1;  // first level handled by the one-block tail kernel (-1: none)
+   // AMPE_B200_MG_GRAPH=1 (opt-in): the launches of one solve captured once per (rhs, soln, cycles, form)
+   bool use_graph = false;
+   cudaGraphExec_t graph_exec = nullptr;
+   const double* graph_rhs = nullptr;
+   double* graph_soln = nullptr;
+   int graph_cycles = 0, graph_symm = 0, graph_launches = 0;
 };
 
 namespace {
@@ -212,6 +220,90 @@ __global__ void phasefacops_setc_kernel(Level L, const double* phi, int ngphi, c
    }
 }
 
+// ---- the coarse tail of a V-cycle in ONE block ------------------------------------------------
+// Below TAIL_CELLS cells a level is pure launch latency (7 launches of a few microseconds per level,
+// 5-6 such levels below 64^2 / 16^3).  One block of 1024 threads walks all of them -- descent,
+// coarsest-level sweeps, ascent -- on the same global arrays (L2 resident) with __syncthreads()
+// between the phases; same per-cell functions, same order of phases, so the result is the one of
+// the per-level launches bit for bit.
+constexpr int TAIL_MAX_LEVELS = 8;
+constexpr long long TAIL_CELLS = 4096;
+constexpr int TAIL_THREADS = 1024;
+struct TailLevels {
+   Level L[TAIL_MAX_LEVELS];
+   int two_colour[TAIL_MAX_LEVELS];
+   int n;
+};
+
+__device__ void tail_smooth(const Level& L, int two_colour, int sweeps)
+{
+   const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+   for (int s = 0; s < sweeps; s++) {
+      if (two_colour) {
+         const int h0 = L.n[0] >> 1;
+         const long long half = (long long)h0 * L.n[1] * L.n[2];
+         for (int colour = 0; colour < 2; colour++) {
+            for (long long idx = threadIdx.x; idx < half; idx += blockDim.x) {
+               const int ii = (int)(idx % h0);
+               const long long t = idx / h0;
+               const int j = (int)(t % L.n[1]);
+               const int k = (int)(t / L.n[1]);
+               mg_smooth_cell(L, 2 * ii + ((j + k + colour) & 1), j, k);
+            }
+            __syncthreads();
+         }
+      } else {
+         for (long long idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            int i, j, k;
+            decode(L, idx, i, j, k);
+            mg_residual_cell(L, i, j, k);
+         }
+         __syncthreads();
+         for (long long idx = threadIdx.x; idx < total; idx += blockDim.x) {
+            int i, j, k;
+            decode(L, idx, i, j, k);
+            mg_jacobi_cell(L, JACOBI_OMEGA, i, j, k);
+         }
+         __syncthreads();
+      }
+   }
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS) mg_tail_kernel(TailLevels T, int pre, int post, int coarse)
+{
+   for (int l = 0; l + 1 < T.n; l++) {
+      const Level& F = T.L[l];
+      const Level& C = T.L[l + 1];
+      tail_smooth(F, T.two_colour[l], pre);
+      const long long nf = (long long)F.n[0] * F.n[1] * F.n[2], nc = (long long)C.n[0] * C.n[1] * C.n[2];
+      for (long long idx = threadIdx.x; idx < nf; idx += blockDim.x) {
+         int i, j, k;
+         decode(F, idx, i, j, k);
+         mg_residual_cell(F, i, j, k);
+      }
+      __syncthreads();
+      for (long long idx = threadIdx.x; idx < nc; idx += blockDim.x) {
+         int i, j, k;
+         decode(C, idx, i, j, k);
+         mg_restrict_cell(F, C, i, j, k);
+      }
+      __syncthreads();
+   }
+   tail_smooth(T.L[T.n - 1], T.two_colour[T.n - 1], coarse);
+   for (int l = T.n - 2; l >= 0; l--) {
+      const Level& F = T.L[l];
+      const Level& C = T.L[l + 1];
+      const long long nf = (long long)F.n[0] * F.n[1] * F.n[2];
+      for (long long idx = threadIdx.x; idx < nf; idx += blockDim.x) {
+         int i, j, k;
+         decode(F, idx, i, j, k);
+         mg_prolong_cell(C, F, i, j, k);
+      }
+      __syncthreads();
+      tail_smooth(F, T.two_colour[l], post);
+   }
+}
+
 void smooth(ampe_mg* g, int l, int sweeps, cudaStream_t st)
 {
    const Level& L = g->levels[l];
@@ -231,14 +323,27 @@ void smooth(ampe_mg* g, int l, int sweeps, cudaStream_t st)
 void vcycle(ampe_mg* g, cudaStream_t st)
 {
    const int nl = (int)g->levels.size();
-   for (int l = 0; l + 1 < nl; l++) {
+   // levels [0, top) one launch per phase; levels [top, nl) inside the one-block tail kernel
+   const int top = (g->tail_level >= 0) ? g->tail_level : nl - 1;
+   for (int l = 0; l < top; l++) {
       smooth(g, l, g->pre, st);
       mg_residual_kernel<<<grid_for(cells(g->levels[l])), MT, 0, st>>>(g->levels[l]);
       mg_restrict_kernel<<<grid_for(cells(g->levels[l + 1])), MT, 0, st>>>(g->levels[l], g->levels[l + 1]);
       g->launches += 2;
    }
-   smooth(g, nl - 1, g->coarse, st);
-   for (int l = nl - 2; l >= 0; l--) {
+   if (g->tail_level >= 0) {
+      TailLevels T;
+      T.n = nl - top;
+      for (int l = top; l < nl; l++) {
+         T.L[l - top] = g->levels[l];
+         T.two_colour[l - top] = g->two_colour[l];
+      }
+      mg_tail_kernel<<<1, TAIL_THREADS, 0, st>>>(T, g->pre, g->post, g->coarse);
+      g->launches += 1;
+   } else {
+      smooth(g, nl - 1, g->coarse, st);
+   }
+   for (int l = top - 1; l >= 0; l--) {
       mg_prolong_kernel<<<grid_for(cells(g->levels[l])), MT, 0, st>>>(g->levels[l + 1], g->levels[l]);
       g->launches += 1;
       smooth(g, l, g->post, st);
@@ -311,6 +416,18 @@ int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_sca
       if (!can) break;
       for (int d = 0; d < ndim; d++) cur[d] /= 2;
    }
+   // the coarse tail: every level from the first one with <= TAIL_CELLS cells on (AMPE_B200_MG_TAIL=0: off)
+   const char* tail_env = getenv("AMPE_B200_MG_TAIL");
+   if (!(tail_env && tail_env[0] == '0')) {
+      const int nl = (int)g->levels.size();
+      for (int l = 0; l < nl; l++)
+         if (cells(g->levels[l]) <= TAIL_CELLS && nl - l <= TAIL_MAX_LEVELS) {
+            g->tail_level = l;
+            break;
+         }
+   }
+   const char* graph_env = getenv("AMPE_B200_MG_GRAPH");
+   g->use_graph = graph_env && graph_env[0] == '1';
    *out = g;
    return AMPE_OK;
 }
@@ -318,6 +435,7 @@ int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_sca
 int ampe_mg_destroy(ampe_mg* g)
 {
    if (!g) return AMPE_OK;
+   if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec);
    for (double* b : g->blocks) cudaFree(b);
    delete g;
    return AMPE_OK;
@@ -405,12 +523,35 @@ int ampe_mg_solve(ampe_mg* g, const double* rhs, double* soln, int ncycles, int 
    if (!g || !rhs || !soln || ncycles < 1) return ampe_set_err(AMPE_EINVAL, "ampe_mg_solve: bad argument");
    if (!g->coefficients_set) return ampe_set_err(AMPE_EINVAL, "ampe_mg_solve: operator coefficients not set");
    cudaStream_t st = (cudaStream_t)stream;
-   g->launches = 0;
    const Level& L = g->levels[0];
-   mg_load_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, rhs, symmetrized);
-   for (int c = 0; c < ncycles; c++) vcycle(g, st);
-   mg_store_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, soln, symmetrized);
-   g->launches += 2;
+   auto issue = [&](cudaStream_t s) {
+      g->launches = 0;
+      mg_load_kernel<<<grid_for(cells(L)), MT, 0, s>>>(L, rhs, symmetrized);
+      for (int c = 0; c < ncycles; c++) vcycle(g, s);
+      mg_store_kernel<<<grid_for(cells(L)), MT, 0, s>>>(L, soln, symmetrized);
+      g->launches += 2;
+   };
+   if (g->use_graph && st != nullptr) {
+      // the kernels only read the coefficient arrays through fixed pointers, so a captured solve stays
+      // valid across ampe_mg_set_*; it is re-captured when the vectors or the cycle count change
+      const bool hit = g->graph_exec && g->graph_rhs == rhs && g->graph_soln == soln &&
+                       g->graph_cycles == ncycles && g->graph_symm == symmetrized;
+      if (!hit) {
+         if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec), g->graph_exec = nullptr;
+         cudaGraph_t graph = nullptr;
+         CUDA_OKM(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+         issue(st);
+         CUDA_OKM(cudaStreamEndCapture(st, &graph));
+         CUDA_OKM(cudaGraphInstantiate(&g->graph_exec, graph, 0));
+         cudaGraphDestroy(graph);
+         g->graph_rhs = rhs, g->graph_soln = soln, g->graph_cycles = ncycles, g->graph_symm = symmetrized;
+         g->graph_launches = g->launches;
+      }
+      CUDA_OKM(cudaGraphLaunch(g->graph_exec, st));
+      g->launches = g->graph_launches;
+      return AMPE_OK;
+   }
+   issue(st);
    CUDA_OKM(cudaGetLastError());
    return AMPE_OK;
 }

@@ -62,10 +62,12 @@ class LevelSolver:
         check(self.L.ampe_mg_set_quat(self.h, gamma, _p(mobility), ngm, _ptrs(face_coef), ngfc, None),
               "ampe_mg_set_quat")
 
-    def solve(self, rhs, ncycles=2, symmetrized=False, out=None):
+    def solve(self, rhs, ncycles=2, symmetrized=False, out=None, stream=None):
+        """stream: a torch.cuda.Stream (None = the legacy default stream; AMPE_B200_MG_GRAPH=1 needs a real one)"""
         out = torch.empty_like(rhs) if out is None else out
+        st = None if stream is None else C.c_void_p(stream.cuda_stream)
         check(self.L.ampe_mg_solve(self.h, rhs.data_ptr(), out.data_ptr(), int(ncycles), 1 if symmetrized else 0,
-                                   None), "ampe_mg_solve")
+                                   st), "ampe_mg_solve")
         return out
 
     def apply(self, u):

@@ -283,3 +283,43 @@ def test_reference_kat_phasefac_on_the_device():
     z = g.solve(_cuda(rhs), ncycles=10).cpu().numpy()
     assert np.abs(z - exact)[0, :, :k["nc"]].max() < 1.0e-2
     g.close()
+
+
+@pytest.mark.parametrize("n,dx", [((256, 192), (1.0, 1.0)), ((64, 32, 48), (1.0, 1.0, 1.0)), ((48, 40), (1.0, 0.5))])
+def test_one_block_tail_and_graph_replay_are_bit_identical(n, dx):
+    """the coarse levels inside one block (default) == one launch per phase (AMPE_B200_MG_TAIL=0), bit for bit,
+    with fewer launches; the captured solve (AMPE_B200_MG_GRAPH=1, explicit stream) replays to the same bits"""
+    from ampe_b200.precond import LevelSolver
+    shape, m, c, lows, d = _random_elliptic(n, 17)
+    d = [30.0 * x for x in d]
+    rhs = _cuda(np.random.default_rng(18).standard_normal(shape))
+    outs, launches = {}, {}
+    for mode, env in (("tail", {}), ("levels", {"AMPE_B200_MG_TAIL": "0"}), ("graph", {"AMPE_B200_MG_GRAPH": "1"})):
+        old = {k: os.environ.get(k) for k in ("AMPE_B200_MG_TAIL", "AMPE_B200_MG_GRAPH")}
+        for k in old:
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        try:
+            g = LevelSolver(n, dx)  # the switches are read when the solver is created
+        finally:
+            for k, v in old.items():
+                os.environ.pop(k, None)
+                if v is not None:
+                    os.environ[k] = v
+        g.set_elliptic(m=_cuda(m), ngm=0, c=_cuda(c), ngc=0, d=[_cuda(x) for x in d], ngd=0)
+        stream = torch.cuda.Stream() if mode == "graph" else None
+        if stream is not None:
+            stream.wait_stream(torch.cuda.current_stream())
+        z = g.solve(rhs, ncycles=3, stream=stream)
+        if mode == "graph":
+            z2 = torch.empty_like(z)
+            z2.copy_(z)
+            g.solve(rhs, ncycles=3, out=z, stream=stream)  # second call: replay
+            stream.synchronize()
+            assert torch.equal(z, z2)
+        torch.cuda.synchronize()
+        outs[mode], launches[mode] = z.clone(), g.last_launch_count()
+        g.close()
+    assert torch.equal(outs["tail"], outs["levels"])
+    assert torch.equal(outs["tail"], outs["graph"])
+    assert launches["tail"] < launches["levels"]

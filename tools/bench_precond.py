@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--cases", default="2d:2048x2048,2d:4096x4096,3d:256x256x256,3d:512x512x512")
     ap.add_argument("--cycles", type=int, default=10)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--stream", action="store_true", help="launch on a non-default stream (needed by AMPE_B200_MG_GRAPH=1)")
     a = ap.parse_args()
     hbm, src = peak()
     for case in a.cases.split(","):
@@ -50,15 +51,17 @@ def main():
         g.set_elliptic(m_const=1.0, c_const=1.0, d=sides, ngd=0)
         rhs = torch.randn(shape, dtype=torch.float64, device="cuda")
         out = torch.empty_like(rhs)
+        stream = torch.cuda.Stream() if a.stream else None
         g.solve(rhs, ncycles=2, out=out)
         torch.cuda.synchronize()
         res0 = float((rhs - g.apply(out)).norm() / rhs.norm())
         best = None
         for _ in range(a.reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()  # the library launches on the legacy default stream (stream = NULL), as torch does
-            g.solve(rhs, ncycles=a.cycles, out=out)
-            e1.record()
+            # the library launches on the legacy default stream (stream = NULL), as torch does, unless --stream
+            e0.record(stream)
+            g.solve(rhs, ncycles=a.cycles, out=out, stream=stream)
+            e1.record(stream)
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
             best = ms if best is None else min(best, ms)
@@ -70,7 +73,8 @@ def main():
         print(json.dumps({"case": case, "levels": g.num_levels(), "ms_per_vcycle": per_cycle,
                           "launches_per_solve": launches, "algorithmic_bytes_per_vcycle": bytes_cycle,
                           "achieved_gbs": gbs, "hbm_peak_gbs": hbm, "peak_source": src, "frac": gbs / hbm,
-                          "rel_residual_after_2_cycles": res0, "cells": ncell}))
+                          "rel_residual_after_2_cycles": res0, "cells": ncell,
+                          "tail": os.environ.get("AMPE_B200_MG_TAIL", "1"), "graph": os.environ.get("AMPE_B200_MG_GRAPH", "0")}))
         g.close()
 
 

@@ -6,6 +6,8 @@ AMPE_B200_RUN_EXPERIMENTS=1 timeout -k 5 400 python -m pytest tests/test_gpu_wid
   > gpurun_out/pytest_precond.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_precond.log
 tail -15 gpurun_out/pytest_precond.log
 timeout -k 5 300 python tools/bench_precond.py > gpurun_out/bench_precond.jsonl 2> gpurun_out/bench_precond.err
+AMPE_B200_MG_TAIL=0 timeout -k 5 300 python tools/bench_precond.py >> gpurun_out/bench_precond.jsonl 2>> gpurun_out/bench_precond.err
+AMPE_B200_MG_GRAPH=1 timeout -k 5 300 python tools/bench_precond.py --stream >> gpurun_out/bench_precond.jsonl 2>> gpurun_out/bench_precond.err
 cat gpurun_out/bench_precond.jsonl; tail -3 gpurun_out/bench_precond.err
 timeout -k 5 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_precond.csv \
   python tools/bench_precond.py --cases 2d:2048x2048 --cycles 2 --reps 1 > gpurun_out/ncu_launch_precond.log 2>&1
