@@ -16,7 +16,8 @@
 // of cycles from a zero initial guess makes the solve a fixed linear operator, which is what right-
 // preconditioned GMRES needs, and needs no host synchronisation.
 // All kernels are HBM-bound sweeps (a half sweep reads u, f, c, m, the ND face arrays and writes u:
-// (5 + ND) * 8 bytes per updated cell before cache reuse of the neighbours).
+// (5 + ND) * 8 bytes per updated cell before cache reuse of the neighbours, less where a coefficient is a
+// constant of the block: constants are not stored -- phase 4, temperature 3, composition 3 + ND arrays).
 #include <cuda_runtime.h>
 
 #include <cstdlib>
@@ -43,7 +44,11 @@ struct ampe_mg {
    bool with_s = false;          // quaternion block: column multiplier present
    bool coefficients_set = false;
    std::vector<Level> levels;
-   std::vector<double*> blocks;  // one allocation per level
+   std::vector<double*> blocks;  // work arrays u, f, r (and s): one allocation per level
+   // coefficient arrays, allocated the first time a set_* call needs them as ARRAYS; a coefficient that is
+   // a constant of the block stays unallocated (null pointer in the Level, value in *_const)
+   std::vector<double*> own_c, own_m;
+   std::vector<double*> own_d[3];
    std::vector<char> two_colour; // level can be red-black coloured (all extents even)
    int pre = 1, post = 1, coarse = 8;
    int launches = 0;
@@ -176,9 +181,8 @@ __global__ void mg_store_kernel(Level L, double* soln, int symmetrized)
         idx += (long long)gridDim.x * blockDim.x)
       soln[idx] = (symmetrized && L.s) ? L.u[idx] * L.s[idx] : L.u[idx];
 }
-__global__ void mg_set_elliptic_kernel(Level L, const double* m, int ngm, double m_const, const double* c,
-                                       int ngc, double c_const, P3 d, P3 d2, int have_d, int have_d2, int ngd,
-                                       double d_scale, double d_const, double ih0, double ih1, double ih2)
+__global__ void mg_set_elliptic_kernel(Level L, const double* m, int ngm, const double* c, int ngc, P3 d, P3 d2,
+                                       int have_d2, int ngd, double d_scale, double ih0, double ih1, double ih2)
 {
    const double inv_h2[3] = {ih0, ih1, ih2};
    const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
@@ -186,8 +190,7 @@ __global__ void mg_set_elliptic_kernel(Level L, const double* m, int ngm, double
         idx += (long long)gridDim.x * blockDim.x) {
       int i, j, k;
       decode(L, idx, i, j, k);
-      mg_set_elliptic_cell(L, m, ngm, m_const, c, ngc, c_const, have_d ? d.a : nullptr,
-                           have_d2 ? d2.a : nullptr, ngd, d_scale, d_const, inv_h2, i, j, k);
+      mg_set_elliptic_cell(L, m, ngm, c, ngc, d.a, have_d2 ? d2.a : nullptr, ngd, d_scale, inv_h2, i, j, k);
    }
 }
 __global__ void mg_set_quat_kernel(Level L, double gamma, const double* mobility, int ngm, P3 fc, int ngfc,
@@ -350,6 +353,45 @@ void vcycle(ampe_mg* g, cudaStream_t st)
    }
 }
 
+// which coefficients of the block are arrays, which are constants: pointers and constants of every level
+// (a constant C or M is the same on every level; a constant D / h^2 is divided by 4 per level, exactly
+// what averaging an array of identical values gives)
+int configure(ampe_mg* g, bool var_c, double c_const, bool var_m, double m_const, bool var_d, double d_const)
+{
+   // a captured solve carries the level descriptors (pointers AND constants) as kernel arguments
+   if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec), g->graph_exec = nullptr;
+   const size_t nl = g->levels.size();
+   auto ensure = [&](std::vector<double*>& own, size_t l) -> cudaError_t {
+      if (own.size() < nl) own.resize(nl, nullptr);
+      if (own[l]) return cudaSuccess;
+      return cudaMalloc(&own[l], sizeof(double) * cells(g->levels[l]));
+   };
+   double scale = 1.0;
+   for (size_t l = 0; l < nl; l++) {
+      Level& L = g->levels[l];
+      L.c = nullptr, L.m = nullptr;
+      L.c_const = c_const, L.m_const = m_const;
+      if (var_c) {
+         CUDA_OKM(ensure(g->own_c, l));
+         L.c = g->own_c[l];
+      }
+      if (var_m) {
+         CUDA_OKM(ensure(g->own_m, l));
+         L.m = g->own_m[l];
+      }
+      for (int a = 0; a < 3; a++) {
+         L.d[a] = nullptr;
+         L.d_const[a] = a < g->ndim ? d_const * g->inv_h2[a] * scale : 0.0;
+         if (var_d && a < g->ndim) {
+            CUDA_OKM(ensure(g->own_d[a], l));
+            L.d[a] = g->own_d[a][l];
+         }
+      }
+      scale *= 0.25;
+   }
+   return AMPE_OK;
+}
+
 int build_coarse(ampe_mg* g, cudaStream_t st)
 {
    for (size_t l = 0; l + 1 < g->levels.size(); l++) {
@@ -387,7 +429,7 @@ int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_sca
       L.ndim = ndim;
       for (int d = 0; d < 3; d++) L.n[d] = cur[d];
       const long long nc = (long long)cur[0] * cur[1] * cur[2];
-      const int narr = 2 + (g->with_s ? 1 : 0) + ndim + 3;
+      const int narr = (g->with_s ? 1 : 0) + 3;
       double* blk = nullptr;
       cudaError_t e = cudaMalloc(&blk, sizeof(double) * nc * narr);
       if (e != cudaSuccess) {
@@ -398,12 +440,10 @@ int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_sca
       cudaMemset(blk, 0, sizeof(double) * nc * narr);
       g->blocks.push_back(blk);
       double* p = blk;
-      L.c = p, p += nc;
-      L.m = p, p += nc;
-      L.s = nullptr;
+      L.c = L.m = L.s = nullptr;
+      L.c_const = 1.0, L.m_const = 1.0;
       if (g->with_s) L.s = p, p += nc;
-      for (int d = 0; d < 3; d++) L.d[d] = nullptr;
-      for (int d = 0; d < ndim; d++) L.d[d] = p, p += nc;
+      for (int d = 0; d < 3; d++) L.d[d] = nullptr, L.d_const[d] = 0.0;
       L.u = p, p += nc;
       L.f = p, p += nc;
       L.r = p, p += nc;
@@ -437,6 +477,10 @@ int ampe_mg_destroy(ampe_mg* g)
    if (!g) return AMPE_OK;
    if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec);
    for (double* b : g->blocks) cudaFree(b);
+   for (double* b : g->own_c) cudaFree(b);
+   for (double* b : g->own_m) cudaFree(b);
+   for (int a = 0; a < 3; a++)
+      for (double* b : g->own_d[a]) cudaFree(b);
    delete g;
    return AMPE_OK;
 }
@@ -466,7 +510,15 @@ int ampe_mg_copy_level(ampe_mg* g, int level, int which, double* out, void* stre
       return ampe_set_err(AMPE_EINVAL, "ampe_mg_copy_level: bad argument");
    const Level& L = g->levels[level];
    const double* src = which == 0 ? L.c : which == 1 ? L.m : which == 2 ? L.s : L.d[which - 3];
-   if (!src) return ampe_set_err(AMPE_EINVAL, "ampe_mg_copy_level: this operator has no such array");
+   if (!src) {
+      // a constant of the block: fill the caller's array with it
+      if (which == 2) return ampe_set_err(AMPE_EINVAL, "ampe_mg_copy_level: this operator has no column scale");
+      if (which >= 3 && which - 3 >= g->ndim) return ampe_set_err(AMPE_EINVAL, "ampe_mg_copy_level: no such direction");
+      const double v = which == 0 ? L.c_const : which == 1 ? L.m_const : L.d_const[which - 3];
+      std::vector<double> h((size_t)cells(L), v);
+      CUDA_OKM(cudaMemcpy(out, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice));
+      return AMPE_OK;
+   }
    CUDA_OKM(cudaMemcpyAsync(out, src, sizeof(double) * cells(L), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
    return AMPE_OK;
 }
@@ -491,12 +543,17 @@ int ampe_mg_set_elliptic(ampe_mg* g, const double* m, int ngm, double m_const, c
    }
    cudaStream_t st = (cudaStream_t)stream;
    g->launches = 0;
-   const Level& L = g->levels[0];
-   mg_set_elliptic_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, m, ngm, m_const, c, ngc, c_const, p, p2, d ? 1 : 0,
-                                                             d2 ? 1 : 0, ngd, d_scale, d_const, g->inv_h2[0],
-                                                             g->inv_h2[1], g->inv_h2[2]);
-   g->launches += 1;
-   return build_coarse(g, st);
+   int rc = configure(g, c != nullptr, c_const, m != nullptr, m_const, d != nullptr, d_const);
+   if (rc) return rc;
+   if (m || c || d) {
+      const Level& L = g->levels[0];
+      mg_set_elliptic_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, m, ngm, c, ngc, p, p2, d2 ? 1 : 0, ngd, d_scale,
+                                                                g->inv_h2[0], g->inv_h2[1], g->inv_h2[2]);
+      g->launches += 1;
+      return build_coarse(g, st);
+   }
+   g->coefficients_set = true;  // every coefficient is a constant: nothing to compute on the device
+   return AMPE_OK;
 }
 
 int ampe_mg_set_quat(ampe_mg* g, double gamma, const double* mobility, int ngm, const double* const* face_coef,
@@ -511,6 +568,8 @@ int ampe_mg_set_quat(ampe_mg* g, double gamma, const double* mobility, int ngm, 
    }
    cudaStream_t st = (cudaStream_t)stream;
    g->launches = 0;
+   int rc = configure(g, false, 1.0, true, 0.0, true, 0.0);
+   if (rc) return rc;
    const Level& L = g->levels[0];
    mg_set_quat_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, gamma, mobility, ngm, p, ngfc, g->inv_h2[0],
                                                          g->inv_h2[1], g->inv_h2[2]);
@@ -532,8 +591,7 @@ int ampe_mg_solve(ampe_mg* g, const double* rhs, double* soln, int ncycles, int 
       g->launches += 2;
    };
    if (g->use_graph && st != nullptr) {
-      // the kernels only read the coefficient arrays through fixed pointers, so a captured solve stays
-      // valid across ampe_mg_set_*; it is re-captured when the vectors or the cycle count change
+      // re-captured when the vectors, the cycle count or the coefficients (ampe_mg_set_*) change
       const bool hit = g->graph_exec && g->graph_rhs == rhs && g->graph_soln == soln &&
                        g->graph_cycles == ncycles && g->graph_symm == symmetrized;
       if (!hit) {

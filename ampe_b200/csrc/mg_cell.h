@@ -31,17 +31,25 @@
 
 namespace ampe_mg_cell {
 
+// A coefficient that is a constant of the block (phase: M and D; temperature: M, C and D; composition:
+// M and C) is not stored: its pointer is null and the value sits in the level descriptor, so the
+// sweeps do not read arrays of identical numbers from HBM.
 struct Level {
    int ndim;
    int n[3];      // cells per direction (n[2] = 1 in 2D); periodic
-   double* c;     // cell: C
-   double* m;     // cell: row multiplier
+   double* c;     // cell: C, or nullptr (= c_const)
+   double* m;     // cell: row multiplier, or nullptr (= m_const)
    double* s;     // cell: column multiplier, or nullptr (= 1)
-   double* d[3];  // lower-face coefficient per direction, divided by h^2
+   double* d[3];  // lower-face coefficient per direction, divided by h^2, or nullptr (= d_const[a])
    double* u;     // solution / correction
    double* f;     // right-hand side
    double* r;     // residual (and Jacobi work array)
+   double c_const, m_const, d_const[3];
 };
+
+MG_HD double mg_c(const Level& L, long long o) { return L.c ? L.c[o] : L.c_const; }
+MG_HD double mg_m(const Level& L, long long o) { return L.m ? L.m[o] : L.m_const; }
+MG_HD double mg_d(const Level& L, int a, long long o) { return L.d[a] ? L.d[a][o] : L.d_const[a]; }
 
 MG_HD long long mg_index(const Level& L, int i, int j, int k)
 {
@@ -60,21 +68,21 @@ MG_HD void mg_face_sums(const Level& L, const double* u, int i, int j, int k, do
    dsum = 0.0;
    {
       const long long ou = mg_index(L, mg_up(i, L.n[0]), j, k), od = mg_index(L, mg_dn(i, L.n[0]), j, k);
-      const double du = L.d[0][ou], dd = L.d[0][o];
+      const double du = mg_d(L, 0, ou), dd = mg_d(L, 0, o);
       const double uu = (L.s ? L.s[ou] : 1.0) * u[ou], ud = (L.s ? L.s[od] : 1.0) * u[od];
       flux += du * (uu - ui) - dd * (ui - ud);
       dsum += du + dd;
    }
    {
       const long long ou = mg_index(L, i, mg_up(j, L.n[1]), k), od = mg_index(L, i, mg_dn(j, L.n[1]), k);
-      const double du = L.d[1][ou], dd = L.d[1][o];
+      const double du = mg_d(L, 1, ou), dd = mg_d(L, 1, o);
       const double uu = (L.s ? L.s[ou] : 1.0) * u[ou], ud = (L.s ? L.s[od] : 1.0) * u[od];
       flux += du * (uu - ui) - dd * (ui - ud);
       dsum += du + dd;
    }
    if (L.ndim == 3) {
       const long long ou = mg_index(L, i, j, mg_up(k, L.n[2])), od = mg_index(L, i, j, mg_dn(k, L.n[2]));
-      const double du = L.d[2][ou], dd = L.d[2][o];
+      const double du = mg_d(L, 2, ou), dd = mg_d(L, 2, o);
       const double uu = (L.s ? L.s[ou] : 1.0) * u[ou], ud = (L.s ? L.s[od] : 1.0) * u[od];
       flux += du * (uu - ui) - dd * (ui - ud);
       dsum += du + dd;
@@ -87,7 +95,7 @@ MG_HD double mg_apply_cell(const Level& L, const double* u, int i, int j, int k)
    double flux, dsum;
    mg_face_sums(L, u, i, j, k, flux, dsum);
    const long long o = mg_index(L, i, j, k);
-   return L.c[o] * u[o] + L.m[o] * flux;
+   return mg_c(L, o) * u[o] + mg_m(L, o) * flux;
 }
 
 // r_i = f_i - (A u)_i   (efo_compresvarsca2d)
@@ -104,8 +112,8 @@ MG_HD void mg_smooth_cell(const Level& L, int i, int j, int k)
    mg_face_sums(L, L.u, i, j, k, flux, dsum);
    const long long o = mg_index(L, i, j, k);
    const double si = L.s ? L.s[o] : 1.0;
-   const double residual = L.f[o] - (L.c[o] * L.u[o] + L.m[o] * flux);
-   const double diag = L.c[o] - L.m[o] * si * dsum;
+   const double residual = L.f[o] - (mg_c(L, o) * L.u[o] + mg_m(L, o) * flux);
+   const double diag = mg_c(L, o) - mg_m(L, o) * si * dsum;
    L.u[o] += residual / diag;
 }
 
@@ -115,11 +123,11 @@ MG_HD void mg_jacobi_cell(const Level& L, double omega, int i, int j, int k)
 {
    double dsum = 0.0;
    const long long o = mg_index(L, i, j, k);
-   dsum += L.d[0][mg_index(L, mg_up(i, L.n[0]), j, k)] + L.d[0][o];
-   dsum += L.d[1][mg_index(L, i, mg_up(j, L.n[1]), k)] + L.d[1][o];
-   if (L.ndim == 3) dsum += L.d[2][mg_index(L, i, j, mg_up(k, L.n[2]))] + L.d[2][o];
+   dsum += mg_d(L, 0, mg_index(L, mg_up(i, L.n[0]), j, k)) + mg_d(L, 0, o);
+   dsum += mg_d(L, 1, mg_index(L, i, mg_up(j, L.n[1]), k)) + mg_d(L, 1, o);
+   if (L.ndim == 3) dsum += mg_d(L, 2, mg_index(L, i, j, mg_up(k, L.n[2]))) + mg_d(L, 2, o);
    const double si = L.s ? L.s[o] : 1.0;
-   const double diag = L.c[o] - L.m[o] * si * dsum;
+   const double diag = mg_c(L, o) - mg_m(L, o) * si * dsum;
    L.u[o] += omega * L.r[o] / diag;
 }
 
@@ -140,6 +148,7 @@ MG_HD void mg_restrict_cell(const Level& F, const Level& C, int I, int J, int K)
 // direction a is the mean of the fine faces it covers, divided by 4 (h doubles)
 MG_HD void mg_coarsen_cell(const Level& F, const Level& C, int I, int J, int K)
 {
+   // (constants coarsen on the host: c, m unchanged, d / 4; a stored array is stored on every level)
    const int nk = F.ndim == 3 ? 2 : 1;
    const int k0 = F.ndim == 3 ? 2 * K : 0;
    const double wcell = F.ndim == 3 ? 0.125 : 0.25;
@@ -149,22 +158,28 @@ MG_HD void mg_coarsen_cell(const Level& F, const Level& C, int I, int J, int K)
       for (int b = 0; b < 2; b++)
          for (int a = 0; a < 2; a++) {
             const long long of = mg_index(F, 2 * I + a, 2 * J + b, k0 + c);
-            ac += F.c[of];
-            am += F.m[of];
+            if (F.c) ac += F.c[of];
+            if (F.m) am += F.m[of];
             if (F.s) as += F.s[of];
          }
-   C.c[o] = ac * wcell;
-   C.m[o] = am * wcell;
+   if (C.c) C.c[o] = ac * wcell;
+   if (C.m) C.m[o] = am * wcell;
    if (C.s) C.s[o] = as * wcell;
    const double wface = (F.ndim == 3 ? 0.25 : 0.5) * 0.25;
-   double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-   for (int c = 0; c < nk; c++)
-      for (int b = 0; b < 2; b++) a0 += F.d[0][mg_index(F, 2 * I, 2 * J + b, k0 + c)];
-   for (int c = 0; c < nk; c++)
-      for (int a = 0; a < 2; a++) a1 += F.d[1][mg_index(F, 2 * I + a, 2 * J, k0 + c)];
-   C.d[0][o] = a0 * wface;
-   C.d[1][o] = a1 * wface;
-   if (F.ndim == 3) {
+   if (C.d[0]) {
+      double a0 = 0.0;
+      for (int c = 0; c < nk; c++)
+         for (int b = 0; b < 2; b++) a0 += F.d[0][mg_index(F, 2 * I, 2 * J + b, k0 + c)];
+      C.d[0][o] = a0 * wface;
+   }
+   if (C.d[1]) {
+      double a1 = 0.0;
+      for (int c = 0; c < nk; c++)
+         for (int a = 0; a < 2; a++) a1 += F.d[1][mg_index(F, 2 * I + a, 2 * J, k0 + c)];
+      C.d[1][o] = a1 * wface;
+   }
+   if (F.ndim == 3 && C.d[2]) {
+      double a2 = 0.0;
       for (int b = 0; b < 2; b++)
          for (int a = 0; a < 2; a++) a2 += F.d[2][mg_index(F, 2 * I + a, 2 * J + b, k0)];
       C.d[2][o] = a2 * wface;
@@ -203,23 +218,21 @@ MG_HD long long mg_samrai_index(const Level& L, int axis, int ng, int i, int j, 
    return (long long)(i + ng) + n0 * ((long long)(j + ng) + n1 * (long long)(k + g2));
 }
 
-// scalar block (EllipticFACOps::setM / setC / setD*): arrays may be NULL = the constant
-MG_HD void mg_set_elliptic_cell(const Level& L, const double* m, int ngm, double m_const, const double* c,
-                                int ngc, double c_const, const double* const* d, const double* const* d2,
-                                int ngd, double d_scale, double d_const, const double* inv_h2, int i, int j,
-                                int k)
+// scalar block (EllipticFACOps::setM / setC / setD*): a NULL input array = the constant, which the
+// caller has put into the level descriptor (m_const, c_const, d_const) with the array pointer null
+MG_HD void mg_set_elliptic_cell(const Level& L, const double* m, int ngm, const double* c, int ngc,
+                                const double* const* d, const double* const* d2, int ngd, double d_scale,
+                                const double* inv_h2, int i, int j, int k)
 {
    const long long o = mg_index(L, i, j, k);
-   L.m[o] = m ? m[mg_samrai_index(L, -1, ngm, i, j, k)] : m_const;
-   L.c[o] = c ? c[mg_samrai_index(L, -1, ngc, i, j, k)] : c_const;
+   if (L.m) L.m[o] = m[mg_samrai_index(L, -1, ngm, i, j, k)];
+   if (L.c) L.c[o] = c[mg_samrai_index(L, -1, ngc, i, j, k)];
    for (int a = 0; a < L.ndim; a++) {
-      double D = d_const;
-      if (d) {
-         const long long os = mg_samrai_index(L, a, ngd, i, j, k);
-         D = d[a][os];
-         if (d2) D += d2[a][os];
-         D *= d_scale;
-      }
+      if (!L.d[a]) continue;
+      const long long os = mg_samrai_index(L, a, ngd, i, j, k);
+      double D = d[a][os];
+      if (d2) D += d2[a][os];
+      D *= d_scale;
       L.d[a][o] = D * inv_h2[a];
    }
 }
@@ -236,8 +249,7 @@ MG_HD void mg_set_quat_cell(const Level& L, double gamma, const double* mobility
    const double sq = __builtin_sqrt(mobility[mg_samrai_index(L, -1, ngm, i, j, k)]);
 #endif
    L.s[o] = sq;
-   L.m[o] = gamma * sq;
-   L.c[o] = 1.0;
+   L.m[o] = gamma * sq;  // c = 1 is a constant of this block (c_const)
    for (int a = 0; a < L.ndim; a++) L.d[a][o] = face_coef[a][mg_samrai_index(L, a, ngfc, i, j, k)] * inv_h2[a];
 }
 

@@ -339,7 +339,7 @@ class QuatIntegrator
       }
       if (p.with_phase)
          d_phase_sys_solver->setOperatorCoefficients(d_phase_scratch_id, d_phase_mobility_id, p.epsilon_phase, gamma,
-                                                     p.phi_well_scale, "double");
+                                                     p.phi_well_scale, "double", &p.phi_mobility);
       if (p.with_unsteady_temperature)
          d_temperature_sys_solver->setOperatorCoefficients(1., 1., -gamma * p.thermal_diffusivity);
       if (p.with_concentration && kks) {

@@ -1049,10 +1049,16 @@ class PhaseFACSolver : public EllipticFACSolver
 {
  public:
    PhaseFACSolver(std::shared_ptr<PatchHierarchy> h, int c_scratch_id) : EllipticFACSolver(h), d_c_scratch_id(c_scratch_id) {}
+   // uniform_mobility: the mobility field is known to be one number (computeUniformPhaseMobility,
+   // QuatModel.cc:4277-4291): M is then handed over as a constant and not read per cell by the sweeps
    void setOperatorCoefficients(int phase_id, int phase_mobility_id, double epsilon_phase, double gamma,
-                                double phase_well_scale, const std::string& phase_well_func_type)
+                                double phase_well_scale, const std::string& phase_well_func_type,
+                                const double* uniform_mobility = nullptr)
    {
-      setM(phase_mobility_id);
+      if (uniform_mobility)
+         setMConstant(*uniform_mobility);
+      else
+         setM(phase_mobility_id);
       // C to be set after M since it uses M (setC, PhaseFACOps.cc:58-98)
       auto patch = d_h->getPatchLevel(0)->patches.front();
       auto phi = patch->cell<double>(phase_id), m = patch->cell<double>(phase_mobility_id);

@@ -217,8 +217,8 @@ HostMG::HostMG(int ndim, const int* n, const double* dx, bool with_s) : d_ndim(n
    }
    for (int l = 0; l < 16; l++) {
       const size_t nc = (size_t)cur[0] * cur[1] * cur[2];
-      const int narr = 2 + (with_s ? 1 : 0) + ndim + 3;
-      d_store.emplace_back(nc * narr, 0.0);
+      d_store.emplace_back(nc * ((with_s ? 1 : 0) + 3), 0.0);  // s, u, f, r
+      d_coef.emplace_back();                                  // c, m, d0..d2: allocated when stored as arrays
       Level L;
       L.ndim = ndim;
       for (int d = 0; d < 3; d++) L.n[d] = cur[d];
@@ -235,15 +235,37 @@ HostMG::HostMG(int ndim, const int* n, const double* dx, bool with_s) : d_ndim(n
       Level& L = d_levels[l];
       const size_t nc = (size_t)L.n[0] * L.n[1] * L.n[2];
       double* p = d_store[l].data();
-      L.c = p, p += nc;
-      L.m = p, p += nc;
-      L.s = nullptr;
+      L.c = L.m = L.s = nullptr;
+      L.c_const = L.m_const = 1.0;
       if (with_s) L.s = p, p += nc;
-      for (int d = 0; d < 3; d++) L.d[d] = nullptr;
-      for (int d = 0; d < ndim; d++) L.d[d] = p, p += nc;
+      for (int d = 0; d < 3; d++) L.d[d] = nullptr, L.d_const[d] = 0.0;
       L.u = p, p += nc;
       L.f = p, p += nc;
       L.r = p, p += nc;
+   }
+}
+
+// same rule as configure() in ampe_b200/csrc/mg.cu: a coefficient that is a constant of the block is not
+// stored; C and M constants are level independent, a constant D / h^2 is divided by 4 per level
+void HostMG::configure(bool var_c, double c_const, bool var_m, double m_const, bool var_d, double d_const)
+{
+   double scale = 1.0;
+   for (size_t l = 0; l < d_levels.size(); l++) {
+      Level& L = d_levels[l];
+      const size_t nc = (size_t)L.n[0] * L.n[1] * L.n[2];
+      auto& cf = d_coef[l];
+      auto arr = [&](int which) {
+         if (cf[which].size() != nc) cf[which].assign(nc, 0.0);
+         return cf[which].data();
+      };
+      L.c = var_c ? arr(0) : nullptr;
+      L.m = var_m ? arr(1) : nullptr;
+      L.c_const = c_const, L.m_const = m_const;
+      for (int a = 0; a < 3; a++) {
+         L.d[a] = (var_d && a < d_ndim) ? arr(2 + a) : nullptr;
+         L.d_const[a] = a < d_ndim ? d_const * d_inv_h2[a] * scale : 0.0;
+      }
+      scale *= 0.25;
    }
 }
 
@@ -265,16 +287,18 @@ void HostMG::setElliptic(const double* m, int ngm, double m_const, const double*
                          const double* const* d, const double* const* d2, int ngd, double d_scale, double d_const)
 {
    if (d_with_s) throw std::runtime_error("HostMG::setElliptic on a quaternion solver");
+   configure(c != nullptr, c_const, m != nullptr, m_const, d != nullptr, d_const);
    const Level& L = d_levels[0];
-   MG_FOR_CELLS(L)
-   ampe_mg_cell::mg_set_elliptic_cell(L, m, ngm, m_const, c, ngc, c_const, d, d2, ngd, d_scale, d_const, d_inv_h2,
-                                      i, j, k);
+   if (m || c || d) {
+      MG_FOR_CELLS(L) ampe_mg_cell::mg_set_elliptic_cell(L, m, ngm, c, ngc, d, d2, ngd, d_scale, d_inv_h2, i, j, k);
+   }
    buildCoarse();
 }
 
 void HostMG::setQuat(double gamma, const double* mobility, int ngm, const double* const* face_coef, int ngfc)
 {
    if (!d_with_s) throw std::runtime_error("HostMG::setQuat on a scalar solver");
+   configure(false, 1.0, true, 0.0, true, 0.0);
    const Level& L = d_levels[0];
    MG_FOR_CELLS(L) ampe_mg_cell::mg_set_quat_cell(L, gamma, mobility, ngm, face_coef, ngfc, d_inv_h2, i, j, k);
    buildCoarse();
@@ -334,7 +358,12 @@ void HostMG::apply(const double* u, double* out) const
 const double* HostMG::levelArray(int level, int which) const
 {
    const Level& L = d_levels.at(level);
-   return which == 0 ? L.c : which == 1 ? L.m : which == 2 ? L.s : L.d[which - 3];
+   const double* p = which == 0 ? L.c : which == 1 ? L.m : which == 2 ? L.s : L.d[which - 3];
+   if (p || which == 2 || (which >= 3 && which - 3 >= d_ndim)) return p;
+   // a constant of the block: materialise it for the caller
+   const size_t nc = (size_t)L.n[0] * L.n[1] * L.n[2];
+   d_scratch.assign(nc, which == 0 ? L.c_const : which == 1 ? L.m_const : L.d_const[which - 3]);
+   return d_scratch.data();
 }
 
 // ---- (3) CVSpgmrPrecondSet / CVSpgmrPrecondSolve on the oracle context ---------------------------

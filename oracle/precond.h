@@ -1,5 +1,6 @@
 // TEST INFRASTRUCTURE ONLY (see oracle.h).  Block preconditioners: see precond.cc.
 #pragma once
+#include <array>
 #include <memory>
 #include <vector>
 
@@ -33,6 +34,7 @@ class HostMG
 
  private:
    void buildCoarse();
+   void configure(bool var_c, double c_const, bool var_m, double m_const, bool var_d, double d_const);
    void smooth(int l, int sweeps);
    void vcycle();
    int d_ndim;
@@ -43,6 +45,8 @@ class HostMG
    int d_pre = 1, d_post = 1, d_coarse = 8;
    std::vector<ampe_mg_cell::Level> d_levels;
    std::vector<std::vector<double>> d_store;
+   std::vector<std::array<std::vector<double>, 5>> d_coef;
+   mutable std::vector<double> d_scratch;
    std::vector<bool> d_two_colour;
 };
 
