@@ -1,9 +1,10 @@
 """Timing of the block-preconditioner solve (csrc/mg.cu) on one GPU: ms per V-cycle and per level-0
 half sweep at the BASELINE workload sizes, against the HBM roofline.  One JSON line per case.
-Algorithmic bytes: a colour half-sweep touches u (read + write), f, c, m and ND face
-arrays for half of the cells -> (5 + ND) * 8 B per updated cell; a V(1,1) cycle = 4 half-sweeps +
-residual ((4 + ND) * 8 B / cell + 8 B write) + restriction (8 B / cell read) + prolongation (16 B / cell)
-on level 0, times 1 / (1 - 2^-ND) for the coarse levels.
+Algorithmic bytes of the benchmarked block (M and C constants, D an array per direction --
+the composition block): a colour half-sweep touches u (read + write), f and ND face arrays for half of the
+cells -> (3 + ND) * 8 B per updated cell; a V(1,1) cycle = 4 half-sweeps + residual ((2 + ND) * 8 B read +
+8 B write per cell) + restriction (8 B / cell read) + prolongation (16 B / cell) on level 0, times
+1 / (1 - 2^-ND) for the coarse levels.
 usage (GPU box): python tools/bench_precond.py [--cases 2d:2048x2048,3d:256x256x256] [--cycles 10]"""
 import argparse
 import json
@@ -67,7 +68,7 @@ def main():
             best = ms if best is None else min(best, ms)
         launches = g.last_launch_count()
         per_cycle = best / a.cycles
-        lvl0 = 4 * 0.5 * (5 + nd) * 8 + ((4 + nd) * 8 + 8) + 8 + 16
+        lvl0 = 4 * 0.5 * (3 + nd) * 8 + ((2 + nd) * 8 + 8) + 8 + 16
         bytes_cycle = ncell * lvl0 / (1.0 - 0.5 ** nd)
         gbs = bytes_cycle / (per_cycle * 1e-3) / 1e9
         print(json.dumps({"case": case, "levels": g.num_levels(), "ms_per_vcycle": per_cycle,
