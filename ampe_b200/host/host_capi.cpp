@@ -3,6 +3,7 @@
 #include <cstring>
 #include <string>
 
+#include "FieldsInitializer.h"
 #include "QuatIntegrator.h"
 
 static thread_local std::string g_host_err;
@@ -132,5 +133,23 @@ void ampe_host_precond_stats(void* h, double* out2)
 {
    out2[0] = (double)static_cast<ampe_host::QuatIntegrator*>(h)->precondSetups();
    out2[1] = (double)static_cast<ampe_host::QuatIntegrator*>(h)->precondSolves();
+}
+// ---- initial conditions ----------------------------------------------------
+// FieldsInitializer::initializeLevelFromData(level, init_data_filename, slice_index): fills the HOST arrays
+// of y (ghost 0, this rank's slab) from a NetCDF classic file; no GPU involved.  read_mask bits: 1 phase,
+// 2 temperature, 4 quaternion, 8 concentration (setFieldsToRead).
+int ampe_host_read_initial_conditions(const char* filename, const ampe_rhs_config* cfg, int slice_index,
+                                      int read_mask, const ampe_rhs_fields* y_host)
+{
+   try {
+      if (!filename || !cfg || !y_host) throw std::runtime_error("ampe_host_read_initial_conditions: NULL argument");
+      ampe_host::FieldsInitializer init(*cfg);
+      init.setFieldsToRead(read_mask & 1, read_mask & 2, read_mask & 4, read_mask & 8);
+      init.initializeLevelFromData(filename, slice_index, y_host);
+      return 0;
+   } catch (const std::exception& e) {
+      g_host_err = e.what();
+      return -1;
+   }
 }
 }

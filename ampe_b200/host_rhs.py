@@ -47,8 +47,43 @@ def load_host():
         L.ampe_host_precond_level_solver.restype = vp
         L.ampe_host_precond_level_solver.argtypes = [vp, C.c_int]
         L.ampe_host_precond_stats.argtypes = [vp, vp]
+        L.ampe_host_read_initial_conditions.restype = C.c_int
+        L.ampe_host_read_initial_conditions.argtypes = [C.c_char_p, C.POINTER(_abi.RhsConfig), C.c_int, C.c_int,
+                                                        C.POINTER(_abi.RhsFields)]
         _lib = L
     return _lib
+
+
+def read_initial_conditions(filename, cfg, slice_index=-1, fields=("phase", "temperature", "quat", "conc"),
+                            device=None):
+    """FieldsInitializer::initializeLevelFromData (source/FieldsInitializer.cc:80-360): the state vector of this
+    rank's slab from a NetCDF classic file (`phase`, `quat1..`, `concentration[0]`, `temperature`, dims z, y, x).
+    Returns a dict of float64 tensors in ghost-0 SAMRAI order (pinned host memory when CUDA is available, moved
+    to `device` if given); components the configuration does not have are None."""
+    L = load_host()
+    nz = cfg.n[2] if cfg.ndim == 3 else 1
+    shape = (nz, cfg.n[1], cfg.n[0])
+    pin = torch.cuda.is_available()
+    out = {"phase": None, "quat": None, "conc": None, "temperature": None}
+    if cfg.with_phase and "phase" in fields:
+        out["phase"] = torch.zeros(shape, dtype=torch.float64, pin_memory=pin)
+    if cfg.qlen > 0 and "quat" in fields:
+        out["quat"] = torch.zeros((cfg.qlen,) + shape, dtype=torch.float64, pin_memory=pin)
+    if cfg.with_concentration and "conc" in fields:
+        out["conc"] = torch.zeros(shape, dtype=torch.float64, pin_memory=pin)
+    if cfg.with_unsteady_temperature and "temperature" in fields:
+        out["temperature"] = torch.zeros(shape, dtype=torch.float64, pin_memory=pin)
+    f = _abi.RhsFields()
+    for k in out:
+        setattr(f, "phase" if k == "phase" else k, None if out[k] is None else out[k].data_ptr())
+    mask = (1 if "phase" in fields else 0) | (2 if "temperature" in fields else 0) | (4 if "quat" in fields else 0) | \
+        (8 if "conc" in fields else 0)
+    rc = L.ampe_host_read_initial_conditions(os.fsencode(filename), C.byref(cfg), int(slice_index), mask, C.byref(f))
+    if rc != 0:
+        raise AmpeError(L.ampe_host_last_error().decode())
+    if device is not None:
+        out = {k: (None if v is None else v.to(device, non_blocking=True)) for k, v in out.items()}
+    return out
 
 
 class HostQuatIntegrator:
