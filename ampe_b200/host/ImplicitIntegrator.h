@@ -15,8 +15,9 @@
 //   * optional RIGHT preconditioning by the backend's block preconditioner (the
 //     reference's CVSpgmrPrecondSet / CVSpgmrPrecondSolve, QuatIntegrator.cc:3300-3771): set up after
 //     every fd_flag = 0 residual evaluation, applied once per Krylov vector and once to the solution.
-// CVODE itself (variable step / order, error test) is out of scope: the step is
-// fixed and a Newton failure is returned to the caller instead of retried with a smaller step.
+// advance() takes fixed steps and returns a Newton failure to the caller; advanceTo() adds CVODE's local error
+// test and step-size controller (variable-coefficient BDF2, no order selection).  CVODE's Nordsieck history,
+// order selection and stability-limit detection are not restated (SUNDIALS is not in the reference tree).
 //
 // The algorithm is a template over the vector backend so that the same code drives the device
 // vectors (DeviceOps in QuatIntegrator.h, everything through the C ABI of libampe_b200.so) and a
@@ -34,6 +35,11 @@ struct ImplicitOptions {
    int max_newton_iterations = 3;          // CVODE NLS_MAXCOR
    double newton_tolerance = 0.1;          // CVODE nlscoef
    double linear_tolerance_factor = 0.05;  // CVODE eplifac
+   // advanceTo only (variable step size, CVODE's controller constants, cvode_impl.h / cvode.c)
+   double h_min = 0.0, h_max = 0.0;        // 0 = unbounded (CVodeSetMinStep / CVodeSetMaxStep)
+   long max_steps = 500;                   // CVODE mxstep
+   int max_error_test_failures = 7;        // MXNEF
+   int max_convergence_failures = 10;      // MXNCF
 };
 
 struct ImplicitStats {
@@ -41,9 +47,20 @@ struct ImplicitStats {
         projections = 0, precond_setups = 0, precond_solves = 0;
    double last_newton_update = 0.0;  // WRMS norm of the last Newton correction
    double last_linear_residual = 0.0;
+   // advanceTo
+   long error_test_failures = 0, convergence_failures = 0;
+   double last_step = 0.0, smallest_step = 0.0, largest_step = 0.0, last_error_estimate = 0.0, t_reached = 0.0;
 };
 
-enum { IMPLICIT_OK = 0, IMPLICIT_EINVAL = -1, IMPLICIT_ENEWTON = -20, IMPLICIT_ERHS = -21 };
+enum {
+   IMPLICIT_OK = 0,
+   IMPLICIT_EINVAL = -1,
+   IMPLICIT_ENEWTON = -20,
+   IMPLICIT_ERHS = -21,
+   IMPLICIT_ETOOMUCHWORK = -22,  // CV_TOO_MUCH_WORK: max_steps taken before tend
+   IMPLICIT_EERRTEST = -23,      // CV_ERR_FAILURE: error test failed too often or h = h_min
+   IMPLICIT_ECONV = -24          // CV_CONV_FAILURE: Newton failed too often or h = h_min
+};
 
 // Ops concept:
 //   typedef ... Vec;
@@ -120,6 +137,142 @@ class ImplicitIntegrator
       }
       for (auto& v : V) d_ops.release(v);
       Vec* all[] = {&yprev, &psi, &ycur, &fy, &ewt, &res, &delta, &acor, &ytmp, &wk};
+      for (Vec* v : all) d_ops.release(*v);
+      d_ops.release(d_pv);
+      return rc;
+   }
+
+   // Variable-step BDF1/BDF2 from t0 to tend (y updated in place), first step h0: the stand-in for
+   // CVode(tend, CV_NORMAL) with max order 2.  Variable-coefficient BDF2 on the last two solutions
+   // (step ratio w = h_n / h_{n-1}):  y_{n+1} = [(1+w)^2 y_n - w^2 y_{n-1}] / (1+2w) + [(1+w)/(1+2w)] h_n f(y_{n+1}).
+   // Local error: the accumulated Newton correction acor = y_{n+1} - y_predicted (CVODE's estimate, after the
+   // projection hook has removed its component along q) times the ratio of the leading error terms of corrector
+   // and predictor,
+   //   BDF1, Euler predictor y_n + h f_n                      1/2                       (first step)
+   //   BDF1, linear extrapolation through y_n, y_{n-1}         h / (2h + h1)
+   //   BDF2, quadratic extrapolation through y_n .. y_{n-2}    a / (a + h + h1 + h2),  a = h (h + h1) / (2h + h1)
+   // (h = h_n, h1 = h_{n-1}, h2 = h_{n-2}; equal steps: 1/3 and 2/11).  Step accepted when the WRMS norm dsm of
+   // the estimate is <= 1; next step h * eta, eta = 1 / ((BIAS2 dsm)^(1/(q+1)) + ADDON) with CVODE's constants
+   // (BIAS2 = 6, ADDON = 1e-6, growth <= ETAMX = 10, kept when eta < THRESH = 1.5, shrink >= ETAMIN = 0.1 after a
+   // failed error test, 0.2 after three of them, ETACF = 0.25 after a failed Newton iteration).  BDF2 from the
+   // third step on (the quadratic predictor needs three solutions); no order selection.
+   int advanceTo(Vec& y, double t0, double tend, double h0)
+   {
+      if (!(h0 > 0.0) || !(tend > t0) || (d_opt.order != 1 && d_opt.order != 2) || d_opt.max_krylov_dimension < 1 ||
+          d_opt.max_newton_iterations < 1)
+         return IMPLICIT_EINVAL;
+      const double BIAS2 = 6.0, ADDON = 1.0e-6, ETAMX = 10.0, THRESH = 1.5, ETAMIN = 0.1, ETACF = 0.25;
+      const int m = d_opt.max_krylov_dimension;
+      Vec y1 = d_ops.clone(y), y2 = d_ops.clone(y), psi = d_ops.clone(y), ycur = d_ops.clone(y), fy = d_ops.clone(y),
+          ewt = d_ops.clone(y), res = d_ops.clone(y), delta = d_ops.clone(y), acor = d_ops.clone(y),
+          ytmp = d_ops.clone(y), wk = d_ops.clone(y);
+      d_pv = d_ops.clone(y);
+      std::vector<Vec> V;
+      for (int j = 0; j <= m; j++) V.push_back(d_ops.clone(y));
+      int rc = IMPLICIT_OK;
+      double t = t0, h = std::fmin(h0, tend - t0), h1 = 0.0, h2 = 0.0;  // h1, h2: the last two accepted steps
+      if (d_opt.h_max > 0.0) h = std::fmin(h, d_opt.h_max);
+      long nacc = 0;  // accepted steps = solutions in the history beyond y
+      int nef = 0, ncf = 0;
+      d_stats.smallest_step = 0.0, d_stats.largest_step = 0.0;
+      while (t < tend && rc == IMPLICIT_OK) {
+         if (d_stats.steps >= d_opt.max_steps) {
+            rc = IMPLICIT_ETOOMUCHWORK;
+            break;
+         }
+         const bool bdf2 = d_opt.order == 2 && nacc >= 2;
+         double gamma, cerr;
+         d_ops.errorWeights(y, d_opt.rtol, d_opt.atol, ewt);
+         if (bdf2) {
+            const double w = h / h1;
+            gamma = h * (1.0 + w) / (1.0 + 2.0 * w);
+            d_ops.linearSum((1.0 + w) * (1.0 + w) / (1.0 + 2.0 * w), y, -w * w / (1.0 + 2.0 * w), y1, psi);
+            // quadratic extrapolation through (t, y), (t - h1, y1), (t - h1 - h2, y2) to t + h
+            const double l0 = (h + h1) * (h + h1 + h2) / (h1 * (h1 + h2));
+            const double l1 = -h * (h + h1 + h2) / (h1 * h2);
+            const double l2 = h * (h + h1) / ((h1 + h2) * h2);
+            d_ops.linearSum(l0, y, l1, y1, ycur);
+            d_ops.linearSum(1.0, ycur, l2, y2, ycur);
+            const double a = h * (h + h1) / (2.0 * h + h1);
+            cerr = a / (a + h + h1 + h2);
+         } else {
+            gamma = h;
+            d_ops.scale(1.0, y, psi);
+            if (nacc == 0) {
+               if (d_ops.rhs(t, y, fy, 0) != 0) {
+                  rc = IMPLICIT_ERHS;
+                  break;
+               }
+               d_stats.rhs_evals++;
+               d_ops.linearSum(1.0, y, h, fy, ycur);
+               cerr = 0.5;
+            } else {
+               d_ops.linearSum(1.0 + h / h1, y, -h / h1, y1, ycur);
+               cerr = h / (2.0 * h + h1);
+            }
+         }
+         d_ops.scale(0.0, acor, acor);
+         const int nrc = newton(t + h, gamma, psi, ewt, ycur, fy, res, delta, acor, ytmp, wk, V);
+         if (nrc == IMPLICIT_ERHS) {
+            rc = nrc;
+            break;
+         }
+         double eta;
+         if (nrc != IMPLICIT_OK) {
+            // CVODE cvNlsFailure handling: retry with h * ETACF
+            d_stats.convergence_failures++;
+            if (++ncf >= d_opt.max_convergence_failures || (d_opt.h_min > 0.0 && h <= d_opt.h_min * 1.00001)) {
+               rc = IMPLICIT_ECONV;
+               break;
+            }
+            eta = ETACF;
+         } else {
+            d_ops.applyProjection(t + h, ycur, delta, acor);
+            d_stats.projections++;
+            const double dsm = cerr * wrms(acor, ewt);
+            d_stats.last_error_estimate = dsm;
+            const int q = bdf2 ? 2 : 1;
+            eta = 1.0 / (std::pow(BIAS2 * dsm, 1.0 / (q + 1)) + ADDON);
+            if (dsm <= 1.0) {
+               // accept
+               d_ops.linearSum(1.0, ycur, 1.0, delta, ycur);
+               d_ops.scale(1.0, y1, y2);
+               d_ops.scale(1.0, y, y1);
+               d_ops.scale(1.0, ycur, y);
+               d_ops.postStep(y);
+               t += h;
+               h2 = h1, h1 = h;
+               nacc++, nef = 0, ncf = 0;
+               d_stats.steps++;
+               d_stats.last_step = h;
+               d_stats.largest_step = std::fmax(d_stats.largest_step, h);
+               d_stats.smallest_step = d_stats.smallest_step > 0.0 ? std::fmin(d_stats.smallest_step, h) : h;
+               eta = std::fmin(eta, ETAMX);
+               if (eta < THRESH) eta = 1.0;
+            } else {
+               d_stats.error_test_failures++;
+               if (++nef >= d_opt.max_error_test_failures || (d_opt.h_min > 0.0 && h <= d_opt.h_min * 1.00001)) {
+                  rc = IMPLICIT_EERRTEST;
+                  break;
+               }
+               eta = std::fmax(ETAMIN, std::fmin(eta, 0.9));
+               if (nef >= 3) eta = std::fmin(eta, 0.2);
+            }
+         }
+         h *= eta;
+         if (d_opt.h_max > 0.0) h = std::fmin(h, d_opt.h_max);
+         if (d_opt.h_min > 0.0) h = std::fmax(h, d_opt.h_min);
+         if (t < tend) {
+            const double left = tend - t;
+            if (h >= left * (1.0 - 1.0e-12))
+               h = left;  // land on tend
+            else if (h > 0.5 * left && eta >= 1.0)
+               h = 0.5 * left;  // do not leave a sliver for the last step
+         }
+      }
+      d_stats.t_reached = t;
+      for (auto& v : V) d_ops.release(v);
+      Vec* all[] = {&y1, &y2, &psi, &ycur, &fy, &ewt, &res, &delta, &acor, &ytmp, &wk};
       for (Vec* v : all) d_ops.release(*v);
       d_ops.release(d_pv);
       return rc;

@@ -273,6 +273,19 @@ class QuatIntegrator
       cuda_check(cudaDeviceSynchronize(), "integrateImplicit");
       return rc;
    }
+   // variable steps with the local error test from t0 to tend (ImplicitIntegrator::advanceTo): what
+   // QuatIntegrator::Advance asks of CVode(tend, CV_NORMAL), y stays on the device
+   int integrateAdaptive(const ampe_rhs_fields* y, double t0, double tend, double h0, const ImplicitOptions& opt,
+                         ImplicitStats* stats)
+   {
+      DeviceVectorOps ops(d_ctx, d_cfg, this);
+      ImplicitIntegrator<DeviceVectorOps> integ(ops, opt);
+      ampe_rhs_fields yy = *y;
+      const int rc = integ.advanceTo(yy, t0, tend, h0);
+      if (stats) *stats = integ.stats();
+      cuda_check(cudaDeviceSynchronize(), "integrateAdaptive");
+      return rc;
+   }
    // fixed-step explicit stand-in for QuatIntegrator::Advance (scheme 0 Euler, 1 Heun)
    void integrateFixed(const ampe_rhs_fields* y, const ampe_rhs_fields* work1, const ampe_rhs_fields* work2,
                        double t0, double dt, int nsteps, int scheme)

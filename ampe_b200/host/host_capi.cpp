@@ -78,6 +78,41 @@ int ampe_host_integrate_implicit(void* h, const ampe_rhs_fields* y, double t0, d
       return -1;
    }
 }
+// ImplicitIntegrator::advanceTo on device vectors.  iopt[5]: order, max_krylov_dimension,
+// max_newton_iterations, max_steps, reserved; dopt[6]: rtol, atol, newton_tolerance, linear_tolerance_factor,
+// h_min, h_max; stats_out[16]: the 8 of ampe_host_integrate_implicit, then error_test_failures,
+// convergence_failures, last_step, smallest_step, largest_step, last_error_estimate, t_reached, 0.
+// Returns 0 or an IMPLICIT_E* code (-20 .. -24); -1 with ampe_host_last_error() for everything else.
+int ampe_host_integrate_adaptive(void* h, const ampe_rhs_fields* y, double t0, double tend, double h0,
+                                 const int* iopt, const double* dopt, double* stats_out)
+{
+   try {
+      ampe_host::ImplicitOptions o;
+      if (iopt) {
+         o.order = iopt[0], o.max_krylov_dimension = iopt[1], o.max_newton_iterations = iopt[2];
+         if (iopt[3] > 0) o.max_steps = iopt[3];
+      }
+      if (dopt) {
+         o.rtol = dopt[0], o.atol = dopt[1], o.newton_tolerance = dopt[2], o.linear_tolerance_factor = dopt[3];
+         o.h_min = dopt[4], o.h_max = dopt[5];
+      }
+      ampe_host::ImplicitStats st;
+      const int rc = static_cast<ampe_host::QuatIntegrator*>(h)->integrateAdaptive(y, t0, tend, h0, o, &st);
+      if (stats_out) {
+         const double out[16] = {(double)st.steps, (double)st.rhs_evals, (double)st.jtimes_evals,
+                                 (double)st.newton_iterations, (double)st.linear_iterations, (double)st.projections,
+                                 st.last_newton_update, st.last_linear_residual, (double)st.error_test_failures,
+                                 (double)st.convergence_failures, st.last_step, st.smallest_step, st.largest_step,
+                                 st.last_error_estimate, st.t_reached, 0.0};
+         memcpy(stats_out, out, sizeof(out));
+      }
+      if (rc != 0) g_host_err = "integrateAdaptive: code " + std::to_string(rc);
+      return rc;
+   } catch (const std::exception& e) {
+      g_host_err = e.what();
+      return -1;
+   }
+}
 // ---- block preconditioners ------------------------------------------------
 // QuatIntegrator::setupPreconditioners; ncycles V-cycles per block solve, 0 = preconditioner off
 int ampe_host_set_preconditioner(void* h, int ncycles, int precond_has_dquatdphi)

@@ -36,6 +36,9 @@ def load_host():
         L.ampe_host_integrate_implicit.restype = C.c_int
         L.ampe_host_integrate_implicit.argtypes = [vp, C.POINTER(_abi.RhsFields), C.c_double, C.c_double, C.c_int,
                                                    vp, vp, vp]
+        L.ampe_host_integrate_adaptive.restype = C.c_int
+        L.ampe_host_integrate_adaptive.argtypes = [vp, C.POINTER(_abi.RhsFields), C.c_double, C.c_double, C.c_double,
+                                                   vp, vp, vp]
         L.ampe_host_set_preconditioner.restype = C.c_int
         L.ampe_host_set_preconditioner.argtypes = [vp, C.c_int, C.c_int]
         L.ampe_host_precond_dquatdphi.restype = C.c_int
@@ -134,6 +137,26 @@ class HostQuatIntegrator:
         names = ("steps", "rhs_evals", "jtimes_evals", "newton_iterations", "linear_iterations", "projections",
                  "last_newton_update", "last_linear_residual")
         return rc, dict(zip(names, list(st)))
+
+    ADAPTIVE_STATS = ("steps", "rhs_evals", "jtimes_evals", "newton_iterations", "linear_iterations", "projections",
+                      "last_newton_update", "last_linear_residual", "error_test_failures", "convergence_failures",
+                      "last_step", "smallest_step", "largest_step", "last_error_estimate", "t_reached")
+
+    def integrateAdaptive(self, y, tend, h0, t0=0.0, order=2, max_krylov=5, max_newton=3, rtol=3e-6, atol=3e-4,
+                          newton_tol=0.1, lin_factor=0.05, h_min=0.0, h_max=0.0, max_steps=500):
+        """variable-step BDF1/BDF2 with CVODE's local error test and step controller from t0 to tend on the device
+        (host/ImplicitIntegrator.h advanceTo), y updated in place.  Returns (rc, stats); rc 0 or IMPLICIT_E*
+        (-20 Newton, -22 too much work, -23 error test, -24 convergence)."""
+        iopt = (C.c_int * 5)(int(order), int(max_krylov), int(max_newton), int(max_steps), 0)
+        dopt = (C.c_double * 6)(float(rtol), float(atol), float(newton_tol), float(lin_factor), float(h_min),
+                                float(h_max))
+        st = (C.c_double * 16)()
+        fy = y.fields()
+        rc = self.L.ampe_host_integrate_adaptive(self.h, C.byref(fy), float(t0), float(tend), float(h0), iopt, dopt,
+                                                 st)
+        if rc == -1:
+            raise AmpeError(self.L.ampe_host_last_error().decode())
+        return rc, dict(zip(self.ADAPTIVE_STATS, list(st)))
 
     # ---- block preconditioners (SURVEY.md 8f rank 3) ----
     def setupPreconditioners(self, ncycles=2, precond_has_dquatdphi=False):

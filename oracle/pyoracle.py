@@ -71,6 +71,9 @@ def lib(perf=False):
         L.oracle_integrate_implicit.restype = C.c_int
         L.oracle_integrate_implicit.argtypes = [C.c_void_p, C.POINTER(_abi.RhsFields), dbl, dbl, C.c_int,
                                                 C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_integrate_adaptive.restype = C.c_int
+        L.oracle_integrate_adaptive.argtypes = [C.c_void_p, C.POINTER(_abi.RhsFields), dbl, dbl, dbl,
+                                                C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_quatfindsymm.restype = C.c_int
         L.oracle_quatfindsymm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.oracle_k_quat_symm_rotation.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
@@ -248,6 +251,22 @@ class Oracle:
     def precond_block(self, block):
         h = self.L.oracle_precond_block(self.h, int(block))
         return HostMG(handle=h, owner=self) if h else None
+
+    ADAPTIVE_STATS = ("steps", "rhs_evals", "jtimes_evals", "newton_iterations", "linear_iterations", "projections",
+                      "last_newton_update", "last_linear_residual", "error_test_failures", "convergence_failures",
+                      "last_step", "smallest_step", "largest_step", "last_error_estimate", "t_reached")
+
+    def integrate_adaptive(self, y, tend, h0, t0=0.0, order=2, max_krylov=5, max_newton=3, rtol=3e-6, atol=3e-4,
+                           newton_tol=0.1, lin_factor=0.05, h_min=0.0, h_max=0.0, max_steps=500):
+        """ImplicitIntegrator::advanceTo driven by the oracle's RHS: variable steps with the local error test
+        from t0 to tend; y advanced in place; returns (rc, stats)"""
+        iopt = np.array([order, max_krylov, max_newton, max_steps, 0], dtype=np.int32)
+        dopt = np.array([rtol, atol, newton_tol, lin_factor, h_min, h_max], dtype=np.float64)
+        st = np.zeros(16)
+        fy = _fields(y)
+        rc = self.L.oracle_integrate_adaptive(self.h, C.byref(fy), float(t0), float(tend), float(h0), _ptr(iopt),
+                                              _ptr(dopt), _ptr(st))
+        return rc, dict(zip(self.ADAPTIVE_STATS, st.tolist()))
 
     def phase_concentrations(self):
         cl = np.zeros(self.ncell)

@@ -173,3 +173,46 @@ extern "C" int oracle_integrate_implicit(void* ctx, const ampe_rhs_fields* y, do
       if (src[k]) memcpy(src[k], v.comp[k].data(), sizeof(double) * ncell * depth[k]);
    return rc;
 }
+
+// advanceTo (variable step, local error test).  iopt[5]: order, max_krylov_dimension, max_newton_iterations,
+// max_steps, (reserved); dopt[6]: rtol, atol, newton_tolerance, linear_tolerance_factor, h_min, h_max;
+// stats_out[16]: the 8 of oracle_integrate_implicit, then error_test_failures, convergence_failures,
+// last_step, smallest_step, largest_step, last_error_estimate, t_reached, 0
+extern "C" int oracle_integrate_adaptive(void* ctx, const ampe_rhs_fields* y, double t0, double tend, double h0,
+                                         const int* iopt, const double* dopt, double* stats_out)
+{
+   Ctx* c = (Ctx*)ctx;
+   const ampe_rhs_config& cfg = c->cfg;
+   size_t ncell = 1;
+   for (int d = 0; d < cfg.ndim; d++) ncell *= (size_t)cfg.n[d];
+   HVec v;
+   double* src[4] = {y->phase, y->quat, y->conc, y->temperature};
+   const size_t depth[4] = {1, (size_t)(cfg.qlen > 0 ? cfg.qlen : 1), 1, 1};
+   for (int k = 0; k < 4; k++)
+      if (src[k]) v.comp[k].assign(src[k], src[k] + ncell * depth[k]);
+   ampe_host::ImplicitOptions o;
+   if (iopt) {
+      o.order = iopt[0], o.max_krylov_dimension = iopt[1], o.max_newton_iterations = iopt[2];
+      if (iopt[3] > 0) o.max_steps = iopt[3];
+   }
+   if (dopt) {
+      o.rtol = dopt[0], o.atol = dopt[1], o.newton_tolerance = dopt[2], o.linear_tolerance_factor = dopt[3];
+      o.h_min = dopt[4], o.h_max = dopt[5];
+   }
+   OracleOps ops(c);
+   ampe_host::ImplicitIntegrator<OracleOps> integ(ops, o);
+   const int rc = integ.advanceTo(v, t0, tend, h0);
+   const ampe_host::ImplicitStats& st = integ.stats();
+   if (stats_out) {
+      const double out[16] = {(double)st.steps, (double)st.rhs_evals, (double)st.jtimes_evals,
+                              (double)st.newton_iterations, (double)st.linear_iterations, (double)st.projections,
+                              st.last_newton_update, st.last_linear_residual, (double)st.error_test_failures,
+                              (double)st.convergence_failures, st.last_step, st.smallest_step, st.largest_step,
+                              st.last_error_estimate, st.t_reached, 0.0};
+      memcpy(stats_out, out, sizeof(out));
+   }
+   c->precond_stats[0] = (double)st.precond_setups, c->precond_stats[1] = (double)st.precond_solves;
+   for (int k = 0; k < 4; k++)
+      if (src[k]) memcpy(src[k], v.comp[k].data(), sizeof(double) * ncell * depth[k]);
+   return rc;
+}

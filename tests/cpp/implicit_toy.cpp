@@ -160,5 +160,79 @@ int main()
       std::printf("starved_newton_rc %d\n", integ.advance(y, 0.0, 1.0, 1));
       std::printf("bad_step_rc %d\n", integ.advance(y, 0.0, -1.0, 1));
    }
+   // ---- advanceTo: variable steps with the local error test.  Semi-discrete diffusion: the exact solution of
+   // the ODE system is amp_m exp(lambda_m t) per Fourier mode (rates 27 .. 1290), so the GLOBAL error of the
+   // adaptive run can be compared with the tolerance it was asked for.
+   for (int tolcase = 0; tolcase < 3; tolcase++) {
+      ToyOps ops;
+      ops.kind = 0, ops.D = 0.7, ops.h = 1.0 / N, ops.n = N;
+      ImplicitOptions o;
+      o.order = 2;
+      const double tol = tolcase == 0 ? 1e-3 : tolcase == 1 ? 1e-5 : 1e-7;
+      o.rtol = tol, o.atol = tol * 1e-2;
+      o.max_krylov_dimension = 12, o.max_newton_iterations = 4;
+      o.newton_tolerance = 0.05;
+      o.max_steps = 20000;
+      const int modes[3] = {1, 3, 7};
+      const double amp[3] = {1.0, 0.5, 0.25};
+      std::vector<double> y(N);
+      for (int i = 0; i < N; i++) {
+         y[i] = 2.0;
+         for (int m = 0; m < 3; m++) y[i] += amp[m] * std::cos(2.0 * PI * modes[m] * i / N);
+      }
+      const double tend = 0.05;
+      ImplicitIntegrator<ToyOps> integ(ops, o);
+      const int rc = integ.advanceTo(y, 0.0, tend, 1.0e-6);
+      double err = 0.0;
+      for (int i = 0; i < N; i++) {
+         double want = 2.0;
+         for (int m = 0; m < 3; m++) {
+            const double lam = -4.0 * ops.D / (ops.h * ops.h) * std::pow(std::sin(PI * modes[m] / N), 2);
+            want += amp[m] * std::exp(lam * tend) * std::cos(2.0 * PI * modes[m] * i / N);
+         }
+         err = std::fmax(err, std::fabs(y[i] - want));
+      }
+      const ampe_host::ImplicitStats& st = integ.stats();
+      std::printf("adaptive%d_rc %d\n", tolcase, rc);
+      std::printf("adaptive%d_err_over_tol %.4f\n", tolcase, err / tol);
+      std::printf("adaptive%d_steps %ld\n", tolcase, st.steps);
+      std::printf("adaptive%d_error_test_failures %ld\n", tolcase, st.error_test_failures);
+      std::printf("adaptive%d_step_growth %.3e\n", tolcase, st.largest_step / st.smallest_step);
+      std::printf("adaptive%d_t_reached_err %.3e\n", tolcase, std::fabs(st.t_reached - tend));
+   }
+   // nonlinear: y' = -y^3 to t = 1 against the exact solution
+   {
+      ToyOps ops;
+      ops.kind = 1, ops.n = 1;
+      ImplicitOptions o;
+      o.order = 2;
+      o.rtol = 1e-6, o.atol = 1e-9;
+      o.max_newton_iterations = 4;
+      std::vector<double> y = {1.0};
+      ImplicitIntegrator<ToyOps> integ(ops, o);
+      const int rc = integ.advanceTo(y, 0.0, 1.0, 1.0e-4);
+      std::printf("adaptive_cubic_rc %d\n", rc);
+      std::printf("adaptive_cubic_err %.3e\n", std::fabs(y[0] - 1.0 / std::sqrt(3.0)));
+      std::printf("adaptive_cubic_steps %ld\n", integ.stats().steps);
+   }
+   // the failure codes: too much work, a minimum step that cannot meet the tolerance, bad arguments
+   {
+      ToyOps ops;
+      ops.kind = 1, ops.n = 1;
+      ImplicitOptions o;
+      o.order = 2;
+      o.rtol = 1e-8, o.atol = 1e-11;
+      o.max_newton_iterations = 4;
+      o.max_steps = 5;
+      std::vector<double> y = {1.0};
+      ImplicitIntegrator<ToyOps> a(ops, o);
+      std::printf("adaptive_too_much_work_rc %d\n", a.advanceTo(y, 0.0, 1.0, 1.0e-4));
+      o.max_steps = 500, o.h_min = 0.25, o.max_newton_iterations = 12;
+      y = {1.0};
+      ImplicitIntegrator<ToyOps> b(ops, o);
+      std::printf("adaptive_hmin_rc %d\n", b.advanceTo(y, 0.0, 1.0, 0.25));
+      ImplicitIntegrator<ToyOps> c(ops, o);
+      std::printf("adaptive_bad_interval_rc %d\n", c.advanceTo(y, 1.0, 1.0, 0.1));
+   }
    return 0;
 }

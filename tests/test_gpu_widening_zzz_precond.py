@@ -323,3 +323,35 @@ def test_one_block_tail_and_graph_replay_are_bit_identical(n, dx):
     assert torch.equal(outs["tail"], outs["levels"])
     assert torch.equal(outs["tail"], outs["graph"])
     assert launches["tail"] < launches["levels"]
+
+
+@pytest.mark.parametrize("name,mult,precond", [("pfhub1a", 200, 0), ("dendrite2d", 300, 2), ("gg3d_hbsm", 120, 2)])
+def test_adaptive_integration_matches_oracle_backend(name, mult, precond):
+    """ImplicitIntegrator::advanceTo on device vectors (variable steps, local error test) against the same
+    template driven by the CPU oracle: same number of steps and failures, fields within 1e-8"""
+    from oracle import pyoracle
+    kw = dict(rtol=1e-6, atol=1e-8, max_krylov=30, max_newton=4, max_steps=2000)
+    dt = parity.TRAJ_DT[name]
+    cfg, st, y, h, rot = _device_context(name)
+    if precond:
+        h.setupPreconditioners(precond)
+    rc, sg = h.integrateAdaptive(y, mult * dt, dt, **kw)
+    torch.cuda.synchronize()
+    yo = {k: (None if v is None else v.numpy().copy()) for k, v in st.items()}
+    o = pyoracle.Oracle(cfg)
+    if cfg.conc_rhs_form in (2, 3):
+        o.set_ref(yo["conc"].ravel().copy(), yo["conc"].ravel().copy())
+    if rot is not None:
+        o.set_rotations(rot)
+    o.set_preconditioner(precond)
+    rco, so = o.integrate_adaptive(yo, mult * dt, dt, **kw)
+    assert rc == 0 and rco == 0, (sg, so)
+    assert sg["steps"] == so["steps"] and sg["error_test_failures"] == so["error_test_failures"], (sg, so)
+    assert abs(sg["t_reached"] - mult * dt) <= 1e-12 * mult * dt
+    for k in ("phase", "quat", "conc", "temperature"):
+        if yo.get(k) is None:
+            continue
+        scale = max(np.abs(yo[k]).max(), 1e-300)
+        assert np.abs(y[k].cpu().numpy() - yo[k]).max() <= 1e-8 * scale, (k, sg, so)
+    o.close()
+    h.close()

@@ -104,3 +104,62 @@ def test_default_tolerances_are_the_reference_defaults():
         assert frag in text
     _, _, _, rc, stats = _implicit("pfhub1a", parity.TRAJ_DT["pfhub1a"] * 20, 5)
     assert rc == 0 and stats["steps"] == 5
+
+
+# ---- advanceTo: variable steps with the local error test ------------------------------------------------------
+def test_adaptive_controller_on_closed_form_problems(toy):
+    """semi-discrete diffusion (decay rates 27 .. 1290) against its exact solution: the run lands on tend, the
+    step grows by orders of magnitude as the fast modes die, the work scales like tol^(-1/3) (second order) and
+    the global error follows the tolerance (error-per-step control: ~tol^(2/3)); failure codes are reported"""
+    for k in range(3):
+        assert toy["adaptive%d_rc" % k] == 0
+        assert toy["adaptive%d_t_reached_err" % k] == 0.0
+        assert toy["adaptive%d_step_growth" % k] > 100.0
+        assert toy["adaptive%d_error_test_failures" % k] <= 3
+    assert toy["adaptive0_err_over_tol"] < 5 and toy["adaptive1_err_over_tol"] < 20 and toy["adaptive2_err_over_tol"] < 80
+    # 100x tighter tolerance: 100^(1/3) = 4.6x the steps for a second-order method
+    assert 3.0 < toy["adaptive1_steps"] / toy["adaptive0_steps"] < 6.0
+    assert 3.0 < toy["adaptive2_steps"] / toy["adaptive1_steps"] < 6.0
+    assert toy["adaptive_cubic_rc"] == 0 and toy["adaptive_cubic_err"] < 5e-5
+    assert toy["adaptive_too_much_work_rc"] == -22
+    assert toy["adaptive_hmin_rc"] == -23
+    assert toy["adaptive_bad_interval_rc"] == -1
+
+
+def test_adaptive_pfhub1a_against_a_fine_trajectory():
+    """Cahn-Hilliard (C1) from t = 0 to 200 explicit steps' worth of time: the adaptive run agrees with a Heun
+    trajectory of 4x smaller steps to its tolerance, conserves the total composition, and needs far fewer steps
+    than the explicit integrator because the step grows while the spinodal structure coarsens"""
+    from oracle import pyoracle
+    dt = parity.TRAJ_DT["pfhub1a"]
+    cfg, st = parity.make_case("pfhub1a")
+    tend = 200 * dt
+    yref, _ = parity.oracle_trajectory(cfg, st, dt / 4, 800, scheme=1)
+    y = {k: (None if v is None else v.numpy().copy()) for k, v in st.items()}
+    o = pyoracle.Oracle(cfg)
+    rc, stats = o.integrate_adaptive(y, tend, dt, rtol=1e-6, atol=1e-8, max_krylov=30, max_newton=4, max_steps=2000)
+    o.close()
+    assert rc == 0, stats
+    assert abs(stats["t_reached"] - tend) < 1e-12 * tend
+    assert stats["steps"] < 120 and stats["largest_step"] > 3 * stats["smallest_step"], stats
+    assert np.abs(y["conc"] - yref["conc"]).max() < 2e-5, stats
+    assert abs(y["conc"].sum() - st["conc"].numpy().sum()) < 1e-10
+
+
+def test_adaptive_full_model_with_preconditioner():
+    """GG3D_HBSM over 120 explicit steps' worth of time with AMPE's default tolerances, preconditioned: finishes,
+    quaternions stay unit, composition is conserved, steps beyond the explicit limit are taken"""
+    from oracle import pyoracle
+    name = "gg3d_hbsm"
+    dt = parity.TRAJ_DT[name]
+    cfg, st = parity.make_case(name)
+    y = {k: (None if v is None else v.numpy().copy()) for k, v in st.items()}
+    o = pyoracle.Oracle(cfg)
+    o.set_preconditioner(2)
+    rc, stats = o.integrate_adaptive(y, 120 * dt, dt, max_krylov=10, max_newton=4)
+    o.close()
+    assert rc == 0, stats
+    assert stats["largest_step"] > 6 * dt, stats  # the explicit stability limit is ~5 dt
+    q = y["quat"].reshape(cfg.qlen, -1)
+    assert np.abs((q * q).sum(0) - 1.0).max() < 1e-14
+    assert abs(y["conc"].sum() - st["conc"].numpy().sum()) < 1e-9 * abs(st["conc"].numpy().sum())
