@@ -90,12 +90,13 @@ def test_quaternion_block_operator_and_solve(n, dx):
     h = pyoracle.HostMG(n, dx, with_s=True)
     h.set_quat(gamma, mob_g, 1, fc, 0)
     rhs = rng.standard_normal(shape)
-    z = g.solve(_cuda(rhs), ncycles=3, symmetrized=True).cpu().numpy()
-    zh = h.solve(rhs, ncycles=3, symmetrized=True)
+    z = g.solve(_cuda(rhs), ncycles=5, symmetrized=True).cpu().numpy()
+    zh = h.solve(rhs, ncycles=5, symmetrized=True)
     assert np.abs(z - zh).max() <= 1e-12 * np.abs(zh).max()
     s = np.sqrt(mob)
     res = rhs / s - pyoracle.quat_stencil_apply(n, dx, gamma, np.sqrt(mob_g), 1, fc, z / s)
-    assert np.linalg.norm(res) < 0.05 * np.linalg.norm(rhs / s)
+    # cell-to-cell random mobility and face coefficients: ~0.35 per cycle (0.005 after five on the CPU)
+    assert np.linalg.norm(res) < 0.02 * np.linalg.norm(rhs / s)
     g.close()
 
 
@@ -312,6 +313,7 @@ def test_one_block_tail_and_graph_replay_are_bit_identical(n, dx):
             stream.wait_stream(torch.cuda.current_stream())
         z = g.solve(rhs, ncycles=3, stream=stream)
         if mode == "graph":
+            stream.synchronize()
             z2 = torch.empty_like(z)
             z2.copy_(z)
             g.solve(rhs, ncycles=3, out=z, stream=stream)  # second call: replay
