@@ -22,6 +22,7 @@
 
 #include <cstdlib>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/ampe_b200_precond.h"
@@ -53,6 +54,10 @@ struct ampe_mg {
    int pre = 1, post = 1, coarse = 8;
    int launches = 0;
    int tail_level = -1;  // first level handled by the one-block tail kernel (-1: none)
+   // fused red-black sweep (mg_rb_tile_pass): per level the second u array of the ping-pong and the tile
+   // shape; t[0] == 0: the level uses the two colour half-sweeps
+   std::vector<double*> alt_u;
+   std::vector<ampe_mg_cell::TileShape> tile;
    // AMPE_B200_MG_GRAPH=1 (opt-in): the launches of one solve captured once per (rhs, soln, cycles, form)
    bool use_graph = false;
    cudaGraphExec_t graph_exec = nullptr;
@@ -307,11 +312,31 @@ __global__ void __launch_bounds__(TAIL_THREADS) mg_tail_kernel(TailLevels T, int
    }
 }
 
+// one red-black sweep in one pass: a block per tile, the tile of u (halo two) in shared memory
+__global__ void __launch_bounds__(MT) mg_rb_fused_kernel(Level L, const double* u_in, double* u_out, TileShape T, int nt0,
+                                                         int nt1)
+{
+   extern __shared__ double mg_tile[];
+   const int b = blockIdx.x;
+   const int t0 = b % nt0, t1 = (b / nt0) % nt1, t2 = b / (nt0 * nt1);
+   mg_rb_tile_pass(L, u_in, u_out, mg_tile, T, t0 * T.t[0], t1 * T.t[1], t2 * T.t[2], (int)threadIdx.x, (int)blockDim.x);
+}
+
 void smooth(ampe_mg* g, int l, int sweeps, cudaStream_t st)
 {
-   const Level& L = g->levels[l];
+   const Level L = g->levels[l];
    const long long nc = cells(L);
    for (int s = 0; s < sweeps; s++) {
+      if (g->tile[l].t[0] > 0) {
+         const TileShape T = g->tile[l];
+         Level& Lm = g->levels[l];
+         const int nt0 = Lm.n[0] / T.t[0], nt1 = Lm.n[1] / T.t[1], nt2 = Lm.n[2] / T.t[2];
+         const size_t smem = sizeof(double) * (T.t[0] + 4) * (T.t[1] + 4) * (Lm.ndim == 3 ? T.t[2] + 4 : 1);
+         mg_rb_fused_kernel<<<nt0 * nt1 * nt2, MT, smem, st>>>(Lm, Lm.u, g->alt_u[l], T, nt0, nt1);
+         std::swap(Lm.u, g->alt_u[l]);  // the sweep wrote the other array of the ping-pong
+         g->launches += 1;
+         continue;
+      }
       if (g->two_colour[l]) {
          mg_smooth_rb_kernel<<<grid_for(nc / 2), MT, 0, st>>>(L, 0);
          mg_smooth_rb_kernel<<<grid_for(nc / 2), MT, 0, st>>>(L, 1);
@@ -468,6 +493,32 @@ int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_sca
    }
    const char* graph_env = getenv("AMPE_B200_MG_GRAPH");
    g->use_graph = graph_env && graph_env[0] == '1';
+   // fused red-black sweeps on the levels above the tail whose extents the tile divides (AMPE_B200_MG_FUSED=0:
+   // off; off under graph capture, whose kernel arguments would freeze the ping-pong pointers)
+   const char* fused_env = getenv("AMPE_B200_MG_FUSED");
+   const bool fused = !(fused_env && fused_env[0] == '0') && !g->use_graph;
+   g->alt_u.assign(g->levels.size(), nullptr);
+   g->tile.assign(g->levels.size(), TileShape{{0, 0, 0}});
+   for (size_t l = 0; fused && l < g->levels.size(); l++) {
+      const Level& L = g->levels[l];
+      if (!g->two_colour[l] || cells(L) <= TAIL_CELLS || (g->tail_level >= 0 && (int)l >= g->tail_level)) continue;
+      auto pick = [](int n, int first) {
+         for (int t = first; t >= 2; t /= 2)
+            if (n % t == 0) return t;
+         return 0;
+      };
+      TileShape T;
+      T.t[0] = pick(L.n[0], ndim == 3 ? 32 : 64);
+      T.t[1] = pick(L.n[1], ndim == 3 ? 8 : 16);
+      T.t[2] = ndim == 3 ? pick(L.n[2], 8) : 1;
+      if (T.t[0] < 8 || T.t[1] < 2 || T.t[2] < 1) continue;  // slivers: the halo would dominate
+      if (cudaMalloc(&g->alt_u[l], sizeof(double) * cells(L)) != cudaSuccess) {
+         g->alt_u[l] = nullptr;
+         cudaGetLastError();
+         continue;
+      }
+      g->tile[l] = T;
+   }
    *out = g;
    return AMPE_OK;
 }
@@ -477,6 +528,7 @@ int ampe_mg_destroy(ampe_mg* g)
    if (!g) return AMPE_OK;
    if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec);
    for (double* b : g->blocks) cudaFree(b);
+   for (double* b : g->alt_u) cudaFree(b);
    for (double* b : g->own_c) cudaFree(b);
    for (double* b : g->own_m) cudaFree(b);
    for (int a = 0; a < 3; a++)

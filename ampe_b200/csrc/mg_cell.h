@@ -117,6 +117,106 @@ MG_HD void mg_smooth_cell(const Level& L, int i, int j, int k)
    L.u[o] += residual / diag;
 }
 
+// ---- one red-black sweep in ONE pass over a tile (fused smoother) ---------------------------------
+// The two colour half-sweeps each move every array in full (a 32 B sector holds two cells of each
+// colour).  Here a tile of TX x TY (x TZ) cells is staged with a halo of two into `tile` (shared
+// memory on the device), the red cells of the tile grown by one are updated in place, then the black
+// cells of the tile, and the tile is written to u_out: u_in is only read, so neighbouring tiles see old
+// values and the result is the one of the two half-sweeps bit for bit (the halo's red updates are
+// recomputed by the neighbour from the same data).  The caller swaps u_in / u_out afterwards.
+// Written as phases of thread-strided loops separated by MG_TILE_SYNC so that the host can run the very
+// same index arithmetic with one "thread" (tid 0 of 1).  Requires even extents (two-colouring).
+struct TileShape {
+   int t[3];  // tile extents (t[2] = 1 in 2D)
+};
+MG_HD int mg_wrap(int i, int n)
+{
+   i %= n;
+   return i < 0 ? i + n : i;
+}
+// Gauss-Seidel value of cell (gi,gj,gk) (global, in range) from the staged tile: same operation order
+// as mg_face_sums + mg_smooth_cell
+MG_HD double mg_gs_from_tile(const Level& L, const double* tile, int p0, int p1, int li, int lj, int lk, int gi, int gj,
+                             int gk)
+{
+   // tile index of local (li,lj,lk) with the halo of two: (li+2) + p0 ((lj+2) + p1 (lk+hz))
+   const int hz = L.ndim == 3 ? 2 : 0;
+   const long long tc = (long long)(li + 2) + (long long)p0 * ((lj + 2) + (long long)p1 * (lk + hz));
+   const long long o = mg_index(L, gi, gj, gk);
+   const double si = L.s ? L.s[o] : 1.0;
+   const double uc = tile[tc];
+   const double ui = si * uc;
+   double flux = 0.0, dsum = 0.0;
+   {
+      const long long ou = mg_index(L, mg_up(gi, L.n[0]), gj, gk), od = mg_index(L, mg_dn(gi, L.n[0]), gj, gk);
+      const double du = mg_d(L, 0, ou), dd = mg_d(L, 0, o);
+      const double uu = (L.s ? L.s[ou] : 1.0) * tile[tc + 1], ud = (L.s ? L.s[od] : 1.0) * tile[tc - 1];
+      flux += du * (uu - ui) - dd * (ui - ud);
+      dsum += du + dd;
+   }
+   {
+      const long long ou = mg_index(L, gi, mg_up(gj, L.n[1]), gk), od = mg_index(L, gi, mg_dn(gj, L.n[1]), gk);
+      const double du = mg_d(L, 1, ou), dd = mg_d(L, 1, o);
+      const double uu = (L.s ? L.s[ou] : 1.0) * tile[tc + p0], ud = (L.s ? L.s[od] : 1.0) * tile[tc - p0];
+      flux += du * (uu - ui) - dd * (ui - ud);
+      dsum += du + dd;
+   }
+   if (L.ndim == 3) {
+      const long long ou = mg_index(L, gi, gj, mg_up(gk, L.n[2])), od = mg_index(L, gi, gj, mg_dn(gk, L.n[2]));
+      const double du = mg_d(L, 2, ou), dd = mg_d(L, 2, o);
+      const long long pz = (long long)p0 * p1;
+      const double uu = (L.s ? L.s[ou] : 1.0) * tile[tc + pz], ud = (L.s ? L.s[od] : 1.0) * tile[tc - pz];
+      flux += du * (uu - ui) - dd * (ui - ud);
+      dsum += du + dd;
+   }
+   const double residual = L.f[o] - (mg_c(L, o) * uc + mg_m(L, o) * flux);
+   const double diag = mg_c(L, o) - mg_m(L, o) * si * dsum;
+   return uc + residual / diag;
+}
+
+#ifdef __CUDA_ARCH__
+#define MG_TILE_SYNC() __syncthreads()
+#else
+#define MG_TILE_SYNC() ((void)0)
+#endif
+
+// one tile with origin (o0,o1,o2) (multiples of the tile extents; extents of L are multiples of them too)
+MG_HD void mg_rb_tile_pass(const Level& L, const double* u_in, double* u_out, double* tile, TileShape T, int o0, int o1,
+                           int o2, int tid, int nthreads)
+{
+   const int hz = L.ndim == 3 ? 2 : 0;
+   const int p0 = T.t[0] + 4, p1 = T.t[1] + 4, p2 = T.t[2] + 2 * hz;
+   // phase 0: stage u_in with the halo of two (periodic images)
+   for (int t = tid; t < p0 * p1 * p2; t += nthreads) {
+      const int a = t % p0, b = (t / p0) % p1, c = t / (p0 * p1);
+      const int gi = mg_wrap(o0 + a - 2, L.n[0]), gj = mg_wrap(o1 + b - 2, L.n[1]);
+      const int gk = L.ndim == 3 ? mg_wrap(o2 + c - 2, L.n[2]) : 0;
+      tile[t] = u_in[mg_index(L, gi, gj, gk)];
+   }
+   MG_TILE_SYNC();
+   // phases 1, 2: red cells of the tile grown by one, then black cells of the tile, in place
+   for (int colour = 0; colour < 2; colour++) {
+      const int g = colour == 0 ? 1 : 0;  // growth of the region
+      const int gz = L.ndim == 3 ? g : 0;
+      const int e0 = T.t[0] + 2 * g, e1 = T.t[1] + 2 * g, e2 = T.t[2] + 2 * gz;
+      for (int t = tid; t < e0 * e1 * e2; t += nthreads) {
+         const int li = t % e0 - g, lj = (t / e0) % e1 - g, lk = t / (e0 * e1) - gz;
+         const int gi = mg_wrap(o0 + li, L.n[0]), gj = mg_wrap(o1 + lj, L.n[1]);
+         const int gk = L.ndim == 3 ? mg_wrap(o2 + lk, L.n[2]) : 0;
+         if (((gi + gj + gk) & 1) != colour) continue;
+         const double v = mg_gs_from_tile(L, tile, p0, p1, li, lj, lk, gi, gj, gk);
+         tile[(long long)(li + 2) + (long long)p0 * ((lj + 2) + (long long)p1 * (lk + hz))] = v;
+      }
+      MG_TILE_SYNC();
+   }
+   // phase 3: the tile goes to u_out
+   for (int t = tid; t < T.t[0] * T.t[1] * T.t[2]; t += nthreads) {
+      const int li = t % T.t[0], lj = (t / T.t[0]) % T.t[1], lk = t / (T.t[0] * T.t[1]);
+      u_out[mg_index(L, o0 + li, o1 + lj, L.ndim == 3 ? o2 + lk : 0)] =
+          tile[(long long)(li + 2) + (long long)p0 * ((lj + 2) + (long long)p1 * (lk + hz))];
+   }
+}
+
 // damped Jacobi for levels whose periodic wrap breaks the two-colouring (an odd extent):
 // u += omega r / diagonal with r computed beforehand by mg_residual_cell
 MG_HD void mg_jacobi_cell(const Level& L, double omega, int i, int j, int k)

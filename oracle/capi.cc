@@ -97,6 +97,11 @@ int oracle_mg_solve(void* g, const double* rhs, double* soln, int ncycles, int s
 }
 void oracle_mg_apply(void* g, const double* u, double* out) { ((HostMG*)g)->apply(u, out); }
 void oracle_mg_set_sweeps(void* g, int pre, int post, int coarse) { ((HostMG*)g)->setSweeps(pre, post, coarse); }
+int oracle_mg_set_fused(void* g, int on, long long min_cells)
+{
+   ((HostMG*)g)->setFused(on != 0, min_cells);
+   return ((HostMG*)g)->fusedLevels();
+}
 int oracle_mg_num_levels(void* g) { return ((HostMG*)g)->numLevels(); }
 void oracle_mg_level_extents(void* g, int level, int* n_out)
 {

@@ -304,10 +304,53 @@ void HostMG::setQuat(double gamma, const double* mobility, int ngm, const double
    buildCoarse();
 }
 
+void HostMG::setFused(bool on, long long min_cells)
+{
+   d_tile.assign(d_levels.size(), ampe_mg_cell::TileShape{{0, 0, 0}});
+   d_alt_u.resize(d_levels.size());
+   for (size_t l = 0; on && l < d_levels.size(); l++) {
+      const Level& L = d_levels[l];
+      const long long nc = (long long)L.n[0] * L.n[1] * L.n[2];
+      if (!d_two_colour[l] || nc <= min_cells) continue;
+      auto pick = [](int n, int first) {
+         for (int t = first; t >= 2; t /= 2)
+            if (n % t == 0) return t;
+         return 0;
+      };
+      ampe_mg_cell::TileShape T;
+      T.t[0] = pick(L.n[0], d_ndim == 3 ? 32 : 64);
+      T.t[1] = pick(L.n[1], d_ndim == 3 ? 8 : 16);
+      T.t[2] = d_ndim == 3 ? pick(L.n[2], 8) : 1;
+      if (T.t[0] < 8 || T.t[1] < 2 || T.t[2] < 1) continue;
+      d_alt_u[l].assign((size_t)nc, 0.0);
+      d_tile[l] = T;
+   }
+}
+
+int HostMG::fusedLevels() const
+{
+   int n = 0;
+   for (const auto& T : d_tile) n += T.t[0] > 0;
+   return n;
+}
+
 void HostMG::smooth(int l, int sweeps)
 {
-   const Level& L = d_levels[l];
+   Level& L = d_levels[l];
    for (int s = 0; s < sweeps; s++) {
+      if (!d_tile.empty() && d_tile[l].t[0] > 0) {
+         // the device runs one block per tile; here one "thread" per tile walks the same phases
+         const ampe_mg_cell::TileShape T = d_tile[l];
+         std::vector<double> tile((size_t)(T.t[0] + 4) * (T.t[1] + 4) * (L.ndim == 3 ? T.t[2] + 4 : 1));
+         double* alt = d_alt_u[l].data();
+         for (int o2 = 0; o2 < L.n[2]; o2 += T.t[2])
+            for (int o1 = 0; o1 < L.n[1]; o1 += T.t[1])
+               for (int o0 = 0; o0 < L.n[0]; o0 += T.t[0])
+                  ampe_mg_cell::mg_rb_tile_pass(L, L.u, alt, tile.data(), T, o0, o1, o2, 0, 1);
+         // ping-pong: the level's u lives in d_store; copy back instead of swapping owners
+         std::memcpy(L.u, alt, sizeof(double) * d_alt_u[l].size());
+         continue;
+      }
       if (d_two_colour[l]) {
          for (int colour = 0; colour < 2; colour++)
             MG_FOR_CELLS(L)

@@ -28,6 +28,10 @@ class HostMG
    void solve(const double* rhs, double* soln, int ncycles, bool symmetrized);
    void apply(const double* u, double* out) const;
    void setSweeps(int pre, int post, int coarse) { d_pre = pre, d_post = post, d_coarse = coarse; }
+   // one red-black sweep per pass over tiles (mg_rb_tile_pass), same tile choice as ampe_b200/csrc/mg.cu;
+   // min_cells: levels with fewer cells keep the colour half-sweeps (the device uses the tail threshold 4096)
+   void setFused(bool on, long long min_cells = 4096);
+   int fusedLevels() const;
    int numLevels() const { return (int)d_levels.size(); }
    const int* levelExtents(int l) const { return d_levels.at(l).n; }
    const double* levelArray(int level, int which) const;
@@ -48,6 +52,8 @@ class HostMG
    std::vector<std::array<std::vector<double>, 5>> d_coef;
    mutable std::vector<double> d_scratch;
    std::vector<bool> d_two_colour;
+   std::vector<ampe_mg_cell::TileShape> d_tile;
+   std::vector<std::vector<double>> d_alt_u;
 };
 
 int precond_setup(Ctx* c, double gamma, int ncycles, bool has_dquatdphi);

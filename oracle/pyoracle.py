@@ -127,6 +127,8 @@ def lib(perf=False):
         L.oracle_mg_solve.argtypes = [vp, vp, vp, ci, ci]
         L.oracle_mg_apply.argtypes = [vp, vp, vp]
         L.oracle_mg_set_sweeps.argtypes = [vp, ci, ci, ci]
+        L.oracle_mg_set_fused.restype = ci
+        L.oracle_mg_set_fused.argtypes = [vp, ci, C.c_longlong]
         L.oracle_mg_num_levels.restype = ci
         L.oracle_mg_num_levels.argtypes = [vp]
         L.oracle_mg_level_extents.argtypes = [vp, ci, vp]
@@ -333,6 +335,11 @@ class HostMG:
 
     def set_sweeps(self, pre, post, coarse):
         self.L.oracle_mg_set_sweeps(self.h, pre, post, coarse)
+
+    def set_fused(self, on=True, min_cells=4096):
+        """one red-black sweep per pass over tiles (mg_rb_tile_pass) on the levels with more than min_cells
+        cells; returns the number of levels that use it"""
+        return self.L.oracle_mg_set_fused(self.h, 1 if on else 0, int(min_cells))
 
     def num_levels(self):
         return self.L.oracle_mg_num_levels(self.h)

@@ -289,14 +289,16 @@ def test_reference_kat_phasefac_on_the_device():
 @pytest.mark.parametrize("n,dx", [((256, 192), (1.0, 1.0)), ((64, 32, 48), (1.0, 1.0, 1.0)), ((48, 40), (1.0, 0.5))])
 def test_one_block_tail_and_graph_replay_are_bit_identical(n, dx):
     """the coarse levels inside one block (default) == one launch per phase (AMPE_B200_MG_TAIL=0), bit for bit,
-    with fewer launches; the captured solve (AMPE_B200_MG_GRAPH=1, explicit stream) replays to the same bits"""
+    with fewer launches; the fused red-black tile pass (default) == the two colour half-sweeps
+    (AMPE_B200_MG_FUSED=0); the captured solve (AMPE_B200_MG_GRAPH=1, explicit stream) replays to the same bits"""
     from ampe_b200.precond import LevelSolver
     shape, m, c, lows, d = _random_elliptic(n, 17)
     d = [30.0 * x for x in d]
     rhs = _cuda(np.random.default_rng(18).standard_normal(shape))
     outs, launches = {}, {}
-    for mode, env in (("tail", {}), ("levels", {"AMPE_B200_MG_TAIL": "0"}), ("graph", {"AMPE_B200_MG_GRAPH": "1"})):
-        old = {k: os.environ.get(k) for k in ("AMPE_B200_MG_TAIL", "AMPE_B200_MG_GRAPH")}
+    for mode, env in (("tail", {}), ("levels", {"AMPE_B200_MG_TAIL": "0"}), ("unfused", {"AMPE_B200_MG_FUSED": "0"}),
+                      ("graph", {"AMPE_B200_MG_GRAPH": "1"})):
+        old = {k: os.environ.get(k) for k in ("AMPE_B200_MG_TAIL", "AMPE_B200_MG_GRAPH", "AMPE_B200_MG_FUSED")}
         for k in old:
             os.environ.pop(k, None)
         os.environ.update(env)
@@ -323,6 +325,7 @@ def test_one_block_tail_and_graph_replay_are_bit_identical(n, dx):
         outs[mode], launches[mode] = z.clone(), g.last_launch_count()
         g.close()
     assert torch.equal(outs["tail"], outs["levels"])
+    assert torch.equal(outs["tail"], outs["unfused"])
     assert torch.equal(outs["tail"], outs["graph"])
     assert launches["tail"] < launches["levels"]
 

@@ -433,3 +433,33 @@ def test_reference_kat_phasefac():
     z = mg.solve(rhs, ncycles=10)
     err = np.abs(z - exact)[0, :, :k["nc"]].max()
     assert err < 1.0e-2, err
+
+
+# ---- fused red-black sweep (one pass over tiles, halo of two, ping-pong) ---------------------------------------
+@pytest.mark.parametrize("n,dx,quat", [((128, 96), (0.3, 0.2), False), ((64, 16), (1.0, 1.0), False),
+                                       ((32, 24, 16), (0.5, 0.4, 0.25), False), ((64, 8, 8), (1.0, 1.0, 1.0), False),
+                                       ((96, 80), (0.3, 0.2), True), ((32, 16, 24), (1.0, 1.0, 1.0), True)])
+def test_fused_red_black_pass_is_bit_identical(n, dx, quat):
+    """mg_rb_tile_pass (what the device runs with one block per tile) == the two colour half-sweeps, bit for
+    bit, on every level it applies to -- including tiles as wide as the level (halo cells alias interior cells
+    through the periodic wrap) and the quaternion block's column scale"""
+    ndim = len(n)
+    rng = np.random.default_rng(51)
+    shape = (n[2] if ndim == 3 else 1, n[1], n[0])
+    rhs = rng.standard_normal(shape)
+    outs = []
+    for fused in (False, True):
+        if quat:
+            mob = 0.1 + np.random.default_rng(52).random(shape)
+            fc = [_side_from_lower(-(5.0 + 20.0 * np.random.default_rng(53 + a).random(shape)), 2 - a) for a in range(ndim)]
+            mg = pyoracle.HostMG(n, dx, with_s=True)
+            mg.set_quat(0.37, _ghosted(mob, 1, ndim), 1, fc, 0)
+        else:
+            _, m, c, lows, d = _random_elliptic(n, 54)
+            mg = pyoracle.HostMG(n, dx)
+            mg.set_elliptic(m=m, ngm=0, c=c, ngc=0, d=[20.0 * x for x in d], ngd=0)
+        mg.set_sweeps(2, 1, 8)
+        if fused:
+            assert mg.set_fused(True, min_cells=256) >= 1
+        outs.append(mg.solve(rhs, ncycles=3, symmetrized=quat))
+    assert np.array_equal(outs[0], outs[1])

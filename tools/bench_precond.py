@@ -1,8 +1,9 @@
 """Timing of the block-preconditioner solve (csrc/mg.cu) on one GPU: ms per V-cycle and per level-0
 half sweep at the BASELINE workload sizes, against the HBM roofline.  One JSON line per case.
 Algorithmic bytes of the benchmarked block (M and C constants, D an array per direction --
-the composition block): a colour half-sweep touches u (read + write), f and ND face arrays for half of the
-cells -> (3 + ND) * 8 B per updated cell; a V(1,1) cycle = 4 half-sweeps + residual ((2 + ND) * 8 B read +
+the composition block): a sweep reads u, f and ND face arrays and writes u -> (3 + ND) * 8 B per cell (what the
+fused tile pass moves; the two colour half-sweeps move twice that at sector granularity); a V(1,1) cycle = 2
+sweeps = 4 half-sweeps of (3 + ND) * 8 / 2 B + residual ((2 + ND) * 8 B read +
 8 B write per cell) + restriction (8 B / cell read) + prolongation (16 B / cell) on level 0, times
 1 / (1 - 2^-ND) for the coarse levels.
 usage (GPU box): python tools/bench_precond.py [--cases 2d:2048x2048,3d:256x256x256] [--cycles 10]"""
@@ -75,7 +76,8 @@ def main():
                           "launches_per_solve": launches, "algorithmic_bytes_per_vcycle": bytes_cycle,
                           "achieved_gbs": gbs, "hbm_peak_gbs": hbm, "peak_source": src, "frac": gbs / hbm,
                           "rel_residual_after_2_cycles": res0, "cells": ncell,
-                          "tail": os.environ.get("AMPE_B200_MG_TAIL", "1"), "graph": os.environ.get("AMPE_B200_MG_GRAPH", "0")}))
+                          "tail": os.environ.get("AMPE_B200_MG_TAIL", "1"), "graph": os.environ.get("AMPE_B200_MG_GRAPH", "0"),
+                          "fused": os.environ.get("AMPE_B200_MG_FUSED", "1")}))
         g.close()
 
 
