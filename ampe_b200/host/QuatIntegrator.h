@@ -587,7 +587,12 @@ class QuatIntegrator
    {
       (void)time;
       const ampe_rhs_config& p = d_cfg;
-      if (!p.with_unsteady_temperature) fillConstant(d_temperature_scratch_id, p.T_uniform);
+      if (!p.with_unsteady_temperature && !d_uniform_temperature_filled) {
+         // setTemperatureField with a uniform T: the scratch array never changes, fill it once (the
+         // preconditioner set-up comes through here at every Newton iteration)
+         fillConstant(d_temperature_scratch_id, p.T_uniform);
+         d_uniform_temperature_filled = true;
+      }
       if (p.with_phase) fillScratchField(y->phase, d_phase_scratch_id, 1);
       if (p.qlen > 0) fillScratchField(y->quat, d_quat_scratch_id, p.qlen);
       if (p.with_concentration) fillScratchField(y->conc, d_conc_scratch_id, 1);
@@ -672,6 +677,7 @@ class QuatIntegrator
    std::shared_ptr<PhaseConcentrationsStrategy> d_phase_conc_strategy;
    std::shared_ptr<TemperatureRHSStrategy> d_temperature_rhs_strategy;
    // block preconditioners (named like the reference's members, QuatIntegrator.h)
+   bool d_uniform_temperature_filled = false;
    bool d_use_preconditioner = false;
    int d_precond_cycles = 0;
    long d_precond_setups = 0, d_precond_solves = 0;

@@ -490,7 +490,9 @@ class QuatMobilityStrategy
    explicit QuatMobilityStrategy(const ampe_rhs_config& cfg) : d_cfg(cfg) {}
    void computePhaseMobility(std::shared_ptr<PatchHierarchy> h, int, int mobility_id)
    {
-      // computeUniformPhaseMobility: fill with phi_mobility
+      // computeUniformPhaseMobility: fill with phi_mobility (a constant: once per array)
+      if (d_uniform_filled_id == mobility_id) return;
+      d_uniform_filled_id = mobility_id;
       for (auto& patch : *h->getPatchLevel(0)) {
          auto m = patch->cell<double>(mobility_id);
          std::vector<double> v(m->size(), d_cfg.phi_mobility);
@@ -527,6 +529,7 @@ class QuatMobilityStrategy
 
  private:
    ampe_rhs_config d_cfg;
+   int d_uniform_filled_id = -1;
 };
 
 // ---- DerivDiffusionCoeffForQuat (DerivDiffusionCoeffForQuat.cc:60-148) ---------------------------
