@@ -199,11 +199,14 @@ MG_HD void mg_rb_tile_pass(const Level& L, const double* u_in, double* u_out, do
       const int g = colour == 0 ? 1 : 0;  // growth of the region
       const int gz = L.ndim == 3 ? g : 0;
       const int e0 = T.t[0] + 2 * g, e1 = T.t[1] + 2 * g, e2 = T.t[2] + 2 * gz;
-      for (int t = tid; t < e0 * e1 * e2; t += nthreads) {
-         const int li = t % e0 - g, lj = (t / e0) % e1 - g, lk = t / (e0 * e1) - gz;
+      const int h0 = e0 >> 1;  // e0 is even: every row of the region holds h0 cells of each colour
+      for (int t = tid; t < h0 * e1 * e2; t += nthreads) {
+         const int ii = t % h0, lj = (t / h0) % e1 - g, lk = t / (h0 * e1) - gz;
+         // first cell of the colour in this row: (o0 + li + o1 + lj + o2 + lk) & 1 == colour, li = 2 ii + a - g
+         const int a = (colour + o0 + g + o1 + lj + o2 + lk + 8) & 1;
+         const int li = 2 * ii + a - g;
          const int gi = mg_wrap(o0 + li, L.n[0]), gj = mg_wrap(o1 + lj, L.n[1]);
          const int gk = L.ndim == 3 ? mg_wrap(o2 + lk, L.n[2]) : 0;
-         if (((gi + gj + gk) & 1) != colour) continue;
          const double v = mg_gs_from_tile(L, tile, p0, p1, li, lj, lk, gi, gj, gk);
          tile[(long long)(li + 2) + (long long)p0 * ((lj + 2) + (long long)p1 * (lk + hz))] = v;
       }
