@@ -138,6 +138,16 @@ __global__ void mg_restrict_kernel(Level F, Level C)
       mg_restrict_cell(F, C, i, j, k);
    }
 }
+__global__ void mg_restrict_residual_kernel(Level F, Level C)
+{
+   const long long total = (long long)C.n[0] * C.n[1] * C.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x) {
+      int i, j, k;
+      decode(C, idx, i, j, k);
+      mg_restrict_residual_cell(F, C, i, j, k);
+   }
+}
 __global__ void mg_coarsen_kernel(Level F, Level C)
 {
    const long long total = (long long)C.n[0] * C.n[1] * C.n[2];
@@ -355,9 +365,9 @@ void vcycle(ampe_mg* g, cudaStream_t st)
    const int top = (g->tail_level >= 0) ? g->tail_level : nl - 1;
    for (int l = 0; l < top; l++) {
       smooth(g, l, g->pre, st);
-      mg_residual_kernel<<<grid_for(cells(g->levels[l])), MT, 0, st>>>(g->levels[l]);
-      mg_restrict_kernel<<<grid_for(cells(g->levels[l + 1])), MT, 0, st>>>(g->levels[l], g->levels[l + 1]);
-      g->launches += 2;
+      // residual and restriction in one pass (r is neither written nor re-read)
+      mg_restrict_residual_kernel<<<grid_for(cells(g->levels[l + 1])), MT, 0, st>>>(g->levels[l], g->levels[l + 1]);
+      g->launches += 1;
    }
    if (g->tail_level >= 0) {
       TailLevels T;

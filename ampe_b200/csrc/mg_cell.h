@@ -247,6 +247,23 @@ MG_HD void mg_restrict_cell(const Level& F, const Level& C, int I, int J, int K)
    C.u[o] = 0.0;
 }
 
+// the two above in one pass: the coarse cell computes the residuals of its children itself (same
+// expressions, same order of accumulation: bit-identical), so r is neither written nor re-read
+MG_HD void mg_restrict_residual_cell(const Level& F, const Level& C, int I, int J, int K)
+{
+   const int nk = F.ndim == 3 ? 2 : 1;
+   double acc = 0.0;
+   for (int c = 0; c < nk; c++)
+      for (int b = 0; b < 2; b++)
+         for (int a = 0; a < 2; a++) {
+            const int i = 2 * I + a, j = 2 * J + b, k = (F.ndim == 3 ? 2 * K : 0) + c;
+            acc += F.f[mg_index(F, i, j, k)] - mg_apply_cell(F, F.u, i, j, k);
+         }
+   const long long o = mg_index(C, I, J, K);
+   C.f[o] = acc * (F.ndim == 3 ? 0.125 : 0.25);
+   C.u[o] = 0.0;
+}
+
 // coarse coefficients of cell (I,J,K): cell fields are the children's mean; the lower face in
 // direction a is the mean of the fine faces it covers, divided by 4 (h doubles)
 MG_HD void mg_coarsen_cell(const Level& F, const Level& C, int I, int J, int K)

@@ -306,6 +306,7 @@ void HostMG::setQuat(double gamma, const double* mobility, int ngm, const double
 
 void HostMG::setFused(bool on, long long min_cells)
 {
+   d_fused_restriction = on;
    d_tile.assign(d_levels.size(), ampe_mg_cell::TileShape{{0, 0, 0}});
    d_alt_u.resize(d_levels.size());
    for (size_t l = 0; on && l < d_levels.size(); l++) {
@@ -368,8 +369,12 @@ void HostMG::vcycle()
    for (int l = 0; l + 1 < nl; l++) {
       smooth(l, d_pre);
       const Level &F = d_levels[l], &Cl = d_levels[l + 1];
-      MG_FOR_CELLS(F) ampe_mg_cell::mg_residual_cell(F, i, j, k);
-      MG_FOR_CELLS(Cl) ampe_mg_cell::mg_restrict_cell(F, Cl, i, j, k);
+      if (d_fused_restriction) {
+         MG_FOR_CELLS(Cl) ampe_mg_cell::mg_restrict_residual_cell(F, Cl, i, j, k);
+      } else {
+         MG_FOR_CELLS(F) ampe_mg_cell::mg_residual_cell(F, i, j, k);
+         MG_FOR_CELLS(Cl) ampe_mg_cell::mg_restrict_cell(F, Cl, i, j, k);
+      }
    }
    smooth(nl - 1, d_coarse);
    for (int l = nl - 2; l >= 0; l--) {

@@ -53,6 +53,7 @@ class HostMG
    mutable std::vector<double> d_scratch;
    std::vector<bool> d_two_colour;
    std::vector<ampe_mg_cell::TileShape> d_tile;
+   bool d_fused_restriction = false;  // residual + restriction in one pass (mg_restrict_residual_cell)
    std::vector<std::vector<double>> d_alt_u;
 };
 

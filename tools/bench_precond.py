@@ -3,8 +3,8 @@ half sweep at the BASELINE workload sizes, against the HBM roofline.  One JSON l
 Algorithmic bytes of the benchmarked block (M and C constants, D an array per direction --
 the composition block): a sweep reads u, f and ND face arrays and writes u -> (3 + ND) * 8 B per cell (what the
 fused tile pass moves; the two colour half-sweeps move twice that at sector granularity); a V(1,1) cycle = 2
-sweeps = 4 half-sweeps of (3 + ND) * 8 / 2 B + residual ((2 + ND) * 8 B read +
-8 B write per cell) + restriction (8 B / cell read) + prolongation (16 B / cell) on level 0, times
+sweeps + the fused residual-restriction ((2 + ND) * 8 B read per cell) + prolongation (16 B / cell)
+on level 0, times
 1 / (1 - 2^-ND) for the coarse levels.
 usage (GPU box): python tools/bench_precond.py [--cases 2d:2048x2048,3d:256x256x256] [--cycles 10]"""
 import argparse
@@ -69,7 +69,7 @@ def main():
             best = ms if best is None else min(best, ms)
         launches = g.last_launch_count()
         per_cycle = best / a.cycles
-        lvl0 = 4 * 0.5 * (3 + nd) * 8 + ((2 + nd) * 8 + 8) + 8 + 16
+        lvl0 = 2 * (3 + nd) * 8 + (2 + nd) * 8 + 16
         bytes_cycle = ncell * lvl0 / (1.0 - 0.5 ** nd)
         gbs = bytes_cycle / (per_cycle * 1e-3) / 1e9
         print(json.dumps({"case": case, "levels": g.num_levels(), "ms_per_vcycle": per_cycle,
