@@ -236,12 +236,70 @@ __global__ void ch_energy_kernel(const __grid_constant__ ChArgs A, double* parti
    }
 }
 
+// ---- scalar diagnostics (QuatModel::printScalarDiagnostics, QuatModel.cc:2543-2690) ---------------
+// one pass over phi, c, T: per block sum |phi|, sum phi, sum c, sum |c phi|, sum T, max c, max T, min T
+__global__ void scalar_diag_kernel(const double* phi, const double* conc, const double* T, long long n,
+                                   double* partial)
+{
+   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, mc = -1.0e300, mt = -1.0e300, nt = 1.0e300;
+   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const double p = phi ? phi[i] : 1.0, cc = conc ? conc[i] : 0.0;
+      a0 += fabs(p);
+      a1 += p;
+      a2 += cc;
+      a3 += fabs(cc * p);
+      mc = fmax(mc, cc);
+      if (T) {
+         const double t = T[i];
+         a4 += t;
+         mt = fmax(mt, t);
+         nt = fmin(nt, t);
+      }
+   }
+   __shared__ double red[8][VT / 32];
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) {
+      a0 += __shfl_down_sync(0xffffffffu, a0, o);
+      a1 += __shfl_down_sync(0xffffffffu, a1, o);
+      a2 += __shfl_down_sync(0xffffffffu, a2, o);
+      a3 += __shfl_down_sync(0xffffffffu, a3, o);
+      a4 += __shfl_down_sync(0xffffffffu, a4, o);
+      mc = fmax(mc, __shfl_down_sync(0xffffffffu, mc, o));
+      mt = fmax(mt, __shfl_down_sync(0xffffffffu, mt, o));
+      nt = fmin(nt, __shfl_down_sync(0xffffffffu, nt, o));
+   }
+   if (threadIdx.x % 32 == 0) {
+      const int w = threadIdx.x / 32;
+      red[0][w] = a0, red[1][w] = a1, red[2][w] = a2, red[3][w] = a3, red[4][w] = a4;
+      red[5][w] = mc, red[6][w] = mt, red[7][w] = nt;
+   }
+   __syncthreads();
+   if (threadIdx.x < 8) {
+      const int v = threadIdx.x;
+      double r = red[v][0];
+      for (int w = 1; w < VT / 32; w++) r = v < 5 ? r + red[v][w] : (v == 7 ? fmin(r, red[v][w]) : fmax(r, red[v][w]));
+      partial[(long long)blockIdx.x * 8 + v] = r;
+   }
+}
+// lane v < 8 folds value v over the blocks in block order (deterministic)
+__global__ void scalar_diag_final_kernel(const double* partial, long long nblocks, double* out)
+{
+   const int v = threadIdx.x;
+   if (v >= 8) return;
+   double r = partial[v];
+   for (long long b = 1; b < nblocks; b++) {
+      const double t = partial[b * 8 + v];
+      r = v < 5 ? r + t : (v == 7 ? fmin(r, t) : fmax(r, t));
+   }
+   out[v] = r;
+}
+
 int ensure_scratch(ampe_rhs_ctx* c, long long nblocks)
 {
    if (nblocks > c->partials_cap) {
       cudaFree(c->partials);
       c->partials = nullptr;
-      CUDA_OKV(cudaMalloc(&c->partials, (size_t)nblocks * 6 * sizeof(double)));
+      CUDA_OKV(cudaMalloc(&c->partials, (size_t)nblocks * 8 * sizeof(double)));
       c->partials_cap = nblocks;
    }
    if (!c->red_out) CUDA_OKV(cudaMalloc(&c->red_out, 8 * sizeof(double)));
@@ -489,5 +547,52 @@ extern "C" int ampe_integrate_fixed(ampe_rhs_ctx* c, const ampe_rhs_fields* y, c
       t += dt;
    }
    CUDA_OKV(cudaGetLastError());
+   return AMPE_OK;
+}
+
+// QuatModel::printScalarDiagnostics (QuatModel.cc:2543-2690) on this rank's cells.  out[12]: domain volume,
+// volume of solid (evaluateVolumeSolid: L1 norm of phi), its fraction, integral concentration
+// (evaluateIntegralConcentration), max concentration, integral phase concentration
+// (evaluateIntegralPhaseConcentration: L1 norm of c phi), Cex = (cphi - c0 vphi) / c0V0, min / max / average
+// temperature, thermal energy (computeThermalEnergy: -L int phi + int cp T), 0
+extern "C" int ampe_scalar_diagnostics(ampe_rhs_ctx* c, const ampe_rhs_fields* y, double* out, void* stream)
+{
+   if (!c || !y || !out) return ampe_set_err(AMPE_EINVAL, "null argument");
+   const Params& p = c->p;
+   const ampe_rhs_config& cfg = c->cfg;
+   if ((p.with_phase && !y->phase) || (p.with_conc && !y->conc) || (p.with_T && !y->temperature))
+      return ampe_set_err(AMPE_EINVAL, "scalar diagnostics: a component of y is NULL");
+   cudaStream_t st = (cudaStream_t)stream;
+   const int blocks = (int)((c->ncell + VT - 1) / VT < RED_BLOCKS ? (c->ncell + VT - 1) / VT : RED_BLOCKS);
+   int rc = ensure_scratch(c, RED_BLOCKS);
+   if (rc) return rc;
+   scalar_diag_kernel<<<blocks, VT, 0, st>>>(p.with_phase ? y->phase : nullptr, p.with_conc ? y->conc : nullptr,
+                                            p.with_T ? y->temperature : nullptr, c->ncell, c->partials);
+   scalar_diag_final_kernel<<<1, 32, 0, st>>>(c->partials, blocks, c->red_out);
+   CUDA_OKV(cudaGetLastError());
+   double r[8];
+   CUDA_OKV(cudaMemcpyAsync(r, c->red_out, sizeof(r), cudaMemcpyDeviceToHost, st));
+   CUDA_OKV(cudaStreamSynchronize(st));
+   double dv = 1.0;
+   for (int d = 0; d < cfg.ndim; d++) dv *= cfg.dx[d];
+   const double vol = dv * (double)c->ncell;
+   for (int n = 0; n < 12; n++) out[n] = 0.0;
+   out[0] = vol;
+   const double vphi = p.with_phase ? r[0] * dv : vol;  // QuatModel.cc:2606
+   out[1] = vphi;
+   out[2] = vphi / vol;
+   if (p.with_conc) {
+      const double c0V0 = r[2] * dv, cphi = r[3] * dv, c0 = c0V0 / vol;
+      out[3] = c0V0;
+      out[4] = r[5];
+      out[5] = cphi;
+      out[6] = (cphi - c0 * vphi) / c0V0;
+   }
+   if (p.with_T) {
+      out[7] = r[7], out[8] = r[6], out[9] = r[4] * dv / vol;
+      out[10] = (p.with_phase ? -1. * cfg.latent_heat * (r[1] * dv) : 0.0) + cfg.cp * (r[4] * dv);
+   } else {
+      out[7] = out[8] = out[9] = cfg.T_uniform;
+   }
    return AMPE_OK;
 }

@@ -76,6 +76,8 @@ def load():
     L.ampe_integrate_fixed.argtypes = [vp, pf, pf, pf, dbl, dbl, ci, ci, vp]
     L.ampe_energy_eval.restype = ci
     L.ampe_energy_eval.argtypes = [vp, pf, pd, vp]
+    L.ampe_scalar_diagnostics.restype = ci
+    L.ampe_scalar_diagnostics.argtypes = [vp, pf, pd, vp]
     L.ampe_apply_projection.restype = ci
     L.ampe_apply_projection.argtypes = [vp, pf, pf, pf, vp]
     L.ampe_rhs_compute_symmetry_rotations.restype = ci

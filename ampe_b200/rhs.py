@@ -162,6 +162,19 @@ class QuatIntegratorRHS:
         names = ("total", "phase", "orient", "qint", "well", "free")
         return {k: out[i] for i, k in enumerate(names)}
 
+    DIAGNOSTICS = ("volume", "volume_solid", "solid_fraction", "integral_concentration", "max_concentration",
+                   "integral_phase_concentration", "cex", "min_temperature", "max_temperature",
+                   "average_temperature", "thermal_energy")
+
+    def printScalarDiagnostics(self, y):
+        """QuatModel::printScalarDiagnostics (QuatModel.cc:2543-2690): the scalars the reference prints every
+        d_scalar_diag_interval -- volume fraction of solid, integral / max concentration, Cex, temperature
+        extrema and average, thermal energy -- as a dict (this rank's cells)"""
+        out = (C.c_double * 12)()
+        fy = y.fields()
+        check(self.L.ampe_scalar_diagnostics(self.h, C.byref(fy), out, self._stream()), "printScalarDiagnostics")
+        return {k: out[i] for i, k in enumerate(self.DIAGNOSTICS)}
+
     def applyProjection(self, time, y, corr, epsProj, err):
         """QuatIntegrator::applyProjection (QuatIntegrator.cc:3911-3962): corr <- 0 except the
         quaternion part, where y + corr is normalised; err loses its component along q.  Returns 0."""

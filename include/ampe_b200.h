@@ -236,6 +236,13 @@ int ampe_integrate_fixed(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, const ampe
  * sum [w (c-ca)^2 (cb-c)^2 + kappa/2 |grad c|^2] dV: out[0] total, [1] gradient, [4] well.   */
 int ampe_energy_eval(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, double* out, void* stream);
 
+/* QuatModel::printScalarDiagnostics (QuatModel.cc:2543-2690), this rank's cells.  out[12] (host): domain
+ * volume, volume of solid (evaluateVolumeSolid, QuatModel.cc:5170: L1 norm of phi), its fraction, integral
+ * concentration (:5106), max concentration, integral phase concentration (:5130: L1 norm of c phi),
+ * Cex = (cphi - c0 vphi) / c0V0 (:2655), min / max / average temperature, thermal energy
+ * (computeThermalEnergy, :5373: -L int phi + int cp T), 0.  A multi-rank caller combines the ranks.   */
+int ampe_scalar_diagnostics(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, double* out, void* stream);
+
 /* ---- the CVODE projection hook.
  * QuatIntegrator::applyProjection(time, y, corr, epsProj, err) (QuatIntegrator.cc:3911-3962,
  * CVODEAbstractFunctions.h applyProjection): every evolved component of corr is zeroed; when the

@@ -26,6 +26,10 @@ void oracle_get_phase_concentrations(void* c, double* cl, double* ca)
    get_phase_concentrations((Ctx*)c, cl, ca);
 }
 int oracle_energy(void* c, const ampe_rhs_fields* y, double* out) { return energy((Ctx*)c, y, out); }
+int oracle_scalar_diagnostics(void* c, const ampe_rhs_fields* y, double* out)
+{
+   return scalar_diagnostics((Ctx*)c, y, out);
+}
 // ---- block preconditioners (precond.cc) --------------------------------------------------------
 // ncycles > 0: oracle_integrate_implicit runs right-preconditioned GMRES with that many V-cycles
 void oracle_set_preconditioner(void* c, int ncycles, int has_dquatdphi)

@@ -55,5 +55,6 @@ void compute_conc_flux_kks_ebs(Ctx* c);
 
 // scalar energy diagnostics (energy.cc)
 int energy(Ctx* c, const ampe_rhs_fields* y, double* out);
+int scalar_diagnostics(Ctx* c, const ampe_rhs_fields* y, double* out);
 
 }  // namespace oracle

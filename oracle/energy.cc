@@ -261,4 +261,61 @@ int energy(Ctx* c, const ampe_rhs_fields* y, double* out)
    return status;
 }
 
+// QuatModel::printScalarDiagnostics (QuatModel.cc:2543-2690) on one uniform level: the weights of
+// HierarchyCellDataOpsReal::{L1Norm, integral} are the cell volume.  out[12]: see ampe_scalar_diagnostics.
+int scalar_diagnostics(Ctx* c, const ampe_rhs_fields* y, double* out)
+{
+   const ampe_rhs_config& p = c->cfg;
+   size_t ncell = 1;
+   double weight = 1.0;
+   for (int d = 0; d < p.ndim; d++) {
+      ncell *= (size_t)p.n[d];
+      weight = weight * p.dx[d];
+   }
+   for (int n = 0; n < 12; n++) out[n] = 0.0;
+   const double vol = weight * (double)ncell;
+   out[0] = vol;
+   double vphi = vol;  // QuatModel.cc:2606
+   double sum_phi = 0.0;
+   if (p.with_phase) {
+      // evaluateVolumeSolid (:5170): L1Norm(phase, weight)
+      double l1 = 0.0;
+      for (size_t i = 0; i < ncell; i++) {
+         l1 = l1 + fabs(y->phase[i]) * weight;
+         sum_phi = sum_phi + y->phase[i] * weight;
+      }
+      vphi = l1;
+   }
+   out[1] = vphi;
+   out[2] = vphi / vol;
+   if (p.with_concentration) {
+      // evaluateIntegralConcentration (:5106), max, evaluateIntegralPhaseConcentration (:5130)
+      double c0V0 = 0.0, cmax = y->conc[0], cphi = 0.0;
+      for (size_t i = 0; i < ncell; i++) {
+         c0V0 = c0V0 + y->conc[i] * weight;
+         if (y->conc[i] > cmax) cmax = y->conc[i];
+         const double prod = y->conc[i] * (p.with_phase ? y->phase[i] : 1.0);
+         cphi = cphi + fabs(prod) * weight;
+      }
+      const double c0 = c0V0 / vol;
+      out[3] = c0V0, out[4] = cmax, out[5] = cphi;
+      out[6] = (cphi - c0 * vphi) / c0V0;  // :2655
+   }
+   if (p.with_unsteady_temperature) {
+      double tmin = y->temperature[0], tmax = y->temperature[0], tint = 0.0, cenergy = 0.0;
+      for (size_t i = 0; i < ncell; i++) {
+         const double t = y->temperature[i];
+         if (t < tmin) tmin = t;
+         if (t > tmax) tmax = t;
+         tint = tint + t * weight;
+         cenergy = cenergy + (p.cp * t) * weight;  // computeThermalEnergy (:5373): multiply(cp, T), integral
+      }
+      out[7] = tmin, out[8] = tmax, out[9] = tint / vol;
+      out[10] = (p.with_phase ? sum_phi * (-1. * p.latent_heat) : 0.0) + cenergy;
+   } else {
+      out[7] = out[8] = out[9] = p.T_uniform;
+   }
+   return 0;
+}
+
 }  // namespace oracle

@@ -53,6 +53,8 @@ def lib(perf=False):
         L.oracle_get_phase_concentrations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_energy.restype = C.c_int
         L.oracle_energy.argtypes = [C.c_void_p, C.POINTER(_abi.RhsFields), C.c_void_p]
+        L.oracle_scalar_diagnostics.restype = C.c_int
+        L.oracle_scalar_diagnostics.argtypes = [C.c_void_p, C.POINTER(_abi.RhsFields), C.c_void_p]
         for f in ("interp_func", "deriv_interp_func", "second_deriv_interp_func", "well_func",
                   "deriv_well_func"):
             fn = getattr(L, "oracle_" + f)
@@ -196,6 +198,16 @@ class Oracle:
         out = np.zeros(8)
         st = self.L.oracle_energy(self.h, C.byref(_fields(y)), _ptr(out))
         return st, out
+
+    DIAGNOSTICS = ("volume", "volume_solid", "solid_fraction", "integral_concentration", "max_concentration",
+                   "integral_phase_concentration", "cex", "min_temperature", "max_temperature",
+                   "average_temperature", "thermal_energy")
+
+    def scalar_diagnostics(self, y):
+        """QuatModel::printScalarDiagnostics: dict of the DIAGNOSTICS"""
+        out = np.zeros(12)
+        assert self.L.oracle_scalar_diagnostics(self.h, C.byref(_fields(y)), _ptr(out)) == 0
+        return dict(zip(self.DIAGNOSTICS, out.tolist()))
 
     def integrate_implicit(self, y, dt, nsteps, t0=0.0, order=2, max_krylov=5, max_newton=3, rtol=3e-6,
                            atol=3e-4, newton_tol=0.1, lin_factor=0.05):

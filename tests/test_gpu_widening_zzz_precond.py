@@ -360,3 +360,26 @@ def test_adaptive_integration_matches_oracle_backend(name, mult, precond):
         assert np.abs(y[k].cpu().numpy() - yo[k]).max() <= 1e-8 * scale, (k, sg, so)
     o.close()
     h.close()
+
+
+@pytest.mark.parametrize("name", ["dendrite2d", "auni3d", "pfhub1a"])
+def test_scalar_diagnostics_match_the_restatement(name):
+    """ampe_scalar_diagnostics (QuatModel::printScalarDiagnostics: solid fraction, integral / max concentration,
+    Cex, temperature extrema / average, thermal energy) against the CPU restatement; the sums differ only by
+    their order (1e-12), extrema are exact"""
+    from ampe_b200 import rhs
+    from oracle import pyoracle
+    cfg, st = parity.make_case(name)
+    y = rhs.to_device(st)
+    r = rhs.QuatIntegratorRHS(cfg)
+    got = r.printScalarDiagnostics(y)
+    o = pyoracle.Oracle(cfg)
+    ref = o.scalar_diagnostics({k: (None if v is None else v.numpy().copy()) for k, v in st.items()})
+    o.close()
+    assert set(got) == set(ref)
+    for k in ref:
+        if k in ("max_concentration", "min_temperature", "max_temperature"):
+            assert got[k] == ref[k], k
+        else:
+            assert got[k] == pytest.approx(ref[k], rel=1e-12, abs=1e-13 * max(1.0, abs(ref[k]))), k
+    r.close()

@@ -98,3 +98,44 @@ def test_explicit_cahn_hilliard_steps_decrease_the_energy():
     _, energies = parity.oracle_trajectory(cfg, st, parity.TRAJ_DT["pfhub1a"], 60, energy_every=10)
     f = np.array([e[0] for e in energies])
     assert np.all(np.diff(f) < 0.0)
+
+
+# ---- QuatModel::printScalarDiagnostics ------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["dendrite2d", "auni3d", "pfhub1a"])
+def test_scalar_diagnostics_restatement(name):
+    """volume of solid = L1 norm of phi times the cell volume, integral / max concentration, Cex =
+    (int |c phi| - c0 int |phi|) / int c, temperature extrema / average, thermal energy = -L int phi + cp int T
+    (QuatModel.cc:2543-2690, 5106-5180, 5373-5392) against numpy"""
+    import parity
+    from oracle import pyoracle
+    cfg, st = parity.make_case(name)
+    y = {k: (None if v is None else v.numpy().copy()) for k, v in st.items()}
+    o = pyoracle.Oracle(cfg)
+    d = o.scalar_diagnostics(y)
+    o.close()
+    dv = float(np.prod([cfg.dx[a] for a in range(cfg.ndim)]))
+    ncell = cfg.n[0] * cfg.n[1] * (cfg.n[2] if cfg.ndim == 3 else 1)
+    vol = dv * ncell
+    assert d["volume"] == pytest.approx(vol, rel=1e-14)
+    if cfg.with_phase:
+        assert d["volume_solid"] == pytest.approx(np.abs(y["phase"]).sum() * dv, rel=1e-12)
+        assert d["solid_fraction"] == pytest.approx(np.abs(y["phase"]).mean(), rel=1e-12)
+    else:
+        assert d["solid_fraction"] == 1.0
+    if cfg.with_concentration:
+        c = y["conc"]
+        phi = y["phase"] if cfg.with_phase else np.ones_like(c)
+        assert d["integral_concentration"] == pytest.approx(c.sum() * dv, rel=1e-12)
+        assert d["max_concentration"] == c.max()
+        cphi = np.abs(c * phi).sum() * dv
+        assert d["integral_phase_concentration"] == pytest.approx(cphi, rel=1e-12)
+        expect = (cphi - c.sum() * dv / vol * d["volume_solid"]) / (c.sum() * dv)
+        assert d["cex"] == pytest.approx(expect, rel=1e-9, abs=1e-13)
+    if cfg.with_unsteady_temperature:
+        T = y["temperature"]
+        assert d["min_temperature"] == T.min() and d["max_temperature"] == T.max()
+        assert d["average_temperature"] == pytest.approx(T.mean(), rel=1e-12)
+        assert d["thermal_energy"] == pytest.approx(-cfg.latent_heat * y["phase"].sum() * dv + cfg.cp * T.sum() * dv,
+                                                    rel=1e-11)
+    else:
+        assert d["min_temperature"] == d["max_temperature"] == d["average_temperature"] == cfg.T_uniform

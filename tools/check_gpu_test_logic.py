@@ -134,7 +134,19 @@ class FakeHost:
         self.o.close()
 
 
+class FakeRHS:
+    def __init__(self, cfg, device=None):
+        self.o = pyoracle.Oracle(cfg)
+
+    def printScalarDiagnostics(self, y):
+        return self.o.scalar_diagnostics({k: (None if v is None else v.numpy()) for k, v in y.items()})
+
+    def close(self):
+        self.o.close()
+
+
 def main():
+    rhs.QuatIntegratorRHS = FakeRHS
     precond.LevelSolver = FakeLevelSolver
     precond.phasefacops_setc = fake_setc
     host_rhs.HostQuatIntegrator = FakeHost
