@@ -383,3 +383,31 @@ def test_scalar_diagnostics_match_the_restatement(name):
         else:
             assert got[k] == pytest.approx(ref[k], rel=1e-12, abs=1e-13 * max(1.0, abs(ref[k]))), k
     r.close()
+
+
+def test_cahnhilliard_regression_deck_on_the_device(tmp_path):
+    """tests/CahnHilliard/test2d.py end to end on the device (see tests/test_regression_cahnhilliard.py):
+    NetCDF initial conditions -> device, variable-step implicit integration to t = 300 with
+    printScalarDiagnostics every 10 time units; consecutive composition integrals within 1e-5 relative"""
+    from ampe_b200 import host_rhs, netcdf_classic, rhs
+    from test_regression_cahnhilliard import deck, make_initial
+    cfg = deck()
+    path = str(tmp_path / "64x64.nc")
+    netcdf_classic.write(path, {"concentration0": make_initial(64, 64)})
+    y = rhs.to_device(host_rhs.read_initial_conditions(path, cfg))
+    h = host_rhs.HostQuatIntegrator(cfg, True)
+    diag = rhs.QuatIntegratorRHS(cfg)
+    atol, old, t, step = 1.0e-4, -1.0, 0.0, 1.0e-3
+    while t < 300.0:
+        rc, st = h.integrateAdaptive(y, t + 10.0, step, t0=t, rtol=1e-2 * atol, atol=atol, max_steps=5000)
+        assert rc == 0, st
+        t, step = st["t_reached"], st["last_step"]
+        conc = diag.printScalarDiagnostics(y)["integral_concentration"]
+        old = conc if old < 0.0 else old
+        assert abs(conc - old) <= 1.0e-5 * conc, (t, conc, old)
+        old = conc
+    assert t >= 300.0
+    c = y["conc"].cpu().numpy()
+    assert c.max() - c.min() > 0.3
+    h.close()
+    diag.close()

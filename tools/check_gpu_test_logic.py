@@ -183,6 +183,14 @@ def main():
         if marks:
             cases = [c if isinstance(c, tuple) else (c,) for c in marks[0].args[1]]
         for c in cases:
+            if "tmp_path" in fn.__code__.co_varnames[:fn.__code__.co_argcount]:
+                import pathlib
+                import tempfile
+                with tempfile.TemporaryDirectory() as d:
+                    fn(pathlib.Path(d))
+                ran += 1
+                print("ok", name, "(tmp_path)")
+                continue
             fn(*c)
             ran += 1
             print("ok", name, c)
