@@ -35,6 +35,10 @@ struct ImplicitOptions {
    int max_newton_iterations = 3;          // CVODE NLS_MAXCOR
    double newton_tolerance = 0.1;          // CVODE nlscoef
    double linear_tolerance_factor = 0.05;  // CVODE eplifac
+   // side of the preconditioner: false = right (the stopping test measures the true linear residual), true = left
+   // like the reference's setPreconditioningType(PREC_LEFT) (QuatIntegrator.cc:1583): GMRES on P A x = P b, the
+   // stopping test then measures the preconditioned residual
+   bool precondition_left = false;
    // advanceTo only (variable step size, CVODE's controller constants, cvode_impl.h / cvode.c)
    double h_min = 0.0, h_max = 0.0;        // 0 = unbounded (CVodeSetMinStep / CVodeSetMaxStep)
    long max_steps = 500;                   // CVODE mxstep
@@ -338,18 +342,34 @@ class ImplicitIntegrator
    {
       const int m = d_opt.max_krylov_dimension;
       const double invN = 1.0 / (double)d_ops.length();
+      const bool pre = d_ops.preconditioned();
+      const bool left = pre && d_opt.precondition_left;
       d_ops.scale(0.0, x, x);
-      const double beta = std::sqrt(d_ops.wdot(b, b, ewt) * invN);
+      if (left) {
+         d_ops.precondSolve(b, V[0]);  // P b
+         d_stats.precond_solves++;
+      }
+      const Vec& b0 = left ? V[0] : b;
+      const double beta = std::sqrt(d_ops.wdot(b0, b0, ewt) * invN);
       d_stats.last_linear_residual = beta;
-      if (beta <= tol) return IMPLICIT_OK;
+      if (beta <= tol) {
+         // the predictor already solves the (preconditioned) system to the tolerance: x = 0
+         return IMPLICIT_OK;
+      }
       std::vector<std::vector<double> > H(m + 1, std::vector<double>(m, 0.0));
       std::vector<double> cs(m, 0.0), sn(m, 0.0), g(m + 1, 0.0);
       g[0] = beta;
-      d_ops.scale(1.0 / beta, b, V[0]);
+      d_ops.scale(1.0 / beta, b0, V[0]);
       int k = 0;
       for (int j = 0; j < m; j++) {
          int rc;
-         if (d_ops.preconditioned()) {
+         if (left) {
+            rc = jtimes(t, gamma, ewt, y, fy, V[j], d_pv, ytmp);  // left preconditioning: the Krylov space of P A
+            if (rc == IMPLICIT_OK) {
+               d_ops.precondSolve(d_pv, wk);
+               d_stats.precond_solves++;
+            }
+         } else if (pre) {
             d_ops.precondSolve(V[j], d_pv);  // right preconditioning: the Krylov space of A P
             d_stats.precond_solves++;
             rc = jtimes(t, gamma, ewt, y, fy, d_pv, wk, ytmp);
@@ -395,7 +415,7 @@ class ImplicitIntegrator
          c[i] = s / H[i][i];
       }
       for (int i = 0; i < k; i++) d_ops.linearSum(1.0, x, c[i], V[i], x);
-      if (d_ops.preconditioned() && k > 0) {
+      if (pre && !left && k > 0) {
          d_ops.scale(1.0, x, wk);
          d_ops.precondSolve(wk, x);  // x = P (sum c_i v_i)
          d_stats.precond_solves++;

@@ -266,7 +266,9 @@ class QuatIntegrator
                          ImplicitStats* stats)
    {
       DeviceVectorOps ops(d_ctx, d_cfg, this);
-      ImplicitIntegrator<DeviceVectorOps> integ(ops, opt);
+      ImplicitOptions o = opt;
+      o.precondition_left = d_precond_left;
+      ImplicitIntegrator<DeviceVectorOps> integ(ops, o);
       ampe_rhs_fields yy = *y;
       const int rc = integ.advance(yy, t0, dt, nsteps);
       if (stats) *stats = integ.stats();
@@ -279,7 +281,9 @@ class QuatIntegrator
                          ImplicitStats* stats)
    {
       DeviceVectorOps ops(d_ctx, d_cfg, this);
-      ImplicitIntegrator<DeviceVectorOps> integ(ops, opt);
+      ImplicitOptions o = opt;
+      o.precondition_left = d_precond_left;
+      ImplicitIntegrator<DeviceVectorOps> integ(ops, o);
       ampe_rhs_fields yy = *y;
       const int rc = integ.advanceTo(yy, t0, tend, h0);
       if (stats) *stats = integ.stats();
@@ -298,10 +302,11 @@ class QuatIntegrator
    // defaults except precond_has_dquatdphi = false (block diagonal).  ncycles = V-cycles per block
    // solve (the reference iterates FAC cycles to CVODE's delta; a fixed count keeps the
    // preconditioner a fixed linear operator); 0 switches the preconditioner off.
-   void setupPreconditioners(int ncycles, bool precond_has_dquatdphi = false)
+   void setupPreconditioners(int ncycles, bool precond_has_dquatdphi = false, bool precondition_left = false)
    {
       const ampe_rhs_config& p = d_cfg;
       d_precond_cycles = ncycles;
+      d_precond_left = precondition_left;  // PREC_LEFT (QuatIntegrator.cc:1583) instead of right preconditioning
       d_precond_has_dquatdphi = precond_has_dquatdphi && p.with_phase && p.evolve_quat;  // :485
       d_use_preconditioner = ncycles > 0;
       if (!d_use_preconditioner) return;
@@ -683,6 +688,7 @@ class QuatIntegrator
    long d_precond_setups = 0, d_precond_solves = 0;
    int d_phase_precond_c_id = -1, d_conc_l_g0_id = -1, d_conc_a_g0_id = -1;
    bool d_precond_has_dquatdphi = false;
+   bool d_precond_left = false;
    double d_precond_gamma = 0.0;
    int d_quat_mobility_deriv_id = -1, d_quat_diffusion_deriv_id = -1, d_phase_sol_id = -1, d_quat_rhs_id = -1,
        d_sqrt_m_id = -1, d_face_coef_scratch_id = -1;

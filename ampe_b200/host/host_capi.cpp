@@ -115,10 +115,11 @@ int ampe_host_integrate_adaptive(void* h, const ampe_rhs_fields* y, double t0, d
 }
 // ---- block preconditioners ------------------------------------------------
 // QuatIntegrator::setupPreconditioners; ncycles V-cycles per block solve, 0 = preconditioner off
-int ampe_host_set_preconditioner(void* h, int ncycles, int precond_has_dquatdphi)
+int ampe_host_set_preconditioner(void* h, int ncycles, int precond_has_dquatdphi, int precondition_left)
 {
    try {
-      static_cast<ampe_host::QuatIntegrator*>(h)->setupPreconditioners(ncycles, precond_has_dquatdphi != 0);
+      static_cast<ampe_host::QuatIntegrator*>(h)->setupPreconditioners(ncycles, precond_has_dquatdphi != 0,
+                                                                       precondition_left != 0);
       return 0;
    } catch (const std::exception& e) {
       g_host_err = e.what();

@@ -40,7 +40,7 @@ def load_host():
         L.ampe_host_integrate_adaptive.argtypes = [vp, C.POINTER(_abi.RhsFields), C.c_double, C.c_double, C.c_double,
                                                    vp, vp, vp]
         L.ampe_host_set_preconditioner.restype = C.c_int
-        L.ampe_host_set_preconditioner.argtypes = [vp, C.c_int, C.c_int]
+        L.ampe_host_set_preconditioner.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         L.ampe_host_precond_dquatdphi.restype = C.c_int
         L.ampe_host_precond_dquatdphi.argtypes = [vp, vp, vp]
         L.ampe_host_precond_set.restype = C.c_int
@@ -159,10 +159,12 @@ class HostQuatIntegrator:
         return rc, dict(zip(self.ADAPTIVE_STATS, list(st)))
 
     # ---- block preconditioners ----
-    def setupPreconditioners(self, ncycles=2, precond_has_dquatdphi=False):
+    def setupPreconditioners(self, ncycles=2, precond_has_dquatdphi=False, precondition_left=False):
         """QuatIntegrator::setupPreconditioners: ncycles V-cycles per block solve; 0 = off.  integrateImplicit
-        then runs right-preconditioned GMRES.  precond_has_dquatdphi: with the dquat/dphi coupling block."""
-        self._chk(self.L.ampe_host_set_preconditioner(self.h, int(ncycles), 1 if precond_has_dquatdphi else 0))
+        then runs right-preconditioned GMRES (precondition_left: PREC_LEFT like the reference instead).
+        precond_has_dquatdphi: with the dquat/dphi coupling block."""
+        self._chk(self.L.ampe_host_set_preconditioner(self.h, int(ncycles), 1 if precond_has_dquatdphi else 0,
+                                                      1 if precondition_left else 0))
 
     def multiplyDQuatDPhiBlock(self, phase, qlen):
         """QuatSysSolver::multiplyDQuatDPhiBlock on a ghost-0 CUDA tensor; returns (qlen, ...) tensor"""

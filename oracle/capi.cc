@@ -32,10 +32,11 @@ int oracle_scalar_diagnostics(void* c, const ampe_rhs_fields* y, double* out)
 }
 // ---- block preconditioners (precond.cc) --------------------------------------------------------
 // ncycles > 0: oracle_integrate_implicit runs right-preconditioned GMRES with that many V-cycles
-void oracle_set_preconditioner(void* c, int ncycles, int has_dquatdphi)
+void oracle_set_preconditioner(void* c, int ncycles, int has_dquatdphi, int left)
 {
    ((Ctx*)c)->precond_cycles = ncycles;
    ((Ctx*)c)->precond_dquatdphi = has_dquatdphi != 0;
+   ((Ctx*)c)->precond_left = left != 0;
 }
 void oracle_precond_stats(void* c, double* out2)
 {

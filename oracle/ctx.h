@@ -42,6 +42,7 @@ struct Ctx {
    void* precond = nullptr;     // block preconditioners (precond.cc)
    int precond_cycles = 0;      // > 0: the implicit integrator runs right-preconditioned (stepper.cc)
    bool precond_dquatdphi = false;  // with the dquat/dphi coupling block
+   bool precond_left = false;       // PREC_LEFT like the reference (default here: right)
    double precond_stats[2] = {0, 0};  // set-ups, solves of the last implicit integration
 };
 

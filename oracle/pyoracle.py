@@ -106,7 +106,7 @@ def lib(perf=False):
         L.oracle_calphad_diffusion_mobility.argtypes = [pdb, C.c_int, dbl, dbl]
         # block preconditioners (precond.cc)
         vp, pvp, ci = C.c_void_p, C.POINTER(C.c_void_p), C.c_int
-        L.oracle_set_preconditioner.argtypes = [vp, ci, ci]
+        L.oracle_set_preconditioner.argtypes = [vp, ci, ci, ci]
         L.oracle_precond_dquatdphi.restype = ci
         L.oracle_precond_dquatdphi.argtypes = [vp, vp, vp]
         L.oracle_precond_stats.argtypes = [vp, vp]
@@ -224,10 +224,11 @@ class Oracle:
         return rc, dict(zip(names, st.tolist()))
 
     # ---- block preconditioners (precond.cc) ----
-    def set_preconditioner(self, ncycles, dquatdphi=False):
+    def set_preconditioner(self, ncycles, dquatdphi=False, left=False):
         """ncycles > 0: integrate_implicit runs right-preconditioned GMRES (CVSpgmrPrecondSet / Solve);
-        dquatdphi: with the lower-triangular dquat/dphi coupling block (precond_has_dquatdphi)"""
-        self.L.oracle_set_preconditioner(self.h, int(ncycles), 1 if dquatdphi else 0)
+        dquatdphi: with the lower-triangular dquat/dphi coupling block (precond_has_dquatdphi); left: PREC_LEFT like
+        the reference instead of right preconditioning"""
+        self.L.oracle_set_preconditioner(self.h, int(ncycles), 1 if dquatdphi else 0, 1 if left else 0)
 
     def precond_stats(self):
         out = np.zeros(2)

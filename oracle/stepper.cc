@@ -158,6 +158,7 @@ extern "C" int oracle_integrate_implicit(void* ctx, const ampe_rhs_fields* y, do
    ampe_host::ImplicitOptions o;
    if (iopt) o.order = iopt[0], o.max_krylov_dimension = iopt[1], o.max_newton_iterations = iopt[2];
    if (dopt) o.rtol = dopt[0], o.atol = dopt[1], o.newton_tolerance = dopt[2], o.linear_tolerance_factor = dopt[3];
+   o.precondition_left = c->precond_left;
    OracleOps ops(c);
    ampe_host::ImplicitIntegrator<OracleOps> integ(ops, o);
    const int rc = integ.advance(v, t0, dt, nsteps);
@@ -199,6 +200,7 @@ extern "C" int oracle_integrate_adaptive(void* ctx, const ampe_rhs_fields* y, do
       o.rtol = dopt[0], o.atol = dopt[1], o.newton_tolerance = dopt[2], o.linear_tolerance_factor = dopt[3];
       o.h_min = dopt[4], o.h_max = dopt[5];
    }
+   o.precondition_left = c->precond_left;
    OracleOps ops(c);
    ampe_host::ImplicitIntegrator<OracleOps> integ(ops, o);
    const int rc = integ.advanceTo(v, t0, tend, h0);

@@ -463,3 +463,30 @@ def test_fused_red_black_pass_is_bit_identical(n, dx, quat):
             assert mg.set_fused(True, min_cells=256) >= 1
         outs.append(mg.solve(rhs, ncycles=3, symmetrized=quat))
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("name,mult", [("gg3d_hbsm", 40), ("dendrite2d", 50)])
+def test_left_preconditioning_like_the_reference(name, mult):
+    """PREC_LEFT (QuatIntegrator.cc:1583): GMRES on P A x = P b stops on the preconditioned residual; the steps it
+    converges to are those of the right-preconditioned run (1e-8), with no more Krylov vectors"""
+    dt = parity.TRAJ_DT[name] * mult
+    kw = dict(order=2, rtol=1e-8, atol=1e-10, max_krylov=30, max_newton=8)
+    runs = {}
+    for left in (False, True):
+        cfg, st = parity.make_case(name)
+        y = {k: (None if v is None else v.numpy().copy()) for k, v in st.items()}
+        o = pyoracle.Oracle(cfg)
+        if cfg.conc_rhs_form in (2, 3):
+            o.set_ref(y["conc"].ravel().copy(), y["conc"].ravel().copy())
+        o.set_preconditioner(2, left=left)
+        rc, stats = o.integrate_implicit(y, dt, 3, **kw)
+        stats.update(o.precond_stats())
+        o.close()
+        assert rc == 0, stats
+        runs[left] = (y, stats)
+    assert runs[True][1]["linear_iterations"] <= runs[False][1]["linear_iterations"]
+    # one extra solve per linear system (P b) instead of one per solution (P sum c_i v_i)
+    assert runs[True][1]["precond_solves"] >= runs[True][1]["linear_iterations"]
+    for k, v in runs[False][0].items():
+        if v is not None:
+            assert np.abs(runs[True][0][k] - v).max() < 1e-8 * max(np.abs(v).max(), 1e-300), k
