@@ -18,6 +18,13 @@
  * initial guess (a fixed linear operator, no host synchronisation) with the reference's red-black
  * Gauss-Seidel update as the smoother (efo_rbgswithfluxmax*, 2d/ellipticfacops.m4:60-130).
  *
+ * Implementation notes (csrc/mg.cu): coefficients that are constants of a block are not stored;
+ * above 4096 cells a sweep is one fused red-black pass over shared-memory tiles, residual and restriction are
+ * one pass, and every level from 4096 cells down runs inside one block -- all bit-identical to the plain
+ * colour half-sweeps.  Environment switches read by ampe_mg_create: AMPE_B200_MG_FUSED=0, AMPE_B200_MG_TAIL=0
+ * (the plain variants, for A/B runs), AMPE_B200_MG_GRAPH=1 (a solve captured once and replayed; needs a
+ * non-default stream).
+ *
  * Arrays named "SAMRAI layout" are device pointers laid out like CellData / SideData over the box
  * [0, n-1] with the stated ghost width (i fastest); rhs / soln / u / out are ghost-0 cell arrays.
  * Array-of-pointer arguments are HOST arrays of device pointers.  Return codes: ampe_b200.h.
