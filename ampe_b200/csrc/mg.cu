@@ -43,6 +43,7 @@ struct ampe_mg {
    int n[3] = {1, 1, 1};
    double inv_h2[3] = {0, 0, 0};
    bool with_s = false;          // quaternion block: column multiplier present
+   int ncomp = 1;                // components solved together with the one matrix (quaternion block: qlen)
    bool coefficients_set = false;
    std::vector<Level> levels;
    std::vector<double*> blocks;  // work arrays u, f, r (and s): one allocation per level
@@ -184,8 +185,11 @@ __global__ void mg_load_kernel(Level L, const double* rhs, int symmetrized)
    const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
         idx += (long long)gridDim.x * blockDim.x) {
-      L.f[idx] = (symmetrized && L.s) ? rhs[idx] / L.s[idx] : rhs[idx];
-      L.u[idx] = 0.0;
+      for (int m = 0; m < L.nc; m++) {
+         const long long q = idx + m * L.cs;
+         L.f[q] = (symmetrized && L.s) ? rhs[q] / L.s[idx] : rhs[q];
+         L.u[q] = 0.0;
+      }
    }
 }
 // soln = u (times s: QuatFACOps::multiplyMobilitySqrt)
@@ -194,7 +198,10 @@ __global__ void mg_store_kernel(Level L, double* soln, int symmetrized)
    const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
         idx += (long long)gridDim.x * blockDim.x)
-      soln[idx] = (symmetrized && L.s) ? L.u[idx] * L.s[idx] : L.u[idx];
+      for (int m = 0; m < L.nc; m++) {
+         const long long q = idx + m * L.cs;
+         soln[q] = (symmetrized && L.s) ? L.u[q] * L.s[idx] : L.u[q];
+      }
 }
 __global__ void mg_set_elliptic_kernel(Level L, const double* m, int ngm, const double* c, int ngc, P3 d, P3 d2,
                                        int have_d2, int ngd, double d_scale, double ih0, double ih1, double ih2)
@@ -329,7 +336,10 @@ __global__ void __launch_bounds__(MT) mg_rb_fused_kernel(Level L, const double* 
    extern __shared__ double mg_tile[];
    const int b = blockIdx.x;
    const int t0 = b % nt0, t1 = (b / nt0) % nt1, t2 = b / (nt0 * nt1);
-   mg_rb_tile_pass(L, u_in, u_out, mg_tile, T, t0 * T.t[0], t1 * T.t[1], t2 * T.t[2], (int)threadIdx.x, (int)blockDim.x);
+   // the components share the matrix: the coefficient reads of the second and later components hit L1 / L2
+   for (int m = 0; m < L.nc; m++)
+      mg_rb_tile_pass(L, L.f + m * L.cs, u_in + m * L.cs, u_out + m * L.cs, mg_tile, T, t0 * T.t[0], t1 * T.t[1],
+                      t2 * T.t[2], (int)threadIdx.x, (int)blockDim.x);
 }
 
 void smooth(ampe_mg* g, int l, int sweeps, cudaStream_t st)
@@ -442,9 +452,10 @@ int build_coarse(ampe_mg* g, cudaStream_t st)
 
 extern "C" {
 
-int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_scale, ampe_mg** out)
+int ampe_mg_create_multi(int ndim, const int* n, const double* dx, int with_column_scale, int ncomp, ampe_mg** out)
 {
-   if (!out || !n || !dx || (ndim != 2 && ndim != 3)) return ampe_set_err(AMPE_EINVAL, "ampe_mg_create: bad argument");
+   if (!out || !n || !dx || (ndim != 2 && ndim != 3) || ncomp < 1 || ncomp > 8)
+      return ampe_set_err(AMPE_EINVAL, "ampe_mg_create: bad argument");
    int ndev = 0;
    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
       return ampe_set_err(AMPE_ENOGPU, "ampe_mg_create: no CUDA device (there is no CPU fallback)");
@@ -453,6 +464,7 @@ int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_sca
    ampe_mg* g = new ampe_mg;
    g->ndim = ndim;
    g->with_s = with_column_scale != 0;
+   g->ncomp = ncomp;
    for (int d = 0; d < 3; d++) {
       g->n[d] = d < ndim ? n[d] : 1;
       g->inv_h2[d] = d < ndim ? 1.0 / (dx[d] * dx[d]) : 0.0;
@@ -464,7 +476,7 @@ int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_sca
       L.ndim = ndim;
       for (int d = 0; d < 3; d++) L.n[d] = cur[d];
       const long long nc = (long long)cur[0] * cur[1] * cur[2];
-      const int narr = (g->with_s ? 1 : 0) + 3;
+      const int narr = (g->with_s ? 1 : 0) + 3 * ncomp;
       double* blk = nullptr;
       cudaError_t e = cudaMalloc(&blk, sizeof(double) * nc * narr);
       if (e != cudaSuccess) {
@@ -479,9 +491,10 @@ int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_sca
       L.c_const = 1.0, L.m_const = 1.0;
       if (g->with_s) L.s = p, p += nc;
       for (int d = 0; d < 3; d++) L.d[d] = nullptr, L.d_const[d] = 0.0;
-      L.u = p, p += nc;
-      L.f = p, p += nc;
-      L.r = p, p += nc;
+      L.nc = ncomp, L.cs = nc;
+      L.u = p, p += nc * ncomp;
+      L.f = p, p += nc * ncomp;
+      L.r = p, p += nc * ncomp;
       g->levels.push_back(L);
       bool even = true;
       for (int d = 0; d < ndim; d++) even = even && (cur[d] % 2 == 0);
@@ -522,7 +535,7 @@ int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_sca
       T.t[1] = pick(L.n[1], ndim == 3 ? 8 : 16);
       T.t[2] = ndim == 3 ? pick(L.n[2], 8) : 1;
       if (T.t[0] < 8 || T.t[1] < 2 || T.t[2] < 1) continue;  // slivers: the halo would dominate
-      if (cudaMalloc(&g->alt_u[l], sizeof(double) * cells(L)) != cudaSuccess) {
+      if (cudaMalloc(&g->alt_u[l], sizeof(double) * cells(L) * ncomp) != cudaSuccess) {
          g->alt_u[l] = nullptr;
          cudaGetLastError();
          continue;
@@ -531,6 +544,11 @@ int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_sca
    }
    *out = g;
    return AMPE_OK;
+}
+
+int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_scale, ampe_mg** out)
+{
+   return ampe_mg_create_multi(ndim, n, dx, with_column_scale, 1, out);
 }
 
 int ampe_mg_destroy(ampe_mg* g)
@@ -548,6 +566,7 @@ int ampe_mg_destroy(ampe_mg* g)
 }
 
 int ampe_mg_num_levels(const ampe_mg* g) { return g ? (int)g->levels.size() : 0; }
+int ampe_mg_num_components(const ampe_mg* g) { return g ? g->ncomp : 0; }
 int ampe_mg_last_launch_count(const ampe_mg* g) { return g ? g->launches : 0; }
 
 int ampe_mg_set_sweeps(ampe_mg* g, int pre, int post, int coarse)
@@ -705,6 +724,7 @@ int ampe_k_phasefacops_setc(int ndim, const int* ifirst, const int* ilast, const
    }
    L.c = L.m = L.s = L.u = L.f = L.r = nullptr;
    L.d[0] = L.d[1] = L.d[2] = nullptr;
+   L.nc = 1, L.cs = 0;
    phasefacops_setc_kernel<<<grid_for(cells(L)), MT, 0, (cudaStream_t)stream>>>(L, phi, ngphi, m, ngm, gamma,
                                                                               phi_well_scale, t, c, ngc);
    CUDA_OKM(cudaGetLastError());

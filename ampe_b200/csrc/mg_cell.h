@@ -45,6 +45,10 @@ struct Level {
    double* f;     // right-hand side
    double* r;     // residual (and Jacobi work array)
    double c_const, m_const, d_const[3];
+   // u, f, r hold nc components (the qlen components of the quaternion block share one matrix: one pass
+   // updates all of them and reads the coefficients once); component m starts at m * cs
+   int nc;
+   long long cs;
 };
 
 MG_HD double mg_c(const Level& L, long long o) { return L.c ? L.c[o] : L.c_const; }
@@ -102,19 +106,25 @@ MG_HD double mg_apply_cell(const Level& L, const double* u, int i, int j, int k)
 MG_HD void mg_residual_cell(const Level& L, int i, int j, int k)
 {
    const long long o = mg_index(L, i, j, k);
-   L.r[o] = L.f[o] - mg_apply_cell(L, L.u, i, j, k);
+   for (int m = 0; m < L.nc; m++) {
+      const long long q = m * L.cs;
+      L.r[o + q] = L.f[o + q] - mg_apply_cell(L, L.u + q, i, j, k);
+   }
 }
 
 // Gauss-Seidel update of one cell (efo_rbgswithfluxmaxvardcvarsf2d): u += residual / diagonal
 MG_HD void mg_smooth_cell(const Level& L, int i, int j, int k)
 {
-   double flux, dsum;
-   mg_face_sums(L, L.u, i, j, k, flux, dsum);
    const long long o = mg_index(L, i, j, k);
    const double si = L.s ? L.s[o] : 1.0;
-   const double residual = L.f[o] - (mg_c(L, o) * L.u[o] + mg_m(L, o) * flux);
-   const double diag = mg_c(L, o) - mg_m(L, o) * si * dsum;
-   L.u[o] += residual / diag;
+   for (int m = 0; m < L.nc; m++) {
+      double* u = L.u + m * L.cs;
+      double flux, dsum;
+      mg_face_sums(L, u, i, j, k, flux, dsum);
+      const double residual = L.f[o + m * L.cs] - (mg_c(L, o) * u[o] + mg_m(L, o) * flux);
+      const double diag = mg_c(L, o) - mg_m(L, o) * si * dsum;
+      u[o] += residual / diag;
+   }
 }
 
 // ---- one red-black sweep in ONE pass over a tile (fused smoother) ---------------------------------
@@ -136,8 +146,8 @@ MG_HD int mg_wrap(int i, int n)
 }
 // Gauss-Seidel value of cell (gi,gj,gk) (global, in range) from the staged tile: same operation order
 // as mg_face_sums + mg_smooth_cell
-MG_HD double mg_gs_from_tile(const Level& L, const double* tile, int p0, int p1, int li, int lj, int lk, int gi, int gj,
-                             int gk)
+MG_HD double mg_gs_from_tile(const Level& L, const double* f, const double* tile, int p0, int p1, int li, int lj, int lk,
+                             int gi, int gj, int gk)
 {
    // tile index of local (li,lj,lk) with the halo of two: (li+2) + p0 ((lj+2) + p1 (lk+hz))
    const int hz = L.ndim == 3 ? 2 : 0;
@@ -169,7 +179,7 @@ MG_HD double mg_gs_from_tile(const Level& L, const double* tile, int p0, int p1,
       flux += du * (uu - ui) - dd * (ui - ud);
       dsum += du + dd;
    }
-   const double residual = L.f[o] - (mg_c(L, o) * uc + mg_m(L, o) * flux);
+   const double residual = f[o] - (mg_c(L, o) * uc + mg_m(L, o) * flux);
    const double diag = mg_c(L, o) - mg_m(L, o) * si * dsum;
    return uc + residual / diag;
 }
@@ -181,8 +191,9 @@ MG_HD double mg_gs_from_tile(const Level& L, const double* tile, int p0, int p1,
 #endif
 
 // one tile with origin (o0,o1,o2) (multiples of the tile extents; extents of L are multiples of them too)
-MG_HD void mg_rb_tile_pass(const Level& L, const double* u_in, double* u_out, double* tile, TileShape T, int o0, int o1,
-                           int o2, int tid, int nthreads)
+// (one component: u_in, u_out and f point at it; the caller loops over the components of the level)
+MG_HD void mg_rb_tile_pass(const Level& L, const double* f, const double* u_in, double* u_out, double* tile, TileShape T,
+                           int o0, int o1, int o2, int tid, int nthreads)
 {
    const int hz = L.ndim == 3 ? 2 : 0;
    const int p0 = T.t[0] + 4, p1 = T.t[1] + 4, p2 = T.t[2] + 2 * hz;
@@ -207,7 +218,7 @@ MG_HD void mg_rb_tile_pass(const Level& L, const double* u_in, double* u_out, do
          const int li = 2 * ii + a - g;
          const int gi = mg_wrap(o0 + li, L.n[0]), gj = mg_wrap(o1 + lj, L.n[1]);
          const int gk = L.ndim == 3 ? mg_wrap(o2 + lk, L.n[2]) : 0;
-         const double v = mg_gs_from_tile(L, tile, p0, p1, li, lj, lk, gi, gj, gk);
+         const double v = mg_gs_from_tile(L, f, tile, p0, p1, li, lj, lk, gi, gj, gk);
          tile[(long long)(li + 2) + (long long)p0 * ((lj + 2) + (long long)p1 * (lk + hz))] = v;
       }
       MG_TILE_SYNC();
@@ -218,6 +229,7 @@ MG_HD void mg_rb_tile_pass(const Level& L, const double* u_in, double* u_out, do
       u_out[mg_index(L, o0 + li, o1 + lj, L.ndim == 3 ? o2 + lk : 0)] =
           tile[(long long)(li + 2) + (long long)p0 * ((lj + 2) + (long long)p1 * (lk + hz))];
    }
+   MG_TILE_SYNC();  // the tile may be re-staged for the next component
 }
 
 // damped Jacobi for levels whose periodic wrap breaks the two-colouring (an odd extent):
@@ -231,20 +243,23 @@ MG_HD void mg_jacobi_cell(const Level& L, double omega, int i, int j, int k)
    if (L.ndim == 3) dsum += mg_d(L, 2, mg_index(L, i, j, mg_up(k, L.n[2]))) + mg_d(L, 2, o);
    const double si = L.s ? L.s[o] : 1.0;
    const double diag = mg_c(L, o) - mg_m(L, o) * si * dsum;
-   L.u[o] += omega * L.r[o] / diag;
+   for (int m = 0; m < L.nc; m++) L.u[o + m * L.cs] += omega * L.r[o + m * L.cs] / diag;
 }
 
 // coarse cell (I,J,K): f_c = mean of the children's residuals, u_c = 0
 MG_HD void mg_restrict_cell(const Level& F, const Level& C, int I, int J, int K)
 {
    const int nk = F.ndim == 3 ? 2 : 1;
-   double acc = 0.0;
-   for (int c = 0; c < nk; c++)
-      for (int b = 0; b < 2; b++)
-         for (int a = 0; a < 2; a++) acc += F.r[mg_index(F, 2 * I + a, 2 * J + b, (F.ndim == 3 ? 2 * K : 0) + c)];
    const long long o = mg_index(C, I, J, K);
-   C.f[o] = acc * (F.ndim == 3 ? 0.125 : 0.25);
-   C.u[o] = 0.0;
+   for (int m = 0; m < F.nc; m++) {
+      const double* r = F.r + m * F.cs;
+      double acc = 0.0;
+      for (int c = 0; c < nk; c++)
+         for (int b = 0; b < 2; b++)
+            for (int a = 0; a < 2; a++) acc += r[mg_index(F, 2 * I + a, 2 * J + b, (F.ndim == 3 ? 2 * K : 0) + c)];
+      C.f[o + m * C.cs] = acc * (F.ndim == 3 ? 0.125 : 0.25);
+      C.u[o + m * C.cs] = 0.0;
+   }
 }
 
 // the two above in one pass: the coarse cell computes the residuals of its children itself (same
@@ -252,16 +267,19 @@ MG_HD void mg_restrict_cell(const Level& F, const Level& C, int I, int J, int K)
 MG_HD void mg_restrict_residual_cell(const Level& F, const Level& C, int I, int J, int K)
 {
    const int nk = F.ndim == 3 ? 2 : 1;
-   double acc = 0.0;
-   for (int c = 0; c < nk; c++)
-      for (int b = 0; b < 2; b++)
-         for (int a = 0; a < 2; a++) {
-            const int i = 2 * I + a, j = 2 * J + b, k = (F.ndim == 3 ? 2 * K : 0) + c;
-            acc += F.f[mg_index(F, i, j, k)] - mg_apply_cell(F, F.u, i, j, k);
-         }
    const long long o = mg_index(C, I, J, K);
-   C.f[o] = acc * (F.ndim == 3 ? 0.125 : 0.25);
-   C.u[o] = 0.0;
+   for (int m = 0; m < F.nc; m++) {
+      const long long q = m * F.cs;
+      double acc = 0.0;
+      for (int c = 0; c < nk; c++)
+         for (int b = 0; b < 2; b++)
+            for (int a = 0; a < 2; a++) {
+               const int i = 2 * I + a, j = 2 * J + b, k = (F.ndim == 3 ? 2 * K : 0) + c;
+               acc += F.f[mg_index(F, i, j, k) + q] - mg_apply_cell(F, F.u + q, i, j, k);
+            }
+      C.f[o + m * C.cs] = acc * (F.ndim == 3 ? 0.125 : 0.25);
+      C.u[o + m * C.cs] = 0.0;
+   }
 }
 
 // coarse coefficients of cell (I,J,K): cell fields are the children's mean; the lower face in
@@ -313,19 +331,22 @@ MG_HD void mg_prolong_cell(const Level& C, const Level& F, int i, int j, int k)
    const int I = i >> 1, J = j >> 1, K = F.ndim == 3 ? (k >> 1) : 0;
    const int I2 = (i & 1) ? mg_up(I, C.n[0]) : mg_dn(I, C.n[0]);
    const int J2 = (j & 1) ? mg_up(J, C.n[1]) : mg_dn(J, C.n[1]);
-   double e;
-   if (F.ndim == 3) {
-      const int K2 = (k & 1) ? mg_up(K, C.n[2]) : mg_dn(K, C.n[2]);
-      const double ea = 0.75 * (0.75 * C.u[mg_index(C, I, J, K)] + 0.25 * C.u[mg_index(C, I2, J, K)]) +
-                        0.25 * (0.75 * C.u[mg_index(C, I, J2, K)] + 0.25 * C.u[mg_index(C, I2, J2, K)]);
-      const double eb = 0.75 * (0.75 * C.u[mg_index(C, I, J, K2)] + 0.25 * C.u[mg_index(C, I2, J, K2)]) +
-                        0.25 * (0.75 * C.u[mg_index(C, I, J2, K2)] + 0.25 * C.u[mg_index(C, I2, J2, K2)]);
-      e = 0.75 * ea + 0.25 * eb;
-   } else {
-      e = 0.75 * (0.75 * C.u[mg_index(C, I, J, 0)] + 0.25 * C.u[mg_index(C, I2, J, 0)]) +
-          0.25 * (0.75 * C.u[mg_index(C, I, J2, 0)] + 0.25 * C.u[mg_index(C, I2, J2, 0)]);
+   for (int m = 0; m < F.nc; m++) {
+      const double* cu = C.u + m * C.cs;
+      double e;
+      if (F.ndim == 3) {
+         const int K2 = (k & 1) ? mg_up(K, C.n[2]) : mg_dn(K, C.n[2]);
+         const double ea = 0.75 * (0.75 * cu[mg_index(C, I, J, K)] + 0.25 * cu[mg_index(C, I2, J, K)]) +
+                           0.25 * (0.75 * cu[mg_index(C, I, J2, K)] + 0.25 * cu[mg_index(C, I2, J2, K)]);
+         const double eb = 0.75 * (0.75 * cu[mg_index(C, I, J, K2)] + 0.25 * cu[mg_index(C, I2, J, K2)]) +
+                           0.25 * (0.75 * cu[mg_index(C, I, J2, K2)] + 0.25 * cu[mg_index(C, I2, J2, K2)]);
+         e = 0.75 * ea + 0.25 * eb;
+      } else {
+         e = 0.75 * (0.75 * cu[mg_index(C, I, J, 0)] + 0.25 * cu[mg_index(C, I2, J, 0)]) +
+             0.25 * (0.75 * cu[mg_index(C, I, J2, 0)] + 0.25 * cu[mg_index(C, I2, J2, 0)]);
+      }
+      F.u[mg_index(F, i, j, k) + m * F.cs] += e;
    }
-   F.u[mg_index(F, i, j, k)] += e;
 }
 
 // ---- finest-level coefficients from SAMRAI-layout PatchData ------------------------------------

@@ -618,7 +618,8 @@ class QuatSysSolver
       if (!d_mg) {
          int n[3];
          for (int d = 0; d < 3; d++) n[d] = patch->getBox().numberCells(d);
-         check(ampe_mg_create(patch->getBox().ndim, n, patch->getDx(), 1, &d_mg), "ampe_mg_create(quat)");
+         check(ampe_mg_create_multi(patch->getBox().ndim, n, patch->getDx(), 1, d_cfg.qlen, &d_mg),
+               "ampe_mg_create(quat)");
       }
       auto mob = patch->cell<double>(mobility_id);
       auto fc = patch->side<double>(d_fc_id);
@@ -633,11 +634,8 @@ class QuatSysSolver
    bool solveSystem(double* q_soln, const double* q_rhs, int ncycles)
    {
       if (!d_mg) throw std::runtime_error("QuatSysSolver::solveSystem before setOperatorCoefficients");
-      auto patch = d_h->getPatchLevel(0)->patches.front();
-      size_t nc = 1;
-      for (int d = 0; d < patch->getBox().ndim; d++) nc *= (size_t)patch->getBox().numberCells(d);
-      for (int m = 0; m < d_cfg.qlen; m++)
-         check(ampe_mg_solve(d_mg, q_rhs + nc * m, q_soln + nc * m, ncycles, 1, nullptr), "QuatSysSolver::solveSystem");
+      // all qlen depths in one solve: they share the matrix, every pass reads the coefficients once
+      check(ampe_mg_solve(d_mg, q_rhs, q_soln, ncycles, 1, nullptr), "QuatSysSolver::solveSystem");
       return true;
    }
    ampe_mg* levelSolver() const { return d_mg; }

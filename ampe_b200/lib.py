@@ -90,6 +90,10 @@ def load():
     pvp = C.POINTER(vp)
     L.ampe_mg_create.restype = ci
     L.ampe_mg_create.argtypes = [ci, C.POINTER(ci), pd, ci, pvp]
+    L.ampe_mg_create_multi.restype = ci
+    L.ampe_mg_create_multi.argtypes = [ci, C.POINTER(ci), pd, ci, ci, pvp]
+    L.ampe_mg_num_components.restype = ci
+    L.ampe_mg_num_components.argtypes = [vp]
     L.ampe_mg_destroy.restype = ci
     L.ampe_mg_destroy.argtypes = [vp]
     L.ampe_mg_set_elliptic.restype = ci

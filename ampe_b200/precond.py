@@ -27,7 +27,7 @@ def _p(t):
 class LevelSolver:
     """ampe_mg: create / setOperatorCoefficients / solveSystem on the device"""
 
-    def __init__(self, n=None, dx=None, with_column_scale=False, handle=None, owner=None):
+    def __init__(self, n=None, dx=None, with_column_scale=False, handle=None, owner=None, ncomp=1):
         self.L = load()
         self._owner = owner  # borrowed handle (a HostQuatIntegrator's block solver)
         self._keep = None
@@ -38,7 +38,8 @@ class LevelSolver:
         nn = (C.c_int * 3)(*(list(n) + [1] * (3 - ndim)))
         hh = (C.c_double * 3)(*(list(dx) + [0.0] * (3 - ndim)))
         self.h = C.c_void_p()
-        check(self.L.ampe_mg_create(ndim, nn, hh, 1 if with_column_scale else 0, C.byref(self.h)), "ampe_mg_create")
+        check(self.L.ampe_mg_create_multi(ndim, nn, hh, 1 if with_column_scale else 0, int(ncomp), C.byref(self.h)),
+              "ampe_mg_create")
         self._own = True
 
     def close(self):

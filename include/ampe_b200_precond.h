@@ -43,6 +43,12 @@ typedef struct ampe_mg ampe_mg;
 /* EllipticFACSolver::initializeSolverState / QuatSysSolver::initializeSolverState: allocates every
  * level on the device.  with_column_scale != 0: the quaternion block (ampe_mg_set_quat).          */
 int ampe_mg_create(int ndim, const int* n, const double* dx, int with_column_scale, ampe_mg** out);
+/* ncomp (<= 8) components solved together with the one matrix -- the qlen components of the quaternion block,
+ * which QuatLevelSolver::solveSystem solves depth by depth with the same matrix (QuatLevelSolver.cc:1386-1635):
+ * rhs / soln of ampe_mg_solve are then depth-ncomp arrays; every pass updates all components and reads the
+ * coefficients once.                                                                                       */
+int ampe_mg_create_multi(int ndim, const int* n, const double* dx, int with_column_scale, int ncomp, ampe_mg** out);
+int ampe_mg_num_components(const ampe_mg* mg);
 int ampe_mg_destroy(ampe_mg* mg);
 
 /* EllipticFACOps::setM / setMConstant, setCPatchDataId / setCConstant, setDPatchDataId /

@@ -66,10 +66,11 @@ int oracle_precond_apply(void* c, int block, const double* u, double* out)
 void* oracle_precond_block(void* c, int block) { return precond_block((Ctx*)c, block); }
 
 // host loop over the product's per-cell multigrid functions, same calls as ampe_mg_* with HOST arrays
-void* oracle_mg_create(int ndim, const int* n, const double* dx, int with_s)
+void* oracle_mg_create(int ndim, const int* n, const double* dx, int with_s, int ncomp)
 {
-   return new HostMG(ndim, n, dx, with_s != 0);
+   return new HostMG(ndim, n, dx, with_s != 0, ncomp);
 }
+int oracle_mg_num_components(void* g) { return ((HostMG*)g)->numComponents(); }
 void oracle_mg_destroy(void* g) { delete (HostMG*)g; }
 int oracle_mg_set_elliptic(void* g, const double* m, int ngm, double m_const, const double* c, int ngc,
                            double c_const, const double* const* d, const double* const* d2, int ngd,

@@ -207,7 +207,8 @@ void multicomponent_multiply(const Box& b, View factor, View var, int vnc)
 // ---- (2) host loop over the product's per-cell multigrid arithmetic ------------------------------
 using ampe_mg_cell::Level;
 
-HostMG::HostMG(int ndim, const int* n, const double* dx, bool with_s) : d_ndim(ndim), d_with_s(with_s)
+HostMG::HostMG(int ndim, const int* n, const double* dx, bool with_s, int ncomp)
+    : d_ndim(ndim), d_nc(ncomp < 1 ? 1 : ncomp), d_with_s(with_s)
 {
    int cur[3] = {1, 1, 1};
    for (int d = 0; d < 3; d++) {
@@ -217,7 +218,7 @@ HostMG::HostMG(int ndim, const int* n, const double* dx, bool with_s) : d_ndim(n
    }
    for (int l = 0; l < 16; l++) {
       const size_t nc = (size_t)cur[0] * cur[1] * cur[2];
-      d_store.emplace_back(nc * ((with_s ? 1 : 0) + 3), 0.0);  // s, u, f, r
+      d_store.emplace_back(nc * ((with_s ? 1 : 0) + 3 * d_nc), 0.0);  // s, then u, f, r with d_nc components each
       d_coef.emplace_back();                                  // c, m, d0..d2: allocated when stored as arrays
       Level L;
       L.ndim = ndim;
@@ -239,9 +240,10 @@ HostMG::HostMG(int ndim, const int* n, const double* dx, bool with_s) : d_ndim(n
       L.c_const = L.m_const = 1.0;
       if (with_s) L.s = p, p += nc;
       for (int d = 0; d < 3; d++) L.d[d] = nullptr, L.d_const[d] = 0.0;
-      L.u = p, p += nc;
-      L.f = p, p += nc;
-      L.r = p, p += nc;
+      L.nc = d_nc, L.cs = (long long)nc;
+      L.u = p, p += nc * d_nc;
+      L.f = p, p += nc * d_nc;
+      L.r = p, p += nc * d_nc;
    }
 }
 
@@ -323,7 +325,7 @@ void HostMG::setFused(bool on, long long min_cells)
       T.t[1] = pick(L.n[1], d_ndim == 3 ? 8 : 16);
       T.t[2] = d_ndim == 3 ? pick(L.n[2], 8) : 1;
       if (T.t[0] < 8 || T.t[1] < 2 || T.t[2] < 1) continue;
-      d_alt_u[l].assign((size_t)nc, 0.0);
+      d_alt_u[l].assign((size_t)nc * d_nc, 0.0);
       d_tile[l] = T;
    }
 }
@@ -347,7 +349,9 @@ void HostMG::smooth(int l, int sweeps)
          for (int o2 = 0; o2 < L.n[2]; o2 += T.t[2])
             for (int o1 = 0; o1 < L.n[1]; o1 += T.t[1])
                for (int o0 = 0; o0 < L.n[0]; o0 += T.t[0])
-                  ampe_mg_cell::mg_rb_tile_pass(L, L.u, alt, tile.data(), T, o0, o1, o2, 0, 1);
+                  for (int m = 0; m < L.nc; m++)  // the device loops the components inside the block too
+                     ampe_mg_cell::mg_rb_tile_pass(L, L.f + m * L.cs, L.u + m * L.cs, alt + m * L.cs, tile.data(), T, o0,
+                                                   o1, o2, 0, 1);
          // ping-pong: the level's u lives in d_store; copy back instead of swapping owners
          std::memcpy(L.u, alt, sizeof(double) * d_alt_u[l].size());
          continue;
@@ -389,12 +393,15 @@ void HostMG::solve(const double* rhs, double* soln, int ncycles, bool symmetrize
    if (!d_set) throw std::runtime_error("HostMG::solve: coefficients not set");
    const Level& L = d_levels[0];
    const size_t nc = (size_t)L.n[0] * L.n[1] * L.n[2];
-   for (size_t o = 0; o < nc; o++) {
-      L.f[o] = (symmetrized && L.s) ? rhs[o] / L.s[o] : rhs[o];
-      L.u[o] = 0.0;
-   }
+   for (int m = 0; m < L.nc; m++)
+      for (size_t o = 0; o < nc; o++) {
+         L.f[o + m * nc] = (symmetrized && L.s) ? rhs[o + m * nc] / L.s[o] : rhs[o + m * nc];
+         L.u[o + m * nc] = 0.0;
+      }
    for (int c = 0; c < ncycles; c++) vcycle();
-   for (size_t o = 0; o < nc; o++) soln[o] = (symmetrized && L.s) ? L.u[o] * L.s[o] : L.u[o];
+   for (int m = 0; m < L.nc; m++)
+      for (size_t o = 0; o < nc; o++)
+         soln[o + m * nc] = (symmetrized && L.s) ? L.u[o + m * nc] * L.s[o] : L.u[o + m * nc];
 }
 
 void HostMG::apply(const double* u, double* out) const
@@ -507,7 +514,7 @@ int precond_setup(Ctx* c, double gamma, int ncycles, bool has_dquatdphi)
       for (size_t o = 0; o < c->quat_mobility.data.size(); o++) P.sqrt_m.data[o] = sqrt(c->quat_mobility.data[o]);
       const double* fc[3] = {nullptr, nullptr, nullptr};
       for (int a = 0; a < D; a++) fc[a] = c->face_coef.a[a].data.data();
-      if (!P.quat) P.quat.reset(new HostMG(D, n, p.dx, true));
+      if (!P.quat) P.quat.reset(new HostMG(D, n, p.dx, true, p.qlen));
       P.quat->setQuat(gamma, c->quat_mobility.data.data(), 1, fc, 0);
    }
    // setCoefficients with d_precond_has_dquatdphi (QuatIntegrator.cc:2978-2983, 3064-3070)
@@ -590,7 +597,7 @@ int precond_solve(Ctx* c, const ampe_rhs_fields* r, const ampe_rhs_fields* z)
          for (size_t o = 0; o < nc * (size_t)p.qlen; o++) P.quat_rhs.data[o] = P.gamma * P.quat_rhs.data[o] + r->quat[o];
          rq = P.quat_rhs.data.data();
       }
-      for (int m = 0; m < p.qlen; m++) P.quat->solve(rq + nc * m, z->quat + nc * m, P.ncycles, true);
+      P.quat->solve(rq, z->quat, P.ncycles, true);  // all qlen components in one pass per sweep
    }
    if (p.with_unsteady_temperature) P.temp->solve(r->temperature, z->temperature, P.ncycles, false);
    if (p.with_concentration) {

@@ -21,7 +21,9 @@ void quat_stencil_apply(const Box& b, const double* h, double gamma, View sqrt_m
 class HostMG
 {
  public:
-   HostMG(int ndim, const int* n, const double* dx, bool with_s);
+   // ncomp components solved together with one matrix (the quaternion block: qlen)
+   HostMG(int ndim, const int* n, const double* dx, bool with_s, int ncomp = 1);
+   int numComponents() const { return d_nc; }
    void setElliptic(const double* m, int ngm, double m_const, const double* c, int ngc, double c_const,
                     const double* const* d, const double* const* d2, int ngd, double d_scale, double d_const);
    void setQuat(double gamma, const double* mobility, int ngm, const double* const* face_coef, int ngfc);
@@ -42,6 +44,7 @@ class HostMG
    void smooth(int l, int sweeps);
    void vcycle();
    int d_ndim;
+   int d_nc = 1;
    bool d_with_s;
    bool d_set = false;
    int d_n[3];

@@ -119,7 +119,9 @@ def lib(perf=False):
         L.oracle_precond_block.restype = vp
         L.oracle_precond_block.argtypes = [vp, ci]
         L.oracle_mg_create.restype = vp
-        L.oracle_mg_create.argtypes = [ci, vp, vp, ci]
+        L.oracle_mg_create.argtypes = [ci, vp, vp, ci, ci]
+        L.oracle_mg_num_components.restype = ci
+        L.oracle_mg_num_components.argtypes = [vp]
         L.oracle_mg_destroy.argtypes = [vp]
         L.oracle_mg_set_elliptic.restype = ci
         L.oracle_mg_set_elliptic.argtypes = [vp, vp, ci, dbl, vp, ci, dbl, pvp, pvp, ci, dbl, dbl]
@@ -309,14 +311,15 @@ class HostMG:
     """host loop over the product's per-cell multigrid functions (oracle/precond.cc part 2): the same
     calls as ampe_b200's device solver (ampe_mg_*), on numpy arrays"""
 
-    def __init__(self, n=None, dx=None, with_s=False, handle=None, owner=None):
+    def __init__(self, n=None, dx=None, with_s=False, handle=None, owner=None, ncomp=1):
+        """ncomp components solved together with one matrix (rhs / solution arrays of shape (ncomp, nz, ny, nx))"""
         self.L = lib()
         self._owner = owner  # borrowed handle of an Oracle context
         if handle is not None:
             self.h, self._own = handle, False
         else:
             self.h = self.L.oracle_mg_create(len(n), _ivec(n), (C.c_double * 3)(*(list(dx) + [0.0] * (3 - len(dx)))),
-                                             1 if with_s else 0)
+                                             1 if with_s else 0, int(ncomp))
             self._own = True
         self._keep = []
 

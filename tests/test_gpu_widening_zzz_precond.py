@@ -411,3 +411,32 @@ def test_cahnhilliard_regression_deck_on_the_device(tmp_path):
     assert c.max() - c.min() > 0.3
     h.close()
     diag.close()
+
+
+@pytest.mark.parametrize("n,dx", [((128, 96), (0.3, 0.2)), ((32, 16, 24), (1.0, 1.0, 1.0))])
+def test_components_solved_together_on_the_device(n, dx):
+    """ampe_mg_create_multi: the four quaternion components in one solver (every pass updates all of them) ==
+    four separate device solves bit for bit, == the host loop to 1e-12"""
+    from ampe_b200.precond import LevelSolver
+    from oracle import pyoracle
+    ndim = len(n)
+    shape = (n[2] if ndim == 3 else 1, n[1], n[0])
+    mob = 0.1 + np.random.default_rng(61).random(shape)
+    fc = [_side_from_lower(-(5.0 + 20.0 * np.random.default_rng(62 + a).random(shape)), 2 - a) for a in range(ndim)]
+    rhs = np.random.default_rng(63).standard_normal((4,) + shape)
+    mob_g = _ghosted(mob, 1, ndim)
+
+    def device(ncomp):
+        g = LevelSolver(n, dx, with_column_scale=True, ncomp=ncomp)
+        g.set_quat(0.37, _cuda(mob_g), 1, [_cuda(x) for x in fc], 0)
+        return g
+    g4, g1 = device(4), device(1)
+    together = g4.solve(_cuda(rhs), ncycles=3, symmetrized=True)
+    separate = torch.stack([g1.solve(_cuda(rhs[m]), ncycles=3, symmetrized=True) for m in range(4)])
+    assert torch.equal(together, separate)
+    h = pyoracle.HostMG(n, dx, with_s=True, ncomp=4)
+    h.set_quat(0.37, mob_g, 1, fc, 0)
+    zh = h.solve(rhs, ncycles=3, symmetrized=True)
+    assert np.abs(together.cpu().numpy() - zh).max() <= 1e-12 * np.abs(zh).max()
+    g4.close()
+    g1.close()

@@ -490,3 +490,26 @@ def test_left_preconditioning_like_the_reference(name, mult):
     for k, v in runs[False][0].items():
         if v is not None:
             assert np.abs(runs[True][0][k] - v).max() < 1e-8 * max(np.abs(v).max(), 1e-300), k
+
+
+@pytest.mark.parametrize("n,dx,fused", [((96, 80), (0.3, 0.2), False), ((96, 80), (0.3, 0.2), True),
+                                        ((32, 16, 24), (1.0, 1.0, 1.0), True)])
+def test_components_solved_together_equal_separate_solves(n, dx, fused):
+    """the qlen components of the quaternion block share one matrix: one solver with ncomp components (every
+    pass updates all of them, coefficients read once) == one solve per component, bit for bit"""
+    ndim = len(n)
+    shape = (n[2] if ndim == 3 else 1, n[1], n[0])
+    mob = 0.1 + np.random.default_rng(61).random(shape)
+    fc = [_side_from_lower(-(5.0 + 20.0 * np.random.default_rng(62 + a).random(shape)), 2 - a) for a in range(ndim)]
+    rhs = np.random.default_rng(63).standard_normal((4,) + shape)
+
+    def solver(ncomp):
+        mg = pyoracle.HostMG(n, dx, with_s=True, ncomp=ncomp)
+        mg.set_quat(0.37, _ghosted(mob, 1, ndim), 1, fc, 0)
+        if fused:
+            assert mg.set_fused(True, min_cells=256) >= 1
+        return mg
+    together = solver(4).solve(rhs, ncycles=3, symmetrized=True)
+    one = solver(1)
+    separate = np.stack([one.solve(rhs[m], ncycles=3, symmetrized=True) for m in range(4)])
+    assert together.shape == separate.shape and np.array_equal(together, separate)

@@ -22,8 +22,8 @@ import ampe_b200.rhs as rhs  # noqa: E402
 
 
 class FakeLevelSolver:
-    def __init__(self, n=None, dx=None, with_column_scale=False, handle=None, owner=None):
-        self.g = handle if handle is not None else pyoracle.HostMG(n, dx, with_s=with_column_scale)
+    def __init__(self, n=None, dx=None, with_column_scale=False, handle=None, owner=None, ncomp=1):
+        self.g = handle if handle is not None else pyoracle.HostMG(n, dx, with_s=with_column_scale, ncomp=ncomp)
         self.launches = 3 if os.environ.get("AMPE_B200_MG_TAIL") == "0" else 1  # the switch is read at creation
 
     @staticmethod
