@@ -6,6 +6,7 @@ AMPE_B200_RUN_EXPERIMENTS=1 timeout -k 5 400 python -m pytest tests/test_gpu_wid
   > gpurun_out/pytest_precond.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_precond.log
 tail -15 gpurun_out/pytest_precond.log
 timeout -k 5 300 python tools/bench_precond.py > gpurun_out/bench_precond.jsonl 2> gpurun_out/bench_precond.err
+timeout -k 5 300 python tools/bench_precond.py --quat >> gpurun_out/bench_precond.jsonl 2>> gpurun_out/bench_precond.err
 AMPE_B200_MG_TAIL=0 timeout -k 5 300 python tools/bench_precond.py >> gpurun_out/bench_precond.jsonl 2>> gpurun_out/bench_precond.err
 AMPE_B200_MG_FUSED=0 timeout -k 5 300 python tools/bench_precond.py >> gpurun_out/bench_precond.jsonl 2>> gpurun_out/bench_precond.err
 AMPE_B200_MG_GRAPH=1 timeout -k 5 300 python tools/bench_precond.py --stream >> gpurun_out/bench_precond.jsonl 2>> gpurun_out/bench_precond.err
