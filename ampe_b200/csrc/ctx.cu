@@ -258,6 +258,9 @@ static int dispatch_q(const FusedArgs& A, cudaStream_t st, int* nlaunch)
 // ---- context ------------------------------------------------------------------------------
 static long long slab_ghosted_cells(const ampe_rhs_ctx* c) { return c->plane * (c->ns + 2LL * c->ng); }
 
+static int alloc_device_arrays(ampe_rhs_ctx* c);
+extern "C" int ampe_rhs_destroy(ampe_rhs_ctx* c);
+
 extern "C" int ampe_rhs_create(const ampe_rhs_config* cfg, ampe_rhs_ctx** out)
 {
    if (!cfg || !out) return set_err(AMPE_EINVAL, "null argument");
@@ -282,7 +285,22 @@ extern "C" int ampe_rhs_create(const ampe_rhs_config* cfg, ampe_rhs_ctx** out)
    memset(&c->halo_hi, 0, sizeof(c->halo_hi));
    memset(&c->dev_y, 0, sizeof(c->dev_y));
    memset(&c->dev_ydot, 0, sizeof(c->dev_ydot));
+   // any failure below releases what was allocated so far and hands no context back
+   rc = alloc_device_arrays(c);
+   if (rc) {
+      ampe_rhs_destroy(c);
+      *out = nullptr;
+      return rc;
+   }
    *out = c;
+   return AMPE_OK;
+}
+
+static int alloc_device_arrays(ampe_rhs_ctx* c)
+{
+   const Params& p = c->p;
+   const ampe_rhs_config* cfg = &c->cfg;
+   int rc = AMPE_OK;
    const size_t gb = (size_t)slab_ghosted_cells(c) * sizeof(double);
    if (p.conc_form == AMPE_CONC_KKS || p.conc_form == AMPE_CONC_EBS) {
       CUDA_OK(cudaMalloc(&c->cl, gb));
@@ -594,11 +612,11 @@ int ampe_launch_energy(ampe_rhs_ctx* c, const ampe_rhs_fields* y, cudaStream_t s
       nb *= (ns + TY - 1) / TY;
    else
       nb *= (long long)((p.n[1] + TY - 1) / TY) * ((ns + TZ - 1) / TZ);
-   if (nb > c->partials_cap) {
-      cudaFree(c->partials);
-      c->partials = nullptr;
-      CUDA_OK(cudaMalloc(&c->partials, (size_t)nb * 6 * sizeof(double)));
-      c->partials_cap = nb;
+   // one allocator for the per-block partial sums (vecops.cu): the capacity is counted in blocks of
+   // 8 doubles everywhere, so an energy evaluation can never leave a buffer the reductions overrun
+   {
+      int rc = ampe_ensure_scratch(c, nb);
+      if (rc) return rc;
    }
    *nblocks = nb;
    Ranges kks, cells;

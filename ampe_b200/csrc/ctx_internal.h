@@ -44,5 +44,7 @@ struct ampe_rhs_ctx {
 };
 
 int ampe_set_err(int code, const std::string& msg);
+// per-block partial sums of the reductions: room for `nblocks` blocks of 8 doubles (vecops.cu)
+int ampe_ensure_scratch(ampe_rhs_ctx* c, long long nblocks);
 // one evaluation of the fused kernel family in "energy" mode (ctx.cu): fills c->partials
 int ampe_launch_energy(ampe_rhs_ctx* c, const ampe_rhs_fields* y, cudaStream_t st, long long* nblocks);

@@ -230,16 +230,31 @@ int ampe_k_anisotropic_gradient_flux(int ndim, const int* ifirst, const int* ila
 int ampe_k_computerhspbg(int ndim, const int* ifirst, const int* ilast, const double* dx,
                          double misorientation_factor, double epsilonq, double* const* flux,
                          int ngflux, const double* temp, int ngtemp, double phi_well_scale,
-                         const double* phi, int ngphi, const double* orient_grad_mod, int ngogm,
-                         double* rhs, int ngrhs, char phi_well_type, char orient_interp_type1,
-                         char orient_interp_type2, int with_orient, void* stream)
+                         double eta_well_scale, const double* phi, int ngphi, const double* eta, int ngeta,
+                         const double* orient_grad_mod, int ngogm, double* rhs, int ngrhs,
+                         const char* phi_well_type, const char* eta_well_type, const char* phi_interp_type,
+                         const char* orient_interp_type1, const char* orient_interp_type2, int with_orient,
+                         int three_phase, void* stream)
 {
-   if (phi_well_type != 'd' && phi_well_type != 's')
+   // full argument list of COMPUTERHSPBG (QuatFort.h:90-110, 2d/quatrhs.m4:264-405): character arguments by
+   // pointer as Fortran takes them, the eta block only dereferenced when three_phase != 0
+   if (!phi_well_type || !orient_interp_type1 || !orient_interp_type2)
+      return ampe_set_err(AMPE_EINVAL, "computerhspbg: null character argument");
+   const char pwt = phi_well_type[0], oi1 = orient_interp_type1[0], oi2 = orient_interp_type2[0];
+   if (pwt != 'd' && pwt != 's')
       return ampe_set_err(AMPE_EINVAL, "Error in deriv_well_func: type unknown");
+   char ewt = 'd', pit = 'p';
+   if (three_phase != 0) {
+      if (!eta || !eta_well_type || !phi_interp_type)
+         return ampe_set_err(AMPE_EINVAL, "computerhspbg: three_phase needs eta, eta_well_type and phi_interp_type");
+      ewt = eta_well_type[0], pit = phi_interp_type[0];
+      if (ewt != 'd' && ewt != 's') return ampe_set_err(AMPE_EINVAL, "Error in well_func: type unknown");
+   }
    const Box b = mkbox(ndim, ifirst, ilast);
    const DV3 fl = sides(flux, b, ngflux);
    const CV T = view(temp, b, -1, ngtemp), ph = view(phi, b, -1, ngphi);
    const CV ogm = view(orient_grad_mod, b, -1, ngogm);
+   const CV et = view(three_phase != 0 ? eta : phi, b, -1, three_phase != 0 ? ngeta : ngphi);
    const DV r = view(rhs, b, -1, ngrhs);
    double di[3] = {0, 0, 0};
    for (int d = 0; d < ndim; d++) di[d] = 1.0 / dx[d];
@@ -252,10 +267,15 @@ int ampe_k_computerhspbg(int ndim, const int* ifirst, const int* ilast, const do
       diff_term = diff_term + (fl.a[1](i, j + 1, k) - fl.a[1](i, j, k)) * d1;
       if (ndim == 3) diff_term = diff_term + (fl.a[2](i, j, k + 1) - fl.a[2](i, j, k)) * d2;
       double v = diff_term;
-      v = v - phi_well_scale * deriv_well_func(ph(i, j, k), phi_well_type);
+      v = v - phi_well_scale * deriv_well_func(ph(i, j, k), pwt);
+      if (three_phase != 0) {
+         // eta energy well (2d/quatrhs.m4:356-372)
+         const double h_prime = deriv_interp_func(ph(i, j, k), pit);
+         v = v - eta_well_scale * h_prime * well_func(et(i, j, k), ewt);
+      }
       if (with_orient != 0) {
-         const double p1 = deriv_interp_func(ph(i, j, k), orient_interp_type1);
-         const double p2 = deriv_interp_func(ph(i, j, k), orient_interp_type2);
+         const double p1 = deriv_interp_func(ph(i, j, k), oi1);
+         const double p2 = deriv_interp_func(ph(i, j, k), oi2);
          v = v - misorientation_factor * T(i, j, k) * p1 * ogm(i, j, k) -
              p2 * epsilonq2 * ogm(i, j, k) * ogm(i, j, k);
       }

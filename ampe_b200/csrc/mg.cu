@@ -57,7 +57,9 @@ struct ampe_mg {
    int tail_level = -1;  // first level handled by the one-block tail kernel (-1: none)
    // fused red-black sweep (mg_rb_tile_pass): per level the second u array of the ping-pong and the tile
    // shape; t[0] == 0: the level uses the two colour half-sweeps
-   std::vector<double*> alt_u;
+   // alt_u[l] is the partner of Level.u and is SWAPPED with it after every sweep, so after an odd number of
+   // sweeps it points into blocks[l]; alt_owned[l] keeps the allocation made for it and is what destroy frees
+   std::vector<double*> alt_u, alt_owned;
    std::vector<ampe_mg_cell::TileShape> tile;
    // AMPE_B200_MG_GRAPH=1 (opt-in): the launches of one solve captured once per (rhs, soln, cycles, form)
    bool use_graph = false;
@@ -176,7 +178,8 @@ __global__ void mg_apply_kernel(Level L, const double* u, double* out)
         idx += (long long)gridDim.x * blockDim.x) {
       int i, j, k;
       decode(L, idx, i, j, k);
-      out[idx] = mg_apply_cell(L, u, i, j, k);
+      // every component of a multi-component solver (quaternion block): one matrix, component stride L.cs
+      for (int m = 0; m < L.nc; m++) out[idx + m * L.cs] = mg_apply_cell(L, u + m * L.cs, i, j, k);
    }
 }
 // f = rhs (divided by s: QuatFACOps::divideMobilitySqrt), u = 0
@@ -521,6 +524,7 @@ int ampe_mg_create_multi(int ndim, const int* n, const double* dx, int with_colu
    const char* fused_env = getenv("AMPE_B200_MG_FUSED");
    const bool fused = !(fused_env && fused_env[0] == '0') && !g->use_graph;
    g->alt_u.assign(g->levels.size(), nullptr);
+   g->alt_owned.assign(g->levels.size(), nullptr);
    g->tile.assign(g->levels.size(), TileShape{{0, 0, 0}});
    for (size_t l = 0; fused && l < g->levels.size(); l++) {
       const Level& L = g->levels[l];
@@ -540,6 +544,7 @@ int ampe_mg_create_multi(int ndim, const int* n, const double* dx, int with_colu
          cudaGetLastError();
          continue;
       }
+      g->alt_owned[l] = g->alt_u[l];
       g->tile[l] = T;
    }
    *out = g;
@@ -556,7 +561,7 @@ int ampe_mg_destroy(ampe_mg* g)
    if (!g) return AMPE_OK;
    if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec);
    for (double* b : g->blocks) cudaFree(b);
-   for (double* b : g->alt_u) cudaFree(b);
+   for (double* b : g->alt_owned) cudaFree(b);
    for (double* b : g->own_c) cudaFree(b);
    for (double* b : g->own_m) cudaFree(b);
    for (int a = 0; a < 3; a++)

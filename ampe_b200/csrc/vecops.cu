@@ -294,7 +294,9 @@ __global__ void scalar_diag_final_kernel(const double* partial, long long nblock
    out[v] = r;
 }
 
-int ensure_scratch(ampe_rhs_ctx* c, long long nblocks)
+}  // namespace
+
+int ampe_ensure_scratch(ampe_rhs_ctx* c, long long nblocks)
 {
    if (nblocks > c->partials_cap) {
       cudaFree(c->partials);
@@ -306,10 +308,12 @@ int ensure_scratch(ampe_rhs_ctx* c, long long nblocks)
    return AMPE_OK;
 }
 
+namespace {
+
 template <int MODE>
 int reduce_components(ampe_rhs_ctx* c, const Comp& v, double* host_out, cudaStream_t st)
 {
-   int rc = ensure_scratch(c, RED_BLOCKS);
+   int rc = ampe_ensure_scratch(c, RED_BLOCKS);
    if (rc) return rc;
    for (int n = 0; n < v.n; n++) {
       const int blocks = (int)((v.len[n] + VT - 1) / VT < RED_BLOCKS ? (v.len[n] + VT - 1) / VT : RED_BLOCKS);
@@ -395,7 +399,7 @@ extern "C" int ampe_vec_wdot(ampe_rhs_ctx* c, const ampe_rhs_fields* x, const am
    Comp v, vw;
    int rc = components(c, x, y, nullptr, v);
    if (!rc) rc = components(c, w, nullptr, nullptr, vw);
-   if (!rc) rc = ensure_scratch(c, RED_BLOCKS);
+   if (!rc) rc = ampe_ensure_scratch(c, RED_BLOCKS);
    if (rc) return rc;
    cudaStream_t st = (cudaStream_t)stream;
    for (int n = 0; n < v.n; n++) {
@@ -452,7 +456,7 @@ extern "C" int ampe_energy_eval(ampe_rhs_ctx* c, const ampe_rhs_fields* y, doubl
    if (p.conc_form == AMPE_CONC_CAHN_HILLIARD) {
       if (!y->conc) return ampe_set_err(AMPE_EINVAL, "conc missing");
       nblocks = RED_BLOCKS;
-      int rc = ensure_scratch(c, nblocks);
+      int rc = ampe_ensure_scratch(c, nblocks);
       if (rc) return rc;
       ChArgs A;
       A.p = p;
@@ -477,7 +481,7 @@ extern "C" int ampe_energy_eval(ampe_rhs_ctx* c, const ampe_rhs_fields* y, doubl
       if (!p.with_phase) return AMPE_OK;  // QuatModel.cc:4953: no evaluator without a phase field
       if (p.ndim == 3 && p.nu > 0.0)
          return ampe_set_err(AMPE_EINVAL, "3D anisotropic interface energy is not on the path");
-      int rc = ensure_scratch(c, 1);
+      int rc = ampe_ensure_scratch(c, 1);
       if (rc) return rc;
       rc = ampe_launch_energy(c, y, st, &nblocks);
       if (rc) return rc;
@@ -564,7 +568,7 @@ extern "C" int ampe_scalar_diagnostics(ampe_rhs_ctx* c, const ampe_rhs_fields* y
       return ampe_set_err(AMPE_EINVAL, "scalar diagnostics: a component of y is NULL");
    cudaStream_t st = (cudaStream_t)stream;
    const int blocks = (int)((c->ncell + VT - 1) / VT < RED_BLOCKS ? (c->ncell + VT - 1) / VT : RED_BLOCKS);
-   int rc = ensure_scratch(c, RED_BLOCKS);
+   int rc = ampe_ensure_scratch(c, RED_BLOCKS);
    if (rc) return rc;
    scalar_diag_kernel<<<blocks, VT, 0, st>>>(p.with_phase ? y->phase : nullptr, p.with_conc ? y->conc : nullptr,
                                             p.with_T ? y->temperature : nullptr, c->ncell, c->partials);

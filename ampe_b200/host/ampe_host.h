@@ -793,12 +793,15 @@ class PhaseRHSStrategyWithQ : public PhaseRHSStrategy
       const int with_orient = d_cfg.evolve_quat ? 1 : 0;
       double* qgm = with_orient ? patch->cell<double>(d_quat_grad_modulus_id)->getPointer() : nullptr;
       auto f = flux->pointers(0);
-      // well_func_type = 'd' (PhaseRHSStrategyWithQ.cc:243)
+      const char well_func_type = 'd';
+      const char interpf = d_cfg.energy_interp;
+      const char oi1 = d_cfg.orient_interp1, oi2 = d_cfg.orient_interp2;
+      // PhaseRHSStrategyWithQ.cc:247-263 argument for argument (two-phase models: no eta, three_phase = 0)
       check(ampe_k_computerhspbg(AMPE_BOX_ARGS(patch), patch->getDx(), 2.0 * d_cfg.H_parameter,
                                  d_cfg.epsilon_q, f.data(), flux->getGhostCellWidth(), T->getPointer(),
-                                 T->getGhostCellWidth(), d_cfg.phi_well_scale, phase->getPointer(),
-                                 phase->getGhostCellWidth(), qgm, 0, rhs->getPointer(), 0, 'd',
-                                 d_cfg.orient_interp1, d_cfg.orient_interp2, with_orient, nullptr),
+                                 T->getGhostCellWidth(), d_cfg.phi_well_scale, 0.0, phase->getPointer(),
+                                 phase->getGhostCellWidth(), nullptr, 0, qgm, 0, rhs->getPointer(), 0,
+                                 &well_func_type, &well_func_type, &interpf, &oi1, &oi2, with_orient, 0, nullptr),
             "COMPUTERHSPBG");
       if (d_free_energy_strategy)
          d_free_energy_strategy->addDrivingForce(time, *patch, d_temperature_scratch_id,

@@ -38,13 +38,16 @@ int ampe_k_anisotropic_gradient_flux(int ndim, const int* ifirst, const int* ila
                                      const double* dx, double epsilon, double nu, int knumber,
                                      const double* phase, int ngphase, const double* quat, int ngq,
                                      int qlen, double* const* flux, int ngflux, void* stream);
-/* COMPUTERHSPBG (QuatFort.h:90), three_phase = 0 */
+/* COMPUTERHSPBG (QuatFort.h:90-110): the reference's full argument list in its order (character arguments by
+ * pointer, as Fortran takes them); eta / eta_well_type / phi_interp_type are read only when three_phase != 0 */
 int ampe_k_computerhspbg(int ndim, const int* ifirst, const int* ilast, const double* dx,
                          double misorientation_factor, double epsilonq, double* const* flux,
                          int ngflux, const double* temp, int ngtemp, double phi_well_scale,
-                         const double* phi, int ngphi, const double* orient_grad_mod, int ngogm,
-                         double* rhs, int ngrhs, char phi_well_type, char orient_interp_type1,
-                         char orient_interp_type2, int with_orient, void* stream);
+                         double eta_well_scale, const double* phi, int ngphi, const double* eta, int ngeta,
+                         const double* orient_grad_mod, int ngogm, double* rhs, int ngrhs,
+                         const char* phi_well_type, const char* eta_well_type, const char* phi_interp_type,
+                         const char* orient_interp_type1, const char* orient_interp_type2, int with_orient,
+                         int three_phase, void* stream);
 /* PHASERHS_FENERGY (2d/quatrhs.m4:587) */
 int ampe_k_phaserhs_fenergy(int ndim, const int* ifirst, const int* ilast, const double* fl,
                             const double* fa, const double* phi, int ngphi, double* rhs, int ngrhs,

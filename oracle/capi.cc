@@ -323,4 +323,30 @@ double oracle_calphad_diffusion_mobility(const ampe_calphad_binary* db, int phas
 {
    return calphad_diffusion_mobility_binary(*db, phase, c0, T);
 }
+// piecewise entry points of quatrhs.m4 for the GPU tests of the ampe_k_* kernels
+void oracle_k_anisotropic_gradient_flux(int ndim, const int* lo, const int* hi, const double* dx, double epsilon,
+                                        double nu, int knumber, double* phase, int ngphase, double* quat, int ngq,
+                                        int qlen, double* const* flux, int ngflux)
+{
+   Box b = mkbox(ndim, lo, hi);
+   View f[3];
+   for (int a = 0; a < ndim; a++) f[a] = make_view(flux[a], b, a, ngflux, 1);
+   anisotropic_gradient_flux(b, dx, epsilon, nu, knumber, make_view(phase, b, -1, ngphase, 1),
+                             make_view(quat, b, -1, ngq, qlen), qlen, f);
+}
+void oracle_k_computerhspbg(int ndim, const int* lo, const int* hi, const double* dx, double misorientation_factor,
+                            double epsilonq, double* const* flux, int ngflux, double* temp, int ngtemp,
+                            double phi_well_scale, double eta_well_scale, double* phi, int ngphi, double* eta,
+                            int ngeta, double* ogm, int ngogm, double* rhs, int ngrhs, char phi_well_type,
+                            char eta_well_type, char phi_interp_type, char oi1, char oi2, int with_orient,
+                            int three_phase)
+{
+   Box b = mkbox(ndim, lo, hi);
+   View f[3];
+   for (int a = 0; a < ndim; a++) f[a] = make_view(flux[a], b, a, ngflux, 1);
+   computerhspbg(b, dx, misorientation_factor, epsilonq, f, make_view(temp, b, -1, ngtemp, 1), phi_well_scale,
+                 eta_well_scale, make_view(phi, b, -1, ngphi, 1), eta ? make_view(eta, b, -1, ngeta, 1) : View(),
+                 ogm ? make_view(ogm, b, -1, ngogm, 1) : View(), make_view(rhs, b, -1, ngrhs, 1), phi_well_type,
+                 eta_well_type, phi_interp_type, oi1, oi2, with_orient, three_phase);
+}
 }

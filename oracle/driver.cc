@@ -243,9 +243,11 @@ int eval(Ctx* c, double time, const ampe_rhs_fields* y, const ampe_rhs_fields* y
          compute_free_energies(c);  // computeFreeEnergyLiquid / SolidA
 
       // PhaseRHSStrategyWithQ.cc:243-263
+      // (two-phase models: ptr_eta = NULL, eta_well_scale unused, three_phase = 0)
       computerhspbg(b, p.dx, 2.0 * p.H_parameter, p.epsilon_q, flux, c->temp.v,
-                    p.phi_well_scale, c->phase.v, c->quat_grad_modulus.v, c->rhs_phase.v, 'd',
-                    p.orient_interp1, p.orient_interp2, p.evolve_quat ? 1 : 0);
+                    p.phi_well_scale, 0.0, c->phase.v, View(), c->quat_grad_modulus.v,
+                    c->rhs_phase.v, 'd', 'd', p.energy_interp, p.orient_interp1, p.orient_interp2,
+                    p.evolve_quat ? 1 : 0, 0);
 
       // addDrivingForce
       if (p.free_energy == AMPE_FE_BIASWELL) {

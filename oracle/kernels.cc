@@ -249,11 +249,13 @@ void anisotropic_gradient_flux(const Box& b, const double* h, double epsilon, do
    }
 }
 
-// computerhspbg: 2d/quatrhs.m4:264-405, 3d/quatrhs.m4:357-515 (three_phase=0)
+// computerhspbg: 2d/quatrhs.m4:264-405, 3d/quatrhs.m4:357-515 (full argument list; the eta block runs
+// only for three_phase != 0)
 void computerhspbg(const Box& b, const double* dx, double misorientation_factor,
-                   double epsilonq, View* flux, View temp, double phi_well_scale, View phi,
-                   View orient_grad_mod, View rhs, char phi_well_type, char orient_interp1,
-                   char orient_interp2, int with_orient)
+                   double epsilonq, View* flux, View temp, double phi_well_scale,
+                   double eta_well_scale, View phi, View eta, View orient_grad_mod, View rhs,
+                   char phi_well_type, char eta_well_type, char energy_interp_type,
+                   char orient_interp1, char orient_interp2, int with_orient, int three_phase)
 {
    double dinv[3];
    for (int d = 0; d < b.ndim; d++) dinv[d] = 1.0 / dx[d];
@@ -267,6 +269,15 @@ void computerhspbg(const Box& b, const double* dx, double misorientation_factor,
       rhs(i, j, k) = diff_term;
       const double g_prime = deriv_well_func(phi(i, j, k), phi_well_type);
       rhs(i, j, k) = rhs(i, j, k) - phi_well_scale * g_prime;
+   }
+   if (three_phase != 0) {
+      // eta energy well
+      FOR_CELLS(b, i, j, k)
+      {
+         const double h_prime = deriv_interp_func(phi(i, j, k), energy_interp_type);
+         const double g = well_func(eta(i, j, k), eta_well_type);
+         rhs(i, j, k) = rhs(i, j, k) - eta_well_scale * h_prime * g;
+      }
    }
    if (with_orient != 0) {
       FOR_CELLS(b, i, j, k)

@@ -107,9 +107,10 @@ void compute_flux_isotropic(const Box& b, const double* h, double epsilon, View 
 void anisotropic_gradient_flux(const Box& b, const double* h, double epsilon, double nu,
                                int knumber, View phase, View quat, int qlen, View* flux);
 void computerhspbg(const Box& b, const double* dx, double misorientation_factor,
-                   double epsilonq, View* flux, View temp, double phi_well_scale, View phi,
-                   View orient_grad_mod, View rhs, char phi_well_type, char orient_interp1,
-                   char orient_interp2, int with_orient);
+                   double epsilonq, View* flux, View temp, double phi_well_scale,
+                   double eta_well_scale, View phi, View eta, View orient_grad_mod, View rhs,
+                   char phi_well_type, char eta_well_type, char energy_interp_type,
+                   char orient_interp1, char orient_interp2, int with_orient, int three_phase);
 void phaserhs_fenergy(const Box& b, View fl, View fa, View phi, View rhs, char interp);
 void computerhstemp(const Box& b, const double* dx, double thermal_diffusivity,
                     double latent_heat, View temp, View cp, int with_phase, View phi_rhs,

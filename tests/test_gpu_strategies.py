@@ -77,3 +77,102 @@ def test_anisotropic_3d_piecewise_kernel():
     torch.cuda.synchronize()
     for a in range(3):
         assert torch.allclose(fl[a], fa[a], rtol=1e-13, atol=1e-13)
+
+
+def _side_shapes(n):
+    ndim = len(n)
+    shp = []
+    for a in range(ndim):
+        ext = [n[d] + (1 if d == a else 0) for d in range(ndim)]
+        shp.append(tuple(reversed(ext)))
+    return shp
+
+
+@pytest.mark.parametrize("n,eps4", [((12, 10, 8), 0.05), ((9, 11, 7), 0.02)])
+def test_anisotropic_3d_piecewise_kernel_vs_oracle(n, eps4):
+    """3D anisotropic_gradient_flux (3d/quatrhs.m4:149-349) with eps4 != 0 against the restatement
+    (oracle/kernels.cc anisotropic_gradient_flux), 1e-12 of the largest flux"""
+    import ctypes as C
+    from ampe_b200 import lib
+    from oracle import pyoracle
+    L, O = lib.load(), pyoracle.lib()
+    ng = 1
+    rng = np.random.default_rng(11)
+    gshape = (n[2] + 2, n[1] + 2, n[0] + 2)
+    phase = rng.random(gshape)
+    quat = rng.standard_normal((4,) + gshape)
+    quat /= np.sqrt((quat * quat).sum(0, keepdims=True))
+    dx = (C.c_double * 3)(0.1, 0.11, 0.12)
+    lo = (C.c_int * 3)(0, 0, 0)
+    hi = (C.c_int * 3)(n[0] - 1, n[1] - 1, n[2] - 1)
+    shp = _side_shapes(n)
+    ref = [np.zeros(s) for s in shp]
+    pr = (C.c_void_p * 3)(*[a.ctypes.data for a in ref])
+    O.oracle_k_anisotropic_gradient_flux.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                                     C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                     C.c_int, C.c_int, C.c_void_p, C.c_int]
+    O.oracle_k_anisotropic_gradient_flux.restype = None
+    O.oracle_k_anisotropic_gradient_flux(3, lo, hi, dx, 0.25, eps4, 4, phase.ctypes.data, ng, quat.ctypes.data, ng,
+                                         4, pr, 0)
+    dphase, dquat = torch.as_tensor(phase).cuda(), torch.as_tensor(quat).cuda()
+    got = [torch.zeros(s, dtype=torch.float64).cuda() for s in shp]
+    pg = (C.c_void_p * 3)(*[f.data_ptr() for f in got])
+    L.ampe_k_anisotropic_gradient_flux.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
+                                                   C.c_double, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                                   C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    assert L.ampe_k_anisotropic_gradient_flux(3, lo, hi, dx, 0.25, eps4, 4, dphase.data_ptr(), ng,
+                                              dquat.data_ptr(), ng, 4, pg, 0, None) == 0
+    torch.cuda.synchronize()
+    for a in range(3):
+        scale = np.abs(ref[a]).max()
+        assert scale > 0
+        # the anisotropic term must matter, otherwise the comparison says nothing about eps4
+        assert np.abs(got[a].cpu().numpy() - ref[a]).max() <= 1e-12 * scale, a
+
+
+@pytest.mark.parametrize("ndim,three_phase", [(2, 0), (2, 1), (3, 1)])
+def test_computerhspbg_full_argument_list(ndim, three_phase):
+    """COMPUTERHSPBG with the reference's complete argument list (QuatFort.h:90-110), including the eta energy
+    well of the three-phase models (2d/quatrhs.m4:356-372)"""
+    import ctypes as C
+    from ampe_b200 import lib
+    from oracle import pyoracle
+    L, O = lib.load(), pyoracle.lib()
+    n = (13, 9) if ndim == 2 else (10, 7, 6)
+    rng = np.random.default_rng(5 + ndim + three_phase)
+    cell = tuple(reversed([v + 2 for v in n]))        # ghost width 1 arrays
+    cell0 = tuple(reversed(n))
+    phi, eta, temp = rng.random(cell), rng.random(cell), 900.0 + 50.0 * rng.random(cell)
+    ogm = rng.random(cell0)
+    shp = _side_shapes(n)
+    flux = [rng.standard_normal(s) for s in shp]
+    dx = (C.c_double * 3)(0.2, 0.25, 0.3)
+    lo = (C.c_int * 3)(0, 0, 0)
+    hi = (C.c_int * 3)(*([v - 1 for v in n] + [0] * (3 - ndim)))
+    ref = np.zeros(cell0)
+    pf = (C.c_void_p * 3)(*[a.ctypes.data for a in flux])
+    ci, vp, dbl, ch = C.c_int, C.c_void_p, C.c_double, C.c_char
+    O.oracle_k_computerhspbg.argtypes = [ci, vp, vp, vp, dbl, dbl, vp, ci, vp, ci, dbl, dbl, vp, ci, vp, ci, vp, ci,
+                                         vp, ci, ch, ch, ch, ch, ch, ci, ci]
+    O.oracle_k_computerhspbg.restype = None
+    O.oracle_k_computerhspbg(ndim, lo, hi, dx, 1.7, 0.3, pf, 0, temp.ctypes.data, 1, 2.5, 1.3, phi.ctypes.data, 1,
+                             eta.ctypes.data, 1, ogm.ctypes.data, 0, ref.ctypes.data, 0, b"d", b"s", b"p", b"q", b"p",
+                             1, three_phase)
+    d = lambda a: torch.as_tensor(a).cuda()
+    dphi, deta, dtemp, dogm = d(phi), d(eta), d(temp), d(ogm)
+    dflux = [d(a) for a in flux]
+    got = torch.zeros(cell0, dtype=torch.float64).cuda()
+    pg = (C.c_void_p * 3)(*[f.data_ptr() for f in dflux])
+    cp = C.c_char_p
+    L.ampe_k_computerhspbg.argtypes = [ci, vp, vp, vp, dbl, dbl, vp, ci, vp, ci, dbl, dbl, vp, ci, vp, ci, vp, ci, vp,
+                                       ci, cp, cp, cp, cp, cp, ci, ci, vp]
+    rc = L.ampe_k_computerhspbg(ndim, lo, hi, dx, 1.7, 0.3, pg, 0, dtemp.data_ptr(), 1, 2.5, 1.3, dphi.data_ptr(), 1,
+                                deta.data_ptr() if three_phase else None, 1, dogm.data_ptr(), 0, got.data_ptr(), 0,
+                                b"d", b"s", b"p", b"q", b"p", 1, three_phase, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert np.abs(got.cpu().numpy() - ref).max() <= 1e-13 * np.abs(ref).max()
+    # three_phase without eta is an argument error, as is an unknown well type
+    assert L.ampe_k_computerhspbg(ndim, lo, hi, dx, 1.7, 0.3, pg, 0, dtemp.data_ptr(), 1, 2.5, 1.3, dphi.data_ptr(),
+                                  1, None, 1, dogm.data_ptr(), 0, got.data_ptr(), 0, b"d", b"s", b"p", b"q", b"p", 1,
+                                  1, None) != 0

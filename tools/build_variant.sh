@@ -9,7 +9,7 @@ out=$root/variants/$name
 mkdir -p $out
 cd $root/ampe_b200/csrc
 pids=""
-for f in ctx vecops symmetry tma_host kernels_piecewise fused3_2d_q0 fused3_2d_q2 fused3_2d_q4 fused3_3d_q0 fused3_3d_q2 fused3_3d_q4 fused3_fixed_dendrite fused3_fixed_auni2d fused3_fixed_3d; do
+for f in $(ls *.cu | sed 's/\.cu$//'); do
   if [ -f $f.cu ]; then
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -std=c++17 --extended-lambda -Xcompiler -fPIC $flags -c -o $out/$f.o $f.cu &
   pids="$pids $!"

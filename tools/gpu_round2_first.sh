@@ -12,4 +12,4 @@ AMPE_B200_RUN_EXPERIMENTS=1 timeout -k 5 600 python -m pytest tests -m gpu -q \
 echo "pytest rc=$?" >> gpurun_out/pytest_experiments.log
 tail -25 gpurun_out/pytest_experiments.log
 bash tools/gpu_precond.sh
-bash tools/gpu_split3d.sh > gpurun_out/split3d_ab.log 2>&1; tail -12 gpurun_out/split3d_ab.log
+bash tools/gpu_split3d.sh "$@" > gpurun_out/split3d_ab.log 2>&1; tail -12 gpurun_out/split3d_ab.log
