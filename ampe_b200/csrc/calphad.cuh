@@ -6,6 +6,7 @@
 // and the in-tree CALPHADMobility.{h,cc} formulas.  Model equations:
 // doc/latex/manual/appendix.tex:517-599.
 #pragma once
+#include "fastmath.cuh"
 #include "params.h"
 #include "pointwise.cuh"
 
@@ -32,6 +33,17 @@ AMPE_DEV double xlogx_deriv2(double x)
 }
 // log(1e-8) as glibc rounds it (host-evaluated constant, same value the CPU side uses)
 #define AMPE_LOG_SMALLX (-18.420680743952367)
+// the extension branch of xlogx_deriv (x <= 1e-8)
+AMPE_DEV double xlogx_deriv_ext(double x) { return (1. + AMPE_LOG_SMALLX) + (x - AMPE_SMALLX) * (1. / AMPE_SMALLX); }
+#ifdef AMPE_KKS_LIBM_LOG
+#define AMPE_KKS_LOG(x) log(x)
+#define AMPE_KKS_RCP(x) (1.0 / (x))
+#else
+#define AMPE_KKS_LOG(x) log_fast(x)
+#define AMPE_KKS_RCP(x) rcp_fast(x)
+#endif
+// xlogx_deriv2 with the comparison already made: 1/x above the extension, 1e8 below
+AMPE_DEV double xlogx_deriv2_fast(double x, bool above) { return above ? AMPE_KKS_RCP(above ? x : 1.0) : 1. / AMPE_SMALLX; }
 
 AMPE_DEV double fmix(const double* L, double c)
 {
@@ -84,23 +96,31 @@ AMPE_DEV int kks_newton(const CalphadT& t, double c0, double hphi, double& cl, d
       const double xi0 = t.RTinv * (t.fA[0] - t.fB[0] + fmix_deriv(t.L[0], cl));
       const double xi1 = t.RTinv * (t.fA[1] - t.fB[1] + fmix_deriv(t.L[1], ca));
       const double f0 = -c0 + (1.0 - hphi) * cl + hphi * ca;
-      // xlogx_deriv(x) = log(x) + 1 above the 1e-8 extension
+      // xlogx_deriv(x) = log(x) + 1 above the 1e-8 extension.  Branch-free: the four logarithms are taken of a
+      // normal argument in every lane (log_fast, fastmath.cuh: < 1 ulp, no range handling) and interleave;
+      // the extension is a select.  AMPE_KKS_LIBM_LOG switches back to CUDA's log() (A/B builds).
       const double a0 = cl, a1 = 1. - cl, a2 = ca, a3 = 1. - ca;
-      double d0, d1, d2, d3;
-      if (a0 > AMPE_SMALLX) { lg[0] = log(a0); d0 = lg[0] + 1.0; } else d0 = xlogx_deriv(a0, AMPE_LOG_SMALLX);
-      if (a1 > AMPE_SMALLX) { lg[1] = log(a1); d1 = lg[1] + 1.0; } else d1 = xlogx_deriv(a1, AMPE_LOG_SMALLX);
-      if (a2 > AMPE_SMALLX) { lg[2] = log(a2); d2 = lg[2] + 1.0; } else d2 = xlogx_deriv(a2, AMPE_LOG_SMALLX);
-      if (a3 > AMPE_SMALLX) { lg[3] = log(a3); d3 = lg[3] + 1.0; } else d3 = xlogx_deriv(a3, AMPE_LOG_SMALLX);
+      const bool b0 = a0 > AMPE_SMALLX, b1 = a1 > AMPE_SMALLX, b2 = a2 > AMPE_SMALLX, b3 = a3 > AMPE_SMALLX;
+      lg[0] = AMPE_KKS_LOG(b0 ? a0 : 1.0);
+      lg[1] = AMPE_KKS_LOG(b1 ? a1 : 1.0);
+      lg[2] = AMPE_KKS_LOG(b2 ? a2 : 1.0);
+      lg[3] = AMPE_KKS_LOG(b3 ? a3 : 1.0);
+      const double d0 = b0 ? lg[0] + 1.0 : xlogx_deriv_ext(a0);
+      const double d1 = b1 ? lg[1] + 1.0 : xlogx_deriv_ext(a1);
+      const double d2 = b2 ? lg[2] + 1.0 : xlogx_deriv_ext(a2);
+      const double d3 = b3 ? lg[3] + 1.0 : xlogx_deriv_ext(a3);
       const double f1 = d0 - d1 - d2 + d3 + (xi0 - xi1);
       if (fabs(f0) < tol && fabs(f1) < tol) return it;
       if (it == max_its) return -1;
       const double dxi0 = t.RTinv * fmix_deriv2(t.L[0], cl);
       const double dxi1 = t.RTinv * fmix_deriv2(t.L[1], ca);
       const double J00 = (1.0 - hphi), J01 = hphi;
-      const double J10 = dxi0 + xlogx_deriv2(cl) + xlogx_deriv2(1. - cl);
-      const double J11 = -dxi1 - xlogx_deriv2(ca) - xlogx_deriv2(1. - ca);
+      // the Jacobian only steers the iteration (the converged values are fixed by the residual): its
+      // reciprocals are the straight-line ones
+      const double J10 = dxi0 + xlogx_deriv2_fast(a0, b0) + xlogx_deriv2_fast(a1, b1);
+      const double J11 = -dxi1 - xlogx_deriv2_fast(a2, b2) - xlogx_deriv2_fast(a3, b3);
       const double D = J00 * J11 - J01 * J10;
-      const double Dinv = 1.0 / D;
+      const double Dinv = AMPE_KKS_RCP(D);
       const double D0 = f0 * J11 - J01 * f1;
       const double D1 = J00 * f1 - f0 * J10;
       cl = cl - alpha * (Dinv * D0);

@@ -69,6 +69,23 @@ static void fill_calphadT(const ampe_calphad_binary& db, double T, CalphadT& o)
       }
 }
 
+// max |dG/RT| of the four atomic mobilities (getDeltaG, CALPHADMobility.cc:158-168) over c in [-1/2, 3/2]
+static double mobility_exponent_bound(const CalphadT& t)
+{
+   double worst = 0.0;
+   for (int i = 0; i <= 400; i++) {
+      const double c0 = -0.5 + 2.0 * i / 400.0, c1 = 1.0 - c0, dc = c0 - c1;
+      for (int sp = 0; sp < 2; sp++)
+         for (int ph = 0; ph < 2; ph++) {
+            const double* qq = t.qAB[sp][ph];
+            const double dG = c0 * t.qA[sp][ph] + c1 * t.qB[sp][ph] +
+                              c0 * c1 * (qq[0] + dc * (qq[1] + dc * (qq[2] + dc * qq[3])));
+            worst = fmax(worst, fabs(dG * t.RTinv));
+         }
+   }
+   return worst * 1.05;  // sampling margin
+}
+
 int ampe_derive_params(const ampe_rhs_config& c, Params& p)
 {
    memset(&p, 0, sizeof(p));
@@ -174,7 +191,13 @@ int ampe_derive_params(const ampe_rhs_config& c, Params& p)
    p.newton_max_its = c.newton_max_its;
    p.newton_tol = c.newton_tol;
    p.newton_alpha = c.newton_alpha;
-   if (c.free_energy == AMPE_FE_CALPHAD) fill_calphadT(c.calphad, T, p.ct);
+   if (c.free_energy == AMPE_FE_CALPHAD) {
+      fill_calphadT(c.calphad, T, p.ct);
+      // the face mobilities evaluate exp(dG/RT) without a range clamp (fastmath.cuh exp_fast<false>): bound the
+      // exponent over every concentration a face average can take, c in [-1/2, 3/2]
+      if (p.conc_form == AMPE_CONC_EBS && mobility_exponent_bound(p.ct) > 690.0)
+         return set_err(AMPE_EINVAL, "CALPHAD mobility parameters: |dG/RT| exceeds 690 for c in [-1/2, 3/2]");
+   }
    return AMPE_OK;
 }
 
@@ -362,6 +385,8 @@ extern "C" int ampe_rhs_destroy(ampe_rhs_ctx* c)
       cudaFree(c->dev_ydot.conc);
       cudaFree(c->dev_ydot.temperature);
    }
+   for (int i = 0; i < 3; i++)
+      if (c->ev_t[i]) cudaEventDestroy(c->ev_t[i]);
    if (c->own_stream) {
       cudaStreamDestroy(c->own_stream);
       cudaStreamDestroy(c->k_stream);
@@ -534,6 +559,8 @@ static int eval_ranges(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs
    Field fq = make_field(c, y->quat, c->halo_lo.quat, c->halo_hi.quat, p.qlen);
    Field fc = make_field(c, y->conc, c->halo_lo.conc, c->halo_hi.conc, 1);
 
+   const bool timed = c->time_kernels && first && last && !en;
+   if (timed) CUDA_OK(cudaEventRecord(c->ev_t[0], st));
    // ---- per-cell KKS solve on the slab and its ghost planes ------------------------------
    if (p.conc_form == AMPE_CONC_KKS || p.conc_form == AMPE_CONC_EBS) {
       if (p.free_energy == AMPE_FE_CALPHAD && !c->have_ref)
@@ -562,6 +589,7 @@ static int eval_ranges(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs
       }
    }
 
+   if (timed) CUDA_OK(cudaEventRecord(c->ev_t[1], st));
    FusedArgs A;
    A.p = p;
    A.phi = fphi;
@@ -597,6 +625,7 @@ static int eval_ranges(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs
       if (rc) return rc;
       c->launches += nlaunch;
    }
+   if (timed) CUDA_OK(cudaEventRecord(c->ev_t[2], st));
    if (last && A.write_lag) c->lag_valid = true;
    return AMPE_OK;
 }
@@ -704,6 +733,28 @@ extern "C" int ampe_rhs_newton_failures(ampe_rhs_ctx* c, void* stream)
 }
 
 extern "C" int ampe_rhs_last_launch_count(const ampe_rhs_ctx* c) { return c ? c->launches : 0; }
+
+// Per-kernel device times of whole-slab evaluations (bench.py's roofline of the dominant kernel): CUDA events on
+// the launching stream around the KKS pre-pass and around the fused kernel.
+extern "C" int ampe_rhs_set_kernel_timing(ampe_rhs_ctx* c, int on)
+{
+   if (!c) return set_err(AMPE_EINVAL, "null context");
+   if (on && !c->ev_t[0])
+      for (int i = 0; i < 3; i++) CUDA_OK(cudaEventCreate(&c->ev_t[i]));
+   c->time_kernels = on != 0;
+   return AMPE_OK;
+}
+extern "C" int ampe_rhs_last_kernel_ms(ampe_rhs_ctx* c, double* kks_ms, double* fused_ms)
+{
+   if (!c || !c->ev_t[0] || !kks_ms || !fused_ms) return set_err(AMPE_EINVAL, "kernel timing is not enabled");
+   float a = 0.f, b = 0.f;
+   CUDA_OK(cudaEventSynchronize(c->ev_t[2]));
+   CUDA_OK(cudaEventElapsedTime(&a, c->ev_t[0], c->ev_t[1]));
+   CUDA_OK(cudaEventElapsedTime(&b, c->ev_t[1], c->ev_t[2]));
+   *kks_ms = a;
+   *fused_ms = b;
+   return AMPE_OK;
+}
 
 extern "C" int ampe_rhs_eval_host(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* yh,
                                   const ampe_rhs_fields* ydh, int fd_flag)

@@ -39,6 +39,10 @@ struct ampe_rhs_ctx {
    double* partials = nullptr;
    long long partials_cap = 0;
    double* red_out = nullptr;
+   // opt-in per-kernel timing of one evaluation (ampe_rhs_set_kernel_timing): events on the launching stream
+   // before the KKS pre-pass, between it and the fused kernel, and after the fused kernel
+   bool time_kernels = false;
+   cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};
    cudaStream_t own_stream = nullptr, k_stream = nullptr, out_stream = nullptr;
    cudaEvent_t ev_in[AMPE_MAX_HOST_CHUNKS], ev_k[AMPE_MAX_HOST_CHUNKS];
 };

@@ -133,7 +133,7 @@ AMPE_DEV double ebs_phase_diffusivity(const CalphadT& t, int ph, double c0)
       const double* qq = t.qAB[sp][ph];
       const double poly = fma(dc, fma(dc, fma(dc, qq[3], qq[2]), qq[1]), qq[0]);
       const double dG = fma(cc, poly, fma(c0, t.qA[sp][ph], c1 * t.qB[sp][ph]));
-      m[sp] = exp_fast(dG * t.RTinv);
+      m[sp] = exp_fast<false>(dG * t.RTinv);  // range checked on the host: mobility_exponent_bound (ctx.cu)
    }
    const double mm = fma(c0, m[1], c1 * m[0]) * t.RTinv;
    if (c0 > AMPE_SMALLX && c1 > AMPE_SMALLX) {

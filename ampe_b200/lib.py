@@ -55,6 +55,10 @@ def load():
     L.ampe_rhs_newton_failures.argtypes = [vp, vp]
     L.ampe_rhs_last_launch_count.restype = ci
     L.ampe_rhs_last_launch_count.argtypes = [vp]
+    L.ampe_rhs_set_kernel_timing.restype = ci
+    L.ampe_rhs_set_kernel_timing.argtypes = [vp, ci]
+    L.ampe_rhs_last_kernel_ms.restype = ci
+    L.ampe_rhs_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     pd = C.POINTER(C.c_double)
     L.ampe_vec_linear_sum.restype = ci
     L.ampe_vec_linear_sum.argtypes = [vp, dbl, pf, dbl, pf, pf, vp]

@@ -218,6 +218,15 @@ class QuatIntegratorRHS:
     def lastLaunchCount(self):
         return self.L.ampe_rhs_last_launch_count(self.h)
 
+    def setKernelTiming(self, on=True):
+        check(self.L.ampe_rhs_set_kernel_timing(self.h, 1 if on else 0), "setKernelTiming")
+
+    def lastKernelMs(self):
+        """(KKS pre-pass, fused kernel) device times of the last whole-slab evaluation, milliseconds"""
+        a, b = C.c_double(0.0), C.c_double(0.0)
+        check(self.L.ampe_rhs_last_kernel_ms(self.h, C.byref(a), C.byref(b)), "lastKernelMs")
+        return a.value, b.value
+
 
 def to_device(state, device="cuda"):
     """dict of CPU tensors (fields.make_state) -> SolutionVector on the GPU"""

@@ -195,6 +195,12 @@ int ampe_rhs_copy_phase_concentrations(ampe_rhs_ctx* ctx, double* cl_out, double
 int ampe_rhs_newton_failures(ampe_rhs_ctx* ctx, void* stream);
 /* kernels launched by the last ampe_rhs_eval                                 */
 int ampe_rhs_last_launch_count(const ampe_rhs_ctx* ctx);
+/* Measurement aid (no reference counterpart; AMPE times these phases with its own tbox::Timer objects,
+ * QuatIntegrator.cc:3140-3160 t_rhs_timer / t_phase_conc_timer): when switched on, every whole-slab evaluation
+ * records CUDA events on its stream around the KKS pre-pass and around the fused kernel;
+ * ampe_rhs_last_kernel_ms waits for the last evaluation and returns both durations in milliseconds. */
+int ampe_rhs_set_kernel_timing(ampe_rhs_ctx* ctx, int on);
+int ampe_rhs_last_kernel_ms(ampe_rhs_ctx* ctx, double* kks_ms, double* fused_ms);
 
 /* host-buffer convenience used by the reference-facing plugin path: copies
  * y host->device, evaluates, copies ydot device->host (pinned or pageable).  */

@@ -79,8 +79,6 @@ def test_default_options_run():
     assert rc == 0 and stats["steps"] == 5
 
 
-@pytest.mark.skipif(not os.environ.get("AMPE_B200_RUN_EXPERIMENTS"),
-                    reason="written after the last GPU call of round 1: set AMPE_B200_RUN_EXPERIMENTS=1")
 def test_newton_failure_code():
     """a step far beyond what two Newton iterations can absorb comes back as IMPLICIT_ENEWTON instead of a
     silent wrong answer (the CPU run of the same template returns the same code)"""

@@ -13,9 +13,8 @@ import parity
 
 # opt-in feature, opt-in tests: they join the default GPU suite once a GPU run has shown them green
 # (tools/gpu_split3d.sh sets the variable)
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("AMPE_B200_RUN_EXPERIMENTS"),
-                                 reason="experiment: set AMPE_B200_RUN_EXPERIMENTS=1 (first GPU run pending)")]
+# first executed on a B200 in round 2 (profiles/r02a_pytest_experiments.log): green, part of the default GPU suite
+pytestmark = pytest.mark.gpu
 
 
 def _run(split, cfg, st, fds, part_sequence=(0,)):

@@ -10,7 +10,7 @@
   context's (1e-12), CVSpgmrPrecondSolve equals the CPU solve (1e-10).
 * the right-preconditioned implicit trajectory on the device against the same template driven by the CPU
   oracle: 1e-8, and fewer Krylov vectors than the unpreconditioned run.
-Added at the end of round 1 without a GPU left: first executed by a later GPU run."""
+Added at the end of round 1 without a GPU left; first executed (green) by the first GPU call of round 2."""
 import os
 
 import numpy as np
@@ -19,10 +19,8 @@ import torch
 
 import parity
 
-# new code, not yet executed on a GPU: the tests join the default GPU suite once a run has shown them green
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("AMPE_B200_RUN_EXPERIMENTS"),
-                                 reason="set AMPE_B200_RUN_EXPERIMENTS=1 (first GPU run pending)")]
+# first executed on a B200 in round 2 (profiles/r02a_pytest_experiments.log): 32 green, part of the default GPU suite
+pytestmark = pytest.mark.gpu
 
 from test_oracle_precond import BLOCKS, _evolved, _ghosted, _random_elliptic, _side_from_lower  # noqa: E402
 

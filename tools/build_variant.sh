@@ -11,7 +11,7 @@ cd $root/ampe_b200/csrc
 pids=""
 for f in $(ls *.cu | sed 's/\.cu$//'); do
   if [ -f $f.cu ]; then
-  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -std=c++17 --extended-lambda -Xcompiler -fPIC $flags -c -o $out/$f.o $f.cu &
+  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=${FMAD:-false} -std=c++17 --extended-lambda -Xcompiler -fPIC $flags -c -o $out/$f.o $f.cu &
   pids="$pids $!"
   fi
 done
