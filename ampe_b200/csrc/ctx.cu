@@ -424,7 +424,8 @@ extern "C" int ampe_rhs_set_ref_concentrations(ampe_rhs_ctx* c, const double* cl
    if (cl_ref && ca_ref) {
       if (c->cfg.nranks > 1)
          return set_err(AMPE_EINVAL,
-                        "multi-rank: pass NULL (copy last c_l,c_a incl. ghost planes)");
+                        "several ranks: use ampe_rhs_set_ref_concentrations_slab (ghost planes come from the "
+                        "neighbours), or pass NULL (copy the last c_l, c_a incl. ghost planes)");
       int rc = fill_slab_ghosted(c, c->cl_ref, cl_ref, st);
       if (rc) return rc;
       rc = fill_slab_ghosted(c, c->ca_ref, ca_ref, st);
@@ -457,7 +458,8 @@ extern "C" int ampe_rhs_set_symmetry_rotations(ampe_rhs_ctx* c, const int* const
 {
    if (!c || !c->p.symm) return set_err(AMPE_EINVAL, "context is not symmetry aware");
    if (c->cfg.nranks > 1)
-      return set_err(AMPE_EINVAL, "symmetry-aware path is single-rank in this build");
+      return set_err(AMPE_EINVAL, "several ranks: use ampe_rhs_set_symmetry_rotations_slab (the ghost planes of "
+                                  "the indices come from the neighbours)");
    for (int d = 0; d < c->p.ndim; d++) {
       int rc = fill_slab_ghosted(c, c->iq[d], iqrot[d], (cudaStream_t)stream);
       if (rc) return rc;
@@ -756,8 +758,10 @@ extern "C" int ampe_rhs_last_kernel_ms(ampe_rhs_ctx* c, double* kks_ms, double* 
    return AMPE_OK;
 }
 
-extern "C" int ampe_rhs_eval_host(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* yh,
-                                  const ampe_rhs_fields* ydh, int fd_flag)
+// h != NULL: slab rank with neighbours (halo.cu) -- the ghost planes travel device to device, pushed as soon as
+// the chunks that hold this rank's boundary planes have landed
+static int eval_host_impl(ampe_rhs_ctx* c, ampe_halo* h, double time, const ampe_rhs_fields* yh,
+                          const ampe_rhs_fields* ydh, int fd_flag)
 {
    if (!c || !yh || !ydh) return set_err(AMPE_EINVAL, "null argument");
    const Params& p = c->p;
@@ -803,7 +807,7 @@ extern "C" int ampe_rhs_eval_host(ampe_rhs_ctx* c, double time, const ampe_rhs_f
    if (nchunk > ns / (4 * ng)) nchunk = ns / (4 * ng);
    if (nchunk > AMPE_MAX_HOST_CHUNKS) nchunk = AMPE_MAX_HOST_CHUNKS;
    if (nchunk < 1) nchunk = 1;
-   if (c->have_halo) nchunk = 1;  // halo buffers: the caller sequences the exchange itself
+   if (c->have_halo && !h) nchunk = 1;  // caller-owned halo buffers: the caller sequences the exchange itself
    cudaStream_t s_in = c->own_stream, s_k = c->k_stream, s_out = c->out_stream;
    auto h2d_planes = [&](int b, int e) -> int {
       const size_t off = (size_t)b * pl, bytes = (size_t)(e - b) * pl * sizeof(double);
@@ -844,6 +848,20 @@ extern "C" int ampe_rhs_eval_host(ampe_rhs_ctx* c, double time, const ampe_rhs_f
       CUDA_OK(cudaStreamWaitEvent(s_k, c->ev_in[j], 0));
       Ranges kks, cells;
       const bool fin = (j == nchunk - 1);
+      if (h) {
+         // my lowest planes are in the first chunk, my highest in the last: push each side as soon as it is on
+         // the device; before the closing evaluation wait for the neighbours' planes
+         if (j == 0) {
+            rc = ampe_halo_push(h, &c->dev_y, 1, s_k);
+            if (rc) return rc;
+         }
+         if (fin) {
+            rc = ampe_halo_push(h, &c->dev_y, 2, s_k);
+            if (rc) return rc;
+            rc = ampe_halo_wait(h, s_k);
+            if (rc) return rc;
+         }
+      }
       if (nchunk == 1) {
          kks.add(-ng, ns + ng);
          cells.add(0, ns);
@@ -873,6 +891,18 @@ extern "C" int ampe_rhs_eval_host(ampe_rhs_ctx* c, double time, const ampe_rhs_f
    CUDA_OK(cudaStreamSynchronize(s_k));
    (void)time;
    return AMPE_OK;
+}
+
+extern "C" int ampe_rhs_eval_host(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* yh,
+                                  const ampe_rhs_fields* ydh, int fd_flag)
+{
+   return eval_host_impl(c, nullptr, time, yh, ydh, fd_flag);
+}
+extern "C" int ampe_rhs_eval_slab_host(ampe_rhs_ctx* c, ampe_halo* h, double time, const ampe_rhs_fields* yh,
+                                       const ampe_rhs_fields* ydh, int fd_flag)
+{
+   if (!h) return set_err(AMPE_EINVAL, "ampe_rhs_eval_slab_host: null halo");
+   return eval_host_impl(c, h, time, yh, ydh, fd_flag);
 }
 
 extern "C" const char* ampe_last_error(void) { return g_err.c_str(); }

@@ -366,8 +366,11 @@ int launch_symm_rotation(int depth, int a, const int* L, const int* H, CV q, IWV
 // rot_a(cell) for the LOWER face of every interior cell; neighbours wrap periodically (single rank)
 template <int Q, int ND>
 __global__ void symm_rotation_ctx_kernel(int n0, int n1, int n2, const double* __restrict__ q, int* rot0,
-                                         int* rot1, int* rot2, SymmConst sc)
+                                         int* rot1, int* rot2, SymmConst sc, const double* __restrict__ q_lo,
+                                         long long lo_comp, int ng)
 {
+   // q_lo != null (slab rank with neighbours): the ng planes below plane 0 along the slab axis (component
+   // stride lo_comp) instead of the periodic wrap inside this rank
    __shared__ double s_qr[48 * 4];
    __shared__ int s_conj[48];
    load_table(s_qr, s_conj);
@@ -386,8 +389,17 @@ __global__ void symm_rotation_ctx_kernel(int n0, int n1, int n2, const double* _
          const int jj = (a == 1) ? (j == 0 ? n1 - 1 : j - 1) : j;
          const int kk = (a == 2) ? (k == 0 ? n2 - 1 : k - 1) : k;
          const long long nb = ii + (long long)n0 * (jj + (long long)n1 * kk);
+         const bool below = q_lo && a == ND - 1 && ((ND == 3) ? k == 0 : j == 0);
+         if (below) {
+            // the neighbour's highest plane: the last of its ng ghost planes held here
+            const long long pl = (ND == 3) ? (long long)n0 * n1 : n0;
+            const long long o = (long long)(ng - 1) * pl + ((ND == 3) ? i + (long long)n0 * j : i);
 #pragma unroll
-         for (int m = 0; m < Q; m++) q2[m] = q[nb + m * ncell];
+            for (int m = 0; m < Q; m++) q2[m] = q_lo[o + m * lo_comp];
+         } else {
+#pragma unroll
+            for (int m = 0; m < Q; m++) q2[m] = q[nb + m * ncell];
+         }
          int* rot = (a == 0) ? rot0 : ((a == 1) ? rot1 : rot2);
          rot[t] = findsymm_any<Q>(s_qr, s_conj, q1, q2, rot[t], q2p, sc);
       }
@@ -464,7 +476,11 @@ int ampe_rhs_compute_symmetry_rotations(ampe_rhs_ctx* c, const ampe_rhs_fields* 
    if (!c || !y) return ampe_set_err(AMPE_EINVAL, "null argument");
    if (!c->p.symm) return ampe_set_err(AMPE_EINVAL, "context is not symmetry aware");
    if (!y->quat) return ampe_set_err(AMPE_EINVAL, "quat missing");
-   if (c->cfg.nranks > 1) return ampe_set_err(AMPE_EINVAL, "symmetry-aware path is single-rank in this build");
+   // slab rank with neighbours: the caller has exchanged the ghost planes of y (ampe_halo_push / ampe_halo_wait, or
+   // ampe_rhs_compute_symmetry_rotations_slab, which does both)
+   const bool slab = c->have_halo && c->halo_lo.quat;
+   if (c->cfg.nranks > 1 && !slab)
+      return ampe_set_err(AMPE_EINVAL, "several ranks: use ampe_rhs_compute_symmetry_rotations_slab");
    int rc = ensure_table();
    if (rc) return rc;
    const Params& p = c->p;
@@ -477,7 +493,8 @@ int ampe_rhs_compute_symmetry_rotations(ampe_rhs_ctx* c, const ampe_rhs_fields* 
    const int nb = blocks_for(c->ncell);
    const int n2 = p.ndim == 3 ? p.n[2] : 1;
 #define LAUNCH(Q, ND) \
-   symm_rotation_ctx_kernel<Q, ND><<<nb, 256, 0, st>>>(p.n[0], p.n[1], n2, y->quat, r[0], r[1], r[2], sc)
+   symm_rotation_ctx_kernel<Q, ND><<<nb, 256, 0, st>>>(p.n[0], p.n[1], n2, y->quat, r[0], r[1], r[2], sc, \
+                                                       slab ? c->halo_lo.quat : nullptr, (long long)ng * pl, ng)
    if (p.ndim == 2) {
       if (p.qlen == 4) LAUNCH(4, 2);
       else if (p.qlen == 2) LAUNCH(2, 2);
@@ -492,6 +509,7 @@ int ampe_rhs_compute_symmetry_rotations(ampe_rhs_ctx* c, const ampe_rhs_fields* 
 #undef LAUNCH
    rc = check_last("compute_symmetry_rotations");
    if (rc) return rc;
+   if (slab) return AMPE_OK;  // the ghost planes of the indices come from the neighbours (halo.cu)
    // ghost planes along the slab axis: periodic images of the interior planes
    for (int d = 0; d < p.ndim; d++) {
       int* base = c->iq[d];

@@ -3,10 +3,15 @@ replaces SAMRAI's RefineSchedule::fillData on the RHS path
 (reference: QuatIntegrator::fillScratch, source/QuatIntegrator.cc:2873-2955).
 
 One process per GPU; rank r owns planes [r*ns, (r+1)*ns) of a periodic global
-domain.  Per evaluation each rank sends its first/last `ng` planes of every
-state component to its two neighbours (NCCL send/recv over NVLink, or gloo on
-CPU for the tests) and evaluates the interior planes while the messages are in
-flight; no collective is involved (the RHS has none: SURVEY.md 8e)."""
+domain.  The exchange itself lives behind the C ABI (csrc/halo.cu, ampe_halo_* /
+ampe_rhs_eval_slab): every rank pushes its first/last `ng` planes of every state
+component straight into its neighbours' HBM over NVLink (peer-mapped receive
+buffers, epoch flags) and evaluates the interior planes meanwhile; `DistributedRHS`
+only ships the opaque set-up handles between the ranks (torch.distributed stands
+in for the MPI_Sendrecv AMPE would use).  `SlabHalo` is the torch.distributed
+(NCCL send/recv, gloo on CPU) exchange of the same planes: transport "nccl" of
+`DistributedRHS`, and what the gloo tests of the slab indexing run on."""
+import ctypes as C
 import os
 
 import torch
@@ -120,40 +125,113 @@ class SlabHalo:
         return torch.cat([tmp.lo["phase"], t, tmp.hi["phase"]], dim=slab_dim(self.ndim)).contiguous()
 
 
+_HANDLE_BYTES = 128  # AMPE_HALO_HANDLE_BYTES (include/ampe_b200.h)
+
+
 class DistributedRHS:
-    """evaluateRHSFunction on a slab-decomposed periodic domain, halo exchange
-    overlapped with the interior evaluation.
+    """evaluateRHSFunction on a slab-decomposed periodic domain.
 
-    The whole step (pack, NCCL send/recv on a communication stream, interior kernels, boundary
-    kernels) is captured into a CUDA graph per (y, y_dot, fd_flag) buffer set and replayed:
-    for the 2D workloads one evaluation is ~0.1 ms, less than the host-side cost of issuing
-    the exchange.  `use_graphs=False` (or a failed capture) runs the same sequence eagerly."""
+    transport "ipc" (default on a GPU): the C-ABI exchange, one call per evaluation (ampe_rhs_eval_slab).
+    transport "nccl" (AMPE_B200_HALO=nccl): ghost planes by torch.distributed into buffers handed to
+    ampe_rhs_set_halo, interior / boundary split driven from here."""
 
-    def __init__(self, rhs, rank, nranks, group=None, use_graphs=None):
+    def __init__(self, rhs, rank, nranks, group=None, transport=None):
         self.rhs = rhs
+        self.rank, self.nranks, self.group = rank, nranks, group
         cfg = rhs.cfg
-        self.halo = SlabHalo(cfg.ndim, rhs.nghosts(), rank, nranks, group)
-        # the exchange must not queue behind the interior kernel's blocks: high-priority stream
-        # (bench.py also sets TORCH_NCCL_HIGH_PRIORITY=1 for NCCL's own stream)
-        self.comm_stream = torch.cuda.Stream(priority=-1)
-        self.interior_first = os.environ.get("AMPE_B200_HALO_ORDER", "interior") == "interior"
-        self._set = False
-        # opt-in (AMPE_B200_GRAPHS=1): capturing NCCL send/recv needs a quiescent communicator on
-        # every rank; the eager sequence is the default
-        if use_graphs is None:
-            use_graphs = os.environ.get("AMPE_B200_GRAPHS") == "1"
-        self.use_graphs = bool(use_graphs)
-        self._graphs = {}
-        self._seen = {}
+        self.transport = transport or os.environ.get("AMPE_B200_HALO", "ipc")
         self._launches = 0
+        self.h = None
+        if self.transport == "ipc":
+            try:
+                self._connect()
+            except Exception as e:  # no CUDA IPC between these processes: the NCCL transport does the same exchange
+                import sys
+                print("ampe_b200.halo: peer-mapped exchange unavailable (%r); using the NCCL transport" % (e,),
+                      file=sys.stderr)
+                self.transport = "nccl"
+        if self.transport != "ipc":
+            self.halo = SlabHalo(cfg.ndim, rhs.nghosts(), rank, nranks, group)
+            # the exchange must not queue behind the interior kernel's blocks: high-priority stream
+            self.comm_stream = torch.cuda.Stream(priority=-1)
+            self._set = False
 
-    def resetRefPhaseConcentrations(self, cl_ref, ca_ref):
+    # ---- set-up of the C-ABI exchange: create, export, ship the handles, connect -----------------
+    def _connect(self):
+        from .lib import check
+        L = self.rhs.L
+        h = C.c_void_p()
+        check(L.ampe_halo_create(self.rhs.h, self.rank, self.nranks, C.byref(h)), "ampe_halo_create")
+        mine = C.create_string_buffer(_HANDLE_BYTES)
+        check(L.ampe_halo_export(h, mine), "ampe_halo_export")
+        blobs = [None] * self.nranks
+        dist.all_gather_object(blobs, bytes(mine.raw), group=self.group)
+        prev = C.create_string_buffer(blobs[(self.rank - 1) % self.nranks], _HANDLE_BYTES)
+        nxt = C.create_string_buffer(blobs[(self.rank + 1) % self.nranks], _HANDLE_BYTES)
+        rc = L.ampe_halo_connect(h, prev, nxt)
+        # every rank must know whether every rank connected (a half-connected ring would hang in the first wait)
+        ok = [None] * self.nranks
+        dist.all_gather_object(ok, int(rc), group=self.group)
+        if any(v != 0 for v in ok):
+            L.ampe_halo_destroy(h)
+            check(rc, "ampe_halo_connect")
+            raise RuntimeError("a neighbour could not map the receive buffers (codes %r)" % (ok,))
+        self.h = h
+        dist.barrier(group=self.group)
+
+    def close(self):
+        if self.h is not None:
+            self.rhs.L.ampe_halo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _stream():
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def resetRefPhaseConcentrations(self, cl_ref=None, ca_ref=None):
+        """interior arrays (ghost 0) of this rank, or nothing = "the last computed c_l, c_a" (ghost planes
+        included: QuatModel::resetRefPhaseConcentrations copies whole arrays)"""
+        if cl_ref is None:
+            self.rhs.resetRefPhaseConcentrations()
+            return
+        if self.transport == "ipc":
+            from .lib import check
+            self._keep_ref = (cl_ref, ca_ref)
+            check(self.rhs.L.ampe_rhs_set_ref_concentrations_slab(self.rhs.h, self.h, cl_ref.data_ptr(),
+                                                                  ca_ref.data_ptr(), self._stream()), "set_ref_slab")
+            return
         ndim = self.rhs.cfg.ndim
         shp = (1, self.rhs.cfg.n[2] if ndim == 3 else 1, self.rhs.cfg.n[1], self.rhs.cfg.n[0])
         g0 = self.halo.ghosted(cl_ref.reshape(shp))
         g1 = self.halo.ghosted(ca_ref.reshape(shp))
         self.rhs.setRefPhaseConcentrationsGhosted(g0, g1)
         self._ref = (g0, g1)
+
+    def setSymmetryRotations(self, iqrot):
+        """rotation indices of this rank's lower faces (ghost 0); the ghost planes come from the neighbours"""
+        if self.transport != "ipc":
+            raise RuntimeError("the symmetry-aware path on several ranks needs the peer-mapped exchange")
+        from .lib import check
+        arr = (C.c_void_p * 3)()
+        self._iq = [t.to(torch.int32).contiguous() for t in iqrot]
+        for d, t in enumerate(self._iq):
+            arr[d] = t.data_ptr()
+        check(self.rhs.L.ampe_rhs_set_symmetry_rotations_slab(self.rhs.h, self.h, arr, self._stream()),
+              "set_rotations_slab")
+
+    def computeSymmetryRotations(self, y):
+        """QuatModel::computeSymmetryRotations on this rank's slab (ghost planes of y and of the indices from the
+        neighbours)"""
+        from .lib import check
+        fy = y.fields()
+        check(self.rhs.L.ampe_rhs_compute_symmetry_rotations_slab(self.rhs.h, self.h, C.byref(fy), self._stream()),
+              "computeSymmetryRotations (slab)")
 
     def _eager(self, time, y, y_dot, fd_flag):
         main = torch.cuda.current_stream()
@@ -164,55 +242,42 @@ class DistributedRHS:
             self._set = True
         # y is ready once `main` reaches this point; the interior planes are launched FIRST so
         # that the GPU computes while the host posts the exchange
-        if self.interior_first:
-            ready = main.record_event()
-            self.rhs.evaluateRHSFunction(time, y, y_dot, fd_flag, part=1)  # interior planes
-            self.comm_stream.wait_event(ready)
-            with torch.cuda.stream(self.comm_stream):
-                works = self.halo.start(y)
-        else:
-            self.comm_stream.wait_stream(main)
-            with torch.cuda.stream(self.comm_stream):
-                works = self.halo.start(y)
-            self.rhs.evaluateRHSFunction(time, y, y_dot, fd_flag, part=1)  # interior planes
+        ready = main.record_event()
+        self.rhs.evaluateRHSFunction(time, y, y_dot, fd_flag, part=1)  # interior planes
+        self.comm_stream.wait_event(ready)
         with torch.cuda.stream(self.comm_stream):
+            works = self.halo.start(y)
             self.halo.finish(works)
         main.wait_stream(self.comm_stream)
         self.rhs.evaluateRHSFunction(time, y, y_dot, fd_flag, part=2)  # boundary planes
-        self._launches = self.rhs.lastLaunchCount()
+        self._launches = self.rhs.lastLaunchCount() + 2
 
     def lastLaunchCount(self):
         return self._launches
 
     def evaluateRHSFunction(self, time, y, y_dot, fd_flag=0):
-        if not self.use_graphs:
+        if self.transport != "ipc":
             self._eager(time, y, y_dot, fd_flag)
             return 0
-        key = (tuple(0 if y.get(k) is None else y[k].data_ptr() for k in COMPONENTS),
-               tuple(0 if y_dot.get(k) is None else y_dot[k].data_ptr() for k in COMPONENTS),
-               int(fd_flag != 0))
-        g = self._graphs.get(key)
-        if g is not None:
-            g.replay()
-            return 0
-        # the first two evaluations of a buffer set run eagerly (allocations, kernel attributes,
-        # NCCL channel set-up all happen there); the third is captured
-        seen = self._seen.get(key, 0)
-        self._seen[key] = seen + 1
-        if seen < 2 or len(self._graphs) >= 16:
-            self._eager(time, y, y_dot, fd_flag)
-            return 0
-        try:
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._eager(time, y, y_dot, fd_flag)
-            self._graphs[key] = g
-            g.replay()
-        except Exception as e:  # capture not possible here: stay eager
-            import sys
-            print("ampe_b200.halo: CUDA graph capture failed (%r); running eagerly" % (e,), file=sys.stderr)
-            self.use_graphs = False
-            torch.cuda.synchronize()
-            self._eager(time, y, y_dot, fd_flag)
+        from .lib import check
+        fy, fd = y.fields(), y_dot.fields()
+        check(self.rhs.L.ampe_rhs_eval_slab(self.rhs.h, self.h, float(time), C.byref(fy), C.byref(fd), int(fd_flag),
+                                            self._stream()), "ampe_rhs_eval_slab")
+        self._launches = self.rhs.L.ampe_halo_last_launch_count(self.h)
+        return 0
+
+    def evaluateRHSFunctionHost(self, time, y_host, ydot_host, fd_flag=0):
+        """HOST buffers of this rank's slab (pinned): chunk pipeline H2D | kernels | D2H, ghost planes device to
+        device"""
+        if self.transport != "ipc":
+            raise RuntimeError("the host-buffer path on several ranks needs the peer-mapped exchange")
+        from . import _abi
+        from .lib import check
+        fy, fd = _abi.RhsFields(), _abi.RhsFields()
+        for k in COMPONENTS:
+            a, b = y_host.get(k), ydot_host.get(k)
+            setattr(fy, k, None if a is None else a.data_ptr())
+            setattr(fd, k, None if b is None else b.data_ptr())
+        check(self.rhs.L.ampe_rhs_eval_slab_host(self.rhs.h, self.h, float(time), C.byref(fy), C.byref(fd),
+                                                 int(fd_flag)), "ampe_rhs_eval_slab_host")
         return 0

@@ -55,6 +55,31 @@ def load():
     L.ampe_rhs_newton_failures.argtypes = [vp, vp]
     L.ampe_rhs_last_launch_count.restype = ci
     L.ampe_rhs_last_launch_count.argtypes = [vp]
+    # slab ghost-plane exchange (csrc/halo.cu)
+    L.ampe_halo_create.restype = ci
+    L.ampe_halo_create.argtypes = [vp, ci, ci, C.POINTER(vp)]
+    L.ampe_halo_export.restype = ci
+    L.ampe_halo_export.argtypes = [vp, vp]
+    L.ampe_halo_connect.restype = ci
+    L.ampe_halo_connect.argtypes = [vp, vp, vp]
+    L.ampe_halo_destroy.restype = ci
+    L.ampe_halo_destroy.argtypes = [vp]
+    L.ampe_rhs_eval_slab.restype = ci
+    L.ampe_rhs_eval_slab.argtypes = [vp, vp, dbl, pf, pf, ci, vp]
+    L.ampe_rhs_eval_slab_host.restype = ci
+    L.ampe_rhs_eval_slab_host.argtypes = [vp, vp, dbl, pf, pf, ci]
+    L.ampe_halo_push.restype = ci
+    L.ampe_halo_push.argtypes = [vp, pf, ci, vp]
+    L.ampe_halo_wait.restype = ci
+    L.ampe_halo_wait.argtypes = [vp, vp]
+    L.ampe_rhs_set_ref_concentrations_slab.restype = ci
+    L.ampe_rhs_set_ref_concentrations_slab.argtypes = [vp, vp, vp, vp, vp]
+    L.ampe_rhs_set_symmetry_rotations_slab.restype = ci
+    L.ampe_rhs_set_symmetry_rotations_slab.argtypes = [vp, vp, C.POINTER(vp), vp]
+    L.ampe_rhs_compute_symmetry_rotations_slab.restype = ci
+    L.ampe_rhs_compute_symmetry_rotations_slab.argtypes = [vp, vp, pf, vp]
+    L.ampe_halo_last_launch_count.restype = ci
+    L.ampe_halo_last_launch_count.argtypes = [vp]
     L.ampe_rhs_set_kernel_timing.restype = ci
     L.ampe_rhs_set_kernel_timing.argtypes = [vp, ci]
     L.ampe_rhs_last_kernel_ms.restype = ci

@@ -185,6 +185,50 @@ int ampe_rhs_eval_boundary(ampe_rhs_ctx* ctx, double time,
                            const ampe_rhs_fields* ydot, int fd_flag,
                            void* stream);
 
+/* ---- slab ghost-plane exchange between GPUs (fillScratch's RefineSchedule::fillData over MPI,
+ * QuatIntegrator.cc:2873-2955, 2948-2954) -------------------------------------------------------
+ * One rank per GPU, 1-D slabs along the slowest axis, periodic in the rank index.  Every rank owns receive
+ * buffers in its own HBM (two parities x {lower, upper} x every state component x nghosts planes) and arrival
+ * flags, in ONE allocation that the two neighbours map: CUDA IPC between processes, peer access inside one
+ * process.  Per evaluation a rank PUSHES its boundary planes of y straight into the neighbours' buffers with one
+ * kernel (NVLink stores, then a system-scope fence, then the epoch flag) and a one-thread kernel waits for the
+ * neighbours' flags: no packing, no library collective, no host synchronisation; the interior planes are
+ * evaluated while the planes travel.  Double buffering by epoch parity orders the reuse of a buffer behind the
+ * neighbour's previous-but-one evaluation without a second handshake.  nranks == 1 needs none of this (the
+ * kernels wrap periodically inside the rank).
+ *
+ * Set-up, once: create on every rank, export the opaque handle, ship it to both neighbours with the host
+ * application's own transport (MPI_Sendrecv in AMPE; torch.distributed in the tests; a socket in tests/cpp),
+ * connect with the neighbours' handles. */
+typedef struct ampe_halo ampe_halo;
+#define AMPE_HALO_HANDLE_BYTES 128
+int ampe_halo_create(ampe_rhs_ctx* ctx, int rank, int nranks, ampe_halo** out);
+int ampe_halo_export(ampe_halo* h, void* handle /* AMPE_HALO_HANDLE_BYTES */);
+int ampe_halo_connect(ampe_halo* h, const void* handle_prev, const void* handle_next);
+int ampe_halo_destroy(ampe_halo* h);
+/* evaluateRHSFunction on a slab with neighbours: push, interior planes, wait, boundary planes.  Collective over
+ * the ranks in the sense that every rank must call it once per evaluation, in the same order. */
+int ampe_rhs_eval_slab(ampe_rhs_ctx* ctx, ampe_halo* h, double time, const ampe_rhs_fields* y,
+                       const ampe_rhs_fields* ydot, int fd_flag, void* stream);
+/* the same through HOST buffers (the slab moves through the chunk pipeline of ampe_rhs_eval_host, the ghost
+ * planes device to device) */
+int ampe_rhs_eval_slab_host(ampe_rhs_ctx* ctx, ampe_halo* h, double time, const ampe_rhs_fields* y_host,
+                            const ampe_rhs_fields* ydot_host, int fd_flag);
+/* the two halves, for callers that sequence the overlap themselves: sides bit 0 = my lowest planes to the lower
+ * neighbour, bit 1 = my highest planes to the upper neighbour; an epoch is complete when both were pushed */
+int ampe_halo_push(ampe_halo* h, const ampe_rhs_fields* y, int sides, void* stream);
+int ampe_halo_wait(ampe_halo* h, void* stream);
+/* Newton reference concentrations / symmetry rotations of a slab rank: interior arrays (ghost 0) in, the ghost
+ * planes along the slab axis come from the neighbours (collective) */
+int ampe_rhs_set_ref_concentrations_slab(ampe_rhs_ctx* ctx, ampe_halo* h, const double* cl_ref,
+                                         const double* ca_ref, void* stream);
+int ampe_rhs_set_symmetry_rotations_slab(ampe_rhs_ctx* ctx, ampe_halo* h, const int* const* iqrot, void* stream);
+/* QuatModel::computeSymmetryRotations (QuatModel.cc:4978-5055) on a slab rank: ghost planes of y exchanged, faces
+ * searched, ghost planes of the indices fetched from the neighbours (collective) */
+int ampe_rhs_compute_symmetry_rotations_slab(ampe_rhs_ctx* ctx, ampe_halo* h, const ampe_rhs_fields* y, void* stream);
+/* launches of the last ampe_rhs_eval_slab (exchange kernels included) */
+int ampe_halo_last_launch_count(const ampe_halo* h);
+
 /* device pointers to ctx-owned c_l, c_a (ghost 0) after an evaluation        */
 int ampe_rhs_get_phase_concentrations(ampe_rhs_ctx* ctx, double** cl,
                                       double** ca);

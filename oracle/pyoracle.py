@@ -425,3 +425,118 @@ def project(n, depth, q, ngq, corr, ngc, err, nge):
     ndim = len(n)
     lib().oracle_k_project(ndim, _ivec([0] * ndim), _ivec([v - 1 for v in n]), int(depth), _ptr(q), int(ngq),
                            _ptr(corr), int(ngc), _ptr(err), int(nge))
+
+
+# ---- extended-precision arbiter (liboracle_ld.so: the same sources with double -> long double) ------------------
+_LD_CLASSES = {}
+
+
+def _ld_type(t):
+    """ctypes type with every c_double replaced by c_longdouble (structures and arrays recursively)"""
+    if t is C.c_double:
+        return C.c_longdouble
+    if isinstance(t, type) and issubclass(t, C.Array):
+        return _ld_type(t._type_) * t._length_
+    if isinstance(t, type) and issubclass(t, C.Structure):
+        if t not in _LD_CLASSES:
+            _LD_CLASSES[t] = type(t.__name__ + "LD", (C.Structure,),
+                                  {"_fields_": [(n, _ld_type(ft)) for n, ft in t._fields_]})
+        return _LD_CLASSES[t]
+    return t
+
+
+def _ld_copy(src, dst):
+    for name, ft in type(src)._fields_:
+        v = getattr(src, name)
+        if isinstance(v, C.Array):
+            _ld_copy_array(v, getattr(dst, name))
+        elif isinstance(v, C.Structure):
+            _ld_copy(v, getattr(dst, name))
+        else:
+            setattr(dst, name, v)
+
+
+def _ld_copy_array(src, dst):
+    for i in range(len(src)):
+        if isinstance(src[i], C.Array):
+            _ld_copy_array(src[i], dst[i])
+        elif isinstance(src[i], C.Structure):
+            _ld_copy(src[i], dst[i])
+        else:
+            dst[i] = src[i]
+
+
+def lib_ld():
+    if "ld" not in _libs:
+        path = os.path.join(_HERE, "liboracle_ld.so")
+        if not os.path.exists(path) or _stale(path):
+            subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle_ld.so"])
+        L = C.CDLL(path)
+        L.oracle_ld_create.restype = C.c_void_p
+        L.oracle_ld_create.argtypes = [C.c_void_p]
+        L.oracle_ld_destroy.argtypes = [C.c_void_p]
+        L.oracle_ld_set_ref.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_ld_set_rotations.argtypes = [C.c_void_p, C.c_void_p]
+        L.oracle_ld_eval.restype = C.c_int
+        L.oracle_ld_eval.argtypes = [C.c_void_p, C.c_longdouble, C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_ld_get_phase_concentrations.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        assert L.oracle_ld_sizeof_real() == np.dtype(np.longdouble).itemsize
+        _libs["ld"] = L
+    return _libs["ld"]
+
+
+class OracleLD:
+    """The restatement evaluated in long double (64-bit mantissa): the arbiter for outputs that two correct fp64
+    evaluations cannot agree on to 1e-12.  Inputs are the SAME fp64 fields (widened exactly), outputs are returned
+    as numpy longdouble arrays."""
+
+    def __init__(self, cfg):
+        self.L = lib_ld()
+        self.cfg = cfg
+        self.cfg_ld = _ld_type(type(cfg))()
+        _ld_copy(cfg, self.cfg_ld)
+        self.h = self.L.oracle_ld_create(C.byref(self.cfg_ld))
+        self.ncell = cfg.n[0] * cfg.n[1] * (cfg.n[2] if cfg.ndim == 3 else 1)
+
+    def close(self):
+        if self.h:
+            self.L.oracle_ld_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    @staticmethod
+    def _wide(a):
+        return None if a is None else np.ascontiguousarray(a, dtype=np.longdouble)
+
+    def _fields(self, d):
+        f = _ld_type(_abi.RhsFields)()
+        for k in ("phase", "quat", "conc", "temperature"):
+            a = d.get(k)
+            setattr(f, k, None if a is None else a.ctypes.data)
+        return f
+
+    def set_ref(self, cl, ca):
+        self._ref = (self._wide(cl), self._wide(ca))
+        self.L.oracle_ld_set_ref(self.h, _ptr(self._ref[0]), _ptr(self._ref[1]))
+
+    def set_rotations(self, iqrot):
+        arr = (C.c_void_p * 3)()
+        self._iq = [np.ascontiguousarray(a, dtype=np.int32) for a in iqrot]
+        for d, a in enumerate(self._iq):
+            arr[d] = a.ctypes.data
+        self.L.oracle_ld_set_rotations(self.h, arr)
+
+    def eval(self, time, y, fd_flag=0):
+        yw = {k: self._wide(v) for k, v in y.items()}
+        ydot = {k: (None if v is None else np.zeros_like(v)) for k, v in yw.items()}
+        fy, fd = self._fields(yw), self._fields(ydot)
+        st = self.L.oracle_ld_eval(self.h, float(time), C.byref(fy), C.byref(fd), int(fd_flag))
+        return st, ydot
+
+    def phase_concentrations(self):
+        cl = np.zeros(self.ncell, dtype=np.longdouble)
+        ca = np.zeros(self.ncell, dtype=np.longdouble)
+        self.L.oracle_ld_get_phase_concentrations(self.h, _ptr(cl), _ptr(ca))
+        return cl, ca

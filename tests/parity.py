@@ -113,22 +113,109 @@ def run_gpu(cfg, st, fd_flags=(0,), rotations=None, ref=None, perturb=None):
     return outs, extra, launches
 
 
-def compare(name, cfg, st, fd_flags=(0,), rotations=None):
-    o_outs, o_extra = run_oracle(cfg, st, fd_flags, rotations)
-    g_outs, g_extra, _ = run_gpu(cfg, st, fd_flags, rotations)
-    errs = {}
-    for n, ((status, yo), yg) in enumerate(zip(o_outs, g_outs)):
-        assert status == 0, "oracle Newton failure"
+# ---- extended-precision arbiter -----------------------------------------------------------------
+# Some outputs are ill-conditioned in fp64: the composition RHS of the CALPHAD models is a divergence of
+# fluxes D(c_l, c_a) (c_i(x) - c_i(x-h)) of Newton-solved concentrations (the differences cancel 3-4
+# digits), the symmetry-aware quaternion RHS subtracts nearly equal symmetric / non-symmetric
+# differences.  There the restatement ITSELF is 1e-11 .. 1e-10 away from the same formulas evaluated in
+# long double (64-bit mantissa; oracle/liboracle_ld.so is the same source with double -> long double), so
+# that two correct fp64 implementations -- the reference's and the device's, with different logarithm
+# and operation-fusion details -- cannot agree to 1e-12 with each other.  Criterion:
+#     |gpu - oracle| <= 1e-12                       (all well-conditioned outputs: unchanged), or
+#     |gpu - ld|     <= ARBITER_FACTOR |oracle - ld| + 1e-12
+# i.e. the device is as close to the exact evaluation of the reference's formulas as the reference's own
+# fp64 arithmetic is (factor 3: both errors are maxima over a few thousand cells of rounding noise).
+ARBITER_FACTOR = 3.0
+
+
+def rel_err_ld(a, ref_ld):
+    a = np.asarray(a, dtype=np.longdouble).ravel()
+    ref = np.asarray(ref_ld, dtype=np.longdouble).ravel()
+    scale = np.maximum(np.abs(ref), FLOOR * max(np.abs(ref).max(), np.longdouble(1e-300)))
+    return float((np.abs(a - ref) / scale).max())
+
+
+def needs_arbiter(cfg):
+    return cfg.free_energy == 2 or bool(cfg.symmetry_aware)
+
+
+def run_arbiter(cfg, st, fd_flags=(0,), rotations=None, ref=None):
+    """the restatement in long double on the same fp64 inputs: [ydot per fd_flag], (cl, ca)"""
+    from oracle import pyoracle
+    y = {k: (None if v is None else v.numpy().copy()) for k, v in st.items()}
+    o = pyoracle.OracleLD(cfg)
+    if cfg.conc_rhs_form in (2, 3):
+        r = ref if ref is not None else (y["conc"].ravel().copy(), y["conc"].ravel().copy())
+        o.set_ref(np.ascontiguousarray(r[0]), np.ascontiguousarray(r[1]))
+    if cfg.symmetry_aware:
+        o.set_rotations(rotations)
+    outs = []
+    for fd in fd_flags:
+        status, yd = o.eval(0.0, y, fd_flag=fd)
+        assert status == 0, "arbiter Newton failure"
+        outs.append(yd)
+    extra = o.phase_concentrations() if cfg.conc_rhs_form in (2, 3) else None
+    o.close()
+    return outs, extra
+
+
+class Errs(dict):
+    """key -> |gpu - oracle| (floor metric); .ld[key] = (|gpu - ld|, |oracle - ld|) where the arbiter ran"""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self.ld = {}
+
+
+def check(errs, tol=TOL):
+    for k, v in errs.items():
+        if v <= tol:
+            continue
+        ld = getattr(errs, "ld", {}).get(k)
+        assert ld is not None, "%s: %.3e > %.1e and no arbiter (%s)" % (k, v, tol, dict(errs))
+        g, o = ld
+        assert g <= ARBITER_FACTOR * o + tol, (
+            "%s: |gpu-oracle| %.3e, |gpu-ld| %.3e > %.1f x |oracle-ld| %.3e (%s)" % (k, v, g, ARBITER_FACTOR, o,
+                                                                                 dict(errs)))
+
+
+def check_one(key, gpu, oracle, ld=None, tol=TOL):
+    """one output array against the oracle's, arbitrated by the long-double result when given"""
+    e = Errs({key: rel_err(gpu, oracle)})
+    if ld is not None:
+        e.ld[key] = (rel_err_ld(gpu, ld), rel_err_ld(oracle, ld))
+    check(e, tol)
+    return e[key]
+
+
+def compare_outputs(cfg, fd_flags, o_outs, o_extra, g_outs, g_extra, ld=None):
+    """errors of GPU outputs against oracle outputs, with the arbiter's numbers when given"""
+    errs = Errs()
+    for n, (yo, yg) in enumerate(zip(o_outs, g_outs)):
         for k in ("phase", "quat", "conc", "temperature"):
             if yo.get(k) is None:
                 continue
             if k == "quat" and not cfg.evolve_quat:
                 continue
-            errs["fd%d:%s" % (fd_flags[n], k)] = rel_err(yg[k], yo[k])
+            key = "fd%d:%s" % (fd_flags[n], k)
+            errs[key] = rel_err(yg[k], yo[k])
+            if ld is not None:
+                errs.ld[key] = (rel_err_ld(yg[k], ld[0][n][k]), rel_err_ld(yo[k], ld[0][n][k]))
     if o_extra is not None:
-        errs["cl"] = rel_err(g_extra[0], o_extra[0])
-        errs["ca"] = rel_err(g_extra[1], o_extra[1])
+        for i, key in enumerate(("cl", "ca")):
+            errs[key] = rel_err(g_extra[i], o_extra[i])
+            if ld is not None:
+                errs.ld[key] = (rel_err_ld(g_extra[i], ld[1][i]), rel_err_ld(o_extra[i], ld[1][i]))
     return errs
+
+
+def compare(name, cfg, st, fd_flags=(0,), rotations=None):
+    o_outs, o_extra = run_oracle(cfg, st, fd_flags, rotations)
+    g_outs, g_extra, _ = run_gpu(cfg, st, fd_flags, rotations)
+    for status, _yo in o_outs:
+        assert status == 0, "oracle Newton failure"
+    ld = run_arbiter(cfg, st, fd_flags, rotations) if needs_arbiter(cfg) else None
+    return compare_outputs(cfg, fd_flags, [yo for _s, yo in o_outs], o_extra, g_outs, g_extra, ld)
 
 
 # ---- fixed-step trajectories (north_star: field trajectories within 1e-8 after 100 steps) ----

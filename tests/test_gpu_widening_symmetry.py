@@ -182,9 +182,9 @@ def test_compute_symmetry_rotations_and_symmetry_aware_rhs():
     o_outs, _ = parity.run_oracle(cfg, st, (0,), want)
     status, yo = o_outs[0]
     assert status == 0
+    ld, _ = parity.run_arbiter(cfg, st, (0,), want)
     for k in ("phase", "quat", "conc"):
-        tol = 1e-11 if k == "conc" else parity.TOL
-        assert parity.rel_err(yd[k].cpu().numpy(), yo[k]) <= tol, k
+        parity.check_one(k, yd[k].cpu().numpy(), yo[k], ld[0][k])
     r.close()
 
 

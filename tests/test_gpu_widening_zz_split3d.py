@@ -72,5 +72,4 @@ def test_split_matches_oracle():
         errs = parity.compare("auni3d", cfg, st, fd_flags=(0, 1))
     finally:
         os.environ.pop("AMPE_B200_SPLIT3D", None)
-    for k, v in errs.items():
-        assert v <= (1e-11 if k.endswith("conc") else parity.TOL), (k, v, errs)
+    parity.check(errs)
