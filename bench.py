@@ -258,6 +258,14 @@ def main():
     ydot = y.like()
     r = rhs.QuatIntegratorRHS(cfg, dev)
     drv = DistributedRHS(r, rank, world) if world > 1 else r
+    if world > 1:
+        config["halo_transport"] = drv.transport  # "ipc": ampe_halo_* (peer-mapped NVLink stores); "nccl": torch.distributed
+        if drv.transport != "ipc" and cfg.symmetry_aware:
+            # without the peer-mapped exchange the rotation indices' ghost planes cannot be fetched: say so
+            cfg.symmetry_aware = 0
+            config["workload"] += " (symmetry off: NCCL transport)"
+            r = rhs.QuatIntegratorRHS(cfg, dev)
+            drv = DistributedRHS(r, rank, world, transport="nccl")
     kks = cfg.conc_rhs_form in (2, 3)
     if cfg.symmetry_aware:
         n = r.ncell
@@ -402,13 +410,26 @@ def main():
                 h2d += t.numel() * 8
                 if k != "quat" or cfg.evolve_quat:
                     d2h += t.numel() * 8
+        if world > 1 and drv.transport != "ipc":
+            def host_step():  # NCCL transport: plain copies around the device evaluation
+                for k in rhs.COMPONENTS:
+                    if yh[k] is not None:
+                        y_timed[k].copy_(yh[k], non_blocking=True)
+                drv.evaluateRHSFunction(0.0, y_timed, ydot, 0)
+                for k in rhs.COMPONENTS:
+                    if ydh[k] is not None and (k != "quat" or cfg.evolve_quat):
+                        ydh[k].copy_(ydot[k], non_blocking=True)
+                torch.cuda.synchronize()
+        else:
+            def host_step():
+                drv.evaluateRHSFunctionHost(0.0, yh, ydh, 0)
         for _ in range(2):
-            drv.evaluateRHSFunctionHost(0.0, yh, ydh, 0)
+            host_step()
         n_e2e = max(3, min(args.steps, 10))
         barrier()
         t0 = time.perf_counter()
         for _ in range(n_e2e):
-            drv.evaluateRHSFunctionHost(0.0, yh, ydh, 0)
+            host_step()
         barrier()
         dt_e = global_max((time.perf_counter() - t0) / n_e2e)
         e2e = {"value": r.ncell * world / dt_e / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": h2d * world,

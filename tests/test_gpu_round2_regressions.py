@@ -34,7 +34,7 @@ def test_energy_then_scalar_diagnostics_on_640x512():
         if k in ("max_concentration", "min_temperature", "max_temperature"):
             assert d1[k] == ref[k], k
         else:
-            assert d1[k] == pytest.approx(ref[k], rel=1e-12, abs=1e-13 * max(1.0, abs(ref[k]))), k
+            assert d1[k] == pytest.approx(ref[k], rel=1e-10), k  # sums of 3e5 terms in another order
     assert e1["total"] == pytest.approx(float(eref[0]), rel=1e-11)
     r.close()
     torch.cuda.synchronize()
