@@ -964,9 +964,9 @@ int ampe_k_compute_phase_concentrations(const ampe_rhs_config* cfg, const int* i
       if (calphad) {
          x0 = lr(i, j, k);
          x1 = ar(i, j, k);
-         double lg[4];
+         KksFinal fin;
          if (kks_newton(p.ct, c(i, j, k), hphi, x0, x1, p.newton_tol, p.newton_max_its,
-                        p.newton_alpha, lg) < 0)
+                        p.newton_alpha, fin) < 0)
             atomicAdd(nfail, 1);
       } else {
          const double h = clamp01(hphi), cc = c(i, j, k);

@@ -46,11 +46,39 @@ struct FusedArgs {
    int split3d;              // host side only: AMPE_B200_SPLIT3D, two launches per 3D EBS evaluation
 };
 
+// -DAMPE_SYMM_NOINLINE: the qlen-4 rotation as ONE out-of-line function (arguments and result in registers).
+// The symmetry-aware tile kernel inlines ~40 rotations per face pair: 5700 SASS instructions (91 KB), and ncu
+// shows "no instruction" as the top stall of its face phase (profiles/r02a_ncu_full_auni2d.txt) -- the kernel
+// is bounded by instruction fetch, not by arithmetic.
+struct Quat4 {
+   double a, b, c, d;
+};
+static __device__ __noinline__ Quat4 symm_rotate4_call(double q0, double q1, double q2, double q3, int iq,
+                                                       const double (*s_qr)[4], const int* s_conj)
+{
+   if (iq < 0) iq = s_conj[-iq - 1];
+   Quat4 r;
+   if (iq == 1) {
+      r.a = q0, r.b = q1, r.c = q2, r.d = q3;
+   } else {
+      const double* b = s_qr[iq - 1];
+      r.a = q0 * b[0] - q1 * b[1] - q2 * b[2] - q3 * b[3];
+      r.b = q0 * b[1] + q1 * b[0] + q2 * b[3] - q3 * b[2];
+      r.c = q0 * b[2] + q2 * b[0] + q3 * b[1] - q1 * b[3];
+      r.d = q0 * b[3] + q3 * b[0] + q1 * b[2] - q2 * b[1];
+   }
+   return r;
+}
+
 template <int Q>
 AMPE_DEV void symm_rotate(const double* q, int iq, double* qp, const double (*s_qr)[4],
                           const int* s_conj)
 {
    if (Q == 4) {
+#ifdef AMPE_SYMM_NOINLINE
+      const Quat4 r = symm_rotate4_call(q[0], q[1], q[2], q[3], iq, s_qr, s_conj);
+      qp[0] = r.a, qp[1] = r.b, qp[2] = r.c, qp[3] = r.d;
+#else
       if (iq < 0) iq = s_conj[-iq - 1];
       if (iq == 1) {
 #pragma unroll
@@ -58,6 +86,7 @@ AMPE_DEV void symm_rotate(const double* q, int iq, double* qp, const double (*s_
       } else {
          quatmult4(q, s_qr[iq - 1], qp);
       }
+#endif
    } else if (Q == 2) {
       // quatsymmrotate2 (quat.f:449-520): rotations (1,0),(0,1),(-1,0),(0,-1); conj 1,4,3,2
       if (iq < 0) iq = (iq == -2) ? 4 : ((iq == -4) ? 2 : -iq);
@@ -143,13 +172,13 @@ __global__ void __launch_bounds__(256, AMPE_KKS_MINB) kks_kernel(const __grid_co
       if (p.free_energy == AMPE_FE_CALPHAD) {
          x0 = A.cl_ref[og];
          x1 = A.ca_ref[og];
-         double lg[4];
+         KksFinal fin;
          const int st = kks_newton(p.ct, conc, hphi, x0, x1, p.newton_tol, p.newton_max_its,
-                                   p.newton_alpha, lg);
+                                   p.newton_alpha, fin);
          if (st < 0) atomicAdd(A.nfail, 1);
          if (A.df && sl >= 0 && sl < ns)
             A.df[(long long)sl * plane + inplane] =
-                calphad_driving_force(p.ct, x0, x1, lg, p.inv_vm_l, p.inv_vm_a);
+                calphad_driving_force(p.ct, x0, x1, fin, p.inv_vm_l, p.inv_vm_a);
       } else {
          const double h = clamp01(hphi);
          x0 = (conc - h * (p.quad_ceq[1] - p.quad_rla * p.quad_ceq[0])) /

@@ -76,19 +76,26 @@ AMPE_DEV void stage_tile(const FusedArgs& A, double* s, int* s_iq, int ox, int o
    (void)n1;
    // A staged row has SX = 32 + 2 XH elements: one warp copies x = 0..31 of a row per instruction,
    // the tail elements of all rows are gathered into one extra pass of the block.
+   // Index arithmetic is split by what it depends on: the wrapped global column of a staged x (one modulo per
+   // thread, outside the row loop) and the per-row plane offsets (no division: a row index only needs a
+   // compare-and-shift wrap); copy_elem adds the two.  (r01c: staging and index arithmetic were 21.6 % of the
+   // Dendrite2D kernel's instructions, two modulos per staged element.)
    {
       constexpr int NROWS = TT::SY * TT::SZ;
-      // element (row r, staged x) of every staged field
-      auto copy_elem = [&](int r, int xs) {
+      auto wrap_col = [&](int xs) {
          int gx = (ox - TT::XH + xs) % n0;
-         gx = (gx < 0) ? gx + n0 : gx;
+         return (gx < 0) ? gx + n0 : gx;
+      };
+      // element (row r, staged x) of every staged field; gx = wrap_col(xs)
+      auto copy_elem = [&](int r, int xs, int gx) {
          const int lj = r % TT::SY - 1;
          const int lk = (ND == 3) ? (r / TT::SY - 1) : 0;
          int sl;
          int inplane = gx;  // offset inside a slab plane
          if (ND == 3) {
-            int gj = (oy + lj) % n1;
+            int gj = oy + lj;  // in [-1, n1 + TY]: tiles overhang the domain by less than one tile
             gj = (gj < 0) ? gj + n1 : gj;
+            gj = (gj >= n1) ? gj % n1 : gj;
             sl = oz + lk;
             inplane += n0 * gj;
          } else {
@@ -131,10 +138,16 @@ AMPE_DEV void stage_tile(const FusedArgs& A, double* s, int* s_iq, int ox, int o
             for (int a = 0; a < ND; a++) cp_async4(s_iq + a * S + d, A.iq[a] + og);
          }
       };
+      const int gx_lane = wrap_col(lane);
 #pragma unroll 1
-      for (int r = warp; r < NROWS; r += NW) copy_elem(r, lane);
+      for (int r = warp; r < NROWS; r += NW) copy_elem(r, lane, gx_lane);
+      // tail: (SX - 32) elements per row; consecutive threads take the tail elements of one row
+      constexpr int NTAIL = TT::SX - 32;
 #pragma unroll 1
-      for (int t = threadIdx.x; t < (TT::SX - 32) * NROWS; t += NT) copy_elem(t / (TT::SX - 32), 32 + t % (TT::SX - 32));
+      for (int t = threadIdx.x; t < NTAIL * NROWS; t += NT) {
+         const int xs = 32 + t % NTAIL;
+         copy_elem(t / NTAIL, xs, wrap_col(xs));
+      }
       cp_async_wait_all();
    }
 }
