@@ -15,7 +15,7 @@ AMPE_ENOGPU = -4
 
 FLUX_SIMPLE, FLUX_ISOTROPIC, FLUX_ANISOTROPIC = 0, 1, 2
 CONC_NONE, CONC_CAHN_HILLIARD, CONC_KKS, CONC_EBS = 0, 1, 2, 3
-FE_NONE, FE_BIASWELL, FE_CALPHAD, FE_QUADRATIC = 0, 1, 2, 3
+FE_NONE, FE_BIASWELL, FE_CALPHAD, FE_QUADRATIC, FE_DELTAT = 0, 1, 2, 3, 4
 
 
 class CalphadSpecies(C.Structure):
@@ -113,6 +113,9 @@ class RhsConfig(C.Structure):
         ("calphad", CalphadBinary),
         ("nranks", C.c_int),
         ("rank", C.c_int),
+        ("zero_slope", C.c_int * 3),
+        ("dtemperaturedt", C.c_double),
+        ("target_temperature", C.c_double),
     ]
 
 

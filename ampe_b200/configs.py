@@ -205,6 +205,76 @@ def gg3d_hbsm(nx=512, ny=512, nz=512):
     return c
 
 
+# ---- the reference's regression decks (tests/*/test*.py): model blocks as the decks give them, with the unit
+# conversions of QuatModelParameters.cc (thermal diffusivity cm^2/s -> um^2/s: x 1e8, :576; latent heat and cp
+# J/mol -> pJ/um^3: x 1e-6 / V_m, :557, :616)
+def dendrite_test2d():
+    """tests/Dendrite/2d.input: KWCcomplex (qlen 2, H_parameter unset -> 0: the orientation only feeds the
+    anisotropy, evolveQuat() false), anisotropic phase flux, FreeEnergyModel "linear"
+    (DeltaTemperatureFreeEnergyStrategy), unsteady heat equation in units of the melting temperature, slope-0
+    boundaries on every side, 240 x 240 cells on 160 x 160 um."""
+    c = _base(2, (240, 240), (0.0, 0.0), (160.0, 160.0))
+    c.qlen = 2
+    c.with_phase = 1
+    c.with_unsteady_temperature = 1
+    c.evolve_quat = 0
+    c.phase_flux_type = _abi.FLUX_ANISOTROPIC
+    c.free_energy = _abi.FE_DELTAT
+    c.epsilon_anisotropy = 0.05
+    c.H_parameter = 0.0
+    c.epsilon_phase = 2.0
+    c.phi_mobility = 0.25
+    c.quat_mobility = 1.0
+    c.epsilon_q = 0.0
+    c.meltingT = 1.0
+    vm = 1.0e-6
+    c.vm_liquid = c.vm_solid = vm
+    c.cp = 17.020371256848037 * (1.0e-6 / vm)
+    c.latent_heat = 17.020371256848037 * (1.0e-6 / vm)
+    c.thermal_diffusivity = 10.0e-8 * 1.0e8
+    c.phi_well_scale = 0.25
+    c.energy_interp = _ch("p")
+    c.zero_slope[0] = c.zero_slope[1] = 1
+    return c
+
+
+def single_grain_auni_test2d():
+    """tests/SingleGrainGrowthAuNi/2d.input: phase + composition (no orientation), CALPHAD KKS, EBS composition
+    flux, temperature ramp 1450 K - 200 K/s t (target 1220 K), slope-0 boundaries, 64 x 64 cells on 1.8 x 1.8 um."""
+    c = _base(2, (64, 64), (0.0, 0.0), (1.8, 1.8))
+    c.qlen = 0
+    c.with_phase = 1
+    c.with_concentration = 1
+    c.evolve_quat = 0
+    c.phase_flux_type = _abi.FLUX_SIMPLE
+    c.conc_rhs_form = _abi.CONC_EBS
+    c.free_energy = _abi.FE_CALPHAD
+    c.T_uniform = 1450.0
+    c.dtemperaturedt = -200.0
+    c.target_temperature = 1220.0
+    c.epsilon_phase = 0.25
+    c.phi_mobility = 6.4
+    c.phi_well_scale = 2.5
+    c.energy_interp = _ch("p")
+    c.conc_interp = _ch("p")
+    c.avg_func = _ch("a")
+    c.conc_avg_func = _ch("a")
+    c.vm_liquid = c.vm_solid = 7.68e-6
+    c.newton_max_its = 50
+    c.calphad = load_calphad()
+    c.zero_slope[0] = c.zero_slope[1] = 1
+    return c
+
+
+def two_grains_quadratic_test3d():
+    """tests/TwoGrainsQuadratic/3d.input: the GG3D_HBSM model block on 64 x 64 x 48 cells (3.2 x 3.2 x 2.4 um,
+    periodic: Geometry has no periodic_dimension, PFModel.cc:173-179), temperature ramp 873 K - 20 K/s t."""
+    c = gg3d_hbsm(nx=64, ny=64, nz=48)
+    c.dtemperaturedt = -20.0
+    c.target_temperature = 573.0
+    return c
+
+
 BUILDERS = {
     "pfhub1a": pfhub1a,
     "dendrite2d": dendrite2d,

@@ -86,7 +86,22 @@ static double mobility_exponent_bound(const CalphadT& t)
    return worst * 1.05;  // sampling margin
 }
 
-int ampe_derive_params(const ampe_rhs_config& c, Params& p)
+// ScalarTemperatureStrategy::getCurrentTemperature (ScalarTemperatureStrategy.cc:57-75)
+double ampe_uniform_temperature(const ampe_rhs_config& c, double time)
+{
+   double t = c.T_uniform + c.dtemperaturedt * time;
+   if (c.dtemperaturedt < 0. && t < c.target_temperature)
+      t = c.target_temperature;
+   else if (c.target_temperature > 0.0 && c.dtemperaturedt > 0. && t > c.target_temperature)
+      t = c.target_temperature;
+   return t;
+}
+
+int ampe_derive_params_at(const ampe_rhs_config& c, double T_now, Params& p);
+int ampe_derive_params(const ampe_rhs_config& c, Params& p) { return ampe_derive_params_at(c, c.T_uniform, p); }
+
+// T_now: the uniform temperature of this evaluation (T_uniform unless the deck ramps it in time)
+int ampe_derive_params_at(const ampe_rhs_config& c, double T_now, Params& p)
 {
    memset(&p, 0, sizeof(p));
    if (c.ndim != 2 && c.ndim != 3) return set_err(AMPE_EINVAL, "ndim must be 2 or 3");
@@ -98,6 +113,13 @@ int ampe_derive_params(const ampe_rhs_config& c, Params& p)
    p.qlen = c.qlen;
    for (int d = 0; d < 3; d++) p.n[d] = d < c.ndim ? c.n[d] : 1;
    p.ng = (c.conc_rhs_form == AMPE_CONC_CAHN_HILLIARD) ? 2 : 1;
+   for (int d = 0; d < c.ndim; d++) p.clamp[d] = c.zero_slope[d] ? 1 : 0;
+   if ((p.clamp[0] || p.clamp[1] || p.clamp[2]) && p.ng != 1)
+      return set_err(AMPE_EINVAL, "zero-slope boundaries: ghost width 1 models only (not Cahn-Hilliard)");
+   if ((p.clamp[0] || p.clamp[1] || p.clamp[2]) && c.symmetry_aware)
+      return set_err(AMPE_EINVAL, "zero-slope boundaries with the symmetry-aware path are not supported");
+   if (p.clamp[c.ndim - 1] && c.nranks > 1)
+      return set_err(AMPE_EINVAL, "a zero-slope boundary along the slab axis needs a single rank");
    p.with_phase = c.with_phase;
    p.with_conc = c.with_concentration;
    p.with_T = c.with_unsteady_temperature;
@@ -156,7 +178,7 @@ int ampe_derive_params(const ampe_rhs_config& c, Params& p)
    p.quat_mobility = c.quat_mobility;
    p.min_quat_mobility = c.min_quat_mobility;
    p.quat_mobility_alt = c.quat_mobility_alt_scale;
-   p.T_uniform = c.T_uniform;
+   p.T_uniform = T_now;
    p.thermal_diffusivity = c.thermal_diffusivity;
    p.latent_heat = c.latent_heat;
    p.cp = c.cp;
@@ -165,12 +187,17 @@ int ampe_derive_params(const ampe_rhs_config& c, Params& p)
    // computerhsbiaswell: pi = 4.*atan(1.) is REAL*4 (2d/quatrhs.m4:834)
    p.bias_coeff = c.bias_well_alpha / (double)(4.f * atanf(1.f));
    p.bias_gamma = c.bias_well_gamma;
+   // computerhsdeltatemperature: alpha = latentheat/tm (2d/quatrhs.m4:919)
+   if (c.free_energy == AMPE_FE_DELTAT) {
+      if (!(c.meltingT > 0.)) return set_err(AMPE_EINVAL, "the linear free energy needs meltingT > 0");
+      p.deltaT_alpha = c.latent_heat / c.meltingT;
+   }
    p.conc_mobility = c.conc_mobility;
    p.ch_ca = c.ch_ca;
    p.ch_cb = c.ch_cb;
    p.ch_well_scale = c.ch_well_scale;
    p.ch_kappa = c.ch_kappa;
-   const double T = c.T_uniform;
+   const double T = T_now;
    p.quad_A[0] = c.quad_A_l;
    p.quad_A[1] = c.quad_A_s;
    p.quad_ceq[0] = c.quad_Ceq_l + (T - c.quad_Tref) * c.quad_m_l;
@@ -409,10 +436,12 @@ static int fill_slab_ghosted(ampe_rhs_ctx* c, T* dst, const T* src, cudaStream_t
    const long long pl = c->plane;
    const int ng = c->ng, ns = c->ns;
    CUDA_OK(cudaMemcpyAsync(dst + ng * pl, src, sizeof(T) * pl * ns, cudaMemcpyDeviceToDevice, st));
-   CUDA_OK(cudaMemcpyAsync(dst, src + (long long)(ns - ng) * pl, sizeof(T) * pl * ng,
+   // ghost planes: the opposite interior planes (periodic) or the adjacent ones (zero slope, ghost width 1)
+   const bool clamp = c->p.clamp[c->p.ndim - 1] != 0;
+   CUDA_OK(cudaMemcpyAsync(dst, src + (clamp ? 0 : (long long)(ns - ng) * pl), sizeof(T) * pl * ng,
                            cudaMemcpyDeviceToDevice, st));
-   CUDA_OK(cudaMemcpyAsync(dst + (long long)(ng + ns) * pl, src, sizeof(T) * pl * ng,
-                           cudaMemcpyDeviceToDevice, st));
+   CUDA_OK(cudaMemcpyAsync(dst + (long long)(ng + ns) * pl, src + (clamp ? (long long)(ns - ng) * pl : 0),
+                           sizeof(T) * pl * ng, cudaMemcpyDeviceToDevice, st));
    return AMPE_OK;
 }
 
@@ -492,9 +521,15 @@ static Field make_field(const ampe_rhs_ctx* c, const double* base, const double*
       f.hi = hi;
       f.hcomp = (long long)c->ng * c->plane;
    } else {
-      // periodic wrap inside this rank: the ghost planes ARE the opposite interior planes
-      f.lo = base ? base + (long long)(c->ns - c->ng) * c->plane : nullptr;
-      f.hi = base;
+      if (c->p.clamp[c->p.ndim - 1]) {
+         // zero-slope boundary along the slab axis (ghost width 1): the ghost plane is the adjacent interior plane
+         f.lo = base;
+         f.hi = base ? base + (long long)(c->ns - c->ng) * c->plane : nullptr;
+      } else {
+         // periodic wrap inside this rank: the ghost planes ARE the opposite interior planes
+         f.lo = base ? base + (long long)(c->ns - c->ng) * c->plane : nullptr;
+         f.hi = base;
+      }
       f.hcomp = c->ncell;
    }
    (void)depth;
@@ -662,11 +697,24 @@ int ampe_launch_energy(ampe_rhs_ctx* c, const ampe_rhs_fields* y, cudaStream_t s
 }
 
 // part: 0 = everything, 1 = interior (no ghost plane needed), 2 = boundary planes
+// the uniform temperature of an evaluation at `time` (decks that ramp it: setTemperatureField at
+// QuatIntegrator.cc:3191 runs inside every evaluateRHSFunction); T-dependent parameters follow
+static int set_time(ampe_rhs_ctx* c, double time)
+{
+   if (c->cfg.dtemperaturedt == 0.0) return AMPE_OK;
+   const double T = ampe_uniform_temperature(c->cfg, time);
+   if (T == c->p.T_uniform) return AMPE_OK;
+   return ampe_derive_params_at(c->cfg, T, c->p);
+}
+
 static int eval_part(ampe_rhs_ctx* c, double time, const ampe_rhs_fields* y,
                      const ampe_rhs_fields* ydot, int fd_flag, cudaStream_t st, int part)
 {
-   (void)time;
    if (!c) return set_err(AMPE_EINVAL, "null argument");
+   {
+      int rc = set_time(c, time);
+      if (rc) return rc;
+   }
    const int ns = c->ns, ng = c->ng;
    if (part != 0 && ns < 4 * ng) return set_err(AMPE_EINVAL, "slab too thin to split");
    Ranges kks, cells;
@@ -764,6 +812,10 @@ static int eval_host_impl(ampe_rhs_ctx* c, ampe_halo* h, double time, const ampe
                           const ampe_rhs_fields* ydh, int fd_flag)
 {
    if (!c || !yh || !ydh) return set_err(AMPE_EINVAL, "null argument");
+   {
+      int rc = set_time(c, time);
+      if (rc) return rc;
+   }
    const Params& p = c->p;
    const size_t nb = (size_t)c->ncell * sizeof(double);
    if (!c->have_dev) {
@@ -889,7 +941,6 @@ static int eval_host_impl(ampe_rhs_ctx* c, ampe_halo* h, double time, const ampe
    CUDA_OK(cudaStreamSynchronize(s_out));
    // the next call overwrites dev_y on s_in: it must not overtake this call's kernels
    CUDA_OK(cudaStreamSynchronize(s_k));
-   (void)time;
    return AMPE_OK;
 }
 

@@ -70,6 +70,7 @@ static int launch_tma(const FusedArgs& A, cudaStream_t st, const char** err)
    const int nslab = A.s_end - A.s_begin;
    if (nslab <= 0) return AMPE_OK;
    if (!tma_enabled()) return -1;
+   if (p.clamp[0] || p.clamp[1]) return -1;  // physical boundaries: the cp.async tile kernel clamps while staging
    const unsigned long long n0 = p.n[0], ns = p.n[1], ncell = n0 * ns;
    TmaMaps M;
    int bad = tma_encode_3d(&M.phi, A.phi.base, n0, ns, 1, ncell, TT::SX, TT::SY);

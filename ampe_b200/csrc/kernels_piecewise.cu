@@ -341,6 +341,32 @@ int ampe_k_computerhsbiaswell(int ndim, const int* ifirst, const int* ilast, con
    });
 }
 
+// COMPUTERHSDELTATEMPERATURE (QuatFort.h:203; 2d/quatrhs.m4:893-940, 3d/quatrhs.m4:1040-1087)
+int ampe_k_computerhsdeltatemperature(int ndim, const int* ifirst, const int* ilast, const double* phi, int ngphi,
+                                      const double* temp, int ngtemp, double tm, double latentheat, double* rhs,
+                                      int ngrhs, const char* energy_interp_type, void* stream)
+{
+   if (!energy_interp_type || !(tm > 0.0)) return ampe_set_err(AMPE_EINVAL, "computerhsdeltatemperature: bad argument");
+   const Box b = mkbox(ndim, ifirst, ilast);
+   const CV ph = view(phi, b, -1, ngphi), T = view(temp, b, -1, ngtemp);
+   const DV r = view(rhs, b, -1, ngrhs);
+   const double alpha = latentheat / tm;
+   const double woff = (double)(0.25f / 6.f);  // REAL*4 expression in the 3D routine
+   const char it = energy_interp_type[0];
+   int L[3], H[3];
+   cell_bounds(b, 0, L, H);
+   return for_box(L, H, ST(stream), [=] __device__(int i, int j, int k) {
+      double wtemp;
+      if (ndim == 2)
+         wtemp = 0.75 * T(i, j, k) + 0.0625 * (T(i - 1, j, k) + T(i, j - 1, k) + T(i + 1, j, k) + T(i, j + 1, k));
+      else
+         wtemp = 0.75 * T(i, j, k) + woff * (T(i - 1, j, k) + T(i, j - 1, k) + T(i + 1, j, k) + T(i, j + 1, k) +
+                                             T(i, j, k - 1) + T(i, j, k + 1));
+      const double m = alpha * (tm - wtemp);
+      r(i, j, k) = r(i, j, k) + m * deriv_interp_func(ph(i, j, k), it);
+   });
+}
+
 // ---- quatdiffs.m4 / quatgrad.m4 -------------------------------------------------------------
 int ampe_k_quatdiffs(int ndim, const int* lo, const int* hi, int depth, const double* q, int ngq,
                      double* const* diff, int ngdiff, void* stream)

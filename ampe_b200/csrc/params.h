@@ -25,6 +25,7 @@ struct Params {
    int ng;        // ghost width of the state (1; 2 for Cahn-Hilliard)
    int with_phase, with_conc, with_T, evolve_quat;
    int flux_type, conc_form, free_energy, symm, modulus_from_cells;
+   int clamp[3];   // 1: zero-slope physical boundary in this direction (ghost = adjacent interior cell), 0: periodic
    int libm_trig;  // 1: evaluate the anisotropy with atan/acos/sincos exactly as written in the reference
    char energy_interp, conc_interp, diffusion_interp, orient_interp1, orient_interp2;
    char avg_func, conc_avg_func, grad_floor_type, quat_mobility_func;
@@ -51,6 +52,7 @@ struct Params {
    double thermal_diffusivity, latent_heat, cp, meltingT;
    double latent_over_cp;          // latent_heat/cp   computerhstemp
    double bias_coeff, bias_gamma;  // alpha/pi_f32, gamma   computerhsbiaswell
+   double deltaT_alpha;            // latent_heat/Tm        computerhsdeltatemperature
    double conc_mobility;
    double ch_ca, ch_cb, ch_well_scale, ch_kappa;
    // quadratic

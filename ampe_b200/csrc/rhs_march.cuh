@@ -86,10 +86,19 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
       int e = threadIdx.x + n * NT;
       e = (e < SP) ? e : -1;
       const int ee = (e < 0) ? 0 : e;
-      int gx = (ox - 1 + ee % SX) % n0;
-      gx = (gx < 0) ? gx + n0 : gx;
-      int gy = (oy - 1 + ee / SX) % n1;
-      gy = (gy < 0) ? gy + n1 : gy;
+      int gx = ox - 1 + ee % SX, gy = oy - 1 + ee / SX;
+      if (p.clamp[0]) {  // zero-slope boundary: the ghost cell is the adjacent interior cell
+         gx = (gx < 0) ? 0 : ((gx >= n0) ? n0 - 1 : gx);
+      } else {
+         gx %= n0;
+         gx = (gx < 0) ? gx + n0 : gx;
+      }
+      if (p.clamp[1]) {
+         gy = (gy < 0) ? 0 : ((gy >= n1) ? n1 - 1 : gy);
+      } else {
+         gy %= n1;
+         gy = (gy < 0) ? gy + n1 : gy;
+      }
       e_d[n] = e;
       e_ip[n] = gx + n0 * gy;
    }
@@ -102,7 +111,8 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
       long long qcomp;
       if (A.wrap_slab) {
          // one rank: the ghost planes are the opposite interior planes of the same array
-         const int slw = (sl < 0) ? sl + ns : ((sl >= ns) ? sl - ns : sl);
+         const int slw = p.clamp[2] ? ((sl < 0) ? 0 : ((sl >= ns) ? ns - 1 : sl))
+                                    : ((sl < 0) ? sl + ns : ((sl >= ns) ? sl - ns : sl));
          const long long o = (long long)slw * plane;
          b_phi = A.phi.base + o;
          b_T = WT ? A.T.base + o : nullptr;

@@ -544,6 +544,29 @@ struct Rhs3 {
             // computerhsbiaswell (2d/quatrhs.m4:834-843)
             const double m = p.bias_coeff * AMPE_ATAN(p.bias_gamma * (p.meltingT - temp));
             rhs = rhs + m * phi * (1.0 - phi);
+         } else if (free_energy == AMPE_FE_DELTAT) {
+            // computerhsdeltatemperature (2d/quatrhs.m4:893-940, 3d/quatrhs.m4:1040-1087): the temperature is
+            // smoothed over the cell and its face neighbours; 3D: woff = 0.25/6. is a REAL*4 expression
+            double wtemp;
+            if constexpr (WT) {
+               const double* sT = s + TT::O_T;
+               if constexpr (ND == 2) {
+                  wtemp = 0.75 * temp + 0.0625 * (sT[c - 1] + sT[c - TT::SX] + sT[c + 1] + sT[c + TT::SX]);
+               } else {
+                  const double woff = (double)(0.25f / 6.f);
+                  wtemp = 0.75 * temp + woff * (sT[c - 1] + sT[c - TT::SX] + sT[c + 1] + sT[c + TT::SX] +
+                                                sT[c + z.m] + sT[c + z.p]);
+               }
+            } else {
+               if constexpr (ND == 2) {
+                  wtemp = 0.75 * temp + 0.0625 * (temp + temp + temp + temp);
+               } else {
+                  const double woff = (double)(0.25f / 6.f);
+                  wtemp = 0.75 * temp + woff * (temp + temp + temp + temp + temp + temp);
+               }
+            }
+            const double m = p.deltaT_alpha * (p.meltingT - wtemp);
+            rhs = rhs + m * deriv_interp_func(phi, AMPE_SEL(energy_interp));
          } else if (CONC == AMPE_CONC_EBS && free_energy == AMPE_FE_CALPHAD) {
             // CALPHADFreeEnergyStrategyBinary.cc:321-323, 638-663: (f_l-f_a) - mu (c_l-c_a) comes
             // from the KKS kernel, which has the logarithms of the converged c_l, c_a at hand

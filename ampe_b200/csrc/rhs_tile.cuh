@@ -83,7 +83,9 @@ AMPE_DEV void stage_tile(const FusedArgs& A, double* s, int* s_iq, int ox, int o
    {
       constexpr int NROWS = TT::SY * TT::SZ;
       auto wrap_col = [&](int xs) {
-         int gx = (ox - TT::XH + xs) % n0;
+         int gx = ox - TT::XH + xs;
+         if (p.clamp[0]) return (gx < 0) ? 0 : ((gx >= n0) ? n0 - 1 : gx);  // zero-slope boundary
+         gx %= n0;
          return (gx < 0) ? gx + n0 : gx;
       };
       // element (row r, staged x) of every staged field; gx = wrap_col(xs)
@@ -94,8 +96,12 @@ AMPE_DEV void stage_tile(const FusedArgs& A, double* s, int* s_iq, int ox, int o
          int inplane = gx;  // offset inside a slab plane
          if (ND == 3) {
             int gj = oy + lj;  // in [-1, n1 + TY]: tiles overhang the domain by less than one tile
-            gj = (gj < 0) ? gj + n1 : gj;
-            gj = (gj >= n1) ? gj % n1 : gj;
+            if (p.clamp[1]) {
+               gj = (gj < 0) ? 0 : ((gj >= n1) ? n1 - 1 : gj);
+            } else {
+               gj = (gj < 0) ? gj + n1 : gj;
+               gj = (gj >= n1) ? gj % n1 : gj;
+            }
             sl = oz + lk;
             inplane += n0 * gj;
          } else {
@@ -108,7 +114,9 @@ AMPE_DEV void stage_tile(const FusedArgs& A, double* s, int* s_iq, int ox, int o
          const long long og = (long long)(sl + 1) * plane + inplane;  // slab-ghosted ctx arrays
          if (A.wrap_slab) {
             // one rank: the ghost planes are the opposite interior planes of the same array
-            const int slw = (sl < 0) ? sl + ns : ((sl >= ns) ? sl - ns : sl);
+            // (or, with a zero-slope boundary along the slab axis, the adjacent interior plane)
+            const int slw = p.clamp[ND - 1] ? ((sl < 0) ? 0 : ((sl >= ns) ? ns - 1 : sl))
+                                            : ((sl < 0) ? sl + ns : ((sl >= ns) ? sl - ns : sl));
             const long long o = (long long)slw * plane + inplane;
             cp_async8(s + TT::O_PHI + d, A.phi.base + o);
             if (WT) cp_async8(s + TT::O_T + d, A.T.base + o);

@@ -48,6 +48,7 @@ extern "C" {
 #define AMPE_FE_BIASWELL 1  /* BiasDoubleWellUTRCFreeEnergyStrategy           */
 #define AMPE_FE_CALPHAD 2   /* CALPHADFreeEnergyStrategyBinary                */
 #define AMPE_FE_QUADRATIC 3 /* QuadraticFreeEnergyStrategy                    */
+#define AMPE_FE_DELTAT 4    /* DeltaTemperatureFreeEnergyStrategy (FreeEnergyModel type "linear") */
 
 #define AMPE_MAX_TC 6 /* max number of temperature intervals per species G(T) */
 
@@ -131,6 +132,15 @@ typedef struct ampe_rhs_config {
    /* slab decomposition along the slowest axis (z in 3D, y in 2D): this
     * rank owns n[ndim-1] planes; ghost planes come from the neighbours.      */
    int nranks, rank;
+
+   /* physical boundaries (Geometry.periodic_dimension, ModelParameters.BoundaryConditions): 0 = periodic in
+    * this direction, 1 = every field has boundary = "slope", "0" on both faces of the direction
+    * (QuatRefinePatchStrategy -> CartesianRobinBcHelper with a = 0, b = 1, g = 0: the ghost cells take the value of
+    * the adjacent interior cell, edge / corner ghosts included).  Ghost width 1 models only.              */
+   int zero_slope[3];
+   /* ScalarTemperatureStrategy (ScalarTemperatureStrategy.cc:57-75): the uniform temperature of an evaluation
+    * at `time` is T_uniform + dtemperaturedt * time, limited by target_temperature                          */
+   double dtemperaturedt, target_temperature;
 } ampe_rhs_config;
 
 /* Device pointers of one state / RHS vector, SAMRAI CellData ghost 0:

@@ -58,6 +58,10 @@ int ampe_k_computerhstemp(int ndim, const int* ifirst, const int* ilast, const d
                           int ngtemp, const double* cp, int ngcp, int with_phase,
                           const double* phi_rhs, int ngphi_rhs, double* rhs, int ngrhs,
                           void* stream);
+/* COMPUTERHSDELTATEMPERATURE (QuatFort.h:203): DeltaTemperatureFreeEnergyStrategy::addDrivingForce */
+int ampe_k_computerhsdeltatemperature(int ndim, const int* ifirst, const int* ilast, const double* phi, int ngphi,
+                                      const double* temp, int ngtemp, double tm, double latentheat, double* rhs,
+                                      int ngrhs, const char* energy_interp_type, void* stream);
 /* COMPUTERHSBIASWELL (QuatFort.h:185) */
 int ampe_k_computerhsbiaswell(int ndim, const int* ifirst, const int* ilast, const double* phi,
                               int ngphi, const double* temp, int ngtemp, double alpha, double gamma,

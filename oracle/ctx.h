@@ -15,6 +15,7 @@ namespace oracle {
 
 struct Ctx {
    ampe_rhs_config cfg;
+   double T0 = 0.0;  // T_uniform of the deck; cfg.T_uniform holds the temperature of the current evaluation
    Box box;
    int ng;  // nghosts_required(): 1, or 2 for Cahn-Hilliard (QuatModelParameters.h:305-311)
    // scratch state with ghosts (fillScratch targets)

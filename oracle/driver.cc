@@ -17,6 +17,7 @@ Ctx* create(const ampe_rhs_config& cfg)
 {
    Ctx* c = new Ctx;
    c->cfg = cfg;
+   c->T0 = cfg.T_uniform;
    Box& b = c->box;
    b.ndim = cfg.ndim;
    for (int d = 0; d < 3; d++) {
@@ -91,11 +92,22 @@ static inline int wrap(int i, int n)
    i %= n;
    return i < 0 ? i + n : i;
 }
+// ghost index -> source index: periodic image, or (zero-slope physical boundary: boundary_N = "slope", "0" in
+// every BoundaryConditions block, CartesianRobinBcHelper with a = 0, b = 1, g = 0, whose type-1 and corner
+// formulas both reduce to the adjacent interior value) the nearest interior cell
+static inline int ghost_src(int i, int n, int zero_slope)
+{
+   if (zero_slope) return i < 0 ? 0 : (i >= n ? n - 1 : i);
+   return wrap(i, n);
+}
 
 // fillScratch (QuatIntegrator.cc:2873-2955) on a fully periodic single patch:
 // copy y -> scratch interior, ghosts = periodic images (incl. edges/corners).
+static const int* g_zero_slope = nullptr;  // of the context being evaluated (set by eval / set_ref)
 static void fill_periodic(const Box& b, const double* src, Field& dst, int ng, int depth)
 {
+   static const int none[3] = {0, 0, 0};
+   const int* zs = g_zero_slope ? g_zero_slope : none;
    const int n0 = b.hi[0] + 1, n1 = b.hi[1] + 1, n2 = b.hi[2] + 1;
    const int g2 = (b.ndim == 3) ? ng : 0;
    for (int m = 0; m < depth; m++)
@@ -103,7 +115,7 @@ static void fill_periodic(const Box& b, const double* src, Field& dst, int ng, i
       for (int k = -g2; k < n2 + g2; k++)
          for (int j = -ng; j < n1 + ng; j++)
             for (int i = -ng; i < n0 + ng; i++) {
-               const int is = wrap(i, n0), js = wrap(j, n1), ks = wrap(k, n2);
+               const int is = ghost_src(i, n0, zs[0]), js = ghost_src(j, n1, zs[1]), ks = ghost_src(k, n2, zs[2]);
                dst.v(i, j, k, m) =
                    src[(size_t)is + (size_t)n0 * (js + (size_t)n1 * (ks + (size_t)n2 * m))];
             }
@@ -136,6 +148,7 @@ void set_ref(Ctx* c, const double* cl_ref, const double* ca_ref)
 {
    // resetRefPhaseConcentrations (QuatModel.cc:5218-5231): whole-array copy,
    // ghosts included (here ghosts = periodic images of the given arrays)
+   g_zero_slope = c->cfg.zero_slope;
    if (cl_ref && ca_ref) {
       fill_periodic(c->box, cl_ref, c->cl_ref, c->ng, 1);
       fill_periodic(c->box, ca_ref, c->ca_ref, c->ng, 1);
@@ -167,7 +180,17 @@ static void views(SideField& s, View* v, int ndim, int m0 = 0)
 int eval(Ctx* c, double time, const ampe_rhs_fields* y, const ampe_rhs_fields* ydot,
          int fd_flag)
 {
-   (void)time;
+   g_zero_slope = c->cfg.zero_slope;
+   // setTemperatureField (QuatIntegrator.cc:3191) -> ScalarTemperatureStrategy::getCurrentTemperature
+   // (ScalarTemperatureStrategy.cc:57-75): the uniform temperature of this evaluation
+   if (c->cfg.dtemperaturedt != 0.0) {
+      double t = c->T0 + c->cfg.dtemperaturedt * time;
+      if (c->cfg.dtemperaturedt < 0. && t < c->cfg.target_temperature)
+         t = c->cfg.target_temperature;
+      else if (c->cfg.target_temperature > 0.0 && c->cfg.dtemperaturedt > 0. && t > c->cfg.target_temperature)
+         t = c->cfg.target_temperature;
+      c->cfg.T_uniform = t;
+   }
    const ampe_rhs_config& p = c->cfg;
    const Box& b = c->box;
    const int D = p.ndim, Q = p.qlen, ng = c->ng;
@@ -255,6 +278,10 @@ int eval(Ctx* c, double time, const ampe_rhs_fields* y, const ampe_rhs_fields* y
          for (auto& v : c->te.data) v = p.meltingT;
          computerhsbiaswell(b, c->phase.v, c->temp.v, p.bias_well_alpha, p.bias_well_gamma,
                             c->te.v, c->rhs_phase.v);
+      } else if (p.free_energy == AMPE_FE_DELTAT) {
+         // DeltaTemperatureFreeEnergyStrategy::addDrivingForce (DeltaTemperatureFreeEnergyStrategy.cc:96-153)
+         computerhsdeltatemperature(b, c->phase.v, c->temp.v, p.meltingT, p.latent_heat, c->rhs_phase.v,
+                                    p.energy_interp);
       } else if (p.free_energy == AMPE_FE_CALPHAD || p.free_energy == AMPE_FE_QUADRATIC) {
          add_driving_force(c);
       }

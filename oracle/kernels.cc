@@ -293,6 +293,27 @@ void computerhspbg(const Box& b, const double* dx, double misorientation_factor,
    }
 }
 
+// computerhsdeltatemperature: 2d/quatrhs.m4:893-940, 3d/quatrhs.m4:1040-1087
+void computerhsdeltatemperature(const Box& b, View phi, View temp, double tm, double latentheat, View rhs,
+                                char energy_interp_type)
+{
+   const double alpha = latentheat / tm;
+   const double woff = (double)(0.25f / 6.f);  // "woff = 0.25/6." is a REAL*4 expression (3d/quatrhs.m4:1062)
+   FOR_CELLS(b, i, j, k)
+   {
+      double wtemp;
+      if (b.ndim == 2)
+         wtemp = 0.75 * temp(i, j, k) +
+                 0.0625 * (temp(i - 1, j, k) + temp(i, j - 1, k) + temp(i + 1, j, k) + temp(i, j + 1, k));
+      else
+         wtemp = 0.75 * temp(i, j, k) + woff * (temp(i - 1, j, k) + temp(i, j - 1, k) + temp(i + 1, j, k) +
+                                                temp(i, j + 1, k) + temp(i, j, k - 1) + temp(i, j, k + 1));
+      const double m = alpha * (tm - wtemp);
+      const double h_prime = deriv_interp_func(phi(i, j, k), energy_interp_type);
+      rhs(i, j, k) = rhs(i, j, k) + m * h_prime;
+   }
+}
+
 // phaserhs_fenergy: 2d/quatrhs.m4:587-631
 void phaserhs_fenergy(const Box& b, View fl, View fa, View phi, View rhs, char interp)
 {

@@ -111,6 +111,8 @@ void computerhspbg(const Box& b, const double* dx, double misorientation_factor,
                    double eta_well_scale, View phi, View eta, View orient_grad_mod, View rhs,
                    char phi_well_type, char eta_well_type, char energy_interp_type,
                    char orient_interp1, char orient_interp2, int with_orient, int three_phase);
+void computerhsdeltatemperature(const Box& b, View phi, View temp, double tm, double latentheat, View rhs,
+                                char energy_interp_type);
 void phaserhs_fenergy(const Box& b, View fl, View fa, View phi, View rhs, char interp);
 void computerhstemp(const Box& b, const double* dx, double thermal_diffusivity,
                     double latent_heat, View temp, View cp, int with_phase, View phi_rhs,

@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""Generate the initial conditions of the reference's regression decks by running the reference's OWN generator,
+utils/make_nuclei.py, unmodified, with the command lines its tests use (tests/Dendrite/test2d.py:11-15,
+tests/SingleGrainGrowthAuNi/test2d.py:11-15, tests/TwoGrainsQuadratic/test3d.py:11-15).  The generator writes
+NetCDF-4 through the `netCDF4` module, which this image does not have: a stand-in module with the handful of calls
+the script makes (Dataset / createDimension / createVariable / var[:, :, :] = array / close) captures the arrays,
+which are committed as compressed fixtures under tests/golden/ (single precision, as the generator writes them).
+Run in the build container only (needs /root/reference):   python tools/make_reference_nuclei.py"""
+import os
+import runpy
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_UTILS = "/root/reference/utils"
+
+DECKS = {
+    # name: argv of make_nuclei.py as in the reference's test script
+    "dendrite": ["--nx", "240", "--ny", "240", "--nz", "1", "-r", "16", "--center0", "0, 0, 0", "-w", "1.4"],
+    "single_grain_auni": ["--nx", "64", "--ny", "64", "--nz", "1", "-r", "16", "--center0", "0, 0, 0", "-c", "0.25",
+                          "--concentration-in", "0.096"],
+    "two_grains_quadratic": ["--nx", "64", "--ny", "64", "--nz", "48", "-r", "8", "--concentration-in", "0.1",
+                             "--concentration-out", "0.06", "--ngrains", "2", "-q", "4"],
+}
+
+
+class _Var:
+    def __init__(self, store, name, dtype, shape):
+        self.store, self.name = store, name
+        self.store[name] = np.zeros(shape, dtype=np.float32 if dtype == "f" else np.float64)
+
+    def __setitem__(self, key, value):
+        self.store[self.name][key] = value
+
+
+class _Dataset:
+    captured = None
+
+    def __init__(self, filename, mode="w", format=None):
+        self.dims, self.vars = {}, {}
+        _Dataset.captured = self.vars
+
+    def createDimension(self, name, n):
+        self.dims[name] = n
+
+    def createVariable(self, name, dtype, dims):
+        return _Var(self.vars, name, dtype, tuple(self.dims[d] for d in dims))
+
+    def close(self):
+        pass
+
+
+def run(argv):
+    fake = types.ModuleType("netCDF4")
+    fake.Dataset = _Dataset
+    sys.modules["netCDF4"] = fake
+    sys.path.insert(0, REF_UTILS)
+    old = sys.argv
+    sys.argv = ["make_nuclei.py"] + argv + ["unused.nc"]
+    try:
+        runpy.run_path(os.path.join(REF_UTILS, "make_nuclei.py"), run_name="__main__")
+    finally:
+        sys.argv = old
+        sys.path.remove(REF_UTILS)
+    return dict(_Dataset.captured)
+
+
+if __name__ == "__main__":
+    out = os.path.join(ROOT, "tests", "golden")
+    for name, argv in DECKS.items():
+        fields = run(argv)
+        path = os.path.join(out, "ic_%s.npz" % name)
+        np.savez_compressed(path, **fields)
+        print(name, {k: (v.shape, str(v.dtype), float(v.min()), float(v.max())) for k, v in fields.items()},
+              "%d bytes" % os.path.getsize(path))
