@@ -397,3 +397,98 @@ def test_slab_decomposition_equals_single_rank(name):
                 assert torch.equal(out1[k], slab_planes(ref1[k], ndim, slice(lo_i, hi_i))), (name, rank, split, k, "fd1")
         r2.close()
     r.close()
+
+
+@pytest.mark.parametrize("case", ["dendrite_deck", "single_grain_deck", "auni3d_all_clamped", "gg3d_mixed",
+                                  "dendrite2d_x_only", "auni2d_ramp"])
+def test_zero_slope_boundaries_and_temperature_ramp(case):
+    """physical boundaries boundary_N = "slope", "0" (ghost = adjacent interior cell, corners included) per
+    direction, the DeltaTemperature free energy and the ScalarTemperatureStrategy ramp T(t): the fused path against
+    the restatement on the same fields, fd_flag 0 / 1 / 0, evaluated at a time t > 0"""
+    from ampe_b200 import configs, fields, rhs
+    from oracle import pyoracle
+    time = 0.0
+    if case == "dendrite_deck":
+        cfg = configs.dendrite_test2d()
+        base = "dendrite2d"
+    elif case == "single_grain_deck":
+        cfg = configs.single_grain_auni_test2d()
+        base, time = "auni2d", 0.17
+    elif case == "auni3d_all_clamped":
+        cfg = configs.auni3d(nx=36, ny=20, nz=12)
+        cfg.zero_slope[0] = cfg.zero_slope[1] = cfg.zero_slope[2] = 1
+        base = "auni3d"
+    elif case == "gg3d_mixed":
+        cfg = configs.gg3d_hbsm(nx=36, ny=20, nz=12)
+        cfg.zero_slope[1] = cfg.zero_slope[2] = 1       # periodic in x only
+        cfg.dtemperaturedt, cfg.target_temperature, base, time = -20.0, 573.0, "gg3d_hbsm", 0.05
+    elif case == "dendrite2d_x_only":
+        cfg = configs.dendrite2d(nx=72, ny=56)
+        cfg.zero_slope[0] = 1
+        base = "dendrite2d"
+    else:
+        cfg = configs.auni2d(nx=72, ny=56, symmetry=False)
+        cfg.dtemperaturedt, cfg.target_temperature, base, time = -200.0, 1220.0, "auni2d", 0.4
+    # fields of the same family on this grid (several grains, smooth noise); the deck models reuse them
+    c2 = configs.BUILDERS[base](**({"nx": cfg.n[0], "ny": cfg.n[1]} if cfg.ndim == 2 else
+                                   {"nx": cfg.n[0], "ny": cfg.n[1], "nz": cfg.n[2]}))
+    _, st = parity.make_case(base, **({"nx": cfg.n[0], "ny": cfg.n[1]} if cfg.ndim == 2 else
+                                      {"nx": cfg.n[0], "ny": cfg.n[1], "nz": cfg.n[2]}))
+    if cfg.qlen == 0:
+        st["quat"] = None
+    if not cfg.with_concentration:
+        st["conc"] = None
+    if cfg.with_unsteady_temperature and st.get("temperature") is None:
+        st["temperature"] = (0.7 + 0.3 * st["phase"]).contiguous()
+    if not cfg.with_unsteady_temperature:
+        st["temperature"] = None
+    y_np = {k: (None if v is None else v.numpy().copy()) for k, v in st.items()}
+    fds = (0, 1, 0)
+    outs = {}
+    for who in ("oracle", "ld"):
+        o = pyoracle.Oracle(cfg) if who == "oracle" else pyoracle.OracleLD(cfg)
+        if cfg.conc_rhs_form in (2, 3):
+            o.set_ref(y_np["conc"].ravel().copy(), y_np["conc"].ravel().copy())
+        res = []
+        for fd in fds:
+            if who == "oracle":
+                status, yd = o.eval(time, y_np, fd)
+            else:
+                status, yd = o.eval(time, y_np, fd)
+            assert status == 0
+            res.append(yd)
+        outs[who] = (res, o.phase_concentrations() if cfg.conc_rhs_form in (2, 3) else None)
+        o.close()
+    y = rhs.to_device(st)
+    r = rhs.QuatIntegratorRHS(cfg)
+    if cfg.conc_rhs_form in (2, 3):
+        c0 = y["conc"].reshape(-1).clone()
+        r.resetRefPhaseConcentrations(c0, c0.clone())
+    g = []
+    for fd in fds:
+        yd = y.like()
+        r.evaluateRHSFunction(time, y, yd, fd)
+        torch.cuda.synchronize()
+        g.append({k: (None if v is None else v.cpu().numpy()) for k, v in yd.items()})
+    gx = None
+    if cfg.conc_rhs_form in (2, 3):
+        cl, ca = r.phaseConcentrations()
+        gx = (cl.cpu().numpy(), ca.cpu().numpy())
+        assert r.newtonFailures() == 0
+    r.close()
+    errs = parity.compare_outputs(cfg, fds, outs["oracle"][0], outs["oracle"][1], g, gx,
+                                  (outs["ld"][0], outs["ld"][1]))
+    parity.check(errs)
+    # the boundary really is not periodic: the result differs from the periodic model's
+    if case in ("dendrite_deck", "auni3d_all_clamped"):
+        cfgp = type(cfg).from_buffer_copy(cfg)
+        cfgp.zero_slope[0] = cfgp.zero_slope[1] = cfgp.zero_slope[2] = 0
+        rp = rhs.QuatIntegratorRHS(cfgp)
+        if cfgp.conc_rhs_form in (2, 3):
+            c0 = y["conc"].reshape(-1).clone()
+            rp.resetRefPhaseConcentrations(c0, c0.clone())
+        ydp = y.like()
+        rp.evaluateRHSFunction(time, y, ydp, 0)
+        torch.cuda.synchronize()
+        assert not np.array_equal(ydp["phase"].cpu().numpy(), g[0]["phase"])
+        rp.close()

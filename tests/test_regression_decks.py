@@ -1,0 +1,151 @@
+"""The reference's regression decks with non-periodic boundaries / the models the periodic bench configurations
+do not touch, end to end with the reference's OWN acceptance numbers -- the only reference-held pins of the whole
+integrated right-hand side:
+
+  tests/Dendrite/test2d.py             solid fraction 0.10 +- 0.01 after t = 300          (anisotropic phase flux,
+                                       DeltaTemperature free energy, heat equation, slope-0 boundaries)
+  tests/SingleGrainGrowthAuNi/test2d.py  solid fraction 0.32 +- 0.01 after t = 0.3, integral of the composition
+                                       constant to 1e-4                                    (CALPHAD KKS Newton, EBS
+                                       composition flux, temperature ramp, slope-0 boundaries)
+  tests/TwoGrainsQuadratic/test3d.py   solid fraction 0.13 +- 0.01 after t = 0.08          (quadratic KKS, quaternion
+                                       RHS, 3D, periodic; GPU only -- its grain-volume lines need GrainDiagnostics,
+                                       which is out of scope)
+
+Initial conditions: the arrays the reference's generator utils/make_nuclei.py writes for the tests' own command
+lines (tests/golden/ic_*.npz, produced by tools/make_reference_nuclei.py running that script unmodified), written
+to a NetCDF classic file and read back through FieldsInitializer.  Time integration: the variable-step implicit
+integrator under the decks' tolerances (Integrator{atol}, rtol = 1e-2 atol, QuatIntegrator.cc:285-289).
+CPU: the restatement as the backend (Dendrite in full; the AuNi deck up to t = 0.04, its unpreconditioned steps are
+small).  GPU (-m gpu): all three on the device through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from ampe_b200 import configs, host_rhs, netcdf_classic
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def initial_conditions(name, cfg, tmp_path, init_t=None, init_q=None):
+    ic = np.load(os.path.join(ROOT, "tests", "golden", "ic_%s.npz" % name))
+    path = str(tmp_path / ("%s.nc" % name))
+    netcdf_classic.write(path, {k: ic[k] for k in ic.files})
+    fields = tuple(k for k, present in (("phase", True), ("quat", "quat1" in ic.files),
+                                        ("conc", "concentration0" in ic.files)) if present)
+    y = host_rhs.read_initial_conditions(path, cfg, fields=fields)
+    y = {k: (None if v is None else v.numpy().copy()) for k, v in y.items()}
+    nz = cfg.n[2] if cfg.ndim == 3 else 1
+    shape = (nz, cfg.n[1], cfg.n[0])
+    if init_q is not None:   # InitialConditions{init_q}: uniform orientation
+        y["quat"] = np.ascontiguousarray(np.broadcast_to(np.asarray(init_q, dtype=np.float64)[:, None, None, None],
+                                                         (len(init_q),) + shape))
+    if init_t is not None:   # InitialConditions{init_t}: uniform initial temperature
+        y["temperature"] = np.full(shape, float(init_t))
+    return y
+
+
+def run_oracle_deck(cfg, y, end_time, interval, atol, h0, stop_at=None):
+    from oracle import pyoracle
+    o = pyoracle.Oracle(cfg, perf=True)
+    o.L.oracle_set_num_threads(len(os.sched_getaffinity(0)))
+    if cfg.conc_rhs_form in (2, 3):
+        o.set_ref(y["conc"].ravel().copy(), y["conc"].ravel().copy())
+    t, h, steps, hist = 0.0, h0, 0, []
+    while t < (stop_at or end_time):
+        rc, st = o.integrate_adaptive(y, t + interval, h, t0=t, rtol=1e-2 * atol, atol=atol, max_steps=20000)
+        assert rc == 0, (rc, st)
+        t, h, steps = st["t_reached"], st["last_step"], steps + int(st["steps"])
+        hist.append((t, o.scalar_diagnostics(y)))
+    o.close()
+    return hist, steps
+
+
+def test_dendrite_deck_cpu(tmp_path):
+    """tests/Dendrite/test2d.py:36-44: after t > 300 the solid fraction is 0.1 +- 0.01"""
+    cfg = configs.dendrite_test2d()
+    y = initial_conditions("dendrite", cfg, tmp_path, init_t=0.7, init_q=(1.0, 0.0))
+    hist, steps = run_oracle_deck(cfg, y, 300.0, 15.0, 1.0e-4, 1.0e-3)
+    t, d = hist[-1]
+    assert t >= 300.0
+    assert abs(d["solid_fraction"] - 0.1) <= 1.0e-2, d["solid_fraction"]
+    assert steps <= 400  # the deck's max_timesteps
+    # growth is monotone; the far field stays at the initial undercooling, the solid sits near the melting point
+    fr = [x["solid_fraction"] for _t, x in hist]
+    assert all(b > a for a, b in zip(fr, fr[1:]))
+    assert 0.7 - 1e-6 <= d["min_temperature"] < 0.75 and 0.95 < d["max_temperature"] < 1.05
+
+
+def test_single_grain_auni_deck_cpu_start(tmp_path):
+    """tests/SingleGrainGrowthAuNi/test2d.py up to t = 0.04 (the full deck runs in the GPU suite): the integral of
+    the composition stays within 1e-4 of its first value (test2d.py:43-51) and the grain grows along the recorded
+    trajectory of the full run (0.0569 at t = 0.02, 0.0746 at t = 0.04)"""
+    cfg = configs.single_grain_auni_test2d()
+    y = initial_conditions("single_grain_auni", cfg, tmp_path)
+    hist, steps = run_oracle_deck(cfg, y, 0.3, 0.02, 1.0e-5, 1.0e-6, stop_at=0.04)
+    c0 = hist[0][1]["integral_concentration"]
+    for t, d in hist:
+        assert abs(d["integral_concentration"] - c0) <= 1.0e-4
+    assert hist[0][1]["solid_fraction"] == pytest.approx(0.0569, abs=5e-4)
+    assert hist[1][1]["solid_fraction"] == pytest.approx(0.0746, abs=5e-4)
+
+
+# ---- the same decks on the device ----------------------------------------------------------------
+def run_device_deck(cfg, y_np, end_time, interval, atol, h0, precond_cycles=0, max_total_steps=40000):
+    import torch
+    from ampe_b200 import rhs
+    y = rhs.SolutionVector({k: (None if v is None else torch.as_tensor(np.ascontiguousarray(v)).cuda())
+                            for k, v in y_np.items()})
+    h = host_rhs.HostQuatIntegrator(cfg, True)
+    if precond_cycles:
+        h.setupPreconditioners(precond_cycles)
+    diag = rhs.QuatIntegratorRHS(cfg)
+    if cfg.conc_rhs_form in (2, 3):
+        c0 = y["conc"].reshape(-1).clone()
+        h.resetRefPhaseConcentrations(c0, c0.clone())
+    t, step, steps, hist = 0.0, h0, 0, []
+    while t < end_time:
+        rc, st = h.integrateAdaptive(y, t + interval, step, t0=t, rtol=1e-2 * atol, atol=atol, max_steps=20000)
+        assert rc == 0, (rc, st)
+        t, step, steps = st["t_reached"], st["last_step"], steps + int(st["steps"])
+        assert steps <= max_total_steps
+        hist.append((t, diag.printScalarDiagnostics(y)))
+    h.close()
+    diag.close()
+    return hist, steps
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_dendrite_deck_gpu(tmp_path):
+    cfg = configs.dendrite_test2d()
+    y = initial_conditions("dendrite", cfg, tmp_path, init_t=0.7, init_q=(1.0, 0.0))
+    hist, steps = run_device_deck(cfg, y, 300.0, 15.0, 1.0e-4, 1.0e-3)
+    t, d = hist[-1]
+    assert t >= 300.0 and steps <= 400
+    assert abs(d["solid_fraction"] - 0.1) <= 1.0e-2, d["solid_fraction"]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_single_grain_auni_deck_gpu(tmp_path):
+    cfg = configs.single_grain_auni_test2d()
+    y = initial_conditions("single_grain_auni", cfg, tmp_path)
+    hist, steps = run_device_deck(cfg, y, 0.3, 0.02, 1.0e-5, 1.0e-6)
+    c0 = hist[0][1]["integral_concentration"]
+    for t, d in hist:
+        assert abs(d["integral_concentration"] - c0) <= 1.0e-4
+    t, d = hist[-1]
+    assert t >= 0.3
+    assert abs(d["solid_fraction"] - 0.32) <= 1.0e-2, d["solid_fraction"]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_two_grains_quadratic_deck_gpu(tmp_path):
+    cfg = configs.two_grains_quadratic_test3d()
+    y = initial_conditions("two_grains_quadratic", cfg, tmp_path)
+    hist, steps = run_device_deck(cfg, y, 0.08, 0.01, 1.0e-4, 1.0e-7, precond_cycles=2)
+    t, d = hist[-1]
+    assert t >= 0.08
+    assert abs(d["solid_fraction"] - 0.13) <= 1.0e-2, d["solid_fraction"]
