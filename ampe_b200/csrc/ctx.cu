@@ -652,6 +652,9 @@ static int eval_ranges(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs
    A.wrap_slab = c->have_halo ? 0 : 1;
    A.df = c->df;
    A.split3d = c->split3d ? 1 : 0;
+   A.wait_flag[0] = c->wait_flag[0];
+   A.wait_flag[1] = c->wait_flag[1];
+   A.wait_epoch = c->wait_epoch;
    A.use_lag = use_lag ? 1 : 0;
    A.write_lag = (recompute && c->cfg.lag_quat_sidegrad && !en) ? 1 : 0;
    for (int r = 0; r < cells.n; r++) {

@@ -27,6 +27,9 @@ struct ampe_rhs_ctx {
    int* conj_dev = nullptr;
    ampe_rhs_fields halo_lo, halo_hi;
    bool have_halo = false;
+   // set by halo.cu around an evaluation whose boundary blocks wait for the ghost planes themselves
+   const unsigned long long* wait_flag[2] = {nullptr, nullptr};
+   unsigned long long wait_epoch = 0;
    bool have_ref = false;
    bool lag_valid = false;
    bool generic_only = false;  // AMPE_B200_GENERIC at create time

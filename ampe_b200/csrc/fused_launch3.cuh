@@ -70,6 +70,7 @@ static int launch_tma(const FusedArgs& A, cudaStream_t st, const char** err)
    const int nslab = A.s_end - A.s_begin;
    if (nslab <= 0) return AMPE_OK;
    if (!tma_enabled()) return -1;
+   if (A.wait_epoch) return -1;              // slab ranks waiting inside the kernel: cp.async tile kernel
    if (p.clamp[0] || p.clamp[1]) return -1;  // physical boundaries: the cp.async tile kernel clamps while staging
    const unsigned long long n0 = p.n[0], ns = p.n[1], ncell = n0 * ns;
    TmaMaps M;

@@ -414,6 +414,29 @@ int ampe_rhs_eval_slab(ampe_rhs_ctx* c, ampe_halo* h, double time, const ampe_rh
    bool overlap = msg >= ((size_t)1 << 20) && c->ns >= 4 * c->ng;
    if (force) overlap = (force[0] == '1') && c->ns >= 4 * c->ng;
    int rc;
+   // Models without a KKS pre-pass (one fused kernel per evaluation): the push runs on the exchange stream and
+   // the kernel's own boundary blocks wait for the arrival flags (rhs_common.cuh wait_ghost_planes) -- no wait
+   // launch, the planes travel while every other block computes.  AMPE_B200_HALO_INKERNEL=0 switches it off.
+   const Params& p = c->p;
+   const bool one_kernel = !(p.conc_form == AMPE_CONC_KKS || p.conc_form == AMPE_CONC_EBS) &&
+                           p.conc_form != AMPE_CONC_CAHN_HILLIARD;
+   const char* ik = getenv("AMPE_B200_HALO_INKERNEL");
+   if (one_kernel && !(ik && ik[0] == '0') && !force) {
+      CUDA_OKH(cudaEventRecord(h->ev_ready, st));  // y is final once `st` gets here
+      CUDA_OKH(cudaStreamWaitEvent(h->comm, h->ev_ready, 0));
+      rc = ampe_halo_push(h, y, 3, h->comm);
+      if (rc) return rc;
+      const unsigned long long e = ++h->epoch_wait[0];
+      select_parity(h, (int)(e & 1));
+      c->wait_flag[0] = h->flag(h->region, 0, 0);
+      c->wait_flag[1] = h->flag(h->region, 0, 1);
+      c->wait_epoch = e;
+      rc = ampe_rhs_eval(c, time, y, ydot, fd_flag, st);
+      c->wait_epoch = 0;
+      if (rc) return rc;
+      h->launches += ampe_rhs_last_launch_count(c);
+      return AMPE_OK;
+   }
    if (overlap) {
       CUDA_OKH(cudaEventRecord(h->ev_ready, st));  // y is final once `st` gets here
       CUDA_OKH(cudaStreamWaitEvent(h->comm, h->ev_ready, 0));

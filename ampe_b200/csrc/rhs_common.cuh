@@ -44,7 +44,35 @@ struct FusedArgs {
    const double* df;    // CALPHAD driving force (f_l-f_a)-mu(c_l-c_a) per cell from the KKS kernel
    double* energy_partials;  // non-null: energy diagnostics instead of the RHS (energy_tile.cuh)
    int split3d;              // host side only: AMPE_B200_SPLIT3D, two launches per 3D EBS evaluation
+   // slab ranks (halo.cu): arrival flags of the lower / upper neighbour's ghost planes and the epoch to wait
+   // for.  wait_epoch != 0: the blocks whose stage touches a ghost plane wait for the flag themselves, so that
+   // the neighbours' pushes overlap the evaluation of every other block without a separate wait launch.
+   const unsigned long long* wait_flag[2];
+   unsigned long long wait_epoch;
 };
+
+// block-level wait for the ghost planes this block is about to stage (lo: below plane 0, hi: above plane ns-1)
+AMPE_DEV void wait_ghost_planes(const FusedArgs& A, bool lo, bool hi)
+{
+   if (A.wait_epoch == 0) return;  // uniform: single rank, or the exchange was waited for on the stream
+   if (lo || hi) {
+      if (threadIdx.x == 0) {
+         unsigned long long t0, t;
+         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+         for (int side = 0; side < 2; side++) {
+            if (!(side == 0 ? lo : hi)) continue;
+            const volatile unsigned long long* f = reinterpret_cast<const volatile unsigned long long*>(A.wait_flag[side]);
+            while (*f < A.wait_epoch) {
+               __nanosleep(64);
+               asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+               if (t - t0 > 60ull * 1000ull * 1000ull * 1000ull) __trap();  // a neighbour died: fail loudly
+            }
+         }
+         __threadfence_system();
+      }
+      __syncthreads();
+   }
+}
 
 // -DAMPE_SYMM_NOINLINE: the qlen-4 rotation as ONE out-of-line function (arguments and result in registers).
 // The symmetry-aware tile kernel inlines ~40 rotations per face pair: 5700 SASS instructions (91 KB), and ncu

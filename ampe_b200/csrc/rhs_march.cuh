@@ -182,6 +182,8 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
    const bool evolve_quat = (Q > 0) && AMPE_SEL(evolve_quat);
    (void)evolve_quat;
 
+   // slab ranks: the column's first / last block stages the neighbours' ghost planes
+   wait_ghost_planes(A, z0 == 0, zend >= ns);
    // ---- prologue: planes z0-1 and z0 (z0+1 is prefetched by the first step) -------------------
    load_plane(z0 - 1, 1);
    load_plane(z0, 2);

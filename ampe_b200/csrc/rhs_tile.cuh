@@ -338,6 +338,12 @@ __global__ void __launch_bounds__(TT::NT, (TT::NT <= 256) ? (TT::SYMM ? 2 : (TT:
    const int ox = blockIdx.x * TX;
    const int oy = blockIdx.y * TY + ((ND == 2) ? A.s_begin : 0);
    const int oz = (ND == 3) ? (blockIdx.z * TZ + A.s_begin) : 0;
+   {
+      // ghost planes along the slab axis this tile stages: rows / planes -1 and ns
+      const int ns = (ND == 3) ? p.n[2] : p.n[1];
+      const int o_s = (ND == 3) ? oz : oy, t_s = (ND == 3) ? TZ : TY;
+      wait_ghost_planes(A, o_s == 0, o_s + t_s >= ns);
+   }
    stage_tile<TT>(A, s, s_iq, ox, oy, oz);
    __syncthreads();
    tile_compute<TT>(A, s, s + TT::O_FC, s_iq, s_qr, s_conj, ox, oy, oz);

@@ -8,11 +8,15 @@ import torch.distributed as dist
 _SUM = ("volume", "volume_solid", "integral_concentration", "integral_phase_concentration", "thermal_energy")
 
 
-def combine_scalar_diagnostics(local, group=None, device="cpu"):
+def combine_scalar_diagnostics(local, group=None, device=None):
     """local: the dict of QuatIntegratorRHS.printScalarDiagnostics on this rank -> the dict of the whole domain
-    (every rank gets it).  Without an initialised process group the input is returned unchanged."""
+    (every rank gets it).  Without an initialised process group the input is returned unchanged.
+    device: where the reduction buffers live; default = what the group's backend can reduce (the current CUDA
+    device for NCCL, the host otherwise)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return dict(local)
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else "cpu"
     sums = torch.tensor([local[k] for k in _SUM] + [local["average_temperature"] * local["volume"]],
                         dtype=torch.float64, device=device)
     mx = torch.tensor([local["max_concentration"], local["max_temperature"], -local["min_temperature"]],

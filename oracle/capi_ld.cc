@@ -5,6 +5,9 @@
 // differences of Newton-solved concentrations): tests assert |gpu - ld| <= |oracle - ld| (+ 1e-12 scale).
 #include "ctx.h"
 #include "oracle.h"
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 using namespace oracle;
 
@@ -22,4 +25,12 @@ void oracle_ld_get_phase_concentrations(void* c, double* cl, double* ca)
    get_phase_concentrations((Ctx*)c, cl, ca);
 }
 int oracle_ld_sizeof_real(void) { return (int)sizeof(double); }
+void oracle_ld_set_num_threads(int n)
+{
+#ifdef _OPENMP
+   if (n > 0) omp_set_num_threads(n);
+#else
+   (void)n;
+#endif
+}
 }

@@ -15,8 +15,11 @@ sys.path.insert(0, os.path.dirname(_HERE))
 from ampe_b200 import _abi  # noqa: E402  (struct layouts only)
 
 
+_TARGETS = {False: "liboracle.so", True: "liboracle_perf.so", "par": "liboracle_par.so"}
+
+
 def build(perf=False):
-    target = "liboracle_perf.so" if perf else "liboracle.so"
+    target = _TARGETS[perf]
     subprocess.check_call(["make", "-s", "-C", _HERE, target])
     return os.path.join(_HERE, target)
 
@@ -37,7 +40,7 @@ def _stale(path):
 
 def lib(perf=False):
     if perf not in _libs:
-        path = os.path.join(_HERE, "liboracle_perf.so" if perf else "liboracle.so")
+        path = os.path.join(_HERE, _TARGETS[perf])
         if not os.path.exists(path) or _stale(path):
             build(perf)
         L = C.CDLL(path)

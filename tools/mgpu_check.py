@@ -32,8 +32,11 @@ def rotations(cfg, seed=7):
     return parity.random_rotations(cfg, seed)
 
 
-for overlap in ("0", "1"):
-    os.environ["AMPE_B200_HALO_OVERLAP"] = overlap
+for overlap in (None, "0", "1"):   # None: the library's own choice (in-kernel wait / overlap by message size)
+    if overlap is None:
+        os.environ.pop("AMPE_B200_HALO_OVERLAP", None)
+    else:
+        os.environ["AMPE_B200_HALO_OVERLAP"] = overlap
     for name, kw in SIZES.items():
         cfg = configs.BUILDERS[name](**kw)
         st = fields.make_state(name, cfg)          # the whole domain, same on every rank
