@@ -570,8 +570,13 @@ static int eval_ranges(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs
    if (use_lag && !c->lag_valid)
       return set_err(AMPE_EINVAL, "fd_flag=1 before any fd_flag=0 evaluation (no lagged data)");
 
+   const bool timed = c->time_kernels && first && last && !en;
    // ---- Cahn-Hilliard: composition-only model -------------------------------------------
    if (p.conc_form == AMPE_CONC_CAHN_HILLIARD) {
+      if (timed) {
+         CUDA_OK(cudaEventRecord(c->ev_t[0], st));
+         CUDA_OK(cudaEventRecord(c->ev_t[1], st));
+      }
       ChArgs A;
       A.p = p;
       A.conc = make_field(c, y->conc, c->halo_lo.conc, c->halo_hi.conc, 1);
@@ -588,6 +593,7 @@ static int eval_ranges(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs
          CUDA_OK(cudaGetLastError());
          c->launches++;
       }
+      if (timed) CUDA_OK(cudaEventRecord(c->ev_t[2], st));
       return AMPE_OK;
    }
 
@@ -596,7 +602,6 @@ static int eval_ranges(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs
    Field fq = make_field(c, y->quat, c->halo_lo.quat, c->halo_hi.quat, p.qlen);
    Field fc = make_field(c, y->conc, c->halo_lo.conc, c->halo_hi.conc, 1);
 
-   const bool timed = c->time_kernels && first && last && !en;
    if (timed) CUDA_OK(cudaEventRecord(c->ev_t[0], st));
    // ---- per-cell KKS solve on the slab and its ghost planes ------------------------------
    if (p.conc_form == AMPE_CONC_KKS || p.conc_form == AMPE_CONC_EBS) {
