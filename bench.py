@@ -210,6 +210,9 @@ def main():
                          "state is one time step away from the state the reference concentrations were converged "
                          "on; 'warm' = same state (converges at the first residual check); 'cold' = c_l = c_a = c")
     ap.add_argument("--cold-ref", action="store_true", help="same as --newton cold")
+    ap.add_argument("--no-lag", action="store_true",
+                    help="A/B only: Integrator{lag_quat_sidegrad = FALSE} -- no lagged face arrays are kept, fd_flag=1 "
+                         "evaluations recompute everything (the reference's default is TRUE)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the warm / cold Newton and per-kernel extras")
@@ -253,6 +256,9 @@ def main():
 
     cfg = configs.BUILDERS[args.workload](**kw)
     cfg.nranks, cfg.rank = world, rank
+    if args.no_lag:
+        cfg.lag_quat_sidegrad = 0
+        config["workload"] += ", lag_quat_sidegrad off"
     st = fields.make_state(args.workload, cfg, device=dev, slab=(rank, world))
     y = rhs.SolutionVector(st)
     ydot = y.like()
