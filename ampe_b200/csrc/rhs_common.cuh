@@ -51,9 +51,19 @@ struct FusedArgs {
    unsigned long long wait_epoch;
 };
 
+// zero-slope physical boundary in direction d (-DAMPE_NO_CLAMP compiles the periodic-only kernels: A/B builds)
+#ifdef AMPE_NO_CLAMP
+#define AMPE_CLAMP(d) 0
+#else
+#define AMPE_CLAMP(d) (p.clamp[d])
+#endif
+
 // block-level wait for the ghost planes this block is about to stage (lo: below plane 0, hi: above plane ns-1)
 AMPE_DEV void wait_ghost_planes(const FusedArgs& A, bool lo, bool hi)
 {
+#ifdef AMPE_NO_INKERNEL_WAIT
+   return;
+#endif
    if (A.wait_epoch == 0) return;  // uniform: single rank, or the exchange was waited for on the stream
    if (lo || hi) {
       if (threadIdx.x == 0) {

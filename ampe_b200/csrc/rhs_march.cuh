@@ -28,7 +28,15 @@ namespace ampe {
 // kernels trade re-staged phi planes (HBM has 4x headroom) for registers and resident warps.
 template <int Q_, int CONC_, bool WT_, class SEL_, int TY_, int NZ_, int PART_ = 0>
 struct March3 {
-   static constexpr int ND = 3, Q = Q_, CONC = CONC_, TX = 32, TY = TY_, NZ = NZ_, NT = 32 * TY_;
+   // AMPE_MARCH_EDGE_WARP: one extra warp per block computes the tile's upper edge faces (x = TX: TY faces, y = TY:
+   // 32 faces) and nothing else, so that no warp of the block carries a fourth face per plane (the block barrier
+   // after the faces waits for the slowest warp)
+#ifdef AMPE_MARCH_EDGE_WARP
+   static constexpr int EDGE_WARP = 1;
+#else
+   static constexpr int EDGE_WARP = 0;
+#endif
+   static constexpr int ND = 3, Q = Q_, CONC = CONC_, TX = 32, TY = TY_, NZ = NZ_, NT = 32 * (TY_ + EDGE_WARP);
    static constexpr bool SYMM = false, WT = WT_, HAS_PF = false;
    static constexpr int PART = PART_;
    // resident blocks per SM the register allocation is capped for (tile_shape.h)
@@ -77,6 +85,7 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
    const int ox = blockIdx.x * TX, oy = blockIdx.y * TY;
    const int z0 = A.s_begin + blockIdx.z * TT::NZ;
    const int zend = min(z0 + TT::NZ, A.s_end);
+   const bool own = (row < TY);                // false: the edge warp (AMPE_MARCH_EDGE_WARP)
    const int c = (lane + 1) + SX * (row + 1);  // this thread's cell inside a staged plane
 
    // ---- staging descriptors: the same in-plane elements every plane ------------------------
@@ -87,13 +96,13 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
       e = (e < SP) ? e : -1;
       const int ee = (e < 0) ? 0 : e;
       int gx = ox - 1 + ee % SX, gy = oy - 1 + ee / SX;
-      if (p.clamp[0]) {  // zero-slope boundary: the ghost cell is the adjacent interior cell
+      if (AMPE_CLAMP(0)) {  // zero-slope boundary: the ghost cell is the adjacent interior cell
          gx = (gx < 0) ? 0 : ((gx >= n0) ? n0 - 1 : gx);
       } else {
          gx %= n0;
          gx = (gx < 0) ? gx + n0 : gx;
       }
-      if (p.clamp[1]) {
+      if (AMPE_CLAMP(1)) {
          gy = (gy < 0) ? 0 : ((gy >= n1) ? n1 - 1 : gy);
       } else {
          gy %= n1;
@@ -102,6 +111,7 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
       e_d[n] = e;
       e_ip[n] = gx + n0 * gy;
    }
+   const int src_lo = AMPE_CLAMP(2) ? 0 : ns - 1, src_hi = AMPE_CLAMP(2) ? ns - 1 : 0;
    // cp.async of slab plane sl (-1 .. ns) into ring slot `slot`
    auto load_plane = [&](int sl, int slot) {
       double* dst = smem + slot * SLOT;
@@ -111,8 +121,8 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
       long long qcomp;
       if (A.wrap_slab) {
          // one rank: the ghost planes are the opposite interior planes of the same array
-         const int slw = p.clamp[2] ? ((sl < 0) ? 0 : ((sl >= ns) ? ns - 1 : sl))
-                                    : ((sl < 0) ? sl + ns : ((sl >= ns) ? sl - ns : sl));
+         // ghost width 1: plane -1 / ns is the opposite interior plane (periodic) or the adjacent one (zero slope)
+         const int slw = (sl < 0) ? src_lo : ((sl >= ns) ? src_hi : sl);
          const long long o = (long long)slw * plane;
          b_phi = A.phi.base + o;
          b_T = WT ? A.T.base + o : nullptr;
@@ -149,7 +159,7 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
 
    // ---- global bookkeeping of this thread's column ---------------------------------------------
    const int gi = ox + lane, gj = oy + row;
-   const bool in_i = gi < n0, in_j = gj < n1;
+   const bool in_i = gi < n0, in_j = own && gj < n1;
    const bool inr_x = (gi <= n0) && in_j;  // lower x face bounds a cell of the domain
    const bool inr_y = in_i && (gj <= n1);
    const bool inr_c = in_i && in_j;
@@ -157,8 +167,8 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
    const long long wrap_x = (gi == n0) ? n0 : 0;       // faces of overhanging cells wrap periodically
    const long long wrap_y = (gj == n1) ? plane : 0;
    // tile-edge faces: x = TX handled by warp 0 (lanes < TY), y = TY by the last warp
-   const bool edge_x = (row == 0) && (lane < TY);
-   const bool edge_y = (row == TY - 1);
+   const bool edge_x = (row == (TT::EDGE_WARP ? TY : 0)) && (lane < TY);
+   const bool edge_y = (row == (TT::EDGE_WARP ? TY : TY - 1));
    const int cex = (TX + 1) + SX * (lane + 1);  // staged cell whose lower x face is the tile's x edge
    const int cey = (lane + 1) + SX * (TY + 1);
    bool inr_ex = false, inr_ey = false;
@@ -202,7 +212,7 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
       z.p = (((j + 2) & 3) - ((j + 1) & 3)) * SLOT;
       const bool active = (k >= z0);
       const long long gcell = col + (long long)k * plane;
-      if (active) {
+      if (active && own) {
          // lower x / y faces of the own cell
          {
             const FaceVal v = R::template face<0>(A, sk, s_iq, s_qr, s_conj, c, c - 1, z, gcell - wrap_x, inr_x,
@@ -216,6 +226,8 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
             if (Q > 0) fyq[c] = v.fc;
             if (CONC != 0) fyc[c] = v.cf;
          }
+      }
+      if (active) {
          // upper edge faces of the tile (they belong to the neighbouring column)
          if (edge_x) {
             const FaceVal v = R::template face<0>(A, sk, s_iq, s_qr, s_conj, cex, cex - 1, z,
@@ -232,8 +244,10 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
       }
       // upper z face: between plane k (lower) and k+1; index of the lower face of cell k+1.
       // The block above recomputes the same value in its first step (identical bits).
-      const FaceVal vz = R::template face<2>(A, sk, s_iq, s_qr, s_conj, c + z.p, c, z, gcell + plane, inr_c,
-                                             A.write_lag && inr_c);
+      FaceVal vz;
+      vz.fc = 0.0, vz.pf = 0.0, vz.cf = 0.0;
+      if (own)
+         vz = R::template face<2>(A, sk, s_iq, s_qr, s_conj, c + z.p, c, z, gcell + plane, inr_c, A.write_lag && inr_c);
       __syncthreads();  // in-plane faces visible
       if (active && inr_c) {
          CellFaces<3> F;

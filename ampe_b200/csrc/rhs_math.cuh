@@ -269,8 +269,16 @@ struct Rhs3 {
    // ---- one face: between staged cells cm (lower) and c (upper), normal direction a ----------
    //  gface  index in the lagged arrays;  inrange  the face bounds a cell of the domain;
    //  wr  this work item refreshes the lagged arrays
+   // -DAMPE_FACE_NOINLINE: one out-of-line instance per direction instead of one inlined copy per call site (the
+   // main face pass and the tile-edge pass instantiate the same direction twice: the symmetry-aware tile kernel is
+   // 5500 SASS instructions and stalls on instruction fetch)
+#ifdef AMPE_FACE_NOINLINE
+#define AMPE_FACE_DEV __device__ __noinline__
+#else
+#define AMPE_FACE_DEV AMPE_DEV
+#endif
    template <int a>
-   AMPE_DEV static FaceVal face(const FusedArgs& A, const double* s, const int* s_iq,
+   AMPE_FACE_DEV static FaceVal face(const FusedArgs& A, const double* s, const int* s_iq,
                                 const double (*s_qr)[4], const int* s_conj, int c, int cm, ZOff z,
                                 long long gface, bool inrange, bool wr)
    {

@@ -84,7 +84,7 @@ AMPE_DEV void stage_tile(const FusedArgs& A, double* s, int* s_iq, int ox, int o
       constexpr int NROWS = TT::SY * TT::SZ;
       auto wrap_col = [&](int xs) {
          int gx = ox - TT::XH + xs;
-         if (p.clamp[0]) return (gx < 0) ? 0 : ((gx >= n0) ? n0 - 1 : gx);  // zero-slope boundary
+         if (AMPE_CLAMP(0)) return (gx < 0) ? 0 : ((gx >= n0) ? n0 - 1 : gx);  // zero-slope boundary
          gx %= n0;
          return (gx < 0) ? gx + n0 : gx;
       };
@@ -96,7 +96,7 @@ AMPE_DEV void stage_tile(const FusedArgs& A, double* s, int* s_iq, int ox, int o
          int inplane = gx;  // offset inside a slab plane
          if (ND == 3) {
             int gj = oy + lj;  // in [-1, n1 + TY]: tiles overhang the domain by less than one tile
-            if (p.clamp[1]) {
+            if (AMPE_CLAMP(1)) {
                gj = (gj < 0) ? 0 : ((gj >= n1) ? n1 - 1 : gj);
             } else {
                gj = (gj < 0) ? gj + n1 : gj;
@@ -115,7 +115,7 @@ AMPE_DEV void stage_tile(const FusedArgs& A, double* s, int* s_iq, int ox, int o
          if (A.wrap_slab) {
             // one rank: the ghost planes are the opposite interior planes of the same array
             // (or, with a zero-slope boundary along the slab axis, the adjacent interior plane)
-            const int slw = p.clamp[ND - 1] ? ((sl < 0) ? 0 : ((sl >= ns) ? ns - 1 : sl))
+            const int slw = AMPE_CLAMP(ND - 1) ? ((sl < 0) ? 0 : ((sl >= ns) ? ns - 1 : sl))
                                             : ((sl < 0) ? sl + ns : ((sl >= ns) ? sl - ns : sl));
             const long long o = (long long)slw * plane + inplane;
             cp_async8(s + TT::O_PHI + d, A.phi.base + o);
