@@ -31,10 +31,12 @@ struct March3 {
    // AMPE_MARCH_EDGE_WARP: one extra warp per block computes the tile's upper edge faces (x = TX: TY faces, y = TY:
    // 32 faces) and nothing else, so that no warp of the block carries a fourth face per plane (the block barrier
    // after the faces waits for the slowest warp)
+   // (measured, profiles/r02j_ab.log: AuNi_3D / EBS 13.80 -> 13.38 ms, GG3D / KKS 4.82 -> 5.06 ms: on for the fused
+   //  EBS instantiation, whose faces carry the CALPHAD mobilities; -DAMPE_MARCH_EDGE_WARP=0 / 1 forces it)
 #ifdef AMPE_MARCH_EDGE_WARP
-   static constexpr int EDGE_WARP = 1;
+   static constexpr int EDGE_WARP = AMPE_MARCH_EDGE_WARP;
 #else
-   static constexpr int EDGE_WARP = 0;
+   static constexpr int EDGE_WARP = (CONC_ == AMPE_CONC_EBS && PART_ == 0) ? 1 : 0;
 #endif
    static constexpr int ND = 3, Q = Q_, CONC = CONC_, TX = 32, TY = TY_, NZ = NZ_, NT = 32 * (TY_ + EDGE_WARP);
    static constexpr bool SYMM = false, WT = WT_, HAS_PF = false;

@@ -14,6 +14,14 @@
 
 #include "rhs_math.cuh"
 
+// the per-thread row loops of the face and cell phases: rolled (small code) by default, -DAMPE_TILE_UNROLL_ROWS
+// unrolls them (A/B builds: more independent work per thread, more registers)
+#ifdef AMPE_TILE_UNROLL_ROWS
+#define AMPE_TILE_ROW_UNROLL _Pragma("unroll")
+#else
+#define AMPE_TILE_ROW_UNROLL _Pragma("unroll 1")
+#endif
+
 namespace ampe {
 
 // ---- tile geometry + shared-memory carve-up -----------------------------------------------
@@ -222,7 +230,7 @@ AMPE_DEV void tile_compute(const FusedArgs& A, const double* s, double* sf, cons
          int gj = oy + lj0, gk = oz + lk0;
          long long gcell = gi + (long long)n0 * (gj + (long long)n1 * gk);
          const long long gstep = (long long)RSTEP_J * n0 + (long long)RSTEP_K * plane;
-#pragma unroll 1
+AMPE_TILE_ROW_UNROLL
          for (int u = 0; u < CPT; u++) {
             const bool in_i = gi < n0, in_j = gj < n1, in_k = gk < n2;
             {
@@ -285,7 +293,7 @@ AMPE_DEV void tile_compute(const FusedArgs& A, const double* s, double* sf, cons
       int fb = TT::fidx(lane, lj0, lk0);
       const int gi = ox + lane;
       int gj = oy + lj0, gk = oz + lk0;
-#pragma unroll 1
+AMPE_TILE_ROW_UNROLL
       for (int u = 0; u < CPT; u++) {
          bool ok = (gi < n0) && (gj < n1) && (gk < n2);
          if (ND == 2) ok = ok && (gj < A.s_end);
