@@ -16,10 +16,12 @@
 
 // the per-thread row loops of the face and cell phases: rolled (small code) by default, -DAMPE_TILE_UNROLL_ROWS
 // unrolls them (A/B builds: more independent work per thread, more registers)
+// Measured (profiles/r02k_ab.log): unrolled, the symmetry-aware AuNi_2D kernel gains 3 % (1.905 -> 1.847 ms), the
+// Dendrite2D kernel loses 3 % (0.133 -> 0.137 ms): unrolled for the symmetry-aware instantiations only.
 #ifdef AMPE_TILE_UNROLL_ROWS
 #define AMPE_TILE_ROW_UNROLL _Pragma("unroll")
 #else
-#define AMPE_TILE_ROW_UNROLL _Pragma("unroll 1")
+#define AMPE_TILE_ROW_UNROLL _Pragma("unroll(TT::SYMM ? TT::CPT : 1)")
 #endif
 
 namespace ampe {
