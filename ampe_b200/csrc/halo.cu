@@ -40,7 +40,7 @@ constexpr int MAX_SEG = 16;        // copies of one push: 2 sides x up to 8 comp
 constexpr int AUX_COMPS = 4;       // components of the auxiliary channel (reference concentrations, rotations)
 constexpr size_t FLAG_STRIDE = 64; // bytes between flags
 constexpr size_t FLAG_BYTES = 512;
-constexpr unsigned long long WAIT_TIMEOUT_NS = 60ull * 1000ull * 1000ull * 1000ull;
+constexpr unsigned long long WAIT_TIMEOUT_NS = 300ull * 1000ull * 1000ull * 1000ull;  // a rank may still be setting up
 
 struct PushArgs {
    const char* src[MAX_SEG];

@@ -49,6 +49,10 @@ struct Level {
    // updates all of them and reads the coefficients once); component m starts at m * cs
    int nc;
    long long cs;
+   // zero-slope (homogeneous Neumann) physical boundary per direction: the coefficient of the wrap face (lower face
+   // of the cells with index 0) is zero on every level, so that the periodic index arithmetic of the sweeps never
+   // couples the two ends, and the prolongation does not interpolate across the boundary
+   int clamp[3];
 };
 
 MG_HD double mg_c(const Level& L, long long o) { return L.c ? L.c[o] : L.c_const; }
@@ -324,18 +328,38 @@ MG_HD void mg_coarsen_cell(const Level& F, const Level& C, int I, int J, int K)
    }
 }
 
+// the parent's neighbour on the child's side: periodic image, or the parent itself at a zero-slope boundary
+MG_HD int mg_prolong_nb(int I, int upper, int n, int clamp)
+{
+   if (clamp && ((upper && I + 1 == n) || (!upper && I == 0))) return I;
+   return upper ? mg_up(I, n) : mg_dn(I, n);
+}
+
+// level 0, after the coefficients are set: a constant D becomes an array entry (fill != 0), and the wrap face of a
+// zero-slope direction carries no flux
+MG_HD void mg_boundary_faces_cell(const Level& L, int fill, int i, int j, int k)
+{
+   const long long o = mg_index(L, i, j, k);
+   const int idx[3] = {i, j, k};
+   for (int a = 0; a < L.ndim; a++) {
+      if (!L.d[a]) continue;
+      if (fill) L.d[a][o] = L.d_const[a];
+      if (L.clamp[a] && idx[a] == 0) L.d[a][o] = 0.0;
+   }
+}
+
 // fine cell (i,j,k): u_f += cell-centred (bi/tri)linear interpolation of the coarse correction
 // (weights 3/4 towards the parent, 1/4 towards the parent's neighbour on the child's side)
 MG_HD void mg_prolong_cell(const Level& C, const Level& F, int i, int j, int k)
 {
    const int I = i >> 1, J = j >> 1, K = F.ndim == 3 ? (k >> 1) : 0;
-   const int I2 = (i & 1) ? mg_up(I, C.n[0]) : mg_dn(I, C.n[0]);
-   const int J2 = (j & 1) ? mg_up(J, C.n[1]) : mg_dn(J, C.n[1]);
+   const int I2 = mg_prolong_nb(I, i & 1, C.n[0], C.clamp[0]);
+   const int J2 = mg_prolong_nb(J, j & 1, C.n[1], C.clamp[1]);
    for (int m = 0; m < F.nc; m++) {
       const double* cu = C.u + m * C.cs;
       double e;
       if (F.ndim == 3) {
-         const int K2 = (k & 1) ? mg_up(K, C.n[2]) : mg_dn(K, C.n[2]);
+         const int K2 = mg_prolong_nb(K, k & 1, C.n[2], C.clamp[2]);
          const double ea = 0.75 * (0.75 * cu[mg_index(C, I, J, K)] + 0.25 * cu[mg_index(C, I2, J, K)]) +
                            0.25 * (0.75 * cu[mg_index(C, I, J2, K)] + 0.25 * cu[mg_index(C, I2, J2, K)]);
          const double eb = 0.75 * (0.75 * cu[mg_index(C, I, J, K2)] + 0.25 * cu[mg_index(C, I2, J, K2)]) +

@@ -75,7 +75,7 @@ AMPE_DEV void wait_ghost_planes(const FusedArgs& A, bool lo, bool hi)
             while (*f < A.wait_epoch) {
                __nanosleep(64);
                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-               if (t - t0 > 60ull * 1000ull * 1000ull * 1000ull) __trap();  // a neighbour died: fail loudly
+               if (t - t0 > 300ull * 1000ull * 1000ull * 1000ull) __trap();  // a neighbour died: fail loudly
             }
          }
          __threadfence_system();

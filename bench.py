@@ -460,6 +460,8 @@ def main():
                 "newton": newton, "newton_failures": nf}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()  # nobody pushes into a neighbour's buffers any more
+        drv.close()
         dist.barrier()
         dist.destroy_process_group()
 

@@ -215,6 +215,8 @@ typedef struct ampe_halo ampe_halo;
 int ampe_halo_create(ampe_rhs_ctx* ctx, int rank, int nranks, ampe_halo** out);
 int ampe_halo_export(ampe_halo* h, void* handle /* AMPE_HALO_HANDLE_BYTES */);
 int ampe_halo_connect(ampe_halo* h, const void* handle_prev, const void* handle_next);
+/* destroy BEFORE the context, and only after every rank has finished its last evaluation (the neighbours push into
+ * this rank's buffers): the caller synchronises the ranks first (MPI_Barrier) */
 int ampe_halo_destroy(ampe_halo* h);
 /* evaluateRHSFunction on a slab with neighbours: push, interior planes, wait, boundary planes.  Collective over
  * the ranks in the sense that every rank must call it once per evaluation, in the same order. */
