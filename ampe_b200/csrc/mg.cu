@@ -53,6 +53,7 @@ struct ampe_mg {
    std::vector<double*> own_d[3];
    std::vector<char> two_colour; // level can be red-black coloured (all extents even)
    int pre = 1, post = 1, coarse = 8;
+   int zero_slope[3] = {0, 0, 0};  // homogeneous Neumann boundary per direction (ampe_mg_set_zero_slope)
    int launches = 0;
    int tail_level = -1;  // first level handled by the one-block tail kernel (-1: none)
    // fused red-black sweep (mg_rb_tile_pass): per level the second u array of the ping-pong and the tile
@@ -216,6 +217,16 @@ __global__ void mg_set_elliptic_kernel(Level L, const double* m, int ngm, const 
       int i, j, k;
       decode(L, idx, i, j, k);
       mg_set_elliptic_cell(L, m, ngm, c, ngc, d.a, have_d2 ? d2.a : nullptr, ngd, d_scale, inv_h2, i, j, k);
+   }
+}
+__global__ void mg_boundary_faces_kernel(Level L, int fill)
+{
+   const long long total = (long long)L.n[0] * L.n[1] * L.n[2];
+   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+        idx += (long long)gridDim.x * blockDim.x) {
+      int i, j, k;
+      decode(L, idx, i, j, k);
+      mg_boundary_faces_cell(L, fill, i, j, k);
    }
 }
 __global__ void mg_set_quat_kernel(Level L, double gamma, const double* mobility, int ngm, P3 fc, int ngfc,
@@ -495,6 +506,7 @@ int ampe_mg_create_multi(int ndim, const int* n, const double* dx, int with_colu
       if (g->with_s) L.s = p, p += nc;
       for (int d = 0; d < 3; d++) L.d[d] = nullptr, L.d_const[d] = 0.0;
       L.nc = ncomp, L.cs = nc;
+      L.clamp[0] = L.clamp[1] = L.clamp[2] = 0;
       L.u = p, p += nc * ncomp;
       L.f = p, p += nc * ncomp;
       L.r = p, p += nc * ncomp;
@@ -574,6 +586,17 @@ int ampe_mg_num_levels(const ampe_mg* g) { return g ? (int)g->levels.size() : 0;
 int ampe_mg_num_components(const ampe_mg* g) { return g ? g->ncomp : 0; }
 int ampe_mg_last_launch_count(const ampe_mg* g) { return g ? g->launches : 0; }
 
+int ampe_mg_set_zero_slope(ampe_mg* g, const int* zero_slope)
+{
+   if (!g || !zero_slope) return ampe_set_err(AMPE_EINVAL, "ampe_mg_set_zero_slope: NULL argument");
+   for (int d = 0; d < 3; d++) g->zero_slope[d] = (d < g->ndim && zero_slope[d]) ? 1 : 0;
+   for (Level& L : g->levels)
+      for (int d = 0; d < 3; d++) L.clamp[d] = g->zero_slope[d];
+   g->coefficients_set = false;  // the next set_* call rebuilds the face coefficients with the boundary faces zeroed
+   if (g->graph_exec) cudaGraphExecDestroy(g->graph_exec), g->graph_exec = nullptr;
+   return AMPE_OK;
+}
+
 int ampe_mg_set_sweeps(ampe_mg* g, int pre, int post, int coarse)
 {
    if (!g || pre < 0 || post < 0 || coarse < 1 || pre + post < 1)
@@ -629,13 +652,22 @@ int ampe_mg_set_elliptic(ampe_mg* g, const double* m, int ngm, double m_const, c
    }
    cudaStream_t st = (cudaStream_t)stream;
    g->launches = 0;
-   int rc = configure(g, c != nullptr, c_const, m != nullptr, m_const, d != nullptr, d_const);
+   // a zero-slope boundary needs the face coefficients as arrays (their wrap faces are zeroed), also where D is
+   // a constant of the block
+   const bool bc = g->zero_slope[0] || g->zero_slope[1] || g->zero_slope[2];
+   int rc = configure(g, c != nullptr, c_const, m != nullptr, m_const, d != nullptr || bc, d_const);
    if (rc) return rc;
-   if (m || c || d) {
+   if (m || c || d || bc) {
       const Level& L = g->levels[0];
-      mg_set_elliptic_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, m, ngm, c, ngc, p, p2, d2 ? 1 : 0, ngd, d_scale,
-                                                                g->inv_h2[0], g->inv_h2[1], g->inv_h2[2]);
-      g->launches += 1;
+      if (m || c || d) {
+         mg_set_elliptic_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, m, ngm, c, ngc, p, p2, d2 ? 1 : 0, ngd, d_scale,
+                                                                   g->inv_h2[0], g->inv_h2[1], g->inv_h2[2]);
+         g->launches += 1;
+      }
+      if (bc) {
+         mg_boundary_faces_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, d == nullptr ? 1 : 0);
+         g->launches += 1;
+      }
       return build_coarse(g, st);
    }
    g->coefficients_set = true;  // every coefficient is a constant: nothing to compute on the device
@@ -660,6 +692,10 @@ int ampe_mg_set_quat(ampe_mg* g, double gamma, const double* mobility, int ngm, 
    mg_set_quat_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, gamma, mobility, ngm, p, ngfc, g->inv_h2[0],
                                                          g->inv_h2[1], g->inv_h2[2]);
    g->launches += 1;
+   if (g->zero_slope[0] || g->zero_slope[1] || g->zero_slope[2]) {
+      mg_boundary_faces_kernel<<<grid_for(cells(L)), MT, 0, st>>>(L, 0);
+      g->launches += 1;
+   }
    return build_coarse(g, st);
 }
 
@@ -730,6 +766,7 @@ int ampe_k_phasefacops_setc(int ndim, const int* ifirst, const int* ilast, const
    L.c = L.m = L.s = L.u = L.f = L.r = nullptr;
    L.d[0] = L.d[1] = L.d[2] = nullptr;
    L.nc = 1, L.cs = 0;
+   L.clamp[0] = L.clamp[1] = L.clamp[2] = 0;
    phasefacops_setc_kernel<<<grid_for(cells(L)), MT, 0, (cudaStream_t)stream>>>(L, phi, ngphi, m, ngm, gamma,
                                                                               phi_well_scale, t, c, ngc);
    CUDA_OKM(cudaGetLastError());

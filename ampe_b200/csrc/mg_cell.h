@@ -393,7 +393,7 @@ MG_HD void mg_set_elliptic_cell(const Level& L, const double* m, int ngm, const 
    if (L.m) L.m[o] = m[mg_samrai_index(L, -1, ngm, i, j, k)];
    if (L.c) L.c[o] = c[mg_samrai_index(L, -1, ngc, i, j, k)];
    for (int a = 0; a < L.ndim; a++) {
-      if (!L.d[a]) continue;
+      if (!L.d[a] || !d) continue;  // a constant D stored as an array (zero-slope boundary): mg_boundary_faces_cell
       const long long os = mg_samrai_index(L, a, ngd, i, j, k);
       double D = d[a][os];
       if (d2) D += d2[a][os];

@@ -314,15 +314,19 @@ class QuatIntegrator
       if (p.with_phase && !d_phase_sys_solver) {
          d_phase_precond_c_id = cellVar<double>(1, 0);
          d_phase_sys_solver.reset(new PhaseFACSolver(d_hierarchy, d_phase_precond_c_id));
+         d_phase_sys_solver->setBoundaries(p.zero_slope);
       }
       const bool kks = p.conc_rhs_form == AMPE_CONC_KKS || p.conc_rhs_form == AMPE_CONC_EBS;
       if (p.with_concentration && kks && !d_conc_sys_solver) {
          d_conc_sys_solver.reset(new ConcFACSolver(d_hierarchy));
+         d_conc_sys_solver->setBoundaries(p.zero_slope);
          d_conc_l_g0_id = cellVar<double>(1, 0);
          d_conc_a_g0_id = cellVar<double>(1, 0);
       }
-      if (p.with_unsteady_temperature && !d_temperature_sys_solver)
+      if (p.with_unsteady_temperature && !d_temperature_sys_solver) {
          d_temperature_sys_solver.reset(new TemperatureFACSolver(d_hierarchy));
+         d_temperature_sys_solver->setBoundaries(p.zero_slope);
+      }
       if (d_precond_has_dquatdphi && !d_diffusion4quatderiv) {
          // RegisterVariables with d_precond_has_dquatdphi (QuatIntegrator.cc:1170-1190) and the
          // solver-owned scratch of QuatFACOps (d_sqrt_m_id, d_face_coef_scratch_id)

@@ -620,6 +620,8 @@ class QuatSysSolver
          for (int d = 0; d < 3; d++) n[d] = patch->getBox().numberCells(d);
          check(ampe_mg_create_multi(patch->getBox().ndim, n, patch->getDx(), 1, d_cfg.qlen, &d_mg),
                "ampe_mg_create(quat)");
+         // QuatFACOps::setPhysicalBcCoefObject: the Quat block of BoundaryConditions
+         check(ampe_mg_set_zero_slope(d_mg, d_cfg.zero_slope), "ampe_mg_set_zero_slope(quat)");
       }
       auto mob = patch->cell<double>(mobility_id);
       auto fc = patch->side<double>(d_fc_id);
@@ -1002,6 +1004,8 @@ class EllipticFACSolver
       check(ampe_mg_create(patch->getBox().ndim, n, patch->getDx(), 0, &d_mg), "ampe_mg_create");
    }
    virtual ~EllipticFACSolver() { ampe_mg_destroy(d_mg); }
+   // EllipticFACSolver::setBoundaries("Mixed", ...) with the deck's Robin coefficients: slope-0 per direction
+   void setBoundaries(const int* zero_slope) { check(ampe_mg_set_zero_slope(d_mg, zero_slope), "setBoundaries"); }
    void setM(int m_id) { d_m_id = m_id; }
    void setMConstant(double m) { d_m_id = -1, d_m_const = m; }
    void setCPatchDataId(int c_id) { d_c_id = c_id; }

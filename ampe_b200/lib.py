@@ -133,6 +133,8 @@ def load():
     L.ampe_mg_solve.argtypes = [vp, vp, vp, ci, ci, vp]
     L.ampe_mg_apply.restype = ci
     L.ampe_mg_apply.argtypes = [vp, vp, vp, vp]
+    L.ampe_mg_set_zero_slope.restype = ci
+    L.ampe_mg_set_zero_slope.argtypes = [vp, vp]
     L.ampe_mg_set_sweeps.restype = ci
     L.ampe_mg_set_sweeps.argtypes = [vp, ci, ci, ci]
     L.ampe_mg_num_levels.restype = ci

@@ -76,6 +76,11 @@ class LevelSolver:
         check(self.L.ampe_mg_apply(self.h, u.data_ptr(), out.data_ptr(), None), "ampe_mg_apply")
         return out
 
+    def set_zero_slope(self, zero_slope):
+        """homogeneous Neumann boundary per direction (before the set_* calls)"""
+        zs = (C.c_int * 3)(*(list(zero_slope) + [0] * (3 - len(zero_slope))))
+        check(self.L.ampe_mg_set_zero_slope(self.h, zs), "ampe_mg_set_zero_slope")
+
     def set_sweeps(self, pre, post, coarse):
         check(self.L.ampe_mg_set_sweeps(self.h, pre, post, coarse), "ampe_mg_set_sweeps")
 

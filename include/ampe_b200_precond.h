@@ -72,6 +72,12 @@ int ampe_mg_solve(ampe_mg* mg, const double* rhs, double* soln, int ncycles, int
 int ampe_mg_apply(ampe_mg* mg, const double* u, double* out, void* stream);
 /* pre / post smoothing sweeps per level (default 1, 1) and sweeps on the coarsest level (8)      */
 int ampe_mg_set_sweeps(ampe_mg* mg, int pre, int post, int coarse);
+/* Physical boundaries of the level: zero_slope[d] != 0 = homogeneous Neumann on both faces of direction d (the
+ * blocks of a deck whose BoundaryConditions are "slope", "0": the FAC solvers get their Robin coefficients from the same
+ * database, EllipticFACSolver::setBoundaries / QuatFACOps::setPhysicalBcCoefObject); 0 = periodic.  Call before the
+ * set_* functions: the coefficient of every boundary face is zero on every level, the prolongation does not interpolate
+ * across the boundary. */
+int ampe_mg_set_zero_slope(ampe_mg* mg, const int* zero_slope);
 int ampe_mg_num_levels(const ampe_mg* mg);
 int ampe_mg_level_extents(const ampe_mg* mg, int level, int* n_out /* [3] */);
 /* copy one coefficient array of a level into a caller-owned device array: which = 0 c, 1 m, 2 s,

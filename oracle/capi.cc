@@ -103,6 +103,7 @@ int oracle_mg_solve(void* g, const double* rhs, double* soln, int ncycles, int s
 }
 void oracle_mg_apply(void* g, const double* u, double* out) { ((HostMG*)g)->apply(u, out); }
 void oracle_mg_set_sweeps(void* g, int pre, int post, int coarse) { ((HostMG*)g)->setSweeps(pre, post, coarse); }
+void oracle_mg_set_zero_slope(void* g, const int* zero_slope) { ((HostMG*)g)->setZeroSlope(zero_slope); }
 int oracle_mg_set_fused(void* g, int on, long long min_cells)
 {
    ((HostMG*)g)->setFused(on != 0, min_cells);

@@ -241,6 +241,7 @@ HostMG::HostMG(int ndim, const int* n, const double* dx, bool with_s, int ncomp)
       if (with_s) L.s = p, p += nc;
       for (int d = 0; d < 3; d++) L.d[d] = nullptr, L.d_const[d] = 0.0;
       L.nc = d_nc, L.cs = (long long)nc;
+      L.clamp[0] = L.clamp[1] = L.clamp[2] = 0;
       L.u = p, p += nc * d_nc;
       L.f = p, p += nc * d_nc;
       L.r = p, p += nc * d_nc;
@@ -289,12 +290,23 @@ void HostMG::setElliptic(const double* m, int ngm, double m_const, const double*
                          const double* const* d, const double* const* d2, int ngd, double d_scale, double d_const)
 {
    if (d_with_s) throw std::runtime_error("HostMG::setElliptic on a quaternion solver");
-   configure(c != nullptr, c_const, m != nullptr, m_const, d != nullptr, d_const);
+   const bool bc = d_zero_slope[0] || d_zero_slope[1] || d_zero_slope[2];
+   configure(c != nullptr, c_const, m != nullptr, m_const, d != nullptr || bc, d_const);
    const Level& L = d_levels[0];
    if (m || c || d) {
       MG_FOR_CELLS(L) ampe_mg_cell::mg_set_elliptic_cell(L, m, ngm, c, ngc, d, d2, ngd, d_scale, d_inv_h2, i, j, k);
    }
+   if (bc) {
+      MG_FOR_CELLS(L) ampe_mg_cell::mg_boundary_faces_cell(L, d == nullptr ? 1 : 0, i, j, k);
+   }
    buildCoarse();
+}
+
+void HostMG::setZeroSlope(const int* zero_slope)
+{
+   for (int d = 0; d < 3; d++) d_zero_slope[d] = (d < d_ndim && zero_slope[d]) ? 1 : 0;
+   for (Level& L : d_levels)
+      for (int d = 0; d < 3; d++) L.clamp[d] = d_zero_slope[d];
 }
 
 void HostMG::setQuat(double gamma, const double* mobility, int ngm, const double* const* face_coef, int ngfc)
@@ -303,6 +315,9 @@ void HostMG::setQuat(double gamma, const double* mobility, int ngm, const double
    configure(false, 1.0, true, 0.0, true, 0.0);
    const Level& L = d_levels[0];
    MG_FOR_CELLS(L) ampe_mg_cell::mg_set_quat_cell(L, gamma, mobility, ngm, face_coef, ngfc, d_inv_h2, i, j, k);
+   if (d_zero_slope[0] || d_zero_slope[1] || d_zero_slope[2]) {
+      MG_FOR_CELLS(L) ampe_mg_cell::mg_boundary_faces_cell(L, 0, i, j, k);
+   }
    buildCoarse();
 }
 
@@ -477,7 +492,10 @@ int precond_setup(Ctx* c, double gamma, int ncycles, bool has_dquatdphi)
                const double gamma_m = gamma * m;
                P.phase_c.v(i, j, k) = 1.0 + gamma_m * p.phi_well_scale * g_phi_dbl_prime;
             }
-      if (!P.phase) P.phase.reset(new HostMG(D, n, p.dx, false));
+      if (!P.phase) {
+         P.phase.reset(new HostMG(D, n, p.dx, false));
+         P.phase->setZeroSlope(p.zero_slope);
+      }
       P.phase->setElliptic(c->phase_mobility.data.data(), 1, 0.0, P.phase_c.data.data(), 0, 0.0, nullptr, nullptr, 0,
                            1.0, -gamma * p.epsilon_phase * p.epsilon_phase);
    }
@@ -499,12 +517,18 @@ int precond_setup(Ctx* c, double gamma, int ncycles, bool has_dquatdphi)
             P.conc_d.a[a].data[o] = -gamma * v;
          }
       }
-      if (!P.conc) P.conc.reset(new HostMG(D, n, p.dx, false));
+      if (!P.conc) {
+         P.conc.reset(new HostMG(D, n, p.dx, false));
+         P.conc->setZeroSlope(p.zero_slope);
+      }
       P.conc->setElliptic(nullptr, 0, p.conc_mobility, nullptr, 0, 1.0, d1, ebs ? d2 : nullptr, 0, -gamma, 0.0);
    }
    if (p.with_unsteady_temperature) {
       // QuatIntegrator.cc:3340-3346: m = 1, c = 1, d = -gamma thermal_diffusivity
-      if (!P.temp) P.temp.reset(new HostMG(D, n, p.dx, false));
+      if (!P.temp) {
+         P.temp.reset(new HostMG(D, n, p.dx, false));
+         P.temp->setZeroSlope(p.zero_slope);
+      }
       P.temp->setElliptic(nullptr, 0, 1.0, nullptr, 0, 1.0, nullptr, nullptr, 0, 1.0, -gamma * p.thermal_diffusivity);
    }
    if (p.evolve_quat) {
@@ -514,7 +538,10 @@ int precond_setup(Ctx* c, double gamma, int ncycles, bool has_dquatdphi)
       for (size_t o = 0; o < c->quat_mobility.data.size(); o++) P.sqrt_m.data[o] = sqrt(c->quat_mobility.data[o]);
       const double* fc[3] = {nullptr, nullptr, nullptr};
       for (int a = 0; a < D; a++) fc[a] = c->face_coef.a[a].data.data();
-      if (!P.quat) P.quat.reset(new HostMG(D, n, p.dx, true, p.qlen));
+      if (!P.quat) {
+         P.quat.reset(new HostMG(D, n, p.dx, true, p.qlen));
+         P.quat->setZeroSlope(p.zero_slope);
+      }
       P.quat->setQuat(gamma, c->quat_mobility.data.data(), 1, fc, 0);
    }
    // setCoefficients with d_precond_has_dquatdphi (QuatIntegrator.cc:2978-2983, 3064-3070)

@@ -30,6 +30,8 @@ class HostMG
    void solve(const double* rhs, double* soln, int ncycles, bool symmetrized);
    void apply(const double* u, double* out) const;
    void setSweeps(int pre, int post, int coarse) { d_pre = pre, d_post = post, d_coarse = coarse; }
+   // homogeneous Neumann boundary per direction (same rule as ampe_mg_set_zero_slope); before the set* calls
+   void setZeroSlope(const int* zero_slope);
    // one red-black sweep per pass over tiles (mg_rb_tile_pass), same tile choice as ampe_b200/csrc/mg.cu;
    // min_cells: levels with fewer cells keep the colour half-sweeps (the device uses the tail threshold 4096)
    void setFused(bool on, long long min_cells = 4096);
@@ -50,6 +52,7 @@ class HostMG
    int d_n[3];
    double d_inv_h2[3];
    int d_pre = 1, d_post = 1, d_coarse = 8;
+   int d_zero_slope[3] = {0, 0, 0};
    std::vector<ampe_mg_cell::Level> d_levels;
    std::vector<std::vector<double>> d_store;
    std::vector<std::array<std::vector<double>, 5>> d_coef;

@@ -134,6 +134,7 @@ def lib(perf=False):
         L.oracle_mg_solve.argtypes = [vp, vp, vp, ci, ci]
         L.oracle_mg_apply.argtypes = [vp, vp, vp]
         L.oracle_mg_set_sweeps.argtypes = [vp, ci, ci, ci]
+        L.oracle_mg_set_zero_slope.argtypes = [vp, vp]
         L.oracle_mg_set_fused.restype = ci
         L.oracle_mg_set_fused.argtypes = [vp, ci, C.c_longlong]
         L.oracle_mg_num_levels.restype = ci
@@ -354,6 +355,9 @@ class HostMG:
 
     def set_sweeps(self, pre, post, coarse):
         self.L.oracle_mg_set_sweeps(self.h, pre, post, coarse)
+
+    def set_zero_slope(self, zero_slope):
+        self.L.oracle_mg_set_zero_slope(self.h, _ivec(list(zero_slope)))
 
     def set_fused(self, on=True, min_cells=4096):
         """one red-black sweep per pass over tiles (mg_rb_tile_pass) on the levels with more than min_cells

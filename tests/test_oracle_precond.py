@@ -513,3 +513,46 @@ def test_components_solved_together_equal_separate_solves(n, dx, fused):
     one = solver(1)
     separate = np.stack([one.solve(rhs[m], ncycles=3, symmetrized=True) for m in range(4)])
     assert together.shape == separate.shape and np.array_equal(together, separate)
+
+
+@pytest.mark.parametrize("n,dx", [((64, 48), (0.3, 0.2)), ((32, 16, 24), (0.5, 0.4, 0.25))])
+def test_zero_slope_boundaries_give_the_neumann_operator_and_the_vcycle_contracts(n, dx):
+    """ampe_mg_set_zero_slope / HostMG::setZeroSlope (the blocks of a deck with boundary_N = "slope", "0"): the face
+    coefficient of every boundary face is zero on every level -- the operator is the finite-volume operator with no
+    flux through the boundary (checked against numpy), a constant is in the null space of its diffusion part, and
+    the V-cycle contracts"""
+    from oracle import pyoracle
+    nd = len(n)
+    shape = tuple(reversed(n))
+    rng = np.random.default_rng(1)
+    h = pyoracle.HostMG(n, dx)
+    h.set_zero_slope([1] * nd)
+    dcoef = -0.37
+    h.set_elliptic(m_const=1.0, c_const=1.0, d_const=dcoef)
+    u = rng.standard_normal(shape)
+    ref = u.copy()
+    for a in range(nd):
+        ax = nd - 1 - a
+        up = np.roll(u, -1, ax) - u
+        dn = u - np.roll(u, 1, ax)
+        last = [slice(None)] * nd
+        last[ax] = -1
+        first = [slice(None)] * nd
+        first[ax] = 0
+        up[tuple(last)] = 0.0
+        dn[tuple(first)] = 0.0
+        ref += dcoef / dx[a] ** 2 * (up - dn)
+    got = h.apply(u)
+    assert np.abs(got - ref).max() <= 1e-14 * np.abs(ref).max()
+    one = np.ones(shape)
+    assert np.abs(h.apply(one) - one).max() <= 1e-13          # C u only: no flux anywhere
+    rhs = rng.standard_normal(shape)
+    res = []
+    for nc in (1, 2, 3):
+        z = h.solve(rhs, ncycles=nc)
+        res.append(np.linalg.norm(rhs - h.apply(z)) / np.linalg.norm(rhs))
+    assert res[0] < 0.15 and res[1] < 0.3 * res[0] + 1e-12 and res[2] < 0.3 * res[1] + 1e-12
+    # one periodic direction, one zero-slope direction: different operators
+    hp = pyoracle.HostMG(n, dx)
+    hp.set_elliptic(m_const=1.0, c_const=1.0, d_const=dcoef)
+    assert np.abs(hp.apply(u) - got).max() > 1e-3
