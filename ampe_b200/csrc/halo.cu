@@ -431,9 +431,12 @@ int ampe_rhs_eval_slab(ampe_rhs_ctx* c, ampe_halo* h, double time, const ampe_rh
       c->wait_flag[0] = h->flag(h->region, 0, 0);
       c->wait_flag[1] = h->flag(h->region, 0, 1);
       c->wait_epoch = e;
+      CUDA_OKH(cudaEventRecord(h->ev_arrived, h->comm));  // here: "my push has read y"
       rc = ampe_rhs_eval(c, time, y, ydot, fd_flag, st);
       c->wait_epoch = 0;
       if (rc) return rc;
+      // whatever follows on `st` may overwrite y (a time step): not before the push has read its boundary planes
+      CUDA_OKH(cudaStreamWaitEvent(st, h->ev_arrived, 0));
       h->launches += ampe_rhs_last_launch_count(c);
       return AMPE_OK;
    }

@@ -500,14 +500,19 @@ extern "C" int ampe_energy_eval(ampe_rhs_ctx* c, const ampe_rhs_fields* y, doubl
 // QuatModel::Advance does after the integrator returns) and, for the CALPHAD models, the Newton
 // initial guess is refreshed from the converged c_l, c_a (resetRefPhaseConcentrations,
 // QuatModel.cc:5218-5231).  work1/work2: caller-owned vectors shaped like y (work2 only for Heun).
-extern "C" int ampe_integrate_fixed(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs_fields* work1,
-                                    const ampe_rhs_fields* work2, double t0, double dt, int nsteps,
-                                    int scheme, void* stream)
+// h != NULL: slab rank with neighbours -- every evaluation exchanges the ghost planes (ampe_rhs_eval_slab); the
+// updates of y, the normalisation and the Newton reference reset are local to the rank
+static int integrate_fixed_impl(ampe_rhs_ctx* c, ampe_halo* h, const ampe_rhs_fields* y, const ampe_rhs_fields* work1,
+                                const ampe_rhs_fields* work2, double t0, double dt, int nsteps, int scheme, void* stream)
 {
    if (!c || !y || !work1) return ampe_set_err(AMPE_EINVAL, "null argument");
    if (scheme != 0 && scheme != 1) return ampe_set_err(AMPE_EINVAL, "scheme: 0 (Euler) or 1 (Heun)");
    if (scheme == 1 && !work2) return ampe_set_err(AMPE_EINVAL, "Heun needs work2");
-   if (c->have_halo) return ampe_set_err(AMPE_EINVAL, "multi-rank stepping: drive the exchange from the caller");
+   if (c->have_halo && !h)
+      return ampe_set_err(AMPE_EINVAL, "several ranks: use ampe_integrate_fixed_slab (or drive the exchange from the caller)");
+   auto rhs_eval = [&](double tt, const ampe_rhs_fields* yy, const ampe_rhs_fields* yd) {
+      return h ? ampe_rhs_eval_slab(c, h, tt, yy, yd, 0, stream) : ampe_rhs_eval(c, tt, yy, yd, 0, stream);
+   };
    const Params& p = c->p;
    cudaStream_t st = (cudaStream_t)stream;
    Comp vy;
@@ -516,7 +521,7 @@ extern "C" int ampe_integrate_fixed(ampe_rhs_ctx* c, const ampe_rhs_fields* y, c
    const bool kks = p.conc_form == AMPE_CONC_KKS || p.conc_form == AMPE_CONC_EBS;
    double t = t0;
    for (int s = 0; s < nsteps; s++) {
-      rc = ampe_rhs_eval(c, t, y, work1, 0, stream);
+      rc = rhs_eval(t, y, work1);
       if (rc) return rc;
       if (scheme == 0) {
          for (int n = 0; n < vy.n; n++)
@@ -535,7 +540,7 @@ extern "C" int ampe_integrate_fixed(ampe_rhs_ctx* c, const ampe_rhs_fields* y, c
          // y += dt/2 k1 now; k2 overwrites work1 afterwards
          for (int n = 0; n < vy.n; n++)
             axpy_kernel<<<grid_for(vy.len[n]), VT, 0, st>>>(0.5 * dt, vy.x[n], vy.z[n], vy.len[n]);
-         rc = ampe_rhs_eval(c, t + dt, &ystar, work1, 0, stream);
+         rc = rhs_eval(t + dt, &ystar, work1);
          if (rc) return rc;
          for (int n = 0; n < vy.n; n++)
             axpy_kernel<<<grid_for(vy.len[n]), VT, 0, st>>>(0.5 * dt, vy.x[n], vy.z[n], vy.len[n]);
@@ -552,6 +557,20 @@ extern "C" int ampe_integrate_fixed(ampe_rhs_ctx* c, const ampe_rhs_fields* y, c
    }
    CUDA_OKV(cudaGetLastError());
    return AMPE_OK;
+}
+
+extern "C" int ampe_integrate_fixed(ampe_rhs_ctx* c, const ampe_rhs_fields* y, const ampe_rhs_fields* work1,
+                                    const ampe_rhs_fields* work2, double t0, double dt, int nsteps,
+                                    int scheme, void* stream)
+{
+   return integrate_fixed_impl(c, nullptr, y, work1, work2, t0, dt, nsteps, scheme, stream);
+}
+extern "C" int ampe_integrate_fixed_slab(ampe_rhs_ctx* c, ampe_halo* h, const ampe_rhs_fields* y,
+                                         const ampe_rhs_fields* work1, const ampe_rhs_fields* work2, double t0,
+                                         double dt, int nsteps, int scheme, void* stream)
+{
+   if (!h) return ampe_set_err(AMPE_EINVAL, "ampe_integrate_fixed_slab: null halo");
+   return integrate_fixed_impl(c, h, y, work1, work2, t0, dt, nsteps, scheme, stream);
 }
 
 // QuatModel::printScalarDiagnostics (QuatModel.cc:2543-2690) on this rank's cells.  out[12]: domain volume,

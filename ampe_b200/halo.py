@@ -225,6 +225,19 @@ class DistributedRHS:
         check(self.rhs.L.ampe_rhs_set_symmetry_rotations_slab(self.rhs.h, self.h, arr, self._stream()),
               "set_rotations_slab")
 
+    def integrateFixed(self, y, dt, nsteps, scheme=0, t0=0.0):
+        """nsteps explicit steps (0 Euler, 1 Heun) of this rank's slab on the device, ghost planes exchanged at every
+        evaluation; y updated in place (QuatIntegratorRHS.integrateFixed on several ranks)"""
+        from .lib import check
+        w1 = y.like()
+        w2 = y.like() if scheme == 1 else None
+        fy, f1 = y.fields(), w1.fields()
+        f2 = w2.fields() if w2 is not None else None
+        check(self.rhs.L.ampe_integrate_fixed_slab(self.rhs.h, self.h, C.byref(fy), C.byref(f1),
+                                                   C.byref(f2) if f2 is not None else None, float(t0), float(dt),
+                                                   int(nsteps), int(scheme), self._stream()), "integrateFixed (slab)")
+        torch.cuda.current_stream().synchronize()
+
     def computeSymmetryRotations(self, y):
         """QuatModel::computeSymmetryRotations on this rank's slab (ghost planes of y and of the indices from the
         neighbours)"""

@@ -78,6 +78,8 @@ def load():
     L.ampe_rhs_set_symmetry_rotations_slab.argtypes = [vp, vp, C.POINTER(vp), vp]
     L.ampe_rhs_compute_symmetry_rotations_slab.restype = ci
     L.ampe_rhs_compute_symmetry_rotations_slab.argtypes = [vp, vp, pf, vp]
+    L.ampe_integrate_fixed_slab.restype = ci
+    L.ampe_integrate_fixed_slab.argtypes = [vp, vp, pf, pf, pf, dbl, dbl, ci, ci, vp]
     L.ampe_halo_last_launch_count.restype = ci
     L.ampe_halo_last_launch_count.argtypes = [vp]
     L.ampe_rhs_set_kernel_timing.restype = ci

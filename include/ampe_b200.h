@@ -291,6 +291,9 @@ int ampe_normalize_quat(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, void* strea
 int ampe_integrate_fixed(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, const ampe_rhs_fields* work1,
                          const ampe_rhs_fields* work2, double t0, double dt, int nsteps, int scheme,
                          void* stream);
+/* the same loop on a slab rank: every evaluation exchanges the ghost planes through `h` (collective over the ranks) */
+int ampe_integrate_fixed_slab(ampe_rhs_ctx* ctx, ampe_halo* h, const ampe_rhs_fields* y, const ampe_rhs_fields* work1,
+                              const ampe_rhs_fields* work2, double t0, double dt, int nsteps, int scheme, void* stream);
 /* ---- QuatModel::evaluateEnergy (QuatModel.cc:4888-4976) ->
  * quatenergy / bulkenergy ({2d,3d}/quatenergy.m4).  out[8] = total, phase interface,
  * orientational, q interface, double well, bulk free energy, 0, 0 (host array).  For the

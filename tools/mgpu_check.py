@@ -108,6 +108,32 @@ for overlap in (None, "0", "1"):   # None: the library's own choice (in-kernel w
                     bad += 1
                     print("rank %d %s RHS with the pre-pass indices: %s MISMATCH" % (rank, name, k), flush=True)
             rf.evaluateRHSFunction(0.0, yfull, ref[0], 0)  # the host-path check below uses these indices too
+        if overlap is None or overlap == "1":
+            # time stepping: y changes at every step, so a stale ghost plane or a buffer reused too early shows up as
+            # a difference from the single-rank trajectory (explicit Euler and Heun, Newton reference reset per step)
+            import parity
+            dt = 0.25 * parity.TRAJ_DT[name]   # (the grids here are finer than the ones the step sizes were found on)
+            for scheme, nsteps in ((0, 12), (1, 5)):
+                yf2 = rhs.SolutionVector({k: (None if v is None else v.clone()) for k, v in yfull.items()})
+                ys2 = rhs.SolutionVector({k: (None if v is None else v.clone()) for k, v in y.items()})
+                if kks:
+                    c0f, c0s = yf2["conc"].reshape(-1).clone(), ys2["conc"].reshape(-1).clone()
+                    rf.resetRefPhaseConcentrations(c0f, c0f.clone())
+                    drv.resetRefPhaseConcentrations(c0s, c0s.clone())
+                rf.integrateFixed(yf2, dt, nsteps, scheme=scheme)
+                drv.integrateFixed(ys2, dt, nsteps, scheme=scheme)
+                for k, v in ys2.items():
+                    if v is None:
+                        continue
+                    if not torch.equal(v, cut(yf2[k])):
+                        bad += 1
+                        print("rank %d %s overlap=%s trajectory (scheme %d) %s MISMATCH max abs %.3e" % (
+                            rank, name, overlap, scheme, k, (v - cut(yf2[k])).abs().max().item()), flush=True)
+            if kks:   # back to the reference state of the checks below
+                c0f, c0s = yfull["conc"].reshape(-1).clone(), y["conc"].reshape(-1).clone()
+                rf.resetRefPhaseConcentrations(c0f, c0f.clone())
+                drv.resetRefPhaseConcentrations(c0s, c0s.clone())
+                rf.evaluateRHSFunction(0.0, yfull, ref[0], 0)
         # the host-buffer path of the same slab (fd_flag = 0)
         yh = {k: (None if v is None else v.cpu().pin_memory()) for k, v in y.items()}
         oh = {k: (None if v is None else torch.full_like(v.cpu(), float("nan")).pin_memory()) for k, v in y.items()}
