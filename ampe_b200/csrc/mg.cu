@@ -216,7 +216,9 @@ __global__ void mg_set_elliptic_kernel(Level L, const double* m, int ngm, const 
         idx += (long long)gridDim.x * blockDim.x) {
       int i, j, k;
       decode(L, idx, i, j, k);
-      mg_set_elliptic_cell(L, m, ngm, c, ngc, d.a, have_d2 ? d2.a : nullptr, ngd, d_scale, inv_h2, i, j, k);
+      // (no diffusion arrays given: a constant D, possibly stored as an array for a zero-slope boundary)
+      mg_set_elliptic_cell(L, m, ngm, c, ngc, d.a[0] ? d.a : nullptr, have_d2 ? d2.a : nullptr, ngd, d_scale, inv_h2, i, j,
+                           k);
    }
 }
 __global__ void mg_boundary_faces_kernel(Level L, int fill)
