@@ -139,8 +139,10 @@ int ampe_derive_params_at(const ampe_rhs_config& c, double T_now, Params& p)
    p.conc_avg_func = c.conc_avg_func;
    p.grad_floor_type = c.grad_floor_type;
    p.quat_mobility_func = c.quat_mobility_func;
-   if (p.flux_type == AMPE_FLUX_ANISOTROPIC && (c.ndim != 2 || c.qlen == 0))
-      return set_err(AMPE_EINVAL, "anisotropic phase flux: 2D with orientation only (this build)");
+   if (p.flux_type == AMPE_FLUX_ANISOTROPIC && c.qlen == 0)
+      return set_err(AMPE_EINVAL, "Phase anisotropy requires quaternion orientation");  // PhaseFluxStrategyFactory.h:26
+   if (p.flux_type == AMPE_FLUX_ANISOTROPIC && c.ndim == 3 && (c.qlen != 4 || p.symm))
+      return set_err(AMPE_EINVAL, "3D anisotropic phase flux: qlen 4 without the symmetry-aware path");
    if (p.flux_type == AMPE_FLUX_ISOTROPIC && c.ndim != 2)
       return set_err(AMPE_EINVAL, "isotropic stencil is incomplete in 3D (reference stops)");
    if (p.conc_form == AMPE_CONC_EBS && c.free_energy != AMPE_FE_CALPHAD)

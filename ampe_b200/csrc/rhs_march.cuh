@@ -39,7 +39,9 @@ struct March3 {
    static constexpr int EDGE_WARP = (CONC_ == AMPE_CONC_EBS && PART_ == 0) ? 1 : 0;
 #endif
    static constexpr int ND = 3, Q = Q_, CONC = CONC_, TX = 32, TY = TY_, NZ = NZ_, NT = 32 * (TY_ + EDGE_WARP);
-   static constexpr bool SYMM = false, WT = WT_, HAS_PF = false;
+   // phase flux through the faces (3D anisotropic interface energy): the runtime-selector instantiations carry it,
+   // the compile-time selector sets of the shipped decks use the simple stencil
+   static constexpr bool SYMM = false, WT = WT_, HAS_PF = !SEL_::fixed && (Q_ == 4);
    static constexpr int PART = PART_;
    // resident blocks per SM the register allocation is capped for (tile_shape.h)
    static constexpr int MINB = (PART_ == 0) ? AMPE_MARCH_MINB : ((PART_ == 1) ? AMPE_SPLIT_MINB1 : AMPE_SPLIT_MINB2);
@@ -60,7 +62,8 @@ struct March3 {
    static constexpr int NSLOT = 4;
    // in-plane face values, indexed like the staged plane (lower face of staged cell c)
    static constexpr int O_FXQ = NSLOT * SLOT, O_FYQ = O_FXQ + SP, O_FXC = O_FYQ + SP, O_FYC = O_FXC + SP;
-   static constexpr int O_END = O_FYC + SP;
+   static constexpr int O_FXP = O_FYC + SP, O_FYP = O_FXP + (HAS_PF ? SP : 0);  // phase flux (HAS_PF)
+   static constexpr int O_END = O_FYP + (HAS_PF ? SP : 0);
    static constexpr size_t SMEM_BYTES = (size_t)O_END * sizeof(double);
    static constexpr int NE = (SP + NT - 1) / NT;  // staged elements per thread and field
 };
@@ -191,6 +194,10 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
    double* fyq = smem + TT::O_FYQ;
    double* fxc = smem + TT::O_FXC;
    double* fyc = smem + TT::O_FYC;
+   double* fxp = smem + TT::O_FXP;
+   double* fyp = smem + TT::O_FYP;
+   (void)fxp;
+   (void)fyp;
    const bool evolve_quat = (Q > 0) && AMPE_SEL(evolve_quat);
    (void)evolve_quat;
 
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
    load_plane(z0 - 1, 1);
    load_plane(z0, 2);
 
-   double fzq_lo = 0.0, fzc_lo = 0.0;  // lower z face of the current cell (registers)
+   double fzq_lo = 0.0, fzc_lo = 0.0, fzp_lo = 0.0;  // lower z face of the current cell (registers)
    int j = 0;                          // ring slot of plane k-1
    // step k = z0-1 only produces the z face between planes z0-1 and z0
 #pragma unroll 1
@@ -221,12 +228,14 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
                                                   A.write_lag && inr_x);
             if (Q > 0) fxq[c] = v.fc;
             if (CONC != 0) fxc[c] = v.cf;
+            if constexpr (TT::HAS_PF) fxp[c] = v.pf;
          }
          {
             const FaceVal v = R::template face<1>(A, sk, s_iq, s_qr, s_conj, c, c - SX, z, gcell - wrap_y, inr_y,
                                                   A.write_lag && inr_y);
             if (Q > 0) fyq[c] = v.fc;
             if (CONC != 0) fyc[c] = v.cf;
+            if constexpr (TT::HAS_PF) fyp[c] = v.pf;
          }
       }
       if (active) {
@@ -236,12 +245,14 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
                                                   col_ex + (long long)k * plane, inr_ex, false);
             if (Q > 0) fxq[cex] = v.fc;
             if (CONC != 0) fxc[cex] = v.cf;
+            if constexpr (TT::HAS_PF) fxp[cex] = v.pf;
          }
          if (edge_y) {
             const FaceVal v = R::template face<1>(A, sk, s_iq, s_qr, s_conj, cey, cey - SX, z,
                                                   col_ey + (long long)k * plane, inr_ey, false);
             if (Q > 0) fyq[cey] = v.fc;
             if (CONC != 0) fyc[cey] = v.cf;
+            if constexpr (TT::HAS_PF) fyp[cey] = v.pf;
          }
       }
       // upper z face: between plane k (lower) and k+1; index of the lower face of cell k+1.
@@ -265,11 +276,17 @@ __global__ void __launch_bounds__(TT::NT, TT::MINB) rhs_march_kernel(const __gri
          F.cfu[1] = (CONC != 0) ? fyc[c + SX] : 0.0;
          F.cfl[2] = fzc_lo;
          F.cfu[2] = vz.cf;
-         F.pfl[0] = F.pfl[1] = F.pfu[0] = F.pfu[1] = 0.0;
+         F.pfl[0] = TT::HAS_PF ? fxp[c] : 0.0;
+         F.pfu[0] = TT::HAS_PF ? fxp[c + 1] : 0.0;
+         F.pfl[1] = TT::HAS_PF ? fyp[c] : 0.0;
+         F.pfu[1] = TT::HAS_PF ? fyp[c + SX] : 0.0;
+         F.pfl[2] = fzp_lo;
+         F.pfu[2] = vz.pf;
          R::cell(A, sk, s_iq, s_qr, s_conj, c, z, F, gcell, ncell);
       }
       fzq_lo = vz.fc;
       fzc_lo = vz.cf;
+      fzp_lo = vz.pf;
    }
 }
 

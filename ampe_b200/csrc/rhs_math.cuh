@@ -164,7 +164,7 @@ struct FaceVal {
 template <int ND>
 struct CellFaces {
    double fcl[ND], fcu[ND], cfl[ND], cfu[ND];
-   double pfl[2], pfu[2];
+   double pfl[ND], pfu[ND];
 };
 
 // TT supplies: ND, Q, CONC, SYMM, WT, SEL, HAS_PF, S (doubles per staged field), SX (row pitch),
@@ -307,7 +307,50 @@ struct Rhs3 {
       }
 
       // ---- phase flux, non-simple stencils (2D) ----
-      if constexpr (TT::HAS_PF && Q > 0 && a < 2) if (flux_type == AMPE_FLUX_ANISOTROPIC) {
+      if constexpr (TT::HAS_PF && ND == 3 && Q == 4) if (flux_type == AMPE_FLUX_ANISOTROPIC) {
+         // anisotropic_gradient_flux, 3d/quatrhs.m4:180-349 with compute_dgamma (:149-177): cubic harmonic of the
+         // interface normal rotated into the crystal frame by the face-averaged quaternion (nu = eps4).  Evaluated
+         // with the reference's own operations (division, sqrt): only the runtime-selector kernels carry it.
+         const double* sp = s + TT::O_PHI;
+         const double* sq = s + TT::O_Q;
+         double g[3];
+#pragma unroll
+         for (int t = 0; t < 3; t++) {
+            if (t == a) {
+               g[t] = (phi_c - phi_m) * p.dinv[t];
+            } else {
+               const int ut = up(t, z), dt_ = dn(t, z);
+               g[t] = 0.25 * (sp[cm + ut] - sp[cm + dt_] + sp[c + ut] - sp[c + dt_]) * p.dinv[t];
+            }
+         }
+         const double eps4 = p.nu, epsilon = p.epsilon_phase;
+         const double factor = 4. * eps4 / (1. - 3. * eps4);
+         const double gphi2 = g[0] * g[0] + g[1] * g[1] + g[2] * g[2];
+         double dg_a = 0.0, n4 = 0.0;
+         if (fabs(gphi2) > (double)1.e-12f) {
+            const double nni = 1. / sqrt(gphi2);
+            const double n[4] = {0., g[0] * nni, g[1] * nni, g[2] * nni};
+            double qq[4], qp[4], qtmp[4], np[4], dg[4], dgamma[4];
+#pragma unroll
+            for (int m = 0; m < 4; m++) qq[m] = 0.5 * (sq[m * S + cm] + sq[m * S + c]);
+            qp[0] = qq[0], qp[1] = -qq[1], qp[2] = -qq[2], qp[3] = -qq[3];
+            quatmult4(n, qp, qtmp);
+            quatmult4(qq, qtmp, np);
+            const double a2 = np[1] * np[1], a3 = np[2] * np[2], a4 = np[3] * np[3];
+            n4 = a2 * a2 + a3 * a3 + a4 * a4;
+            dg[0] = 0.;
+            dg[1] = np[1] * (np[1] * np[1] - n4);
+            dg[2] = np[2] * (np[2] * np[2] - n4);
+            dg[3] = np[3] * (np[3] * np[3] - n4);
+            quatmult4(dg, qq, qtmp);
+            quatmult4(qp, qtmp, dgamma);
+            dg_a = dgamma[a + 1];
+         }
+         // (degenerate gradient: the reference's dgamma component of this direction is 0 and sqrt(gphi2) ~ 0)
+         const double gamma = epsilon * (1. - 3. * eps4) * (1. + factor * n4);
+         out.pf = gamma * gamma * g[a] + 16. * epsilon * gamma * eps4 * sqrt(gphi2) * dg_a;
+      }
+      if constexpr (TT::HAS_PF && ND == 2 && Q > 0 && a < 2) if (flux_type == AMPE_FLUX_ANISOTROPIC) {
          // anisotropic_gradient_flux, 2d/quatrhs.m4:154-256
          constexpr int st = (a == 0) ? TT::SX : 1;
          const double* sp = s + TT::O_PHI;
@@ -349,7 +392,7 @@ struct Rhs3 {
          const double e2 = epstheta * epstheta, ed = epstheta * depsdtheta;
          out.pf = (a == 0) ? fma(e2, dphidx, -(ed * dphidy)) : fma(e2, dphidy, ed * dphidx);
       }
-      if constexpr (TT::HAS_PF && a < 2) if (flux_type == AMPE_FLUX_ISOTROPIC) {
+      if constexpr (TT::HAS_PF && ND == 2 && a < 2) if (flux_type == AMPE_FLUX_ISOTROPIC) {
          // compute_flux_isotropic, 2d/quatrhs.m4:106-151
          constexpr int st = (a == 0) ? TT::SX : 1;
          const double* sp = s + TT::O_PHI;
@@ -497,6 +540,7 @@ struct Rhs3 {
          } else {
             diff_term = (F.pfu[0] - F.pfl[0]) * p.dinv[0];
             diff_term = diff_term + (F.pfu[1] - F.pfl[1]) * p.dinv[1];
+            if constexpr (ND == 3) diff_term = diff_term + (F.pfu[ND - 1] - F.pfl[ND - 1]) * p.dinv[ND - 1];
          }
          double rhs = diff_term;
          rhs = rhs - p.phi_well_scale * deriv_well_func(phi, 'd');

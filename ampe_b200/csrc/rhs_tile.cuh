@@ -310,10 +310,8 @@ AMPE_TILE_ROW_UNROLL
                F.fcu[a] = (Q > 0) ? sf[TT::F_FC + fu] : 0.0;
                F.cfl[a] = (CONC != 0) ? sf[TT::F_CF + fl] : 0.0;
                F.cfu[a] = (CONC != 0) ? sf[TT::F_CF + fu] : 0.0;
-               if (a < 2) {
-                  F.pfl[a] = TT::HAS_PF ? sf[TT::F_PF + fl] : 0.0;
-                  F.pfu[a] = TT::HAS_PF ? sf[TT::F_PF + fu] : 0.0;
-               }
+               F.pfl[a] = (TT::HAS_PF && a < 2) ? sf[TT::F_PF + fl] : 0.0;
+               F.pfu[a] = (TT::HAS_PF && a < 2) ? sf[TT::F_PF + fu] : 0.0;
             }
             R::cell(A, s, s_iq, s_qr, s_conj, c, ZT, F, gcell, ncell);
          }

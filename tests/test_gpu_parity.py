@@ -75,14 +75,26 @@ def test_ragged_sizes(name, kw):
 
 
 @pytest.mark.parametrize("variant", ["no_symmetry", "modulus_from_sides", "floor_tanh", "floor_sqrt",
-                                     "harmonic_avg", "lag_off", "isotropic_flux", "frozen_quat"])
+                                     "harmonic_avg", "lag_off", "isotropic_flux", "frozen_quat",
+                                     "anisotropic_3d_kks", "anisotropic_3d_ebs", "anisotropic_3d_clamped"])
 def test_model_switches(variant):
     """the runtime switches of QuatModelParameters that the hot path honours"""
     name = "auni2d"
     if variant in ("isotropic_flux", "frozen_quat"):
         name = "dendrite2d"
+    if variant in ("anisotropic_3d_kks", "anisotropic_3d_clamped"):
+        name = "gg3d_hbsm"
+    if variant == "anisotropic_3d_ebs":
+        name = "auni3d"
     cfg, st = parity.make_case(name)
     rot = None
+    if variant.startswith("anisotropic_3d"):
+        # 3D anisotropic interface energy (3d/quatrhs.m4:149-349) inside the fused marching kernel
+        cfg.symmetry_aware = 0
+        cfg.phase_flux_type = 2
+        cfg.epsilon_anisotropy = 0.05
+        if variant == "anisotropic_3d_clamped":
+            cfg.zero_slope[0] = cfg.zero_slope[2] = 1
     if variant == "no_symmetry":
         cfg.symmetry_aware = 0
     elif variant == "modulus_from_sides":
@@ -331,7 +343,7 @@ def test_full_size_properties(name):
             assert torch.equal(torch.roll(v, shifts[:cfg.ndim], dims), outs[k]), k
 
 
-@pytest.mark.parametrize("name", ["dendrite2d", "auni2d", "gg3d_hbsm", "auni3d", "pfhub1a"])
+@pytest.mark.parametrize("name", ["dendrite2d", "auni2d", "gg3d_hbsm", "auni3d", "pfhub1a", "gg3d_hbsm:anisotropic"])
 def test_slab_decomposition_equals_single_rank(name):
     """two slab 'ranks' on one GPU, ghost planes handed over through ampe_rhs_set_halo (what
     halo.py receives from the neighbour over NCCL): the union of the two slab evaluations is
@@ -339,8 +351,11 @@ def test_slab_decomposition_equals_single_rank(name):
     launch and for the interior/boundary split used to overlap the exchange"""
     from ampe_b200 import configs, rhs
     from ampe_b200.halo import slab_dim, slab_planes
+    name, _, flux = name.partition(":")
     cfg, st = parity.make_case(name)
     cfg.symmetry_aware = 0
+    if flux:
+        cfg.phase_flux_type, cfg.epsilon_anisotropy = 2, 0.05
     ndim = cfg.ndim
     y = rhs.to_device(st)
     r = rhs.QuatIntegratorRHS(cfg)
@@ -368,6 +383,7 @@ def test_slab_decomposition_equals_single_rank(name):
         for d in range(3):
             c2.dx[d] = cfg.dx[d]
         c2.symmetry_aware = 0
+        c2.phase_flux_type, c2.epsilon_anisotropy = cfg.phase_flux_type, cfg.epsilon_anisotropy
         c2.nranks, c2.rank = 2, rank
         take = lambda t, idx: t.index_select(dim, torch.tensor([i % ns for i in idx], device=t.device)).contiguous()
         ys = rhs.SolutionVector({k: (None if v is None else slab_planes(v, ndim, slice(lo_i, hi_i)).contiguous())
