@@ -197,6 +197,25 @@ def cpu_reference(workload, steps, warmup, newton, budget_s=25.0):
             "ms_per_step": dt_wall / done * 1e3, "steps": done}
 
 
+def bind_near_gpu(prop):
+    """restrict this process to the CPUs NVML reports as local to its GPU; returns how many, or None if the
+    platform does not say (single NUMA node, container cpuset, no NVML)"""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        bus = "%08x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        h = nv.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        before = os.sched_getaffinity(0)
+        nv.nvmlDeviceSetCpuAffinity(h)
+        after = os.sched_getaffinity(0)
+        if not after:
+            os.sched_setaffinity(0, before)
+            return None
+        return len(after)
+    except Exception:
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -252,6 +271,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # every rank's pinned host buffers and launching thread on the CPUs next to its GPU (first touch puts the
+        # pages on that NUMA node): the end-to-end leg of N ranks shares the host's memory system.  Not at N = 1,
+        # where the CPU baseline leg wants every host core.
+        config["host_cpus_per_rank"] = bind_near_gpu(torch.cuda.get_device_properties(dev))
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = configs.BUILDERS[args.workload](**kw)
