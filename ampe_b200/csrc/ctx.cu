@@ -118,8 +118,6 @@ int ampe_derive_params_at(const ampe_rhs_config& c, double T_now, Params& p)
       return set_err(AMPE_EINVAL, "zero-slope boundaries: ghost width 1 models only (not Cahn-Hilliard)");
    if ((p.clamp[0] || p.clamp[1] || p.clamp[2]) && c.symmetry_aware)
       return set_err(AMPE_EINVAL, "zero-slope boundaries with the symmetry-aware path are not supported");
-   if (p.clamp[c.ndim - 1] && c.nranks > 1)
-      return set_err(AMPE_EINVAL, "a zero-slope boundary along the slab axis needs a single rank");
    p.with_phase = c.with_phase;
    p.with_conc = c.with_concentration;
    p.with_T = c.with_unsteady_temperature;

@@ -210,20 +210,25 @@ int push_channel(ampe_halo* h, int ch, int nf, const char* const* src_lo, const 
    memset(&A, 0, sizeof(A));
    A.nbytes = nbytes;
    A.value = e;
+   // zero-slope physical boundary along the slab axis (ghost width 1): the first rank's lower ghost plane is its own
+   // lowest plane, the last rank's upper ghost plane its own highest one -- the ring is cut there and the plane goes
+   // into this rank's own receive slot (same flags, same epochs: every rank still gets two arrivals per exchange)
+   const bool cut = h->c->p.clamp[h->c->p.ndim - 1] != 0;
+   const bool self_lo = cut && h->rank == 0, self_hi = cut && h->rank == h->nranks - 1;
    for (int f = 0; f < nf; f++) {
       if (sides & 1) {
          A.src[A.nseg] = src_lo[f];
-         A.dst[A.nseg] = h->buf(h->peer[0], ch, parity, 1, f);
+         A.dst[A.nseg] = self_lo ? h->buf(h->region, ch, parity, 0, f) : h->buf(h->peer[0], ch, parity, 1, f);
          A.nseg++;
       }
       if (sides & 2) {
          A.src[A.nseg] = src_hi[f];
-         A.dst[A.nseg] = h->buf(h->peer[1], ch, parity, 0, f);
+         A.dst[A.nseg] = self_hi ? h->buf(h->region, ch, parity, 1, f) : h->buf(h->peer[1], ch, parity, 0, f);
          A.nseg++;
       }
    }
-   if (sides & 1) A.flag[0] = h->flag(h->peer[0], ch, 1);  // I am the lower neighbour's UPPER neighbour
-   if (sides & 2) A.flag[1] = h->flag(h->peer[1], ch, 0);
+   if (sides & 1) A.flag[0] = self_lo ? h->flag(h->region, ch, 0) : h->flag(h->peer[0], ch, 1);  // the lower neighbour's UPPER side
+   if (sides & 2) A.flag[1] = self_hi ? h->flag(h->region, ch, 1) : h->flag(h->peer[1], ch, 0);
    int rc = launch_push(h, A, st);
    if (rc) return rc;
    h->pushed[ch] |= sides;

@@ -53,35 +53,23 @@ class DeviceVectorOps
       check(ampe_vec_linear_sum(d_ctx, a, &x, b, &y, &z, nullptr), "linearSum");
    }
    void scale(double a, const Vec& x, Vec& z) { check(ampe_vec_scale(d_ctx, a, &x, &z, nullptr), "scale"); }
-   double wdot(const Vec& x, const Vec& y, const Vec& w)
-   {
-      double r = 0.0;
-      check(ampe_vec_wdot(d_ctx, &x, &y, &w, &r, nullptr), "wdot");
-      return r;
-   }
-   long long length() const { return d_length; }
+   // on slab ranks the sums run over every rank's cells: the owner's all-reduce hook is what AMPE's
+   // Sundials_SAMRAIVector gets from SAMRAI_MPI::sumReduction (every rank sees the same bits, so every rank takes the
+   // same step-size and convergence decisions)
+   inline double wdot(const Vec& x, const Vec& y, const Vec& w);
+   inline long long length() const;
    void errorWeights(const Vec& y, double rtol, double atol, Vec& w)
    {
       check(ampe_vec_error_weights(d_ctx, &y, rtol, atol, &w, nullptr), "errorWeights");
    }
-   int rhs(double t, const Vec& y, Vec& ydot, int fd_flag)
-   {
-      check(ampe_rhs_eval(d_ctx, t, &y, &ydot, fd_flag, nullptr), "ampe_rhs_eval");
-      return 0;
-   }
+   inline int rhs(double t, const Vec& y, Vec& ydot, int fd_flag);
    void applyProjection(double, const Vec& y, Vec& corr, Vec& err)
    {
       check(ampe_apply_projection(d_ctx, &y, &corr, &err, nullptr), "applyProjection");
    }
    // what QuatModel::Advance does after the integrator returns: normalizeQuat (QuatModel.cc:4222-4262)
    // and resetRefPhaseConcentrations (QuatModel.cc:5218-5231)
-   void postStep(Vec& y)
-   {
-      if (d_cfg.evolve_quat) check(ampe_normalize_quat(d_ctx, &y, nullptr), "normalizeQuat");
-      const bool kks = d_cfg.conc_rhs_form == AMPE_CONC_KKS || d_cfg.conc_rhs_form == AMPE_CONC_EBS;
-      if (kks && d_cfg.free_energy == AMPE_FE_CALPHAD)
-         check(ampe_rhs_set_ref_concentrations(d_ctx, nullptr, nullptr, nullptr), "resetRef");
-   }
+   inline void postStep(Vec& y);
    // CVSpgmrPrecondSet / CVSpgmrPrecondSolve of the owning QuatIntegrator (defined below the class)
    inline bool preconditioned() const;
    inline int precondSetup(double t, const Vec& y, double gamma);
@@ -100,6 +88,7 @@ class DeviceVectorOps
    QuatIntegrator* d_owner;
    size_t d_ncell;
    long long d_length;
+   mutable long long d_global_length = -1;  // slab ranks: unknowns of all ranks (one reduction, then cached)
 };
 
 class QuatIntegrator
@@ -120,11 +109,42 @@ class QuatIntegrator
       RegisterVariables();
       buildStrategies();
    }
-   ~QuatIntegrator() { ampe_rhs_destroy(d_ctx); }
+   ~QuatIntegrator()
+   {
+      if (d_halo) ampe_halo_destroy(d_halo);
+      ampe_rhs_destroy(d_ctx);
+   }
+
+   // ---- slab ranks (cfg.nranks > 1): the ghost planes along the slab axis come from the neighbours through the
+   // C-ABI exchange (what fillScratch gets from RefineSchedule::fillData over MPI, QuatIntegrator.cc:2873-2955).
+   // The application ships one handle per neighbour at set-up (MPI_Sendrecv in AMPE) and supplies the sum
+   // reduction of the vector operations (SAMRAI_MPI::sumReduction).
+   void haloExport(void* handle)
+   {
+      if (!d_halo) check(ampe_halo_create(d_ctx, d_cfg.rank, d_cfg.nranks, &d_halo), "ampe_halo_create");
+      check(ampe_halo_export(d_halo, handle), "ampe_halo_export");
+   }
+   void haloConnect(const void* handle_prev, const void* handle_next)
+   {
+      if (!d_halo) throw std::runtime_error("haloConnect: haloExport first");
+      check(ampe_halo_connect(d_halo, handle_prev, handle_next), "ampe_halo_connect");
+   }
+   typedef double (*SumReduction)(double local, void* user);
+   void setSumReduction(SumReduction fn, void* user) { d_sum_reduction = fn, d_sum_user = user; }
+   ampe_halo* halo() const { return d_halo; }
+   double sumReduction(double v) const
+   {
+      if (d_cfg.nranks > 1 && !d_sum_reduction) throw std::runtime_error("slab ranks: setSumReduction first");
+      return d_sum_reduction ? d_sum_reduction(v, d_sum_user) : v;
+   }
 
    // QuatModel::resetRefPhaseConcentrations (QuatModel.cc:5218-5231); ghost-0 device arrays
    void resetRefPhaseConcentrations(const double* cl_ref, const double* ca_ref)
    {
+      if (d_halo) {  // slab rank: the ghost planes of the reference state come from the neighbours (collective)
+         check(ampe_rhs_set_ref_concentrations_slab(d_ctx, d_halo, cl_ref, ca_ref, nullptr), "set_ref_slab");
+         return;
+      }
       check(ampe_rhs_set_ref_concentrations(d_ctx, cl_ref, ca_ref, nullptr), "set_ref");
       if (d_conc_l_ref_id < 0) return;
       const Box& b = d_patch->getBox();
@@ -160,9 +180,13 @@ class QuatIntegrator
                            int fd_flag)
    {
       if (d_use_fused) {
-         check(ampe_rhs_eval(d_ctx, time, y, y_dot, fd_flag, nullptr), "ampe_rhs_eval");
+         if (d_halo)
+            check(ampe_rhs_eval_slab(d_ctx, d_halo, time, y, y_dot, fd_flag, nullptr), "ampe_rhs_eval_slab");
+         else
+            check(ampe_rhs_eval(d_ctx, time, y, y_dot, fd_flag, nullptr), "ampe_rhs_eval");
          return 0;
       }
+      if (d_cfg.nranks > 1) throw std::runtime_error("the unfused Strategy path runs on one rank");
       const ampe_rhs_config& p = d_cfg;
       const bool recompute_quat_sidegrad = (fd_flag == 0) || !p.lag_quat_sidegrad;  // :3189
       setCoefficients(time, y, recompute_quat_sidegrad);
@@ -310,22 +334,28 @@ class QuatIntegrator
       d_precond_has_dquatdphi = precond_has_dquatdphi && p.with_phase && p.evolve_quat;  // :485
       d_use_preconditioner = ncycles > 0;
       if (!d_use_preconditioner) return;
-      if (p.nranks > 1) throw std::runtime_error("setupPreconditioners: single rank only");
+      // Slab ranks: block Jacobi over the ranks.  Every rank runs its block solvers on its own slab with no flux
+      // through the faces it shares with its neighbours (the zero-slope treatment of a physical boundary), so a
+      // solve needs no communication; GMRES sees the coupling between the slabs through the Jacobian-vector
+      // products.  The reference's FAC / hypre solvers span the ranks; this changes the Krylov iteration count, not
+      // the converged Newton step.
+      int zs[3] = {p.zero_slope[0], p.zero_slope[1], p.zero_slope[2]};
+      if (p.nranks > 1) zs[p.ndim - 1] = 1;
       if (p.with_phase && !d_phase_sys_solver) {
          d_phase_precond_c_id = cellVar<double>(1, 0);
          d_phase_sys_solver.reset(new PhaseFACSolver(d_hierarchy, d_phase_precond_c_id));
-         d_phase_sys_solver->setBoundaries(p.zero_slope);
+         d_phase_sys_solver->setBoundaries(zs);
       }
       const bool kks = p.conc_rhs_form == AMPE_CONC_KKS || p.conc_rhs_form == AMPE_CONC_EBS;
       if (p.with_concentration && kks && !d_conc_sys_solver) {
          d_conc_sys_solver.reset(new ConcFACSolver(d_hierarchy));
-         d_conc_sys_solver->setBoundaries(p.zero_slope);
+         d_conc_sys_solver->setBoundaries(zs);
          d_conc_l_g0_id = cellVar<double>(1, 0);
          d_conc_a_g0_id = cellVar<double>(1, 0);
       }
       if (p.with_unsteady_temperature && !d_temperature_sys_solver) {
          d_temperature_sys_solver.reset(new TemperatureFACSolver(d_hierarchy));
-         d_temperature_sys_solver->setBoundaries(p.zero_slope);
+         d_temperature_sys_solver->setBoundaries(zs);
       }
       if (d_precond_has_dquatdphi && !d_diffusion4quatderiv) {
          // RegisterVariables with d_precond_has_dquatdphi (QuatIntegrator.cc:1170-1190) and the
@@ -659,6 +689,9 @@ class QuatIntegrator
 
    ampe_rhs_config d_cfg;
    bool d_use_fused;
+   ampe_halo* d_halo = nullptr;
+   SumReduction d_sum_reduction = nullptr;
+   void* d_sum_user = nullptr;
    ampe_rhs_ctx* d_ctx = nullptr;
    std::shared_ptr<PatchHierarchy> d_hierarchy;
    std::shared_ptr<Patch> d_patch;
@@ -702,6 +735,41 @@ class QuatIntegrator
    std::shared_ptr<TemperatureFACSolver> d_temperature_sys_solver;
 };
 
+inline double DeviceVectorOps::wdot(const Vec& x, const Vec& y, const Vec& w)
+{
+   double r = 0.0;
+   check(ampe_vec_wdot(d_ctx, &x, &y, &w, &r, nullptr), "wdot");
+   return (d_owner && d_cfg.nranks > 1) ? d_owner->sumReduction(r) : r;
+}
+inline long long DeviceVectorOps::length() const
+{
+   if (!(d_owner && d_cfg.nranks > 1)) return d_length;
+   if (d_global_length < 0) d_global_length = (long long)d_owner->sumReduction((double)d_length);  // exact up to 2^53
+   return d_global_length;
+}
+inline int DeviceVectorOps::rhs(double t, const Vec& y, Vec& ydot, int fd_flag)
+{
+   if (d_owner && d_owner->halo())
+      check(ampe_rhs_eval_slab(d_ctx, d_owner->halo(), t, &y, &ydot, fd_flag, nullptr), "ampe_rhs_eval_slab");
+   else if (d_cfg.nranks > 1)
+      throw std::runtime_error("slab ranks: connect the ghost-plane exchange first (haloExport / haloConnect)");
+   else
+      check(ampe_rhs_eval(d_ctx, t, &y, &ydot, fd_flag, nullptr), "ampe_rhs_eval");
+   return 0;
+}
+// what QuatModel::Advance does after the integrator returns: normalizeQuat (QuatModel.cc:4222-4262)
+// and resetRefPhaseConcentrations (QuatModel.cc:5218-5231)
+inline void DeviceVectorOps::postStep(Vec& y)
+{
+   if (d_cfg.evolve_quat) check(ampe_normalize_quat(d_ctx, &y, nullptr), "normalizeQuat");
+   const bool kks = d_cfg.conc_rhs_form == AMPE_CONC_KKS || d_cfg.conc_rhs_form == AMPE_CONC_EBS;
+   if (kks && d_cfg.free_energy == AMPE_FE_CALPHAD) {
+      if (d_owner && d_owner->halo())
+         check(ampe_rhs_set_ref_concentrations_slab(d_ctx, d_owner->halo(), nullptr, nullptr, nullptr), "resetRef");
+      else
+         check(ampe_rhs_set_ref_concentrations(d_ctx, nullptr, nullptr, nullptr), "resetRef");
+   }
+}
 inline bool DeviceVectorOps::preconditioned() const { return d_owner && d_owner->usePreconditioner(); }
 inline int DeviceVectorOps::precondSetup(double t, const Vec& y, double gamma)
 {

@@ -621,7 +621,10 @@ class QuatSysSolver
          check(ampe_mg_create_multi(patch->getBox().ndim, n, patch->getDx(), 1, d_cfg.qlen, &d_mg),
                "ampe_mg_create(quat)");
          // QuatFACOps::setPhysicalBcCoefObject: the Quat block of BoundaryConditions
-         check(ampe_mg_set_zero_slope(d_mg, d_cfg.zero_slope), "ampe_mg_set_zero_slope(quat)");
+         // (slab ranks: block Jacobi over the ranks -- no flux through the faces between ranks)
+         int zs[3] = {d_cfg.zero_slope[0], d_cfg.zero_slope[1], d_cfg.zero_slope[2]};
+         if (d_cfg.nranks > 1) zs[d_cfg.ndim - 1] = 1;
+         check(ampe_mg_set_zero_slope(d_mg, zs), "ampe_mg_set_zero_slope(quat)");
       }
       auto mob = patch->cell<double>(mobility_id);
       auto fc = patch->side<double>(d_fc_id);

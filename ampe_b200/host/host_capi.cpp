@@ -42,6 +42,31 @@ int ampe_host_set_symmetry_rotations(void* h, const int* const* iqrot)
       return -1;
    }
 }
+// slab ranks: ghost-plane exchange of the integrator's context and the sum reduction of its vector operations
+int ampe_host_halo_export(void* h, void* handle)
+{
+   try {
+      static_cast<ampe_host::QuatIntegrator*>(h)->haloExport(handle);
+      return 0;
+   } catch (const std::exception& e) {
+      g_host_err = e.what();
+      return -1;
+   }
+}
+int ampe_host_halo_connect(void* h, const void* handle_prev, const void* handle_next)
+{
+   try {
+      static_cast<ampe_host::QuatIntegrator*>(h)->haloConnect(handle_prev, handle_next);
+      return 0;
+   } catch (const std::exception& e) {
+      g_host_err = e.what();
+      return -1;
+   }
+}
+void ampe_host_set_sum_reduction(void* h, double (*fn)(double, void*), void* user)
+{
+   static_cast<ampe_host::QuatIntegrator*>(h)->setSumReduction(fn, user);
+}
 // QuatIntegrator::evaluateRHSFunction(time, y, y_dot, fd_flag)
 int ampe_host_evaluate_rhs_function(void* h, double time, const ampe_rhs_fields* y,
                                     const ampe_rhs_fields* y_dot, int fd_flag)

@@ -14,6 +14,9 @@ _PATH = os.path.join(_HERE, "libampe_b200_host.so")
 _lib = None
 
 
+SUM_REDUCTION = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)  # double (*)(double local, void* user)
+
+
 def load_host():
     global _lib
     if _lib is None:
@@ -33,6 +36,12 @@ def load_host():
         L.ampe_host_evaluate_rhs_function.restype = C.c_int
         L.ampe_host_evaluate_rhs_function.argtypes = [vp, C.c_double, C.POINTER(_abi.RhsFields),
                                                       C.POINTER(_abi.RhsFields), C.c_int]
+        L.ampe_host_halo_export.restype = C.c_int
+        L.ampe_host_halo_export.argtypes = [vp, vp]
+        L.ampe_host_halo_connect.restype = C.c_int
+        L.ampe_host_halo_connect.argtypes = [vp, vp, vp]
+        L.ampe_host_set_sum_reduction.restype = None
+        L.ampe_host_set_sum_reduction.argtypes = [vp, SUM_REDUCTION, vp]
         L.ampe_host_integrate_implicit.restype = C.c_int
         L.ampe_host_integrate_implicit.argtypes = [vp, C.POINTER(_abi.RhsFields), C.c_double, C.c_double, C.c_int,
                                                    vp, vp, vp]
@@ -99,6 +108,34 @@ class HostQuatIntegrator:
     def _chk(self, rc):
         if rc != 0:
             raise AmpeError(self.L.ampe_host_last_error().decode())
+
+    def connectSlabRanks(self, rank, nranks, group=None):
+        """cfg.nranks > 1: map the neighbours' receive buffers (ampe_halo_* behind QuatIntegrator::haloExport /
+        haloConnect; the 128-byte handles travel through torch.distributed here, MPI_Sendrecv in AMPE) and install
+        the sum reduction of the vector operations (SAMRAI_MPI::sumReduction in AMPE).  Collective."""
+        import torch.distributed as dist
+        nb = 128
+        mine = C.create_string_buffer(nb)
+        self._chk(self.L.ampe_host_halo_export(self.h, mine))
+        blobs = [None] * nranks
+        dist.all_gather_object(blobs, bytes(mine.raw), group=group)
+        prev = C.create_string_buffer(blobs[(rank - 1) % nranks], nb)
+        nxt = C.create_string_buffer(blobs[(rank + 1) % nranks], nb)
+        rc = self.L.ampe_host_halo_connect(self.h, prev, nxt)
+        ok = [None] * nranks
+        dist.all_gather_object(ok, int(rc), group=group)
+        if any(v != 0 for v in ok):
+            self._chk(rc)
+            raise AmpeError("a neighbour could not map the receive buffers (codes %r)" % (ok,))
+        on_gpu = dist.get_backend(group) == "nccl"
+
+        def _sum(local, _user):
+            t = torch.tensor([local], dtype=torch.float64, device="cuda" if on_gpu else "cpu")
+            dist.all_reduce(t, group=group)
+            return float(t.item())
+        self._sum_cb = SUM_REDUCTION(_sum)  # keep the trampoline alive as long as the integrator
+        self.L.ampe_host_set_sum_reduction(self.h, self._sum_cb, None)
+        dist.barrier(group=group)
 
     def resetRefPhaseConcentrations(self, cl=None, ca=None):
         self._chk(self.L.ampe_host_reset_ref_phase_concentrations(

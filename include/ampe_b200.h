@@ -205,7 +205,8 @@ int ampe_rhs_eval_boundary(ampe_rhs_ctx* ctx, double time,
  * neighbours' flags: no packing, no library collective, no host synchronisation; the interior planes are
  * evaluated while the planes travel.  Double buffering by epoch parity orders the reuse of a buffer behind the
  * neighbour's previous-but-one evaluation without a second handshake.  nranks == 1 needs none of this (the
- * kernels wrap periodically inside the rank).
+ * kernels wrap periodically inside the rank).  With zero_slope set along the slab axis the ring is cut: the first
+ * rank's lower and the last rank's upper ghost planes are their own adjacent planes (same calls, same handles).
  *
  * Set-up, once: create on every rank, export the opaque handle, ship it to both neighbours with the host
  * application's own transport (MPI_Sendrecv in AMPE; torch.distributed in the tests; a socket in tests/cpp),

@@ -38,3 +38,16 @@ def test_torchrun_ranks_share_or_split_the_gpus(world):
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
     assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
     assert "MGPU CHECK OK" in p.stdout
+
+
+@pytest.mark.timeout(1200)
+def test_regression_decks_on_slab_ranks():
+    """tools/mgpu_deck.py: the Dendrite deck in full and the start of the SingleGrainGrowthAuNi deck integrated by the
+    variable-step implicit integrator on two slab ranks (zero-slope boundaries: the exchange ring is cut; vector
+    reductions through the sum-reduction hook) land on the one-rank solid fraction"""
+    env = dict(os.environ)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tools", "mgpu_deck.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=1100, env=env, cwd=ROOT)
+    assert p.returncode == 0, p.stdout[-4000:] + p.stderr[-4000:]
+    assert "MGPU DECK OK" in p.stdout
