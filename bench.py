@@ -409,6 +409,20 @@ def main():
             tj = json.load(open(tr))
             roofline["traffic"] = tj.get("dram_bytes_per_launch")
             roofline["ncu"] = tj.get("ncu")  # FP64 pipe / issue-slot utilisation of the same kernels (offline capture)
+            # the binding roof, live: FP64 operations of one evaluation (counted by ncu for this workload's per-GPU
+            # grid: thread-level DADD + DMUL + 2 DFMA; the count scales with the cells) over the live device time,
+            # against 148 SMs x 64 FP64 lanes x 2 (FMA) x SM clock
+            ks = (tj.get("ncu") or {}).get("kernels") or []
+            flop = sum(k["fp64_tflops"] * 1e12 * k["ncu_duration_ms"] * 1e-3 for k in ks)
+            if flop > 0 and tj.get("cells"):
+                flop *= r.ncell / float(tj["cells"])
+                sm_hz = float((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+                peak = 148 * 64 * 2 * sm_hz / 1e12
+                roofline["fp64"] = {"achieved": flop / (kms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                                    "frac": flop / (kms * 1e-3) / 1e12 / peak,
+                                    "note": "FMA peak; the library is built --fmad=false (bitwise translation "
+                                            "invariance), so most FP64 issue slots carry one flop: see "
+                                            "roofline.ncu.kernels[].fp64_pipe_pct for the pipe utilisation"}
         except Exception:
             pass
 

@@ -53,7 +53,10 @@ def main():
         seen.add(k["kernel"])
         uniq.append(k)
         per_eval += k["dram_read"] + k["dram_write"]
-    d = {"workload": workload, "dram_bytes_per_launch": per_eval,
+    # cells of the capture = bench.py's default per-GPU grid of the workload (bench.py scales the FLOP count with it)
+    cells = {"auni3d": 1024 * 1024 * 128, "dendrite2d": 2048 * 2048, "auni2d": 4096 * 4096,
+             "gg3d_hbsm": 512 * 512 * 256, "pfhub1a": 200 * 200}.get(workload)
+    d = {"workload": workload, "cells": cells, "dram_bytes_per_launch": per_eval,
          "kernel": " + ".join(k["kernel"].split("<")[0].replace("void ", "") for k in uniq) + " (one evaluateRHSFunction)",
          "source": "profiles/%s_ncu_full_%s.txt (ncu --set full --clock-control none, one launch per kernel)" % (tag, workload),
          "ncu": {"kernels": uniq, "fp64_fma_peak_tflops": 37.2,

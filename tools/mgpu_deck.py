@@ -82,17 +82,25 @@ def slab_of(cfg_builder, cfg, y_np):
 # unpreconditioned AuNi start is stiff: ~650 small steps whose Newton / error-test decisions sit on thresholds, so the
 # last bits of the reduced norms change which steps are retried (641 vs 660 steps measured) -- two valid trajectories
 # under the same tolerances, 1e-7 apart in solid fraction.  With the (different) preconditioners both runs solve
-# every Newton system to the same tolerance, not to the same iterate.
+# every Newton system to the same tolerance, not to the same iterate; block Jacobi is the weaker preconditioner, so
+# more linear solves miss their five Krylov vectors and the controller takes smaller steps (AuNi 492 steps on one
+# rank, 650 on two, 868 on four; TwoGrains 182 / 429 / 779) -- the step count is not compared there, the sharp
+# interface may sit a fraction of a cell apart (pointwise tolerance 0.1), the solid fractions agree to 1e-3.
 CASES = [("dendrite", configs.dendrite_test2d, dict(init_t=0.7, init_q=(1.0, 0.0)), (300.0, 15.0, 1.0e-4, 1.0e-3), 0, 0.10,
           (1e-7, 1e-6, 0.01)),
          ("single_grain_auni", configs.single_grain_auni_test2d, {}, (0.02, 0.02, 1.0e-5, 1.0e-6), 0, None,
           (1e-5, 2e-3, 0.10)),
          # preconditioned: one rank = multigrid over the whole domain, slab ranks = block Jacobi of per-slab multigrids
          ("single_grain_auni", configs.single_grain_auni_test2d, {}, (0.3, 0.02, 1.0e-5, 1.0e-6), 2, 0.32,
-          (2e-3, 5e-2, 0.25)),
+          (2e-3, 1e-1, None)),
          ("two_grains_quadratic", configs.two_grains_quadratic_test3d, {}, (0.08, 0.01, 1.0e-4, 1.0e-7), 2, 0.13,
-          (2e-3, 5e-2, 0.25))]
-for name, builder, ickw, run, cycles, accept, (tol_sf, tol_y, tol_steps) in CASES:
+          (2e-3, 1e-1, None))]
+# usage: mgpu_deck.py [case index ...]   (default: all; ranks sharing ONE GPU are time-sliced, so a deck of a
+# thousand steps with tens of exchanges each takes minutes there and seconds on one GPU per rank)
+import time
+SELECT = [int(a) for a in sys.argv[1:]] or list(range(len(CASES)))
+for name, builder, ickw, run, cycles, accept, (tol_sf, tol_y, tol_steps) in [CASES[i] for i in SELECT]:
+    t_case = time.time()
     cfg = builder()
     assert cfg.n[cfg.ndim - 1] % world == 0
     with tempfile.TemporaryDirectory() as tmp:
@@ -106,14 +114,17 @@ for name, builder, ickw, run, cycles, accept, (tol_sf, tol_y, tol_steps) in CASE
             continue
         err = max(err, (v - cut(yf[k])).abs().max().item())
     sf_f, sf_s = df["solid_fraction"], ds["solid_fraction"]
-    ok = abs(sf_f - sf_s) <= tol_sf and err <= tol_y and abs(ns_ - nf) <= max(3, int(tol_steps * nf))
+    ok = abs(sf_f - sf_s) <= tol_sf and err <= tol_y
+    if tol_steps is not None:
+        ok = ok and abs(ns_ - nf) <= max(3, int(tol_steps * nf))
     if accept is not None:
         ok = ok and abs(sf_s - accept) <= 1e-2
     if not ok:
         bad += 1
     print("rank %d %s (V-cycles %d): one rank %d steps solid fraction %.8f | %d slab ranks %d steps solid fraction %.8f | "
-          "max field difference on this slab %.2e %s" % (rank, name, cycles, nf, sf_f, world, ns_, sf_s, err,
-                                                          "OK" if ok else "MISMATCH"), flush=True)
+          "max field difference on this slab %.2e %s (%.0f s)" % (rank, name, cycles, nf, sf_f, world, ns_, sf_s, err,
+                                                                   "OK" if ok else "MISMATCH", time.time() - t_case),
+          flush=True)
 t = torch.tensor([bad], device=dev if backend == "nccl" else "cpu")
 dist.all_reduce(t)
 if rank == 0:
