@@ -35,7 +35,8 @@ def rotations(cfg, seed=7):
     return parity.random_rotations(cfg, seed)
 
 
-for overlap in (None, "0", "1"):   # None: the library's own choice (in-kernel wait / overlap by message size)
+MODES = (None,) if os.environ.get("MGPU_MODES") == "default" else (None, "0", "1")
+for overlap in MODES:   # None: the library's own choice (in-kernel wait / overlap by message size)
     if overlap is None:
         os.environ.pop("AMPE_B200_HALO_OVERLAP", None)
     else:
