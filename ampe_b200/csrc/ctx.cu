@@ -414,6 +414,7 @@ extern "C" int ampe_rhs_destroy(ampe_rhs_ctx* c)
    }
    for (int i = 0; i < 3; i++)
       if (c->ev_t[i]) cudaEventDestroy(c->ev_t[i]);
+   if (c->grain_label) cudaFree(c->grain_label);
    if (c->own_stream) {
       cudaStreamDestroy(c->own_stream);
       cudaStreamDestroy(c->k_stream);

@@ -44,6 +44,8 @@ struct ampe_rhs_ctx {
    double* red_out = nullptr;
    // opt-in per-kernel timing of one evaluation (ampe_rhs_set_kernel_timing): events on the launching stream
    // before the KKS pre-pass, between it and the fused kernel, and after the fused kernel
+   int* grain_label = nullptr;  // grains.cu scratch: labels, counts, flags, compacted grains
+   int grain_cap = 0;
    bool time_kernels = false;
    cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};
    cudaStream_t own_stream = nullptr, k_stream = nullptr, out_stream = nullptr;

@@ -44,6 +44,11 @@ struct ImplicitOptions {
    long max_steps = 500;                   // CVODE mxstep
    int max_error_test_failures = 7;        // MXNEF
    int max_convergence_failures = 10;      // MXNCF
+   // true: the last step is shortened to land on tend (CVodeSetStopTime).  false: the controller's steps are left
+   // alone and advanceTo returns after the first step that reaches or passes tend -- what AMPE's run loop sees
+   // (QuatIntegrator::Advance takes ONE internal CVODE step per call, CV_ONE_STEP; output intervals are tested against
+   // the time the step landed on, so an output at "t = 0.01" happens a fraction of a step later)
+   bool stop_at_tend = true;
 };
 
 struct ImplicitStats {
@@ -174,7 +179,7 @@ class ImplicitIntegrator
       std::vector<Vec> V;
       for (int j = 0; j <= m; j++) V.push_back(d_ops.clone(y));
       int rc = IMPLICIT_OK;
-      double t = t0, h = std::fmin(h0, tend - t0), h1 = 0.0, h2 = 0.0;  // h1, h2: the last two accepted steps
+      double t = t0, h = d_opt.stop_at_tend ? std::fmin(h0, tend - t0) : h0, h1 = 0.0, h2 = 0.0;  // h1, h2: the last two accepted steps
       if (d_opt.h_max > 0.0) h = std::fmin(h, d_opt.h_max);
       long nacc = 0;  // accepted steps = solutions in the history beyond y
       int nef = 0, ncf = 0;
@@ -266,7 +271,7 @@ class ImplicitIntegrator
          h *= eta;
          if (d_opt.h_max > 0.0) h = std::fmin(h, d_opt.h_max);
          if (d_opt.h_min > 0.0) h = std::fmax(h, d_opt.h_min);
-         if (t < tend) {
+         if (t < tend && d_opt.stop_at_tend) {
             const double left = tend - t;
             if (h >= left * (1.0 - 1.0e-12))
                h = left;  // land on tend

@@ -6,6 +6,9 @@
 //   use_fused = false : the reference's own sequence of Strategy calls, each one a piecewise
 //                       CUDA kernel on SAMRAI-layout PatchData (drop-in check of every Strategy)
 #pragma once
+#include <map>
+#include <vector>
+
 #include "ImplicitIntegrator.h"
 #include "ampe_host.h"
 
@@ -279,6 +282,20 @@ class QuatIntegrator
    void computeSymmetryRotations(const ampe_rhs_fields* y)
    {
       check(ampe_rhs_compute_symmetry_rotations(d_ctx, y, nullptr), "computeSymmetryRotations");
+   }
+   // QuatModel::computeGrainDiagnostics (QuatModel.cc:2690-2705): findAndNumberGrains + computeGrainVolumes; the map
+   // the reference prints as "Volume of grain N = V" (Grains.cc:693-697)
+   std::map<int, double> computeGrainDiagnostics(const ampe_rhs_fields* y, double phase_threshold = 0.85,
+                                                 int max_grains = 65536)
+   {
+      std::vector<int> ids(max_grains);
+      std::vector<double> vol(max_grains);
+      int n = 0;
+      check(ampe_grain_volumes(d_ctx, y, phase_threshold, max_grains, &n, ids.data(), vol.data(), nullptr),
+            "computeGrainDiagnostics");
+      std::map<int, double> out;
+      for (int i = 0; i < n; i++) out[ids[i]] = vol[i];
+      return out;
    }
    void makeQuatFundamental(const ampe_rhs_fields* y)
    {

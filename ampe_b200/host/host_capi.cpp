@@ -104,7 +104,7 @@ int ampe_host_integrate_implicit(void* h, const ampe_rhs_fields* y, double t0, d
    }
 }
 // ImplicitIntegrator::advanceTo on device vectors.  iopt[5]: order, max_krylov_dimension,
-// max_newton_iterations, max_steps, reserved; dopt[6]: rtol, atol, newton_tolerance, linear_tolerance_factor,
+// max_newton_iterations, max_steps, 1 = do not shorten the last step (stop_at_tend off); dopt[6]: rtol, atol, newton_tolerance, linear_tolerance_factor,
 // h_min, h_max; stats_out[16]: the 8 of ampe_host_integrate_implicit, then error_test_failures,
 // convergence_failures, last_step, smallest_step, largest_step, last_error_estimate, t_reached, 0.
 // Returns 0 or an IMPLICIT_E* code (-20 .. -24); -1 with ampe_host_last_error() for everything else.
@@ -116,6 +116,7 @@ int ampe_host_integrate_adaptive(void* h, const ampe_rhs_fields* y, double t0, d
       if (iopt) {
          o.order = iopt[0], o.max_krylov_dimension = iopt[1], o.max_newton_iterations = iopt[2];
          if (iopt[3] > 0) o.max_steps = iopt[3];
+         o.stop_at_tend = iopt[4] == 0;  // iopt[4] = 1: return after the first step at or beyond tend (CV_ONE_STEP loop)
       }
       if (dopt) {
          o.rtol = dopt[0], o.atol = dopt[1], o.newton_tolerance = dopt[2], o.linear_tolerance_factor = dopt[3];

@@ -109,6 +109,10 @@ def load():
     L.ampe_energy_eval.argtypes = [vp, pf, pd, vp]
     L.ampe_scalar_diagnostics.restype = ci
     L.ampe_scalar_diagnostics.argtypes = [vp, pf, pd, vp]
+    L.ampe_grain_volumes.restype = ci
+    L.ampe_grain_volumes.argtypes = [vp, pf, C.c_double, ci, vp, vp, vp, vp]
+    L.ampe_grain_numbers.restype = ci
+    L.ampe_grain_numbers.argtypes = [vp, vp]
     L.ampe_apply_projection.restype = ci
     L.ampe_apply_projection.argtypes = [vp, pf, pf, pf, vp]
     L.ampe_rhs_compute_symmetry_rotations.restype = ci

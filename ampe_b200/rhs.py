@@ -175,6 +175,23 @@ class QuatIntegratorRHS:
         check(self.L.ampe_scalar_diagnostics(self.h, C.byref(fy), out, self._stream()), "printScalarDiagnostics")
         return {k: out[i] for i, k in enumerate(self.DIAGNOSTICS)}
 
+    def computeGrainDiagnostics(self, y, phase_threshold=0.85, max_grains=4096, numbers=False):
+        """QuatModel::computeGrainDiagnostics (QuatModel.cc:2690-2705): Grains::findAndNumberGrains +
+        computeGrainVolumes -- {grain number: volume}, the "Volume of grain N = V" lines of the reference's output;
+        numbers=True also returns the per-cell grain numbers (int32 device tensor, -1 outside grains)"""
+        ids = (C.c_int * max_grains)()
+        vols = (C.c_double * max_grains)()
+        n = C.c_int(0)
+        fy = y.fields()
+        check(self.L.ampe_grain_volumes(self.h, C.byref(fy), float(phase_threshold), int(max_grains), C.byref(n), ids,
+                                        vols, self._stream()), "computeGrainDiagnostics")
+        out = {int(ids[i]): float(vols[i]) for i in range(n.value)}
+        if not numbers:
+            return out
+        num = torch.empty(y["phase"].shape, dtype=torch.int32, device=y["phase"].device)
+        check(self.L.ampe_grain_numbers(self.h, C.c_void_p(num.data_ptr())), "ampe_grain_numbers")
+        return out, num
+
     def applyProjection(self, time, y, corr, epsProj, err):
         """QuatIntegrator::applyProjection (QuatIntegrator.cc:3911-3962): corr <- 0 except the
         quaternion part, where y + corr is normalised; err loses its component along q.  Returns 0."""

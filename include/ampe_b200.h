@@ -295,6 +295,18 @@ int ampe_integrate_fixed(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, const ampe
 /* the same loop on a slab rank: every evaluation exchanges the ghost planes through `h` (collective over the ranks) */
 int ampe_integrate_fixed_slab(ampe_rhs_ctx* ctx, ampe_halo* h, const ampe_rhs_fields* y, const ampe_rhs_fields* work1,
                               const ampe_rhs_fields* work2, double t0, double dt, int nsteps, int scheme, void* stream);
+/* ---- grain diagnostics: QuatModel::computeGrainDiagnostics (QuatModel.cc:2690-2705) ->
+ * Grains::findAndNumberGrains (Grains.cc:263-520) + Grains::computeGrainVolumes (Grains.cc:647-697), the
+ * "Volume of grain N = V" lines the regression decks check.  Cells with phase >= phase_threshold
+ * (GrainDiagnostics{phase_threshold}, default 0.85) that touch through faces form a grain (periodic directions
+ * wrap, zero-slope boundaries do not connect); a grain's number is the lowest global cell index it contains
+ * (i + n0 (j + n1 k)), its volume the sum of its cells' control volumes.  Host outputs, ascending grain number
+ * (the reference's std::map order); more than max_grains grains: AMPE_EINVAL with the count in *ngrains.
+ * ampe_grain_numbers copies the per-cell grain numbers (-1 outside grains; d_grain_number_id) of the last call
+ * into a device array of ncell ints.  Single rank.                                             */
+int ampe_grain_volumes(ampe_rhs_ctx* ctx, const ampe_rhs_fields* y, double phase_threshold, int max_grains,
+                       int* ngrains, int* grain_ids, double* volumes, void* stream);
+int ampe_grain_numbers(ampe_rhs_ctx* ctx, int* grain_number);
 /* ---- QuatModel::evaluateEnergy (QuatModel.cc:4888-4976) ->
  * quatenergy / bulkenergy ({2d,3d}/quatenergy.m4).  out[8] = total, phase interface,
  * orientational, q interface, double well, bulk free energy, 0, 0 (host array).  For the

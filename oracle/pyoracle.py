@@ -209,6 +209,26 @@ class Oracle:
                    "integral_phase_concentration", "cex", "min_temperature", "max_temperature",
                    "average_temperature", "thermal_energy")
 
+    def grain_volumes(self, y, phase_threshold=0.85, max_grains=4096, numbers=False):
+        """Grains::findAndNumberGrains + computeGrainVolumes: {grain number: volume} (and the per-cell numbers)"""
+        cfg = self.cfg
+        n = np.array([cfg.n[0], cfg.n[1], cfg.n[2]], dtype=np.int32)
+        dx = np.array([cfg.dx[0], cfg.dx[1], cfg.dx[2]], dtype=np.float64)
+        zs = np.array([cfg.zero_slope[0], cfg.zero_slope[1], cfg.zero_slope[2]], dtype=np.int32)
+        phase = np.ascontiguousarray(y["phase"], dtype=np.float64)
+        ids = np.zeros(max_grains, dtype=np.int32)
+        vols = np.zeros(max_grains)
+        ng = C.c_int(0)
+        num = np.zeros(phase.size, dtype=np.int32) if numbers else None
+        fn = self.L.oracle_grain_volumes
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_double, C.c_int] + [C.c_void_p] * 4
+        rc = fn(int(cfg.ndim), _ptr(n), _ptr(dx), _ptr(zs), _ptr(phase), float(phase_threshold), int(max_grains),
+                C.addressof(ng), _ptr(ids), _ptr(vols), None if num is None else _ptr(num))
+        assert rc == 0, "more than max_grains grains (%d)" % ng.value
+        out = {int(ids[i]): float(vols[i]) for i in range(ng.value)}
+        return (out, num.reshape(phase.shape)) if numbers else out
+
     def scalar_diagnostics(self, y):
         """QuatModel::printScalarDiagnostics: dict of the DIAGNOSTICS"""
         out = np.zeros(12)

@@ -108,7 +108,11 @@ def test_single_grain_auni_deck_unpreconditioned_start_agrees(tmp_path):
 
 
 # ---- the same decks on the device ----------------------------------------------------------------
-def run_device_deck(cfg, y_np, end_time, interval, atol, h0, precond_cycles=0, max_total_steps=40000):
+def run_device_deck(cfg, y_np, end_time, interval, atol, h0, precond_cycles=0, max_total_steps=40000, grains=None,
+                    run_loop_outputs=False):
+    """run_loop_outputs: outputs the way AMPE's run loop produces them -- one CVODE step per Advance, the output
+    intervals tested against the time the step landed on, so the line for "t = 0.01" is printed a fraction of a step
+    later (stop_at_tend off); otherwise every output lands exactly on its time"""
     import torch
     from ampe_b200 import rhs
     y = rhs.SolutionVector({k: (None if v is None else torch.as_tensor(np.ascontiguousarray(v)).cuda())
@@ -120,13 +124,18 @@ def run_device_deck(cfg, y_np, end_time, interval, atol, h0, precond_cycles=0, m
     if cfg.conc_rhs_form in (2, 3):
         c0 = y["conc"].reshape(-1).clone()
         h.resetRefPhaseConcentrations(c0, c0.clone())
-    t, step, steps, hist = 0.0, h0, 0, []
+    t, step, steps, hist, next_out = 0.0, h0, 0, [], interval
     while t < end_time:
-        rc, st = h.integrateAdaptive(y, t + interval, step, t0=t, rtol=1e-2 * atol, atol=atol, max_steps=20000)
+        rc, st = h.integrateAdaptive(y, next_out, step, t0=t, rtol=1e-2 * atol, atol=atol, max_steps=20000,
+                                     stop_at_tend=not run_loop_outputs)
         assert rc == 0, (rc, st)
         t, step, steps = st["t_reached"], st["last_step"], steps + int(st["steps"])
+        while next_out <= t * (1.0 + 1e-14):
+            next_out += interval
         assert steps <= max_total_steps
         hist.append((t, diag.printScalarDiagnostics(y)))
+        if grains is not None:   # GrainDiagnostics{interval = <the same interval>, phase_threshold}
+            grains.append((t, diag.computeGrainDiagnostics(y, 0.85)))
     h.close()
     diag.close()
     return hist, steps
@@ -162,7 +171,19 @@ def test_single_grain_auni_deck_gpu(tmp_path):
 def test_two_grains_quadratic_deck_gpu(tmp_path):
     cfg = configs.two_grains_quadratic_test3d()
     y = initial_conditions("two_grains_quadratic", cfg, tmp_path)
-    hist, steps = run_device_deck(cfg, y, 0.08, 0.01, 1.0e-4, 1.0e-7, precond_cycles=2)
+    grains = []
+    hist, steps = run_device_deck(cfg, y, 0.08, 0.01, 1.0e-4, 1.0e-7, precond_cycles=2, grains=grains,
+                                  run_loop_outputs=True)
     t, d = hist[-1]
     assert t >= 0.08
     assert abs(d["solid_fraction"] - 0.13) <= 1.0e-2, d["solid_fraction"]
+    # the deck's grain-volume lines (GrainDiagnostics every 0.01 time units, phase_threshold 0.85): the largest and the
+    # smallest "Volume of grain" printed over the run, test3d.py:56-72
+    volumes = [v for _, g in grains for v in g.values()]
+    print("grain volumes over the run:", [(round(t, 5), {k: round(v, 5) for k, v in g.items()}) for t, g in grains])
+    assert abs(max(volumes) - 2.0) <= 0.01, max(volumes)
+    # The smallest volume is the second grain at the FIRST output.  It grows by 5.4e-3 per 1e-3 of time there, so the
+    # reference's +- 0.001 is +- 2e-4 in the time the step after t = 0.01 lands on: exactly at t = 0.0100 the volume is
+    # 0.1773, the run-loop emulation prints at t = 0.01038 and gets 0.17925 (the reference: 0.179)
+    assert min(volumes) == min(grains[0][1].values())
+    assert abs(min(volumes) - 0.179) <= 0.001, (grains[0][0], min(volumes))
