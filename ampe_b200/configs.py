@@ -275,6 +275,38 @@ def two_grains_quadratic_test3d():
     return c
 
 
+def four_corners_test2d():
+    """tests/FourCorners/2d.input: four quarter-disc grains with different orientations (qlen 4 in 2D) growing from the
+    corners of a 64 x 64 box (0.128 x 0.128 um) with slope-0 boundaries; phase + evolving quaternions
+    (H_parameter 0.884e-3, epsilon_orient 0.0447), FreeEnergyModel "linear" at a constant 975 K (melting point 1000 K,
+    latent heat 2e4 J/mol at 1e-5 m^3/mol), Interface{sigma 0.44, delta 2e-3} -> epsilon_phi = sqrt(6 sigma delta),
+    well scale 3 sigma / delta / 16 (QuatModelParameters.cc:842-845)."""
+    import math
+    c = _base(2, (64, 64), (0.0, 0.0), (0.128, 0.128))
+    c.qlen = 4
+    c.with_phase = 1
+    c.evolve_quat = 1
+    c.phase_flux_type = _abi.FLUX_SIMPLE
+    c.free_energy = _abi.FE_DELTAT
+    c.H_parameter = 0.884e-3
+    c.epsilon_q = 0.0447
+    c.quat_mobility = 1.0
+    c.phi_mobility = 1.0
+    sigma, delta = 0.44, 2.0e-3
+    c.epsilon_phase = math.sqrt(6.0 * sigma * delta)
+    c.phi_well_scale = (3.0 * sigma / delta) / 16.0
+    c.T_uniform = 975.0
+    c.meltingT = 1000.0
+    vm = 1.0e-5
+    c.vm_liquid = c.vm_solid = vm
+    c.latent_heat = 2.0e4 * (1.0e-6 / vm)     # J/mol -> pJ/um^3 (QuatModelParameters.cc:616)
+    c.energy_interp = _ch("p")
+    c.avg_func = _ch("a")
+    c.conc_avg_func = _ch("a")
+    c.zero_slope[0] = c.zero_slope[1] = 1
+    return c
+
+
 BUILDERS = {
     "pfhub1a": pfhub1a,
     "dendrite2d": dendrite2d,

@@ -187,3 +187,24 @@ def test_two_grains_quadratic_deck_gpu(tmp_path):
     # 0.1773, the run-loop emulation prints at t = 0.01038 and gets 0.17925 (the reference: 0.179)
     assert min(volumes) == min(grains[0][1].values())
     assert abs(min(volumes) - 0.179) <= 0.001, (grains[0][0], min(volumes))
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_four_corners_deck_gpu(tmp_path):
+    """tests/FourCorners/test2d.py: four grains of different orientation (qlen 4 in 2D, evolving quaternions, "linear"
+    free energy at constant undercooling, slope-0 boundaries) grow until they meet: solid fraction 0.93 +- 0.01 after
+    t = 0.3 and every "Volume of grain" printed then is 0.0028 or 0.0087 (+- 1e-4).  Initial condition: the arrays the
+    reference's utils/make4corners.py writes."""
+    cfg = configs.four_corners_test2d()
+    y = initial_conditions("four_corners", cfg, tmp_path)
+    grains = []
+    hist, steps = run_device_deck(cfg, y, 0.3, 0.05, 2.0e-5, 1.0e-7, precond_cycles=2, grains=grains,
+                                  run_loop_outputs=True)
+    t, d = hist[-1]
+    print("four corners:", steps, "steps, t =", t, "solid fraction", d["solid_fraction"], "grains",
+          [(round(tt, 4), {k: round(v, 6) for k, v in g.items()}) for tt, g in grains])
+    assert t >= 0.3
+    assert abs(d["solid_fraction"] - 0.93) <= 1.0e-2, d["solid_fraction"]
+    for v in grains[-1][1].values():
+        assert abs(v - 0.0028) <= 1.0e-4 or abs(v - 0.0087) <= 1.0e-4, grains[-1]

@@ -23,6 +23,12 @@ DECKS = {
                           "--concentration-in", "0.096"],
     "two_grains_quadratic": ["--nx", "64", "--ny", "64", "--nz", "48", "-r", "8", "--concentration-in", "0.1",
                              "--concentration-out", "0.06", "--ngrains", "2", "-q", "4"],
+    # tests/FourCorners/test2d.py:11-13 (utils/make4corners.py), tests/SolidifyQuaternions/test2d.py:11-14
+    # (utils/make_initial_grains_on_boundary.py, random.seed(112345) inside)
+    "four_corners": ("make4corners.py", ["-x", "64", "-y", "64", "-z", "1"]),
+    "solidify_quaternions": ("make_initial_grains_on_boundary.py",
+                             ["-x", "64", "-y", "32", "-z", "1", "--solid-fraction", "0.25", "--smooth", "0", "--qlen", "4",
+                              "--ngrains", "2"]),
 }
 
 
@@ -52,15 +58,15 @@ class _Dataset:
         pass
 
 
-def run(argv):
+def run(argv, script="make_nuclei.py"):
     fake = types.ModuleType("netCDF4")
     fake.Dataset = _Dataset
     sys.modules["netCDF4"] = fake
     sys.path.insert(0, REF_UTILS)
     old = sys.argv
-    sys.argv = ["make_nuclei.py"] + argv + ["unused.nc"]
+    sys.argv = [script] + argv + ["unused.nc"]
     try:
-        runpy.run_path(os.path.join(REF_UTILS, "make_nuclei.py"), run_name="__main__")
+        runpy.run_path(os.path.join(REF_UTILS, script), run_name="__main__")
     finally:
         sys.argv = old
         sys.path.remove(REF_UTILS)
@@ -69,8 +75,11 @@ def run(argv):
 
 if __name__ == "__main__":
     out = os.path.join(ROOT, "tests", "golden")
+    only = sys.argv[1:]
     for name, argv in DECKS.items():
-        fields = run(argv)
+        if only and name not in only:
+            continue
+        fields = run(*((argv[1], argv[0]) if isinstance(argv, tuple) else (argv,)))
         path = os.path.join(out, "ic_%s.npz" % name)
         np.savez_compressed(path, **fields)
         print(name, {k: (v.shape, str(v.dtype), float(v.min()), float(v.max())) for k, v in fields.items()},
