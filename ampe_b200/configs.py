@@ -275,6 +275,21 @@ def two_grains_quadratic_test3d():
     return c
 
 
+def kks_composition_test2d():
+    """tests/KKScomposition/2d.input: the SingleGrainGrowthAuNi set-up with the KKS form of the composition flux
+    (rhs_form "kks": D(phi) grad c + ... with constant D_solid 0.125, D_liquid 1224.23 um^2/s) and the CALPHAD free
+    energy; Interface{sigma 0.372678, delta 0.035}; temperature ramp 1450 K - 200 K/s t to 1220 K."""
+    import math
+    c = single_grain_auni_test2d()
+    c.conc_rhs_form = _abi.CONC_KKS
+    c.D_solid, c.D_liquid = 0.125, 1224.23
+    c.Q0_solid = c.Q0_liquid = 0.0
+    sigma, delta = 0.372678, 0.035
+    c.epsilon_phase = math.sqrt(6.0 * sigma * delta)
+    c.phi_well_scale = (3.0 * sigma / delta) / 16.0
+    return c
+
+
 def four_corners_test2d():
     """tests/FourCorners/2d.input: four quarter-disc grains with different orientations (qlen 4 in 2D) growing from the
     corners of a 64 x 64 box (0.128 x 0.128 um) with slope-0 boundaries; phase + evolving quaternions

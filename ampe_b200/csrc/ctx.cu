@@ -145,8 +145,8 @@ int ampe_derive_params_at(const ampe_rhs_config& c, double T_now, Params& p)
       return set_err(AMPE_EINVAL, "isotropic stencil is incomplete in 3D (reference stops)");
    if (p.conc_form == AMPE_CONC_EBS && c.free_energy != AMPE_FE_CALPHAD)
       return set_err(AMPE_EINVAL, "EBS composition RHS needs the CALPHAD free energy");
-   if (p.conc_form == AMPE_CONC_KKS && c.free_energy != AMPE_FE_QUADRATIC)
-      return set_err(AMPE_EINVAL, "KKS composition RHS needs the quadratic free energy");
+   if (p.conc_form == AMPE_CONC_KKS && c.free_energy != AMPE_FE_QUADRATIC && c.free_energy != AMPE_FE_CALPHAD)
+      return set_err(AMPE_EINVAL, "KKS composition RHS needs the quadratic or the CALPHAD free energy");
    if ((p.conc_form == AMPE_CONC_EBS || p.conc_form == AMPE_CONC_KKS) && p.with_T)
       return set_err(AMPE_EINVAL, "KKS/EBS with an evolved temperature field is not supported");
    if (p.conc_form == AMPE_CONC_CAHN_HILLIARD && (c.with_phase || c.evolve_quat))

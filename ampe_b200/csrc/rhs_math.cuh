@@ -619,7 +619,8 @@ struct Rhs3 {
             }
             const double m = p.deltaT_alpha * (p.meltingT - wtemp);
             rhs = rhs + m * deriv_interp_func(phi, AMPE_SEL(energy_interp));
-         } else if (CONC == AMPE_CONC_EBS && free_energy == AMPE_FE_CALPHAD) {
+         } else if ((CONC == AMPE_CONC_EBS || CONC == AMPE_CONC_KKS) && free_energy == AMPE_FE_CALPHAD) {
+            // (either composition flux form: rhs_form "ebs" examples/AuNi_*, "kks" tests/KKScomposition)
             // CALPHADFreeEnergyStrategyBinary.cc:321-323, 638-663: (f_l-f_a) - mu (c_l-c_a) comes
             // from the KKS kernel, which has the logarithms of the converged c_l, c_a at hand
             const double hp = deriv_interp_func(phi, AMPE_SEL(energy_interp));

@@ -76,7 +76,8 @@ def test_ragged_sizes(name, kw):
 
 @pytest.mark.parametrize("variant", ["no_symmetry", "modulus_from_sides", "floor_tanh", "floor_sqrt",
                                      "harmonic_avg", "lag_off", "isotropic_flux", "frozen_quat",
-                                     "anisotropic_3d_kks", "anisotropic_3d_ebs", "anisotropic_3d_clamped"])
+                                     "anisotropic_3d_kks", "anisotropic_3d_ebs", "anisotropic_3d_clamped",
+                                     "kks_flux_calphad", "kks_flux_calphad_3d"])
 def test_model_switches(variant):
     """the runtime switches of QuatModelParameters that the hot path honours"""
     name = "auni2d"
@@ -86,8 +87,17 @@ def test_model_switches(variant):
         name = "gg3d_hbsm"
     if variant == "anisotropic_3d_ebs":
         name = "auni3d"
+    if variant == "kks_flux_calphad_3d":
+        name = "auni3d"
     cfg, st = parity.make_case(name)
     rot = None
+    if variant.startswith("kks_flux_calphad"):
+        # rhs_form "kks" with the CALPHAD free energy (tests/KKScomposition): Arrhenius D_solid / D_liquid instead of the
+        # CALPHAD mobilities, the KKS kernel's Newton and driving force as for "ebs"
+        cfg.symmetry_aware = 0
+        cfg.conc_rhs_form = 2
+        cfg.D_solid, cfg.D_liquid = 0.125, 1224.23
+        cfg.Q0_solid, cfg.Q0_liquid = 1.0e4, 2.0e4
     if variant.startswith("anisotropic_3d"):
         # 3D anisotropic interface energy (3d/quatrhs.m4:149-349) inside the fused marching kernel
         cfg.symmetry_aware = 0

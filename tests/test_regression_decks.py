@@ -94,6 +94,21 @@ def test_single_grain_auni_deck_cpu(tmp_path):
     assert steps < 1500
 
 
+def test_kks_composition_deck_cpu(tmp_path):
+    """tests/KKScomposition/test2d.py: the same initial condition with the KKS form of the composition flux (constant
+    D_solid / D_liquid) and the CALPHAD free energy: integral of the composition within 1e-4 of its first value at
+    every output, solid fraction 0.32 +- 0.01 after t = 0.3"""
+    cfg = configs.kks_composition_test2d()
+    y = initial_conditions("single_grain_auni", cfg, tmp_path)
+    hist, steps = run_oracle_deck(cfg, y, 0.3, 0.025, 1.0e-4, 1.0e-6, precond_cycles=2)
+    c0 = hist[0][1]["integral_concentration"]
+    for t, d in hist:
+        assert abs(d["integral_concentration"] - c0) <= 1.0e-4
+    t, d = hist[-1]
+    assert t >= 0.3
+    assert abs(d["solid_fraction"] - 0.32) <= 1.0e-2, d["solid_fraction"]
+
+
 def test_single_grain_auni_deck_unpreconditioned_start_agrees(tmp_path):
     """the first 0.02 time units without the preconditioner (678 small steps) land on the same solid fraction as the
     preconditioned run (about 100 steps): the preconditioner changes the work, not the answer"""
@@ -208,3 +223,18 @@ def test_four_corners_deck_gpu(tmp_path):
     assert abs(d["solid_fraction"] - 0.93) <= 1.0e-2, d["solid_fraction"]
     for v in grains[-1][1].values():
         assert abs(v - 0.0028) <= 1.0e-4 or abs(v - 0.0087) <= 1.0e-4, grains[-1]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_kks_composition_deck_gpu(tmp_path):
+    cfg = configs.kks_composition_test2d()
+    y = initial_conditions("single_grain_auni", cfg, tmp_path)
+    hist, steps = run_device_deck(cfg, y, 0.3, 0.025, 1.0e-4, 1.0e-6, precond_cycles=2)
+    c0 = hist[0][1]["integral_concentration"]
+    for t, d in hist:
+        assert abs(d["integral_concentration"] - c0) <= 1.0e-4
+    t, d = hist[-1]
+    print("KKScomposition:", steps, "steps, solid fraction", d["solid_fraction"])
+    assert t >= 0.3
+    assert abs(d["solid_fraction"] - 0.32) <= 1.0e-2, d["solid_fraction"]
