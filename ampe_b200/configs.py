@@ -322,6 +322,42 @@ def four_corners_test2d():
     return c
 
 
+def _to3d(c, n, hi):
+    """the 3D version of a 2D deck: same model block, one more direction with the same kind of boundary"""
+    c.ndim = 3
+    for d in range(3):
+        c.n[d] = n[d]
+        c.dx[d] = hi[d] / n[d]
+    c.zero_slope[2] = c.zero_slope[1]
+    return c
+
+
+def dendrite_test3d():
+    """tests/Dendrite/3d.input: the 2D deck's model on 60^3 cells (40^3 um), qlen 4 (init_q = 1, 0, 0, 0; H_parameter
+    unset: the orientation only feeds the 3D anisotropy, 3d/quatrhs.m4:149-349), slope-0 on all six sides."""
+    c = _to3d(dendrite_test2d(), (60, 60, 60), (40.0, 40.0, 40.0))
+    c.qlen = 4
+    return c
+
+
+def single_grain_auni_test3d():
+    """tests/SingleGrainGrowthAuNi/3d.input: 32^3 cells on 0.9^3 um, otherwise the 2D deck."""
+    return _to3d(single_grain_auni_test2d(), (32, 32, 32), (0.9, 0.9, 0.9))
+
+
+def kks_composition_test3d():
+    """tests/KKScomposition/3d.input: 32^3 cells on 0.9^3 um; unlike its 2D sibling it runs rhs_form "ebs" (with the
+    Interface{sigma, delta} block of the 2D deck)."""
+    c = _to3d(kks_composition_test2d(), (32, 32, 32), (0.9, 0.9, 0.9))
+    c.conc_rhs_form = _abi.CONC_EBS
+    return c
+
+
+def four_corners_test3d():
+    """tests/FourCorners/3d.input: the 2D deck four cells thick (64 x 64 x 4 on 0.128 x 0.128 x 0.008 um)."""
+    return _to3d(four_corners_test2d(), (64, 64, 4), (0.128, 0.128, 0.008))
+
+
 BUILDERS = {
     "pfhub1a": pfhub1a,
     "dendrite2d": dendrite2d,

@@ -238,3 +238,70 @@ def test_kks_composition_deck_gpu(tmp_path):
     print("KKScomposition:", steps, "steps, solid fraction", d["solid_fraction"])
     assert t >= 0.3
     assert abs(d["solid_fraction"] - 0.32) <= 1.0e-2, d["solid_fraction"]
+
+
+# ---- the 3D versions of the decks (device only: the marching kernel against reference-held numbers) ----------------
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_single_grain_auni_deck_3d_gpu(tmp_path):
+    """tests/SingleGrainGrowthAuNi/test3d.py: CALPHAD KKS Newton + EBS composition flux in 3D (the model of the headline
+    workload, on the marching kernel): composition integral within 1e-4 of its first value, solid fraction 0.33 +- 0.01"""
+    cfg = configs.single_grain_auni_test3d()
+    y = initial_conditions("single_grain_auni3d", cfg, tmp_path)
+    hist, steps = run_device_deck(cfg, y, 0.3, 0.03, 1.0e-5, 1.0e-6, precond_cycles=2)
+    c0 = hist[0][1]["integral_concentration"]
+    for t, d in hist:
+        assert abs(d["integral_concentration"] - c0) <= 1.0e-4
+    t, d = hist[-1]
+    print("SingleGrainGrowthAuNi 3D:", steps, "steps, solid fraction", d["solid_fraction"])
+    assert t >= 0.3
+    assert abs(d["solid_fraction"] - 0.33) <= 1.0e-2, d["solid_fraction"]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_kks_composition_deck_3d_gpu(tmp_path):
+    """tests/KKScomposition/test3d.py (rhs_form "ebs" in 3D with the Interface{} parameters): 0.33 +- 0.01"""
+    cfg = configs.kks_composition_test3d()
+    y = initial_conditions("single_grain_auni3d", cfg, tmp_path)
+    hist, steps = run_device_deck(cfg, y, 0.3, 0.03, 1.0e-4, 1.0e-6, precond_cycles=2)
+    c0 = hist[0][1]["integral_concentration"]
+    for t, d in hist:
+        assert abs(d["integral_concentration"] - c0) <= 1.0e-4
+    t, d = hist[-1]
+    print("KKScomposition 3D:", steps, "steps, solid fraction", d["solid_fraction"])
+    assert t >= 0.3
+    assert abs(d["solid_fraction"] - 0.33) <= 1.0e-2, d["solid_fraction"]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_dendrite_deck_3d_gpu(tmp_path):
+    """tests/Dendrite/test3d.py: the 3D anisotropic interface energy (3d/quatrhs.m4:149-349, inside the marching kernel)
+    with the heat equation: solid fraction 0.15 +- 0.01 after t = 40"""
+    cfg = configs.dendrite_test3d()
+    y = initial_conditions("dendrite3d", cfg, tmp_path, init_t=0.7, init_q=(1.0, 0.0, 0.0, 0.0))
+    hist, steps = run_device_deck(cfg, y, 40.0, 5.0, 1.0e-4, 1.0e-3)
+    t, d = hist[-1]
+    print("Dendrite 3D:", steps, "steps, solid fraction", d["solid_fraction"])
+    assert t >= 40.0
+    assert abs(d["solid_fraction"] - 0.15) <= 1.0e-2, d["solid_fraction"]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_four_corners_deck_3d_gpu(tmp_path):
+    """tests/FourCorners/test3d.py (64 x 64 x 4): solid fraction 0.93 +- 0.01 after t = 0.19 and every grain volume then
+    within 1e-7 of 6.65e-5 or 2.41e-5 (12 cells of 8300; measured 6.6432e-5 and 2.416e-5)"""
+    cfg = configs.four_corners_test3d()
+    y = initial_conditions("four_corners3d", cfg, tmp_path)
+    grains = []
+    hist, steps = run_device_deck(cfg, y, 0.19, 0.01, 2.0e-5, 1.0e-7, precond_cycles=2, grains=grains,
+                                  run_loop_outputs=True)
+    t, d = hist[-1]
+    print("FourCorners 3D:", steps, "steps, t =", t, "solid fraction", d["solid_fraction"], "grains",
+          {k: v for k, v in grains[-1][1].items()})
+    assert t >= 0.19
+    assert abs(d["solid_fraction"] - 0.93) <= 1.0e-2, d["solid_fraction"]
+    for v in grains[-1][1].values():
+        assert abs(v - 6.65e-5) <= 1.0e-7 or abs(v - 2.41e-5) <= 1.0e-7, grains[-1]
