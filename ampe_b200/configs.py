@@ -358,6 +358,14 @@ def four_corners_test3d():
     return _to3d(four_corners_test2d(), (64, 64, 4), (0.128, 0.128, 0.008))
 
 
+def two_grains_quadratic_test2d():
+    """tests/TwoGrainsQuadratic/2d.input: the 3D deck's model block on 64 x 64 cells (3.2 x 3.2 um), periodic."""
+    c = two_grains_quadratic_test3d()
+    c.ndim = 2
+    c.n[2], c.dx[2] = 1, 1.0
+    return c
+
+
 BUILDERS = {
     "pfhub1a": pfhub1a,
     "dendrite2d": dendrite2d,

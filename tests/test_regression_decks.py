@@ -305,3 +305,23 @@ def test_four_corners_deck_3d_gpu(tmp_path):
     assert abs(d["solid_fraction"] - 0.93) <= 1.0e-2, d["solid_fraction"]
     for v in grains[-1][1].values():
         assert abs(v - 6.65e-5) <= 1.0e-7 or abs(v - 2.41e-5) <= 1.0e-7, grains[-1]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_two_grains_quadratic_deck_2d_gpu(tmp_path):
+    """tests/TwoGrainsQuadratic/test2d.py: solid fraction 0.27 +- 0.01 after t = 0.25; over the grain outputs (every 0.05)
+    the largest volume 1.9175 +- 0.01 and the smallest 0.3025 +- 0.01"""
+    cfg = configs.two_grains_quadratic_test2d()
+    y = initial_conditions("two_grains_quadratic2d", cfg, tmp_path)
+    grains = []
+    hist, steps = run_device_deck(cfg, y, 0.25, 0.05, 1.0e-4, 1.0e-7, precond_cycles=2, grains=grains,
+                                  run_loop_outputs=True)
+    t, d = hist[-1]
+    volumes = [v for _, g in grains for v in g.values()]
+    print("TwoGrainsQuadratic 2D:", steps, "steps, solid fraction", d["solid_fraction"], "grain volumes",
+          [(round(tt, 4), {k: round(v, 4) for k, v in g.items()}) for tt, g in grains])
+    assert t >= 0.25
+    assert abs(d["solid_fraction"] - 0.27) <= 1.0e-2, d["solid_fraction"]
+    assert abs(max(volumes) - 1.9175) <= 0.01, max(volumes)
+    assert abs(min(volumes) - 0.3025) <= 0.01, min(volumes)
