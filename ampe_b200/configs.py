@@ -322,6 +322,18 @@ def four_corners_test2d():
     return c
 
 
+def solidify_quaternions_test2d():
+    """tests/SolidifyQuaternions/2d.input: the FourCorners model with orient_interp_func_type1 = type2 = "q" on 64 x 32
+    cells (0.128 x 0.064 um), periodic in x, slope-0 in y; two grains on the lower boundary grow into a liquid whose
+    orientation is random cell by cell."""
+    c = four_corners_test2d()
+    c.n[1] = 32
+    c.orient_interp1 = _ch("q")
+    c.orient_interp2 = _ch("q")
+    c.zero_slope[0] = 0
+    return c
+
+
 def _to3d(c, n, hi):
     """the 3D version of a 2D deck: same model block, one more direction with the same kind of boundary"""
     c.ndim = 3

@@ -325,3 +325,22 @@ def test_two_grains_quadratic_deck_2d_gpu(tmp_path):
     assert abs(d["solid_fraction"] - 0.27) <= 1.0e-2, d["solid_fraction"]
     assert abs(max(volumes) - 1.9175) <= 0.01, max(volumes)
     assert abs(min(volumes) - 0.3025) <= 0.01, min(volumes)
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+def test_solidify_quaternions_deck_gpu(tmp_path):
+    """tests/SolidifyQuaternions/test2d.py: two grains on the lower boundary solidify a liquid of random orientation
+    (periodic in x, slope-0 in y): solid fraction 0.42 +- 0.01 after t = 1 and exactly two grains then.  Initial
+    condition: utils/make_initial_grains_on_boundary.py (random.seed(112345) inside)."""
+    cfg = configs.solidify_quaternions_test2d()
+    y = initial_conditions("solidify_quaternions", cfg, tmp_path)
+    grains = []
+    hist, steps = run_device_deck(cfg, y, 1.0, 0.1, 2.0e-5, 1.0e-7, precond_cycles=2, grains=grains,
+                                  run_loop_outputs=True)
+    t, d = hist[-1]
+    print("SolidifyQuaternions:", steps, "steps, t =", t, "solid fraction", d["solid_fraction"], "grains",
+          {k: round(v, 6) for k, v in grains[-1][1].items()})
+    assert t >= 1.0
+    assert abs(d["solid_fraction"] - 0.42) <= 1.0e-2, d["solid_fraction"]
+    assert len(grains[-1][1]) == 2, grains[-1]

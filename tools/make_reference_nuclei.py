@@ -74,9 +74,16 @@ def run(argv, script="make_nuclei.py"):
     sys.path.insert(0, REF_UTILS)
     old = sys.argv
     sys.argv = [script] + argv + ["unused.nc"]
+    # make_initial_grains_on_boundary.py calls random.randint with integral FLOAT bounds, which Python <= 3.9 accepted
+    # (deprecated in 3.10, a TypeError since 3.12): give it the interpreter it was written for -- same Mersenne Twister,
+    # same draws
+    import random
+    _randint = random.randint
+    random.randint = lambda a, b: _randint(int(a), int(b))
     try:
         runpy.run_path(os.path.join(REF_UTILS, script), run_name="__main__")
     finally:
+        random.randint = _randint
         sys.argv = old
         sys.path.remove(REF_UTILS)
     return dict(_Dataset.captured)
