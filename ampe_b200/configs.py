@@ -378,6 +378,13 @@ def two_grains_quadratic_test2d():
     return c
 
 
+def solidify_quaternions_test3d():
+    """tests/SolidifyQuaternions/3d.input: 48 x 24 x 8 cells (0.096 x 0.048 x 0.016 um), periodic in x and z, slope-0 in y."""
+    c = _to3d(solidify_quaternions_test2d(), (48, 24, 8), (0.096, 0.048, 0.016))
+    c.zero_slope[0], c.zero_slope[1], c.zero_slope[2] = 0, 1, 0
+    return c
+
+
 BUILDERS = {
     "pfhub1a": pfhub1a,
     "dendrite2d": dendrite2d,

@@ -25,6 +25,11 @@ import pytest
 from ampe_b200 import configs, host_rhs, netcdf_classic
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Decks that take thousands of launch-bound steps on a 64 x 32 or 48 x 24 x 8 grid (1.5 - 4 minutes each on a B200) run
+# on request: AMPE_B200_SLOW_DECKS=1.  Their full runs are committed: profiles/r02ac_pytest_decks3d.log (FourCorners 3D),
+# r02af_pytest_solidify.log, r02af_pytest_solidify3d.log.
+slow_deck = pytest.mark.skipif(not os.environ.get("AMPE_B200_SLOW_DECKS"),
+                               reason="minutes of launch-bound time stepping: AMPE_B200_SLOW_DECKS=1 (full runs in profiles/)")
 
 
 def initial_conditions(name, cfg, tmp_path, init_t=None, init_q=None):
@@ -289,6 +294,7 @@ def test_dendrite_deck_3d_gpu(tmp_path):
 
 
 @pytest.mark.gpu
+@slow_deck
 @pytest.mark.timeout(900)
 def test_four_corners_deck_3d_gpu(tmp_path):
     """tests/FourCorners/test3d.py (64 x 64 x 4): solid fraction 0.93 +- 0.01 after t = 0.19 and every grain volume then
@@ -328,6 +334,7 @@ def test_two_grains_quadratic_deck_2d_gpu(tmp_path):
 
 
 @pytest.mark.gpu
+@slow_deck
 @pytest.mark.timeout(900)
 def test_solidify_quaternions_deck_gpu(tmp_path):
     """tests/SolidifyQuaternions/test2d.py: two grains on the lower boundary solidify a liquid of random orientation
@@ -343,4 +350,23 @@ def test_solidify_quaternions_deck_gpu(tmp_path):
           {k: round(v, 6) for k, v in grains[-1][1].items()})
     assert t >= 1.0
     assert abs(d["solid_fraction"] - 0.42) <= 1.0e-2, d["solid_fraction"]
+    assert len(grains[-1][1]) == 2, grains[-1]
+
+
+@pytest.mark.gpu
+@slow_deck
+@pytest.mark.timeout(900)
+def test_solidify_quaternions_deck_3d_gpu(tmp_path):
+    """tests/SolidifyQuaternions/test3d.py (48 x 24 x 8, periodic in x and z, slope-0 in y): solid fraction 0.36 +- 0.01
+    after t = 0.8, exactly two grains then"""
+    cfg = configs.solidify_quaternions_test3d()
+    y = initial_conditions("solidify_quaternions3d", cfg, tmp_path)
+    grains = []
+    hist, steps = run_device_deck(cfg, y, 0.8, 0.1, 2.0e-5, 1.0e-7, precond_cycles=2, grains=grains,
+                                  run_loop_outputs=True)
+    t, d = hist[-1]
+    print("SolidifyQuaternions 3D:", steps, "steps, t =", t, "solid fraction", d["solid_fraction"], "grains",
+          {k: v for k, v in grains[-1][1].items()})
+    assert t >= 0.8
+    assert abs(d["solid_fraction"] - 0.36) <= 1.0e-2, d["solid_fraction"]
     assert len(grains[-1][1]) == 2, grains[-1]

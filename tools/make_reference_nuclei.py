@@ -35,6 +35,10 @@ DECKS = {
     # tests/FourCorners/test2d.py:11-13 (utils/make4corners.py), tests/SolidifyQuaternions/test2d.py:11-14
     # (utils/make_initial_grains_on_boundary.py, random.seed(112345) inside)
     "four_corners": ("make4corners.py", ["-x", "64", "-y", "64", "-z", "1"]),
+    # tests/SolidifyQuaternions/test3d.py:11-14
+    "solidify_quaternions3d": ("make_initial_grains_on_boundary.py",
+                               ["-x", "48", "-y", "24", "-z", "8", "--solid-fraction", "0.25", "--smooth", "0", "--qlen", "4",
+                                "--ngrains", "2"]),
     "solidify_quaternions": ("make_initial_grains_on_boundary.py",
                              ["-x", "64", "-y", "32", "-z", "1", "--solid-fraction", "0.25", "--smooth", "0", "--qlen", "4",
                               "--ngrains", "2"]),
