@@ -385,6 +385,44 @@ def solidify_quaternions_test3d():
     return c
 
 
+def one_grain_quadratic_test(ndim=2):
+    """tests/OneGrainQuadratic/{2d,3d}.input: one grain, no orientation; quadratic free energy with rhs_form "ebs" and
+    diffusion_type "temperature_dependent" (Arrhenius D of each phase weighted with the phase fraction,
+    TbasedCompositionDiffusionStrategy); Interface{sigma 0.1, delta 0.045}; T = 873 K - 20 K/s t (target 573 K);
+    64^2 cells on 3.2^2 um / 48^3 on 2.4^3 um, periodic."""
+    import math
+    if ndim == 2:
+        c = _base(2, (64, 64), (0.0, 0.0), (3.2, 3.2))
+    else:
+        c = _base(3, (48, 48, 48), (0.0, 0.0, 0.0), (2.4, 2.4, 2.4))
+    c.qlen = 0
+    c.with_phase = 1
+    c.with_concentration = 1
+    c.evolve_quat = 0
+    c.phase_flux_type = _abi.FLUX_SIMPLE
+    c.conc_rhs_form = _abi.CONC_EBS
+    c.free_energy = _abi.FE_QUADRATIC
+    c.T_uniform = 873.0
+    c.dtemperaturedt = -20.0
+    c.target_temperature = 573.0
+    sigma, delta = 0.1, 0.045
+    c.epsilon_phase = math.sqrt(6.0 * sigma * delta)
+    c.phi_well_scale = (3.0 * sigma / delta) / 16.0
+    c.phi_mobility = 200.0
+    c.energy_interp = _ch("h")
+    c.conc_interp = _ch("h")          # conc_interp_func_type defaults to phi_interp_func_type
+    c.avg_func = _ch("a")
+    c.conc_avg_func = _ch("a")
+    c.vm_liquid = c.vm_solid = 1.5e-5
+    c.D_solid, c.D_liquid = 1.3e8, 5.6e4
+    c.Q0_solid, c.Q0_liquid = 156377.0, 55329.0
+    c.quad_Tref = 1000.0
+    c.quad_A_l = c.quad_A_s = 1.0e4
+    c.quad_Ceq_l, c.quad_Ceq_s = 0.05, 0.10
+    c.quad_m_l = c.quad_m_s = 0.0
+    return c
+
+
 BUILDERS = {
     "pfhub1a": pfhub1a,
     "dendrite2d": dendrite2d,

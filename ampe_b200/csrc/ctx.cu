@@ -143,8 +143,8 @@ int ampe_derive_params_at(const ampe_rhs_config& c, double T_now, Params& p)
       return set_err(AMPE_EINVAL, "3D anisotropic phase flux: qlen 4 without the symmetry-aware path");
    if (p.flux_type == AMPE_FLUX_ISOTROPIC && c.ndim != 2)
       return set_err(AMPE_EINVAL, "isotropic stencil is incomplete in 3D (reference stops)");
-   if (p.conc_form == AMPE_CONC_EBS && c.free_energy != AMPE_FE_CALPHAD)
-      return set_err(AMPE_EINVAL, "EBS composition RHS needs the CALPHAD free energy");
+   if (p.conc_form == AMPE_CONC_EBS && c.free_energy != AMPE_FE_CALPHAD && c.free_energy != AMPE_FE_QUADRATIC)
+      return set_err(AMPE_EINVAL, "EBS composition RHS needs the CALPHAD or the quadratic free energy");
    if (p.conc_form == AMPE_CONC_KKS && c.free_energy != AMPE_FE_QUADRATIC && c.free_energy != AMPE_FE_CALPHAD)
       return set_err(AMPE_EINVAL, "KKS composition RHS needs the quadratic or the CALPHAD free energy");
    if ((p.conc_form == AMPE_CONC_EBS || p.conc_form == AMPE_CONC_KKS) && p.with_T)
@@ -206,8 +206,9 @@ int ampe_derive_params_at(const ampe_rhs_config& c, double T_now, Params& p)
       p.quad_rla = c.quad_A_l / c.quad_A_s;
       p.quad_ral = c.quad_A_s / c.quad_A_l;
    }
-   if (p.conc_form == AMPE_CONC_KKS) {
-      // concentration_pfmdiffusion (3d/concentrationdiffusion.m4:43-75) for uniform T
+   if (p.conc_form == AMPE_CONC_KKS || (p.conc_form == AMPE_CONC_EBS && c.free_energy == AMPE_FE_QUADRATIC)) {
+      // concentration_pfmdiffusion (3d/concentrationdiffusion.m4:43-75) / concentration_pfmdiffusion_of_temperature
+      // (2d/concentrationdiffusion.m4:382-396) for uniform T
       const double q0l = c.Q0_liquid / R_GAS, q0s = c.Q0_solid / R_GAS;
       const double invT = 2.0 / (T + T);
       p.D_liquid = c.D_liquid * exp(-q0l * invT);

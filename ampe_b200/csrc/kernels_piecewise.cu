@@ -1075,8 +1075,18 @@ int ampe_k_set_ebs_diffusion(const ampe_rhs_config* cfg, const int* ifirst, cons
       int L[3], H[3];
       side_bounds(b, ax, 0, L, H);
       const DV dl = Dl.a[ax], da = Da.a[ax];
+      const bool tbased = cfg->free_energy != AMPE_FE_CALPHAD;
       rc = for_box(L, H, ST(stream), [=] __device__(int i, int j, int k) {
          const int im = i - E(ax, 0), jm = j - E(ax, 1), km = k - E(ax, 2);
+         if (tbased) {
+            // diffusion_type "temperature_dependent": concentration_pfmdiffusion_of_temperature
+            // (2d/concentrationdiffusion.m4:341-430) at the uniform temperature
+            const double vphi = average_func(ph(im, jm, km), ph(i, j, k), p.avg_func);
+            const double hphi = interp_func(vphi, p.diffusion_interp);
+            dl(i, j, k) = (1.0 - hphi) * p.D_liquid;
+            da(i, j, k) = hphi * p.D_solid;
+            return;
+         }
          const double c_l = 0.5 * (l(i, j, k) + l(im, jm, km));
          const double c_a = 0.5 * (a(i, j, k) + a(im, jm, km));
          const double vl = diffusion_mobility(p.ct, 0, c_l) * calphad_d2f(p.ct, c_l, 0);

@@ -408,15 +408,24 @@ struct Rhs3 {
             Dl = inrange ? A.lagD0[a][gface] : 0.0;
             Da = inrange ? A.lagD1[a][gface] : 0.0;
          } else {
-            // MobilityCompositionDiffusionStrategy.cc:296-327 + setPFMDiffOnPatch
-            const double c_l = 0.5 * (scl[c] + scl[cm]);
-            const double c_a = 0.5 * (sca[c] + sca[cm]);
-            const double dl = ebs_phase_diffusivity(p.ct, 0, c_l);
-            const double da = ebs_phase_diffusivity(p.ct, 1, c_a);
-            const double phia = average3(phi_c, phi_m, AMPE_SEL(conc_avg_func));
-            const double hphi = interp3(phia, AMPE_SEL(diffusion_interp));
-            Dl = (1. - hphi) * dl;
-            Da = hphi * da;
+            if (AMPE_SEL(free_energy) == AMPE_FE_CALPHAD) {
+               // MobilityCompositionDiffusionStrategy.cc:296-327 + setPFMDiffOnPatch
+               const double c_l = 0.5 * (scl[c] + scl[cm]);
+               const double c_a = 0.5 * (sca[c] + sca[cm]);
+               const double dl = ebs_phase_diffusivity(p.ct, 0, c_l);
+               const double da = ebs_phase_diffusivity(p.ct, 1, c_a);
+               const double phia = average3(phi_c, phi_m, AMPE_SEL(conc_avg_func));
+               const double hphi = interp3(phia, AMPE_SEL(diffusion_interp));
+               Dl = (1. - hphi) * dl;
+               Da = hphi * da;
+            } else {
+               // diffusion_type "temperature_dependent" (quadratic free energy): concentration_pfmdiffusion_of_temperature
+               // (2d/concentrationdiffusion.m4:341-430) with the uniform-T Arrhenius factors of ampe_derive_params
+               const double vphi = average3(phi_m, phi_c, AMPE_SEL(avg_func));
+               const double hphi = interp3(vphi, AMPE_SEL(diffusion_interp));
+               Dl = (1.0 - hphi) * p.D_liquid;
+               Da = hphi * p.D_solid;
+            }
             if (wr) {
                A.lagD0[a][gface] = Dl;
                A.lagD1[a][gface] = Da;
@@ -625,7 +634,7 @@ struct Rhs3 {
             // from the KKS kernel, which has the logarithms of the converged c_l, c_a at hand
             const double hp = deriv_interp_func(phi, AMPE_SEL(energy_interp));
             rhs += hp * A.df[gcell];
-         } else if (CONC == AMPE_CONC_KKS && free_energy == AMPE_FE_QUADRATIC) {
+         } else if ((CONC == AMPE_CONC_KKS || CONC == AMPE_CONC_EBS) && free_energy == AMPE_FE_QUADRATIC) {
             // QuadraticFreeEnergyStrategy.cc:242-243, 512-530
             const double c_l = s[TT::O_CL + c], c_a = s[TT::O_CA + c];
             double f_l = p.quad_A[0] * (c_l - p.quad_ceq[0]) * (c_l - p.quad_ceq[0]);

@@ -135,6 +135,20 @@ void set_diffusion_coeff_for_concentration(Ctx* c)
             for (int j = b.lo[1]; j <= b.hi[1] + E(a, 1); j++)
                for (int i = b.lo[0]; i <= b.hi[0] + E(a, 0); i++) {
                   const int im = i - E(a, 0), jm = j - E(a, 1), km = k - E(a, 2);
+                  if (p.free_energy != AMPE_FE_CALPHAD) {
+                     // diffusion_type "temperature_dependent": TbasedCompositionDiffusionStrategy::setDiffusion ->
+                     // concentration_pfmdiffusion_of_temperature (2d/concentrationdiffusion.m4:341-430): Arrhenius
+                     // diffusivity of each phase weighted with the phase fraction at the face; avg_func_type and
+                     // diffusion_interp_func_type (CompositionDiffusionStrategyFactory.h:59-72)
+                     const double vphi = average_func(c->phase.v(im, jm, km), c->phase.v(i, j, k), p.avg_func);
+                     const double hphi = interp_func(vphi, p.diffusion_interp);
+                     const double invT = 2.0 / (c->temp.v(im, jm, km) + c->temp.v(i, j, k));
+                     const double diff_liquid = p.D_liquid * exp(-(p.Q0_liquid / GASCONSTANT_R_JPKPMOL) * invT);
+                     const double diff_solid = p.D_solid * exp(-(p.Q0_solid / GASCONSTANT_R_JPKPMOL) * invT);
+                     c->diff_l.a[a].v(i, j, k) = (1.0 - hphi) * diff_liquid;
+                     c->diff_a.a[a].v(i, j, k) = hphi * diff_solid;
+                     continue;
+                  }
                   const double temp = 0.5 * (c->temp.v(i, j, k) + c->temp.v(im, jm, km));
                   const double c_l = 0.5 * (c->cl.v(i, j, k) + c->cl.v(im, jm, km));
                   const double c_a = 0.5 * (c->ca.v(i, j, k) + c->ca.v(im, jm, km));

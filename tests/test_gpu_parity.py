@@ -518,3 +518,27 @@ def test_zero_slope_boundaries_and_temperature_ramp(case):
         torch.cuda.synchronize()
         assert not np.array_equal(ydp["phase"].cpu().numpy(), g[0]["phase"])
         rp.close()
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_ebs_flux_with_quadratic_free_energy(ndim):
+    """rhs_form "ebs" with the quadratic free energy and diffusion_type "temperature_dependent"
+    (TbasedCompositionDiffusionStrategy: tests/OneGrainQuadratic, tests/ConservedVolume): Arrhenius diffusivity of each
+    phase weighted with the phase fraction at the face, closed-form phase concentrations, quadratic driving force --
+    against the restatement, fd_flag 0 / 1 / 0, at a time where the temperature ramp has moved T"""
+    from ampe_b200 import configs
+    cfg = configs.one_grain_quadratic_test(ndim)
+    base = "auni2d" if ndim == 2 else "gg3d_hbsm"
+    small = parity.SMALL[base]
+    cfg.n[0], cfg.n[1] = small["nx"], small["ny"]
+    if ndim == 3:
+        cfg.n[2] = small["nz"]
+    _, st0 = parity.make_case("gg3d_hbsm" if ndim == 3 else "auni2d")
+    phi = st0["phase"]
+    # compositions in the range of the deck (0.06 liquid, 0.1 solid)
+    from ampe_b200 import fields
+    h = fields.h_pbg(phi)
+    conc = (0.1 * h + 0.06 * (1 - h) + fields.smooth_noise(tuple(phi.shape), 1e-3, "cpu", 5)).contiguous()
+    st = {"phase": phi, "quat": None, "conc": conc, "temperature": None}
+    errs = parity.compare(base, cfg, st, fd_flags=(0, 1, 0))
+    _check(errs, cfg)

@@ -114,6 +114,17 @@ def test_kks_composition_deck_cpu(tmp_path):
     assert abs(d["solid_fraction"] - 0.32) <= 1.0e-2, d["solid_fraction"]
 
 
+def test_one_grain_quadratic_deck_cpu(tmp_path):
+    """tests/OneGrainQuadratic/test2d.py: quadratic free energy with rhs_form "ebs" and temperature-dependent diffusion
+    (TbasedCompositionDiffusionStrategy), T ramp: solid fraction 0.21 +- 0.01 after t = 0.25"""
+    cfg = configs.one_grain_quadratic_test(2)
+    y = initial_conditions("one_grain_quadratic2d", cfg, tmp_path)
+    hist, steps = run_oracle_deck(cfg, y, 0.25, 0.05, 1.0e-4, 1.0e-7, precond_cycles=2)
+    t, d = hist[-1]
+    assert t >= 0.25
+    assert abs(d["solid_fraction"] - 0.21) <= 1.0e-2, d["solid_fraction"]
+
+
 def test_single_grain_auni_deck_unpreconditioned_start_agrees(tmp_path):
     """the first 0.02 time units without the preconditioner (678 small steps) land on the same solid fraction as the
     preconditioned run (about 100 steps): the preconditioner changes the work, not the answer"""
@@ -370,3 +381,17 @@ def test_solidify_quaternions_deck_3d_gpu(tmp_path):
     assert t >= 0.8
     assert abs(d["solid_fraction"] - 0.36) <= 1.0e-2, d["solid_fraction"]
     assert len(grains[-1][1]) == 2, grains[-1]
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("ndim,end,target", [(2, 0.25, 0.21), (3, 0.15, 0.14)])
+def test_one_grain_quadratic_deck_gpu(tmp_path, ndim, end, target):
+    """tests/OneGrainQuadratic/test{2,3}d.py: 0.21 +- 0.01 after t = 0.25 (64^2), 0.14 +- 0.01 after t = 0.15 (48^3)"""
+    cfg = configs.one_grain_quadratic_test(ndim)
+    y = initial_conditions("one_grain_quadratic%dd" % ndim, cfg, tmp_path)
+    hist, steps = run_device_deck(cfg, y, end, 0.05, 1.0e-4, 1.0e-7, precond_cycles=2)
+    t, d = hist[-1]
+    print("OneGrainQuadratic %dD:" % ndim, steps, "steps, solid fraction", d["solid_fraction"])
+    assert t >= end
+    assert abs(d["solid_fraction"] - target) <= 1.0e-2, d["solid_fraction"]

@@ -29,6 +29,11 @@ DECKS = {
     "single_grain_auni3d": ["--nx", "32", "--ny", "32", "--nz", "32", "-r", "16", "--center0", "0, 0, 0", "-c", "0.25",
                             "--concentration-in", "0.096"],
     "four_corners3d": ("make4corners.py", ["-x", "64", "-y", "64", "-z", "4"]),
+    # tests/OneGrainQuadratic/test2d.py:11-15, test3d.py:11-15
+    "one_grain_quadratic2d": ["--nx", "64", "--ny", "64", "--nz", "1", "-r", "8", "--concentration-in", "0.1",
+                              "--concentration-out", "0.06", "--ngrains", "1"],
+    "one_grain_quadratic3d": ["--nx", "48", "--ny", "48", "--nz", "48", "-r", "8", "--concentration-in", "0.1",
+                              "--concentration-out", "0.06", "--ngrains", "1"],
     # tests/TwoGrainsQuadratic/test2d.py:11-15
     "two_grains_quadratic2d": ["--nx", "64", "--ny", "64", "--nz", "1", "-r", "8", "--concentration-in", "0.1",
                                "--concentration-out", "0.06", "--ngrains", "2", "-q", "4"],
