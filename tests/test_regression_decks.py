@@ -395,3 +395,4 @@ def test_one_grain_quadratic_deck_gpu(tmp_path, ndim, end, target):
     print("OneGrainQuadratic %dD:" % ndim, steps, "steps, solid fraction", d["solid_fraction"])
     assert t >= end
     assert abs(d["solid_fraction"] - target) <= 1.0e-2, d["solid_fraction"]
+
