@@ -49,6 +49,11 @@ struct ImplicitOptions {
    // (QuatIntegrator::Advance takes ONE internal CVODE step per call, CV_ONE_STEP; output intervals are tested against
    // the time the step landed on, so an output at "t = 0.01" happens a fraction of a step later)
    bool stop_at_tend = true;
+   // CVODE's rule for a linear solve that ran out of Krylov vectors (cvLsSolve): a residual that was only REDUCED is
+   // accepted on the first Newton iteration and is a recoverable convergence failure afterwards (step retried with
+   // h / 4, preconditioner set up again); a residual that was not reduced always is.  false (the default, what every
+   // committed deck result was produced with): the update is taken and the Newton test decides alone.
+   bool strict_linear_convergence = false;
 };
 
 struct ImplicitStats {
@@ -308,6 +313,8 @@ class ImplicitIntegrator
          const double lin_tol = d_opt.linear_tolerance_factor * d_opt.newton_tolerance;
          int rc = gmres(t, gamma, ewt, ycur, fy, res, delta, ytmp, wk, V, lin_tol);
          if (rc != IMPLICIT_OK) return rc;
+         if (d_opt.strict_linear_convergence && d_linear_state != 0 && (it > 0 || d_linear_state == 2))
+            return IMPLICIT_ENEWTON;  // SUNLS_RES_REDUCED after the first iteration / SUNLS_CONV_FAIL
          d_ops.linearSum(1.0, ycur, 1.0, delta, ycur);
          d_ops.linearSum(1.0, acor, 1.0, delta, acor);
          d_stats.newton_iterations++;
@@ -357,6 +364,7 @@ class ImplicitIntegrator
       const Vec& b0 = left ? V[0] : b;
       const double beta = std::sqrt(d_ops.wdot(b0, b0, ewt) * invN);
       d_stats.last_linear_residual = beta;
+      d_linear_state = 0;  // 0 converged, 1 residual reduced but above tol, 2 not reduced
       if (beta <= tol) {
          // the predictor already solves the (preconditioned) system to the tolerance: x = 0
          return IMPLICIT_OK;
@@ -412,6 +420,7 @@ class ImplicitIntegrator
          if (std::fabs(g[j + 1]) <= tol || !(hsub > 0.0)) break;
          d_ops.scale(1.0 / hsub, wk, V[j + 1]);
       }
+      if (!(d_stats.last_linear_residual <= tol)) d_linear_state = (d_stats.last_linear_residual < beta) ? 1 : 2;
       // back substitution, x = sum c_i V_i
       std::vector<double> c(k, 0.0);
       for (int i = k - 1; i >= 0; i--) {
@@ -429,6 +438,7 @@ class ImplicitIntegrator
    }
 
    Ops& d_ops;
+   int d_linear_state = 0;
    Vec d_pv;
    ImplicitOptions d_opt;
    ImplicitStats d_stats;

@@ -195,6 +195,8 @@ extern "C" int oracle_integrate_adaptive(void* ctx, const ampe_rhs_fields* y, do
    if (iopt) {
       o.order = iopt[0], o.max_krylov_dimension = iopt[1], o.max_newton_iterations = iopt[2];
       if (iopt[3] > 0) o.max_steps = iopt[3];
+      o.stop_at_tend = !(iopt[4] & 1);
+      o.strict_linear_convergence = (iopt[4] & 2) != 0;
    }
    if (dopt) {
       o.rtol = dopt[0], o.atol = dopt[1], o.newton_tolerance = dopt[2], o.linear_tolerance_factor = dopt[3];
