@@ -9,10 +9,10 @@
 // the reference's messages (:114-175, :685-707).
 //
 // Format: NetCDF CLASSIC (CDF-1) and 64-bit-offset (CDF-2) files are parsed here directly -- the
-// format the reference reads through its HAVE_NETCDF3 branch.  Files in the NetCDF-4 container are
-// HDF5 files; neither libnetcdf nor libhdf5 is part of this image, so they are rejected with a
-// message naming the conversion (`nccopy -k classic in.nc out.nc`, or format='NETCDF3_CLASSIC' in the
-// reference's utils/*.py writers).
+// format the reference reads through its HAVE_NETCDF3 branch.  Files in the NetCDF-4 container (what
+// the reference's utils/*.py writers produce: format='NETCDF4') are HDF5 files and go through
+// NetCDF4File.h, a reader of the subset of the HDF5 file format such files use (neither libnetcdf nor
+// libhdf5 is part of this image).  The container is recognised by its signature, not by the file name.
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "../../include/ampe_b200.h"
+#include "NetCDF4File.h"
 
 namespace ampe_host {
 
@@ -222,8 +223,20 @@ class FieldsInitializer
    }
    void initializeLevelFromData(const std::string& init_data_filename, int slice_index, const ampe_rhs_fields* y) const
    {
+      if (NetCDF4File::isHdf5(init_data_filename)) {
+         NetCDF4File ncf(init_data_filename);
+         initializeFrom(ncf, slice_index, y);
+      } else {
+         NetCDFClassicFile ncf(init_data_filename);
+         initializeFrom(ncf, slice_index, y);
+      }
+   }
+
+ private:
+   template <class File>
+   void initializeFrom(File& ncf, int slice_index, const ampe_rhs_fields* y) const
+   {
       const ampe_rhs_config& p = d_cfg;
-      NetCDFClassicFile ncf(init_data_filename);
       const bool readQ = d_read_q && p.qlen > 0, readC = d_read_c && p.with_concentration;
       const bool readT = d_read_t && p.with_unsteady_temperature, readP = d_read_phase && p.with_phase;
       std::string cname = "concentration";
@@ -275,7 +288,6 @@ class FieldsInitializer
       if (readC) ncf.get(cname, start, count, need(y->conc, "conc"));
    }
 
- private:
    ampe_rhs_config d_cfg;
    bool d_read_phase = true, d_read_t = true, d_read_q = true, d_read_c = true;
 };

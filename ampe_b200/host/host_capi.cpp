@@ -215,4 +215,33 @@ int ampe_host_read_initial_conditions(const char* filename, const ampe_rhs_confi
       return -1;
    }
 }
+// NetCDF-4 container inspection (host/NetCDF4File.h): shape of a variable / a whole variable of rank <= 3 as doubles.
+// Used by the tests to hold the HDF5 subset reader against files the initial-condition path never sees (any float dataset).
+int ampe_host_hdf5_var_shape(const char* filename, const char* name, int* rank, long long* shape8)
+{
+   try {
+      if (!filename || !name || !rank || !shape8) throw std::runtime_error("ampe_host_hdf5_var_shape: NULL argument");
+      ampe_host::NetCDF4File f(filename);
+      const std::vector<size_t> sh = f.shape(name);
+      if (sh.size() > 8) throw std::runtime_error("more than eight dimensions");
+      *rank = (int)sh.size();
+      for (size_t d = 0; d < sh.size(); d++) shape8[d] = (long long)sh[d];
+      return 0;
+   } catch (const std::exception& e) {
+      g_host_err = e.what();
+      return -1;
+   }
+}
+int ampe_host_hdf5_read_var(const char* filename, const char* name, double* out)
+{
+   try {
+      if (!filename || !name || !out) throw std::runtime_error("ampe_host_hdf5_read_var: NULL argument");
+      ampe_host::NetCDF4File f(filename);
+      f.getAll(name, out);
+      return 0;
+   } catch (const std::exception& e) {
+      g_host_err = e.what();
+      return -1;
+   }
+}
 }

@@ -62,14 +62,33 @@ def load_host():
         L.ampe_host_read_initial_conditions.restype = C.c_int
         L.ampe_host_read_initial_conditions.argtypes = [C.c_char_p, C.POINTER(_abi.RhsConfig), C.c_int, C.c_int,
                                                         C.POINTER(_abi.RhsFields)]
+        L.ampe_host_hdf5_var_shape.restype = C.c_int
+        L.ampe_host_hdf5_var_shape.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]
+        L.ampe_host_hdf5_read_var.restype = C.c_int
+        L.ampe_host_hdf5_read_var.argtypes = [C.c_char_p, C.c_char_p, vp]
         _lib = L
     return _lib
+
+
+def read_hdf5_variable(filename, name):
+    """a whole float / double dataset (rank <= 3) of the root group of an HDF5 / NetCDF-4 file as float64, through the
+    HDF5 subset reader of the initial-condition path (host/NetCDF4File.h)"""
+    import numpy as np
+    L = load_host()
+    rank = C.c_int()
+    shape = (C.c_longlong * 8)()
+    if L.ampe_host_hdf5_var_shape(os.fsencode(filename), name.encode(), C.byref(rank), shape) != 0:
+        raise AmpeError(L.ampe_host_last_error().decode())
+    out = np.zeros(tuple(shape[:rank.value]), dtype=np.float64)
+    if L.ampe_host_hdf5_read_var(os.fsencode(filename), name.encode(), out.ctypes.data) != 0:
+        raise AmpeError(L.ampe_host_last_error().decode())
+    return out
 
 
 def read_initial_conditions(filename, cfg, slice_index=-1, fields=("phase", "temperature", "quat", "conc"),
                             device=None):
     """FieldsInitializer::initializeLevelFromData (source/FieldsInitializer.cc:80-360): the state vector of this
-    rank's slab from a NetCDF classic file (`phase`, `quat1..`, `concentration[0]`, `temperature`, dims z, y, x).
+    rank's slab from a NetCDF file, classic or NetCDF-4 / HDF5 container (`phase`, `quat1..`, `concentration[0]`, `temperature`, dims z, y, x).
     Returns a dict of float64 tensors in ghost-0 SAMRAI order (pinned host memory when CUDA is available, moved
     to `device` if given); components the configuration does not have are None."""
     L = load_host()
