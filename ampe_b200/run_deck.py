@@ -140,8 +140,9 @@ def print_scalar_diagnostics(cfg, d, out):
             out.write("  Cex (HBSM) for component 0 = %.8g\n" % d["cex"])
 
 
-def run(db, cfg, y, backend, h0=None, out=sys.stdout):
+def run(db, cfg, y, backend, h0=None, out=None):
     """PFModel::Run: returns (cycles, time, history of (cycle, time, diagnostics))"""
+    out = sys.stdout if out is None else out
     par = input_deck.run_parameters(db)
     if par["end_time"] is None:
         raise input_deck.DeckError("key 'end_time' is required")
