@@ -247,7 +247,7 @@ def main(argv=None):
         cycles, t, _ = run(db, cfg, y, backend, h0=a.first_step)
     finally:
         backend.close()
-    print("cycles %d, end time %.10g" % (cycles, t))
+    print("Run complete: %d steps, end time %.10g" % (cycles, t))
     return 0
 
 

@@ -1,0 +1,24 @@
+"""Test infrastructure: `python tests/run_deck_cpu.py deck.input` = ampe_b200.run_deck's loop with the CPU restatement as the
+backend, so the reference's test scripts can be pointed at an executable in a container without a GPU (the product's own
+program, `python -m ampe_b200.run_deck`, has the device as its only backend)."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from ampe_b200 import host_rhs, input_deck, run_deck  # noqa: E402
+from test_run_deck import OracleBackend, _read  # noqa: E402
+
+if __name__ == "__main__":
+    deck = sys.argv[1]
+    db = input_deck.load(deck)
+    cfg = input_deck.rhs_config(db)
+    y = run_deck.initial_state(db, cfg, os.path.dirname(os.path.abspath(deck)), _read)
+    backend = OracleBackend(cfg, y, precond_cycles=2)
+    try:
+        cycles, t, _ = run_deck.run(db, cfg, y, backend)
+    finally:
+        backend.close()
+    print("Run complete: %d steps, end time %.10g" % (cycles, t))

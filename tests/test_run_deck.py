@@ -194,3 +194,29 @@ def test_run_deck_program_on_the_device(tmp_path, capsys):
         backend.close()
     assert abs(hist[-1][2]["solid_fraction"] - frac[-1]) <= 2.0e-4, (hist[-1][2]["solid_fraction"], frac[-1])
     assert abs(cycles - int(cyc[-1][2])) <= 3
+
+
+def reference_tree(tmp_path, deck_dir):
+    """tmp/tests/<deck_dir> as the working directory, tmp/utils -> the reference's generators: the layout its test scripts assume"""
+    (tmp_path / "tests" / deck_dir).mkdir(parents=True)
+    os.symlink(REF + "/utils", str(tmp_path / "utils"))
+    return str(tmp_path / "tests" / deck_dir)
+
+
+@pytest.mark.skipif(not os.path.exists(REF + "/tests/OneGrainQuadratic/test2d.py"), reason="runs the reference's own test script (build container only)")
+@pytest.mark.timeout(600)
+def test_reference_test_script_unmodified(tmp_path):
+    """tests/OneGrainQuadratic/test2d.py run as the reference's CTest runs it -- `test2d.py <mpiexec> <-n> <1> <exe> <input>` -- with
+    nothing of it changed: it calls the reference's utils/make_nuclei.py (which finds the netCDF4 stand-in and writes a NetCDF-4
+    container), starts the executable it is given on the deck, parses the output and exits 0 when its acceptance holds.  The
+    executable here is the deck program with the CPU restatement behind it; on the device it is `python -m ampe_b200.run_deck`
+    (profiles/r02ak_reference_test_scripts.log)."""
+    import subprocess
+    import sys
+    cwd = reference_tree(tmp_path, "OneGrainQuadratic")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tools", "netcdf4_shim") + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    exe = "%s %s" % (sys.executable, os.path.join(ROOT, "tests", "run_deck_cpu.py"))
+    r = subprocess.run([sys.executable, REF + "/tests/OneGrainQuadratic/test2d.py", "", "", "", exe, REF + "/tests/OneGrainQuadratic/2d.input"],
+                       cwd=cwd, env=env, capture_output=True, text=True, timeout=500)
+    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
+    assert "fraction" in r.stdout and not os.path.exists(os.path.join(cwd, "nuclei.nc"))   # the script removes its file at the end
