@@ -4,7 +4,7 @@
 # _ref_scratch/ holds the scripts, decks and generators copied from /root/reference for this one call (git-ignored, deleted
 # afterwards: it only exists because /root/reference does not exist on the GPU box).
 mkdir -p gpurun_out
-LOG=$PWD/gpurun_out/r02ak_reference_test_scripts.log
+LOG=$PWD/gpurun_out/${LOGNAME_R02:-r02ak_reference_test_scripts.log}
 : > $LOG
 export PYTHONPATH=$PWD:$PWD/tools/netcdf4_shim:$PYTHONPATH
 ROOT=$PWD
@@ -13,7 +13,7 @@ for case in "$@"; do
   cd $ROOT/_ref_scratch/tests/$deck
   echo "=== tests/$deck/$script  exe = python -m ampe_b200.run_deck" >> $LOG
   start=$(date +%s.%N)
-  timeout 120 python $script "" "" "" "python -m ampe_b200.run_deck" $dim.input $ROOT/_ref_scratch/thermo >> $LOG 2>&1
+  timeout ${DECK_TIMEOUT:-120} python $script "" "" "" "python -m ampe_b200.run_deck" $dim.input $ROOT/_ref_scratch/thermo >> $LOG 2>&1
   rc=$?
   echo "=== tests/$deck/$script exit code $rc  ($(python -c "import time; print('%.1f s' % (time.time() - $start))"))" >> $LOG
   echo "tests/$deck/$script exit code $rc"
