@@ -54,6 +54,12 @@ struct ImplicitOptions {
    // h / 4, preconditioner set up again); a residual that was not reduced always is.  false (the default, what every
    // committed deck result was produced with): the update is taken and the Newton test decides alone.
    bool strict_linear_convergence = false;
+   // CVODE ties the nonlinear tolerance to the error test: dcon = del min(1, crate) / tq[4] <= 1 with tq[4] = nlscoef / tq[2],
+   // tq[2] the coefficient that turns the accumulated correction into the local error estimate (cvSetTqBDF) -- the Newton
+   // error may be nlscoef of the ALLOWED LOCAL ERROR, not nlscoef in the WRMS norm -- and epslin = eplifac tq[4].  true: the
+   // same rule with this integrator's own error coefficient (newton_tolerance / cerr: 0.2 on the first step, 0.3 for BDF1,
+   // about 0.55 for BDF2 at constant step).  false (the default every committed deck number was produced with): del <= nlscoef.
+   bool scale_newton_tolerance = false;
 };
 
 struct ImplicitStats {
@@ -226,7 +232,8 @@ class ImplicitIntegrator
             }
          }
          d_ops.scale(0.0, acor, acor);
-         const int nrc = newton(t + h, gamma, psi, ewt, ycur, fy, res, delta, acor, ytmp, wk, V);
+         const int nrc = newton(t + h, gamma, psi, ewt, ycur, fy, res, delta, acor, ytmp, wk, V,
+                                d_opt.scale_newton_tolerance ? d_opt.newton_tolerance / cerr : d_opt.newton_tolerance);
          if (nrc == IMPLICIT_ERHS) {
             rc = nrc;
             break;
@@ -297,8 +304,9 @@ class ImplicitIntegrator
 
    // inexact Newton on G(y) = y - psi - gamma f(y); ycur holds the predictor on entry, the solution on exit
    int newton(double t, double gamma, const Vec& psi, const Vec& ewt, Vec& ycur, Vec& fy, Vec& res, Vec& delta,
-              Vec& acor, Vec& ytmp, Vec& wk, std::vector<Vec>& V)
+              Vec& acor, Vec& ytmp, Vec& wk, std::vector<Vec>& V, double newton_tolerance = -1.0)
    {
+      if (newton_tolerance <= 0.0) newton_tolerance = d_opt.newton_tolerance;
       double delp = 0.0, crate = 1.0;
       for (int it = 0; it < d_opt.max_newton_iterations; it++) {
          if (d_ops.rhs(t, ycur, fy, 0) != 0) return IMPLICIT_ERHS;
@@ -310,7 +318,7 @@ class ImplicitIntegrator
          // res = -G = psi + gamma f - y
          d_ops.linearSum(1.0, psi, gamma, fy, res);
          d_ops.linearSum(1.0, res, -1.0, ycur, res);
-         const double lin_tol = d_opt.linear_tolerance_factor * d_opt.newton_tolerance;
+         const double lin_tol = d_opt.linear_tolerance_factor * newton_tolerance;
          int rc = gmres(t, gamma, ewt, ycur, fy, res, delta, ytmp, wk, V, lin_tol);
          if (rc != IMPLICIT_OK) return rc;
          if (d_opt.strict_linear_convergence && d_linear_state != 0 && (it > 0 || d_linear_state == 2))
@@ -324,7 +332,7 @@ class ImplicitIntegrator
             crate = std::fmax(0.3 * crate, del / delp);  // CVODE CRDOWN
             if (del > 2.0 * delp) return IMPLICIT_ENEWTON;  // CVODE RDIV: diverging
          }
-         if (del * std::fmin(1.0, crate) <= d_opt.newton_tolerance) return IMPLICIT_OK;
+         if (del * std::fmin(1.0, crate) <= newton_tolerance) return IMPLICIT_OK;
          delp = del;
       }
       return IMPLICIT_ENEWTON;

@@ -197,6 +197,7 @@ extern "C" int oracle_integrate_adaptive(void* ctx, const ampe_rhs_fields* y, do
       if (iopt[3] > 0) o.max_steps = iopt[3];
       o.stop_at_tend = !(iopt[4] & 1);
       o.strict_linear_convergence = (iopt[4] & 2) != 0;
+      o.scale_newton_tolerance = (iopt[4] & 4) != 0;  // bit 2: CVODE's nonlinear tolerance relative to the error test
    }
    if (dopt) {
       o.rtol = dopt[0], o.atol = dopt[1], o.newton_tolerance = dopt[2], o.linear_tolerance_factor = dopt[3];

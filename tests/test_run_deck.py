@@ -220,3 +220,25 @@ def test_reference_test_script_unmodified(tmp_path):
                        cwd=cwd, env=env, capture_output=True, text=True, timeout=500)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
     assert "fraction" in r.stdout and not os.path.exists(os.path.join(cwd, "nuclei.nc"))   # the script removes its file at the end
+
+
+def test_cvode_nonlinear_tolerance_option(tmp_path):
+    """ImplicitOptions::scale_newton_tolerance (CVODE's tq[4] = nlscoef / tq[2]: the Newton error bounded by nlscoef of the allowed
+    LOCAL ERROR instead of nlscoef in the WRMS norm): the same trajectory within the integration tolerance for less nonlinear work"""
+    db = input_deck.parse(DECK)
+    cfg = input_deck.rhs_config(db)
+    _disc_problem(tmp_path)
+    out = {}
+    for flag in (False, True):
+        y = run_deck.initial_state(db, cfg, str(tmp_path), _read)
+        backend = OracleBackend(cfg, y, precond_cycles=2)
+        try:
+            rc, st = backend.o.integrate_adaptive(y, 2.0e-3, 2.0e-9, rtol=1.0e-6, atol=1.0e-4, max_steps=500, scale_newton_tolerance=flag)
+            assert rc == 0, (rc, st)
+            out[flag] = (st, backend.o.scalar_diagnostics(y)["solid_fraction"])
+        finally:
+            backend.close()
+    assert abs(out[True][1] - out[False][1]) <= 2.0e-4
+    assert out[True][0]["newton_iterations"] <= out[False][0]["newton_iterations"]
+    assert out[True][0]["convergence_failures"] <= out[False][0]["convergence_failures"]
+    assert out[True][0]["linear_iterations"] < out[False][0]["linear_iterations"]
