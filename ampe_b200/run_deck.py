@@ -194,6 +194,38 @@ def run(db, cfg, y, backend, h0=None, out=None):
     return cycle, t, history
 
 
+def current_temperature(cfg, t):
+    """ScalarTemperatureStrategy::getCurrentTemperature (ScalarTemperatureStrategy.cc:57-74): the ramp, held at its target"""
+    T = cfg.T_uniform + cfg.dtemperaturedt * t
+    if cfg.dtemperaturedt < 0.0 and T < cfg.target_temperature:
+        return cfg.target_temperature
+    if cfg.target_temperature > 0.0 and cfg.dtemperaturedt > 0.0 and T > cfg.target_temperature:
+        return cfg.target_temperature
+    return T
+
+
+def write_ending_file(db, cfg, y_np, t, directory="."):
+    """InitialConditions{WriteEndingFile{filename}} (PFModel.cc:146-160, FieldsWriter.cc:60-330): the fields at the end of the
+    run as single-precision variables phase / quat1.. / concentration / temperature dimensioned (z, y, x) plus the dimension
+    qlen -- the file a follow-up deck names as its InitialConditions{filename} (examples/AuNi_2D: 9grains_AuNi_initial.input,
+    then 9grains_AuNi.input).  Written as NetCDF classic, the HAVE_NETCDF3 branch of the reference.  Returns the path or None."""
+    ic = db.get("InitialConditions") if isinstance(db.get("InitialConditions"), dict) else {}
+    end = ic.get("WriteEndingFile")
+    if not isinstance(end, dict):
+        return None
+    if "filename" not in end:
+        raise input_deck.DeckError("key 'filename' is required in WriteEndingFile")
+    from . import netcdf_classic
+    nz = cfg.n[2] if cfg.ndim == 3 else 1
+    state = dict(y_np)
+    if state.get("temperature") is None:
+        state["temperature"] = np.full((nz, cfg.n[1], cfg.n[0]), current_temperature(cfg, t))
+    name = str(end["filename"])
+    path = name if os.path.isabs(name) else os.path.join(directory, name)
+    netcdf_classic.write_state(path, state, qlen=cfg.qlen, dtype=np.float32)
+    return path
+
+
 class DeviceBackend:
     """the product's backend: state and integrator on the GPU (host/QuatIntegrator.h through the C ABI)"""
 
@@ -223,6 +255,9 @@ class DeviceBackend:
     def grain_volumes(self, y, threshold):
         return self.diag.computeGrainDiagnostics(y, threshold)
 
+    def download(self, y):
+        return {k: (None if v is None else v.cpu().numpy()) for k, v in y.items()}
+
     def close(self):
         self.integrator.close()
         self.diag.close()
@@ -243,8 +278,10 @@ def main(argv=None):
     backend = DeviceBackend(cfg, a.precond_cycles)
     try:
         y = backend.upload(y_np)
-        backend.y = y
         cycles, t, _ = run(db, cfg, y, backend, h0=a.first_step)
+        written = write_ending_file(db, cfg, backend.download(y), t)
+        if written:
+            print("Open/replace file %s" % written)
     finally:
         backend.close()
     print("Run complete: %d steps, end time %.10g" % (cycles, t))

@@ -19,6 +19,9 @@ if __name__ == "__main__":
     backend = OracleBackend(cfg, y, precond_cycles=2)
     try:
         cycles, t, _ = run_deck.run(db, cfg, y, backend)
+        written = run_deck.write_ending_file(db, cfg, y, t)
+        if written:
+            print("Open/replace file %s" % written)
     finally:
         backend.close()
     print("Run complete: %d steps, end time %.10g" % (cycles, t))

@@ -242,3 +242,34 @@ def test_cvode_nonlinear_tolerance_option(tmp_path):
     assert out[True][0]["newton_iterations"] <= out[False][0]["newton_iterations"]
     assert out[True][0]["convergence_failures"] <= out[False][0]["convergence_failures"]
     assert out[True][0]["linear_iterations"] < out[False][0]["linear_iterations"]
+
+
+def test_write_ending_file_feeds_the_next_deck(tmp_path):
+    """InitialConditions{WriteEndingFile{filename}}: the first stage leaves the file the second stage starts from (the two-deck
+    pattern of examples/AuNi_2D); single precision, the reference's variable names, the scalar temperature of the end time"""
+    from scipy.io import netcdf_file
+    _disc_problem(tmp_path)
+    stage1 = DECK.replace("end_time = 2.e-3", "end_time = 5.e-4").replace(
+        'InitialConditions { filename = "disc.nc" }', 'InitialConditions { filename = "disc.nc" WriteEndingFile { filename = "stage1.nc" } }')
+    db = input_deck.parse(stage1)
+    cfg = input_deck.rhs_config(db)
+    y = run_deck.initial_state(db, cfg, str(tmp_path), _read)
+    backend = OracleBackend(cfg, y, precond_cycles=2)
+    try:
+        cycles, t, _ = run_deck.run(db, cfg, y, backend, out=io.StringIO())
+    finally:
+        backend.close()
+    path = run_deck.write_ending_file(db, cfg, y, t, str(tmp_path))
+    assert path == str(tmp_path / "stage1.nc")
+    f = netcdf_file(path, "r", mmap=False)
+    assert set(f.variables) == {"phase", "concentration", "temperature"} and f.variables["phase"].data.dtype == np.dtype(">f4")
+    assert np.array_equal(f.variables["phase"].data, y["phase"].astype(np.float32))
+    assert np.all(f.variables["temperature"].data == np.float32(873.0 - 20.0 * t))
+    f.close()
+    stage2 = DECK.replace('filename = "disc.nc"', 'filename = "stage1.nc"')
+    db2 = input_deck.parse(stage2)
+    y2 = run_deck.initial_state(db2, cfg, str(tmp_path), _read)
+    assert np.array_equal(y2["phase"], y["phase"].astype(np.float32).astype(np.float64))
+    assert np.array_equal(y2["conc"], y["conc"].astype(np.float32).astype(np.float64))
+    assert run_deck.write_ending_file(db2, cfg, y2, 0.0, str(tmp_path)) is None
+    assert run_deck.current_temperature(cfg, 100.0) == 573.0       # held at the target
