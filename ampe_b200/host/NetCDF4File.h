@@ -87,7 +87,7 @@ class NetCDF4File
    NetCDF4File(const NetCDF4File&) = delete;
    NetCDF4File& operator=(const NetCDF4File&) = delete;
 
-   bool hasVar(const std::string& name) const { return d_vars.count(name) != 0; }
+   bool hasVar(const std::string& name) const { return d_vars.count(name) != 0 || d_unreadable.count(name) != 0; }
    // a NetCDF-4 dimension is stored as a one-dimensional dataset (dimension scale) of its name
    bool hasDim(const std::string& name) const
    {
@@ -105,7 +105,11 @@ class NetCDF4File
    const Var& var(const std::string& name) const
    {
       auto it = d_vars.find(name);
-      if (it == d_vars.end()) throw std::runtime_error("Could not read variable '" + name + "' from input data");
+      if (it == d_vars.end()) {
+         auto bad = d_unreadable.find(name);
+         if (bad != d_unreadable.end()) throw std::runtime_error(bad->second);
+         throw std::runtime_error("Could not read variable '" + name + "' from input data");
+      }
       return it->second;
    }
    std::vector<size_t> shape(const std::string& name) const { return var(name).shape; }
@@ -131,9 +135,8 @@ class NetCDF4File
    // start / count are given for the variable's shape padded with leading unit dimensions to rank 3
    void getBox(const std::string& name, const size_t* start, const size_t* count, double* out)
    {
-      auto vit = d_vars.find(name);
-      if (vit == d_vars.end()) throw std::runtime_error("Could not read variable '" + name + "' from input data");
-      Var& v = vit->second;
+      var(name);  // throws the reference's message (or why the object is unreadable) when the variable is not there
+      Var& v = d_vars.find(name)->second;
       const size_t rank = v.shape.size(), pad = 3 - rank;
       if (v.type_class != 1 || (v.elem_size != 4 && v.elem_size != 8))
          throw std::runtime_error("variable '" + name + "' is neither float nor double");
@@ -196,6 +199,7 @@ class NetCDF4File
    struct Msg {
       int type;
       std::vector<unsigned char> d;
+      bool shared = false;  // the body is a reference into the shared-message table / a committed datatype, not the message
    };
 
    // ---- raw access ---------------------------------------------------------------------------------
@@ -294,8 +298,13 @@ class NetCDF4File
       std::map<std::string, uint64_t> links;
       groupLinks(readHeader(root_header), links);
       for (auto& kv : links) {
-         Var v;
-         if (datasetFromHeader(readHeader(kv.second), v, kv.first)) d_vars[kv.first] = std::move(v);
+         // an object this reader cannot take (a storage form outside the subset, a damaged header) only matters when it is asked for
+         try {
+            Var v;
+            if (datasetFromHeader(readHeader(kv.second), v, kv.first)) d_vars[kv.first] = std::move(v);
+         } catch (const std::runtime_error& e) {
+            d_unreadable[kv.first] = e.what();
+         }
       }
    }
    void checkSizes() const
@@ -341,9 +350,10 @@ class NetCDF4File
          while (c.left() >= 8) {
             const int type = (int)c.u(2);
             const size_t size = c.u(2);
-            c.take(4);  // flags, reserved
+            const int mflags = (int)c.u(1);
+            c.take(3);  // reserved
             if (size > c.left()) break;
-            Msg m{type, std::vector<unsigned char>(c.p + c.pos, c.p + c.pos + size)};
+            Msg m{type, std::vector<unsigned char>(c.p + c.pos, c.p + c.pos + size), (mflags & 2) != 0};
             c.take(size);
             if (type == 0x10) {
                Cur cc(m.d, d_name);
@@ -363,10 +373,10 @@ class NetCDF4File
       while (c.left() >= mh) {
          const int type = (int)c.u(1);
          const size_t size = c.u(2);
-         c.take(1);  // message flags
+         const int mflags = (int)c.u(1);
          if (hflags & 0x04) c.take(2);  // creation order
          if (size > c.left()) break;
-         Msg m{type, std::vector<unsigned char>(c.p + c.pos, c.p + c.pos + size)};
+         Msg m{type, std::vector<unsigned char>(c.p + c.pos, c.p + c.pos + size), (mflags & 2) != 0};
          c.take(size);
          if (type == 0x10) {
             Cur cc(m.d, d_name);
@@ -545,6 +555,8 @@ class NetCDF4File
       bool have_space = false, have_type = false, have_layout = false;
       for (const Msg& m : msgs) {
          Cur c(m.d, d_name);
+         if (m.shared && (m.type == 0x01 || m.type == 0x03 || m.type == 0x08 || m.type == 0x0B))
+            bad("variable '" + name + "': shared header messages / committed datatypes are not supported");
          if (m.type == 0x01) {  // dataspace
             const int ver = (int)c.u(1), rank = (int)c.u(1);
             c.u(1);  // flags: maximum sizes follow the current ones, not needed
@@ -723,6 +735,7 @@ class NetCDF4File
    uint64_t d_base = 0, d_size = 0;
    int d_so = 8, d_sl = 8;
    std::map<std::string, Var> d_vars;
+   std::map<std::string, std::string> d_unreadable;  // object name -> why it could not be taken
 };
 
 }  // namespace ampe_host

@@ -240,3 +240,20 @@ def test_damaged_files_fail_with_a_message(tmp_path):
                 except (AmpeError, ValueError, MemoryError):  # ValueError / MemoryError: numpy refusing a corrupt shape
                     failed += 1
     assert answered > 100 and failed > 100
+
+
+def test_an_unreadable_object_only_matters_when_it_is_asked_for(tmp_path):
+    """a variable stored in a form outside the subset (here: its datatype message turned into a shared-message reference, and
+    a layout of the HDF5 1.10 format) does not make the rest of the file unreadable"""
+    a = np.arange(24.0).reshape(2, 3, 4)
+    path = str(tmp_path / "f.nc")
+    hdf5_writer.write_hdf5(path, {"phase": a, "other": a + 1.0}, style="new")
+    raw = bytearray(open(path, "rb").read())
+    first = raw.index(bytes([0x03, 20, 0, 0]))      # the datatype message of the first dataset written ("phase"): type 3, 20 bytes
+    raw[first + 3] |= 2                               # message flag "shared"
+    open(path, "wb").write(bytes(raw))
+    assert np.array_equal(host_rhs.read_hdf5_variable(path, "other"), a + 1.0)
+    with pytest.raises(AmpeError, match="shared header messages"):
+        host_rhs.read_hdf5_variable(path, "phase")
+    with pytest.raises(AmpeError, match="Could not read variable 'absent'"):
+        host_rhs.read_hdf5_variable(path, "absent")
