@@ -229,9 +229,9 @@ def write_ending_file(db, cfg, y_np, t, directory="."):
 class DeviceBackend:
     """the product's backend: state and integrator on the GPU (host/QuatIntegrator.h through the C ABI)"""
 
-    def __init__(self, cfg, precond_cycles=0):
+    def __init__(self, cfg, precond_cycles=0, scale_newton_tolerance=False):
         from . import host_rhs, rhs
-        self.cfg, self._rhs = cfg, rhs
+        self.cfg, self._rhs, self.scale_newton_tolerance = cfg, rhs, scale_newton_tolerance
         self.integrator = host_rhs.HostQuatIntegrator(cfg, True)
         if precond_cycles:
             self.integrator.setupPreconditioners(precond_cycles)
@@ -247,7 +247,8 @@ class DeviceBackend:
         return y
 
     def integrate(self, y, tend, h, t0, rtol, atol, max_steps):
-        return self.integrator.integrateAdaptive(y, tend, h, t0=t0, rtol=rtol, atol=atol, max_steps=max_steps, stop_at_tend=False)
+        return self.integrator.integrateAdaptive(y, tend, h, t0=t0, rtol=rtol, atol=atol, max_steps=max_steps, stop_at_tend=False,
+                                                 scale_newton_tolerance=self.scale_newton_tolerance)
 
     def scalar_diagnostics(self, y):
         return self.diag.printScalarDiagnostics(y)
@@ -268,6 +269,8 @@ def main(argv=None):
     ap.add_argument("deck")
     ap.add_argument("--precond-cycles", type=int, default=2, help="V-cycles of the block preconditioners (0: none)")
     ap.add_argument("--first-step", type=float, default=None)
+    ap.add_argument("--cvode-newton-tolerance", action="store_true",
+                    help="bound the Newton error by nlscoef of the allowed local error as CVODE does (ImplicitOptions::scale_newton_tolerance)")
     a = ap.parse_args(argv)
     from . import host_rhs
     db = input_deck.load(a.deck)
@@ -275,7 +278,7 @@ def main(argv=None):
     y_np = initial_state(db, cfg, os.path.dirname(os.path.abspath(a.deck)),
                          lambda *args, **kw: {k: (None if v is None else v.numpy()) for k, v in
                                               host_rhs.read_initial_conditions(*args, **kw).items()})
-    backend = DeviceBackend(cfg, a.precond_cycles)
+    backend = DeviceBackend(cfg, a.precond_cycles, a.cvode_newton_tolerance)
     try:
         y = backend.upload(y_np)
         cycles, t, _ = run(db, cfg, y, backend, h0=a.first_step)
