@@ -19,8 +19,26 @@ def _ch(s):
 
 def load_calphad(name="calphadAuNi.json"):
     """thermodynamic_data/calphadAuNi.dat transcribed by tools/make_calphad_json.py"""
-    db = json.load(open(os.path.join(_DATA, name)))
+    return calphad_from_database(json.load(open(os.path.join(_DATA, name))))
+
+
+def load_calphad_dat(path):
+    """a binary CALPHAD data base in the reference's own format (thermodynamic_data/*.dat: a SAMRAI input file with the blocks
+    SpeciesA / SpeciesB {PhaseL, PhaseA {Tc, a, b, c, d2 ...}}, LmixPhaseL / LmixPhaseA {L0..L3}, MobilityParameters) -- what
+    ConcentrationModel{Calphad{filename}} names and CALPHADFreeEnergyFunctionsBinary reads"""
+    from . import input_deck
+
+    def lists(d):
+        return {k: (lists(v) if isinstance(v, dict) else v if isinstance(v, str) else
+                    [float(x) for x in (v if isinstance(v, list) else [v])]) for k, v in d.items()}
+    return calphad_from_database(lists(input_deck.load(path)))
+
+
+def calphad_from_database(db):
     out = _abi.CalphadBinary()
+    for blk in ("SpeciesA", "SpeciesB", "LmixPhaseL", "LmixPhaseA", "MobilityParameters"):
+        if blk not in db:
+            raise ValueError("CALPHAD data base: block '%s' is missing (binary liquid / solid-A data bases only)" % blk)
     for si, sp in enumerate(("SpeciesA", "SpeciesB")):
         for pi, ph in enumerate(("PhaseL", "PhaseA")):
             rec = db[sp][ph]

@@ -71,7 +71,10 @@ def _number(expr):
         if isinstance(node, ast.Constant) and isinstance(node.value, (int, float)):
             return node.value
         if isinstance(node, ast.BinOp) and type(node.op) in _ARITH:
-            return _ARITH[type(node.op)](ev(node.left), ev(node.right))
+            a, b = ev(node.left), ev(node.right)
+            if isinstance(node.op, ast.Pow) and (abs(b) > 64 or abs(a) > 1.0e6):
+                raise DeckError("not a number: %r" % expr)
+            return _ARITH[type(node.op)](a, b)
         if isinstance(node, ast.UnaryOp) and type(node.op) in _ARITH:
             return _ARITH[type(node.op)](ev(node.operand))
         if isinstance(node, ast.Call) and isinstance(node.func, ast.Name) and node.func.id in _FUNCS:
@@ -80,10 +83,15 @@ def _number(expr):
     s = expr.replace("^", "**")
     s = re.sub(r"(?<![\w.])(\d+)\.(?![\d\w])", r"\1.0", s)        # "10." -> "10.0"
     s = re.sub(r"(\d)\.([eE][-+]?\d)", r"\1.0\2", s)              # "1.e-5" -> "1.0e-5"
+    if len(s) > 200 or s.count("**") > 2:
+        raise DeckError("not a number: %r" % expr[:40])
     try:
-        return ev(ast.parse(s, mode="eval").body)
-    except SyntaxError:
+        v = ev(ast.parse(s, mode="eval").body)
+    except (SyntaxError, ZeroDivisionError, OverflowError, ValueError, TypeError, RecursionError, MemoryError):
         raise DeckError("not a number: %r" % expr)
+    if isinstance(v, complex):
+        raise DeckError("not a number: %r" % expr)
+    return v
 
 
 def _value(tok):
@@ -219,8 +227,27 @@ def _zero_slope(model, periodic, ndim):
     return [0 if periodic[d] else 1 for d in range(ndim)]
 
 
-def rhs_config(db, ndim=None):
-    """the `ampe_rhs_config` of a deck (see the module docstring for the routines mirrored)"""
+def _deck_errors(fn):
+    """a missing required key or a value of the wrong kind is an input error with the key's name, as tbox::Database reports it"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kw):
+        try:
+            return fn(*args, **kw)
+        except KeyError as e:
+            raise DeckError("key %s is required" % e)
+        except (TypeError, ValueError, IndexError, ZeroDivisionError, OverflowError, AttributeError) as e:
+            if isinstance(e, DeckError):
+                raise
+            raise DeckError("a value in the deck has the wrong type or range (%s)" % e)
+    return wrapped
+
+
+@_deck_errors
+def rhs_config(db, ndim=None, deck_dir=None):
+    """the `ampe_rhs_config` of a deck (see the module docstring for the routines mirrored); deck_dir: where files the deck names
+    (the CALPHAD data base) are looked for after the working directory"""
     geo = _block(db, "Geometry")
     if geo is None:
         raise DeckError("block 'Geometry' is required")
@@ -463,12 +490,17 @@ def rhs_config(db, ndim=None):
             cal = _block(conc_db, "Calphad")
             if cal is None:
                 raise DeckError("block 'Calphad' is required")
-            name = os.path.splitext(os.path.basename(str(cal.get("filename", "calphadAuNi.dat"))))[0] + ".json"
+            fname = str(_get(cal, "filename", required=True, where="Calphad"))
+            found = [p for p in (fname, os.path.join(deck_dir or ".", fname)) if os.path.isfile(p)]
             try:
-                c.calphad = _configs.load_calphad(name)
+                if found:   # the data base file itself, in the reference's format
+                    c.calphad = _configs.load_calphad_dat(found[0])
+                else:       # not there (the reference's tests link it into the run directory): the packaged transcription
+                    c.calphad = _configs.load_calphad(os.path.splitext(os.path.basename(fname))[0] + ".json")
             except OSError:
-                _unsupported("CALPHAD database %r (ampe_b200/data holds calphadAuNi; tools/make_calphad_json.py converts others)"
-                             % cal.get("filename"))
+                _unsupported("CALPHAD data base %r: the file is not there and ampe_b200/data only holds calphadAuNi" % fname)
+            except (ValueError, KeyError, AssertionError) as e:
+                _unsupported("CALPHAD data base %r (%s)" % (fname, e))
         elif cmodel == "quadratic":
             c.free_energy = _abi.FE_QUADRATIC
             q = _block(conc_db, "Quadratic")
@@ -533,6 +565,7 @@ def rhs_config(db, ndim=None):
     return c
 
 
+@_deck_errors
 def run_parameters(db):
     """what the driver around the integrator reads (PFModel.cc:351-399, :625-640; QuatIntegrator.cc:285-289;
     EventInterval): end time, step limit, tolerances, output interval, initial-condition file and uniform fields"""
@@ -554,3 +587,31 @@ def run_parameters(db):
         "init_c": ic.get("init_c"),
         "slice_index": int(ic.get("slice_index", -1)),
     }
+
+
+def describe(cfg):
+    """the record as a plain dict (the CALPHAD block summarised)"""
+    import ctypes as C
+    out = {}
+    for name, _ in _abi.RhsConfig._fields_:
+        v = getattr(cfg, name)
+        if isinstance(v, C.Array):
+            v = list(v)
+        elif isinstance(v, C.Structure):
+            v = "<%d bytes>" % C.sizeof(v)
+        elif isinstance(v, bytes):
+            v = v.decode()
+        out[name] = v
+    return out
+
+
+if __name__ == "__main__":   # python -m ampe_b200.input_deck deck.input: what the fused path is configured with, or why it refuses
+    import json
+    import sys
+    for path in sys.argv[1:]:
+        try:
+            db = load(path)
+            print(json.dumps({"deck": path, "config": describe(rhs_config(db, deck_dir=os.path.dirname(os.path.abspath(path)))),
+                              "run": run_parameters(db)}, indent=1))
+        except DeckError as e:
+            print(json.dumps({"deck": path, "refused": str(e)}))

@@ -274,7 +274,7 @@ def main(argv=None):
     a = ap.parse_args(argv)
     from . import host_rhs
     db = input_deck.load(a.deck)
-    cfg = input_deck.rhs_config(db)
+    cfg = input_deck.rhs_config(db, deck_dir=os.path.dirname(os.path.abspath(a.deck)))
     y_np = initial_state(db, cfg, os.path.dirname(os.path.abspath(a.deck)),
                          lambda *args, **kw: {k: (None if v is None else v.numpy()) for k, v in
                                               host_rhs.read_initial_conditions(*args, **kw).items()})

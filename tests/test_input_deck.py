@@ -252,3 +252,82 @@ def test_every_deck_of_the_reference_is_configured_or_refused_by_name():
     assert "dilute" in refused["tests/AlCu/2d.input"] or "antitrapping" in refused["tests/AlCu/2d.input"]
     assert "boundary condition" in refused["tests/PlanarFront/2d.input"]
     assert "T_ref" in refused["examples/GG3D_HBSM/gg3d_hbsm.input"]   # a stale example: QuadraticFreeEnergyStrategy.cc:56 needs the key too
+
+
+def _samrai_text(db, indent=0):
+    out = []
+    for k, v in db.items():
+        pad = " " * indent
+        if isinstance(v, dict):
+            out.append("%s%s {\n%s%s}\n" % (pad, k, _samrai_text(v, indent + 3), pad))
+        elif isinstance(v, str):
+            out.append('%s%s = "%s"\n' % (pad, k, v))
+        else:
+            out.append("%s%s = %s   // %d value(s)\n" % (pad, k, ", ".join(repr(float(x)) for x in v), len(v)))
+    return "".join(out)
+
+
+def test_calphad_data_base_in_the_reference_format(tmp_path):
+    """ConcentrationModel{Calphad{filename}}: a data base file in the reference's format next to the deck is read as it is (the
+    packaged transcription only stands in when the file is not there, as in the reference's tests, which link it into the run
+    directory)"""
+    import json
+    db = json.load(open(os.path.join(os.path.dirname(configs.__file__), "data", "calphadAuNi.json")))
+    (tmp_path / "mydb.dat").write_text(_samrai_text(db))
+    assert bytes(configs.load_calphad_dat(str(tmp_path / "mydb.dat"))) == bytes(configs.load_calphad())
+    db["LmixPhaseL"]["L0"][0] += 1.0   # a different data base must give a different record
+    (tmp_path / "other.dat").write_text(_samrai_text(db))
+    deck = GEOMETRY + '''ModelParameters { epsilon_phi = 0.25 phi_well_scale = 2.5 phi_mobility = 6.4 temperature = 1450.
+        ConcentrationModel { model = "calphad" rhs_form = "ebs" molar_volume = 7.68e-6 Calphad { filename = "other.dat" } } }'''
+    c = input_deck.rhs_config(input_deck.parse(deck), deck_dir=str(tmp_path))
+    assert c.calphad.L[0][0][0] == configs.load_calphad().L[0][0][0] + 1.0
+    with pytest.raises(DeckError, match="other.dat"):       # neither the file nor a packaged transcription of that name
+        input_deck.rhs_config(input_deck.parse(deck), deck_dir=str(tmp_path / "nowhere"))
+    del db["MobilityParameters"]
+    (tmp_path / "other.dat").write_text(_samrai_text(db))
+    with pytest.raises(DeckError, match="MobilityParameters"):
+        input_deck.rhs_config(input_deck.parse(deck), deck_dir=str(tmp_path))
+
+
+@needs_reference
+def test_reference_thermodynamic_data_files():
+    """thermodynamic_data/calphadAuNi.dat read directly = the packaged transcription; the binary Cu-Ni data base reads; the ternary
+    ones are refused by what they lack"""
+    assert bytes(configs.load_calphad_dat(REF + "/thermodynamic_data/calphadAuNi.dat")) == bytes(configs.load_calphad())
+    assert configs.load_calphad_dat(REF + "/thermodynamic_data/calphadCuNi.dat").g[0][0].nintervals >= 1
+    with pytest.raises(ValueError, match="LmixPhaseL"):
+        configs.load_calphad_dat(REF + "/thermodynamic_data/calphadMoNbTa.dat")
+
+
+def test_damaged_decks_fail_with_a_deck_error():
+    """random edits of a valid deck: a configuration or a DeckError, nothing else"""
+    import random
+    rng = random.Random(5)
+    base = GEOMETRY + '''model_type = "Quat"  end_time = 1.  Symmetry { enabled = TRUE }
+        ModelParameters { H_parameter = 0.25 epsilon_q = 0.3125 orient_mobility = 0.64 Interface { sigma = 0.1 delta = 0.045 } phi_mobility = 6.4
+           Temperature { type = "scalar" temperature = 1450. dtemperaturedt = -200. }
+           ConcentrationModel { model = "quadratic" rhs_form = "kks" molar_volume = 1.e-5 D_liquid = 1. D_solid = 2.
+              Quadratic { T_ref = 1000. A_liquid = 1.e4 A_solid = 1.e4 Ceq_liquid = 0.05 Ceq_solid = 0.1 m_liquid = 0. m_solid = 0. } }
+           BoundaryConditions { Phase { boundary_2 = "slope", "0" boundary_3 = "slope", "0" } } }'''
+    assert input_deck.rhs_config(input_deck.parse(base)).qlen == 4
+    alphabet = '{}=,"/* \n0123456789.eE-+abcTRUEFALSE'
+    ok = refused = 0
+    for trial in range(1500):
+        t = list(base)
+        for _ in range(rng.randint(1, 4)):
+            i = rng.randrange(len(t))
+            op = rng.random()
+            if op < 0.4:
+                t[i] = rng.choice(alphabet)
+            elif op < 0.7:
+                del t[i]
+            else:
+                t.insert(i, rng.choice(alphabet))
+        try:
+            db = input_deck.parse("".join(t))
+            input_deck.rhs_config(db)
+            input_deck.run_parameters(db)
+            ok += 1
+        except DeckError:
+            refused += 1
+    assert ok > 100 and refused > 100
