@@ -203,23 +203,30 @@ def reference_tree(tmp_path, deck_dir):
     return str(tmp_path / "tests" / deck_dir)
 
 
-@pytest.mark.skipif(not os.path.exists(REF + "/tests/OneGrainQuadratic/test2d.py"), reason="runs the reference's own test script (build container only)")
+@pytest.mark.skipif(not os.path.exists(REF + "/tests/OneGrainQuadratic/test2d.py"), reason="runs the reference's own test scripts (build container only)")
 @pytest.mark.timeout(600)
-def test_reference_test_script_unmodified(tmp_path):
-    """tests/OneGrainQuadratic/test2d.py run as the reference's CTest runs it -- `test2d.py <mpiexec> <-n> <1> <exe> <input>` -- with
-    nothing of it changed: it calls the reference's utils/make_nuclei.py (which finds the netCDF4 stand-in and writes a NetCDF-4
-    container), starts the executable it is given on the deck, parses the output and exits 0 when its acceptance holds.  The
-    executable here is the deck program with the CPU restatement behind it; on the device it is `python -m ampe_b200.run_deck`
-    (profiles/r02ak_reference_test_scripts.log)."""
+@pytest.mark.parametrize("deck,script,init_file", [("OneGrainQuadratic", "test2d.py", "nuclei.nc"),
+                                                   ("CahnHilliard", "test2d.py", "64x64.nc"), ("CahnHilliard", "test3d.py", "32x32x32.nc")])
+def test_reference_test_script_unmodified(tmp_path, deck, script, init_file):
+    """tests/<deck>/test{2,3}d.py run as the reference's CTest runs them -- `test2d.py <mpiexec> <-n> <1> <exe> <input>` -- with
+    nothing of them changed: each calls the reference's generator (utils/make_nuclei.py, tests/CahnHilliard/make_initial.py, which
+    find the netCDF4 stand-in and write a NetCDF-4 container), starts the executable it is given on the deck, parses the output and
+    exits 0 when its acceptance holds (solid fraction 0.21 +- 0.01 within 220 steps; the integral of the composition constant to 1e-5
+    relative over a spinodal decomposition in 2D and in 3D).  The executable here is the deck program with the CPU restatement behind
+    it; on the device it is `python -m ampe_b200.run_deck` (profiles/r02ak_reference_test_scripts.log, r02al_*)."""
     import subprocess
     import sys
-    cwd = reference_tree(tmp_path, "OneGrainQuadratic")
+    cwd = reference_tree(tmp_path, deck)
+    for f in os.listdir(os.path.join(REF, "tests", deck)):     # generators that live next to the deck (make_initial.py)
+        if f.startswith("make_"):
+            os.symlink(os.path.join(REF, "tests", deck, f), os.path.join(cwd, f))
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "tools", "netcdf4_shim") + os.pathsep + os.environ.get("PYTHONPATH", ""))
     exe = "%s %s" % (sys.executable, os.path.join(ROOT, "tests", "run_deck_cpu.py"))
-    r = subprocess.run([sys.executable, REF + "/tests/OneGrainQuadratic/test2d.py", "", "", "", exe, REF + "/tests/OneGrainQuadratic/2d.input"],
+    dim = script[len("test"):-len(".py")]
+    r = subprocess.run([sys.executable, os.path.join(REF, "tests", deck, script), "", "", "", exe, os.path.join(REF, "tests", deck, dim + ".input")],
                        cwd=cwd, env=env, capture_output=True, text=True, timeout=500)
     assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
-    assert "fraction" in r.stdout and not os.path.exists(os.path.join(cwd, "nuclei.nc"))   # the script removes its file at the end
+    assert "cycle" in r.stdout and not os.path.exists(os.path.join(cwd, init_file))   # the script removes its file at the end
 
 
 def test_cvode_nonlinear_tolerance_option(tmp_path):
