@@ -229,12 +229,12 @@ def write_ending_file(db, cfg, y_np, t, directory="."):
 class DeviceBackend:
     """the product's backend: state and integrator on the GPU (host/QuatIntegrator.h through the C ABI)"""
 
-    def __init__(self, cfg, precond_cycles=0, scale_newton_tolerance=False):
+    def __init__(self, cfg, precond_cycles=0, scale_newton_tolerance=False, precondition_left=False, strict_linear=False):
         from . import host_rhs, rhs
-        self.cfg, self._rhs, self.scale_newton_tolerance = cfg, rhs, scale_newton_tolerance
+        self.cfg, self._rhs, self.scale_newton_tolerance, self.strict_linear = cfg, rhs, scale_newton_tolerance, strict_linear
         self.integrator = host_rhs.HostQuatIntegrator(cfg, True)
         if precond_cycles:
-            self.integrator.setupPreconditioners(precond_cycles)
+            self.integrator.setupPreconditioners(precond_cycles, precondition_left=precondition_left)
         self.diag = rhs.QuatIntegratorRHS(cfg)
 
     def upload(self, y_np):
@@ -248,7 +248,7 @@ class DeviceBackend:
 
     def integrate(self, y, tend, h, t0, rtol, atol, max_steps):
         return self.integrator.integrateAdaptive(y, tend, h, t0=t0, rtol=rtol, atol=atol, max_steps=max_steps, stop_at_tend=False,
-                                                 scale_newton_tolerance=self.scale_newton_tolerance)
+                                                 scale_newton_tolerance=self.scale_newton_tolerance, strict_linear=self.strict_linear)
 
     def scalar_diagnostics(self, y):
         return self.diag.printScalarDiagnostics(y)
@@ -271,6 +271,11 @@ def main(argv=None):
     ap.add_argument("--first-step", type=float, default=None)
     ap.add_argument("--cvode-newton-tolerance", action="store_true",
                     help="bound the Newton error by nlscoef of the allowed local error as CVODE does (ImplicitOptions::scale_newton_tolerance)")
+    ap.add_argument("--precondition-left", action="store_true",
+                    help="left preconditioning as AMPE configures CVODE (PREC_LEFT, QuatIntegrator.cc:1583): GMRES tests the "
+                         "preconditioned residual, which is what lets very stiff decks (tests/ConservedVolume) take large steps")
+    ap.add_argument("--cvode-linear-rule", action="store_true",
+                    help="an unconverged linear solve is accepted on the first Newton iteration only (ImplicitOptions::strict_linear_convergence)")
     a = ap.parse_args(argv)
     from . import host_rhs
     db = input_deck.load(a.deck)
@@ -278,7 +283,7 @@ def main(argv=None):
     y_np = initial_state(db, cfg, os.path.dirname(os.path.abspath(a.deck)),
                          lambda *args, **kw: {k: (None if v is None else v.numpy()) for k, v in
                                               host_rhs.read_initial_conditions(*args, **kw).items()})
-    backend = DeviceBackend(cfg, a.precond_cycles, a.cvode_newton_tolerance)
+    backend = DeviceBackend(cfg, a.precond_cycles, a.cvode_newton_tolerance, a.precondition_left, a.cvode_linear_rule)
     try:
         y = backend.upload(y_np)
         cycles, t, _ = run(db, cfg, y, backend, h0=a.first_step)

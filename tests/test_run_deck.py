@@ -280,3 +280,26 @@ def test_write_ending_file_feeds_the_next_deck(tmp_path):
     assert np.array_equal(y2["conc"], y["conc"].astype(np.float32).astype(np.float64))
     assert run_deck.write_ending_file(db2, cfg, y2, 0.0, str(tmp_path)) is None
     assert run_deck.current_temperature(cfg, 100.0) == 573.0       # held at the target
+
+
+def test_left_preconditioning_as_the_reference_configures_cvode(tmp_path):
+    """AMPE runs CVODE with PREC_LEFT (QuatIntegrator.cc:1583): GMRES then tests the PRECONDITIONED residual.  Same trajectory as the
+    right-preconditioned default on a mild problem; on the very stiff tests/ConservedVolume deck it is the difference between
+    ~10 000 and ~450 steps."""
+    db = input_deck.parse(DECK)
+    cfg = input_deck.rhs_config(db)
+    _disc_problem(tmp_path)
+    out = {}
+    for left in (False, True):
+        y = run_deck.initial_state(db, cfg, str(tmp_path), _read)
+        backend = OracleBackend(cfg, y)
+        backend.o.set_preconditioner(2, left=left)
+        try:
+            rc, st = backend.o.integrate_adaptive(y, 2.0e-3, 2.0e-9, rtol=1.0e-6, atol=1.0e-4, max_steps=500)
+            assert rc == 0, (rc, st)
+            out[left] = (st, backend.o.scalar_diagnostics(y))
+        finally:
+            backend.close()
+    assert abs(out[True][1]["solid_fraction"] - out[False][1]["solid_fraction"]) <= 2.0e-4
+    assert abs(out[True][1]["integral_concentration"] - out[False][1]["integral_concentration"]) <= 1.0e-6
+    assert abs(out[True][0]["steps"] - out[False][0]["steps"]) <= 5
