@@ -54,6 +54,11 @@ struct ImplicitOptions {
    // h / 4, preconditioner set up again); a residual that was not reduced always is.  false (the default, what every
    // committed deck result was produced with): the update is taken and the Newton test decides alone.
    bool strict_linear_convergence = false;
+   // CVODE defers step growth after a failed attempt: a failed Newton iteration or error test sets etamax = 1
+   // (cvHandleNFlag, cvDoErrorTest), so the step that finally succeeds keeps its size once (cvPrepareNextStep:
+   // "if etamax = 1, defer step size or order changes") before growth up to ETAMX is allowed again (cvCompleteStep).
+   // false (the default, what every committed deck result was produced with): the controller may grow the step at once.
+   bool hold_step_after_failure = false;
    // CVODE ties the nonlinear tolerance to the error test: dcon = del min(1, crate) / tq[4] <= 1 with tq[4] = nlscoef / tq[2],
    // tq[2] the coefficient that turns the accumulated correction into the local error estimate (cvSetTqBDF) -- the Newton
    // error may be nlscoef of the ALLOWED LOCAL ERROR, not nlscoef in the WRMS norm -- and epslin = eplifac tq[4].  true: the
@@ -194,6 +199,7 @@ class ImplicitIntegrator
       if (d_opt.h_max > 0.0) h = std::fmin(h, d_opt.h_max);
       long nacc = 0;  // accepted steps = solutions in the history beyond y
       int nef = 0, ncf = 0;
+      bool attempt_failed = false;  // an attempt at the current step has failed (CVODE's etamax = 1)
       d_stats.smallest_step = 0.0, d_stats.largest_step = 0.0;
       while (t < tend && rc == IMPLICIT_OK) {
          if (d_stats.steps >= d_opt.max_steps) {
@@ -247,6 +253,7 @@ class ImplicitIntegrator
                break;
             }
             eta = ETACF;
+            attempt_failed = true;
          } else {
             d_ops.applyProjection(t + h, ycur, delta, acor);
             d_stats.projections++;
@@ -270,8 +277,11 @@ class ImplicitIntegrator
                d_stats.smallest_step = d_stats.smallest_step > 0.0 ? std::fmin(d_stats.smallest_step, h) : h;
                eta = std::fmin(eta, ETAMX);
                if (eta < THRESH) eta = 1.0;
+               if (attempt_failed && d_opt.hold_step_after_failure) eta = 1.0;
+               attempt_failed = false;
             } else {
                d_stats.error_test_failures++;
+               attempt_failed = true;
                if (++nef >= d_opt.max_error_test_failures || (d_opt.h_min > 0.0 && h <= d_opt.h_min * 1.00001)) {
                   rc = IMPLICIT_EERRTEST;
                   break;

@@ -200,14 +200,14 @@ class HostQuatIntegrator:
 
     def integrateAdaptive(self, y, tend, h0, t0=0.0, order=2, max_krylov=5, max_newton=3, rtol=3e-6, atol=3e-4,
                           newton_tol=0.1, lin_factor=0.05, h_min=0.0, h_max=0.0, max_steps=500, stop_at_tend=True,
-                          strict_linear=False, scale_newton_tolerance=False):
+                          strict_linear=False, scale_newton_tolerance=False, hold_step_after_failure=False):
         """variable-step BDF1/BDF2 with CVODE's local error test and step controller from t0 to tend on the device
         (host/ImplicitIntegrator.h advanceTo), y updated in place.  Returns (rc, stats); rc 0 or IMPLICIT_E*
         (-20 Newton, -22 too much work, -23 error test, -24 convergence).  stop_at_tend=False: the step sizes are the
         controller's own and the call returns after the first step at or beyond tend (stats["t_reached"] >= tend), the
         way AMPE's run loop meets its output times (one CVODE step per Advance)."""
         iopt = (C.c_int * 5)(int(order), int(max_krylov), int(max_newton), int(max_steps),
-                             (0 if stop_at_tend else 1) | (2 if strict_linear else 0) | (4 if scale_newton_tolerance else 0))
+                             (0 if stop_at_tend else 1) | (2 if strict_linear else 0) | (4 if scale_newton_tolerance else 0) | (8 if hold_step_after_failure else 0))
         dopt = (C.c_double * 6)(float(rtol), float(atol), float(newton_tol), float(lin_factor), float(h_min),
                                 float(h_max))
         st = (C.c_double * 16)()

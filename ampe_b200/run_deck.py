@@ -229,9 +229,11 @@ def write_ending_file(db, cfg, y_np, t, directory="."):
 class DeviceBackend:
     """the product's backend: state and integrator on the GPU (host/QuatIntegrator.h through the C ABI)"""
 
-    def __init__(self, cfg, precond_cycles=0, scale_newton_tolerance=False, precondition_left=False, strict_linear=False):
+    def __init__(self, cfg, precond_cycles=0, scale_newton_tolerance=False, precondition_left=False, strict_linear=False,
+                 hold_step_after_failure=False):
         from . import host_rhs, rhs
         self.cfg, self._rhs, self.scale_newton_tolerance, self.strict_linear = cfg, rhs, scale_newton_tolerance, strict_linear
+        self.hold_step_after_failure = hold_step_after_failure
         self.integrator = host_rhs.HostQuatIntegrator(cfg, True)
         if precond_cycles:
             self.integrator.setupPreconditioners(precond_cycles, precondition_left=precondition_left)
@@ -248,7 +250,8 @@ class DeviceBackend:
 
     def integrate(self, y, tend, h, t0, rtol, atol, max_steps):
         return self.integrator.integrateAdaptive(y, tend, h, t0=t0, rtol=rtol, atol=atol, max_steps=max_steps, stop_at_tend=False,
-                                                 scale_newton_tolerance=self.scale_newton_tolerance, strict_linear=self.strict_linear)
+                                                 scale_newton_tolerance=self.scale_newton_tolerance, strict_linear=self.strict_linear,
+                                                 hold_step_after_failure=self.hold_step_after_failure)
 
     def scalar_diagnostics(self, y):
         return self.diag.printScalarDiagnostics(y)
@@ -276,6 +279,8 @@ def main(argv=None):
                          "preconditioned residual, which is what lets very stiff decks (tests/ConservedVolume) take large steps")
     ap.add_argument("--cvode-linear-rule", action="store_true",
                     help="an unconverged linear solve is accepted on the first Newton iteration only (ImplicitOptions::strict_linear_convergence)")
+    ap.add_argument("--cvode-hold-step", action="store_true",
+                    help="no step growth on the step that follows a failed attempt, CVODE's etamax = 1 (ImplicitOptions::hold_step_after_failure)")
     a = ap.parse_args(argv)
     from . import host_rhs
     db = input_deck.load(a.deck)
@@ -283,7 +288,7 @@ def main(argv=None):
     y_np = initial_state(db, cfg, os.path.dirname(os.path.abspath(a.deck)),
                          lambda *args, **kw: {k: (None if v is None else v.numpy()) for k, v in
                                               host_rhs.read_initial_conditions(*args, **kw).items()})
-    backend = DeviceBackend(cfg, a.precond_cycles, a.cvode_newton_tolerance, a.precondition_left, a.cvode_linear_rule)
+    backend = DeviceBackend(cfg, a.precond_cycles, a.cvode_newton_tolerance, a.precondition_left, a.cvode_linear_rule, a.cvode_hold_step)
     try:
         y = backend.upload(y_np)
         cycles, t, _ = run(db, cfg, y, backend, h0=a.first_step)

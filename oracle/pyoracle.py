@@ -299,10 +299,10 @@ class Oracle:
 
     def integrate_adaptive(self, y, tend, h0, t0=0.0, order=2, max_krylov=5, max_newton=3, rtol=3e-6, atol=3e-4,
                            newton_tol=0.1, lin_factor=0.05, h_min=0.0, h_max=0.0, max_steps=500, stop_at_tend=True,
-                           strict_linear=False, scale_newton_tolerance=False):
+                           strict_linear=False, scale_newton_tolerance=False, hold_step_after_failure=False):
         """ImplicitIntegrator::advanceTo driven by the oracle's RHS: variable steps with the local error test
         from t0 to tend; y advanced in place; returns (rc, stats)"""
-        iopt = np.array([order, max_krylov, max_newton, max_steps, (0 if stop_at_tend else 1) | (2 if strict_linear else 0) | (4 if scale_newton_tolerance else 0)],
+        iopt = np.array([order, max_krylov, max_newton, max_steps, (0 if stop_at_tend else 1) | (2 if strict_linear else 0) | (4 if scale_newton_tolerance else 0) | (8 if hold_step_after_failure else 0)],
                         dtype=np.int32)
         dopt = np.array([rtol, atol, newton_tol, lin_factor, h_min, h_max], dtype=np.float64)
         st = np.zeros(16)

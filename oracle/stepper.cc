@@ -198,6 +198,7 @@ extern "C" int oracle_integrate_adaptive(void* ctx, const ampe_rhs_fields* y, do
       o.stop_at_tend = !(iopt[4] & 1);
       o.strict_linear_convergence = (iopt[4] & 2) != 0;
       o.scale_newton_tolerance = (iopt[4] & 4) != 0;  // bit 2: CVODE's nonlinear tolerance relative to the error test
+      o.hold_step_after_failure = (iopt[4] & 8) != 0;  // bit 3: CVODE's etamax = 1 after a failed attempt
    }
    if (dopt) {
       o.rtol = dopt[0], o.atol = dopt[1], o.newton_tolerance = dopt[2], o.linear_tolerance_factor = dopt[3];

@@ -1,6 +1,7 @@
 """Test infrastructure: `python tests/run_deck_cpu.py deck.input` = ampe_b200.run_deck's loop with the CPU restatement as the
 backend, so the reference's test scripts can be pointed at an executable in a container without a GPU (the product's own
-program, `python -m ampe_b200.run_deck`, has the device as its only backend)."""
+program, `python -m ampe_b200.run_deck`, has the device as its only backend).  AMPE_B200_CPU_DECK_OPTS, a comma-separated list of
+left, strict, scale, hold, cycles=N, selects the integrator options run_deck's command line offers for the device."""
 import os
 import sys
 
@@ -16,7 +17,14 @@ if __name__ == "__main__":
     db = input_deck.load(deck)
     cfg = input_deck.rhs_config(db)
     y = run_deck.initial_state(db, cfg, os.path.dirname(os.path.abspath(deck)), _read)
-    backend = OracleBackend(cfg, y, precond_cycles=2)
+    opts = [o for o in os.environ.get("AMPE_B200_CPU_DECK_OPTS", "").split(",") if o]
+    ncyc = ([int(o[len("cycles="):]) for o in opts if o.startswith("cycles=")] or [2])[0]
+    backend = OracleBackend(cfg, y, precond_cycles=0 if opts else ncyc)
+    if opts:
+        backend.o.set_preconditioner(ncyc, left="left" in opts)
+        backend.integrate = lambda y, tend, h, t0, rtol, atol, max_steps: backend.o.integrate_adaptive(
+            y, tend, h, t0=t0, rtol=rtol, atol=atol, max_steps=max_steps, stop_at_tend=False, strict_linear="strict" in opts,
+            scale_newton_tolerance="scale" in opts, hold_step_after_failure="hold" in opts)
     try:
         cycles, t, _ = run_deck.run(db, cfg, y, backend)
         written = run_deck.write_ending_file(db, cfg, y, t)

@@ -303,3 +303,26 @@ def test_left_preconditioning_as_the_reference_configures_cvode(tmp_path):
     assert abs(out[True][1]["solid_fraction"] - out[False][1]["solid_fraction"]) <= 2.0e-4
     assert abs(out[True][1]["integral_concentration"] - out[False][1]["integral_concentration"]) <= 1.0e-6
     assert abs(out[True][0]["steps"] - out[False][0]["steps"]) <= 5
+
+
+def test_step_held_after_a_failed_attempt(tmp_path):
+    """ImplicitOptions::hold_step_after_failure, CVODE's etamax = 1 (cvHandleNFlag / cvDoErrorTest -> cvPrepareNextStep): the step that
+    succeeds after a failed attempt keeps its size once.  Started with a first step far too large the integrator must fail, and
+    with the rule on the accepted step after each failure is not grown: same answer, never more failures than without it."""
+    db = input_deck.parse(DECK)
+    cfg = input_deck.rhs_config(db)
+    _disc_problem(tmp_path)
+    out = {}
+    for hold in (False, True):
+        y = run_deck.initial_state(db, cfg, str(tmp_path), _read)
+        backend = OracleBackend(cfg, y, precond_cycles=2)
+        try:
+            rc, st = backend.o.integrate_adaptive(y, 2.0e-3, 1.0e-3, rtol=1.0e-6, atol=1.0e-4, max_steps=500, hold_step_after_failure=hold)
+            assert rc == 0, (rc, st)
+            out[hold] = (st, backend.o.scalar_diagnostics(y))
+        finally:
+            backend.close()
+    failures = {k: v[0]["error_test_failures"] + v[0]["convergence_failures"] for k, v in out.items()}
+    assert failures[False] >= 1 and failures[True] >= 1, failures      # the oversized first step was refused
+    assert failures[True] <= failures[False]
+    assert abs(out[True][1]["solid_fraction"] - out[False][1]["solid_fraction"]) <= 2.0e-4

@@ -4,7 +4,8 @@ the build container only), once per (preconditioning side, V-cycles per block so
 quantities: the time reached within max_timesteps and the largest move of the solid fraction between consecutive outputs from
 the fifth on (tests/ConservedVolume/test2d.py: <= 1e-4 and t > 0.01).
 
-    python tools/conserved_volume_cpu.py [left:cycles ...]        e.g.  right:2 left:2 left:10 left:16
+    python tools/conserved_volume_cpu.py [left:cycles ...]        e.g.  right:2 left:2 left:10 left:10:hold
+(hold: ImplicitOptions::hold_step_after_failure, CVODE's etamax = 1 after a failed attempt)
 """
 import io
 import os
@@ -22,7 +23,7 @@ from ampe_b200 import input_deck, run_deck  # noqa: E402
 from test_run_deck import OracleBackend, _read  # noqa: E402
 
 
-def one(deck, cwd, left, cycles):
+def one(deck, cwd, left, cycles, hold=False):
     db = input_deck.load(deck)
     cfg = input_deck.rhs_config(db)
     y = run_deck.initial_state(db, cfg, cwd, _read)
@@ -31,7 +32,8 @@ def one(deck, cwd, left, cycles):
     tot = {}
 
     def integrate(y, tend, h, t0, rtol, atol, max_steps):
-        rc, st = backend.o.integrate_adaptive(y, tend, h, t0=t0, rtol=rtol, atol=atol, max_steps=max_steps, stop_at_tend=False)
+        rc, st = backend.o.integrate_adaptive(y, tend, h, t0=t0, rtol=rtol, atol=atol, max_steps=max_steps, stop_at_tend=False,
+                                                 hold_step_after_failure=hold)
         for k in ("convergence_failures", "error_test_failures", "newton_iterations", "linear_iterations"):
             tot[k] = tot.get(k, 0) + int(st[k])
         return rc, st
@@ -45,8 +47,8 @@ def one(deck, cwd, left, cycles):
     frac = [h[2]["solid_fraction"] for h in hist]
     integral = [h[2]["integral_concentration"] for h in hist]
     move = max([abs(frac[i - 1] - frac[i]) for i in range(4, len(frac))] or [float("nan")])
-    print("%-5s cycles %2d: %d steps, t = %.5f, outputs %d, largest move of the solid fraction from the fifth output %.2e, "
-          "integral c %.4f ... %.4f, %s, %.0f s" % ("left" if left else "right", cycles, cycles_done, t, len(frac), move,
+    print("%-5s cycles %2d%s: %d steps, t = %.5f, outputs %d, largest move of the solid fraction from the fifth output %.2e, "
+          "integral c %.4f ... %.4f, %s, %.0f s" % ("left" if left else "right", cycles, " hold" if hold else "", cycles_done, t, len(frac), move,
                                                     min(integral), max(integral), tot, time.time() - t0), flush=True)
 
 
@@ -59,5 +61,5 @@ if __name__ == "__main__":
         deck = os.path.join(tmp, "2d.input")
         os.symlink(REF + "/tests/ConservedVolume/2d.input", deck)
         for r in runs:
-            side, n = r.split(":")
-            one(deck, tmp, side == "left", int(n))
+            side, n, *opt = r.split(":")
+            one(deck, tmp, side == "left", int(n), "hold" in opt)
